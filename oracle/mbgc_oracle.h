@@ -1,0 +1,134 @@
+/* oracle/mbgc_oracle.h -- TEST INFRASTRUCTURE ONLY.
+ *
+ * Plain-C, single-threaded CPU restatement of the MBGC hot path (the sparse k-mer exact-match finder
+ * and the match/literal stream packing).  It exists to CHECK the CUDA path; nothing under oracle/ is
+ * ever linked into, imported by, or executed from the product library (mbgc_b200/).  Only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may use it.
+ *
+ * Parity status: PINNED.  tests/test_oracle_vs_reference.py checks every entry point below against the
+ * reference's own code compiled from /root/reference (oracle/_ref/libref_matcher.so, oracle/_ref/mbgc)
+ * on the reference's shipped fixtures (example-scripts/, 3 Listeria genomes) and seeded synthetic
+ * collections, and tests/golden/ holds vectors generated from that reference build
+ * (tests/golden/make_golden.py).
+ *
+ * Each function cites the reference file:line it restates (paths relative to /root/reference).
+ */
+#ifndef MBGC_ORACLE_H
+#define MBGC_ORACLE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MBO_NO_LOCK UINT64_MAX /* SW_END_ERASED_FLAG, matching/SlidingWindowSparseEMMatcher.h:46 */
+
+typedef struct mbo_matcher mbo_matcher;
+
+/* (posSrcText, length, posDestText) -- matching/TextMatchers.h:9-17 */
+typedef struct {
+    uint64_t src;
+    uint64_t len;
+    uint64_t dst;
+} mbo_match_t;
+
+/* utils/Hashes.h:28-40 : maRushPrime1HashSimplified<K>, low 32 bits */
+uint32_t mbo_hash(const uint8_t* p, int K);
+/* matching/SlidingWindowSparseEMMatcher.cpp:74-87 : hashed prefix length K from L and minMatchLength */
+int mbo_kmer_from_L(uint32_t L, uint32_t minMatchLength);
+/* matching/SlidingWindowSparseEMMatcher.cpp:99-103 : table size (power of two in [2^24, 2^31]) */
+uint32_t mbo_hash_size(uint64_t maxRefLength, int k1);
+/* utils/helper.cpp:312-358,405-410 : upper-casing reverse complement of src[0..n) into dst[0..n) */
+void mbo_upper_reverse_complement(const uint8_t* src, uint64_t n, uint8_t* dst);
+/* matching/SlidingWindowSparseEMMatcher.cpp:146-171 : which positions one index pass samples.
+ * Writes up to cap (begin,end) pairs (step k1 inside each) to ranges, returns the number of pairs and the
+ * new sampling position through *newSamplingPos. */
+int mbo_insert_ranges(uint64_t samplingPos, int64_t refPos1, int K, int k1, int64_t* ranges, int cap,
+                      uint64_t* newSamplingPos);
+
+/* matching/SlidingWindowSparseEMMatcher.cpp:325-359,494-519 (+ MultipleGenomeMatchingProcessor.cpp:170-176:
+ * k1 even -> "Exp" variant storing pos >> ctz(k1)) */
+mbo_matcher* mbo_create(uint64_t refLengthLimit, uint32_t L, int k1, int k2, int skipMargin);
+void mbo_destroy(mbo_matcher* m);
+/* matching/SlidingWindowSparseEMMatcher.h:93-97 */
+void mbo_disable_sliding_window(mbo_matcher* m);
+void mbo_disable_circular_buffer(mbo_matcher* m);
+void mbo_set_sliding_window_size(mbo_matcher* m, int factor);
+/* matching/SlidingWindowSparseEMMatcher.cpp:402-437,453-458 */
+void mbo_load_ref(mbo_matcher* m, const uint8_t* text, uint64_t len, int loadRC, int addSep, uint8_t sep);
+/* matching/SlidingWindowSparseEMMatcher.cpp:439-451 */
+void mbo_load_separator(mbo_matcher* m, uint8_t sep);
+/* matching/SlidingWindowSparseEMMatcher.cpp:477-492 -> 181-321.  Returns the number of matches; the list
+ * stays owned by the matcher until the next call (mbo_matches).  usePrefilter!=0 keeps the l/r 4-byte
+ * side-probe filter of .cpp:203-204,223-226 (the reference's behaviour); 0 drops it (to test that it is
+ * redundant). Returns UINT64_MAX on the reference's error path (minMatchLength < K). */
+uint64_t mbo_match(mbo_matcher* m, const uint8_t* text, uint64_t len, uint32_t minMatchLength, uint64_t lockPos,
+                   int usePrefilter);
+const mbo_match_t* mbo_matches(const mbo_matcher* m);
+/* matching/SlidingWindowSparseEMMatcher.cpp:361-400 */
+uint64_t mbo_acquire_lock(mbo_matcher* m);
+int mbo_release_lock(mbo_matcher* m, uint64_t lockValue);
+/* matching/SlidingWindowSparseEMMatcher.h:104-113 */
+const uint8_t* mbo_ref(const mbo_matcher* m);
+uint64_t mbo_ref_length(const mbo_matcher* m);
+uint64_t mbo_loading_position(const mbo_matcher* m);
+uint64_t mbo_loaded_ref_length(const mbo_matcher* m);
+uint64_t mbo_max_ref_length(const mbo_matcher* m);
+void mbo_set_position(mbo_matcher* m, uint64_t refPos, int reachedCount);
+const uint32_t* mbo_table(const mbo_matcher* m);
+uint64_t mbo_table_size(const mbo_matcher* m);
+uint64_t mbo_sampling_pos(const mbo_matcher* m);
+int mbo_kmer(const mbo_matcher* m);
+/* counters of the last mbo_match call: probes, non-empty slots, K-mer-equal candidates, accepted pushes */
+void mbo_last_stats(const mbo_matcher* m, uint64_t out4[4]);
+
+/* ---- stream packing: mbgccoder/MBGC_Encoder.cpp:143-427 -------------------------------------------- */
+
+typedef struct {
+    int enableExtensionsWithMismatches; /* MBGC_Params.h: mode presets */
+    int gapBreakingMatchMinLength;
+    int gapDepthOffsetEncoding;
+    int gapDepthMismatchesEncoding;
+    int lazyDecompressionSupport;
+    int frugal64bitLenEncoding;
+    int enable40bitReference;
+    int mismatchesWithExclusion;
+    int mmsMismatchesInitialScore;
+    int mmsMismatchesScoreThreshold;
+    int mmsMismatchPenalty;
+    int mmsMatchBonus;
+    int k;                               /* params->k (minimal match length) */
+    int unmatchedFractionFactor;         /* for the ref-extension decision / loadLiteralsToRef flag */
+} mbo_pack_params_t;
+
+typedef struct mbo_streams mbo_streams;
+mbo_streams* mbo_streams_create(void);
+void mbo_streams_destroy(mbo_streams* s);
+/* stream ids */
+enum { MBO_S_LITERALS = 0, MBO_S_MAPOFF = 1, MBO_S_MAPOFF5 = 2, MBO_S_MAPLEN = 3, MBO_S_GAPDELTA = 4,
+       MBO_S_GAPFLAGS = 5, MBO_S_COUNT = 6 };
+const uint8_t* mbo_stream_data(const mbo_streams* s, int id);
+uint64_t mbo_stream_size(const mbo_streams* s, int id);
+void mbo_streams_clear(mbo_streams* s);
+/* appends SEQ_SEPARATOR_MARK to the literal stream: MBGC_Encoder.cpp:489-491 */
+void mbo_after_sequence(mbo_streams* s);
+/* appends FILE_SEPARATOR_MARK to the flag stream: MBGC_Encoder.cpp:493-496 */
+void mbo_after_target(mbo_streams* s, const mbo_pack_params_t* p);
+
+/* MBGC_Encoder.cpp:143-308 (sequential-mode semantics: targetIdx 0, no dissimilar-contig bail-out,
+ * refExtLoadedPosArr supplied by the caller for the lazy-decompression pairing rule).
+ * matches is modified in place exactly as the reference modifies textMatches (gap-breaking removal,
+ * left shifts); *nMatches receives the surviving count.  Returns unmatchedChars (pre-extension). */
+uint64_t mbo_process_matches(mbo_streams* out, const mbo_pack_params_t* p, const mbo_matcher* m,
+                             mbo_match_t* matches, uint64_t* nMatches, const uint8_t* dest, uint64_t destLen,
+                             uint64_t matchingLockPos, const uint64_t* refExtLoadedPosArr, uint64_t nLoadedPos);
+
+/* coders/ContextAwareMismatchesCoder.cpp:22-27 */
+uint8_t mbo_mismatch2code(uint8_t actual, uint8_t mismatch);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
