@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py -- MBGC match-stage throughput on B200 (and the reference's CPU path beside it).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1]): a synthetic 100-genome E. coli-like collection -- a random 5 Mbp base
+genome (G0) and independent SNP/indel mutants of it ("near" tier of SURVEY.md 8d: p_snp 1e-4, p_indel 1e-5).
+The matcher state is what MBGC has after loading G0 (+ its reverse complement); one STEP = one pass of the hot
+path (probe -> seed runs -> extension -> sequential-equivalent resolve -> match lists on the host) over the
+rank's batch of --genomes target genomes against that frozen state.  With N ranks every rank matches its own
+--genomes mutants of the same collection against its replica of the index (weak scaling, no data-path
+collective: SURVEY.md 8e).
+
+Metric: compression input GB/s of the match stage = FASTA bytes of the matched genomes / time.
+  value  device-resident inputs, CUDA-event time on the matcher's stream, max over ranks
+  e2e    same call through the C ABI with pinned HOST buffers (H2D of the texts and D2H of the match lists
+         inside the timed region)
+  roofline  dominant kernel (k_probe): 6.0 algorithmic bytes per target position / its mean
+         launch time, against the measured HBM copy bandwidth of MEASURED_PEAKS.json
+  cpu_baseline  the reference's own matcher (oracle/_ref/libref_matcher.so; else the C oracle port) on the
+         host cores over the same batch
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from mbgc_b200.synth import fasta_bytes, mgmp_ref_limit, synth_base, synth_mutant  # noqa: E402
+
+SEED = 1234
+HEADER_LEN = len("syn_0000 synthetic E. coli-like genome 0")
+TIERS = {"near": (1e-4, 1e-5), "div": (1e-2, 1e-4)}
+ALG_BYTES_PER_POSITION = 6.0  # 1 ASCII + .25 + .25 packed + 4 table probe + .25 ref + .25 out
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--genomes", type=int, default=100, help="target genomes per rank")
+    ap.add_argument("--length", type=int, default=5_000_000)
+    ap.add_argument("--tier", default="near", choices=list(TIERS))
+    ap.add_argument("--mode", type=int, default=0, help="MBGC mode the matcher parameters come from (0..3)")
+    ap.add_argument("--cpu-sample", type=int, default=100, help="genomes of the batch the CPU baseline is timed on")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+def make_batch(args, rank):
+    """G0 and this rank's target genomes (disjoint mutant indices per rank)."""
+    p_snp, p_indel = TIERS[args.tier]
+    base = synth_base(args.length, SEED)
+    first = 1 + rank * args.genomes
+    targets = [synth_mutant(base, SEED * 1000003 + i, p_snp, p_indel) for i in range(first, first + args.genomes)]
+    return base, targets
+
+
+def skip_margin_of(mode):
+    return 24 if mode >= 2 else 16  # MGMP_Params.h:33-34, MBGC_Params.h:906-909
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def probe_traffic():
+    """dram bytes per probe launch from the committed ncu capture, if one matches this workload"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "probe_traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+class ClockSampler(threading.Thread):
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        super().__init__(daemon=True)
+        self.gpu = gpu
+        self.samples = []
+        self.stop_flag = False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 8:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(float(s[1]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(s[4 + k] == "Active" for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][2]), "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own matcher on the host cores
+# ------------------------------------------------------------------------------------------------------
+
+def cpu_match_stage(base, targets, limit, skip_margin, threads):
+    """Returns (seconds, kind, total matches).  kind = "reference" when oracle/_ref/libref_matcher.so (the
+    reference's SlidingWindowSparseEMMatcher.cpp built unmodified) is there, else "port" (oracle C restatement,
+    single thread)."""
+    ref_so = os.path.join(ROOT, "oracle", "_ref", "libref_matcher.so")
+    n = len(targets)
+    ptrs = (C.c_void_p * n)(*[t.ctypes.data for t in targets])
+    lens = (C.c_uint64 * n)(*[t.size for t in targets])
+    if os.path.exists(ref_so):
+        os.environ.setdefault("OMP_NUM_THREADS", "1")  # index build is racy with more
+        L = C.CDLL(ref_so)
+        L.refm_create.restype = C.c_void_p
+        L.refm_create.argtypes = [C.c_uint64, C.c_uint32, C.c_int, C.c_int, C.c_int]
+        L.refm_disable_sliding_window.argtypes = [C.c_void_p]
+        L.refm_load_ref.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_char]
+        L.refm_match_many.restype = C.c_uint64
+        L.refm_match_many.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.c_uint32,
+                                      C.c_int, C.c_void_p]
+        L.refm_destroy.argtypes = [C.c_void_p]
+        h = L.refm_create(limit, 32, 16, 1, skip_margin)
+        L.refm_disable_sliding_window(h)
+        L.refm_load_ref(h, base.ctypes.data, base.size, 1, 1, b"\0")
+        t0 = time.perf_counter()
+        total = L.refm_match_many(h, n, ptrs, lens, 32, threads, None)
+        dt = time.perf_counter() - t0
+        L.refm_destroy(h)
+        return dt, "reference", int(total), threads
+    subprocess.run(["make", "-s", "oracle"], cwd=os.path.join(ROOT, "oracle"), check=True)
+    L = C.CDLL(os.path.join(ROOT, "oracle", "libmbgc_oracle.so"))
+    L.mbo_create.restype = C.c_void_p
+    L.mbo_create.argtypes = [C.c_uint64, C.c_uint32, C.c_int, C.c_int, C.c_int]
+    L.mbo_disable_sliding_window.argtypes = [C.c_void_p]
+    L.mbo_load_ref.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_uint8]
+    L.mbo_match.restype = C.c_uint64
+    L.mbo_match.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_int]
+    L.mbo_destroy.argtypes = [C.c_void_p]
+    h = L.mbo_create(limit, 32, 16, 1, skip_margin)
+    L.mbo_disable_sliding_window(h)
+    L.mbo_load_ref(h, base.ctypes.data, base.size, 1, 1, 0)
+    t0 = time.perf_counter()
+    total = 0
+    for t in targets:
+        total += L.mbo_match(h, t.ctypes.data, t.size, 32, 2**64 - 1, 1)
+    dt = time.perf_counter() - t0
+    L.mbo_destroy(h)
+    return dt, "port", int(total), 1
+
+
+def workload_name(args):
+    return (f"synthetic {args.genomes}-genome E. coli-like collection per GPU ({args.length / 1e6:g} Mbp base + "
+            f"SNP/indel mutants, tier {args.tier}), mode {args.mode} matcher parameters")
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    base, targets = make_batch(args, 0)
+    sample = targets[:max(1, min(args.cpu_sample, len(targets)))]
+    limit = mgmp_ref_limit(args.genomes * args.gpus + 1, base.size)
+    threads = os.cpu_count() or 1
+    fbytes = sum(fasta_bytes(t.size, HEADER_LEN) for t in sample)
+    times = []
+    kind, cores, total = "port", 1, 0
+    for it in range(args.warmup + args.steps):
+        dt, kind, total, cores = cpu_match_stage(base, sample, limit, skip_margin_of(args.mode), threads)
+        if it >= args.warmup:
+            times.append(dt)
+    sec = sum(times) / len(times)
+    v = fbytes / sec / 1e9
+    line = {
+        "impl": "reference", "metric": "compression input GB/s (match stage)", "value": v, "unit": "GB/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": workload_name(args), "sample_genomes": len(sample), "matches": total},
+        "cpu_baseline": {"value": v, "unit": "GB/s", "cores": cores, "kind": kind,
+                         "sample": f"{len(sample)} of the {args.genomes} target genomes per step "
+                                   f"({fbytes / 1e6:.0f} MB FASTA), matchTexts against the frozen G0+RC index"},
+        "e2e": {"value": v, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args, rank, world):
+    import torch
+    import mbgc_b200
+
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    base, targets = make_batch(args, rank)
+    n = len(targets)
+    limit = mgmp_ref_limit(args.genomes * world + 1, base.size)
+    sm = skip_margin_of(args.mode)
+    m = mbgc_b200.Matcher(limit, 32, 16, 1, sm, device=local)
+    m.disableSlidingWindow()
+    t0 = time.perf_counter()
+    m.loadRef(base, True, True, 0)
+    index_s = time.perf_counter() - t0
+
+    # device-resident batch: texts at 16-byte aligned offsets, 64-byte gaps, 8 KiB tail
+    offs, cur = [], 64
+    for t in targets:
+        offs.append(cur)
+        cur = (cur + t.size + 64 + 15) // 16 * 16
+    dbuf = torch.zeros(cur + 8192, dtype=torch.uint8, device="cuda")
+    pinned = []
+    for t, o in zip(targets, offs):
+        ht = torch.from_numpy(t).pin_memory()
+        pinned.append(ht)
+        dbuf[o:o + t.size].copy_(ht, non_blocking=True)
+    torch.cuda.synchronize()
+    lens = [t.size for t in targets]
+    fbytes = sum(fasta_bytes(x, HEADER_LEN) for x in lens)
+    stream = torch.cuda.ExternalStream(m.stream())
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn):
+        for _ in range(args.warmup):
+            fn()
+        stage = {k: 0.0 for k in mbgc_b200.matcher.T_NAMES}
+        launches0 = m.totalLaunches()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        res = None
+        for _ in range(args.steps):
+            res = fn()
+            for k, v in m.timing().items():
+                stage[k] += v
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            tms = torch.tensor([ms], device="cuda")
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            ms = float(tms.item())
+        return ms, stage, m.totalLaunches() - launches0, res
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms_dev, stage_dev, launches, res = timed(lambda: m.matchBatchDevice(dbuf.data_ptr(), offs, lens, 32))
+    counters = m.counters()
+    host_ptrs = [p.numpy() for p in pinned]
+    ms_e2e, stage_e2e, _, res2 = timed(lambda: m.matchBatch(host_ptrs, 32))
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    n_matches = int(sum(len(r) for r in res))
+    assert n_matches == int(sum(len(r) for r in res2)), "device-resident and host-buffer passes disagree"
+
+    total_bytes = fbytes * world  # every rank has a batch of the same shape
+    value = total_bytes * args.steps / (ms_dev / 1e3) / 1e9
+    e2e = total_bytes * args.steps / (ms_e2e / 1e3) / 1e9
+    peak, peak_src = peaks()
+    probe_launches = max(1, counters["passes"])  # one k_probe launch per pass of at most 256 MiB of text
+    probe_ms = stage_dev["probe"] / args.steps / probe_launches
+    alg_bytes = ALG_BYTES_PER_POSITION * counters["positions"] / probe_launches
+    achieved = alg_bytes / (probe_ms / 1e3) / 1e9
+    kernels_ms = (stage_dev["probe"] + stage_dev["compact"] + stage_dev["extend"] + stage_dev["resolve"]) / args.steps
+    tr = probe_traffic()
+    line = {
+        "metric": "compression input GB/s (match stage)", "value": value, "unit": "GB/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": workload_name(args), "genomes_per_gpu": n, "bases_per_gpu": int(sum(lens)),
+                   "fasta_bytes_per_gpu": int(fbytes), "matches_per_gpu": n_matches, "seeds": counters["seeds"],
+                   "seed_runs": counters["runs"], "ref_limit": int(limit), "table_slots": m.state()["hashSize"],
+                   "skip_margin": sm, "l2": "inputs (>= 500 MB per step) exceed the 126 MB L2; no explicit flush",
+                   "index_build_s": index_s, "parallelism": f"targets sharded over {world} GPU(s), index replicated"},
+        "roofline": {"bound": "hbm", "kernel": "k_probe", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": tr["dram_bytes_per_launch"] if tr else None,
+                     "peak_source": peak_src, "alg_bytes_per_launch": alg_bytes, "launch_ms": probe_ms,
+                     "stage_frac": ALG_BYTES_PER_POSITION * counters["positions"] / (kernels_ms / 1e3) / 1e9 / peak,
+                     "stage_ms": {k: v / args.steps for k, v in stage_dev.items()}},
+        "e2e": {"value": e2e, "unit": "GB/s", "h2d_bytes_per_step": int(sum(lens)),
+                "d2h_bytes_per_step": int(n_matches * 16 + (n + 9) * 4), "ms_per_step": ms_e2e / args.steps,
+                "stage_ms": {k: v / args.steps for k, v in stage_e2e.items()}},
+        "gpu_launches": int(launches),
+        "clocks": sampler.summary(),
+    }
+    if rank == 0 and world == 1 and not args.no_cpu:
+        sample = targets[:max(1, min(args.cpu_sample, n))]
+        sbytes = sum(fasta_bytes(t.size, HEADER_LEN) for t in sample)
+        threads = os.cpu_count() or 1
+        dt, kind, total, cores = cpu_match_stage(base, sample, limit, sm, threads)
+        line["cpu_baseline"] = {"value": sbytes / dt / 1e9, "unit": "GB/s", "cores": cores, "kind": kind,
+                                "sample": f"{len(sample)} of the {n} target genomes ({sbytes / 1e6:.0f} MB FASTA), "
+                                          f"one pass, matchTexts against the frozen G0+RC index, {dt:.2f} s",
+                                "matches": total}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    m.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+    else:
+        run_b200(args, rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,159 @@
+/* include/mbgc_b200.h -- C ABI of the B200-native MBGC match finder (libmbgc_b200.so).
+ *
+ * This is the drop-in boundary for MBGC's one data-parallel hot path: the sparse k-mer exact-match
+ * finder.  The reference has no FFI; its seam is the C++ class SlidingWindowSparseEMMatcher
+ * (/root/reference/matching/SlidingWindowSparseEMMatcher.h:12-126, "ref .h" below; implementation
+ * "ref .cpp" = matching/SlidingWindowSparseEMMatcher.cpp).  Every entry point here replaces one member of
+ * that class, cited per declaration.  mbgc_b200/dropin/SlidingWindowSparseEMMatcher_b200.cpp re-implements
+ * the class against the UNMODIFIED reference header on top of these calls (link-time substitution, see
+ * INTEGRATION.md).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all text is raw ASCII bytes (case-sensitive, N and IUPAC included --
+ *     exactly what the reference hashes and compares);
+ *   - every function that can fail returns 0 on success and a negative MBGCG_E_* code otherwise (the
+ *     reference prints to stderr and exit()s; the shim converts); mbgcg_last_error() gives the text;
+ *   - there is NO CPU fallback: without a CUDA device / the sm_100a kernels, mbgcg_create fails;
+ *   - results are bit-exact with the reference run deterministically (-t 1 / OMP_NUM_THREADS=1);
+ *   - a handle is not thread-safe; callers serialise calls on one handle (the reference's parallel mode
+ *     enters matchTexts concurrently -- the shim takes a mutex).
+ */
+#ifndef MBGC_B200_H
+#define MBGC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MBGCG_NO_LOCK UINT64_MAX /* SW_END_ERASED_FLAG, ref .h:46 */
+
+enum {
+    MBGCG_OK = 0,
+    MBGCG_E_CUDA = -1,     /* CUDA runtime / launch failure, or no device */
+    MBGCG_E_PARAM = -2,    /* the reference's own parameter errors (e.g. minMatchLength < K, ref .cpp:480-483) */
+    MBGCG_E_UNSUPPORTED = -3, /* outside the accelerated scope (k2 != 1, 64-bit table: ref .cpp:505-508) */
+    MBGCG_E_LOCK = -4,     /* "Invalid worker lock value", ref .cpp:388-391 */
+    MBGCG_E_NOMEM = -5
+};
+
+typedef struct mbgcg mbgcg_t;
+
+/* Same layout as PgTools::TextMatch (matching/TextMatchers.h:9-17): 4 x uint64. */
+typedef struct {
+    uint64_t posSrcText;
+    uint64_t length;
+    uint64_t posDestText;
+    uint64_t nextSrcRegionLoadingPos; /* always 0 on return, as in the TextMatch ctor */
+} mbgcg_match_t;
+
+/* Host-visible matcher state = the protected members the reference header's inline getters/setters touch
+ * (ref .h:29-33,45-49,78,93-113). */
+typedef struct {
+    int64_t pos1;
+    uint64_t maxRefLength;
+    int32_t reachedRefLengthCount;
+    int32_t circularBuffer;
+    uint64_t swSize;
+    uint64_t swEnd;
+    uint64_t samplingPos;
+    uint32_t hashSize;
+    int32_t K;
+} mbgcg_state_t;
+
+/* ---- life cycle ----------------------------------------------------------------------------------- */
+
+/* SlidingWindowSparseEMMatcher / SlidingWindowExpSparseEMMatcher constructors (ref .cpp:325-359,494-519);
+ * the variant is chosen as MultipleGenomeMatchingProcessor.cpp:170-176 does (ctz(k1) != 0 -> Exp).
+ * Allocates on `device`: the reference buffer (refLengthLimit bytes), the 2^24..2^31-slot table and its
+ * occupancy bitmap; plus a host mirror of the reference buffer for getRef(). */
+int mbgcg_create(mbgcg_t** out, uint64_t refLengthLimit, uint32_t targetMatchLength, int k1, int k2, int skipMargin,
+                 int device);
+/* ~SlidingWindowSparseEMMatcher (ref .cpp:460-467) */
+void mbgcg_destroy(mbgcg_t* h);
+const char* mbgcg_last_error(const mbgcg_t* h);
+/* text of the last error of a failed mbgcg_create (no handle exists then) */
+const char* mbgcg_create_error(void);
+
+/* ---- window configuration (ref .h:93-97) ------------------------------------------------------------ */
+void mbgcg_disable_sliding_window(mbgcg_t* h);
+void mbgcg_disable_circular_buffer(mbgcg_t* h);
+void mbgcg_set_sliding_window_size(mbgcg_t* h, int factor);
+
+/* ---- reference loading ------------------------------------------------------------------------------ */
+
+/* loadRef(refText, refLength, loadRCRef, addRegionSeparators, regionSeparator)  (ref .cpp:453-458 -> 402-437
+ * -> index build 146-171).  text is a HOST pointer. */
+int mbgcg_load_ref(mbgcg_t* h, const char* text, uint64_t len, int loadRC, int addSeparators, char separator);
+/* loadSeparator (ref .cpp:439-451) */
+int mbgcg_load_separator(mbgcg_t* h, char separator);
+
+/* ---- matching ------------------------------------------------------------------------------------------ */
+
+/* matchTexts(resMatches, destText, destLen, false, false, minMatchLength, matchingLockPos)
+ * (ref .cpp:477-492 -> 181-321).  text is a HOST pointer.  *out points at handle-owned storage valid until
+ * the next match call (the reference clears the caller's vector first, ref .cpp:484). */
+int mbgcg_match(mbgcg_t* h, const char* text, uint64_t len, uint32_t minMatchLength, uint64_t lockPos,
+                const mbgcg_match_t** out, uint64_t* n);
+
+/* n independent matchTexts calls against the SAME frozen matcher state, in one device pass (the unit the
+ * multi-GPU sharding and the speculative sequential schedule work in).  lockPos may be NULL (no locks).
+ * out: all lists concatenated in text order; counts[i] = matches of text i. */
+int mbgcg_match_batch(mbgcg_t* h, int nTexts, const char* const* texts, const uint64_t* lens, uint32_t minMatchLength,
+                      const uint64_t* lockPos, const mbgcg_match_t** out, const uint64_t** counts);
+
+/* Same, but the texts are already resident in device memory (one buffer; text i occupies
+ * [offsets[i], offsets[i]+lens[i]); offsets must be multiples of 16 with >= 64 zero bytes between texts and
+ * >= 8192 readable bytes after the last one).  Nothing is copied host<->device except the final match
+ * lists.  stream: a cudaStream_t (or NULL for the handle's own stream). */
+int mbgcg_match_batch_device(mbgcg_t* h, const void* dText, int nTexts, const uint64_t* offsets, const uint64_t* lens,
+                             uint32_t minMatchLength, const uint64_t* lockPos, const mbgcg_match_t** out,
+                             const uint64_t** counts);
+
+/* ---- sliding-window locks (ref .cpp:361-400) ------------------------------------------------------------ */
+uint64_t mbgcg_acquire_lock(mbgcg_t* h);
+int mbgcg_release_lock(mbgcg_t* h, uint64_t lockValue);
+
+/* ---- getters / setters (ref .h:104-113) ------------------------------------------------------------------ */
+const char* mbgcg_host_ref(const mbgcg_t* h);            /* getRef(): host mirror of the reference buffer */
+uint64_t mbgcg_max_ref_length(const mbgcg_t* h);         /* getMaxRefLength() */
+uint64_t mbgcg_ref_length(const mbgcg_t* h);             /* getRefLength() */
+uint64_t mbgcg_loading_position(const mbgcg_t* h);       /* getLoadingPosition() */
+uint64_t mbgcg_loaded_ref_length(const mbgcg_t* h);      /* getLoadedRefLength() */
+void mbgcg_set_position(mbgcg_t* h, uint64_t refPos, int reachedRefLengthCount); /* setPosition() */
+void mbgcg_get_state(const mbgcg_t* h, mbgcg_state_t* out);
+/* push the members the reference header's inline methods may have changed behind our back */
+void mbgcg_set_state(mbgcg_t* h, const mbgcg_state_t* in);
+
+/* ---- inspection (tests / bench) ------------------------------------------------------------------------- */
+
+/* Copies the low 32 bits of every table slot (= the reference's ht32bit content) to host memory. */
+int mbgcg_copy_table(mbgcg_t* h, uint32_t* out, uint64_t nSlots);
+/* Copies the device reference buffer [from, from+n) to host memory (to check it equals the mirror). */
+int mbgcg_copy_device_ref(mbgcg_t* h, uint64_t from, uint64_t n, char* out);
+
+/* Stage timings of the last match call, CUDA events on the handle's stream, milliseconds. */
+enum {
+    MBGCG_T_H2D = 0,      /* host->device copy of the texts */
+    MBGCG_T_PROBE = 1,    /* K3: hash + occupancy + table gather + K-mer verify -> seeds */
+    MBGCG_T_COMPACT = 2,  /* scans + seed compaction + run detection */
+    MBGCG_T_EXTEND = 3,   /* K4: bidirectional extension of seed runs */
+    MBGCG_T_RESOLVE = 4,  /* K5: sequential-equivalent overlap/skip resolve -> match lists */
+    MBGCG_T_D2H = 5,      /* device->host copy of the match lists */
+    MBGCG_T_TOTAL = 6,    /* first to last event */
+    MBGCG_T_COUNT = 8
+};
+void mbgcg_last_timing(const mbgcg_t* h, float ms[MBGCG_T_COUNT]);
+/* counters of the last match call: positions probed, seeds, seed runs, matches, kernel launches */
+void mbgcg_last_counters(const mbgcg_t* h, uint64_t out[8]);
+/* total kernel launches issued by this handle since creation */
+uint64_t mbgcg_total_launches(const mbgcg_t* h);
+/* the cudaStream_t every kernel and copy of this handle is issued on (to bracket calls with CUDA events) */
+void* mbgcg_stream(const mbgcg_t* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MBGC_B200_H */

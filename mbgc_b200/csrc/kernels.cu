@@ -1,0 +1,839 @@
+// mbgc_b200/csrc/kernels.cu -- hand-written sm_100a kernels of the MBGC match finder.
+//
+// Everything here is integer / byte work bounded by HBM and L2 bandwidth (no tensor cores: nothing on the
+// path is a contraction).  Results are bit-exact with the reference's single-threaded run; the design note
+// for each kernel says which reference loop it replaces (paths relative to /root/reference, ".cpp" =
+// matching/SlidingWindowSparseEMMatcher.cpp).
+//
+// Data flow of one match pass over a batch of target texts ("contigs") against a frozen index:
+//
+//   K3 k_probe        every target position: hash (utils/Hashes.h:28-40) -> occupancy bit (L2) -> table
+//                     slot -> window test (.cpp:211-222) -> K-mer verify (.cpp:298)  => per-tile seed lists
+//   scan + k_compact  tile counts -> dense, position-ordered seed arrays (pos, enc)
+//   k_heads/k_runs    consecutive seeds on one diagonal with spacing k1 collapse into runs (their k-mers
+//                     overlap, so the whole span is known equal without comparing it again)
+//   K4 k_extend       per run: raw left / right reach beyond its first / last seed (.cpp:227-246, 257-259),
+//                     warp-cooperative 8-byte compares; adjacent runs on one diagonal are linked, not re-walked
+//   K5 k_resolve      per contig: the reference's sequential accept / overlap / skip logic (.cpp:250-315)
+//                     replayed over the run list as pure integer arithmetic (no text access)
+//   k_gather          per-contig match lists -> one dense list for the device->host copy
+#include "kernels.h"
+
+#include <cstdio>
+
+namespace mbgc_b200 {
+
+// ------------------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------------------
+
+// 4 bytes at an arbitrary address from two aligned words (buffers carry >= 64 bytes of padding)
+__device__ __forceinline__ uint32_t ld_u32_unaligned(const uint8_t* p) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~static_cast<uintptr_t>(3));
+    return __funnelshift_r(w[0], w[1], static_cast<uint32_t>(a & 3) * 8);
+}
+
+__device__ __forceinline__ uint64_t ld_u64_unaligned(const uint8_t* p) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~static_cast<uintptr_t>(3));
+    const uint32_t sh = static_cast<uint32_t>(a & 3) * 8;
+    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+    return static_cast<uint64_t>(__funnelshift_r(w0, w1, sh)) |
+           (static_cast<uint64_t>(__funnelshift_r(w1, w2, sh)) << 32);
+}
+
+// utils/Hashes.h:28-40 (maRushPrime1HashSimplified<K>): only the low 32 bits are ever used
+__device__ __forceinline__ uint32_t hash_step(uint32_t h, uint32_t w, uint32_t j) { return (h ^ (w + j)) * 171717u; }
+
+__device__ __forceinline__ uint64_t decode_pos(uint32_t enc, int k1ord) {
+    return k1ord >= 0 ? (static_cast<uint64_t>(enc) << k1ord) : static_cast<uint64_t>(enc);
+}
+
+// .cpp:212-220: is a candidate at reference position s usable under the sliding window?
+__device__ __forceinline__ bool window_ok(uint64_t s, int K, uint64_t pos1, uint64_t swStop, int& cls) {
+    const bool endsBefore = s + K < pos1;
+    const bool startsBefore = s < swStop;
+    cls = (endsBefore ? 1 : 0) | (startsBefore ? 2 : 0);
+    if (pos1 <= swStop) return !(!endsBefore && startsBefore);
+    return !(!endsBefore || startsBefore);
+}
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+// largest c in [0, n) with arr[c] <= x   (arr ascending, arr[0] <= x)
+__device__ __forceinline__ int upper_contig(const uint32_t* arr, int n, uint32_t x) {
+    int lo = 0, hi = n;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (arr[mid] <= x) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K2: index insert  (.cpp:146-171)
+//
+// One thread per sampled reference position.  The reference stores ht[hash] = encodedPos with "last writer
+// in program order wins".  Here every sample carries its global program-order sequence number in the high
+// half of a 64-bit slot, so a single atomicMax realises exactly that order across threads, launches and
+// buffer wrap-arounds.  Lanes of a warp that hit the same slot are merged with __match_any_sync first (the
+// highest lane has the highest sequence number), so each distinct slot costs one atomic per warp.
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_index_insert(const uint8_t* __restrict__ ref, unsigned long long* __restrict__ ht,
+                                                      uint32_t* __restrict__ occ, uint32_t hashMask, int KW, int k1,
+                                                      int k1ord, InsertRange r0, InsertRange r1) {
+    const int64_t total = r0.count + r1.count;
+    const int64_t totalPadded = (total + 31) & ~static_cast<int64_t>(31);
+    const int lane = threadIdx.x & 31;
+    for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < totalPadded;
+         idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const bool valid = idx < total;
+        unsigned long long slotKey = (1ull << 40) + lane;  // unique per lane: never merges
+        unsigned long long key = 0;
+        uint32_t slot = 0;
+        if (valid) {
+            const bool second = idx >= r0.count;
+            const int64_t k = second ? idx - r0.count : idx;
+            const int64_t pos = (second ? r1.begin : r0.begin) + k * k1;
+            const uint64_t seq = (second ? r1.seqBase : r0.seqBase) + static_cast<uint64_t>(k);
+            uint32_t h = static_cast<uint32_t>(KW * 4);
+            for (int j = 0; j < KW; j++) h = hash_step(h, ld_u32_unaligned(ref + pos + 4 * j), j);
+            slot = h & hashMask;
+            const uint32_t enc = static_cast<uint32_t>(k1ord >= 0 ? (static_cast<uint64_t>(pos) >> k1ord)
+                                                                   : static_cast<uint64_t>(pos));
+            key = (seq << 32) | enc;
+            slotKey = slot;
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, slotKey);
+        if (valid && lane == 31 - __clz(peers)) {
+            atomicMax(&ht[slot], key);
+            atomicOr(&occ[slot >> 5], 1u << (slot & 31));
+        }
+    }
+}
+
+void launch_index_insert(const uint8_t* ref, unsigned long long* ht, uint32_t* occ, uint32_t hashMask, int K, int k1,
+                         int k1ord, InsertRange r0, InsertRange r1, cudaStream_t st) {
+    const int64_t total = r0.count + r1.count;
+    if (total <= 0) return;
+    int64_t blocks = (total + 255) / 256;
+    const int64_t cap = static_cast<int64_t>(device_sm_count()) * 16;
+    if (blocks > cap) blocks = cap;
+    k_index_insert<<<static_cast<unsigned>(blocks), 256, 0, st>>>(ref, ht, occ, hashMask, K / 4, k1, k1ord, r0, r1);
+}
+
+__global__ void k_table_low32(const unsigned long long* __restrict__ ht, uint32_t* __restrict__ out, uint64_t n) {
+    for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<uint64_t>(gridDim.x) * blockDim.x)
+        out[i] = static_cast<uint32_t>(ht[i]);
+}
+
+void launch_table_low32(const unsigned long long* ht, uint32_t* out, uint64_t n, cudaStream_t st) {
+    k_table_low32<<<device_sm_count() * 8, 256, 0, st>>>(ht, out, n);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// exclusive scan of a uint32 array whose length may live in device memory (no host sync between stages)
+// ------------------------------------------------------------------------------------------------------
+constexpr int SCAN_THREADS = 1024;
+constexpr int SCAN_ITEMS = 4;
+constexpr int SCAN_BLOCK = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* total, uint32_t* sWarp) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t inc = warp_incl_scan(v, lane);
+    if (lane == 31) sWarp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t w = lane < (blockDim.x >> 5) ? sWarp[lane] : 0;
+        const uint32_t wi = warp_incl_scan(w, lane);
+        sWarp[lane] = wi - w;
+        if (lane == 31) sWarp[32] = wi;
+    }
+    __syncthreads();
+    const uint32_t res = inc - v + sWarp[warp];
+    *total = sWarp[32];
+    __syncthreads();
+    return res;
+}
+
+// n = *nPtr (device-resident length) or nConst; clamped to nMax so an overflowing pass cannot write out of bounds
+__device__ __forceinline__ uint32_t scan_len(const uint32_t* nPtr, uint32_t nConst, uint32_t nMax) {
+    const uint32_t n = nPtr ? *nPtr : nConst;
+    return n < nMax ? n : nMax;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(const uint32_t* __restrict__ in, const uint32_t* nPtr,
+                                                              uint32_t nConst, uint32_t nMax,
+                                                              uint32_t* __restrict__ blockSums) {
+    __shared__ uint32_t sWarp[33];
+    const uint32_t n = scan_len(nPtr, nConst, nMax);
+    const uint32_t nBlocks = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    for (uint32_t b = blockIdx.x; b < nBlocks; b += gridDim.x) {
+        uint32_t s = 0;
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k++) {
+            const uint32_t i = b * SCAN_BLOCK + k * SCAN_THREADS + threadIdx.x;
+            if (i < n) s += in[i];
+        }
+        uint32_t total;
+        block_excl_scan(s, &total, sWarp);
+        if (threadIdx.x == 0) blockSums[b] = total;
+    }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_partials(uint32_t* __restrict__ blockSums, const uint32_t* nPtr,
+                                                                uint32_t nConst, uint32_t nMax) {
+    __shared__ uint32_t sWarp[33];
+    const uint32_t n = scan_len(nPtr, nConst, nMax);
+    const uint32_t nBlocks = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < nBlocks; base += SCAN_THREADS) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < nBlocks ? blockSums[i] : 0;
+        uint32_t total;
+        const uint32_t ex = block_excl_scan(v, &total, sWarp);
+        if (i < nBlocks) blockSums[i] = ex + carry;
+        carry += total;
+    }
+    if (threadIdx.x == 0) blockSums[nBlocks] = carry;
+}
+
+// out may alias in.  out[n] receives the grand total.
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_final(const uint32_t* in, uint32_t* out, const uint32_t* nPtr,
+                                                             uint32_t nConst, uint32_t nMax,
+                                                             const uint32_t* __restrict__ blockSums,
+                                                             uint32_t* totalOut) {
+    __shared__ uint32_t sWarp[33];
+    const uint32_t n = scan_len(nPtr, nConst, nMax);
+    const uint32_t nBlocks = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    for (uint32_t b = blockIdx.x; b < nBlocks; b += gridDim.x) {
+        uint32_t v[SCAN_ITEMS];
+        uint32_t s = 0;
+        const uint32_t i0 = b * SCAN_BLOCK + threadIdx.x * SCAN_ITEMS;
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k++) {
+            v[k] = (i0 + k < n) ? in[i0 + k] : 0;
+            s += v[k];
+        }
+        uint32_t total;
+        uint32_t ex = block_excl_scan(s, &total, sWarp) + blockSums[b];
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k++) {
+            if (i0 + k < n) out[i0 + k] = ex;
+            ex += v[k];
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const uint32_t t = blockSums[nBlocks];
+        out[n] = t;
+        if (totalOut) *totalOut = t;
+    }
+}
+
+static int scan_exclusive(const uint32_t* in, uint32_t* out, const uint32_t* nPtr, uint32_t nConst, uint32_t nMax,
+                          uint32_t* blockSums, uint32_t* totalOut, cudaStream_t st) {
+    uint32_t blocks = (nMax + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    const uint32_t cap = static_cast<uint32_t>(device_sm_count()) * 2;
+    if (blocks > cap) blocks = cap;
+    if (blocks == 0) blocks = 1;
+    k_scan_reduce<<<blocks, SCAN_THREADS, 0, st>>>(in, nPtr, nConst, nMax, blockSums);
+    k_scan_partials<<<1, SCAN_THREADS, 0, st>>>(blockSums, nPtr, nConst, nMax);
+    k_scan_final<<<blocks, SCAN_THREADS, 0, st>>>(in, out, nPtr, nConst, nMax, blockSums, totalOut);
+    return 3;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K3: probe  (.cpp:200-226 and the K-mer verify of :298, for every target position)
+//
+// A CTA owns a tile of 4096 consecutive positions of one contig, staged once in shared memory with 16-byte
+// loads.  Each thread owns 16 consecutive positions: it pulls its 16+K-1 bytes as 128-bit shared loads
+// (conflict-free: consecutive threads, consecutive 16-byte words), forms the unaligned 4-byte words with one
+// funnel shift each and runs the K/4 hash rounds of 16 positions as independent chains.  All 16 occupancy
+// words are requested before any is tested (16 loads in flight per thread); only set bits (seeds plus
+// ~load-factor false positives) go on to the 64-bit table slot, the window test and the K-mer compare against
+// the reference.  Seeds leave the CTA position-ordered (block scan of per-thread counts).
+// ------------------------------------------------------------------------------------------------------
+struct ProbeArgs {
+    IndexState ix;
+    BatchDesc b;
+    uint32_t* tileCount;
+    uint32_t* scratchPos;
+    uint32_t* scratchEnc;
+};
+
+template <int KW>
+__global__ void __launch_bounds__(PROBE_THREADS) k_probe(const ProbeArgs a) {
+    constexpr int NPT = PROBE_NPT;
+    constexpr int TILE = PROBE_TILE;
+    constexpr int NW = NPT / 4 + KW;                 // aligned words a thread needs (index NPT/4-1+KW is the funnel partner)
+    constexpr int NV = (NW + 3) / 4;                 // 128-bit loads per thread
+    __shared__ uint4 sText[TILE / 16 + 8];
+    __shared__ uint32_t sWarp[33];
+    __shared__ int sContig;
+
+    const int tid = threadIdx.x;
+    const int K = KW * 4;
+    for (uint32_t tile = blockIdx.x; tile < a.b.nTiles; tile += gridDim.x) {
+        if (tid == 0) sContig = upper_contig(a.b.tileStart, a.b.nContigs, tile);
+        __syncthreads();
+        const int c = sContig;
+        const uint32_t base = (tile - a.b.tileStart[c]) * TILE;  // contig-local position of the tile start
+        const uint32_t N2 = a.b.contigLen[c];
+        const uint32_t nValid = N2 >= static_cast<uint32_t>(K) ? N2 - K + 1 : 0;
+        const uint64_t lock = a.b.contigLock ? a.b.contigLock[c] : NO_LOCK;
+        const uint64_t swStop = lock != NO_LOCK ? lock : a.ix.pos1;
+        const uint4* g = reinterpret_cast<const uint4*>(a.b.text + a.b.contigOff[c] + base);
+        for (int k = tid; k < TILE / 16 + 8; k += PROBE_THREADS) sText[k] = g[k];
+        __syncthreads();
+
+        uint32_t A[NV * 4];
+#pragma unroll
+        for (int k = 0; k < NV; k++) {
+            const uint4 v = sText[tid + k];
+            A[4 * k] = v.x; A[4 * k + 1] = v.y; A[4 * k + 2] = v.z; A[4 * k + 3] = v.w;
+        }
+
+        uint32_t slots[NPT];
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            uint32_t V[NPT / 4 + KW - 1];
+#pragma unroll
+            for (int m = 0; m < NPT / 4 + KW - 1; m++) V[m] = r == 0 ? A[m] : __funnelshift_r(A[m], A[m + 1], 8 * r);
+#pragma unroll
+            for (int q = 0; q < NPT / 4; q++) {
+                uint32_t h = static_cast<uint32_t>(K);
+#pragma unroll
+                for (int j = 0; j < KW; j++) h = hash_step(h, V[q + j], j);
+                slots[4 * q + r] = h & a.ix.hashMask;
+            }
+        }
+        uint32_t occw[NPT];
+#pragma unroll
+        for (int p = 0; p < NPT; p++) occw[p] = __ldg(&a.ix.occ[slots[p] >> 5]);
+
+        const uint32_t p0 = base + tid * NPT;
+        uint32_t encs[NPT];
+        uint32_t mask = 0;
+#pragma unroll
+        for (int p = 0; p < NPT; p++) {
+            encs[p] = 0;
+            if (((occw[p] >> (slots[p] & 31)) & 1u) && p0 + p < nValid) {
+                const uint32_t enc = static_cast<uint32_t>(a.ix.ht[slots[p]]);
+                if (enc != 0) {
+                    const uint64_t s = decode_pos(enc, a.ix.k1ord);
+                    int cls;
+                    if (window_ok(s, K, a.ix.pos1, swStop, cls)) {
+                        const uint8_t* t = reinterpret_cast<const uint8_t*>(sText) + tid * NPT + p;
+                        const uint8_t* r = a.ix.ref + s;
+                        bool eq = true;
+#pragma unroll
+                        for (int j = 0; j < KW; j++) eq = eq && (ld_u32_unaligned(t + 4 * j) == ld_u32_unaligned(r + 4 * j));
+                        if (eq) {
+                            encs[p] = enc;
+                            mask |= 1u << p;
+                        }
+                    }
+                }
+            }
+        }
+        uint32_t total;
+        uint32_t off = block_excl_scan(__popc(mask), &total, sWarp);
+        if (mask) {
+            const uint64_t o = static_cast<uint64_t>(tile) * TILE + off;
+            uint32_t k = 0;
+#pragma unroll
+            for (int p = 0; p < NPT; p++)
+                if (mask & (1u << p)) {
+                    a.scratchPos[o + k] = p0 + p;
+                    a.scratchEnc[o + k] = encs[p];
+                    k++;
+                }
+        }
+        if (tid == 0) a.tileCount[tile] = total;
+    }
+}
+
+bool probe_supports_K(int K) {
+    switch (K) {
+        case 12: case 16: case 20: case 24: case 28: case 32: case 36: case 40: case 44: case 56: return true;
+        default: return false;
+    }
+}
+
+static int g_smCount = 0;
+int device_sm_count() {
+    if (g_smCount == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_smCount, cudaDevAttrMultiProcessorCount, dev);
+        if (g_smCount <= 0) g_smCount = 148;
+    }
+    return g_smCount;
+}
+
+int launch_probe(const IndexState& ix, const BatchDesc& b, const WorkBuffers& w, cudaStream_t st) {
+    if (b.nTiles == 0) {
+        cudaMemsetAsync(w.tileCount, 0, sizeof(uint32_t), st);
+        return 0;
+    }
+    ProbeArgs a{ix, b, w.tileCount, w.scratchPos, w.scratchEnc};
+    uint32_t blocks = b.nTiles;
+    const uint32_t cap = static_cast<uint32_t>(device_sm_count()) * 8;  // persistent: whole waves of resident CTAs
+    if (blocks > cap) blocks = cap;
+#define MBGC_PROBE_CASE(KK) \
+    case KK: k_probe<KK / 4><<<blocks, PROBE_THREADS, 0, st>>>(a); break;
+    switch (ix.K) {
+        MBGC_PROBE_CASE(12) MBGC_PROBE_CASE(16) MBGC_PROBE_CASE(20) MBGC_PROBE_CASE(24) MBGC_PROBE_CASE(28)
+        MBGC_PROBE_CASE(32) MBGC_PROBE_CASE(36) MBGC_PROBE_CASE(40) MBGC_PROBE_CASE(44) MBGC_PROBE_CASE(56)
+        default: return -1;
+    }
+#undef MBGC_PROBE_CASE
+    return 1;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// seed compaction + run detection
+// ------------------------------------------------------------------------------------------------------
+
+// tile-local seed lists -> dense arrays (tileOff = exclusive scan of the tile counts)
+__global__ void __launch_bounds__(256) k_compact(BatchDesc b, const uint32_t* __restrict__ tileOff,
+                                                 const uint32_t* __restrict__ scratchPos,
+                                                 const uint32_t* __restrict__ scratchEnc, uint32_t* __restrict__ seedPos,
+                                                 uint32_t* __restrict__ seedEnc, uint32_t seedCap, uint32_t* counters) {
+    const uint32_t nSeeds = tileOff[b.nTiles];
+    if (nSeeds > seedCap) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) counters[3] = 1;  // overflow: host retries with more room
+        return;
+    }
+    for (uint32_t tile = blockIdx.x; tile < b.nTiles; tile += gridDim.x) {
+        const uint32_t o = tileOff[tile], n = tileOff[tile + 1] - o;
+        const uint64_t src = static_cast<uint64_t>(tile) * PROBE_TILE;
+        for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) {
+            seedPos[o + k] = scratchPos[src + k];
+            seedEnc[o + k] = scratchEnc[src + k];
+        }
+    }
+}
+
+// head[j] = 1 iff seed j starts a run: first seed of its contig, or not (previous pos + k1, previous enc + step),
+// or a different window class (the class fixes the extension bounds tmpStart1/tmpEnd1, .cpp:221-222).
+// Seeds only collapse when their k-mers touch or overlap (k1 <= K); otherwise (protein profile: K = 12 < k1 = 16)
+// the bases between two seeds are unverified and every seed is its own run.
+__global__ void __launch_bounds__(256) k_heads(IndexState ix, BatchDesc b, const uint32_t* __restrict__ tileOff,
+                                               const uint32_t* __restrict__ seedPos, const uint32_t* __restrict__ seedEnc,
+                                               uint32_t* __restrict__ head, const uint32_t* counters) {
+    if (counters[3]) return;
+    __shared__ int sContig;
+    const uint32_t encStep = ix.k1ord >= 0 ? static_cast<uint32_t>(ix.k1 >> ix.k1ord) : static_cast<uint32_t>(ix.k1);
+    for (uint32_t tile = blockIdx.x; tile < b.nTiles; tile += gridDim.x) {
+        __syncthreads();
+        if (threadIdx.x == 0) sContig = upper_contig(b.tileStart, b.nContigs, tile);
+        __syncthreads();
+        const int c = sContig;
+        const uint32_t contigFirst = tileOff[b.tileStart[c]];
+        const uint64_t lock = b.contigLock ? b.contigLock[c] : NO_LOCK;
+        const uint64_t swStop = lock != NO_LOCK ? lock : ix.pos1;
+        const uint32_t o = tileOff[tile], n = tileOff[tile + 1] - o;
+        for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) {
+            const uint32_t j = o + k;
+            uint32_t h = 1;
+            if (j != contigFirst) {
+                const uint32_t e = seedEnc[j], ep = seedEnc[j - 1];
+                if (ix.k1 <= ix.K && seedPos[j] - seedPos[j - 1] == static_cast<uint32_t>(ix.k1) && e - ep == encStep) {
+                    int c0, c1;
+                    window_ok(decode_pos(e, ix.k1ord), ix.K, ix.pos1, swStop, c0);
+                    window_ok(decode_pos(ep, ix.k1ord), ix.K, ix.pos1, swStop, c1);
+                    h = c0 != c1;
+                }
+            }
+            head[j] = h;
+        }
+    }
+}
+
+// runFirst[run] = first seed of the run; runStart[c] = first run of contig c (runStart[nContigs] = nRuns)
+__global__ void __launch_bounds__(256) k_runs(BatchDesc b, const uint32_t* __restrict__ tileOff,
+                                              const uint32_t* __restrict__ headScan, uint32_t* __restrict__ runFirst,
+                                              uint32_t* __restrict__ runStart, uint32_t* counters) {
+    if (counters[3]) return;
+    const uint32_t nSeeds = tileOff[b.nTiles];
+    const uint32_t nRuns = headScan[nSeeds];
+    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+    for (uint32_t j = gtid; j < nSeeds; j += gsz)
+        if (headScan[j + 1] != headScan[j]) runFirst[headScan[j]] = j;
+    for (uint32_t c = gtid; c <= static_cast<uint32_t>(b.nContigs); c += gsz) {
+        const uint32_t s = c < static_cast<uint32_t>(b.nContigs) ? tileOff[b.tileStart[c]] : nSeeds;
+        runStart[c] = headScan[s];  // headScan[nSeeds] = nRuns
+    }
+    if (gtid == 0) {
+        runFirst[nRuns] = nSeeds;
+        counters[0] = nSeeds;
+        counters[1] = nRuns;
+    }
+}
+
+int launch_compact_and_runs(const IndexState& ix, const BatchDesc& b, const WorkBuffers& w, cudaStream_t st) {
+    int launches = 0;
+    const int sm = device_sm_count();
+    // tileCount -> tileOff (in place), tileOff[nTiles] = nSeeds
+    launches += scan_exclusive(w.tileCount, w.tileCount, nullptr, b.nTiles, b.nTiles, w.blockSums, nullptr, st);
+    k_compact<<<sm * 8, 256, 0, st>>>(b, w.tileCount, w.scratchPos, w.scratchEnc, w.seedPos, w.seedEnc, w.seedCap,
+                                      w.counters);
+    k_heads<<<sm * 8, 256, 0, st>>>(ix, b, w.tileCount, w.seedPos, w.seedEnc, w.headScan, w.counters);
+    launches += 2;
+    // head flags -> exclusive scan in place; length lives on the device (tileOff[nTiles])
+    launches += scan_exclusive(w.headScan, w.headScan, w.tileCount + b.nTiles, 0, w.seedCap, w.blockSums, nullptr, st);
+    k_runs<<<sm * 8, 256, 0, st>>>(b, w.tileCount, w.headScan, w.runFirst, w.runStart, w.counters);
+    launches += 1;
+    return launches;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K4: extend  (.cpp:227-246 right, :257-259 / :278-280 raw left)
+//
+// One warp per seed run.  Inside a run every base is already known equal (overlapping verified k-mers), so
+// only the stretch left of the first seed and right of the last seed's k-mer is compared: 32 lanes x 8 bytes
+// per step, XOR + __clzll/__ffsll for the first differing byte, __ballot_sync for the first lane that stops.
+// If the neighbouring run lies on the same diagonal (a sampled k-mer was overwritten in the table, so the seed
+// chain broke although the bases still match) the walk stops at the neighbour's verified span and the run is
+// marked linked; K5 resolves link chains, so no stretch of text is ever compared twice.
+// ------------------------------------------------------------------------------------------------------
+struct ExtendArgs {
+    IndexState ix;
+    BatchDesc b;
+    const uint32_t* tileOff;
+    const uint32_t* seedPos;
+    const uint32_t* seedEnc;
+    const uint32_t* runFirst;
+    const uint32_t* runStart;
+    RunRec* runs;
+    const uint32_t* counters;
+};
+
+__global__ void __launch_bounds__(256) k_extend(const ExtendArgs a) {
+    if (a.counters[3]) return;
+    const uint32_t nRuns = a.counters[1];
+    const int lane = threadIdx.x & 31;
+    const uint32_t warpsTotal = gridDim.x * (blockDim.x >> 5);
+    const int K = a.ix.K, k1 = a.ix.k1;
+    for (uint32_t r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < nRuns; r += warpsTotal) {
+        // contig of this run: largest c with runStart[c] <= r
+        const int c = upper_contig(a.runStart, a.b.nContigs + 1, r);
+        const uint32_t N2 = a.b.contigLen[c];
+        const uint8_t* T = a.b.text + a.b.contigOff[c];
+        const uint64_t lock = a.b.contigLock ? a.b.contigLock[c] : NO_LOCK;
+        const uint64_t swStop = lock != NO_LOCK ? lock : a.ix.pos1;
+        const uint32_t j0 = a.runFirst[r], j1 = a.runFirst[r + 1];
+        const uint32_t firstPos = a.seedPos[j0], enc0 = a.seedEnc[j0];
+        const uint32_t lastPos = a.seedPos[j1 - 1];
+        const int64_t s0 = static_cast<int64_t>(decode_pos(enc0, a.ix.k1ord));
+        const int64_t d = s0 - static_cast<int64_t>(firstPos);  // reference position = target position + d
+        int cls;
+        window_ok(static_cast<uint64_t>(s0), K, a.ix.pos1, swStop, cls);
+        const uint8_t* R = a.ix.ref;
+
+        // ---- left
+        bool leftCand = false;
+        int64_t stopL = d < 0 ? -d : 0;  // target position below which nothing is compared (ref index >= 0)
+        if (r > a.runStart[c]) {
+            const uint32_t pp = a.seedPos[j0 - 1];
+            const int64_t sp = static_cast<int64_t>(decode_pos(a.seedEnc[j0 - 1], a.ix.k1ord));
+            int clsP;
+            window_ok(static_cast<uint64_t>(sp), K, a.ix.pos1, swStop, clsP);
+            if (sp - static_cast<int64_t>(pp) == d && clsP == cls) {
+                leftCand = true;
+                stopL = static_cast<int64_t>(pp) + K;  // end of the previous run's verified span
+            }
+        }
+        int64_t hiEnd = firstPos;  // bytes [.., hiEnd) still to compare, walking left
+        int64_t mism = stopL - 1;  // position of the first mismatch (or the stop bound - 1)
+        bool dataMismatch = false;
+        while (hiEnd > stopL) {
+            const int64_t hi_l = hiEnd - 8 * lane, lo_l = hi_l - 8;
+            int64_t m = INT64_MIN;
+            bool isData = false;
+            if (hi_l > stopL) {
+                const uint64_t x = ld_u64_unaligned(T + lo_l) ^ ld_u64_unaligned(R + lo_l + d);
+                // bytes below stopL are outside the comparison: drop them from the diff
+                uint64_t diff = x;
+                if (lo_l < stopL) diff &= ~0ull << (8 * (stopL - lo_l));
+                if (diff) {
+                    m = lo_l + (63 - __clzll(diff)) / 8;
+                    isData = true;
+                } else if (lo_l <= stopL) {
+                    m = stopL - 1;
+                }
+            } else {
+                m = stopL - 1;
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, m != INT64_MIN);
+            if (bal) {
+                const int src = __ffs(bal) - 1;
+                mism = __shfl_sync(0xffffffffu, m, src);
+                dataMismatch = __shfl_sync(0xffffffffu, isData ? 1 : 0, src) != 0;
+                break;
+            }
+            hiEnd -= 256;
+        }
+        const bool leftLinked = leftCand && !dataMismatch;
+        const uint32_t aFree = static_cast<uint32_t>(mism + 1);
+
+        // ---- right
+        const int64_t refCap = static_cast<int64_t>(a.ix.refLen);
+        int64_t stopR = N2;  // exclusive target bound
+        if (refCap - d < stopR) stopR = refCap - d;
+        bool rightCand = false;
+        if (r + 1 < a.runStart[c + 1]) {
+            const uint32_t np = a.seedPos[j1];
+            const int64_t sn = static_cast<int64_t>(decode_pos(a.seedEnc[j1], a.ix.k1ord));
+            int clsN;
+            window_ok(static_cast<uint64_t>(sn), K, a.ix.pos1, swStop, clsN);
+            if (sn - static_cast<int64_t>(np) == d && clsN == cls && static_cast<int64_t>(np) <= stopR) {
+                rightCand = true;
+                stopR = np;
+            }
+        }
+        int64_t loBeg = static_cast<int64_t>(lastPos) + K;
+        int64_t mismR = stopR;
+        bool dataMismatchR = false;
+        while (loBeg < stopR) {
+            const int64_t lo_l = loBeg + 8 * lane, hi_l = lo_l + 8;
+            int64_t m = INT64_MIN;
+            bool isData = false;
+            if (lo_l < stopR) {
+                const uint64_t x = ld_u64_unaligned(T + lo_l) ^ ld_u64_unaligned(R + lo_l + d);
+                uint64_t diff = x;
+                if (hi_l > stopR) diff &= ~0ull >> (8 * (hi_l - stopR));
+                if (diff) {
+                    m = lo_l + (__ffsll(static_cast<long long>(diff)) - 1) / 8;
+                    isData = true;
+                } else if (hi_l >= stopR) {
+                    m = stopR;
+                }
+            } else {
+                m = stopR;
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, m != INT64_MIN);
+            if (bal) {
+                const int src = __ffs(bal) - 1;
+                mismR = __shfl_sync(0xffffffffu, m, src);
+                dataMismatchR = __shfl_sync(0xffffffffu, isData ? 1 : 0, src) != 0;
+                break;
+            }
+            loBeg += 256;
+        }
+        const bool rightLinked = rightCand && !dataMismatchR;
+        if (lane == 0) {
+            RunRec rec;
+            rec.firstPos = firstPos;
+            rec.nSeeds = j1 - j0;
+            rec.enc0 = enc0;
+            rec.aFree = aFree;
+            rec.bFree = static_cast<uint32_t>(mismR);
+            rec.flags = (leftLinked ? 1u : 0u) | (rightLinked ? 2u : 0u);
+            a.runs[r] = rec;
+        }
+    }
+}
+
+int launch_extend(const IndexState& ix, const BatchDesc& b, const WorkBuffers& w, cudaStream_t st) {
+    ExtendArgs a{ix, b, w.tileCount, w.seedPos, w.seedEnc, w.runFirst, w.runStart, w.runs, w.counters};
+    k_extend<<<device_sm_count() * 8, 256, 0, st>>>(a);
+    return 1;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K5: resolve  (.cpp:250-315)
+//
+// The reference scans a contig left to right; an accepted match makes the cursor jump to matchEnd -
+// skipMargin, and its left edge depends on the stack of matches accepted so far (trim to the previous end,
+// or swallow the previous match when the new diagonal also covers it).  Given the run list this is pure
+// integer arithmetic: for the first seed at or after the cursor, the maximal equal interval [aFree, bFree)
+// of its run replaces every byte comparison of the reference loop.  One warp per contig: the warp stages
+// 32 run records at a time in shared memory, lane 0 replays the state machine.
+// ------------------------------------------------------------------------------------------------------
+struct ResolveArgs {
+    IndexState ix;
+    BatchDesc b;
+    const RunRec* runs;
+    const uint32_t* runStart;
+    MatchRec* matches;
+    uint32_t* matchCount;
+    const uint32_t* counters;
+    uint32_t minMatchLength;
+};
+
+constexpr int RESOLVE_WARPS = 4;
+
+__device__ __forceinline__ int64_t max3(int64_t a, int64_t b, int64_t c) {
+    const int64_t m = a > b ? a : b;
+    return m > c ? m : c;
+}
+
+__global__ void __launch_bounds__(RESOLVE_WARPS * 32) k_resolve(const ResolveArgs a) {
+    if (a.counters[3]) return;
+    __shared__ RunRec sRuns[RESOLVE_WARPS][32];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int warpsTotal = gridDim.x * RESOLVE_WARPS;
+    const int K = a.ix.K, k1 = a.ix.k1, M = a.ix.skipMargin;
+    const int64_t OVERLAP_MATCH_MAX_LENGTH = 1 << 13;  // SlidingWindowSparseEMMatcher.h:18
+    for (int c = blockIdx.x * RESOLVE_WARPS + wib; c < a.b.nContigs; c += warpsTotal) {
+        const uint32_t rs = a.runStart[c], re = a.runStart[c + 1];
+        const uint64_t lock = a.b.contigLock ? a.b.contigLock[c] : NO_LOCK;
+        const int64_t pos1 = static_cast<int64_t>(a.ix.pos1);
+        const int64_t swStop = lock != NO_LOCK ? static_cast<int64_t>(lock) : pos1;
+        const int64_t refLen = static_cast<int64_t>(a.ix.refLen);
+        MatchRec* out = a.matches + rs;
+        uint32_t nOut = 0;
+        int64_t cur = 0;
+        int64_t prevAFree = 0;
+        for (uint32_t base = rs; base < re; base += 32) {
+            if (base + lane < re) sRuns[wib][lane] = a.runs[base + lane];
+            __syncwarp();
+            if (lane == 0) {
+                const uint32_t cnt = re - base < 32 ? re - base : 32;
+                for (uint32_t k = 0; k < cnt; k++) {
+                    const RunRec run = sRuns[wib][k];
+                    const int64_t aRes = (run.flags & 1u) ? prevAFree : static_cast<int64_t>(run.aFree);
+                    prevAFree = aRes;
+                    const int64_t firstPos = run.firstPos;
+                    const int64_t lastPos = firstPos + static_cast<int64_t>(run.nSeeds - 1) * k1;
+                    int64_t bRes = -1;
+                    while (lastPos >= cur) {
+                        int64_t i = firstPos;
+                        if (cur > i) i += ((cur - i + k1 - 1) / k1) * k1;
+                        const int64_t s = static_cast<int64_t>(decode_pos(run.enc0, a.ix.k1ord)) + (i - firstPos);
+                        const int64_t d = s - i;
+                        if (bRes < 0) {  // follow the right-link chain once per run
+                            uint32_t rr = base + k;
+                            uint32_t fl = run.flags;
+                            bRes = run.bFree;
+                            while (fl & 2u) {
+                                rr++;
+                                const RunRec nx = a.runs[rr];
+                                fl = nx.flags;
+                                bRes = nx.bFree;
+                            }
+                        }
+                        const bool endsBefore = s + K < pos1;
+                        const bool startsBefore = s < swStop;
+                        const int64_t hi = endsBefore ? pos1 : refLen;  // tmpEnd1
+                        const int64_t lo = startsBefore ? 0 : swStop;   // tmpStart1
+                        int64_t right1 = bRes + d;
+                        if (hi < right1) right1 = hi;
+
+                        // left edge with overlap resolution (.cpp:251-291); p2 = inclusive matched cursor,
+                        // e = exclusive cursor (the reference's final p2)
+                        int64_t p2 = i, e = 0;
+                        uint32_t idx = nOut;
+                        bool broke = false;
+                        while (idx > 0) {
+                            const MatchRec last = out[idx - 1];
+                            const int64_t lastDst = last.dst, lastEnd = lastDst + last.len;
+                            if (lastEnd < p2) {
+                                const int64_t stop = max3(aRes - 1, lo - d, lastEnd - 1);
+                                if (stop > lastEnd - 1) {
+                                    e = stop;
+                                    broke = true;
+                                    break;
+                                }
+                                p2 = lastEnd;
+                            }
+                            const int64_t lastDelta = p2 - lastDst;
+                            if ((p2 + d) - lo < lastDelta || static_cast<int64_t>(last.len) > OVERLAP_MATCH_MAX_LENGTH ||
+                                aRes > lastDst) {
+                                e = p2 - 1;
+                                broke = true;
+                                break;
+                            }
+                            p2 = lastDst;
+                            idx--;
+                        }
+                        if (!broke) {
+                            e = max3(aRes - 1, lo - d, -1);
+                        } else {
+                            const MatchRec keep = out[idx - 1];
+                            const int64_t overlap = static_cast<int64_t>(keep.dst) + keep.len - (e + 1);
+                            if (overlap > 0) e += overlap;
+                        }
+                        const int64_t len = right1 - (e + d) - 1;
+                        if (len >= static_cast<int64_t>(a.minMatchLength) && idx < re - rs) {
+                            nOut = idx;
+                            MatchRec mr;
+                            mr.src = static_cast<uint64_t>(e + d + 1);
+                            mr.dst = static_cast<uint32_t>(e + 1);
+                            mr.len = static_cast<uint32_t>(len);
+                            out[nOut++] = mr;
+                            int64_t skip = (e + 1 + len) - i;
+                            skip -= skip > M ? M : skip;
+                            cur = i + (skip ? skip : 1);
+                        } else {
+                            cur = i + 1;
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        if (lane == 0) a.matchCount[c] = nOut;
+    }
+}
+
+// matchOff = exclusive scan of matchCount (single block: nContigs is small next to the seed counts)
+__global__ void __launch_bounds__(SCAN_THREADS) k_match_offsets(const uint32_t* __restrict__ matchCount,
+                                                                uint32_t* __restrict__ matchOff, int nContigs,
+                                                                uint32_t* counters) {
+    __shared__ uint32_t sWarp[33];
+    uint32_t carry = 0;
+    for (int base = 0; base < nContigs; base += SCAN_THREADS) {
+        const int i = base + threadIdx.x;
+        const uint32_t v = i < nContigs ? matchCount[i] : 0;
+        uint32_t total;
+        const uint32_t ex = block_excl_scan(v, &total, sWarp);
+        if (i < nContigs) matchOff[i] = ex + carry;
+        carry += total;
+    }
+    if (threadIdx.x == 0) {
+        matchOff[nContigs] = carry;
+        counters[2] = carry;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_gather(const MatchRec* __restrict__ matches, const uint32_t* __restrict__ runStart,
+                                                const uint32_t* __restrict__ matchOff, MatchRec* __restrict__ dense,
+                                                int nContigs, const uint32_t* counters) {
+    if (counters[3]) return;
+    const int lane = threadIdx.x & 31;
+    const int warpsTotal = gridDim.x * (blockDim.x >> 5);
+    for (int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); c < nContigs; c += warpsTotal) {
+        const uint32_t n = matchOff[c + 1] - matchOff[c];
+        const MatchRec* src = matches + runStart[c];
+        MatchRec* dst = dense + matchOff[c];
+        for (uint32_t k = lane; k < n; k += 32) dst[k] = src[k];
+    }
+}
+
+int launch_resolve(const IndexState& ix, const BatchDesc& b, const WorkBuffers& w, uint32_t minMatchLength,
+                   cudaStream_t st) {
+    ResolveArgs a{ix, b, w.runs, w.runStart, w.matches, w.matchCount, w.counters, minMatchLength};
+    int blocks = (b.nContigs + RESOLVE_WARPS - 1) / RESOLVE_WARPS;
+    const int cap = device_sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    k_resolve<<<blocks, RESOLVE_WARPS * 32, 0, st>>>(a);
+    k_match_offsets<<<1, SCAN_THREADS, 0, st>>>(w.matchCount, w.matchOff, b.nContigs, w.counters);
+    k_gather<<<device_sm_count() * 4, 256, 0, st>>>(w.matches, w.runStart, w.matchOff, w.matchesDense, b.nContigs,
+                                                    w.counters);
+    return 3;
+}
+
+}  // namespace mbgc_b200

@@ -1,0 +1,99 @@
+// mbgc_b200/csrc/kernels.h -- host-visible launchers of the sm_100a kernels (kernels.cu).
+//
+// Kernel set ("New kernel" table) and the reference loop each replaces
+// (paths relative to /root/reference):
+//   K2 index_insert      matching/SlidingWindowSparseEMMatcher.cpp:146-171 (processIgnoreCollisionsRef)
+//   K3 probe             .cpp:200-226 + the K-mer verify of :298, for EVERY target position
+//   K4 extend            .cpp:227-246 (right) and the raw left reach of :257-259/:278-280
+//   K5 resolve           .cpp:250-315 (overlap resolution, accept, skip) as a sequential-equivalent walk
+// plus plumbing kernels (exclusive scan, seed compaction, run detection, match gather).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mbgc_b200 {
+
+constexpr int PROBE_THREADS = 256;
+constexpr int PROBE_NPT = 16;                       // positions per thread
+constexpr int PROBE_TILE = PROBE_THREADS * PROBE_NPT;  // positions per tile (4096)
+constexpr uint64_t NO_LOCK = UINT64_MAX;
+
+struct RunRec {          // one seed run = consecutive seeds on one diagonal, spacing k1 (24 bytes)
+    uint32_t firstPos;   // target position of the first seed
+    uint32_t nSeeds;
+    uint32_t enc0;       // table entry (encoded reference position) of the first seed
+    uint32_t aFree;      // left end of the maximal equal interval (valid if !leftLinked)
+    uint32_t bFree;      // right end (exclusive) of the maximal equal interval (valid if !rightLinked)
+    uint32_t flags;      // bit0 leftLinked (aFree = that of the previous run), bit1 rightLinked
+};
+
+struct MatchRec {        // 16 bytes, expanded to the 32-byte TextMatch on the host
+    uint64_t src;
+    uint32_t dst;
+    uint32_t len;
+};
+
+struct IndexState {      // frozen matcher state a match pass runs against
+    const uint8_t* ref;  // device reference buffer (ref[0] is position 0)
+    const unsigned long long* ht;  // 64-bit slots: (insert sequence number << 32) | encoded position
+    const uint32_t* occ; // occupancy bitmap, 1 bit per slot
+    uint32_t hashMask;
+    int K;               // hashed prefix length (bytes), multiple of 4
+    int k1;              // reference sampling step
+    int k1ord;           // >= 0: Exp variant (entry = pos >> k1ord); -1: plain
+    int skipMargin;
+    uint64_t pos1;       // loader cursor
+    uint64_t refLen;     // getRefLength()
+};
+
+struct BatchDesc {       // device pointers describing the texts of one pass
+    const uint8_t* text;
+    const uint64_t* contigOff;   // [nContigs]
+    const uint32_t* contigLen;   // [nContigs]
+    const uint64_t* contigLock;  // [nContigs] or nullptr
+    const uint32_t* tileStart;   // [nContigs+1]
+    int nContigs;
+    uint32_t nTiles;
+};
+
+struct WorkBuffers {     // device scratch of one pass
+    uint32_t* tileCount;     // [nTiles+1] -> exclusive scan in place (tileOffset)
+    uint32_t* scratchPos;    // [nTiles*PROBE_TILE]
+    uint32_t* scratchEnc;    // [nTiles*PROBE_TILE]
+    uint32_t* seedPos;       // [seedCap]
+    uint32_t* seedEnc;       // [seedCap]
+    uint32_t* headScan;      // [seedCap+1]
+    uint32_t* runFirst;      // [seedCap+1]
+    RunRec* runs;            // [seedCap]
+    uint32_t* runStart;      // [nContigs+1]
+    MatchRec* matches;       // [seedCap] per-contig regions at runStart[c]
+    uint32_t* matchCount;    // [nContigs+1] -> exclusive scan (matchOff) in matchOff
+    uint32_t* matchOff;      // [nContigs+1]
+    MatchRec* matchesDense;  // [seedCap]
+    uint32_t* blockSums;     // scan temporaries
+    uint32_t* counters;      // [8]: 0 nSeeds, 1 nRuns, 2 nMatches, 3 overflow flag
+    uint32_t seedCap;
+};
+
+// ---- index build ----
+struct InsertRange {
+    int64_t begin;       // first sampled reference position
+    int64_t count;       // number of samples (step k1)
+    uint64_t seqBase;    // global insert sequence number of the first sample
+};
+void launch_index_insert(const uint8_t* ref, unsigned long long* ht, uint32_t* occ, uint32_t hashMask, int K, int k1,
+                         int k1ord, InsertRange r0, InsertRange r1, cudaStream_t st);
+void launch_table_low32(const unsigned long long* ht, uint32_t* out, uint64_t n, cudaStream_t st);
+
+// ---- match pass ----
+// returns the number of kernel launches issued
+int launch_probe(const IndexState& ix, const BatchDesc& b, const WorkBuffers& w, cudaStream_t st);
+int launch_compact_and_runs(const IndexState& ix, const BatchDesc& b, const WorkBuffers& w, cudaStream_t st);
+int launch_extend(const IndexState& ix, const BatchDesc& b, const WorkBuffers& w, cudaStream_t st);
+int launch_resolve(const IndexState& ix, const BatchDesc& b, const WorkBuffers& w, uint32_t minMatchLength,
+                   cudaStream_t st);
+
+bool probe_supports_K(int K);
+int device_sm_count();
+
+}  // namespace mbgc_b200

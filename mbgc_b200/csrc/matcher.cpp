@@ -1,0 +1,525 @@
+// mbgc_b200/csrc/matcher.cpp -- host logic of B200SparseEMMatcher (see matcher.hpp).
+//
+// Reference citations: ".cpp"/".h" = /root/reference/matching/SlidingWindowSparseEMMatcher.{cpp,h}.
+#include "matcher.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+#include "../../include/mbgc_b200.h"
+
+namespace mbgc_b200 {
+
+namespace {
+
+constexpr uint64_t PAD = 64;            // padding before/after device buffers (unaligned loads may over-read)
+constexpr uint64_t TEXT_GAP = 64;       // bytes between texts of a batch
+constexpr uint64_t TEXT_TAIL = 8192;    // readable bytes after the last text (tile staging over-reads)
+
+inline uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
+
+// utils/helper.cpp:312-358: the upper-casing complement table.  Identity, except the listed IUPAC letters
+// in either case; the reference fills the identity only for CHAR_MIN..CHAR_MAX-1, so 0x7F maps to 0.
+struct ComplementLut {
+    uint8_t t[256];
+    ComplementLut() {
+        for (int i = 0; i < 256; i++) t[i] = static_cast<uint8_t>(i);
+        t[0x7F] = 0;
+        const char* from = "ACGTNUYRKMBDHVWS";
+        const char* to = "TGCANARYMKVHDBSW";
+        for (int i = 0; from[i]; i++) {
+            t[static_cast<uint8_t>(from[i])] = static_cast<uint8_t>(to[i]);
+            t[static_cast<uint8_t>(from[i] + 32)] = static_cast<uint8_t>(to[i]);
+        }
+    }
+};
+const ComplementLut g_lut;
+
+// .cpp:75-87
+int kmer_from_L(int L, uint32_t minMatchLength) {
+    int K;
+    if (L > 110) K = 56;
+    else if (L > 62) K = 44;
+    else if (L > 53) K = 40;
+    else if (L > 46) K = 36;
+    else if (L > 42) K = 32;
+    else if (L > 32) K = 28;
+    else K = (L / 4 - 1) * 4;
+    const int KmmL = (static_cast<int>(minMatchLength) / 4 - 1) * 4;
+    if (KmmL < K) K = KmmL;
+    return K;
+}
+
+// .cpp:118-144
+void calc_coprimes(int L, int K, int& k1, int& k2) {
+    const int t = L - K + 1;
+    if (t >= 20) {
+        k1 = static_cast<int>(std::pow(t, 0.5)) + 1;
+        k2 = k1 - 1;
+        if (k1 * k2 > t) { --k2; --k1; }
+    } else if (t >= 15) { k1 = 5; k2 = 3; }
+    else if (t >= 12) { k1 = 4; k2 = 3; }
+    else if (t >= 10) { k1 = 5; k2 = 2; }
+    else if (t >= 6) { k1 = 3; k2 = 2; }
+    else { k1 = t; k2 = 1; }
+}
+
+}  // namespace
+
+void B200SparseEMMatcher::check(cudaError_t e, const char* what) {
+    if (e != cudaSuccess)
+        throw MatcherError(MBGCG_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+B200SparseEMMatcher::B200SparseEMMatcher(uint64_t refLengthLimit, uint32_t targetMatchLength, int _k1, int _k2,
+                                         int _skipMargin, int dev)
+    : maxRefLength(refLengthLimit), L(static_cast<int>(targetMatchLength)), skipMargin(_skipMargin), device(dev) {
+    int nDev = 0;
+    if (cudaGetDeviceCount(&nDev) != cudaSuccess || nDev == 0)
+        throw MatcherError(MBGCG_E_CUDA, "no CUDA device: the B200 matcher has no CPU fallback");
+    check(cudaSetDevice(device), "cudaSetDevice");
+    if (targetMatchLength < 16)  // MIN_MATCH_LENGTH, .h:23 / .cpp:82-85
+        throw MatcherError(MBGCG_E_PARAM, "Error: Minimal matching length too short!");
+    if (maxRefLength < 2) throw MatcherError(MBGCG_E_PARAM, "reference length limit too small");
+
+    pos1 = static_cast<int64_t>(REF_SHIFT);
+    swEnd = maxRefLength;
+    setSlidingWindowSize(16);  // SW_WIDTH_FACTOR, .h:47
+    K = kmer_from_L(L, targetMatchLength);  // minMatchLength defaults to UINT32_MAX, clamped to L (.cpp:342-344)
+    calc_coprimes(L, K, k1, k2);
+    if (_k1 != -1) k1 = _k1;
+    if (_k2 != -1) k2 = _k2;
+    if (k2 != 1) throw MatcherError(MBGCG_E_UNSUPPORTED, "k2 != 1 is outside the accelerated scope (MBGC always uses k2 = 1)");
+    if (!probe_supports_K(K)) throw MatcherError(MBGCG_E_UNSUPPORTED, "hashed prefix length K not in the reference's hash matrix");
+    uint8_t i = 24;  // HASH_SIZE_MIN_ORDER .. MAX_ORDER, .cpp:99-103
+    do {
+        hashSize = static_cast<uint32_t>(1) << (i++);
+    } while (i <= 31 && hashSize < maxRefLength / static_cast<uint64_t>(k1));
+    if (__builtin_ctz(static_cast<uint32_t>(k1))) {
+        k1ord = __builtin_ctz(static_cast<uint32_t>(k1));
+        if (k1 & (k1 - 1)) throw MatcherError(MBGCG_E_UNSUPPORTED, "even k1 that is not a power of two");
+        samplingPos = static_cast<uint64_t>(k1);  // .cpp:503
+        if ((maxRefLength >> k1ord) >= (1ull << 32))
+            throw MatcherError(MBGCG_E_UNSUPPORTED, "reference needs the 64-bit table (ref .cpp:505-508)");
+    } else {
+        k1ord = -1;
+        samplingPos = REF_SHIFT;
+        if (maxRefLength >= (1ull << 32))
+            throw MatcherError(MBGCG_E_UNSUPPORTED, "reference needs the 64-bit table (ref .cpp:347-350)");
+    }
+
+    hostRef = static_cast<char*>(std::calloc(maxRefLength + PAD, 1));
+    if (!hostRef) throw MatcherError(MBGCG_E_NOMEM, "host mirror allocation failed");
+    check(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate");
+    for (auto& e : ev) check(cudaEventCreate(&e), "cudaEventCreate");
+    check(cudaMalloc(&dRefAlloc, maxRefLength + 2 * PAD), "cudaMalloc(ref)");
+    check(cudaMemsetAsync(dRefAlloc, 0, maxRefLength + 2 * PAD, stream), "memset(ref)");
+    dRef = dRefAlloc + PAD;
+    check(cudaMalloc(&dHt, static_cast<uint64_t>(hashSize) * sizeof(unsigned long long)), "cudaMalloc(table)");
+    check(cudaMemsetAsync(dHt, 0, static_cast<uint64_t>(hashSize) * sizeof(unsigned long long), stream), "memset(table)");
+    check(cudaMalloc(&dOcc, hashSize / 8), "cudaMalloc(occupancy)");
+    check(cudaMemsetAsync(dOcc, 0, hashSize / 8, stream), "memset(occupancy)");
+    check(cudaStreamSynchronize(stream), "init sync");
+}
+
+B200SparseEMMatcher::~B200SparseEMMatcher() {
+    cudaSetDevice(device);
+    if (stream) cudaStreamSynchronize(stream);
+    cudaFree(dRefAlloc);
+    cudaFree(dHt);
+    cudaFree(dOcc);
+    cudaFree(dText);
+    cudaFree(dMeta);
+    cudaFree(dWork);
+    if (hMeta) cudaFreeHost(hMeta);
+    if (hMatches) cudaFreeHost(hMatches);
+    if (hCounts) cudaFreeHost(hCounts);
+    for (auto& e : ev) if (e) cudaEventDestroy(e);
+    if (stream) cudaStreamDestroy(stream);
+    std::free(hostRef);
+}
+
+// ---- index build ---------------------------------------------------------------------------------------
+
+// .cpp:146-171: the chunked (OpenMP) loop and the sequential tail are two independent integer ranges; the
+// kernel gets them with program-order sequence numbers so that "last writer wins" is reproduced exactly.
+void B200SparseEMMatcher::indexPass() {
+    const int64_t chunk = static_cast<int64_t>(k1) * 128;
+    int64_t i1 = static_cast<int64_t>(samplingPos);
+    const int64_t chunkedBegin = i1;
+    if (i1 < (pos1 - K) - chunk) i1 += ((pos1 - K) - chunk - i1 + chunk - 1) / chunk * chunk;
+    InsertRange r0{chunkedBegin, (i1 - chunkedBegin) / k1, insertSeq};
+    int64_t t = k1 + ((pos1 - K - 1) / chunk) * chunk;
+    const int64_t tailBegin = t;
+    if (t < pos1 - K + 1) t += ((pos1 - K + 1) - t + k1 - 1) / k1 * k1;
+    InsertRange r1{tailBegin, (t - tailBegin) / k1, insertSeq + static_cast<uint64_t>(r0.count)};
+    samplingPos = static_cast<uint64_t>(t);
+    const uint64_t n = static_cast<uint64_t>(r0.count + r1.count);
+    if (n == 0) return;
+    if (insertSeq + n >= (1ull << 32))
+        throw MatcherError(MBGCG_E_UNSUPPORTED, "more than 2^32 index samples over the life of one matcher");
+    insertSeq += n;
+    launch_index_insert(dRef, dHt, dOcc, hashSize - 1, K, k1, k1ord, r0, r1, stream);
+    totalLaunches++;
+    check(cudaGetLastError(), "index_insert launch");
+}
+
+// .cpp:402-437 (tail recursion written as a loop)
+void B200SparseEMMatcher::loadSegment(const char* text, uint64_t len, bool rc, bool addSep, char sep) {
+    while (len != 0) {
+        if (static_cast<uint64_t>(pos1) == maxRefLength && swEnd != maxRefLength) {
+            reachedRefLengthCount++;
+            pos1 = static_cast<int64_t>(REF_SHIFT);
+            samplingPos = REF_SHIFT;
+        }
+        const uint64_t tmpEnd = swEnd;
+        uint64_t tmpLen = len;
+        const uint64_t tmpMax = tmpEnd < static_cast<uint64_t>(pos1) ? maxRefLength : tmpEnd;
+        if (static_cast<uint64_t>(pos1) + tmpLen > tmpMax) tmpLen = tmpMax - static_cast<uint64_t>(pos1);
+        char* dst = hostRef + pos1;
+        if (rc) {
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(text) + len - tmpLen;
+            for (uint64_t i = 0; i < tmpLen; i++) dst[tmpLen - 1 - i] = static_cast<char>(g_lut.t[src[i]]);
+        } else
+            std::memcpy(dst, text, tmpLen);
+        const bool sepHit = addSep && static_cast<uint64_t>(pos1) + tmpLen == swEnd;
+        if (sepHit) hostRef[swEnd - 1] = sep;
+        if (tmpLen)
+            check(cudaMemcpyAsync(dRef + pos1, dst, tmpLen, cudaMemcpyHostToDevice, stream), "H2D(ref segment)");
+        else if (sepHit)
+            check(cudaMemcpyAsync(dRef + swEnd - 1, hostRef + swEnd - 1, 1, cudaMemcpyHostToDevice, stream), "H2D(sep)");
+        pos1 += static_cast<int64_t>(tmpLen);
+        indexPass();
+        if (!rc) text += tmpLen;
+        len = (static_cast<uint64_t>(pos1) == tmpEnd) ? 0 : len - tmpLen;
+    }
+}
+
+void B200SparseEMMatcher::loadRef(const char* refText, uint64_t refLength, bool loadRCRef, bool addRegionSeparators,
+                                  char regionSeparator) {
+    check(cudaSetDevice(device), "cudaSetDevice");
+    loadSegment(refText, refLength, false, addRegionSeparators, regionSeparator);
+    if (loadRCRef) loadSegment(refText, refLength, true, addRegionSeparators, regionSeparator);
+    // the caller may free refText right after the call; pageable copies are staged before returning, but
+    // keep the ordering explicit
+    check(cudaStreamSynchronize(stream), "loadRef sync");
+}
+
+void B200SparseEMMatcher::loadSeparator(char regionSeparator) {
+    check(cudaSetDevice(device), "cudaSetDevice");
+    if (static_cast<uint64_t>(pos1) == maxRefLength && swEnd != maxRefLength) {
+        reachedRefLengthCount++;
+        pos1 = static_cast<int64_t>(REF_SHIFT);
+        samplingPos = REF_SHIFT;
+    }
+    if (static_cast<uint64_t>(pos1) == maxRefLength) return;
+    uint64_t at;
+    if (static_cast<uint64_t>(pos1) == swEnd)
+        at = static_cast<uint64_t>(pos1) - 1;
+    else
+        at = static_cast<uint64_t>(pos1++);
+    hostRef[at] = regionSeparator;
+    check(cudaMemcpyAsync(dRef + at, hostRef + at, 1, cudaMemcpyHostToDevice, stream), "H2D(sep)");
+    check(cudaStreamSynchronize(stream), "loadSeparator sync");
+}
+
+// ---- locks: .cpp:361-400 -------------------------------------------------------------------------------
+
+uint64_t B200SparseEMMatcher::acquireWorkerMatchingLockPos() {
+    if (swSize == 0 || !circularBuffer) return swEnd;
+    uint64_t w = static_cast<uint64_t>(pos1) + swSize;
+    if (reachedRefLengthCount || w > maxRefLength) {
+        if (w > maxRefLength) w -= maxRefLength - REF_SHIFT;
+    } else
+        w = maxRefLength;
+    if (workersSwEndPositions.empty()) swEnd = w;
+    workersSwEndPositions.push_back(w);
+    return w;
+}
+
+void B200SparseEMMatcher::releaseWorkerMatchingLockPos(uint64_t lockValue) {
+    if (swSize == 0 || !circularBuffer) return;
+    size_t i = 0;
+    while (i < workersSwEndPositions.size() && workersSwEndPositions[i] != lockValue) i++;
+    if (i == workersSwEndPositions.size())
+        throw MatcherError(MBGCG_E_LOCK, "ERROR: Invalid worker lock value (" + std::to_string(lockValue) + ")");
+    if (i == 0) {
+        do {
+            workersSwEndPositions.pop_front();
+        } while (!workersSwEndPositions.empty() && workersSwEndPositions.front() == SW_END_ERASED_FLAG);
+        swEnd = workersSwEndPositions.empty() ? swEnd : workersSwEndPositions.front();
+    } else
+        workersSwEndPositions[i] = SW_END_ERASED_FLAG;
+}
+
+// ---- matching ------------------------------------------------------------------------------------------
+
+void B200SparseEMMatcher::matchTexts(std::vector<TextMatch>& resMatches, const char* destText, uint64_t destLen,
+                                     bool destIsRef, bool revComplMatching, uint32_t minMatchLength,
+                                     uint64_t matchingLockPos) {
+    if (minMatchLength < static_cast<uint32_t>(K))  // .cpp:480-483
+        throw MatcherError(MBGCG_E_PARAM, "Minimal matching length cannot be smaller than K (" +
+                                              std::to_string(minMatchLength) + " < " + std::to_string(K) + ")");
+    if (destIsRef || revComplMatching)  // .cpp:185-188
+        throw MatcherError(MBGCG_E_PARAM, "Source as destination and reverse-complement matching modes unsupported");
+    std::vector<TextView> one{{destText, destLen}};
+    matchBatch(one, &matchingLockPos, minMatchLength, false, nullptr, nullptr);
+    resMatches = resAll;
+}
+
+void B200SparseEMMatcher::ensureWork(uint64_t textBytes, uint32_t nTiles, int nContigs, uint32_t seedCap) {
+    if (textBytes > dTextCap) {
+        cudaFree(dText);
+        dText = nullptr;
+        dTextCap = 0;
+        const uint64_t cap = align_up(textBytes + textBytes / 4, 1 << 20);
+        check(cudaMalloc(&dText, cap), "cudaMalloc(text)");
+        dTextCap = cap;
+    }
+    // meta: contigOff u64, contigLock u64, contigLen u32, tileStart u32 (+1)
+    const uint64_t metaBytes = align_up(static_cast<uint64_t>(nContigs + 1) * 24 + 64, 256);
+    if (metaBytes > dMetaCap) {
+        cudaFree(dMeta);
+        if (hMeta) cudaFreeHost(hMeta);
+        dMeta = nullptr; hMeta = nullptr; dMetaCap = 0;
+        const uint64_t cap = metaBytes * 2;
+        check(cudaMalloc(&dMeta, cap), "cudaMalloc(meta)");
+        check(cudaHostAlloc(&hMeta, cap, cudaHostAllocDefault), "cudaHostAlloc(meta)");
+        dMetaCap = hMetaCap = cap;
+    }
+    const uint64_t countsBytes = align_up(static_cast<uint64_t>(nContigs + 1) * 4 + 64, 256);
+    if (countsBytes > hCountsCap) {
+        if (hCounts) cudaFreeHost(hCounts);
+        hCounts = nullptr;
+        check(cudaHostAlloc(&hCounts, countsBytes * 2, cudaHostAllocDefault), "cudaHostAlloc(counts)");
+        hCountsCap = countsBytes * 2;
+    }
+    // work buffers, carved from one allocation
+    uint64_t off = 0;
+    auto carve = [&](uint64_t bytes) { const uint64_t o = off; off = align_up(off + bytes, 256); return o; };
+    const uint64_t scratchN = static_cast<uint64_t>(nTiles) * PROBE_TILE;
+    const uint64_t oTileCount = carve((static_cast<uint64_t>(nTiles) + 2) * 4);
+    const uint64_t oScratchPos = carve(scratchN * 4);
+    const uint64_t oScratchEnc = carve(scratchN * 4);
+    const uint64_t oSeedPos = carve(static_cast<uint64_t>(seedCap) * 4);
+    const uint64_t oSeedEnc = carve(static_cast<uint64_t>(seedCap) * 4);
+    const uint64_t oHeadScan = carve((static_cast<uint64_t>(seedCap) + 2) * 4);
+    const uint64_t oRunFirst = carve((static_cast<uint64_t>(seedCap) + 2) * 4);
+    const uint64_t oRuns = carve(static_cast<uint64_t>(seedCap) * sizeof(RunRec));
+    const uint64_t oRunStart = carve((static_cast<uint64_t>(nContigs) + 2) * 4);
+    const uint64_t oMatches = carve(static_cast<uint64_t>(seedCap) * sizeof(MatchRec));
+    const uint64_t oMatchCount = carve((static_cast<uint64_t>(nContigs) + 2) * 4);
+    const uint64_t oMatchOff = carve((static_cast<uint64_t>(nContigs) + 2) * 4);
+    const uint64_t oDense = carve(static_cast<uint64_t>(seedCap) * sizeof(MatchRec));
+    const uint64_t nScan = std::max<uint64_t>(nTiles, seedCap);
+    const uint64_t oBlockSums = carve((nScan / 4096 + 8) * 4);
+    const uint64_t oCounters = carve(64);
+    if (off > dWorkCap) {
+        cudaFree(dWork);
+        dWork = nullptr;
+        dWorkCap = 0;
+        const uint64_t cap = align_up(off + off / 8, 1 << 20);
+        check(cudaMalloc(&dWork, cap), "cudaMalloc(work)");
+        dWorkCap = cap;
+    }
+    wb.tileCount = reinterpret_cast<uint32_t*>(dWork + oTileCount);
+    wb.scratchPos = reinterpret_cast<uint32_t*>(dWork + oScratchPos);
+    wb.scratchEnc = reinterpret_cast<uint32_t*>(dWork + oScratchEnc);
+    wb.seedPos = reinterpret_cast<uint32_t*>(dWork + oSeedPos);
+    wb.seedEnc = reinterpret_cast<uint32_t*>(dWork + oSeedEnc);
+    wb.headScan = reinterpret_cast<uint32_t*>(dWork + oHeadScan);
+    wb.runFirst = reinterpret_cast<uint32_t*>(dWork + oRunFirst);
+    wb.runs = reinterpret_cast<RunRec*>(dWork + oRuns);
+    wb.runStart = reinterpret_cast<uint32_t*>(dWork + oRunStart);
+    wb.matches = reinterpret_cast<MatchRec*>(dWork + oMatches);
+    wb.matchCount = reinterpret_cast<uint32_t*>(dWork + oMatchCount);
+    wb.matchOff = reinterpret_cast<uint32_t*>(dWork + oMatchOff);
+    wb.matchesDense = reinterpret_cast<MatchRec*>(dWork + oDense);
+    wb.blockSums = reinterpret_cast<uint32_t*>(dWork + oBlockSums);
+    wb.counters = reinterpret_cast<uint32_t*>(dWork + oCounters);
+    wb.seedCap = seedCap;
+}
+
+void B200SparseEMMatcher::matchBatch(const std::vector<TextView>& texts, const uint64_t* lockPos, uint32_t minMatchLength,
+                                     bool textsOnDevice, const void* dTextBase, const uint64_t* dOffsets) {
+    check(cudaSetDevice(device), "cudaSetDevice");
+    if (minMatchLength < static_cast<uint32_t>(K))
+        throw MatcherError(MBGCG_E_PARAM, "Minimal matching length cannot be smaller than K (" +
+                                              std::to_string(minMatchLength) + " < " + std::to_string(K) + ")");
+    resAll.clear();
+    resCounts.assign(texts.size(), 0);
+    for (auto& m : stageMs) m = 0;
+    for (auto& c : lastCounters) c = 0;
+    if (texts.empty()) return;
+    for (const auto& t : texts)
+        if (t.len >= (1ull << 32)) throw MatcherError(MBGCG_E_UNSUPPORTED, "target text of 4 GiB or more");
+
+    // split into passes of bounded size (work memory is ~26 bytes per target position)
+    static const uint64_t maxPassBytes = [] {
+        const char* e = std::getenv("MBGC_B200_MAX_PASS_BYTES");
+        return e ? std::strtoull(e, nullptr, 10) : (256ull << 20);
+    }();
+    size_t first = 0;
+    while (first < texts.size()) {
+        size_t last = first;
+        uint64_t bytes = 0;
+        while (last < texts.size() && (last == first || bytes + texts[last].len <= maxPassBytes)) bytes += texts[last++].len;
+        const int nC = static_cast<int>(last - first);
+
+        // layout + tiles
+        std::vector<uint64_t> off(nC);
+        std::vector<uint32_t> tileStart(nC + 1);
+        uint64_t cursor = PAD, positions = 0;
+        uint32_t tiles = 0;
+        for (int c = 0; c < nC; c++) {
+            const uint64_t len = texts[first + c].len;
+            off[c] = textsOnDevice ? dOffsets[first + c] : cursor;
+            cursor = align_up(cursor + len + TEXT_GAP, 16);
+            tileStart[c] = tiles;
+            const uint64_t nValid = len >= static_cast<uint64_t>(K) ? len - K + 1 : 0;
+            tiles += static_cast<uint32_t>((nValid + PROBE_TILE - 1) / PROBE_TILE);
+            positions += nValid;
+        }
+        tileStart[nC] = tiles;
+        const uint64_t textBytes = cursor + TEXT_TAIL;
+
+        uint32_t seedCap = static_cast<uint32_t>(std::min<uint64_t>(positions / 4 + 65536, 0xFFFFFFF0ull));
+        for (int attempt = 0;; attempt++) {
+            ensureWork(textsOnDevice ? 0 : textBytes, tiles, nC, seedCap);
+            // meta -> device
+            uint64_t* hOff = reinterpret_cast<uint64_t*>(hMeta);
+            uint64_t* hLock = hOff + nC;
+            uint32_t* hLen = reinterpret_cast<uint32_t*>(hLock + nC);
+            uint32_t* hTile = hLen + nC;
+            for (int c = 0; c < nC; c++) {
+                hOff[c] = off[c];
+                hLock[c] = lockPos ? lockPos[first + c] : NO_LOCK;
+                hLen[c] = static_cast<uint32_t>(texts[first + c].len);
+                hTile[c] = tileStart[c];
+            }
+            hTile[nC] = tileStart[nC];
+            const uint64_t metaUsed = static_cast<uint64_t>(nC) * 24 + 4;
+            check(cudaEventRecord(ev[0], stream), "event");
+            check(cudaMemcpyAsync(dMeta, hMeta, metaUsed, cudaMemcpyHostToDevice, stream), "H2D(meta)");
+            const uint8_t* textBase;
+            if (textsOnDevice) {
+                textBase = static_cast<const uint8_t*>(dTextBase);
+            } else {
+                for (int c = 0; c < nC; c++)
+                    if (texts[first + c].len)
+                        check(cudaMemcpyAsync(dText + off[c], texts[first + c].data, texts[first + c].len,
+                                              cudaMemcpyHostToDevice, stream), "H2D(text)");
+                textBase = dText;
+            }
+            check(cudaMemsetAsync(wb.counters, 0, 32, stream), "memset(counters)");
+            check(cudaEventRecord(ev[1], stream), "event");
+
+            BatchDesc bd;
+            bd.text = textBase;
+            bd.contigOff = reinterpret_cast<const uint64_t*>(dMeta);
+            bd.contigLock = bd.contigOff + nC;
+            bd.contigLen = reinterpret_cast<const uint32_t*>(bd.contigLock + nC);
+            bd.tileStart = bd.contigLen + nC;
+            bd.nContigs = nC;
+            bd.nTiles = tiles;
+            IndexState ix;
+            ix.ref = dRef;
+            ix.ht = dHt;
+            ix.occ = dOcc;
+            ix.hashMask = hashSize - 1;
+            ix.K = K;
+            ix.k1 = k1;
+            ix.k1ord = k1ord;
+            ix.skipMargin = skipMargin;
+            ix.pos1 = static_cast<uint64_t>(pos1);
+            ix.refLen = getRefLength();
+
+            int launches = 0;
+            launches += launch_probe(ix, bd, wb, stream);
+            check(cudaEventRecord(ev[2], stream), "event");
+            launches += launch_compact_and_runs(ix, bd, wb, stream);
+            check(cudaEventRecord(ev[3], stream), "event");
+            launches += launch_extend(ix, bd, wb, stream);
+            check(cudaEventRecord(ev[4], stream), "event");
+            launches += launch_resolve(ix, bd, wb, minMatchLength, stream);
+            check(cudaEventRecord(ev[5], stream), "event");
+            check(cudaGetLastError(), "match pass launch");
+            totalLaunches += static_cast<uint64_t>(launches);
+            lastCounters[4] += static_cast<uint64_t>(launches);
+
+            // counts first, then exactly the matches
+            uint32_t* hOffs = hCounts;            // [nC+1]
+            uint32_t* hCtr = hCounts + nC + 1;    // [8]
+            check(cudaMemcpyAsync(hOffs, wb.matchOff, (static_cast<uint64_t>(nC) + 1) * 4, cudaMemcpyDeviceToHost, stream), "D2H(counts)");
+            check(cudaMemcpyAsync(hCtr, wb.counters, 32, cudaMemcpyDeviceToHost, stream), "D2H(counters)");
+            check(cudaStreamSynchronize(stream), "match pass sync");
+            if (hCtr[3]) {  // seed capacity exceeded: rerun this pass with the worst-case capacity
+                if (attempt > 0) throw MatcherError(MBGCG_E_NOMEM, "seed buffer overflow after retry");
+                seedCap = static_cast<uint32_t>(std::min<uint64_t>(positions + 65536, 0xFFFFFFF0ull));
+                continue;
+            }
+            const uint32_t total = hOffs[nC];
+            if (total > hMatchesCap) {
+                if (hMatches) cudaFreeHost(hMatches);
+                hMatches = nullptr;
+                hMatchesCap = 0;
+                const uint64_t cap = static_cast<uint64_t>(total) + total / 2 + 4096;
+                check(cudaHostAlloc(&hMatches, cap * sizeof(MatchRec), cudaHostAllocDefault), "cudaHostAlloc(matches)");
+                hMatchesCap = cap;
+            }
+            if (total)
+                check(cudaMemcpyAsync(hMatches, wb.matchesDense, static_cast<uint64_t>(total) * sizeof(MatchRec),
+                                      cudaMemcpyDeviceToHost, stream), "D2H(matches)");
+            check(cudaEventRecord(ev[6], stream), "event");
+            check(cudaStreamSynchronize(stream), "D2H sync");
+
+            const size_t base = resAll.size();
+            resAll.resize(base + total);
+            for (uint32_t k = 0; k < total; k++) {
+                TextMatch& m = resAll[base + k];
+                m.posSrcText = hMatches[k].src;
+                m.length = hMatches[k].len;
+                m.posDestText = hMatches[k].dst;
+                m.nextSrcRegionLoadingPos = 0;
+            }
+            for (int c = 0; c < nC; c++) resCounts[first + c] = hOffs[c + 1] - hOffs[c];
+            float ms;
+            for (int s = 0; s < 6; s++) {
+                check(cudaEventElapsedTime(&ms, ev[s], ev[s + 1]), "event time");
+                stageMs[s] += ms;
+            }
+            check(cudaEventElapsedTime(&ms, ev[0], ev[6]), "event time");
+            stageMs[MBGCG_T_TOTAL] += ms;
+            lastCounters[0] += positions;
+            lastCounters[1] += hCtr[0];
+            lastCounters[2] += hCtr[1];
+            lastCounters[3] += total;
+            lastCounters[5] += 1;  // passes
+            break;
+        }
+        first = last;
+    }
+}
+
+void B200SparseEMMatcher::copyTableLow32(uint32_t* out, uint64_t nSlots) {
+    check(cudaSetDevice(device), "cudaSetDevice");
+    if (nSlots > hashSize) nSlots = hashSize;
+    uint32_t* d = nullptr;
+    check(cudaMalloc(&d, nSlots * 4), "cudaMalloc(table copy)");
+    launch_table_low32(dHt, d, nSlots, stream);
+    totalLaunches++;
+    cudaError_t e = cudaMemcpyAsync(out, d, nSlots * 4, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    cudaFree(d);
+    check(e, "table copy");
+}
+
+void B200SparseEMMatcher::copyDeviceRef(uint64_t from, uint64_t n, char* out) {
+    check(cudaSetDevice(device), "cudaSetDevice");
+    check(cudaMemcpyAsync(out, dRef + from, n, cudaMemcpyDeviceToHost, stream), "D2H(ref)");
+    check(cudaStreamSynchronize(stream), "ref copy sync");
+}
+
+}  // namespace mbgc_b200

@@ -1,0 +1,128 @@
+// mbgc_b200/csrc/matcher.hpp -- host side of the B200 match finder.
+//
+// B200SparseEMMatcher mirrors the public surface of the reference class SlidingWindowSparseEMMatcher
+// (/root/reference/matching/SlidingWindowSparseEMMatcher.h:86-126; same method names, argument meaning and
+// error behaviour -- errors are thrown as MatcherError instead of exit(EXIT_FAILURE)).  The bookkeeping
+// the reference does on the host (circular buffer, sliding window, worker locks, which positions an index
+// pass samples) stays on the host and is restated here; all per-base work runs in the CUDA kernels of
+// kernels.cu.  There is no CPU implementation of the matching itself in this class.
+#pragma once
+#include <cstdint>
+#include <deque>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+
+namespace mbgc_b200 {
+
+struct MatcherError : public std::runtime_error {
+    int code;
+    MatcherError(int c, const std::string& what) : std::runtime_error(what), code(c) {}
+};
+
+struct TextMatch {  // = PgTools::TextMatch, matching/TextMatchers.h:9-17
+    uint64_t posSrcText, length, posDestText, nextSrcRegionLoadingPos;
+};
+
+struct TextView {   // one target text (contig / block) of a batch
+    const char* data;
+    uint64_t len;
+};
+
+class B200SparseEMMatcher {
+public:
+    static constexpr uint64_t REF_SHIFT = 1;                     // ref .h:14
+    static constexpr uint64_t SW_END_ERASED_FLAG = UINT64_MAX;   // ref .h:46
+
+    // ref .cpp:325-359 / 494-519; Exp variant iff ctz(k1) != 0 (MultipleGenomeMatchingProcessor.cpp:170-176)
+    B200SparseEMMatcher(uint64_t refLengthLimit, uint32_t targetMatchLength, int k1, int k2, int skipMargin, int device);
+    ~B200SparseEMMatcher();
+    B200SparseEMMatcher(const B200SparseEMMatcher&) = delete;
+    B200SparseEMMatcher& operator=(const B200SparseEMMatcher&) = delete;
+
+    // ref .h:93-97
+    void disableSlidingWindow() { swSize = 0; swEnd = circularBuffer ? 0 : maxRefLength; }
+    void disableCircularBuffer() { circularBuffer = false; swEnd = maxRefLength; }
+    void setSlidingWindowSize(uint8_t factor) { swSize = maxRefLength / factor; }
+
+    // ref .cpp:453-458
+    void loadRef(const char* refText, uint64_t refLength, bool loadRCRef, bool addRegionSeparators, char regionSeparator);
+    // ref .cpp:439-451
+    void loadSeparator(char regionSeparator);
+
+    // ref .h:104-113
+    const char* getRef() const { return hostRef; }
+    uint64_t getMaxRefLength() const { return maxRefLength; }
+    uint64_t getRefLength() const { return reachedRefLengthCount ? maxRefLength : static_cast<uint64_t>(pos1); }
+    uint64_t getLoadingPosition() const { return static_cast<uint64_t>(pos1); }
+    uint64_t getLoadedRefLength() const {
+        return static_cast<uint64_t>(reachedRefLengthCount) * (maxRefLength - REF_SHIFT) + (static_cast<uint64_t>(pos1) - REF_SHIFT);
+    }
+    void setPosition(uint64_t refPos, int reached) { pos1 = static_cast<int64_t>(refPos); reachedRefLengthCount = reached; }
+
+    // ref .cpp:361-400
+    uint64_t acquireWorkerMatchingLockPos();
+    void releaseWorkerMatchingLockPos(uint64_t lockValue);
+
+    // ref .cpp:477-492: one text
+    void matchTexts(std::vector<TextMatch>& resMatches, const char* destText, uint64_t destLen, bool destIsRef,
+                    bool revComplMatching, uint32_t minMatchLength, uint64_t matchingLockPos = SW_END_ERASED_FLAG);
+
+    // n texts against the same frozen state in one device pass; results concatenated in text order
+    void matchBatch(const std::vector<TextView>& texts, const uint64_t* lockPos, uint32_t minMatchLength,
+                    bool textsOnDevice, const void* dTextBase, const uint64_t* dOffsets);
+    const std::vector<TextMatch>& batchMatches() const { return resAll; }
+    const std::vector<uint64_t>& batchCounts() const { return resCounts; }
+
+    // inspection
+    void copyTableLow32(uint32_t* out, uint64_t nSlots);
+    void copyDeviceRef(uint64_t from, uint64_t n, char* out);
+    void* streamHandle() const { return stream; }
+
+    // state (public like the C struct it is mirrored into)
+    int64_t pos1 = 1;
+    uint64_t maxRefLength = 0;
+    int reachedRefLengthCount = 0;
+    bool circularBuffer = true;
+    uint64_t swSize = 0, swEnd = 0;
+    uint64_t samplingPos = 1;
+    uint32_t hashSize = 0;
+    int L = 0, K = 0, k1 = 0, k2 = 0, skipMargin = 0, k1ord = -1;
+
+    float stageMs[8] = {0};
+    uint64_t lastCounters[8] = {0};
+    uint64_t totalLaunches = 0;
+
+private:
+    void loadSegment(const char* text, uint64_t len, bool rc, bool addSep, char sep);
+    void indexPass();
+    void ensureWork(uint64_t textBytes, uint32_t nTiles, int nContigs, uint32_t seedCap);
+    void check(cudaError_t e, const char* what);
+
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[8] = {};
+    char* hostRef = nullptr;             // host mirror (getRef())
+    uint8_t* dRefAlloc = nullptr;        // device reference buffer with padding
+    uint8_t* dRef = nullptr;             // = dRefAlloc + PAD
+    unsigned long long* dHt = nullptr;
+    uint32_t* dOcc = nullptr;
+    uint64_t insertSeq = 1;              // program-order sequence number of the next index sample
+    std::deque<uint64_t> workersSwEndPositions;
+
+    // per-pass device buffers (grown on demand)
+    uint8_t* dText = nullptr; uint64_t dTextCap = 0;
+    uint8_t* dMeta = nullptr; uint64_t dMetaCap = 0;
+    uint8_t* hMeta = nullptr; uint64_t hMetaCap = 0;   // pinned
+    uint8_t* dWork = nullptr; uint64_t dWorkCap = 0;
+    WorkBuffers wb{};
+    uint32_t wbTiles = 0; int wbContigs = 0;
+    MatchRec* hMatches = nullptr; uint64_t hMatchesCap = 0;  // pinned
+    uint32_t* hCounts = nullptr; uint64_t hCountsCap = 0;    // pinned
+    std::vector<TextMatch> resAll;
+    std::vector<uint64_t> resCounts;
+};
+
+}  // namespace mbgc_b200

@@ -1,0 +1,247 @@
+"""ctypes binding of libmbgc_b200.so (include/mbgc_b200.h) with the reference's method names.
+
+Reference interface mirrored: /root/reference/matching/SlidingWindowSparseEMMatcher.h:86-126
+(loadRef, loadSeparator, matchTexts, acquire/releaseWorkerMatchingLockPos, getRef, getRefLength, ...).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+NO_LOCK = 2**64 - 1  # SW_END_ERASED_FLAG
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+u8p = C.POINTER(C.c_uint8)
+u64p = C.POINTER(C.c_uint64)
+
+T_NAMES = ("h2d", "probe", "compact", "extend", "resolve", "d2h", "total")
+
+
+class MatcherError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"mbgc_b200 error {code}: {msg}")
+        self.code = code
+
+
+class _State(C.Structure):
+    _fields_ = [("pos1", C.c_int64), ("maxRefLength", C.c_uint64), ("reachedRefLengthCount", C.c_int32),
+                ("circularBuffer", C.c_int32), ("swSize", C.c_uint64), ("swEnd", C.c_uint64),
+                ("samplingPos", C.c_uint64), ("hashSize", C.c_uint32), ("K", C.c_int32)]
+
+
+def lib_path():
+    return os.path.join(_HERE, "libmbgc_b200.so")
+
+
+def load_library():
+    """Loads libmbgc_b200.so.  Raises if it has not been built: the matcher has no other implementation."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        raise MatcherError(-1, f"{path} is missing -- build it with `python -m mbgc_b200.build` "
+                               "(there is no CPU fallback for the matcher)")
+    L = C.CDLL(path)
+    vp = C.c_void_p
+    L.mbgcg_create.restype = C.c_int
+    L.mbgcg_create.argtypes = [C.POINTER(vp), C.c_uint64, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.mbgcg_destroy.argtypes = [vp]
+    L.mbgcg_last_error.restype = C.c_char_p
+    L.mbgcg_last_error.argtypes = [vp]
+    L.mbgcg_create_error.restype = C.c_char_p
+    L.mbgcg_disable_sliding_window.argtypes = [vp]
+    L.mbgcg_disable_circular_buffer.argtypes = [vp]
+    L.mbgcg_set_sliding_window_size.argtypes = [vp, C.c_int]
+    L.mbgcg_load_ref.restype = C.c_int
+    L.mbgcg_load_ref.argtypes = [vp, vp, C.c_uint64, C.c_int, C.c_int, C.c_char]
+    L.mbgcg_load_separator.restype = C.c_int
+    L.mbgcg_load_separator.argtypes = [vp, C.c_char]
+    L.mbgcg_match.restype = C.c_int
+    L.mbgcg_match.argtypes = [vp, vp, C.c_uint64, C.c_uint32, C.c_uint64, C.POINTER(vp), u64p]
+    L.mbgcg_match_batch.restype = C.c_int
+    L.mbgcg_match_batch.argtypes = [vp, C.c_int, C.POINTER(vp), u64p, C.c_uint32, u64p, C.POINTER(vp), C.POINTER(vp)]
+    L.mbgcg_match_batch_device.restype = C.c_int
+    L.mbgcg_match_batch_device.argtypes = [vp, vp, C.c_int, u64p, u64p, C.c_uint32, u64p, C.POINTER(vp), C.POINTER(vp)]
+    L.mbgcg_acquire_lock.restype = C.c_uint64
+    L.mbgcg_acquire_lock.argtypes = [vp]
+    L.mbgcg_release_lock.restype = C.c_int
+    L.mbgcg_release_lock.argtypes = [vp, C.c_uint64]
+    L.mbgcg_host_ref.restype = vp
+    L.mbgcg_host_ref.argtypes = [vp]
+    for f in ("mbgcg_max_ref_length", "mbgcg_ref_length", "mbgcg_loading_position", "mbgcg_loaded_ref_length",
+              "mbgcg_total_launches"):
+        getattr(L, f).restype = C.c_uint64
+        getattr(L, f).argtypes = [vp]
+    L.mbgcg_set_position.argtypes = [vp, C.c_uint64, C.c_int]
+    L.mbgcg_get_state.argtypes = [vp, C.POINTER(_State)]
+    L.mbgcg_set_state.argtypes = [vp, C.POINTER(_State)]
+    L.mbgcg_copy_table.restype = C.c_int
+    L.mbgcg_copy_table.argtypes = [vp, vp, C.c_uint64]
+    L.mbgcg_copy_device_ref.restype = C.c_int
+    L.mbgcg_copy_device_ref.argtypes = [vp, C.c_uint64, C.c_uint64, vp]
+    L.mbgcg_last_timing.argtypes = [vp, C.POINTER(C.c_float)]
+    L.mbgcg_last_counters.argtypes = [vp, u64p]
+    L.mbgcg_stream.restype = vp
+    L.mbgcg_stream.argtypes = [vp]
+    _LIB = L
+    return L
+
+
+def _as_u8(buf):
+    if isinstance(buf, np.ndarray):
+        return np.ascontiguousarray(buf, dtype=np.uint8)
+    return np.frombuffer(bytes(buf), dtype=np.uint8)
+
+
+class Matcher:
+    """SlidingWindowSparseEMMatcher on a B200.  Match lists come back as uint64 arrays of shape (n, 3) with
+    columns (posSrcText, length, posDestText) -- the TextMatch fields of matching/TextMatchers.h:9-17."""
+
+    def __init__(self, ref_length_limit, L=32, k1=16, k2=1, skip_margin=16, device=0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.mbgcg_create(C.byref(h), ref_length_limit, L, k1, k2, skip_margin, device)
+        if rc != 0:
+            raise MatcherError(rc, self.lib.mbgcg_create_error().decode())
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mbgcg_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def _check(self, rc):
+        if rc != 0:
+            raise MatcherError(rc, self.lib.mbgcg_last_error(self.h).decode())
+
+    # -- reference-named methods -------------------------------------------------------------------
+    def disableSlidingWindow(self):
+        self.lib.mbgcg_disable_sliding_window(self.h)
+
+    def disableCircularBuffer(self):
+        self.lib.mbgcg_disable_circular_buffer(self.h)
+
+    def setSlidingWindowSize(self, factor):
+        self.lib.mbgcg_set_sliding_window_size(self.h, factor)
+
+    def loadRef(self, refText, loadRCRef=False, addRegionSeparators=True, regionSeparator=0):
+        a = _as_u8(refText)
+        self._check(self.lib.mbgcg_load_ref(self.h, a.ctypes.data, a.size, int(loadRCRef), int(addRegionSeparators),
+                                            bytes([regionSeparator])))
+
+    def loadSeparator(self, regionSeparator=0):
+        self._check(self.lib.mbgcg_load_separator(self.h, bytes([regionSeparator])))
+
+    def matchTexts(self, destText, minMatchLength=32, matchingLockPos=NO_LOCK):
+        a = _as_u8(destText)
+        out = C.c_void_p()
+        n = C.c_uint64()
+        self._check(self.lib.mbgcg_match(self.h, a.ctypes.data, a.size, minMatchLength, matchingLockPos,
+                                         C.byref(out), C.byref(n)))
+        return self._matches(out, n.value)
+
+    def matchBatch(self, texts, minMatchLength=32, lockPos=None):
+        """list of texts -> list of (n_i, 3) arrays, all matched against the same frozen state."""
+        arrs = [_as_u8(t) for t in texts]
+        n = len(arrs)
+        ptrs = (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
+        lens = (C.c_uint64 * n)(*[a.size for a in arrs])
+        locks = (C.c_uint64 * n)(*lockPos) if lockPos is not None else None
+        out, counts = C.c_void_p(), C.c_void_p()
+        self._check(self.lib.mbgcg_match_batch(self.h, n, ptrs, lens, minMatchLength, locks, C.byref(out),
+                                               C.byref(counts)))
+        return self._split(out, counts, n)
+
+    def matchBatchDevice(self, dTextPtr, offsets, lens, minMatchLength=32, lockPos=None):
+        """texts already resident in device memory (see mbgcg_match_batch_device for the layout rules)."""
+        n = len(lens)
+        offs = (C.c_uint64 * n)(*offsets)
+        ls = (C.c_uint64 * n)(*lens)
+        locks = (C.c_uint64 * n)(*lockPos) if lockPos is not None else None
+        out, counts = C.c_void_p(), C.c_void_p()
+        self._check(self.lib.mbgcg_match_batch_device(self.h, dTextPtr, n, offs, ls, minMatchLength, locks,
+                                                      C.byref(out), C.byref(counts)))
+        return self._split(out, counts, n)
+
+    def acquireWorkerMatchingLockPos(self):
+        return self.lib.mbgcg_acquire_lock(self.h)
+
+    def releaseWorkerMatchingLockPos(self, lockValue):
+        self._check(self.lib.mbgcg_release_lock(self.h, lockValue))
+
+    def getRef(self, n=None):
+        n = self.getMaxRefLength() if n is None else n
+        return np.ctypeslib.as_array(C.cast(self.lib.mbgcg_host_ref(self.h), u8p), shape=(n,))
+
+    def getMaxRefLength(self):
+        return self.lib.mbgcg_max_ref_length(self.h)
+
+    def getRefLength(self):
+        return self.lib.mbgcg_ref_length(self.h)
+
+    def getLoadingPosition(self):
+        return self.lib.mbgcg_loading_position(self.h)
+
+    def getLoadedRefLength(self):
+        return self.lib.mbgcg_loaded_ref_length(self.h)
+
+    def setPosition(self, refPos, reachedRefLengthCount):
+        self.lib.mbgcg_set_position(self.h, refPos, reachedRefLengthCount)
+
+    # -- inspection ----------------------------------------------------------------------------------
+    def state(self):
+        s = _State()
+        self.lib.mbgcg_get_state(self.h, C.byref(s))
+        return {n: getattr(s, n) for n, _ in _State._fields_}
+
+    def table(self):
+        n = self.state()["hashSize"]
+        out = np.empty(n, dtype=np.uint32)
+        self._check(self.lib.mbgcg_copy_table(self.h, out.ctypes.data, n))
+        return out
+
+    def deviceRef(self, start, n):
+        out = np.empty(n, dtype=np.uint8)
+        self._check(self.lib.mbgcg_copy_device_ref(self.h, start, n, out.ctypes.data))
+        return out
+
+    def timing(self):
+        ms = (C.c_float * 8)()
+        self.lib.mbgcg_last_timing(self.h, ms)
+        return {name: ms[i] for i, name in enumerate(T_NAMES)}
+
+    def counters(self):
+        c = (C.c_uint64 * 8)()
+        self.lib.mbgcg_last_counters(self.h, c)
+        return {"positions": c[0], "seeds": c[1], "runs": c[2], "matches": c[3], "launches": c[4],
+                "passes": c[5]}
+
+    def stream(self):
+        """cudaStream_t (as int) all work of this matcher is issued on"""
+        return self.lib.mbgcg_stream(self.h)
+
+    def totalLaunches(self):
+        return self.lib.mbgcg_total_launches(self.h)
+
+    # -- helpers -------------------------------------------------------------------------------------
+    @staticmethod
+    def _matches(out, n):
+        if n == 0:
+            return np.zeros((0, 3), dtype=np.uint64)
+        a = np.ctypeslib.as_array(C.cast(out, u64p), shape=(n, 4))
+        return a[:, :3].copy()
+
+    def _split(self, out, counts, n):
+        cnt = np.ctypeslib.as_array(C.cast(counts, u64p), shape=(n,)).copy() if n else np.zeros(0, np.uint64)
+        allm = self._matches(out, int(cnt.sum()))
+        res, o = [], 0
+        for c in cnt:
+            res.append(allm[o:o + int(c)])
+            o += int(c)
+        return res

@@ -90,6 +90,23 @@ void refm_get_matches(void* hv, uint64_t* out3) {
     }
 }
 
+// n independent matchTexts calls against the frozen matcher state on `threads` OpenMP threads -- what the
+// reference's parallel workers do between two reference extensions (MultipleGenomeMatchingProcessor.cpp:379).
+// Used as the all-cores CPU baseline of the match stage.  Returns the total number of matches.
+uint64_t refm_match_many(void* hv, int n, const char* const* texts, const uint64_t* lens, uint32_t minMatchLength,
+                         int threads, uint64_t* countsOut) {
+    Handle* h = (Handle*) hv;
+    uint64_t total = 0;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads) reduction(+ : total)
+    for (int i = 0; i < n; i++) {
+        std::vector<PgTools::TextMatch> res;
+        h->m->matchTexts(res, texts[i], lens[i], false, false, minMatchLength);
+        if (countsOut) countsOut[i] = res.size();
+        total += res.size();
+    }
+    return total;
+}
+
 const char* refm_ref(void* hv) { return ((Handle*) hv)->m->getRef(); }
 uint64_t refm_ref_length(void* hv) { return ((Handle*) hv)->m->getRefLength(); }
 uint64_t refm_loading_position(void* hv) { return ((Handle*) hv)->m->getLoadingPosition(); }

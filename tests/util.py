@@ -5,9 +5,13 @@ import ctypes as C
 import os
 import subprocess
 
+import sys
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 REF_DIR = os.path.join(ORACLE_DIR, "_ref")
 FIXTURES = os.path.join(REF_DIR, "fixtures")
@@ -339,56 +343,4 @@ def write_fasta(path, records, width=80):
                 f.write(seq[i:i + width] + b"\n")
 
 
-_ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
-
-
-def synth_base(length, seed):
-    rng = np.random.default_rng(seed)
-    return _ACGT[rng.integers(0, 4, length)]
-
-
-def synth_mutant(base, seed, p_snp, p_indel):
-    """SNPs ~Binomial(L,p_snp) at uniform positions (uniform different base); alternating
-    deletions/insertions of length U[1,19] at Binomial(L,p_indel) sites."""
-    rng = np.random.default_rng(seed)
-    L = base.size
-    g = base.copy()
-    ns = rng.binomial(L, p_snp)
-    if ns:
-        pos = rng.integers(0, L, ns)
-        code = np.searchsorted(_ACGT, g[pos])  # A,C,G,T sorted ascending in ASCII
-        g[pos] = _ACGT[(code + rng.integers(1, 4, ns)) % 4]
-    ni = rng.binomial(L, p_indel)
-    if ni:
-        sites = np.sort(rng.integers(0, L, ni))
-        lens = rng.integers(1, 20, ni)
-        parts, prev = [], 0
-        for t, (sp, ln) in enumerate(zip(sites, lens)):
-            if sp < prev:
-                continue
-            parts.append(g[prev:sp])
-            if t % 2 == 0:
-                prev = min(L, sp + ln)  # deletion
-            else:
-                parts.append(_ACGT[rng.integers(0, 4, ln)])  # insertion
-                prev = sp
-        parts.append(g[prev:])
-        g = np.concatenate(parts)
-    return g
-
-
-def synth_collection(n, length, seed, p_snp, p_indel):
-    """genome 0 = base, genomes 1..n-1 = independent mutants of the base."""
-    base = synth_base(length, seed)
-    return [base] + [synth_mutant(base, seed * 1000003 + i, p_snp, p_indel) for i in range(1, n)]
-
-
-def mgmp_ref_limit(n_files, basic_len, rc=True):
-    """MultipleGenomeMatchingProcessor.cpp:130-134,152-168 for sub-4GiB references."""
-    clz = 32 - int(n_files).bit_length()
-    tmp = 15 - clz // 3
-    tmp = 5 if tmp < 5 else (12 if tmp > 12 else tmp)
-    factor = 1 << tmp
-    basic = max(basic_len, 1 << 21)
-    lim = factor * basic * (2 if rc else 1)
-    return min(lim, 2**32 - 1)
+from mbgc_b200.synth import synth_base, synth_mutant, synth_collection, mgmp_ref_limit  # noqa: E402,F401
