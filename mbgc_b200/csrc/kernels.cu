@@ -7,9 +7,10 @@
 //
 // Data flow of one match pass over a batch of target texts ("contigs") against a frozen index:
 //
-//   K3 k_probe        every target position: hash (utils/Hashes.h:28-40) -> occupancy bit (L2) -> table
-//                     slot -> window test (.cpp:211-222) -> K-mer verify (.cpp:298)  => per-tile seed lists
-//   scan + k_compact  tile counts -> dense, position-ordered seed arrays (pos, enc)
+//   K3 k_probe        every target position: hash (utils/Hashes.h:28-40) -> shared-memory filter -> occupancy
+//                     bit (L2) -> table slot -> window test (.cpp:211-222) -> K-mer verify (.cpp:298)
+//                     => position-indexed seed staging per 512-position chunk
+//   scan + k_compact  chunk counts -> dense, position-ordered seed arrays (pos, enc)
 //   k_heads/k_runs    consecutive seeds on one diagonal with spacing k1 collapse into runs (their k-mers
 //                     overlap, so the whole span is known equal without comparing it again)
 //   K4 k_extend       per run: raw left / right reach beyond its first / last seed (.cpp:227-246, 257-259),
@@ -32,6 +33,13 @@ __device__ __forceinline__ uint32_t ld_u32_unaligned(const uint8_t* p) {
     const uintptr_t a = reinterpret_cast<uintptr_t>(p);
     const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~static_cast<uintptr_t>(3));
     return __funnelshift_r(w[0], w[1], static_cast<uint32_t>(a & 3) * 8);
+}
+
+// same through the read-only path (global memory that no kernel of the pass writes)
+__device__ __forceinline__ uint32_t ldg_u32_unaligned(const uint8_t* p) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~static_cast<uintptr_t>(3));
+    return __funnelshift_r(__ldg(w), __ldg(w + 1), static_cast<uint32_t>(a & 3) * 8);
 }
 
 __device__ __forceinline__ uint64_t ld_u64_unaligned(const uint8_t* p) {
@@ -88,7 +96,8 @@ __device__ __forceinline__ int upper_contig(const uint32_t* arr, int n, uint32_t
 // highest lane has the highest sequence number), so each distinct slot costs one atomic per warp.
 // ------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_index_insert(const uint8_t* __restrict__ ref, unsigned long long* __restrict__ ht,
-                                                      uint32_t* __restrict__ occ, uint32_t hashMask, int KW, int k1,
+                                                      uint32_t* __restrict__ occ, uint32_t* __restrict__ filter,
+                                                      uint32_t filterBits, uint32_t hashMask, int KW, int k1,
                                                       int k1ord, InsertRange r0, InsertRange r1) {
     const int64_t total = r0.count + r1.count;
     const int64_t totalPadded = (total + 31) & ~static_cast<int64_t>(31);
@@ -98,7 +107,7 @@ __global__ void __launch_bounds__(256) k_index_insert(const uint8_t* __restrict_
         const bool valid = idx < total;
         unsigned long long slotKey = (1ull << 40) + lane;  // unique per lane: never merges
         unsigned long long key = 0;
-        uint32_t slot = 0;
+        uint32_t slot = 0, hfull = 0;
         if (valid) {
             const bool second = idx >= r0.count;
             const int64_t k = second ? idx - r0.count : idx;
@@ -107,6 +116,7 @@ __global__ void __launch_bounds__(256) k_index_insert(const uint8_t* __restrict_
             uint32_t h = static_cast<uint32_t>(KW * 4);
             for (int j = 0; j < KW; j++) h = hash_step(h, ld_u32_unaligned(ref + pos + 4 * j), j);
             slot = h & hashMask;
+            hfull = h;
             const uint32_t enc = static_cast<uint32_t>(k1ord >= 0 ? (static_cast<uint64_t>(pos) >> k1ord)
                                                                    : static_cast<uint64_t>(pos));
             key = (seq << 32) | enc;
@@ -115,19 +125,24 @@ __global__ void __launch_bounds__(256) k_index_insert(const uint8_t* __restrict_
         const unsigned peers = __match_any_sync(0xffffffffu, slotKey);
         if (valid && lane == 31 - __clz(peers)) {
             atomicMax(&ht[slot], key);
-            atomicOr(&occ[slot >> 5], 1u << (slot & 31));
+            atomicOr(&occ[slot >> 5], 0x80000000u >> (slot & 31));  // bit i lives at 31 - (i & 31), see k_probe
+        }
+        if (valid) {  // first-level (shared-memory) filter of the probe kernel; bits are never cleared
+            const uint32_t fi = __umulhi(hfull, filterBits);
+            atomicOr(&filter[fi >> 5], 0x80000000u >> (fi & 31));
         }
     }
 }
 
-void launch_index_insert(const uint8_t* ref, unsigned long long* ht, uint32_t* occ, uint32_t hashMask, int K, int k1,
-                         int k1ord, InsertRange r0, InsertRange r1, cudaStream_t st) {
+void launch_index_insert(const uint8_t* ref, unsigned long long* ht, uint32_t* occ, uint32_t* filter, uint32_t filterBits,
+                         uint32_t hashMask, int K, int k1, int k1ord, InsertRange r0, InsertRange r1, cudaStream_t st) {
     const int64_t total = r0.count + r1.count;
     if (total <= 0) return;
     int64_t blocks = (total + 255) / 256;
     const int64_t cap = static_cast<int64_t>(device_sm_count()) * 16;
     if (blocks > cap) blocks = cap;
-    k_index_insert<<<static_cast<unsigned>(blocks), 256, 0, st>>>(ref, ht, occ, hashMask, K / 4, k1, k1ord, r0, r1);
+    k_index_insert<<<static_cast<unsigned>(blocks), 256, 0, st>>>(ref, ht, occ, filter, filterBits, hashMask, K / 4, k1,
+                                                                  k1ord, r0, r1);
 }
 
 __global__ void k_table_low32(const unsigned long long* __restrict__ ht, uint32_t* __restrict__ out, uint64_t n) {
@@ -254,55 +269,69 @@ static int scan_exclusive(const uint32_t* in, uint32_t* out, const uint32_t* nPt
 // ------------------------------------------------------------------------------------------------------
 // K3: probe  (.cpp:200-226 and the K-mer verify of :298, for every target position)
 //
-// A CTA owns a tile of 4096 consecutive positions of one contig, staged once in shared memory with 16-byte
-// loads.  Each thread owns 16 consecutive positions: it pulls its 16+K-1 bytes as 128-bit shared loads
-// (conflict-free: consecutive threads, consecutive 16-byte words), forms the unaligned 4-byte words with one
-// funnel shift each and runs the K/4 hash rounds of 16 positions as independent chains.  All 16 occupancy
-// words are requested before any is tested (16 loads in flight per thread); only set bits (seeds plus
-// ~load-factor false positives) go on to the 64-bit table slot, the window test and the K-mer compare against
-// the reference.  Seeds leave the CTA position-ordered (block scan of per-thread counts).
+// Warp-autonomous: a warp owns a chunk of 512 consecutive positions of one contig (lane = 16 positions) and
+// never synchronises with other warps, so the SM hides latency with 24-32 resident warps instead of idling
+// at block barriers.  Per chunk:
+//   1. each lane pulls its 16+K-1 bytes as coalesced 128-bit loads (the 2nd/3rd hit L1: neighbour lanes just
+//      fetched them), forms the unaligned 4-byte words with one funnel shift each and runs the K/4 hash rounds
+//      of its 16 positions as independent chains;
+//   2. first-level filter in SHARED memory: a ~1.5 Mbit Bloom-style bitmap (bit = mulhi(hash, bits)) that every
+//      CTA copies from global once per launch.  A divergent global load costs one L1TEX wavefront per lane
+//      (~1 lookup/clk/SM, the measured wall of the first version); a shared-memory lookup costs ~3 wavefronts
+//      per warp.  With a 10 Mbp reference (625 k sampled k-mers) ~30 % of the positions survive;
+//   3. survivors test the exact occupancy bitmap in global memory (L2-resident, predicated loads: only the
+//      surviving lanes generate wavefronts);
+//   4. set bits (seeds + load-factor false positives) read the 64-bit table slot, apply the window test and
+//      compare the K-mer against the reference;
+//   5. seeds are staged position-indexed (enc at scratchEnc[position], a 16-bit mask per lane): order is
+//      implicit, no scan or barrier in the hot kernel.  k_compact turns the staging into dense arrays.
 // ------------------------------------------------------------------------------------------------------
 struct ProbeArgs {
     IndexState ix;
     BatchDesc b;
-    uint32_t* tileCount;
-    uint32_t* scratchPos;
+    const uint4* chunkDesc;  // per chunk: text byte offset (lo, hi), contig-local base position, nValid of the contig
+    const uint32_t* chunkContig;
+    uint32_t* chunkCount;
+    uint16_t* seedMask;
     uint32_t* scratchEnc;
 };
 
-template <int KW>
-__global__ void __launch_bounds__(PROBE_THREADS) k_probe(const ProbeArgs a) {
+template <int KW, bool FILTER>
+__global__ void __launch_bounds__(FILTER ? PROBE_THREADS_FILTER : PROBE_THREADS_PLAIN, 1) k_probe(const ProbeArgs a) {
     constexpr int NPT = PROBE_NPT;
-    constexpr int TILE = PROBE_TILE;
-    constexpr int NW = NPT / 4 + KW;                 // aligned words a thread needs (index NPT/4-1+KW is the funnel partner)
-    constexpr int NV = (NW + 3) / 4;                 // 128-bit loads per thread
-    __shared__ uint4 sText[TILE / 16 + 8];
-    __shared__ uint32_t sWarp[33];
-    __shared__ int sContig;
-
-    const int tid = threadIdx.x;
+    constexpr int NW = NPT / 4 + KW;  // aligned words a lane needs (the last one is only a funnel-shift partner)
+    constexpr int NV = (NW + 3) / 4;  // 128-bit loads per lane
+    extern __shared__ uint32_t sFilter[];
     const int K = KW * 4;
-    for (uint32_t tile = blockIdx.x; tile < a.b.nTiles; tile += gridDim.x) {
-        if (tid == 0) sContig = upper_contig(a.b.tileStart, a.b.nContigs, tile);
+    const int lane = threadIdx.x & 31;
+    if (FILTER) {
+        const uint4* src = reinterpret_cast<const uint4*>(a.ix.filter);
+        uint4* dst = reinterpret_cast<uint4*>(sFilter);
+        for (uint32_t k = threadIdx.x; k < a.ix.filterWords / 4; k += blockDim.x) dst[k] = src[k];
         __syncthreads();
-        const int c = sContig;
-        const uint32_t base = (tile - a.b.tileStart[c]) * TILE;  // contig-local position of the tile start
-        const uint32_t N2 = a.b.contigLen[c];
-        const uint32_t nValid = N2 >= static_cast<uint32_t>(K) ? N2 - K + 1 : 0;
-        const uint64_t lock = a.b.contigLock ? a.b.contigLock[c] : NO_LOCK;
-        const uint64_t swStop = lock != NO_LOCK ? lock : a.ix.pos1;
-        const uint4* g = reinterpret_cast<const uint4*>(a.b.text + a.b.contigOff[c] + base);
-        for (int k = tid; k < TILE / 16 + 8; k += PROBE_THREADS) sText[k] = g[k];
-        __syncthreads();
+    }
+    const uint32_t warpsTotal = gridDim.x * (blockDim.x >> 5);
+    for (uint32_t g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); g < a.b.nTiles; g += warpsTotal) {
+        const uint4 desc = __ldg(&a.chunkDesc[g]);
+        const uint8_t* ctext = a.b.text + ((static_cast<uint64_t>(desc.y) << 32) | desc.x);  // text of the chunk start
+        const uint32_t base = desc.z;    // contig-local position of the chunk start
+        const uint32_t nValid = desc.w;  // positions of the contig that can start a K-mer
+        const uint32_t p0 = base + lane * NPT;
 
         uint32_t A[NV * 4];
+        {
+            const uint4* gp = reinterpret_cast<const uint4*>(ctext + lane * NPT);
 #pragma unroll
-        for (int k = 0; k < NV; k++) {
-            const uint4 v = sText[tid + k];
-            A[4 * k] = v.x; A[4 * k + 1] = v.y; A[4 * k + 2] = v.z; A[4 * k + 3] = v.w;
+            for (int k = 0; k < NV; k++) {
+                const uint4 v = __ldg(gp + k);
+                A[4 * k] = v.x; A[4 * k + 1] = v.y; A[4 * k + 2] = v.z; A[4 * k + 3] = v.w;
+            }
         }
-
+        // Bit bookkeeping: filter and occupancy words store bit i at position 31 - (i & 31), so "w << (i & 31)"
+        // (one wrapping shift) brings the tested bit to bit 31 and one funnel shift appends it to a mask.
+        // pass: appended in (r, q) order, hit: appended in p order => position p sits at bit 15 - n.
         uint32_t slots[NPT];
+        uint32_t pass = 0;
 #pragma unroll
         for (int r = 0; r < 4; r++) {
             uint32_t V[NPT / 4 + KW - 1];
@@ -314,51 +343,85 @@ __global__ void __launch_bounds__(PROBE_THREADS) k_probe(const ProbeArgs a) {
 #pragma unroll
                 for (int j = 0; j < KW; j++) h = hash_step(h, V[q + j], j);
                 slots[4 * q + r] = h & a.ix.hashMask;
+                if (FILTER) {
+                    const uint32_t fi = __umulhi(h, a.ix.filterBits);
+                    pass = __funnelshift_l(sFilter[fi >> 5] << (fi & 31), pass, 1);
+                }
             }
         }
+        if (!FILTER) pass = 0xffffu;
+
         uint32_t occw[NPT];
 #pragma unroll
-        for (int p = 0; p < NPT; p++) occw[p] = __ldg(&a.ix.occ[slots[p] >> 5]);
-
-        const uint32_t p0 = base + tid * NPT;
-        uint32_t encs[NPT];
-        uint32_t mask = 0;
-#pragma unroll
         for (int p = 0; p < NPT; p++) {
-            encs[p] = 0;
-            if (((occw[p] >> (slots[p] & 31)) & 1u) && p0 + p < nValid) {
-                const uint32_t enc = static_cast<uint32_t>(a.ix.ht[slots[p]]);
+            occw[p] = 0;
+            if (pass & (1u << (15 - ((p & 3) * 4 + (p >> 2))))) occw[p] = __ldg(&a.ix.occ[slots[p] >> 5]);
+        }
+        uint32_t hit = 0;
+#pragma unroll
+        for (int p = 0; p < NPT; p++) hit = __funnelshift_l(occw[p] << (slots[p] & 31), hit, 1);
+        // positions past the last valid one never probe (position p = bit 15 - p)
+        if (p0 + NPT > nValid) hit &= p0 >= nValid ? 0u : (0xffffu << (p0 + NPT - nValid));
+        hit &= 0xffffu;
+
+        uint32_t mask = 0;
+        if (hit) {
+            const uint64_t lock = a.b.contigLock ? a.b.contigLock[a.chunkContig[g]] : NO_LOCK;
+            const uint64_t swStop = lock != NO_LOCK ? lock : a.ix.pos1;
+            do {
+                const int bit = 31 - __clz(hit);
+                hit &= ~(1u << bit);
+                const int p = 15 - bit;
+                // slots[p] for a run-time p: a 4-level select tree keeps the array in registers
+                uint32_t s8[8], s4[4], s2[2];
+#pragma unroll
+                for (int k = 0; k < 8; k++) s8[k] = (p & 1) ? slots[2 * k + 1] : slots[2 * k];
+#pragma unroll
+                for (int k = 0; k < 4; k++) s4[k] = (p & 2) ? s8[2 * k + 1] : s8[2 * k];
+#pragma unroll
+                for (int k = 0; k < 2; k++) s2[k] = (p & 4) ? s4[2 * k + 1] : s4[2 * k];
+                const uint32_t slot = (p & 8) ? s2[1] : s2[0];
+                const uint32_t enc = static_cast<uint32_t>(__ldg(&a.ix.ht[slot]));
                 if (enc != 0) {
                     const uint64_t s = decode_pos(enc, a.ix.k1ord);
                     int cls;
                     if (window_ok(s, K, a.ix.pos1, swStop, cls)) {
-                        const uint8_t* t = reinterpret_cast<const uint8_t*>(sText) + tid * NPT + p;
-                        const uint8_t* r = a.ix.ref + s;
-                        bool eq = true;
+                        // target K-mer from the lane's own registers: words A[q .. q+KW] for q = p / 4 through a
+                        // 2-level select, then one funnel shift per word (no loads)
+                        const int q = p >> 2;
+                        const uint32_t sh = static_cast<uint32_t>(p & 3) * 8;
+                        uint32_t B[KW + 1];
 #pragma unroll
-                        for (int j = 0; j < KW; j++) eq = eq && (ld_u32_unaligned(t + 4 * j) == ld_u32_unaligned(r + 4 * j));
-                        if (eq) {
-                            encs[p] = enc;
+                        for (int m = 0; m <= KW; m++) {
+                            const uint32_t lo = (q & 1) ? A[m + 1] : A[m];
+                            const uint32_t hi = (q & 1) ? A[m + 3] : A[m + 2];
+                            B[m] = (q & 2) ? hi : lo;
+                        }
+                        const uint8_t* r = a.ix.ref + s;
+                        uint32_t diff = 0;
+                        if ((s & 15) == 0 && KW <= 8) {  // Exp variant with k1 >= 16: two aligned 128-bit loads
+                            const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(r));
+                            const uint4 r1 = __ldg(reinterpret_cast<const uint4*>(r) + 1);
+                            const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+                            for (int j = 0; j < KW; j++) diff |= __funnelshift_r(B[j], B[j + 1], sh) ^ rw[j < 8 ? j : 0];
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < KW; j++) diff |= __funnelshift_r(B[j], B[j + 1], sh) ^ ldg_u32_unaligned(r + 4 * j);
+                        }
+                        if (diff == 0) {
+                            a.scratchEnc[static_cast<uint64_t>(g) * PROBE_CHUNK + lane * NPT + p] = enc;
                             mask |= 1u << p;
                         }
                     }
                 }
-            }
+            } while (hit);
         }
-        uint32_t total;
-        uint32_t off = block_excl_scan(__popc(mask), &total, sWarp);
-        if (mask) {
-            const uint64_t o = static_cast<uint64_t>(tile) * TILE + off;
-            uint32_t k = 0;
+        a.seedMask[static_cast<uint64_t>(g) * 32 + lane] = static_cast<uint16_t>(mask);
+        uint32_t cnt = __popc(mask);
 #pragma unroll
-            for (int p = 0; p < NPT; p++)
-                if (mask & (1u << p)) {
-                    a.scratchPos[o + k] = p0 + p;
-                    a.scratchEnc[o + k] = encs[p];
-                    k++;
-                }
-        }
-        if (tid == 0) a.tileCount[tile] = total;
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        if (lane == 0) a.chunkCount[g] = cnt;
     }
 }
 
@@ -380,46 +443,89 @@ int device_sm_count() {
     return g_smCount;
 }
 
-int launch_probe(const IndexState& ix, const BatchDesc& b, const WorkBuffers& w, cudaStream_t st) {
+// chunk -> contig table and self-contained chunk descriptors (one binary search per chunk, once per pass)
+__global__ void __launch_bounds__(256) k_chunk_contig(BatchDesc b, int K, uint32_t* __restrict__ chunkContig,
+                                                      uint4* __restrict__ chunkDesc) {
+    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < b.nTiles; g += gridDim.x * blockDim.x) {
+        const uint32_t c = static_cast<uint32_t>(upper_contig(b.tileStart, b.nContigs, g));
+        chunkContig[g] = c;
+        const uint32_t base = (g - b.tileStart[c]) * PROBE_CHUNK;
+        const uint64_t off = b.contigOff[c] + base;
+        const uint32_t N2 = b.contigLen[c];
+        chunkDesc[g] = make_uint4(static_cast<uint32_t>(off), static_cast<uint32_t>(off >> 32), base,
+                                  N2 >= static_cast<uint32_t>(K) ? N2 - K + 1 : 0);
+    }
+}
+
+template <int KW>
+static void launch_probe_k(const ProbeArgs& a, bool useFilter, cudaStream_t st) {
+    const int sm = device_sm_count();
+    if (useFilter) {
+        const size_t smem = static_cast<size_t>(a.ix.filterWords) * 4;
+        static bool attrSet = false;
+        if (!attrSet) {
+            cudaFuncSetAttribute(k_probe<KW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(PROBE_FILTER_BYTES));
+            attrSet = true;
+        }
+        k_probe<KW, true><<<sm, PROBE_THREADS_FILTER, smem, st>>>(a);
+    } else {
+        uint32_t blocks = (a.b.nTiles + PROBE_THREADS_PLAIN / 32 - 1) / (PROBE_THREADS_PLAIN / 32);
+        const uint32_t cap = static_cast<uint32_t>(sm) * 2;
+        if (blocks > cap) blocks = cap;
+        k_probe<KW, false><<<blocks, PROBE_THREADS_PLAIN, 0, st>>>(a);
+    }
+}
+
+int launch_probe(const IndexState& ix, const BatchDesc& b, const WorkBuffers& w, bool useFilter, cudaStream_t st) {
     if (b.nTiles == 0) {
         cudaMemsetAsync(w.tileCount, 0, sizeof(uint32_t), st);
         return 0;
     }
-    ProbeArgs a{ix, b, w.tileCount, w.scratchPos, w.scratchEnc};
-    uint32_t blocks = b.nTiles;
-    const uint32_t cap = static_cast<uint32_t>(device_sm_count()) * 8;  // persistent: whole waves of resident CTAs
-    if (blocks > cap) blocks = cap;
+    k_chunk_contig<<<device_sm_count() * 4, 256, 0, st>>>(b, ix.K, w.chunkContig, w.chunkDesc);
+    ProbeArgs a{ix, b, w.chunkDesc, w.chunkContig, w.tileCount, w.seedMask, w.scratchEnc};
 #define MBGC_PROBE_CASE(KK) \
-    case KK: k_probe<KK / 4><<<blocks, PROBE_THREADS, 0, st>>>(a); break;
+    case KK: launch_probe_k<KK / 4>(a, useFilter, st); break;
     switch (ix.K) {
         MBGC_PROBE_CASE(12) MBGC_PROBE_CASE(16) MBGC_PROBE_CASE(20) MBGC_PROBE_CASE(24) MBGC_PROBE_CASE(28)
         MBGC_PROBE_CASE(32) MBGC_PROBE_CASE(36) MBGC_PROBE_CASE(40) MBGC_PROBE_CASE(44) MBGC_PROBE_CASE(56)
         default: return -1;
     }
 #undef MBGC_PROBE_CASE
-    return 1;
+    return 2;
 }
 
 // ------------------------------------------------------------------------------------------------------
 // seed compaction + run detection
 // ------------------------------------------------------------------------------------------------------
 
-// tile-local seed lists -> dense arrays (tileOff = exclusive scan of the tile counts)
-__global__ void __launch_bounds__(256) k_compact(BatchDesc b, const uint32_t* __restrict__ tileOff,
-                                                 const uint32_t* __restrict__ scratchPos,
+// position-indexed seed staging -> dense, position-ordered arrays.  One warp per chunk; chunkOff = exclusive
+// scan of the chunk counts.
+__global__ void __launch_bounds__(256) k_compact(BatchDesc b, const uint32_t* __restrict__ chunkContig,
+                                                 const uint32_t* __restrict__ chunkOff,
+                                                 const uint16_t* __restrict__ seedMask,
                                                  const uint32_t* __restrict__ scratchEnc, uint32_t* __restrict__ seedPos,
                                                  uint32_t* __restrict__ seedEnc, uint32_t seedCap, uint32_t* counters) {
-    const uint32_t nSeeds = tileOff[b.nTiles];
+    const uint32_t nSeeds = chunkOff[b.nTiles];
     if (nSeeds > seedCap) {
         if (blockIdx.x == 0 && threadIdx.x == 0) counters[3] = 1;  // overflow: host retries with more room
         return;
     }
-    for (uint32_t tile = blockIdx.x; tile < b.nTiles; tile += gridDim.x) {
-        const uint32_t o = tileOff[tile], n = tileOff[tile + 1] - o;
-        const uint64_t src = static_cast<uint64_t>(tile) * PROBE_TILE;
-        for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) {
-            seedPos[o + k] = scratchPos[src + k];
-            seedEnc[o + k] = scratchEnc[src + k];
+    const int lane = threadIdx.x & 31;
+    const uint32_t warpsTotal = gridDim.x * (blockDim.x >> 5);
+    for (uint32_t g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); g < b.nTiles; g += warpsTotal) {
+        const uint32_t o = chunkOff[g];
+        if (chunkOff[g + 1] == o) continue;
+        uint32_t m = seedMask[static_cast<uint64_t>(g) * 32 + lane];
+        const uint32_t c = __popc(m);
+        uint32_t k = o + warp_incl_scan(c, lane) - c;
+        const uint32_t base = (g - b.tileStart[chunkContig[g]]) * PROBE_CHUNK + lane * PROBE_NPT;
+        const uint64_t src = static_cast<uint64_t>(g) * PROBE_CHUNK + lane * PROBE_NPT;
+        while (m) {
+            const int p = __ffs(m) - 1;
+            m &= m - 1;
+            seedPos[k] = base + p;
+            seedEnc[k] = scratchEnc[src + p];
+            k++;
         }
     }
 }
@@ -428,22 +534,22 @@ __global__ void __launch_bounds__(256) k_compact(BatchDesc b, const uint32_t* __
 // or a different window class (the class fixes the extension bounds tmpStart1/tmpEnd1, .cpp:221-222).
 // Seeds only collapse when their k-mers touch or overlap (k1 <= K); otherwise (protein profile: K = 12 < k1 = 16)
 // the bases between two seeds are unverified and every seed is its own run.
-__global__ void __launch_bounds__(256) k_heads(IndexState ix, BatchDesc b, const uint32_t* __restrict__ tileOff,
+__global__ void __launch_bounds__(256) k_heads(IndexState ix, BatchDesc b, const uint32_t* __restrict__ chunkContig,
+                                               const uint32_t* __restrict__ chunkOff,
                                                const uint32_t* __restrict__ seedPos, const uint32_t* __restrict__ seedEnc,
                                                uint32_t* __restrict__ head, const uint32_t* counters) {
     if (counters[3]) return;
-    __shared__ int sContig;
+    const int lane = threadIdx.x & 31;
+    const uint32_t warpsTotal = gridDim.x * (blockDim.x >> 5);
     const uint32_t encStep = ix.k1ord >= 0 ? static_cast<uint32_t>(ix.k1 >> ix.k1ord) : static_cast<uint32_t>(ix.k1);
-    for (uint32_t tile = blockIdx.x; tile < b.nTiles; tile += gridDim.x) {
-        __syncthreads();
-        if (threadIdx.x == 0) sContig = upper_contig(b.tileStart, b.nContigs, tile);
-        __syncthreads();
-        const int c = sContig;
-        const uint32_t contigFirst = tileOff[b.tileStart[c]];
+    for (uint32_t g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); g < b.nTiles; g += warpsTotal) {
+        const uint32_t o = chunkOff[g], n = chunkOff[g + 1] - o;
+        if (n == 0) continue;
+        const uint32_t c = chunkContig[g];
+        const uint32_t contigFirst = chunkOff[b.tileStart[c]];
         const uint64_t lock = b.contigLock ? b.contigLock[c] : NO_LOCK;
         const uint64_t swStop = lock != NO_LOCK ? lock : ix.pos1;
-        const uint32_t o = tileOff[tile], n = tileOff[tile + 1] - o;
-        for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) {
+        for (uint32_t k = lane; k < n; k += 32) {
             const uint32_t j = o + k;
             uint32_t h = 1;
             if (j != contigFirst) {
@@ -486,9 +592,9 @@ int launch_compact_and_runs(const IndexState& ix, const BatchDesc& b, const Work
     const int sm = device_sm_count();
     // tileCount -> tileOff (in place), tileOff[nTiles] = nSeeds
     launches += scan_exclusive(w.tileCount, w.tileCount, nullptr, b.nTiles, b.nTiles, w.blockSums, nullptr, st);
-    k_compact<<<sm * 8, 256, 0, st>>>(b, w.tileCount, w.scratchPos, w.scratchEnc, w.seedPos, w.seedEnc, w.seedCap,
-                                      w.counters);
-    k_heads<<<sm * 8, 256, 0, st>>>(ix, b, w.tileCount, w.seedPos, w.seedEnc, w.headScan, w.counters);
+    k_compact<<<sm * 8, 256, 0, st>>>(b, w.chunkContig, w.tileCount, w.seedMask, w.scratchEnc, w.seedPos, w.seedEnc,
+                                      w.seedCap, w.counters);
+    k_heads<<<sm * 8, 256, 0, st>>>(ix, b, w.chunkContig, w.tileCount, w.seedPos, w.seedEnc, w.headScan, w.counters);
     launches += 2;
     // head flags -> exclusive scan in place; length lives on the device (tileOff[nTiles])
     launches += scan_exclusive(w.headScan, w.headScan, w.tileCount + b.nTiles, 0, w.seedCap, w.blockSums, nullptr, st);
@@ -645,10 +751,32 @@ __global__ void __launch_bounds__(256) k_extend(const ExtendArgs a) {
     }
 }
 
+// Link chains (adjacent runs on one diagonal whose gap compared equal) share one maximal interval: copy the
+// chain's left end forward and its right end backward so that K5 reads final values.  Every run belongs to
+// exactly one chain and only the thread of the chain end (start) walks it: no races.
+__global__ void __launch_bounds__(256) k_links(RunRec* __restrict__ runs, const uint32_t* counters) {
+    if (counters[3]) return;
+    const uint32_t nRuns = counters[1];
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < nRuns; r += gridDim.x * blockDim.x) {
+        const uint32_t fl = runs[r].flags;
+        if (!(fl & 2u) && (fl & 1u)) {  // chain end (chains have >= 2 runs): push bFree backward
+            const uint32_t b = runs[r].bFree;
+            uint32_t q = r;
+            while (runs[q].flags & 1u) runs[--q].bFree = b;  // a left-linked run always has a predecessor
+        }
+        if (!(fl & 1u) && (fl & 2u)) {  // chain start: push aFree forward
+            const uint32_t a = runs[r].aFree;
+            uint32_t q = r;
+            while (runs[q].flags & 2u) runs[++q].aFree = a;
+        }
+    }
+}
+
 int launch_extend(const IndexState& ix, const BatchDesc& b, const WorkBuffers& w, cudaStream_t st) {
     ExtendArgs a{ix, b, w.tileCount, w.seedPos, w.seedEnc, w.runFirst, w.runStart, w.runs, w.counters};
     k_extend<<<device_sm_count() * 8, 256, 0, st>>>(a);
-    return 1;
+    k_links<<<device_sm_count() * 4, 256, 0, st>>>(w.runs, w.counters);
+    return 2;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -693,9 +821,10 @@ __global__ void __launch_bounds__(RESOLVE_WARPS * 32) k_resolve(const ResolveArg
         const int64_t swStop = lock != NO_LOCK ? static_cast<int64_t>(lock) : pos1;
         const int64_t refLen = static_cast<int64_t>(a.ix.refLen);
         MatchRec* out = a.matches + rs;
+        MatchRec top;  // = out[nOut - 1], kept in registers: the common case never re-reads global memory
+        top.src = 0; top.dst = 0; top.len = 0;
         uint32_t nOut = 0;
         int64_t cur = 0;
-        int64_t prevAFree = 0;
         for (uint32_t base = rs; base < re; base += 32) {
             if (base + lane < re) sRuns[wib][lane] = a.runs[base + lane];
             __syncwarp();
@@ -703,8 +832,7 @@ __global__ void __launch_bounds__(RESOLVE_WARPS * 32) k_resolve(const ResolveArg
                 const uint32_t cnt = re - base < 32 ? re - base : 32;
                 for (uint32_t k = 0; k < cnt; k++) {
                     const RunRec run = sRuns[wib][k];
-                    const int64_t aRes = (run.flags & 1u) ? prevAFree : static_cast<int64_t>(run.aFree);
-                    prevAFree = aRes;
+                    const int64_t aRes = run.aFree;  // link chains already resolved by k_links
                     const int64_t firstPos = run.firstPos;
                     const int64_t lastPos = firstPos + static_cast<int64_t>(run.nSeeds - 1) * k1;
                     int64_t bRes = -1;
@@ -713,17 +841,7 @@ __global__ void __launch_bounds__(RESOLVE_WARPS * 32) k_resolve(const ResolveArg
                         if (cur > i) i += ((cur - i + k1 - 1) / k1) * k1;
                         const int64_t s = static_cast<int64_t>(decode_pos(run.enc0, a.ix.k1ord)) + (i - firstPos);
                         const int64_t d = s - i;
-                        if (bRes < 0) {  // follow the right-link chain once per run
-                            uint32_t rr = base + k;
-                            uint32_t fl = run.flags;
-                            bRes = run.bFree;
-                            while (fl & 2u) {
-                                rr++;
-                                const RunRec nx = a.runs[rr];
-                                fl = nx.flags;
-                                bRes = nx.bFree;
-                            }
-                        }
+                        bRes = run.bFree;
                         const bool endsBefore = s + K < pos1;
                         const bool startsBefore = s < swStop;
                         const int64_t hi = endsBefore ? pos1 : refLen;  // tmpEnd1
@@ -737,7 +855,7 @@ __global__ void __launch_bounds__(RESOLVE_WARPS * 32) k_resolve(const ResolveArg
                         uint32_t idx = nOut;
                         bool broke = false;
                         while (idx > 0) {
-                            const MatchRec last = out[idx - 1];
+                            const MatchRec last = idx == nOut ? top : out[idx - 1];
                             const int64_t lastDst = last.dst, lastEnd = lastDst + last.len;
                             if (lastEnd < p2) {
                                 const int64_t stop = max3(aRes - 1, lo - d, lastEnd - 1);
@@ -761,7 +879,7 @@ __global__ void __launch_bounds__(RESOLVE_WARPS * 32) k_resolve(const ResolveArg
                         if (!broke) {
                             e = max3(aRes - 1, lo - d, -1);
                         } else {
-                            const MatchRec keep = out[idx - 1];
+                            const MatchRec keep = idx == nOut ? top : out[idx - 1];
                             const int64_t overlap = static_cast<int64_t>(keep.dst) + keep.len - (e + 1);
                             if (overlap > 0) e += overlap;
                         }
@@ -773,6 +891,7 @@ __global__ void __launch_bounds__(RESOLVE_WARPS * 32) k_resolve(const ResolveArg
                             mr.dst = static_cast<uint32_t>(e + 1);
                             mr.len = static_cast<uint32_t>(len);
                             out[nOut++] = mr;
+                            top = mr;
                             int64_t skip = (e + 1 + len) - i;
                             skip -= skip > M ? M : skip;
                             cur = i + (skip ? skip : 1);

@@ -13,9 +13,12 @@
 
 namespace mbgc_b200 {
 
-constexpr int PROBE_THREADS = 256;
-constexpr int PROBE_NPT = 16;                       // positions per thread
-constexpr int PROBE_TILE = PROBE_THREADS * PROBE_NPT;  // positions per tile (4096)
+constexpr int PROBE_NPT = 16;                       // positions per lane
+constexpr int PROBE_CHUNK = 32 * PROBE_NPT;         // positions per warp-chunk (512)
+constexpr int PROBE_THREADS_FILTER = 768;           // 1 CTA per SM next to the shared-memory filter
+constexpr int PROBE_THREADS_PLAIN = 512;
+constexpr uint32_t PROBE_FILTER_BYTES = 192 * 1024; // first-level filter, copied to shared memory by every CTA
+constexpr uint32_t PROBE_FILTER_BITS = PROBE_FILTER_BYTES * 8;
 constexpr uint64_t NO_LOCK = UINT64_MAX;
 
 struct RunRec {          // one seed run = consecutive seeds on one diagonal, spacing k1 (24 bytes)
@@ -37,6 +40,9 @@ struct IndexState {      // frozen matcher state a match pass runs against
     const uint8_t* ref;  // device reference buffer (ref[0] is position 0)
     const unsigned long long* ht;  // 64-bit slots: (insert sequence number << 32) | encoded position
     const uint32_t* occ; // occupancy bitmap, 1 bit per slot
+    const uint32_t* filter;  // first-level filter: bit mulhi(hash, filterBits) set for every inserted k-mer
+    uint32_t filterBits;
+    uint32_t filterWords;
     uint32_t hashMask;
     int K;               // hashed prefix length (bytes), multiple of 4
     int k1;              // reference sampling step
@@ -51,15 +57,17 @@ struct BatchDesc {       // device pointers describing the texts of one pass
     const uint64_t* contigOff;   // [nContigs]
     const uint32_t* contigLen;   // [nContigs]
     const uint64_t* contigLock;  // [nContigs] or nullptr
-    const uint32_t* tileStart;   // [nContigs+1]
+    const uint32_t* tileStart;   // [nContigs+1] first chunk of each contig
     int nContigs;
-    uint32_t nTiles;
+    uint32_t nTiles;             // number of 512-position chunks
 };
 
 struct WorkBuffers {     // device scratch of one pass
-    uint32_t* tileCount;     // [nTiles+1] -> exclusive scan in place (tileOffset)
-    uint32_t* scratchPos;    // [nTiles*PROBE_TILE]
-    uint32_t* scratchEnc;    // [nTiles*PROBE_TILE]
+    uint32_t* tileCount;     // [nChunks+1] seeds per chunk -> exclusive scan in place (chunk offsets)
+    uint32_t* chunkContig;   // [nChunks]
+    uint4* chunkDesc;        // [nChunks] text offset lo/hi, contig-local base position, nValid
+    uint16_t* seedMask;      // [nChunks*32] per-lane 16-bit seed masks
+    uint32_t* scratchEnc;    // [nChunks*PROBE_CHUNK] position-indexed table entries of the seeds
     uint32_t* seedPos;       // [seedCap]
     uint32_t* seedEnc;       // [seedCap]
     uint32_t* headScan;      // [seedCap+1]
@@ -81,13 +89,13 @@ struct InsertRange {
     int64_t count;       // number of samples (step k1)
     uint64_t seqBase;    // global insert sequence number of the first sample
 };
-void launch_index_insert(const uint8_t* ref, unsigned long long* ht, uint32_t* occ, uint32_t hashMask, int K, int k1,
-                         int k1ord, InsertRange r0, InsertRange r1, cudaStream_t st);
+void launch_index_insert(const uint8_t* ref, unsigned long long* ht, uint32_t* occ, uint32_t* filter, uint32_t filterBits,
+                         uint32_t hashMask, int K, int k1, int k1ord, InsertRange r0, InsertRange r1, cudaStream_t st);
 void launch_table_low32(const unsigned long long* ht, uint32_t* out, uint64_t n, cudaStream_t st);
 
 // ---- match pass ----
 // returns the number of kernel launches issued
-int launch_probe(const IndexState& ix, const BatchDesc& b, const WorkBuffers& w, cudaStream_t st);
+int launch_probe(const IndexState& ix, const BatchDesc& b, const WorkBuffers& w, bool useFilter, cudaStream_t st);
 int launch_compact_and_runs(const IndexState& ix, const BatchDesc& b, const WorkBuffers& w, cudaStream_t st);
 int launch_extend(const IndexState& ix, const BatchDesc& b, const WorkBuffers& w, cudaStream_t st);
 int launch_resolve(const IndexState& ix, const BatchDesc& b, const WorkBuffers& w, uint32_t minMatchLength,

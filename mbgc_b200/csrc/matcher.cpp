@@ -121,6 +121,8 @@ B200SparseEMMatcher::B200SparseEMMatcher(uint64_t refLengthLimit, uint32_t targe
     check(cudaMemsetAsync(dHt, 0, static_cast<uint64_t>(hashSize) * sizeof(unsigned long long), stream), "memset(table)");
     check(cudaMalloc(&dOcc, hashSize / 8), "cudaMalloc(occupancy)");
     check(cudaMemsetAsync(dOcc, 0, hashSize / 8, stream), "memset(occupancy)");
+    check(cudaMalloc(&dFilter, PROBE_FILTER_BYTES), "cudaMalloc(filter)");
+    check(cudaMemsetAsync(dFilter, 0, PROBE_FILTER_BYTES, stream), "memset(filter)");
     check(cudaStreamSynchronize(stream), "init sync");
 }
 
@@ -130,6 +132,7 @@ B200SparseEMMatcher::~B200SparseEMMatcher() {
     cudaFree(dRefAlloc);
     cudaFree(dHt);
     cudaFree(dOcc);
+    cudaFree(dFilter);
     cudaFree(dText);
     cudaFree(dMeta);
     cudaFree(dWork);
@@ -161,7 +164,7 @@ void B200SparseEMMatcher::indexPass() {
     if (insertSeq + n >= (1ull << 32))
         throw MatcherError(MBGCG_E_UNSUPPORTED, "more than 2^32 index samples over the life of one matcher");
     insertSeq += n;
-    launch_index_insert(dRef, dHt, dOcc, hashSize - 1, K, k1, k1ord, r0, r1, stream);
+    launch_index_insert(dRef, dHt, dOcc, dFilter, PROBE_FILTER_BITS, hashSize - 1, K, k1, k1ord, r0, r1, stream);
     totalLaunches++;
     check(cudaGetLastError(), "index_insert launch");
 }
@@ -299,9 +302,11 @@ void B200SparseEMMatcher::ensureWork(uint64_t textBytes, uint32_t nTiles, int nC
     // work buffers, carved from one allocation
     uint64_t off = 0;
     auto carve = [&](uint64_t bytes) { const uint64_t o = off; off = align_up(off + bytes, 256); return o; };
-    const uint64_t scratchN = static_cast<uint64_t>(nTiles) * PROBE_TILE;
+    const uint64_t scratchN = static_cast<uint64_t>(nTiles) * PROBE_CHUNK;
     const uint64_t oTileCount = carve((static_cast<uint64_t>(nTiles) + 2) * 4);
-    const uint64_t oScratchPos = carve(scratchN * 4);
+    const uint64_t oChunkContig = carve((static_cast<uint64_t>(nTiles) + 2) * 4);
+    const uint64_t oChunkDesc = carve((static_cast<uint64_t>(nTiles) + 2) * 16);
+    const uint64_t oSeedMask = carve((static_cast<uint64_t>(nTiles) + 1) * 32 * 2);
     const uint64_t oScratchEnc = carve(scratchN * 4);
     const uint64_t oSeedPos = carve(static_cast<uint64_t>(seedCap) * 4);
     const uint64_t oSeedEnc = carve(static_cast<uint64_t>(seedCap) * 4);
@@ -325,7 +330,9 @@ void B200SparseEMMatcher::ensureWork(uint64_t textBytes, uint32_t nTiles, int nC
         dWorkCap = cap;
     }
     wb.tileCount = reinterpret_cast<uint32_t*>(dWork + oTileCount);
-    wb.scratchPos = reinterpret_cast<uint32_t*>(dWork + oScratchPos);
+    wb.chunkContig = reinterpret_cast<uint32_t*>(dWork + oChunkContig);
+    wb.chunkDesc = reinterpret_cast<uint4*>(dWork + oChunkDesc);
+    wb.seedMask = reinterpret_cast<uint16_t*>(dWork + oSeedMask);
     wb.scratchEnc = reinterpret_cast<uint32_t*>(dWork + oScratchEnc);
     wb.seedPos = reinterpret_cast<uint32_t*>(dWork + oSeedPos);
     wb.seedEnc = reinterpret_cast<uint32_t*>(dWork + oSeedEnc);
@@ -361,6 +368,7 @@ void B200SparseEMMatcher::matchBatch(const std::vector<TextView>& texts, const u
         const char* e = std::getenv("MBGC_B200_MAX_PASS_BYTES");
         return e ? std::strtoull(e, nullptr, 10) : (256ull << 20);
     }();
+    static const bool noFilterEnv = std::getenv("MBGC_B200_NO_FILTER") != nullptr;
     size_t first = 0;
     while (first < texts.size()) {
         size_t last = first;
@@ -379,7 +387,7 @@ void B200SparseEMMatcher::matchBatch(const std::vector<TextView>& texts, const u
             cursor = align_up(cursor + len + TEXT_GAP, 16);
             tileStart[c] = tiles;
             const uint64_t nValid = len >= static_cast<uint64_t>(K) ? len - K + 1 : 0;
-            tiles += static_cast<uint32_t>((nValid + PROBE_TILE - 1) / PROBE_TILE);
+            tiles += static_cast<uint32_t>((nValid + PROBE_CHUNK - 1) / PROBE_CHUNK);
             positions += nValid;
         }
         tileStart[nC] = tiles;
@@ -428,6 +436,9 @@ void B200SparseEMMatcher::matchBatch(const std::vector<TextView>& texts, const u
             ix.ref = dRef;
             ix.ht = dHt;
             ix.occ = dOcc;
+            ix.filter = dFilter;
+            ix.filterBits = PROBE_FILTER_BITS;
+            ix.filterWords = PROBE_FILTER_BYTES / 4;
             ix.hashMask = hashSize - 1;
             ix.K = K;
             ix.k1 = k1;
@@ -437,7 +448,9 @@ void B200SparseEMMatcher::matchBatch(const std::vector<TextView>& texts, const u
             ix.refLen = getRefLength();
 
             int launches = 0;
-            launches += launch_probe(ix, bd, wb, stream);
+            // the shared-memory filter only pays while it is sparse (entries <~ bits)
+            const bool useFilter = insertSeq < static_cast<uint64_t>(PROBE_FILTER_BITS) * 3 / 2 && !noFilterEnv;
+            launches += launch_probe(ix, bd, wb, useFilter, stream);
             check(cudaEventRecord(ev[2], stream), "event");
             launches += launch_compact_and_runs(ix, bd, wb, stream);
             check(cudaEventRecord(ev[3], stream), "event");

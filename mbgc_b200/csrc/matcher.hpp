@@ -109,6 +109,7 @@ private:
     uint8_t* dRef = nullptr;             // = dRefAlloc + PAD
     unsigned long long* dHt = nullptr;
     uint32_t* dOcc = nullptr;
+    uint32_t* dFilter = nullptr;         // first-level probe filter (copied to shared memory by the probe kernel)
     uint64_t insertSeq = 1;              // program-order sequence number of the next index sample
     std::deque<uint64_t> workersSwEndPositions;
 
