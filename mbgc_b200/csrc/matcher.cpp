@@ -99,7 +99,6 @@ B200SparseEMMatcher::B200SparseEMMatcher(uint64_t refLengthLimit, uint32_t targe
     } while (i <= 31 && hashSize < maxRefLength / static_cast<uint64_t>(k1));
     if (__builtin_ctz(static_cast<uint32_t>(k1))) {
         k1ord = __builtin_ctz(static_cast<uint32_t>(k1));
-        if (k1 & (k1 - 1)) throw MatcherError(MBGCG_E_UNSUPPORTED, "even k1 that is not a power of two");
         samplingPos = static_cast<uint64_t>(k1);  // .cpp:503
         if ((maxRefLength >> k1ord) >= (1ull << 32))
             throw MatcherError(MBGCG_E_UNSUPPORTED, "reference needs the 64-bit table (ref .cpp:505-508)");

@@ -1,0 +1,188 @@
+// mbgc_b200/dropin/SlidingWindowSparseEMMatcher_b200.cpp
+//
+// Link-time substitute for /root/reference/matching/SlidingWindowSparseEMMatcher.cpp.
+//
+// It is compiled against the UNMODIFIED reference header (matching/SlidingWindowSparseEMMatcher.h) and
+// defines every out-of-line member that header declares and the rest of MBGC calls (constructors,
+// destructor, loadRef, loadSeparator, matchTexts, acquire/releaseWorkerMatchingLockPos) on top of the C ABI of
+// include/mbgc_b200.h, i.e. on the CUDA kernels.  Everything else of `mbgc` is built from the reference's own
+// sources (oracle/Makefile target `dropin`), so MultipleGenomeMatchingProcessor and MBGC_Encoder run unchanged:
+// same call sites (MultipleGenomeMatchingProcessor.cpp:171-183,274,286,379,441,456; MBGC_Encoder.cpp:181,318-330,
+// 376-380,501-508,558-561,883), same archive bytes.
+//
+// The reference header's inline methods (disableSlidingWindow, setSlidingWindowSize, disableCircularBuffer,
+// setPosition, getRef, getRefLength, getLoadingPosition, getLoadedRefLength; .h:93-113) read and write the
+// protected members directly, so the members stay authoritative for the host-visible state: it is pushed into
+// the handle before, and pulled back after, every call (mbgcg_set_state / mbgcg_get_state).  The handle itself
+// lives in the otherwise unused ht64bit pointer; start1 points at the handle's host mirror of the reference.
+//
+// Errors keep the reference's behaviour: message on stderr, exit(EXIT_FAILURE).
+#include "SlidingWindowSparseEMMatcher.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <mutex>
+
+#include "mbgc_b200.h"
+
+namespace {
+
+// The reference's parallel mode enters matchTexts from several OpenMP threads while another one runs loadRef
+// (SURVEY.md 8b "Threading").  A handle is not thread-safe; serialising is a legal schedule of that mode.
+std::mutex g_lock;
+
+inline mbgcg_t* handle_of(uint64_t* slot) { return reinterpret_cast<mbgcg_t*>(slot); }
+
+[[noreturn]] void die(const char* msg) {
+    fprintf(stderr, "%s\n\n", msg);
+    exit(EXIT_FAILURE);
+}
+
+int device_from_env() {
+    const char* e = std::getenv("MBGC_B200_DEVICE");
+    return e ? std::atoi(e) : 0;
+}
+
+}  // namespace
+
+#define MBGCG_PUSH_STATE(h)                                       \
+    do {                                                          \
+        mbgcg_state_t st_;                                        \
+        mbgcg_get_state((h), &st_);                               \
+        st_.pos1 = pos1;                                          \
+        st_.reachedRefLengthCount = reachedRefLengthCount;        \
+        st_.circularBuffer = circularBuffer ? 1 : 0;              \
+        st_.swSize = swSize;                                      \
+        st_.swEnd = swEnd;                                        \
+        st_.samplingPos = samplingPos;                            \
+        mbgcg_set_state((h), &st_);                               \
+    } while (0)
+
+#define MBGCG_PULL_STATE(h)                                       \
+    do {                                                          \
+        mbgcg_state_t st_;                                        \
+        mbgcg_get_state((h), &st_);                               \
+        pos1 = st_.pos1;                                          \
+        reachedRefLengthCount = st_.reachedRefLengthCount;        \
+        swEnd = st_.swEnd;                                        \
+        samplingPos = st_.samplingPos;                            \
+    } while (0)
+
+// ref .cpp:325-359 (skipHtInit is irrelevant here: the table lives on the device either way)
+SlidingWindowSparseEMMatcher::SlidingWindowSparseEMMatcher(const size_t refLengthLimit, const uint32_t targetMatchLength,
+                                                           int _k1, int _k2, int skipMargin, uint32_t minMatchLength,
+                                                           bool skipHtInit)
+        : maxRefLength(refLengthLimit), L(targetMatchLength), skipMargin(skipMargin) {
+    (void) minMatchLength;
+    (void) skipHtInit;
+    mbgcg_t* h = nullptr;
+    if (mbgcg_create(&h, refLengthLimit, targetMatchLength, _k1, _k2, skipMargin, device_from_env()) != MBGCG_OK)
+        die(mbgcg_create_error());
+    ht64bit = reinterpret_cast<std::uint64_t*>(h);
+    ht32bit = nullptr;
+    ht64bitFlag = false;
+    mbgcg_state_t st;
+    mbgcg_get_state(h, &st);
+    start1 = const_cast<char*>(mbgcg_host_ref(h));
+    pos1 = st.pos1;
+    maxRefLength = st.maxRefLength;
+    swSize = st.swSize;
+    swEnd = st.swEnd;
+    samplingPos = st.samplingPos;
+    hash_size = st.hashSize;
+    hash_size_minus_one = hash_size - 1;
+    K = st.K;
+    k1 = _k1;
+    k2 = _k2;
+    *PgHelpers::devout << "SparseEM (B200): k-mer exact match length = " << L << "; hash pattern length = " << K
+                       << "; HASH_SIZE = " << hash_size << "; k1 = " << k1 << "; k2 = " << k2
+                       << "; skipMargin = " << skipMargin << std::endl;
+}
+
+// ref .cpp:494-519: the C ABI picks the Exp variant from ctz(k1) exactly as MultipleGenomeMatchingProcessor does
+SlidingWindowExpSparseEMMatcher::SlidingWindowExpSparseEMMatcher(const size_t refLengthLimit,
+                                                                 const uint32_t targetMatchLength, int _k1, int _k2,
+                                                                 int skipMargin, uint32_t minMatchLength)
+        : SlidingWindowSparseEMMatcher(refLengthLimit, targetMatchLength, _k1, _k2, skipMargin, minMatchLength, true),
+          k1ord(__builtin_ctz((uint32_t) _k1)) {
+    if (_k1 % 2) die("Error initializing ExpSparseMEM: incorrect k1");
+}
+
+SlidingWindowExpRandSparseEMMatcher::SlidingWindowExpRandSparseEMMatcher(const size_t, const uint32_t, int, int, int,
+                                                                         uint32_t)
+        : SlidingWindowExpSparseEMMatcher(2, 32, 16, 1, 0) {
+    die("SlidingWindowExpRandSparseEMMatcher is not part of the accelerated path (never selected by MBGC)");
+}
+
+// ref .cpp:460-467
+SlidingWindowSparseEMMatcher::~SlidingWindowSparseEMMatcher() {
+    std::lock_guard<std::mutex> g(g_lock);
+    mbgcg_destroy(handle_of(ht64bit));
+    ht64bit = nullptr;
+    start1 = nullptr;
+}
+
+// ref .cpp:453-458
+void SlidingWindowSparseEMMatcher::loadRef(const char* refText, size_t refLength, bool loadRCRef, bool addRegionSeparators,
+                                           char regionSeparator) {
+    std::lock_guard<std::mutex> g(g_lock);
+    mbgcg_t* h = handle_of(ht64bit);
+    MBGCG_PUSH_STATE(h);
+    if (mbgcg_load_ref(h, refText, refLength, loadRCRef, addRegionSeparators, regionSeparator) != MBGCG_OK)
+        die(mbgcg_last_error(h));
+    MBGCG_PULL_STATE(h);
+}
+
+// ref .cpp:439-451
+void SlidingWindowSparseEMMatcher::loadSeparator(char regionSeparator) {
+    std::lock_guard<std::mutex> g(g_lock);
+    mbgcg_t* h = handle_of(ht64bit);
+    MBGCG_PUSH_STATE(h);
+    if (mbgcg_load_separator(h, regionSeparator) != MBGCG_OK) die(mbgcg_last_error(h));
+    MBGCG_PULL_STATE(h);
+}
+
+// ref .cpp:361-378
+size_t SlidingWindowSparseEMMatcher::acquireWorkerMatchingLockPos() {
+    std::lock_guard<std::mutex> g(g_lock);
+    mbgcg_t* h = handle_of(ht64bit);
+    MBGCG_PUSH_STATE(h);
+    const size_t v = mbgcg_acquire_lock(h);
+    MBGCG_PULL_STATE(h);
+    return v;
+}
+
+// ref .cpp:380-400
+void SlidingWindowSparseEMMatcher::releaseWorkerMatchingLockPos(size_t lockValue) {
+    std::lock_guard<std::mutex> g(g_lock);
+    mbgcg_t* h = handle_of(ht64bit);
+    MBGCG_PUSH_STATE(h);
+    if (mbgcg_release_lock(h, lockValue) != MBGCG_OK) die(mbgcg_last_error(h));
+    MBGCG_PULL_STATE(h);
+}
+
+// ref .cpp:477-492
+void SlidingWindowSparseEMMatcher::matchTexts(vector<TextMatch>& resMatches, const char* destText, size_t destLen,
+                                              bool destIsRef, bool revComplMatching, uint32_t minMatchLength,
+                                              size_t matchingLockPos) {
+    if (destIsRef || revComplMatching)  // ref .cpp:185-188
+        die("Source as destination and reverse-complement matching modes unsupported");
+    std::lock_guard<std::mutex> g(g_lock);
+    mbgcg_t* h = handle_of(ht64bit);
+    MBGCG_PUSH_STATE(h);
+    const mbgcg_match_t* out = nullptr;
+    uint64_t n = 0;
+    if (mbgcg_match(h, destText, destLen, minMatchLength, matchingLockPos, &out, &n) != MBGCG_OK)
+        die(mbgcg_last_error(h));
+    resMatches.clear();
+    resMatches.reserve(n);
+    for (uint64_t i = 0; i < n; i++)
+        resMatches.push_back(TextMatch(out[i].posSrcText, out[i].length, out[i].posDestText));
+}
+
+// ref .cpp:470-475
+void SlidingWindowSparseEMMatcher::matchTexts(vector<TextMatch>& resMatches, const string& destText, bool destIsRef,
+                                              bool revComplMatching, uint32_t minMatchLength, size_t matchingLockPos) {
+    matchTexts(resMatches, destText.data(), destText.size(), destIsRef, revComplMatching, minMatchLength,
+               matchingLockPos);
+}

@@ -38,7 +38,7 @@ def test_scenarios_match_oracle(sc, skip_margin):
         o.close()
 
 
-@pytest.mark.parametrize("L,k1,sm", [(32, 7, 16), (32, 8, 24), (32, 32, 16), (24, 16, 24), (20, 16, 16), (16, 16, 16),
+@pytest.mark.parametrize("L,k1,sm", [(32, 7, 16), (32, 8, 24), (32, 12, 16), (32, 6, 0), (32, 32, 16), (24, 16, 24), (20, 16, 16), (16, 16, 16),
                                       (16, 4, 0), (48, 16, 16), (64, 16, 0), (40, 5, 3), (120, 16, 16)])
 def test_parameter_variants(L, k1, sm):
     """other (L, k1, skipMargin) than MBGC's defaults: plain (odd k1) and Exp variants, K = 12..56, K < k1"""
