@@ -212,6 +212,7 @@ def run_reference(args, rank):
 def run_b200(args, rank, world):
     import torch
     import mbgc_b200
+    from mbgc_b200.dist import max_over_ranks
 
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -267,11 +268,7 @@ def run_b200(args, rank, world):
                 stage[k] += v
         e1.record(stream)
         barrier()
-        ms = e0.elapsed_time(e1)
-        if dist is not None:
-            tms = torch.tensor([ms], device="cuda")
-            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-            ms = float(tms.item())
+        ms = max_over_ranks(e0.elapsed_time(e1), "cuda")  # device time, max over ranks
         return ms, stage, m.totalLaunches() - launches0, res
 
     sampler = ClockSampler(local)

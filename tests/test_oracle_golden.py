@@ -1,0 +1,99 @@
+"""The CPU oracle against the golden vectors generated FROM THE REFERENCE (tests/golden/make_golden.py):
+match lists, table contents and cursor state of every scenario; the six encoder streams of the deterministic
+schedule; hash known answers.  Needs neither /root/reference nor oracle/_ref at run time."""
+import hashlib
+import json
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+from scenarios import all_scenarios, replay
+from seq_schedule import encode_streams
+from util import FIXTURES, GOLDEN, OracleMatcher, have_fixtures, oracle_lib, ptr
+
+G = json.load(open(os.path.join(GOLDEN, "golden.json")))
+
+
+def digest(arrs):
+    h = hashlib.sha256()
+    for a in arrs:
+        h.update(np.ascontiguousarray(a, dtype=np.uint64).tobytes())
+        h.update(b"|")
+    return h.hexdigest()
+
+
+@pytest.mark.parametrize("skip_margin", [16, 24])
+@pytest.mark.parametrize("sc", all_scenarios(), ids=lambda s: s["name"])
+def test_scenarios(sc, skip_margin):
+    want = G["scenarios"][f"{sc['name']}/{skip_margin}"]
+    o = OracleMatcher(sc["limit"], 32, 16, 1, skip_margin)
+    res, state = replay(o, sc)
+    assert [len(x) for x in res] == want["counts"]
+    assert digest(res) == want["matches"]
+    assert [int(x) for x in state] == want["state"]
+    assert hashlib.sha256(o.table().tobytes()).hexdigest() == want["table"]
+    o.close()
+
+
+def test_prefilter_is_redundant():
+    """the l/r 4-byte side-probe filter (ref .cpp:203-204,223-226) never changes a result: the CUDA path omits it"""
+    for sc in all_scenarios()[:6]:
+        a = OracleMatcher(sc["limit"])
+        b = OracleMatcher(sc["limit"])
+        ra, _ = replay(a, sc)
+        orig = b.match
+        b.match = lambda t, ml=32, lock=2**64 - 1: orig(t, ml, lock, prefilter=False)
+        rb, _ = replay(b, sc)
+        for x, y in zip(ra, rb):
+            assert np.array_equal(x, y)
+
+
+def test_hash_known_answers():
+    """every slot the reference wrote for a seeded text: slot = hash28(k-mer) & mask, value = pos >> 4"""
+    lib = oracle_lib()
+    h = G["hash"]
+    rng = np.random.default_rng(h["text_seed"])
+    text = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, h["text_len"])]
+    ref = np.concatenate([np.zeros(1, np.uint8), text])  # reference position 1 = text[0]
+    mask = lib.mbo_hash_size(1 << 20, 16) - 1
+    want = {s: v for s, v in h["slots"]}
+    got = {}
+    for pos in range(16, text.size + 1 - 28 + 1, 16):
+        got[lib.mbo_hash(ptr(np.ascontiguousarray(ref[pos:pos + 28])), 28) & mask] = pos >> 4
+    assert got == want
+
+
+def _golden_collection(d):
+    from mbgc_b200.synth import synth_collection, write_fasta
+    gs = synth_collection(6, 200_000, 99, 5e-3, 5e-4)
+    paths = []
+    for i, g in enumerate(gs):
+        p = os.path.join(d, f"g{i:04d}.fna")
+        write_fasta(p, f"syn_{i:04d} synthetic E. coli-like genome {i}", g)
+        paths.append(p)
+    return paths
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_streams_of_sequential_schedule(mode):
+    """matchTexts + processMatches + extension decisions, replayed with the oracle, give the reference's streams"""
+    want = G["streams"][str(mode)]
+    with tempfile.TemporaryDirectory() as d:
+        out, _ = encode_streams(_golden_collection(d), mode)
+    for name in ("literals", "gapDelta", "gapFlags", "mapOff", "mapLen"):
+        assert len(out[name]) == want[name]["size"], name
+        assert hashlib.sha256(out[name]).hexdigest() == want[name]["sha256"], name
+
+
+@pytest.mark.skipif(not have_fixtures(), reason="reference fixtures not present (oracle/_ref/fixtures)")
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_streams_listeria(mode):
+    want = G["listeria"][str(mode)]
+    paths = [os.path.join(FIXTURES, l.strip()) for l in open(os.path.join(FIXTURES, "seqlist.txt"))]
+    out, stats = encode_streams(paths, mode)
+    for name in ("literals", "gapDelta", "gapFlags", "mapOff", "mapLen"):
+        assert hashlib.sha256(out[name]).hexdigest() == want[name]["sha256"], name
+    if mode == 1:  # the reference's own dev counters
+        assert stats["matches"] == 29731 and stats["unmatched"] == 5009573 and stats["ref_length"] == 16584539
