@@ -143,10 +143,16 @@ enum {
     MBGCG_T_RESOLVE = 4,  /* K5: sequential-equivalent overlap/skip resolve -> match lists */
     MBGCG_T_D2H = 5,      /* device->host copy of the match lists */
     MBGCG_T_TOTAL = 6,    /* first to last event */
-    MBGCG_T_COUNT = 8
+    /* parts of MBGCG_T_PROBE */
+    MBGCG_T_ANCHOR = 7,   /* fast path: first 16 positions of every 512-position chunk */
+    MBGCG_T_CLEAN = 8,    /* fast path: chunk == reference on the anchor's diagonal? */
+    MBGCG_T_FULLPROBE = 9,/* full probe of the chunks the fast path left over (or of all chunks) */
+    MBGCG_T_MEMO = 10,    /* self-probe of the reference (only when the index changed since the last one) */
+    MBGCG_T_COUNT = 12
 };
 void mbgcg_last_timing(const mbgcg_t* h, float ms[MBGCG_T_COUNT]);
-/* counters of the last match call: positions probed, seeds, seed runs, matches, kernel launches */
+/* counters of the last match call: 0 positions, 1 seed segments, 2 seed runs, 3 matches, 4 kernel launches,
+ * 5 passes, 6 chunks, 7 chunks that went through the full probe */
 void mbgcg_last_counters(const mbgcg_t* h, uint64_t out[8]);
 /* total kernel launches issued by this handle since creation */
 uint64_t mbgcg_total_launches(const mbgcg_t* h);

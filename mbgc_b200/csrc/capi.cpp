@@ -18,6 +18,7 @@ struct mbgcg {
 };
 
 static_assert(sizeof(mbgcg_match_t) == sizeof(TextMatch), "TextMatch layout");
+static_assert(MBGCG_T_COUNT == MBGCG_T_COUNT_, "timing slots");
 
 static thread_local std::string g_createError;
 
@@ -148,6 +149,7 @@ void mbgcg_get_state(const mbgcg_t* h, mbgcg_state_t* out) {
 
 void mbgcg_set_state(mbgcg_t* h, const mbgcg_state_t* in) {
     B200SparseEMMatcher* m = h->m;
+    if (m->pos1 != in->pos1 || m->reachedRefLengthCount != in->reachedRefLengthCount) m->invalidateMemo();
     m->pos1 = in->pos1;
     m->reachedRefLengthCount = in->reachedRefLengthCount;
     m->circularBuffer = in->circularBuffer != 0;

@@ -294,15 +294,105 @@ struct ProbeArgs {
     uint32_t* chunkCount;
     uint16_t* seedMask;
     uint32_t* scratchEnc;
+    const uint32_t* workList;    // nullptr: every chunk; else the chunks the fast path (k_clean) left over
+    const uint32_t* workCount;   // device-resident length of workList
+    unsigned long long* anchor;  // k_anchor output
 };
+
+__host__ __device__ constexpr int probe_words(int KW) { return ((PROBE_NPT / 4 + KW + 3) / 4) * 4; }  // aligned words a lane holds
+
+// 16 consecutive positions of one lane: hash (utils/Hashes.h:28-40) -> slot, first-level filter, occupancy bit.
+// A = the lane's aligned text words.  Returns the mask of positions whose occupancy bit is set (position p at
+// bit 15 - p).  Bit bookkeeping: filter and occupancy words store bit i at position 31 - (i & 31), so
+// "w << (i & 31)" (one wrapping shift) brings the tested bit to bit 31 and one funnel shift appends it to a mask.
+template <int KW, bool FILTER>
+__device__ __forceinline__ uint32_t probe_lane16(const IndexState& ix, const uint32_t* sFilter,
+                                                 const uint32_t (&A)[probe_words(KW)], uint32_t (&slots)[PROBE_NPT]) {
+    constexpr int NPT = PROBE_NPT;
+    uint32_t pass = 0;  // appended in (r, q) order
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        uint32_t V[NPT / 4 + KW - 1];
+#pragma unroll
+        for (int m = 0; m < NPT / 4 + KW - 1; m++) V[m] = r == 0 ? A[m] : __funnelshift_r(A[m], A[m + 1], 8 * r);
+#pragma unroll
+        for (int q = 0; q < NPT / 4; q++) {
+            uint32_t h = static_cast<uint32_t>(KW * 4);
+#pragma unroll
+            for (int j = 0; j < KW; j++) h = hash_step(h, V[q + j], j);
+            slots[4 * q + r] = h & ix.hashMask;
+            if (FILTER) {
+                const uint32_t fi = __umulhi(h, ix.filterBits);
+                pass = __funnelshift_l(sFilter[fi >> 5] << (fi & 31), pass, 1);
+            }
+        }
+    }
+    if (!FILTER) pass = 0xffffu;
+    uint32_t occw[NPT];
+#pragma unroll
+    for (int p = 0; p < NPT; p++) {
+        occw[p] = 0;
+        if (pass & (1u << (15 - ((p & 3) * 4 + (p >> 2))))) occw[p] = __ldg(&ix.occ[slots[p] >> 5]);
+    }
+    uint32_t hit = 0;  // appended in p order
+#pragma unroll
+    for (int p = 0; p < NPT; p++) hit = __funnelshift_l(occw[p] << (slots[p] & 31), hit, 1);
+    return hit & 0xffffu;
+}
+
+// slots[p] for a run-time p: a 4-level select tree keeps the array in registers
+__device__ __forceinline__ uint32_t select16(const uint32_t (&slots)[PROBE_NPT], int p) {
+    uint32_t s8[8], s4[4], s2[2];
+#pragma unroll
+    for (int k = 0; k < 8; k++) s8[k] = (p & 1) ? slots[2 * k + 1] : slots[2 * k];
+#pragma unroll
+    for (int k = 0; k < 4; k++) s4[k] = (p & 2) ? s8[2 * k + 1] : s8[2 * k];
+#pragma unroll
+    for (int k = 0; k < 2; k++) s2[k] = (p & 4) ? s4[2 * k + 1] : s4[2 * k];
+    return (p & 8) ? s2[1] : s2[0];
+}
+
+// candidate at lane position p: table slot -> window test (.cpp:212-220) -> K-mer compare (.cpp:298).
+// Returns the table entry of a verified seed, else 0.
+template <int KW>
+__device__ __forceinline__ uint32_t verify_candidate(const IndexState& ix, const uint32_t (&A)[probe_words(KW)], int p,
+                                                     uint32_t slot, uint64_t swStop) {
+    const uint32_t enc = static_cast<uint32_t>(__ldg(&ix.ht[slot]));
+    if (enc == 0) return 0;
+    const uint64_t s = decode_pos(enc, ix.k1ord);
+    int cls;
+    if (!window_ok(s, KW * 4, ix.pos1, swStop, cls)) return 0;
+    // target K-mer from the lane's own registers: words A[q .. q+KW] for q = p / 4 through a 2-level select, then
+    // one funnel shift per word (no loads)
+    const int q = p >> 2;
+    const uint32_t sh = static_cast<uint32_t>(p & 3) * 8;
+    uint32_t B[KW + 1];
+#pragma unroll
+    for (int m = 0; m <= KW; m++) {
+        const uint32_t lo = (q & 1) ? A[m + 1] : A[m];
+        const uint32_t hi = (q & 1) ? A[m + 3] : A[m + 2];
+        B[m] = (q & 2) ? hi : lo;
+    }
+    const uint8_t* r = ix.ref + s;
+    uint32_t diff = 0;
+    if ((s & 15) == 0 && KW <= 8) {  // Exp variant with k1 >= 16: two aligned 128-bit loads
+        const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(r));
+        const uint4 r1 = __ldg(reinterpret_cast<const uint4*>(r) + 1);
+        const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+        for (int j = 0; j < KW; j++) diff |= __funnelshift_r(B[j], B[j + 1], sh) ^ rw[j < 8 ? j : 0];
+    } else {
+#pragma unroll
+        for (int j = 0; j < KW; j++) diff |= __funnelshift_r(B[j], B[j + 1], sh) ^ ldg_u32_unaligned(r + 4 * j);
+    }
+    return diff == 0 ? enc : 0;
+}
 
 template <int KW, bool FILTER>
 __global__ void __launch_bounds__(FILTER ? PROBE_THREADS_FILTER : PROBE_THREADS_PLAIN, 1) k_probe(const ProbeArgs a) {
     constexpr int NPT = PROBE_NPT;
-    constexpr int NW = NPT / 4 + KW;  // aligned words a lane needs (the last one is only a funnel-shift partner)
-    constexpr int NV = (NW + 3) / 4;  // 128-bit loads per lane
+    constexpr int NWA = probe_words(KW);
     extern __shared__ uint32_t sFilter[];
-    const int K = KW * 4;
     const int lane = threadIdx.x & 31;
     if (FILTER) {
         const uint4* src = reinterpret_cast<const uint4*>(a.ix.filter);
@@ -311,58 +401,28 @@ __global__ void __launch_bounds__(FILTER ? PROBE_THREADS_FILTER : PROBE_THREADS_
         __syncthreads();
     }
     const uint32_t warpsTotal = gridDim.x * (blockDim.x >> 5);
-    for (uint32_t g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); g < a.b.nTiles; g += warpsTotal) {
+    const uint32_t nWork = a.workList ? *a.workCount : a.b.nTiles;
+    for (uint32_t k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); k < nWork; k += warpsTotal) {
+        const uint32_t g = a.workList ? a.workList[k] : k;
         const uint4 desc = __ldg(&a.chunkDesc[g]);
         const uint8_t* ctext = a.b.text + ((static_cast<uint64_t>(desc.y) << 32) | desc.x);  // text of the chunk start
         const uint32_t base = desc.z;    // contig-local position of the chunk start
         const uint32_t nValid = desc.w;  // positions of the contig that can start a K-mer
         const uint32_t p0 = base + lane * NPT;
 
-        uint32_t A[NV * 4];
+        uint32_t A[NWA];
         {
             const uint4* gp = reinterpret_cast<const uint4*>(ctext + lane * NPT);
 #pragma unroll
-            for (int k = 0; k < NV; k++) {
-                const uint4 v = __ldg(gp + k);
-                A[4 * k] = v.x; A[4 * k + 1] = v.y; A[4 * k + 2] = v.z; A[4 * k + 3] = v.w;
+            for (int v = 0; v < NWA / 4; v++) {
+                const uint4 x = __ldg(gp + v);
+                A[4 * v] = x.x; A[4 * v + 1] = x.y; A[4 * v + 2] = x.z; A[4 * v + 3] = x.w;
             }
         }
-        // Bit bookkeeping: filter and occupancy words store bit i at position 31 - (i & 31), so "w << (i & 31)"
-        // (one wrapping shift) brings the tested bit to bit 31 and one funnel shift appends it to a mask.
-        // pass: appended in (r, q) order, hit: appended in p order => position p sits at bit 15 - n.
         uint32_t slots[NPT];
-        uint32_t pass = 0;
-#pragma unroll
-        for (int r = 0; r < 4; r++) {
-            uint32_t V[NPT / 4 + KW - 1];
-#pragma unroll
-            for (int m = 0; m < NPT / 4 + KW - 1; m++) V[m] = r == 0 ? A[m] : __funnelshift_r(A[m], A[m + 1], 8 * r);
-#pragma unroll
-            for (int q = 0; q < NPT / 4; q++) {
-                uint32_t h = static_cast<uint32_t>(K);
-#pragma unroll
-                for (int j = 0; j < KW; j++) h = hash_step(h, V[q + j], j);
-                slots[4 * q + r] = h & a.ix.hashMask;
-                if (FILTER) {
-                    const uint32_t fi = __umulhi(h, a.ix.filterBits);
-                    pass = __funnelshift_l(sFilter[fi >> 5] << (fi & 31), pass, 1);
-                }
-            }
-        }
-        if (!FILTER) pass = 0xffffu;
-
-        uint32_t occw[NPT];
-#pragma unroll
-        for (int p = 0; p < NPT; p++) {
-            occw[p] = 0;
-            if (pass & (1u << (15 - ((p & 3) * 4 + (p >> 2))))) occw[p] = __ldg(&a.ix.occ[slots[p] >> 5]);
-        }
-        uint32_t hit = 0;
-#pragma unroll
-        for (int p = 0; p < NPT; p++) hit = __funnelshift_l(occw[p] << (slots[p] & 31), hit, 1);
+        uint32_t hit = probe_lane16<KW, FILTER>(a.ix, sFilter, A, slots);
         // positions past the last valid one never probe (position p = bit 15 - p)
-        if (p0 + NPT > nValid) hit &= p0 >= nValid ? 0u : (0xffffu << (p0 + NPT - nValid));
-        hit &= 0xffffu;
+        if (p0 + NPT > nValid) hit &= p0 >= nValid ? 0u : (0xffffu << (p0 + NPT - nValid)) & 0xffffu;
 
         uint32_t mask = 0;
         if (hit) {
@@ -372,48 +432,10 @@ __global__ void __launch_bounds__(FILTER ? PROBE_THREADS_FILTER : PROBE_THREADS_
                 const int bit = 31 - __clz(hit);
                 hit &= ~(1u << bit);
                 const int p = 15 - bit;
-                // slots[p] for a run-time p: a 4-level select tree keeps the array in registers
-                uint32_t s8[8], s4[4], s2[2];
-#pragma unroll
-                for (int k = 0; k < 8; k++) s8[k] = (p & 1) ? slots[2 * k + 1] : slots[2 * k];
-#pragma unroll
-                for (int k = 0; k < 4; k++) s4[k] = (p & 2) ? s8[2 * k + 1] : s8[2 * k];
-#pragma unroll
-                for (int k = 0; k < 2; k++) s2[k] = (p & 4) ? s4[2 * k + 1] : s4[2 * k];
-                const uint32_t slot = (p & 8) ? s2[1] : s2[0];
-                const uint32_t enc = static_cast<uint32_t>(__ldg(&a.ix.ht[slot]));
-                if (enc != 0) {
-                    const uint64_t s = decode_pos(enc, a.ix.k1ord);
-                    int cls;
-                    if (window_ok(s, K, a.ix.pos1, swStop, cls)) {
-                        // target K-mer from the lane's own registers: words A[q .. q+KW] for q = p / 4 through a
-                        // 2-level select, then one funnel shift per word (no loads)
-                        const int q = p >> 2;
-                        const uint32_t sh = static_cast<uint32_t>(p & 3) * 8;
-                        uint32_t B[KW + 1];
-#pragma unroll
-                        for (int m = 0; m <= KW; m++) {
-                            const uint32_t lo = (q & 1) ? A[m + 1] : A[m];
-                            const uint32_t hi = (q & 1) ? A[m + 3] : A[m + 2];
-                            B[m] = (q & 2) ? hi : lo;
-                        }
-                        const uint8_t* r = a.ix.ref + s;
-                        uint32_t diff = 0;
-                        if ((s & 15) == 0 && KW <= 8) {  // Exp variant with k1 >= 16: two aligned 128-bit loads
-                            const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(r));
-                            const uint4 r1 = __ldg(reinterpret_cast<const uint4*>(r) + 1);
-                            const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-                            for (int j = 0; j < KW; j++) diff |= __funnelshift_r(B[j], B[j + 1], sh) ^ rw[j < 8 ? j : 0];
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < KW; j++) diff |= __funnelshift_r(B[j], B[j + 1], sh) ^ ldg_u32_unaligned(r + 4 * j);
-                        }
-                        if (diff == 0) {
-                            a.scratchEnc[static_cast<uint64_t>(g) * PROBE_CHUNK + lane * NPT + p] = enc;
-                            mask |= 1u << p;
-                        }
-                    }
+                const uint32_t enc = verify_candidate<KW>(a.ix, A, p, select16(slots, p), swStop);
+                if (enc) {
+                    a.scratchEnc[static_cast<uint64_t>(g) * PROBE_CHUNK + lane * NPT + p] = enc;
+                    mask |= 1u << p;
                 }
             } while (hit);
         }
@@ -422,6 +444,196 @@ __global__ void __launch_bounds__(FILTER ? PROBE_THREADS_FILTER : PROBE_THREADS_
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
         if (lane == 0) a.chunkCount[g] = cnt;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Fast path for near-identical texts (the README's 1k E. coli regime): most 512-position chunks of a target
+// are byte-identical to a stretch of the reference, and probing identical bytes gives identical answers.
+//
+//   memo    (per index state) the reference buffer is probed once as if it were a text, window test off
+//           ("self-probe").  memoX has one bit per 16 reference positions: 0 = probing those 16 positions
+//           gives exactly the default answer -- one seed, at the sampled (16-aligned) position, pointing at
+//           itself; 1 = anything else (a repeat found elsewhere, an overwritten or unsampled slot).
+//   k_anchor  one LANE per chunk probes the chunk's first 16 positions in full; the first verified seed
+//           proposes the chunk's diagonal d (reference position - target position).
+//   k_clean   one WARP per chunk: if the chunk's 512 + K-1 bytes equal the reference on diagonal d, all
+//           covered memo bits are 0 and the window class is uniform, then the chunk's seeds are exactly the 32
+//           positions with (i + d) % 16 == 0 and entries (i + d) >> 4: it leaves as ONE 32-seed segment.
+//           Everything else goes to the work list of k_probe.  A chunk is only ever declared clean when the
+//           full probe would provably return the same seeds, so the seed-run list downstream is identical.
+//
+// Needs k1 == 16 (Exp variant, MBGC's only setting) and a reference buffer that has not wrapped; the host
+// falls back to the full probe of every chunk otherwise.
+// ------------------------------------------------------------------------------------------------------
+template <int KW>
+__global__ void __launch_bounds__(256) k_anchor(const ProbeArgs a) {
+    constexpr int NPT = PROBE_NPT;
+    constexpr int NWA = probe_words(KW);
+    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < a.b.nTiles; g += gridDim.x * blockDim.x) {
+        const uint4 desc = __ldg(&a.chunkDesc[g]);
+        const uint8_t* ctext = a.b.text + ((static_cast<uint64_t>(desc.y) << 32) | desc.x);
+        const uint32_t base = desc.z, nValid = desc.w;
+        uint32_t A[NWA];
+        {
+            const uint4* gp = reinterpret_cast<const uint4*>(ctext);
+#pragma unroll
+            for (int v = 0; v < NWA / 4; v++) {
+                const uint4 x = __ldg(gp + v);
+                A[4 * v] = x.x; A[4 * v + 1] = x.y; A[4 * v + 2] = x.z; A[4 * v + 3] = x.w;
+            }
+        }
+        uint32_t slots[NPT];
+        uint32_t hit = probe_lane16<KW, false>(a.ix, nullptr, A, slots);
+        if (base + NPT > nValid) hit &= base >= nValid ? 0u : (0xffffu << (base + NPT - nValid)) & 0xffffu;
+        unsigned long long an = 0;
+        if (hit) {
+            const uint64_t lock = a.b.contigLock ? a.b.contigLock[a.chunkContig[g]] : NO_LOCK;
+            const uint64_t swStop = lock != NO_LOCK ? lock : a.ix.pos1;
+            do {
+                const int bit = 31 - __clz(hit);
+                hit &= ~(1u << bit);
+                const int p = 15 - bit;
+                const uint32_t enc = verify_candidate<KW>(a.ix, A, p, select16(slots, p), swStop);
+                if (enc) {
+                    an = (static_cast<unsigned long long>(p) << 32) | enc;
+                    break;
+                }
+            } while (hit);
+        }
+        a.anchor[g] = an;
+    }
+}
+
+struct CleanArgs {
+    IndexState ix;
+    BatchDesc b;
+    const uint4* chunkDesc;
+    const uint32_t* chunkContig;
+    const unsigned long long* anchor;
+    const uint32_t* memoX;
+    const uint32_t* memoE;
+    uint64_t memoLen;
+    uint32_t* chunkCount;
+    uint16_t* seedMask;
+    uint32_t* scratchEnc;
+    uint8_t* chunkSegN;
+    uint32_t* workList;
+    uint32_t* counters;
+};
+
+constexpr int CLEAN_UNROLL = 4;  // chunks a warp has in flight (the kernel is a chain of dependent loads)
+
+__global__ void __launch_bounds__(256) k_clean(const CleanArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int K = a.ix.K;
+    const uint32_t warpsTotal = gridDim.x * (blockDim.x >> 5);
+    const uint32_t nTiles = a.b.nTiles;
+    for (uint32_t gb = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * CLEAN_UNROLL; gb < nTiles;
+         gb += warpsTotal * CLEAN_UNROLL) {
+        // round 1: descriptor, anchor (and the contig's lock, if the batch has any)
+        uint4 desc[CLEAN_UNROLL];
+        unsigned long long an[CLEAN_UNROLL];
+        uint32_t cc[CLEAN_UNROLL];
+#pragma unroll
+        for (int u = 0; u < CLEAN_UNROLL; u++) {
+            const uint32_t g = gb + u < nTiles ? gb + u : nTiles - 1;
+            desc[u] = __ldg(&a.chunkDesc[g]);
+            an[u] = a.anchor[g];
+            cc[u] = a.b.contigLock ? __ldg(&a.chunkContig[g]) : 0;
+        }
+        // round 2: everything that depends on the anchor's diagonal
+        bool ok[CLEAN_UNROLL];
+        uint32_t pin[CLEAN_UNROLL], diff[CLEAN_UNROLL], xbit[CLEAN_UNROLL], ebit[CLEAN_UNROLL];
+        int64_t r0[CLEAN_UNROLL];
+#pragma unroll
+        for (int u = 0; u < CLEAN_UNROLL; u++) {
+            const uint32_t base = desc[u].z, nValid = desc[u].w;
+            const uint32_t enc = static_cast<uint32_t>(an[u]);
+            ok[u] = gb + u < nTiles && enc != 0 && base + PROBE_CHUNK <= nValid;  // warp-uniform
+            r0[u] = static_cast<int64_t>(decode_pos(enc, a.ix.k1ord)) - static_cast<int64_t>(an[u] >> 32);
+            ok[u] = ok[u] && r0[u] >= 1 && static_cast<uint64_t>(r0[u]) + PROBE_CHUNK + K - 1 <= a.memoLen;
+            pin[u] = (16u - (static_cast<uint32_t>(r0[u]) & 15u)) & 15u;  // first position with (i + d) % 16 == 0
+            diff[u] = 0; xbit[u] = 0; ebit[u] = 0;
+            if (ok[u]) {
+                const uint64_t lock = a.b.contigLock ? __ldg(&a.b.contigLock[cc[u]]) : NO_LOCK;
+                const uint64_t swStop = lock != NO_LOCK ? lock : a.ix.pos1;
+                const uint64_t sFirst = static_cast<uint64_t>(r0[u]) + pin[u], sLast = sFirst + 31 * 16;
+                int c0, c1;
+                const bool w0 = window_ok(sFirst, K, a.ix.pos1, swStop, c0);
+                const bool w1 = window_ok(sLast, K, a.ix.pos1, swStop, c1);
+                ok[u] = w0 && w1 && c0 == c1;  // both window predicates are monotone in s: uniform class in between
+            }
+            if (ok[u]) {
+                // memo state of the group of 16 reference positions around this lane's grid position
+                // (lane 0 also answers for the partial group before the first grid position)
+                const uint64_t grp = (static_cast<uint64_t>(r0[u]) + pin[u]) / 16 + lane;
+                xbit[u] = (__ldg(&a.memoX[grp >> 5]) >> (grp & 31)) & 1u;
+                ebit[u] = (__ldg(&a.memoE[grp >> 5]) >> (grp & 31)) & 1u;
+                if (lane == 0 && pin[u]) xbit[u] |= (__ldg(&a.memoX[(grp - 1) >> 5]) >> ((grp - 1) & 31)) & 1u;
+                // 512 + K-1 bytes of text against the reference on the diagonal
+                const uint8_t* T = a.b.text + ((static_cast<uint64_t>(desc[u].y) << 32) | desc[u].x);
+                const uint8_t* R = a.ix.ref + r0[u];
+                const uint4 t = __ldg(reinterpret_cast<const uint4*>(T) + lane);
+                const uintptr_t ra = reinterpret_cast<uintptr_t>(R + 16 * lane);
+                const uint32_t* rw = reinterpret_cast<const uint32_t*>(ra & ~static_cast<uintptr_t>(3));
+                const uint32_t sh = static_cast<uint32_t>(ra & 3) * 8;
+                const uint32_t w0 = __ldg(rw), w1 = __ldg(rw + 1), w2 = __ldg(rw + 2), w3 = __ldg(rw + 3), w4 = __ldg(rw + 4);
+                diff[u] = (t.x ^ __funnelshift_r(w0, w1, sh)) | (t.y ^ __funnelshift_r(w1, w2, sh)) |
+                          (t.z ^ __funnelshift_r(w2, w3, sh)) | (t.w ^ __funnelshift_r(w3, w4, sh));
+                if (lane < (K + 2) / 4)  // the K-1 bytes the chunk's last k-mers reach past it (rounded up to words)
+                    diff[u] |= ldg_u32_unaligned(T + PROBE_CHUNK + 4 * lane) ^ ldg_u32_unaligned(R + PROBE_CHUNK + 4 * lane);
+            }
+        }
+        // round 3: verdicts
+#pragma unroll
+        for (int u = 0; u < CLEAN_UNROLL; u++) {
+            if (gb + u >= nTiles) break;
+            const uint32_t g = gb + u;
+            const bool clean = ok[u] && !__any_sync(0xffffffffu, diff[u] != 0 || xbit[u] != 0);
+            if (clean) {
+                // seeds = grid positions whose group is in the default state; maximal stretches leave as segments
+                const unsigned D = __ballot_sync(0xffffffffu, ebit[u] == 0);
+                const unsigned S = D & ~(D << 1);
+                if ((S >> lane) & 1u)
+                    a.scratchEnc[static_cast<uint64_t>(g) * PROBE_CHUNK + pin[u] + 16 * lane] =
+                        static_cast<uint32_t>((static_cast<uint64_t>(r0[u]) + pin[u]) / 16 + lane);
+                a.seedMask[static_cast<uint64_t>(g) * 32 + lane] = ebit[u] == 0 ? static_cast<uint16_t>(1u << pin[u]) : 0;
+                if (lane == 0) {
+                    a.chunkCount[g] = __popc(S);
+                    a.chunkSegN[g] = 1;
+                }
+            } else if (lane == 0) {
+                a.chunkSegN[g] = 0;
+                a.workList[atomicAdd(&a.counters[5], 1u)] = g;
+            }
+        }
+    }
+}
+
+// memo bits from a finished self-probe pass: the "text" is the reference buffer from position 0, so chunk g,
+// lane l is the group of 16 reference positions number 32 g + l.  A group is
+//   default  one seed, at the grid position, pointing at itself            (X = 0, E = 0)
+//   empty    no seed at all: its sampled k-mer lost the table slot          (X = 0, E = 1)
+//   other    anything else, or not completely probed (end of the reference) (X = 1)
+__global__ void __launch_bounds__(256) k_memo(uint32_t nTiles, uint32_t nValid, const uint16_t* __restrict__ seedMask,
+                                              const uint32_t* __restrict__ scratchEnc, uint32_t* __restrict__ memoX,
+                                              uint32_t* __restrict__ memoE) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warpsTotal = gridDim.x * (blockDim.x >> 5);
+    for (uint32_t g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); g < nTiles; g += warpsTotal) {
+        const uint32_t m = seedMask[static_cast<uint64_t>(g) * 32 + lane];
+        const uint32_t grp = g * 32 + lane;
+        const bool probed = static_cast<uint64_t>(grp) * 16 + 16 <= nValid;
+        bool def = false;
+        if (m == 1u) def = scratchEnc[static_cast<uint64_t>(g) * PROBE_CHUNK + lane * PROBE_NPT] == grp;
+        const bool empty = m == 0u;
+        const unsigned x = __ballot_sync(0xffffffffu, !probed || !(def || empty));
+        const unsigned e = __ballot_sync(0xffffffffu, empty);
+        if (lane == 0) {
+            memoX[g] = x;
+            memoE[g] = e;
+        }
     }
 }
 
@@ -458,8 +670,15 @@ __global__ void __launch_bounds__(256) k_chunk_contig(BatchDesc b, int K, uint32
 }
 
 template <int KW>
-static void launch_probe_k(const ProbeArgs& a, bool useFilter, cudaStream_t st) {
+static void launch_probe_k(const ProbeArgs& a, bool useFilter, int mode, cudaStream_t st) {
     const int sm = device_sm_count();
+    if (mode == 1) {  // anchors: one lane per chunk
+        uint32_t blocks = (a.b.nTiles + 255) / 256;
+        const uint32_t cap = static_cast<uint32_t>(sm) * 8;
+        if (blocks > cap) blocks = cap;
+        k_anchor<KW><<<blocks, 256, 0, st>>>(a);
+        return;
+    }
     if (useFilter) {
         const size_t smem = static_cast<size_t>(a.ix.filterWords) * 4;
         static bool attrSet = false;
@@ -476,22 +695,54 @@ static void launch_probe_k(const ProbeArgs& a, bool useFilter, cudaStream_t st) 
     }
 }
 
-int launch_probe(const IndexState& ix, const BatchDesc& b, const WorkBuffers& w, bool useFilter, cudaStream_t st) {
-    if (b.nTiles == 0) {
-        cudaMemsetAsync(w.tileCount, 0, sizeof(uint32_t), st);
-        return 0;
-    }
-    k_chunk_contig<<<device_sm_count() * 4, 256, 0, st>>>(b, ix.K, w.chunkContig, w.chunkDesc);
-    ProbeArgs a{ix, b, w.chunkDesc, w.chunkContig, w.tileCount, w.seedMask, w.scratchEnc};
+static int dispatch_probe(const ProbeArgs& a, bool useFilter, int mode, cudaStream_t st) {
 #define MBGC_PROBE_CASE(KK) \
-    case KK: launch_probe_k<KK / 4>(a, useFilter, st); break;
-    switch (ix.K) {
+    case KK: launch_probe_k<KK / 4>(a, useFilter, mode, st); break;
+    switch (a.ix.K) {
         MBGC_PROBE_CASE(12) MBGC_PROBE_CASE(16) MBGC_PROBE_CASE(20) MBGC_PROBE_CASE(24) MBGC_PROBE_CASE(28)
         MBGC_PROBE_CASE(32) MBGC_PROBE_CASE(36) MBGC_PROBE_CASE(40) MBGC_PROBE_CASE(44) MBGC_PROBE_CASE(56)
         default: return -1;
     }
 #undef MBGC_PROBE_CASE
-    return 2;
+    return 1;
+}
+
+int launch_chunk_desc(const IndexState& ix, const BatchDesc& b, const WorkBuffers& w, cudaStream_t st) {
+    if (b.nTiles == 0) {
+        cudaMemsetAsync(w.tileCount, 0, sizeof(uint32_t), st);
+        return 0;
+    }
+    k_chunk_contig<<<device_sm_count() * 4, 256, 0, st>>>(b, ix.K, w.chunkContig, w.chunkDesc);
+    return 1;
+}
+
+int launch_probe(const IndexState& ix, const BatchDesc& b, const WorkBuffers& w, bool useFilter, bool useWorkList,
+                 cudaStream_t st) {
+    if (b.nTiles == 0) return 0;
+    ProbeArgs a{ix, b, w.chunkDesc, w.chunkContig, w.tileCount, w.seedMask, w.scratchEnc,
+                useWorkList ? w.workList : nullptr, useWorkList ? w.counters + 5 : nullptr, w.anchor};
+    return dispatch_probe(a, useFilter, 0, st);
+}
+
+int launch_anchor(const IndexState& ix, const BatchDesc& b, const WorkBuffers& w, cudaStream_t st) {
+    if (b.nTiles == 0) return 0;
+    ProbeArgs a{ix, b, w.chunkDesc, w.chunkContig, w.tileCount, w.seedMask, w.scratchEnc, nullptr, nullptr, w.anchor};
+    return dispatch_probe(a, false, 1, st);
+}
+
+int launch_clean(const IndexState& ix, const BatchDesc& b, const WorkBuffers& w, const MemoState& memo, cudaStream_t st) {
+    if (b.nTiles == 0) return 0;
+    CleanArgs a{ix, b, w.chunkDesc, w.chunkContig, w.anchor, memo.memoX, memo.memoE, memo.memoLen, w.tileCount,
+                w.seedMask, w.scratchEnc, w.chunkSegN, w.workList, w.counters};
+    k_clean<<<device_sm_count() * 8, 256, 0, st>>>(a);
+    return 1;
+}
+
+int launch_memo(const BatchDesc& b, const WorkBuffers& w, uint32_t nValid, uint32_t* memoX, uint32_t* memoE,
+                cudaStream_t st) {
+    if (b.nTiles == 0) return 0;
+    k_memo<<<device_sm_count() * 4, 256, 0, st>>>(b.nTiles, nValid, w.seedMask, w.scratchEnc, memoX, memoE);
+    return 1;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -503,8 +754,10 @@ int launch_probe(const IndexState& ix, const BatchDesc& b, const WorkBuffers& w,
 __global__ void __launch_bounds__(256) k_compact(BatchDesc b, const uint32_t* __restrict__ chunkContig,
                                                  const uint32_t* __restrict__ chunkOff,
                                                  const uint16_t* __restrict__ seedMask,
-                                                 const uint32_t* __restrict__ scratchEnc, uint32_t* __restrict__ seedPos,
-                                                 uint32_t* __restrict__ seedEnc, uint32_t seedCap, uint32_t* counters) {
+                                                 const uint32_t* __restrict__ scratchEnc,
+                                                 const uint8_t* __restrict__ chunkSegN, uint32_t* __restrict__ seedPos,
+                                                 uint32_t* __restrict__ seedEnc, uint8_t* __restrict__ seedN,
+                                                 uint32_t seedCap, uint32_t* counters) {
     const uint32_t nSeeds = chunkOff[b.nTiles];
     if (nSeeds > seedCap) {
         if (blockIdx.x == 0 && threadIdx.x == 0) counters[3] = 1;  // overflow: host retries with more room
@@ -516,15 +769,31 @@ __global__ void __launch_bounds__(256) k_compact(BatchDesc b, const uint32_t* __
         const uint32_t o = chunkOff[g];
         if (chunkOff[g + 1] == o) continue;
         uint32_t m = seedMask[static_cast<uint64_t>(g) * 32 + lane];
-        const uint32_t c = __popc(m);
-        uint32_t k = o + warp_incl_scan(c, lane) - c;
         const uint32_t base = (g - b.tileStart[chunkContig[g]]) * PROBE_CHUNK + lane * PROBE_NPT;
         const uint64_t src = static_cast<uint64_t>(g) * PROBE_CHUNK + lane * PROBE_NPT;
+        if (chunkSegN && chunkSegN[g]) {
+            // clean chunk (k_clean): at most one seed per lane, all on one diagonal and k1 apart; every maximal
+            // stretch of lanes with a seed leaves as one segment
+            const unsigned D = __ballot_sync(0xffffffffu, m != 0);
+            const unsigned S = D & ~(D << 1);
+            if ((S >> lane) & 1u) {
+                const uint32_t k = o + __popc(S & ((1u << lane) - 1u));
+                const int p = __ffs(m) - 1;
+                seedPos[k] = base + p;
+                seedEnc[k] = scratchEnc[src + p];
+                // consecutive lanes with a seed from here on (64-bit so that 32 ones give 32)
+                seedN[k] = static_cast<uint8_t>(__ffsll(static_cast<long long>(~static_cast<unsigned long long>(D >> lane))) - 1);
+            }
+            continue;
+        }
+        const uint32_t c = __popc(m);
+        uint32_t k = o + warp_incl_scan(c, lane) - c;
         while (m) {
             const int p = __ffs(m) - 1;
             m &= m - 1;
             seedPos[k] = base + p;
             seedEnc[k] = scratchEnc[src + p];
+            seedN[k] = 1;
             k++;
         }
     }
@@ -537,7 +806,8 @@ __global__ void __launch_bounds__(256) k_compact(BatchDesc b, const uint32_t* __
 __global__ void __launch_bounds__(256) k_heads(IndexState ix, BatchDesc b, const uint32_t* __restrict__ chunkContig,
                                                const uint32_t* __restrict__ chunkOff,
                                                const uint32_t* __restrict__ seedPos, const uint32_t* __restrict__ seedEnc,
-                                               uint32_t* __restrict__ head, const uint32_t* counters) {
+                                               const uint8_t* __restrict__ seedN, uint32_t* __restrict__ head,
+                                               const uint32_t* counters) {
     if (counters[3]) return;
     const int lane = threadIdx.x & 31;
     const uint32_t warpsTotal = gridDim.x * (blockDim.x >> 5);
@@ -553,8 +823,11 @@ __global__ void __launch_bounds__(256) k_heads(IndexState ix, BatchDesc b, const
             const uint32_t j = o + k;
             uint32_t h = 1;
             if (j != contigFirst) {
-                const uint32_t e = seedEnc[j], ep = seedEnc[j - 1];
-                if (ix.k1 <= ix.K && seedPos[j] - seedPos[j - 1] == static_cast<uint32_t>(ix.k1) && e - ep == encStep) {
+                // last seed of the previous segment (a segment = seedN seeds, spacing k1, entries ascending)
+                const uint32_t nm1 = seedN[j - 1] - 1u;
+                const uint32_t e = seedEnc[j], ep = seedEnc[j - 1] + nm1 * encStep;
+                const uint32_t pp = seedPos[j - 1] + nm1 * static_cast<uint32_t>(ix.k1);
+                if (ix.k1 <= ix.K && seedPos[j] - pp == static_cast<uint32_t>(ix.k1) && e - ep == encStep) {
                     int c0, c1;
                     window_ok(decode_pos(e, ix.k1ord), ix.K, ix.pos1, swStop, c0);
                     window_ok(decode_pos(ep, ix.k1ord), ix.K, ix.pos1, swStop, c1);
@@ -587,14 +860,17 @@ __global__ void __launch_bounds__(256) k_runs(BatchDesc b, const uint32_t* __res
     }
 }
 
-int launch_compact_and_runs(const IndexState& ix, const BatchDesc& b, const WorkBuffers& w, cudaStream_t st) {
+int launch_compact_and_runs(const IndexState& ix, const BatchDesc& b, const WorkBuffers& w, bool segments,
+                            cudaStream_t st) {
     int launches = 0;
     const int sm = device_sm_count();
     // tileCount -> tileOff (in place), tileOff[nTiles] = nSeeds
     launches += scan_exclusive(w.tileCount, w.tileCount, nullptr, b.nTiles, b.nTiles, w.blockSums, nullptr, st);
-    k_compact<<<sm * 8, 256, 0, st>>>(b, w.chunkContig, w.tileCount, w.seedMask, w.scratchEnc, w.seedPos, w.seedEnc,
-                                      w.seedCap, w.counters);
-    k_heads<<<sm * 8, 256, 0, st>>>(ix, b, w.chunkContig, w.tileCount, w.seedPos, w.seedEnc, w.headScan, w.counters);
+    k_compact<<<sm * 8, 256, 0, st>>>(b, w.chunkContig, w.tileCount, w.seedMask, w.scratchEnc,
+                                      segments ? w.chunkSegN : nullptr, w.seedPos, w.seedEnc, w.seedN, w.seedCap,
+                                      w.counters);
+    k_heads<<<sm * 8, 256, 0, st>>>(ix, b, w.chunkContig, w.tileCount, w.seedPos, w.seedEnc, w.seedN, w.headScan,
+                                    w.counters);
     launches += 2;
     // head flags -> exclusive scan in place; length lives on the device (tileOff[nTiles])
     launches += scan_exclusive(w.headScan, w.headScan, w.tileCount + b.nTiles, 0, w.seedCap, w.blockSums, nullptr, st);
@@ -619,6 +895,7 @@ struct ExtendArgs {
     const uint32_t* tileOff;
     const uint32_t* seedPos;
     const uint32_t* seedEnc;
+    const uint8_t* seedN;
     const uint32_t* runFirst;
     const uint32_t* runStart;
     RunRec* runs;
@@ -640,7 +917,8 @@ __global__ void __launch_bounds__(256) k_extend(const ExtendArgs a) {
         const uint64_t swStop = lock != NO_LOCK ? lock : a.ix.pos1;
         const uint32_t j0 = a.runFirst[r], j1 = a.runFirst[r + 1];
         const uint32_t firstPos = a.seedPos[j0], enc0 = a.seedEnc[j0];
-        const uint32_t lastPos = a.seedPos[j1 - 1];
+        const uint32_t lastPos = a.seedPos[j1 - 1] + (a.seedN[j1 - 1] - 1u) * static_cast<uint32_t>(k1);
+        const uint32_t encStep = a.ix.k1ord >= 0 ? static_cast<uint32_t>(k1 >> a.ix.k1ord) : static_cast<uint32_t>(k1);
         const int64_t s0 = static_cast<int64_t>(decode_pos(enc0, a.ix.k1ord));
         const int64_t d = s0 - static_cast<int64_t>(firstPos);  // reference position = target position + d
         int cls;
@@ -651,8 +929,9 @@ __global__ void __launch_bounds__(256) k_extend(const ExtendArgs a) {
         bool leftCand = false;
         int64_t stopL = d < 0 ? -d : 0;  // target position below which nothing is compared (ref index >= 0)
         if (r > a.runStart[c]) {
-            const uint32_t pp = a.seedPos[j0 - 1];
-            const int64_t sp = static_cast<int64_t>(decode_pos(a.seedEnc[j0 - 1], a.ix.k1ord));
+            const uint32_t nm1 = a.seedN[j0 - 1] - 1u;  // last seed of the previous segment
+            const uint32_t pp = a.seedPos[j0 - 1] + nm1 * static_cast<uint32_t>(k1);
+            const int64_t sp = static_cast<int64_t>(decode_pos(a.seedEnc[j0 - 1] + nm1 * encStep, a.ix.k1ord));
             int clsP;
             window_ok(static_cast<uint64_t>(sp), K, a.ix.pos1, swStop, clsP);
             if (sp - static_cast<int64_t>(pp) == d && clsP == cls) {
@@ -741,11 +1020,11 @@ __global__ void __launch_bounds__(256) k_extend(const ExtendArgs a) {
         if (lane == 0) {
             RunRec rec;
             rec.firstPos = firstPos;
-            rec.nSeeds = j1 - j0;
+            rec.nSeeds = (lastPos - firstPos) / static_cast<uint32_t>(k1) + 1;
             rec.enc0 = enc0;
             rec.aFree = aFree;
             rec.bFree = static_cast<uint32_t>(mismR);
-            rec.flags = (leftLinked ? 1u : 0u) | (rightLinked ? 2u : 0u);
+            rec.flags = (leftLinked ? 1u : 0u) | (rightLinked ? 2u : 0u) | (static_cast<uint32_t>(c) << 2);
             a.runs[r] = rec;
         }
     }
@@ -773,7 +1052,7 @@ __global__ void __launch_bounds__(256) k_links(RunRec* __restrict__ runs, const 
 }
 
 int launch_extend(const IndexState& ix, const BatchDesc& b, const WorkBuffers& w, cudaStream_t st) {
-    ExtendArgs a{ix, b, w.tileCount, w.seedPos, w.seedEnc, w.runFirst, w.runStart, w.runs, w.counters};
+    ExtendArgs a{ix, b, w.tileCount, w.seedPos, w.seedEnc, w.seedN, w.runFirst, w.runStart, w.runs, w.counters};
     k_extend<<<device_sm_count() * 8, 256, 0, st>>>(a);
     k_links<<<device_sm_count() * 4, 256, 0, st>>>(w.runs, w.counters);
     return 2;
@@ -786,173 +1065,343 @@ int launch_extend(const IndexState& ix, const BatchDesc& b, const WorkBuffers& w
 // skipMargin, and its left edge depends on the stack of matches accepted so far (trim to the previous end,
 // or swallow the previous match when the new diagonal also covers it).  Given the run list this is pure
 // integer arithmetic: for the first seed at or after the cursor, the maximal equal interval [aFree, bFree)
-// of its run replaces every byte comparison of the reference loop.  One warp per contig: the warp stages
-// 32 run records at a time in shared memory, lane 0 replays the state machine.
+// of its run replaces every byte comparison of the reference loop.
+//
+// Parallelism: ISLANDS.  Let P be a target position that no run's equal interval contains in its interior
+// (bFree <= P for every earlier run, aFree >= P for every later one).  Then nothing crosses P: a match of an
+// earlier run ends at or before P, so the cursor (matchEnd - skipMargin, or seed + 1) is still at or before the
+// first seed after P; and a later run can neither be trimmed by nor swallow a match from before P, because its
+// left walk stops at aFree >= P >= every earlier match end (the reference's comparisons at .cpp:257-266 evaluate
+// exactly as with an empty stack).  So the runs between two such cuts -- an island -- replay independently with
+// an empty stack and cursor 0, and the contig's list is the concatenation of the islands' lists.  Cuts are where
+// prefix-max(bFree) <= suffix-min(aFree): two scans over the run list.  Every mismatch between a target and the
+// reference is a cut unless a repeat bridges it, so islands are a handful of runs; one thread replays one island.
 // ------------------------------------------------------------------------------------------------------
+constexpr int ISL_THREADS = 256;
+constexpr int ISL_ITEMS = 4;
+constexpr int ISL_TILE = ISL_THREADS * ISL_ITEMS;
+
+template <bool IS_MAX>
+__device__ __forceinline__ unsigned long long op64(unsigned long long x, unsigned long long y) {
+    return IS_MAX ? (x > y ? x : y) : (x < y ? x : y);
+}
+template <bool IS_MAX>
+__device__ __forceinline__ unsigned long long ident64() { return IS_MAX ? 0ull : ~0ull; }
+
+// inclusive scan of one value per thread over the block; *total = reduction of the whole block
+template <bool IS_MAX>
+__device__ __forceinline__ unsigned long long block_scan64(unsigned long long v, unsigned long long* sWarp,
+                                                           unsigned long long* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nWarps = blockDim.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v = op64<IS_MAX>(v, t);
+    }
+    if (lane == 31) sWarp[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned long long w = lane < nWarps ? sWarp[lane] : ident64<IS_MAX>();
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w = op64<IS_MAX>(w, t);
+        }
+        sWarp[32 + lane] = w;  // inclusive over warps
+    }
+    __syncthreads();
+    if (warp > 0) v = op64<IS_MAX>(v, sWarp[32 + warp - 1]);
+    *total = sWarp[32 + nWarps - 1];
+    __syncthreads();
+    return v;
+}
+
+// scan keys: the contig index in the high half makes one global scan behave as a per-contig scan
+__device__ __forceinline__ unsigned long long key_b(const RunRec& r) {
+    return (static_cast<unsigned long long>(r.flags >> 2) << 32) | r.bFree;
+}
+__device__ __forceinline__ unsigned long long key_a(const RunRec& r) {
+    return (static_cast<unsigned long long>(r.flags >> 2) << 32) | r.aFree;
+}
+
+// per tile: max of key_b, min of key_a
+__global__ void __launch_bounds__(ISL_THREADS) k_island_reduce(const RunRec* __restrict__ runs, const uint32_t* counters,
+                                                               unsigned long long* __restrict__ tileFwd,
+                                                               unsigned long long* __restrict__ tileBwd) {
+    if (counters[3]) return;
+    __shared__ unsigned long long sWarp[64];
+    const uint32_t nRuns = counters[1];
+    const uint32_t nTiles = (nRuns + ISL_TILE - 1) / ISL_TILE;
+    for (uint32_t t = blockIdx.x; t < nTiles; t += gridDim.x) {
+        unsigned long long mx = 0ull, mn = ~0ull;
+#pragma unroll
+        for (int k = 0; k < ISL_ITEMS; k++) {
+            const uint32_t r = t * ISL_TILE + k * ISL_THREADS + threadIdx.x;
+            if (r < nRuns) {
+                const RunRec rr = runs[r];
+                mx = op64<true>(mx, key_b(rr));
+                mn = op64<false>(mn, key_a(rr));
+            }
+        }
+        unsigned long long tot;
+        block_scan64<true>(mx, sWarp, &tot);
+        if (threadIdx.x == 0) tileFwd[t] = tot;
+        block_scan64<false>(mn, sWarp, &tot);
+        if (threadIdx.x == 0) tileBwd[t] = tot;
+    }
+}
+
+// tileFwd -> exclusive prefix max (carry into each tile); tileBwd -> exclusive suffix min
+__global__ void __launch_bounds__(1024) k_island_partials(const uint32_t* counters, unsigned long long* __restrict__ tileFwd,
+                                                          unsigned long long* __restrict__ tileBwd) {
+    if (counters[3]) return;
+    __shared__ unsigned long long sWarp[64];
+    __shared__ unsigned long long sInc[1024];
+    const uint32_t nRuns = counters[1];
+    const uint32_t nTiles = (nRuns + ISL_TILE - 1) / ISL_TILE;
+    unsigned long long carry = 0ull;
+    for (uint32_t base = 0; base < nTiles; base += blockDim.x) {
+        const uint32_t i = base + threadIdx.x;
+        unsigned long long tot;
+        sInc[threadIdx.x] = block_scan64<true>(i < nTiles ? tileFwd[i] : 0ull, sWarp, &tot);
+        __syncthreads();
+        const unsigned long long ex = threadIdx.x ? sInc[threadIdx.x - 1] : 0ull;
+        __syncthreads();
+        if (i < nTiles) tileFwd[i] = op64<true>(ex, carry);
+        carry = op64<true>(carry, tot);
+    }
+    carry = ~0ull;
+    for (uint32_t base = 0; base < nTiles; base += blockDim.x) {
+        const uint32_t q = base + threadIdx.x;  // tiles in reverse order
+        const uint32_t i = nTiles - 1 - q;
+        unsigned long long tot;
+        sInc[threadIdx.x] = block_scan64<false>(q < nTiles ? tileBwd[i] : ~0ull, sWarp, &tot);
+        __syncthreads();
+        const unsigned long long ex = threadIdx.x ? sInc[threadIdx.x - 1] : ~0ull;
+        __syncthreads();
+        if (q < nTiles) tileBwd[i] = op64<false>(ex, carry);
+        carry = op64<false>(carry, tot);
+    }
+}
+
+// isHead[r] = 1 iff run r starts an island: first run of its contig, or prefix-max(bFree) of the contig's earlier
+// runs <= suffix-min(aFree) of run r and the later ones
+__global__ void __launch_bounds__(ISL_THREADS) k_island_heads(const RunRec* __restrict__ runs, const uint32_t* counters,
+                                                              const unsigned long long* __restrict__ tileFwd,
+                                                              const unsigned long long* __restrict__ tileBwd,
+                                                              uint32_t* __restrict__ isHead) {
+    if (counters[3]) return;
+    __shared__ unsigned long long sWarp[64];
+    __shared__ unsigned long long sFwdEx[ISL_THREADS];
+    const uint32_t nRuns = counters[1];
+    const uint32_t nTiles = (nRuns + ISL_TILE - 1) / ISL_TILE;
+    for (uint32_t t = blockIdx.x; t < nTiles; t += gridDim.x) {
+        const uint32_t r0 = t * ISL_TILE + threadIdx.x * ISL_ITEMS;  // this thread's ISL_ITEMS consecutive runs
+        unsigned long long kb[ISL_ITEMS], ka[ISL_ITEMS];
+        uint32_t contig[ISL_ITEMS];
+#pragma unroll
+        for (int k = 0; k < ISL_ITEMS; k++) {
+            kb[k] = 0ull; ka[k] = ~0ull; contig[k] = 0;
+            if (r0 + k < nRuns) {
+                const RunRec rr = runs[r0 + k];
+                kb[k] = key_b(rr); ka[k] = key_a(rr); contig[k] = rr.flags >> 2;
+            }
+        }
+        // forward: exclusive prefix max
+        unsigned long long loc = 0ull;
+#pragma unroll
+        for (int k = 0; k < ISL_ITEMS; k++) loc = op64<true>(loc, kb[k]);
+        unsigned long long tot;
+        const unsigned long long inc = block_scan64<true>(loc, sWarp, &tot);
+        sFwdEx[threadIdx.x] = inc;
+        __syncthreads();
+        unsigned long long run = op64<true>(threadIdx.x ? sFwdEx[threadIdx.x - 1] : 0ull, tileFwd[t]);
+        __syncthreads();
+        unsigned long long fwdEx[ISL_ITEMS];
+#pragma unroll
+        for (int k = 0; k < ISL_ITEMS; k++) {
+            fwdEx[k] = run;
+            run = op64<true>(run, kb[k]);
+        }
+        // backward: inclusive suffix min (threads scanned in reverse order)
+        loc = ~0ull;
+#pragma unroll
+        for (int k = 0; k < ISL_ITEMS; k++) loc = op64<false>(loc, ka[k]);
+        // reverse the thread order through shared memory, scan, reverse back
+        sFwdEx[ISL_THREADS - 1 - threadIdx.x] = loc;
+        __syncthreads();
+        const unsigned long long rev = sFwdEx[threadIdx.x];
+        __syncthreads();
+        const unsigned long long incR = block_scan64<false>(rev, sWarp, &tot);
+        sFwdEx[threadIdx.x] = incR;  // inclusive over reversed threads 0..x
+        __syncthreads();
+        // this thread (reversed index q = ISL_THREADS-1-threadIdx.x): min over the threads after it = inclusive at q-1
+        const int q = ISL_THREADS - 1 - threadIdx.x;
+        unsigned long long after = op64<false>(q ? sFwdEx[q - 1] : ~0ull, tileBwd[t]);
+        __syncthreads();
+#pragma unroll
+        for (int k = ISL_ITEMS - 1; k >= 0; k--) {
+            after = op64<false>(after, ka[k]);  // inclusive suffix min at run r0 + k
+            if (r0 + k < nRuns) {
+                const bool head = static_cast<uint32_t>(fwdEx[k] >> 32) != contig[k] || (fwdEx[k] >> 32) != (after >> 32) ||
+                                  static_cast<uint32_t>(fwdEx[k]) <= static_cast<uint32_t>(after);
+                isHead[r0 + k] = head ? 1u : 0u;
+            }
+        }
+    }
+}
+
 struct ResolveArgs {
     IndexState ix;
     BatchDesc b;
     const RunRec* runs;
     const uint32_t* runStart;
+    const uint32_t* isHead;
     MatchRec* matches;
-    uint32_t* matchCount;
+    uint32_t* matchCountRun;  // [nRuns+1] matches of the island starting at this run (0 for other runs)
     const uint32_t* counters;
     uint32_t minMatchLength;
 };
-
-constexpr int RESOLVE_WARPS = 4;
 
 __device__ __forceinline__ int64_t max3(int64_t a, int64_t b, int64_t c) {
     const int64_t m = a > b ? a : b;
     return m > c ? m : c;
 }
 
-__global__ void __launch_bounds__(RESOLVE_WARPS * 32) k_resolve(const ResolveArgs a) {
+__global__ void __launch_bounds__(128) k_resolve(const ResolveArgs a) {
     if (a.counters[3]) return;
-    __shared__ RunRec sRuns[RESOLVE_WARPS][32];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int warpsTotal = gridDim.x * RESOLVE_WARPS;
+    const uint32_t nRuns = a.counters[1];
     const int K = a.ix.K, k1 = a.ix.k1, M = a.ix.skipMargin;
+    const bool k1Pow2 = (k1 & (k1 - 1)) == 0;
+    const int k1Shift = 31 - __clz(k1);
     const int64_t OVERLAP_MATCH_MAX_LENGTH = 1 << 13;  // SlidingWindowSparseEMMatcher.h:18
-    for (int c = blockIdx.x * RESOLVE_WARPS + wib; c < a.b.nContigs; c += warpsTotal) {
-        const uint32_t rs = a.runStart[c], re = a.runStart[c + 1];
+    const int64_t pos1 = static_cast<int64_t>(a.ix.pos1);
+    const int64_t refLen = static_cast<int64_t>(a.ix.refLen);
+    for (uint32_t rs = blockIdx.x * blockDim.x + threadIdx.x; rs < nRuns; rs += gridDim.x * blockDim.x) {
+        if (!a.isHead[rs]) {
+            a.matchCountRun[rs] = 0;
+            continue;
+        }
+        uint32_t re = rs + 1;  // island = runs [rs, re)
+        while (re < nRuns && !a.isHead[re]) re++;
+        const uint32_t c = a.runs[rs].flags >> 2;
         const uint64_t lock = a.b.contigLock ? a.b.contigLock[c] : NO_LOCK;
-        const int64_t pos1 = static_cast<int64_t>(a.ix.pos1);
         const int64_t swStop = lock != NO_LOCK ? static_cast<int64_t>(lock) : pos1;
-        const int64_t refLen = static_cast<int64_t>(a.ix.refLen);
         MatchRec* out = a.matches + rs;
         MatchRec top;  // = out[nOut - 1], kept in registers: the common case never re-reads global memory
         top.src = 0; top.dst = 0; top.len = 0;
         uint32_t nOut = 0;
         int64_t cur = 0;
-        for (uint32_t base = rs; base < re; base += 32) {
-            if (base + lane < re) sRuns[wib][lane] = a.runs[base + lane];
-            __syncwarp();
-            if (lane == 0) {
-                const uint32_t cnt = re - base < 32 ? re - base : 32;
-                for (uint32_t k = 0; k < cnt; k++) {
-                    const RunRec run = sRuns[wib][k];
-                    const int64_t aRes = run.aFree;  // link chains already resolved by k_links
-                    const int64_t firstPos = run.firstPos;
-                    const int64_t lastPos = firstPos + static_cast<int64_t>(run.nSeeds - 1) * k1;
-                    int64_t bRes = -1;
-                    while (lastPos >= cur) {
-                        int64_t i = firstPos;
-                        if (cur > i) i += ((cur - i + k1 - 1) / k1) * k1;
-                        const int64_t s = static_cast<int64_t>(decode_pos(run.enc0, a.ix.k1ord)) + (i - firstPos);
-                        const int64_t d = s - i;
-                        bRes = run.bFree;
-                        const bool endsBefore = s + K < pos1;
-                        const bool startsBefore = s < swStop;
-                        const int64_t hi = endsBefore ? pos1 : refLen;  // tmpEnd1
-                        const int64_t lo = startsBefore ? 0 : swStop;   // tmpStart1
-                        int64_t right1 = bRes + d;
-                        if (hi < right1) right1 = hi;
+        for (uint32_t r = rs; r < re; r++) {
+            const RunRec run = a.runs[r];
+            const int64_t aRes = run.aFree;  // link chains already resolved by k_links
+            const int64_t firstPos = run.firstPos;
+            const int64_t lastPos = firstPos + static_cast<int64_t>(run.nSeeds - 1) * k1;
+            while (lastPos >= cur) {
+                int64_t i = firstPos;
+                if (cur > i) {  // first seed of the run at or after the cursor (32-bit math: targets are < 4 GiB)
+                    const uint32_t gap = static_cast<uint32_t>(cur - i) + static_cast<uint32_t>(k1) - 1;
+                    i += k1Pow2 ? ((gap >> k1Shift) << k1Shift) : (gap / static_cast<uint32_t>(k1)) * static_cast<uint32_t>(k1);
+                }
+                const int64_t s = static_cast<int64_t>(decode_pos(run.enc0, a.ix.k1ord)) + (i - firstPos);
+                const int64_t d = s - i;
+                const bool endsBefore = s + K < pos1;
+                const bool startsBefore = s < swStop;
+                const int64_t hi = endsBefore ? pos1 : refLen;  // tmpEnd1
+                const int64_t lo = startsBefore ? 0 : swStop;   // tmpStart1
+                int64_t right1 = static_cast<int64_t>(run.bFree) + d;
+                if (hi < right1) right1 = hi;
 
-                        // left edge with overlap resolution (.cpp:251-291); p2 = inclusive matched cursor,
-                        // e = exclusive cursor (the reference's final p2)
-                        int64_t p2 = i, e = 0;
-                        uint32_t idx = nOut;
-                        bool broke = false;
-                        while (idx > 0) {
-                            const MatchRec last = idx == nOut ? top : out[idx - 1];
-                            const int64_t lastDst = last.dst, lastEnd = lastDst + last.len;
-                            if (lastEnd < p2) {
-                                const int64_t stop = max3(aRes - 1, lo - d, lastEnd - 1);
-                                if (stop > lastEnd - 1) {
-                                    e = stop;
-                                    broke = true;
-                                    break;
-                                }
-                                p2 = lastEnd;
-                            }
-                            const int64_t lastDelta = p2 - lastDst;
-                            if ((p2 + d) - lo < lastDelta || static_cast<int64_t>(last.len) > OVERLAP_MATCH_MAX_LENGTH ||
-                                aRes > lastDst) {
-                                e = p2 - 1;
-                                broke = true;
-                                break;
-                            }
-                            p2 = lastDst;
-                            idx--;
+                // left edge with overlap resolution (.cpp:251-291); p2 = inclusive matched cursor,
+                // e = exclusive cursor (the reference's final p2)
+                int64_t p2 = i, e = 0;
+                uint32_t idx = nOut;
+                bool broke = false;
+                while (idx > 0) {
+                    const MatchRec last = idx == nOut ? top : out[idx - 1];
+                    const int64_t lastDst = last.dst, lastEnd = lastDst + last.len;
+                    if (lastEnd < p2) {
+                        const int64_t stop = max3(aRes - 1, lo - d, lastEnd - 1);
+                        if (stop > lastEnd - 1) {
+                            e = stop;
+                            broke = true;
+                            break;
                         }
-                        if (!broke) {
-                            e = max3(aRes - 1, lo - d, -1);
-                        } else {
-                            const MatchRec keep = idx == nOut ? top : out[idx - 1];
-                            const int64_t overlap = static_cast<int64_t>(keep.dst) + keep.len - (e + 1);
-                            if (overlap > 0) e += overlap;
-                        }
-                        const int64_t len = right1 - (e + d) - 1;
-                        if (len >= static_cast<int64_t>(a.minMatchLength) && idx < re - rs) {
-                            nOut = idx;
-                            MatchRec mr;
-                            mr.src = static_cast<uint64_t>(e + d + 1);
-                            mr.dst = static_cast<uint32_t>(e + 1);
-                            mr.len = static_cast<uint32_t>(len);
-                            out[nOut++] = mr;
-                            top = mr;
-                            int64_t skip = (e + 1 + len) - i;
-                            skip -= skip > M ? M : skip;
-                            cur = i + (skip ? skip : 1);
-                        } else {
-                            cur = i + 1;
-                        }
+                        p2 = lastEnd;
                     }
+                    const int64_t lastDelta = p2 - lastDst;
+                    if ((p2 + d) - lo < lastDelta || static_cast<int64_t>(last.len) > OVERLAP_MATCH_MAX_LENGTH ||
+                        aRes > lastDst) {
+                        e = p2 - 1;
+                        broke = true;
+                        break;
+                    }
+                    p2 = lastDst;
+                    idx--;
+                }
+                if (!broke) {
+                    e = max3(aRes - 1, lo - d, -1);
+                } else {
+                    const MatchRec keep = idx == nOut ? top : out[idx - 1];
+                    const int64_t overlap = static_cast<int64_t>(keep.dst) + keep.len - (e + 1);
+                    if (overlap > 0) e += overlap;
+                }
+                const int64_t len = right1 - (e + d) - 1;
+                if (len >= static_cast<int64_t>(a.minMatchLength) && idx < re - rs) {
+                    nOut = idx;
+                    MatchRec mr;
+                    mr.src = static_cast<uint64_t>(e + d + 1);
+                    mr.dst = static_cast<uint32_t>(e + 1);
+                    mr.len = static_cast<uint32_t>(len);
+                    out[nOut++] = mr;
+                    top = mr;
+                    int64_t skip = (e + 1 + len) - i;
+                    skip -= skip > M ? M : skip;
+                    cur = i + (skip ? skip : 1);
+                } else {
+                    cur = i + 1;
                 }
             }
-            __syncwarp();
         }
-        if (lane == 0) a.matchCount[c] = nOut;
+        a.matchCountRun[rs] = nOut;
     }
 }
 
-// matchOff = exclusive scan of matchCount (single block: nContigs is small next to the seed counts)
-__global__ void __launch_bounds__(SCAN_THREADS) k_match_offsets(const uint32_t* __restrict__ matchCount,
-                                                                uint32_t* __restrict__ matchOff, int nContigs,
-                                                                uint32_t* counters) {
-    __shared__ uint32_t sWarp[33];
-    uint32_t carry = 0;
-    for (int base = 0; base < nContigs; base += SCAN_THREADS) {
-        const int i = base + threadIdx.x;
-        const uint32_t v = i < nContigs ? matchCount[i] : 0;
-        uint32_t total;
-        const uint32_t ex = block_excl_scan(v, &total, sWarp);
-        if (i < nContigs) matchOff[i] = ex + carry;
-        carry += total;
-    }
-    if (threadIdx.x == 0) {
-        matchOff[nContigs] = carry;
-        counters[2] = carry;
-    }
-}
-
-__global__ void __launch_bounds__(256) k_gather(const MatchRec* __restrict__ matches, const uint32_t* __restrict__ runStart,
-                                                const uint32_t* __restrict__ matchOff, MatchRec* __restrict__ dense,
-                                                int nContigs, const uint32_t* counters) {
+// island lists -> one dense list; matchOffRun = exclusive scan of matchCountRun (matchOffRun[nRuns] = total)
+__global__ void __launch_bounds__(256) k_gather(const MatchRec* __restrict__ matches, const uint32_t* __restrict__ isHead,
+                                                const uint32_t* __restrict__ matchOffRun,
+                                                const uint32_t* __restrict__ runStart, MatchRec* __restrict__ dense,
+                                                uint32_t* __restrict__ matchOff, int nContigs, uint32_t* counters) {
     if (counters[3]) return;
-    const int lane = threadIdx.x & 31;
-    const int warpsTotal = gridDim.x * (blockDim.x >> 5);
-    for (int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); c < nContigs; c += warpsTotal) {
-        const uint32_t n = matchOff[c + 1] - matchOff[c];
-        const MatchRec* src = matches + runStart[c];
-        MatchRec* dst = dense + matchOff[c];
-        for (uint32_t k = lane; k < n; k += 32) dst[k] = src[k];
+    const uint32_t nRuns = counters[1];
+    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+    for (uint32_t r = gtid; r < nRuns; r += gsz) {
+        if (!isHead[r]) continue;
+        const uint32_t o = matchOffRun[r], n = matchOffRun[r + 1] - o;
+        for (uint32_t k = 0; k < n; k++) dense[o + k] = matches[r + k];
     }
+    for (uint32_t c = gtid; c <= static_cast<uint32_t>(nContigs); c += gsz) matchOff[c] = matchOffRun[runStart[c]];
+    if (gtid == 0) counters[2] = matchOffRun[nRuns];
 }
 
 int launch_resolve(const IndexState& ix, const BatchDesc& b, const WorkBuffers& w, uint32_t minMatchLength,
                    cudaStream_t st) {
-    ResolveArgs a{ix, b, w.runs, w.runStart, w.matches, w.matchCount, w.counters, minMatchLength};
-    int blocks = (b.nContigs + RESOLVE_WARPS - 1) / RESOLVE_WARPS;
-    const int cap = device_sm_count() * 8;
-    if (blocks > cap) blocks = cap;
-    if (blocks < 1) blocks = 1;
-    k_resolve<<<blocks, RESOLVE_WARPS * 32, 0, st>>>(a);
-    k_match_offsets<<<1, SCAN_THREADS, 0, st>>>(w.matchCount, w.matchOff, b.nContigs, w.counters);
-    k_gather<<<device_sm_count() * 4, 256, 0, st>>>(w.matches, w.runStart, w.matchOff, w.matchesDense, b.nContigs,
-                                                    w.counters);
-    return 3;
+    const int sm = device_sm_count();
+    int launches = 0;
+    // islands: headScan (free after k_runs) takes the island-head flags, blockSums-sized u64 temporaries the tile carries
+    k_island_reduce<<<sm * 4, ISL_THREADS, 0, st>>>(w.runs, w.counters, w.islandFwd, w.islandBwd);
+    k_island_partials<<<1, 1024, 0, st>>>(w.counters, w.islandFwd, w.islandBwd);
+    k_island_heads<<<sm * 4, ISL_THREADS, 0, st>>>(w.runs, w.counters, w.islandFwd, w.islandBwd, w.headScan);
+    launches += 3;
+    // runFirst (free after k_extend) takes the per-island match counts, then their exclusive scan
+    ResolveArgs a{ix, b, w.runs, w.runStart, w.headScan, w.matches, w.runFirst, w.counters, minMatchLength};
+    k_resolve<<<sm * 16, 128, 0, st>>>(a);
+    launches += 1;
+    launches += scan_exclusive(w.runFirst, w.runFirst, w.counters + 1, 0, w.seedCap, w.blockSums, nullptr, st);
+    k_gather<<<sm * 8, 256, 0, st>>>(w.matches, w.headScan, w.runFirst, w.runStart, w.matchesDense, w.matchOff,
+                                     b.nContigs, w.counters);
+    launches += 1;
+    return launches;
 }
 
 }  // namespace mbgc_b200

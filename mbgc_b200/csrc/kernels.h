@@ -63,23 +63,28 @@ struct BatchDesc {       // device pointers describing the texts of one pass
 };
 
 struct WorkBuffers {     // device scratch of one pass
-    uint32_t* tileCount;     // [nChunks+1] seeds per chunk -> exclusive scan in place (chunk offsets)
+    uint32_t* tileCount;     // [nChunks+1] seed segments per chunk -> exclusive scan in place (chunk offsets)
     uint32_t* chunkContig;   // [nChunks]
+    unsigned long long* anchor;  // [nChunks] first verified seed among the first 16 positions: (pos in chunk << 32) | entry
+    uint8_t* chunkSegN;      // [nChunks] 1 = clean chunk (its entries are segments of k1-spaced seeds), 0 = plain seeds
+    uint32_t* workList;      // [nChunks] chunks that need the full probe (fast path only)
     uint4* chunkDesc;        // [nChunks] text offset lo/hi, contig-local base position, nValid
     uint16_t* seedMask;      // [nChunks*32] per-lane 16-bit seed masks
     uint32_t* scratchEnc;    // [nChunks*PROBE_CHUNK] position-indexed table entries of the seeds
-    uint32_t* seedPos;       // [seedCap]
-    uint32_t* seedEnc;       // [seedCap]
-    uint32_t* headScan;      // [seedCap+1]
-    uint32_t* runFirst;      // [seedCap+1]
+    uint32_t* seedPos;       // [seedCap] first target position of the segment
+    uint32_t* seedEnc;       // [seedCap] table entry of its first seed
+    uint8_t* seedN;          // [seedCap] seeds in the segment (spacing k1, entries ascending by k1 >> k1ord)
+    uint32_t* headScan;      // [seedCap+2] run-head flags -> scan; later the island-head flag of every run
+    uint32_t* runFirst;      // [seedCap+2] first segment of every run; later matches per island -> scan
     RunRec* runs;            // [seedCap]
     uint32_t* runStart;      // [nContigs+1]
     MatchRec* matches;       // [seedCap] per-contig regions at runStart[c]
-    uint32_t* matchCount;    // [nContigs+1] -> exclusive scan (matchOff) in matchOff
+    unsigned long long* islandFwd;  // [seedCap/1024+2] per-tile carries of the island scans
+    unsigned long long* islandBwd;
     uint32_t* matchOff;      // [nContigs+1]
     MatchRec* matchesDense;  // [seedCap]
     uint32_t* blockSums;     // scan temporaries
-    uint32_t* counters;      // [8]: 0 nSeeds, 1 nRuns, 2 nMatches, 3 overflow flag
+    uint32_t* counters;      // [8]: 0 nSegments, 1 nRuns, 2 nMatches, 3 overflow flag, 5 work-list length
     uint32_t seedCap;
 };
 
@@ -95,8 +100,24 @@ void launch_table_low32(const unsigned long long* ht, uint32_t* out, uint64_t n,
 
 // ---- match pass ----
 // returns the number of kernel launches issued
-int launch_probe(const IndexState& ix, const BatchDesc& b, const WorkBuffers& w, bool useFilter, cudaStream_t st);
-int launch_compact_and_runs(const IndexState& ix, const BatchDesc& b, const WorkBuffers& w, cudaStream_t st);
+int launch_chunk_desc(const IndexState& ix, const BatchDesc& b, const WorkBuffers& w, cudaStream_t st);
+// full probe of every chunk (useWorkList = false) or of the chunks the fast path could not prove clean
+int launch_probe(const IndexState& ix, const BatchDesc& b, const WorkBuffers& w, bool useFilter, bool useWorkList,
+                 cudaStream_t st);
+// fast path for near-identical texts (needs the self-probe memo of the reference, see kernels.cu):
+// anchors (first 16 positions of every chunk) + clean-chunk test; fills the work list for launch_probe
+struct MemoState {
+    const uint32_t* memoX;   // 1 bit per 16 reference positions: 1 = probing them gives something unusual
+    const uint32_t* memoE;   // 1 = probing them gives no seed at all (the sampled k-mer lost its table slot)
+    uint64_t memoLen;        // reference positions [0, memoLen) are covered
+};
+int launch_anchor(const IndexState& ix, const BatchDesc& b, const WorkBuffers& w, cudaStream_t st);
+int launch_clean(const IndexState& ix, const BatchDesc& b, const WorkBuffers& w, const MemoState& memo, cudaStream_t st);
+// memo from a finished self-probe pass (the reference buffer probed as a text, window test disabled)
+int launch_memo(const BatchDesc& b, const WorkBuffers& w, uint32_t nValid, uint32_t* memoX, uint32_t* memoE,
+                cudaStream_t st);
+int launch_compact_and_runs(const IndexState& ix, const BatchDesc& b, const WorkBuffers& w, bool segments,
+                            cudaStream_t st);
 int launch_extend(const IndexState& ix, const BatchDesc& b, const WorkBuffers& w, cudaStream_t st);
 int launch_resolve(const IndexState& ix, const BatchDesc& b, const WorkBuffers& w, uint32_t minMatchLength,
                    cudaStream_t st);

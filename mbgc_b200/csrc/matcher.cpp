@@ -17,6 +17,7 @@ namespace {
 constexpr uint64_t PAD = 64;            // padding before/after device buffers (unaligned loads may over-read)
 constexpr uint64_t TEXT_GAP = 64;       // bytes between texts of a batch
 constexpr uint64_t TEXT_TAIL = 8192;    // readable bytes after the last text (tile staging over-reads)
+constexpr uint64_t REF_TAIL = 8192;     // same after the reference buffer (the self-probe reads it as a text)
 
 inline uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
 
@@ -113,8 +114,8 @@ B200SparseEMMatcher::B200SparseEMMatcher(uint64_t refLengthLimit, uint32_t targe
     if (!hostRef) throw MatcherError(MBGCG_E_NOMEM, "host mirror allocation failed");
     check(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate");
     for (auto& e : ev) check(cudaEventCreate(&e), "cudaEventCreate");
-    check(cudaMalloc(&dRefAlloc, maxRefLength + 2 * PAD), "cudaMalloc(ref)");
-    check(cudaMemsetAsync(dRefAlloc, 0, maxRefLength + 2 * PAD, stream), "memset(ref)");
+    check(cudaMalloc(&dRefAlloc, maxRefLength + PAD + REF_TAIL), "cudaMalloc(ref)");
+    check(cudaMemsetAsync(dRefAlloc, 0, maxRefLength + PAD + REF_TAIL, stream), "memset(ref)");
     dRef = dRefAlloc + PAD;
     check(cudaMalloc(&dHt, static_cast<uint64_t>(hashSize) * sizeof(unsigned long long)), "cudaMalloc(table)");
     check(cudaMemsetAsync(dHt, 0, static_cast<uint64_t>(hashSize) * sizeof(unsigned long long), stream), "memset(table)");
@@ -132,6 +133,7 @@ B200SparseEMMatcher::~B200SparseEMMatcher() {
     cudaFree(dHt);
     cudaFree(dOcc);
     cudaFree(dFilter);
+    cudaFree(dMemoX);
     cudaFree(dText);
     cudaFree(dMeta);
     cudaFree(dWork);
@@ -163,6 +165,7 @@ void B200SparseEMMatcher::indexPass() {
     if (insertSeq + n >= (1ull << 32))
         throw MatcherError(MBGCG_E_UNSUPPORTED, "more than 2^32 index samples over the life of one matcher");
     insertSeq += n;
+    passesSinceInsert = 0;
     launch_index_insert(dRef, dHt, dOcc, dFilter, PROBE_FILTER_BITS, hashSize - 1, K, k1, k1ord, r0, r1, stream);
     totalLaunches++;
     check(cudaGetLastError(), "index_insert launch");
@@ -304,17 +307,22 @@ void B200SparseEMMatcher::ensureWork(uint64_t textBytes, uint32_t nTiles, int nC
     const uint64_t scratchN = static_cast<uint64_t>(nTiles) * PROBE_CHUNK;
     const uint64_t oTileCount = carve((static_cast<uint64_t>(nTiles) + 2) * 4);
     const uint64_t oChunkContig = carve((static_cast<uint64_t>(nTiles) + 2) * 4);
+    const uint64_t oAnchor = carve((static_cast<uint64_t>(nTiles) + 2) * 8);
+    const uint64_t oChunkSegN = carve(static_cast<uint64_t>(nTiles) + 64);
+    const uint64_t oWorkList = carve((static_cast<uint64_t>(nTiles) + 2) * 4);
     const uint64_t oChunkDesc = carve((static_cast<uint64_t>(nTiles) + 2) * 16);
     const uint64_t oSeedMask = carve((static_cast<uint64_t>(nTiles) + 1) * 32 * 2);
     const uint64_t oScratchEnc = carve(scratchN * 4);
     const uint64_t oSeedPos = carve(static_cast<uint64_t>(seedCap) * 4);
     const uint64_t oSeedEnc = carve(static_cast<uint64_t>(seedCap) * 4);
+    const uint64_t oSeedN = carve(static_cast<uint64_t>(seedCap) + 64);
     const uint64_t oHeadScan = carve((static_cast<uint64_t>(seedCap) + 2) * 4);
     const uint64_t oRunFirst = carve((static_cast<uint64_t>(seedCap) + 2) * 4);
     const uint64_t oRuns = carve(static_cast<uint64_t>(seedCap) * sizeof(RunRec));
     const uint64_t oRunStart = carve((static_cast<uint64_t>(nContigs) + 2) * 4);
     const uint64_t oMatches = carve(static_cast<uint64_t>(seedCap) * sizeof(MatchRec));
-    const uint64_t oMatchCount = carve((static_cast<uint64_t>(nContigs) + 2) * 4);
+    const uint64_t oIslandFwd = carve((static_cast<uint64_t>(seedCap) / 1024 + 4) * 8);
+    const uint64_t oIslandBwd = carve((static_cast<uint64_t>(seedCap) / 1024 + 4) * 8);
     const uint64_t oMatchOff = carve((static_cast<uint64_t>(nContigs) + 2) * 4);
     const uint64_t oDense = carve(static_cast<uint64_t>(seedCap) * sizeof(MatchRec));
     const uint64_t nScan = std::max<uint64_t>(nTiles, seedCap);
@@ -330,22 +338,123 @@ void B200SparseEMMatcher::ensureWork(uint64_t textBytes, uint32_t nTiles, int nC
     }
     wb.tileCount = reinterpret_cast<uint32_t*>(dWork + oTileCount);
     wb.chunkContig = reinterpret_cast<uint32_t*>(dWork + oChunkContig);
+    wb.anchor = reinterpret_cast<unsigned long long*>(dWork + oAnchor);
+    wb.chunkSegN = dWork + oChunkSegN;
+    wb.workList = reinterpret_cast<uint32_t*>(dWork + oWorkList);
     wb.chunkDesc = reinterpret_cast<uint4*>(dWork + oChunkDesc);
     wb.seedMask = reinterpret_cast<uint16_t*>(dWork + oSeedMask);
     wb.scratchEnc = reinterpret_cast<uint32_t*>(dWork + oScratchEnc);
     wb.seedPos = reinterpret_cast<uint32_t*>(dWork + oSeedPos);
     wb.seedEnc = reinterpret_cast<uint32_t*>(dWork + oSeedEnc);
+    wb.seedN = dWork + oSeedN;
     wb.headScan = reinterpret_cast<uint32_t*>(dWork + oHeadScan);
     wb.runFirst = reinterpret_cast<uint32_t*>(dWork + oRunFirst);
     wb.runs = reinterpret_cast<RunRec*>(dWork + oRuns);
     wb.runStart = reinterpret_cast<uint32_t*>(dWork + oRunStart);
     wb.matches = reinterpret_cast<MatchRec*>(dWork + oMatches);
-    wb.matchCount = reinterpret_cast<uint32_t*>(dWork + oMatchCount);
+    wb.islandFwd = reinterpret_cast<unsigned long long*>(dWork + oIslandFwd);
+    wb.islandBwd = reinterpret_cast<unsigned long long*>(dWork + oIslandBwd);
     wb.matchOff = reinterpret_cast<uint32_t*>(dWork + oMatchOff);
     wb.matchesDense = reinterpret_cast<MatchRec*>(dWork + oDense);
     wb.blockSums = reinterpret_cast<uint32_t*>(dWork + oBlockSums);
     wb.counters = reinterpret_cast<uint32_t*>(dWork + oCounters);
     wb.seedCap = seedCap;
+}
+
+void B200SparseEMMatcher::fillIndexState(IndexState& ix) const {
+    ix.ref = dRef;
+    ix.ht = dHt;
+    ix.occ = dOcc;
+    ix.filter = dFilter;
+    ix.filterBits = PROBE_FILTER_BITS;
+    ix.filterWords = PROBE_FILTER_BYTES / 4;
+    ix.hashMask = hashSize - 1;
+    ix.K = K;
+    ix.k1 = k1;
+    ix.k1ord = k1ord;
+    ix.skipMargin = skipMargin;
+    ix.pos1 = static_cast<uint64_t>(pos1);
+    ix.refLen = getRefLength();
+}
+
+// Fast-path policy (kernels.cu, "Fast path for near-identical texts").  The memo costs one full probe of the
+// loaded reference and pays back over the clean chunks of every pass until the index changes again, so it is
+// (re)built when  loaded reference <= expected clean fraction x positions of this pass x passes the index has
+// already stayed unchanged.  The clean fraction is measured by the fast path itself when it runs and estimated
+// from the match lists (share of the text covered by matches >= 1024) when it does not.
+bool B200SparseEMMatcher::wantMemo(uint64_t positions) {
+    // MBGC_B200_FASTPATH = 0: never, 1: whenever it is applicable (tests), unset: the cost model below
+    const char* env = std::getenv("MBGC_B200_FASTPATH");
+    const int forced = env ? std::atoi(env) : -1;
+    if (forced == 0 || k1 != 16 || k1ord != 4 || K < 16 || reachedRefLengthCount != 0) return false;
+    if (pos1 <= static_cast<int64_t>(K) || static_cast<uint64_t>(pos1) >= (1ull << 32) - 65536) return false;
+    if (forced == 1) return true;
+    if (cleanEstimate < 0.05) return false;
+    if (memoSeq == insertSeq) return true;
+    const double benefit = cleanEstimate * static_cast<double>(positions) *
+                           static_cast<double>(std::max<uint64_t>(1, passesSinceInsert));
+    return static_cast<double>(pos1) <= benefit;
+}
+
+// self-probe: the loaded reference [0, pos1) probed as one text against its own index, window test disabled
+void B200SparseEMMatcher::buildMemo() {
+    const uint64_t len = static_cast<uint64_t>(pos1);
+    const uint64_t nValid = len - K + 1;
+    const uint32_t tiles = static_cast<uint32_t>((nValid + PROBE_CHUNK - 1) / PROBE_CHUNK);
+    const uint64_t words = static_cast<uint64_t>(tiles) + 8;
+    if (words > memoCapWords) {
+        cudaFree(dMemoX);
+        dMemoX = nullptr;
+        memoCapWords = 0;
+        check(cudaMalloc(&dMemoX, (words + words / 4) * 8), "cudaMalloc(memo)");  // X words, then E words
+        memoCapWords = words + words / 4;
+    }
+    uint32_t* dMemoE = dMemoX + memoCapWords;
+    ensureWork(0, tiles, 1, 1024);
+    uint64_t* hOff = reinterpret_cast<uint64_t*>(hMeta);
+    uint64_t* hLock = hOff + 1;
+    uint32_t* hLen = reinterpret_cast<uint32_t*>(hLock + 1);
+    uint32_t* hTile = hLen + 1;
+    hOff[0] = 0;
+    hLock[0] = NO_LOCK;
+    hLen[0] = static_cast<uint32_t>(len);
+    hTile[0] = 0;
+    hTile[1] = tiles;
+    check(cudaEventRecord(ev[10], stream), "event");
+    check(cudaMemcpyAsync(dMeta, hMeta, 28, cudaMemcpyHostToDevice, stream), "H2D(meta)");
+    check(cudaMemsetAsync(dMemoX, 0xFF, memoCapWords * 8, stream), "memset(memo)");
+    BatchDesc bd;
+    bd.text = dRef;
+    bd.contigOff = reinterpret_cast<const uint64_t*>(dMeta);
+    bd.contigLock = bd.contigOff + 1;
+    bd.contigLen = reinterpret_cast<const uint32_t*>(bd.contigLock + 1);
+    bd.tileStart = bd.contigLen + 1;
+    bd.nContigs = 1;
+    bd.nTiles = tiles;
+    IndexState ix;
+    fillIndexState(ix);
+    ix.pos1 = 1ull << 62;  // every candidate "ends before" the cursor: the window test always passes
+    int launches = launch_chunk_desc(ix, bd, wb, stream);
+    launches += launch_probe(ix, bd, wb, useSharedFilter(), false, stream);
+    launches += launch_memo(bd, wb, static_cast<uint32_t>(nValid), dMemoX, dMemoE, stream);
+    check(cudaEventRecord(ev[11], stream), "event");
+    check(cudaGetLastError(), "memo launch");
+    // the batch pass reuses hMeta: wait until the copy above has read it
+    check(cudaStreamSynchronize(stream), "memo sync");
+    float ms = 0;
+    check(cudaEventElapsedTime(&ms, ev[10], ev[11]), "event time");
+    stageMs[MBGCG_T_MEMO] += ms;
+    stageMs[MBGCG_T_TOTAL] += ms;
+    totalLaunches += static_cast<uint64_t>(launches);
+    lastCounters[4] += static_cast<uint64_t>(launches);
+    memoSeq = insertSeq;
+    memoLen = len;
+}
+
+bool B200SparseEMMatcher::useSharedFilter() const {
+    static const bool noFilterEnv = std::getenv("MBGC_B200_NO_FILTER") != nullptr;
+    // the shared-memory filter only pays while it is sparse (entries <~ bits)
+    return insertSeq < static_cast<uint64_t>(PROBE_FILTER_BITS) * 3 / 2 && !noFilterEnv;
 }
 
 void B200SparseEMMatcher::matchBatch(const std::vector<TextView>& texts, const uint64_t* lockPos, uint32_t minMatchLength,
@@ -367,7 +476,6 @@ void B200SparseEMMatcher::matchBatch(const std::vector<TextView>& texts, const u
         const char* e = std::getenv("MBGC_B200_MAX_PASS_BYTES");
         return e ? std::strtoull(e, nullptr, 10) : (256ull << 20);
     }();
-    static const bool noFilterEnv = std::getenv("MBGC_B200_NO_FILTER") != nullptr;
     size_t first = 0;
     while (first < texts.size()) {
         size_t last = first;
@@ -392,6 +500,9 @@ void B200SparseEMMatcher::matchBatch(const std::vector<TextView>& texts, const u
         tileStart[nC] = tiles;
         const uint64_t textBytes = cursor + TEXT_TAIL;
 
+        bool useFast = wantMemo(positions);
+        if (useFast && memoSeq != insertSeq) buildMemo();
+        passesSinceInsert++;
         uint32_t seedCap = static_cast<uint32_t>(std::min<uint64_t>(positions / 4 + 65536, 0xFFFFFFF0ull));
         for (int attempt = 0;; attempt++) {
             ensureWork(textsOnDevice ? 0 : textBytes, tiles, nC, seedCap);
@@ -428,30 +539,27 @@ void B200SparseEMMatcher::matchBatch(const std::vector<TextView>& texts, const u
             bd.contigOff = reinterpret_cast<const uint64_t*>(dMeta);
             bd.contigLock = bd.contigOff + nC;
             bd.contigLen = reinterpret_cast<const uint32_t*>(bd.contigLock + nC);
+            if (!lockPos) bd.contigLock = nullptr;  // no worker locks in this batch: kernels skip the lookup
             bd.tileStart = bd.contigLen + nC;
             bd.nContigs = nC;
             bd.nTiles = tiles;
             IndexState ix;
-            ix.ref = dRef;
-            ix.ht = dHt;
-            ix.occ = dOcc;
-            ix.filter = dFilter;
-            ix.filterBits = PROBE_FILTER_BITS;
-            ix.filterWords = PROBE_FILTER_BYTES / 4;
-            ix.hashMask = hashSize - 1;
-            ix.K = K;
-            ix.k1 = k1;
-            ix.k1ord = k1ord;
-            ix.skipMargin = skipMargin;
-            ix.pos1 = static_cast<uint64_t>(pos1);
-            ix.refLen = getRefLength();
+            fillIndexState(ix);
 
             int launches = 0;
-            // the shared-memory filter only pays while it is sparse (entries <~ bits)
-            const bool useFilter = insertSeq < static_cast<uint64_t>(PROBE_FILTER_BITS) * 3 / 2 && !noFilterEnv;
-            launches += launch_probe(ix, bd, wb, useFilter, stream);
+            launches += launch_chunk_desc(ix, bd, wb, stream);
+            if (useFast) {
+                launches += launch_anchor(ix, bd, wb, stream);
+                check(cudaEventRecord(ev[7], stream), "event");
+                launches += launch_clean(ix, bd, wb, MemoState{dMemoX, dMemoX + memoCapWords, memoLen}, stream);
+                check(cudaEventRecord(ev[8], stream), "event");
+            } else {
+                check(cudaEventRecord(ev[7], stream), "event");
+                check(cudaEventRecord(ev[8], stream), "event");
+            }
+            launches += launch_probe(ix, bd, wb, useSharedFilter(), useFast, stream);
             check(cudaEventRecord(ev[2], stream), "event");
-            launches += launch_compact_and_runs(ix, bd, wb, stream);
+            launches += launch_compact_and_runs(ix, bd, wb, useFast, stream);
             check(cudaEventRecord(ev[3], stream), "event");
             launches += launch_extend(ix, bd, wb, stream);
             check(cudaEventRecord(ev[4], stream), "event");
@@ -504,6 +612,23 @@ void B200SparseEMMatcher::matchBatch(const std::vector<TextView>& texts, const u
             }
             check(cudaEventElapsedTime(&ms, ev[0], ev[6]), "event time");
             stageMs[MBGCG_T_TOTAL] += ms;
+            check(cudaEventElapsedTime(&ms, ev[1], ev[7]), "event time");
+            stageMs[MBGCG_T_ANCHOR] += ms;
+            check(cudaEventElapsedTime(&ms, ev[7], ev[8]), "event time");
+            stageMs[MBGCG_T_CLEAN] += ms;
+            check(cudaEventElapsedTime(&ms, ev[8], ev[2]), "event time");
+            stageMs[MBGCG_T_FULLPROBE] += ms;
+            // clean-fraction estimate for the fast-path policy (see wantMemo)
+            if (useFast && tiles) {
+                cleanEstimate = static_cast<double>(tiles - std::min(hCtr[5], tiles)) / tiles;
+            } else if (positions) {
+                uint64_t covered = 0;
+                for (uint32_t k = 0; k < total; k++)
+                    if (hMatches[k].len >= 1024) covered += hMatches[k].len;
+                cleanEstimate = static_cast<double>(covered) / static_cast<double>(positions);
+            }
+            lastCounters[6] += tiles;
+            lastCounters[7] += useFast ? hCtr[5] : tiles;
             lastCounters[0] += positions;
             lastCounters[1] += hCtr[0];
             lastCounters[2] += hCtr[1];

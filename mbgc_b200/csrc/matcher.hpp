@@ -15,6 +15,8 @@
 
 #include "kernels.h"
 
+constexpr int MBGCG_T_COUNT_ = 12;  // = MBGCG_T_COUNT of include/mbgc_b200.h (checked in capi.cpp)
+
 namespace mbgc_b200 {
 
 struct MatcherError : public std::runtime_error {
@@ -60,7 +62,13 @@ public:
     uint64_t getLoadedRefLength() const {
         return static_cast<uint64_t>(reachedRefLengthCount) * (maxRefLength - REF_SHIFT) + (static_cast<uint64_t>(pos1) - REF_SHIFT);
     }
-    void setPosition(uint64_t refPos, int reached) { pos1 = static_cast<int64_t>(refPos); reachedRefLengthCount = reached; }
+    void setPosition(uint64_t refPos, int reached) {
+        pos1 = static_cast<int64_t>(refPos);
+        reachedRefLengthCount = reached;
+        invalidateMemo();
+    }
+    // the fast path's self-probe memo describes reference bytes [0, memoLen) under the table as of memoSeq
+    void invalidateMemo() { memoSeq = 0; }
 
     // ref .cpp:361-400
     uint64_t acquireWorkerMatchingLockPos();
@@ -91,19 +99,23 @@ public:
     uint32_t hashSize = 0;
     int L = 0, K = 0, k1 = 0, k2 = 0, skipMargin = 0, k1ord = -1;
 
-    float stageMs[8] = {0};
+    float stageMs[MBGCG_T_COUNT_] = {0};
     uint64_t lastCounters[8] = {0};
     uint64_t totalLaunches = 0;
 
 private:
     void loadSegment(const char* text, uint64_t len, bool rc, bool addSep, char sep);
     void indexPass();
+    bool wantMemo(uint64_t positions);
+    void buildMemo();
+    bool useSharedFilter() const;
+    void fillIndexState(IndexState& ix) const;
     void ensureWork(uint64_t textBytes, uint32_t nTiles, int nContigs, uint32_t seedCap);
     void check(cudaError_t e, const char* what);
 
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[8] = {};
+    cudaEvent_t ev[12] = {};
     char* hostRef = nullptr;             // host mirror (getRef())
     uint8_t* dRefAlloc = nullptr;        // device reference buffer with padding
     uint8_t* dRef = nullptr;             // = dRefAlloc + PAD
@@ -111,6 +123,12 @@ private:
     uint32_t* dOcc = nullptr;
     uint32_t* dFilter = nullptr;         // first-level probe filter (copied to shared memory by the probe kernel)
     uint64_t insertSeq = 1;              // program-order sequence number of the next index sample
+    // fast path (kernels.cu, k_anchor / k_clean): self-probe memo of the reference + adaptive policy
+    uint32_t* dMemoX = nullptr; uint64_t memoCapWords = 0;
+    uint64_t memoSeq = 0;                // insertSeq the memo was built at (0 = none)
+    uint64_t memoLen = 0;                // reference positions covered
+    uint64_t passesSinceInsert = 0;      // match passes since the index last changed
+    double cleanEstimate = 0.5;          // expected fraction of clean chunks (updated from every pass)
     std::deque<uint64_t> workersSwEndPositions;
 
     // per-pass device buffers (grown on demand)

@@ -16,7 +16,7 @@ _LIB = None
 u8p = C.POINTER(C.c_uint8)
 u64p = C.POINTER(C.c_uint64)
 
-T_NAMES = ("h2d", "probe", "compact", "extend", "resolve", "d2h", "total")
+T_NAMES = ("h2d", "probe", "compact", "extend", "resolve", "d2h", "total", "anchor", "clean", "fullprobe", "memo")
 
 
 class MatcherError(RuntimeError):
@@ -212,7 +212,7 @@ class Matcher:
         return out
 
     def timing(self):
-        ms = (C.c_float * 8)()
+        ms = (C.c_float * 12)()
         self.lib.mbgcg_last_timing(self.h, ms)
         return {name: ms[i] for i, name in enumerate(T_NAMES)}
 
@@ -220,7 +220,7 @@ class Matcher:
         c = (C.c_uint64 * 8)()
         self.lib.mbgcg_last_counters(self.h, c)
         return {"positions": c[0], "seeds": c[1], "runs": c[2], "matches": c[3], "launches": c[4],
-                "passes": c[5]}
+                "passes": c[5], "chunks": c[6], "chunks_full_probe": c[7]}
 
     def stream(self):
         """cudaStream_t (as int) all work of this matcher is issued on"""

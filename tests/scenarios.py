@@ -83,10 +83,34 @@ def many_small_contigs(seed=21, n=300):
     return dict(limit=1 << 22, ops=[("load", base, True), ("batch", texts)], name=f"small{seed}")
 
 
+def repeat_rich_near(seed=41, length=400_000, n=4):
+    """near-identical targets of a reference full of repeats: duplicated elements (a later copy overwrites the
+    table slot of an earlier one), tandem repeats, homopolymers, N runs, a lower-case stretch.  Exercises the
+    fast path's memo (which chunks may be declared clean) against repeats on and off the sampling grid."""
+    r = _rng(seed)
+    base = synth_base(length, seed).copy()
+    elem = base[50_000:56_000].copy()
+    for at in (120_003, 200_010, 300_007):      # copies at different phases of the 16-grid
+        base[at:at + elem.size] = elem
+    unit = _ACGT[r.integers(0, 4, 48)]           # tandem repeat, period 48 = 3 x 16
+    base[250_000:250_000 + 48 * 60] = np.tile(unit, 60)
+    base[20_000:21_500] = ord("A")
+    base[330_000:331_000] = ord("N")
+    base[350_000:352_000] = np.frombuffer(bytes(base[350_000:352_000]).lower(), dtype=np.uint8)
+    ops = [("load", base, True)]
+    texts = [synth_mutant(base, seed * 7919 + i, 2e-4, 2e-5) for i in range(1, n)]
+    texts.append(base.copy())                                    # identical copy
+    texts.append(np.concatenate([base[77:150_000], base[10:90_000]]))  # rearranged, off-grid
+    ops.append(("batch", texts))
+    ops += [("sep",), ("match", texts[0], None), ("load", texts[1], True), ("match", texts[2], None), ("sep",),
+            ("match", texts[0], None), ("batch", texts[:3])]
+    return dict(limit=1 << 23, ops=ops, name=f"repeats{seed}")
+
+
 def all_scenarios():
     return [near_collection(), near_collection(seed=12, n=3, length=300_000, p_snp=1e-4, p_indel=1e-5),
             growing_collection(), wrapping_collection(), wrapping_collection(seed=10, sliding=True, limit=700_003),
-            pathological(), many_small_contigs()]
+            pathological(), many_small_contigs(), repeat_rich_near()]
 
 
 def replay(m, sc, batch=True, min_len=32):
