@@ -273,10 +273,10 @@ def run_b200(args, rank, world):
 
     sampler = ClockSampler(local)
     sampler.start()
-    ms_dev, stage_dev, launches, res = timed(lambda: m.matchBatchDevice(dbuf.data_ptr(), offs, lens, 32))
+    ms_dev, stage_dev, launches, res = timed(lambda: m.matchBatchDevice(dbuf.data_ptr(), offs, lens, 32, copy=False))
     counters = m.counters()
     host_ptrs = [p.numpy() for p in pinned]
-    ms_e2e, stage_e2e, _, res2 = timed(lambda: m.matchBatch(host_ptrs, 32))
+    ms_e2e, stage_e2e, _, res2 = timed(lambda: m.matchBatch(host_ptrs, 32, copy=False))
     sampler.stop_flag = True
     sampler.join(timeout=2)
     n_matches = int(sum(len(r) for r in res))

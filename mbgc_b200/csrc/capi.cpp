@@ -100,7 +100,7 @@ int mbgcg_match_batch(mbgcg_t* h, int nTexts, const char* const* texts, const ui
         std::vector<TextView> tv(static_cast<size_t>(nTexts));
         for (int i = 0; i < nTexts; i++) tv[i] = TextView{texts[i], lens[i]};
         h->m->matchBatch(tv, lockPos, minMatchLength, false, nullptr, nullptr);
-        *out = reinterpret_cast<const mbgcg_match_t*>(h->m->batchMatches().data());
+        *out = reinterpret_cast<const mbgcg_match_t*>(h->m->batchMatches());
         *counts = h->m->batchCounts().data();
     });
 }
@@ -117,7 +117,7 @@ int mbgcg_match_batch_device(mbgcg_t* h, const void* dText, int nTexts, const ui
             tv[i] = TextView{nullptr, lens[i]};
         }
         h->m->matchBatch(tv, lockPos, minMatchLength, true, dText, offsets);
-        *out = reinterpret_cast<const mbgcg_match_t*>(h->m->batchMatches().data());
+        *out = reinterpret_cast<const mbgcg_match_t*>(h->m->batchMatches());
         *counts = h->m->batchCounts().data();
     });
 }

@@ -518,92 +518,90 @@ struct CleanArgs {
     uint16_t* seedMask;
     uint32_t* scratchEnc;
     uint8_t* chunkSegN;
+    uint2* chunkSeg;
     uint32_t* workList;
     uint32_t* counters;
 };
 
-constexpr int CLEAN_UNROLL = 4;  // chunks a warp has in flight (the kernel is a chain of dependent loads)
-
+// Eight lanes per chunk, four chunks per warp: the per-chunk scalar work (descriptor, diagonal, window class,
+// memo window) is a few dozen instructions that every lane of the chunk repeats, so fewer lanes per chunk means
+// fewer issue slots; each lane compares 4 x 16 bytes, the pieces interleaved so that the 8 lanes of a chunk read
+// 128 contiguous bytes per load instruction.
 __global__ void __launch_bounds__(256) k_clean(const CleanArgs a) {
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, sub = lane & 7, cg = lane >> 3;
     const int K = a.ix.K;
+    const int tailWords = (K + 2) / 4;  // the K-1 bytes the chunk's last k-mers reach past it, rounded up to words
     const uint32_t warpsTotal = gridDim.x * (blockDim.x >> 5);
     const uint32_t nTiles = a.b.nTiles;
-    for (uint32_t gb = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * CLEAN_UNROLL; gb < nTiles;
-         gb += warpsTotal * CLEAN_UNROLL) {
-        // round 1: descriptor, anchor (and the contig's lock, if the batch has any)
-        uint4 desc[CLEAN_UNROLL];
-        unsigned long long an[CLEAN_UNROLL];
-        uint32_t cc[CLEAN_UNROLL];
-#pragma unroll
-        for (int u = 0; u < CLEAN_UNROLL; u++) {
-            const uint32_t g = gb + u < nTiles ? gb + u : nTiles - 1;
-            desc[u] = __ldg(&a.chunkDesc[g]);
-            an[u] = a.anchor[g];
-            cc[u] = a.b.contigLock ? __ldg(&a.chunkContig[g]) : 0;
+    for (uint32_t gb = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 4; gb < nTiles; gb += warpsTotal * 4) {
+        const bool valid = gb + cg < nTiles;
+        const uint32_t g = valid ? gb + cg : nTiles - 1;
+        const uint4 desc = __ldg(&a.chunkDesc[g]);
+        const unsigned long long an = a.anchor[g];
+        uint64_t lock = NO_LOCK;
+        if (a.b.contigLock) lock = __ldg(&a.b.contigLock[__ldg(&a.chunkContig[g])]);
+        const uint32_t base = desc.z, nValid = desc.w;
+        const uint32_t enc = static_cast<uint32_t>(an);
+        bool ok = valid && enc != 0 && base + PROBE_CHUNK <= nValid;
+        // reference position of the chunk start on the anchor's diagonal
+        const int64_t r0 = static_cast<int64_t>(decode_pos(enc, a.ix.k1ord)) - static_cast<int64_t>(an >> 32);
+        ok = ok && r0 >= 1 && static_cast<uint64_t>(r0) + PROBE_CHUNK + K - 1 <= a.memoLen;
+        const uint32_t pin = (16u - (static_cast<uint32_t>(r0) & 15u)) & 15u;  // first position with (i + d) % 16 == 0
+        if (ok) {
+            const uint64_t swStop = lock != NO_LOCK ? lock : a.ix.pos1;
+            const uint64_t sFirst = static_cast<uint64_t>(r0) + pin, sLast = sFirst + 31 * 16;
+            int c0, c1;
+            const bool w0 = window_ok(sFirst, K, a.ix.pos1, swStop, c0);
+            const bool w1 = window_ok(sLast, K, a.ix.pos1, swStop, c1);
+            ok = w0 && w1 && c0 == c1;  // both window predicates are monotone in s: uniform class in between
         }
-        // round 2: everything that depends on the anchor's diagonal
-        bool ok[CLEAN_UNROLL];
-        uint32_t pin[CLEAN_UNROLL], diff[CLEAN_UNROLL], xbit[CLEAN_UNROLL], ebit[CLEAN_UNROLL];
-        int64_t r0[CLEAN_UNROLL];
+        const uint8_t* T = a.b.text + ((static_cast<uint64_t>(desc.y) << 32) | desc.x);
+        const uint8_t* R = ok ? a.ix.ref + r0 : T;  // chunks that already failed compare the text with itself
+        // memo window: bit 0 = the partial group before the first grid position, bits 1..32 = the groups of the
+        // chunk's 32 grid positions
+        const uint64_t grp0 = ok ? (static_cast<uint64_t>(r0) + pin) / 16 : 1;
+        const uint64_t wi = (grp0 - 1) >> 5;
+        const uint32_t ws = static_cast<uint32_t>(grp0 - 1) & 31u;
+        const uint64_t xw = (static_cast<uint64_t>(__ldg(&a.memoX[wi + 1])) << 32 | __ldg(&a.memoX[wi])) >> ws;
+        const uint64_t ew = (static_cast<uint64_t>(__ldg(&a.memoE[wi + 1])) << 32 | __ldg(&a.memoE[wi])) >> ws;
+
+        // 512 + K-1 bytes of text against the reference on the diagonal
+        const uintptr_t ra = reinterpret_cast<uintptr_t>(R + 16 * sub);
+        const uint32_t* rp = reinterpret_cast<const uint32_t*>(ra & ~static_cast<uintptr_t>(3));
+        const uint32_t sh = static_cast<uint32_t>(ra & 3) * 8;
+        const uint4* tp = reinterpret_cast<const uint4*>(T) + sub;
+        uint4 tw[4];
+        uint32_t rw[4][5];
 #pragma unroll
-        for (int u = 0; u < CLEAN_UNROLL; u++) {
-            const uint32_t base = desc[u].z, nValid = desc[u].w;
-            const uint32_t enc = static_cast<uint32_t>(an[u]);
-            ok[u] = gb + u < nTiles && enc != 0 && base + PROBE_CHUNK <= nValid;  // warp-uniform
-            r0[u] = static_cast<int64_t>(decode_pos(enc, a.ix.k1ord)) - static_cast<int64_t>(an[u] >> 32);
-            ok[u] = ok[u] && r0[u] >= 1 && static_cast<uint64_t>(r0[u]) + PROBE_CHUNK + K - 1 <= a.memoLen;
-            pin[u] = (16u - (static_cast<uint32_t>(r0[u]) & 15u)) & 15u;  // first position with (i + d) % 16 == 0
-            diff[u] = 0; xbit[u] = 0; ebit[u] = 0;
-            if (ok[u]) {
-                const uint64_t lock = a.b.contigLock ? __ldg(&a.b.contigLock[cc[u]]) : NO_LOCK;
-                const uint64_t swStop = lock != NO_LOCK ? lock : a.ix.pos1;
-                const uint64_t sFirst = static_cast<uint64_t>(r0[u]) + pin[u], sLast = sFirst + 31 * 16;
-                int c0, c1;
-                const bool w0 = window_ok(sFirst, K, a.ix.pos1, swStop, c0);
-                const bool w1 = window_ok(sLast, K, a.ix.pos1, swStop, c1);
-                ok[u] = w0 && w1 && c0 == c1;  // both window predicates are monotone in s: uniform class in between
-            }
-            if (ok[u]) {
-                // memo state of the group of 16 reference positions around this lane's grid position
-                // (lane 0 also answers for the partial group before the first grid position)
-                const uint64_t grp = (static_cast<uint64_t>(r0[u]) + pin[u]) / 16 + lane;
-                xbit[u] = (__ldg(&a.memoX[grp >> 5]) >> (grp & 31)) & 1u;
-                ebit[u] = (__ldg(&a.memoE[grp >> 5]) >> (grp & 31)) & 1u;
-                if (lane == 0 && pin[u]) xbit[u] |= (__ldg(&a.memoX[(grp - 1) >> 5]) >> ((grp - 1) & 31)) & 1u;
-                // 512 + K-1 bytes of text against the reference on the diagonal
-                const uint8_t* T = a.b.text + ((static_cast<uint64_t>(desc[u].y) << 32) | desc[u].x);
-                const uint8_t* R = a.ix.ref + r0[u];
-                const uint4 t = __ldg(reinterpret_cast<const uint4*>(T) + lane);
-                const uintptr_t ra = reinterpret_cast<uintptr_t>(R + 16 * lane);
-                const uint32_t* rw = reinterpret_cast<const uint32_t*>(ra & ~static_cast<uintptr_t>(3));
-                const uint32_t sh = static_cast<uint32_t>(ra & 3) * 8;
-                const uint32_t w0 = __ldg(rw), w1 = __ldg(rw + 1), w2 = __ldg(rw + 2), w3 = __ldg(rw + 3), w4 = __ldg(rw + 4);
-                diff[u] = (t.x ^ __funnelshift_r(w0, w1, sh)) | (t.y ^ __funnelshift_r(w1, w2, sh)) |
-                          (t.z ^ __funnelshift_r(w2, w3, sh)) | (t.w ^ __funnelshift_r(w3, w4, sh));
-                if (lane < (K + 2) / 4)  // the K-1 bytes the chunk's last k-mers reach past it (rounded up to words)
-                    diff[u] |= ldg_u32_unaligned(T + PROBE_CHUNK + 4 * lane) ^ ldg_u32_unaligned(R + PROBE_CHUNK + 4 * lane);
+        for (int k = 0; k < 4; k++) {
+            tw[k] = __ldg(tp + 8 * k);
+#pragma unroll
+            for (int m = 0; m < 5; m++) rw[k][m] = __ldg(rp + 32 * k + m);
+        }
+        uint32_t diff = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            diff |= (tw[k].x ^ __funnelshift_r(rw[k][0], rw[k][1], sh)) | (tw[k].y ^ __funnelshift_r(rw[k][1], rw[k][2], sh)) |
+                    (tw[k].z ^ __funnelshift_r(rw[k][2], rw[k][3], sh)) | (tw[k].w ^ __funnelshift_r(rw[k][3], rw[k][4], sh));
+#pragma unroll
+        for (int w = 0; w < 2; w++) {  // tail: word sub, and word sub + 8 for K > 32
+            const int tl = sub + 8 * w;
+            if (tl < tailWords) {
+                const uint32_t* rt = rp - 4 * sub + PROBE_CHUNK / 4 + tl;  // R + PROBE_CHUNK + 4 tl, rounded down to a word
+                diff |= __ldg(reinterpret_cast<const uint32_t*>(T + PROBE_CHUNK) + tl) ^ __funnelshift_r(__ldg(rt), __ldg(rt + 1), sh);
             }
         }
-        // round 3: verdicts
-#pragma unroll
-        for (int u = 0; u < CLEAN_UNROLL; u++) {
-            if (gb + u >= nTiles) break;
-            const uint32_t g = gb + u;
-            const bool clean = ok[u] && !__any_sync(0xffffffffu, diff[u] != 0 || xbit[u] != 0);
+        const unsigned bad = (__ballot_sync(0xffffffffu, diff != 0) >> (8 * cg)) & 0xffu;
+        const bool clean = ok && bad == 0 && static_cast<uint32_t>(xw >> 1) == 0 && !(pin && (xw & 1));
+        if (sub == 0 && valid) {
             if (clean) {
                 // seeds = grid positions whose group is in the default state; maximal stretches leave as segments
-                const unsigned D = __ballot_sync(0xffffffffu, ebit[u] == 0);
-                const unsigned S = D & ~(D << 1);
-                if ((S >> lane) & 1u)
-                    a.scratchEnc[static_cast<uint64_t>(g) * PROBE_CHUNK + pin[u] + 16 * lane] =
-                        static_cast<uint32_t>((static_cast<uint64_t>(r0[u]) + pin[u]) / 16 + lane);
-                a.seedMask[static_cast<uint64_t>(g) * 32 + lane] = ebit[u] == 0 ? static_cast<uint16_t>(1u << pin[u]) : 0;
-                if (lane == 0) {
-                    a.chunkCount[g] = __popc(S);
-                    a.chunkSegN[g] = 1;
-                }
-            } else if (lane == 0) {
+                // (k_compact_clean expands the mask D)
+                const uint32_t D = ~static_cast<uint32_t>(ew >> 1);
+                a.chunkCount[g] = __popc(D & ~(D << 1));
+                a.chunkSegN[g] = static_cast<uint8_t>(0x80u | pin);
+                a.chunkSeg[g] = make_uint2(static_cast<uint32_t>(grp0), D);
+            } else {
                 a.chunkSegN[g] = 0;
                 a.workList[atomicAdd(&a.counters[5], 1u)] = g;
             }
@@ -733,7 +731,7 @@ int launch_anchor(const IndexState& ix, const BatchDesc& b, const WorkBuffers& w
 int launch_clean(const IndexState& ix, const BatchDesc& b, const WorkBuffers& w, const MemoState& memo, cudaStream_t st) {
     if (b.nTiles == 0) return 0;
     CleanArgs a{ix, b, w.chunkDesc, w.chunkContig, w.anchor, memo.memoX, memo.memoE, memo.memoLen, w.tileCount,
-                w.seedMask, w.scratchEnc, w.chunkSegN, w.workList, w.counters};
+                w.seedMask, w.scratchEnc, w.chunkSegN, w.chunkSeg, w.workList, w.counters};
     k_clean<<<device_sm_count() * 8, 256, 0, st>>>(a);
     return 1;
 }
@@ -749,14 +747,15 @@ int launch_memo(const BatchDesc& b, const WorkBuffers& w, uint32_t nValid, uint3
 // seed compaction + run detection
 // ------------------------------------------------------------------------------------------------------
 
-// position-indexed seed staging -> dense, position-ordered arrays.  One warp per chunk; chunkOff = exclusive
-// scan of the chunk counts.
+// position-indexed seed staging -> dense, position-ordered segment arrays.  chunkOff = exclusive scan of the
+// chunk counts.  One warp per fully probed chunk (all chunks, or the fast path's work list).
 __global__ void __launch_bounds__(256) k_compact(BatchDesc b, const uint32_t* __restrict__ chunkContig,
                                                  const uint32_t* __restrict__ chunkOff,
                                                  const uint16_t* __restrict__ seedMask,
                                                  const uint32_t* __restrict__ scratchEnc,
-                                                 const uint8_t* __restrict__ chunkSegN, uint32_t* __restrict__ seedPos,
-                                                 uint32_t* __restrict__ seedEnc, uint8_t* __restrict__ seedN,
+                                                 const uint32_t* __restrict__ workList, const uint32_t* workCount,
+                                                 uint32_t* __restrict__ seedPos, uint32_t* __restrict__ seedEnc,
+                                                 uint8_t* __restrict__ seedN, uint32_t* __restrict__ seedContig,
                                                  uint32_t seedCap, uint32_t* counters) {
     const uint32_t nSeeds = chunkOff[b.nTiles];
     if (nSeeds > seedCap) {
@@ -765,77 +764,91 @@ __global__ void __launch_bounds__(256) k_compact(BatchDesc b, const uint32_t* __
     }
     const int lane = threadIdx.x & 31;
     const uint32_t warpsTotal = gridDim.x * (blockDim.x >> 5);
-    for (uint32_t g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); g < b.nTiles; g += warpsTotal) {
+    const uint32_t nWork = workList ? *workCount : b.nTiles;
+    for (uint32_t w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < nWork; w += warpsTotal) {
+        const uint32_t g = workList ? workList[w] : w;
         const uint32_t o = chunkOff[g];
         if (chunkOff[g + 1] == o) continue;
         uint32_t m = seedMask[static_cast<uint64_t>(g) * 32 + lane];
-        const uint32_t base = (g - b.tileStart[chunkContig[g]]) * PROBE_CHUNK + lane * PROBE_NPT;
+        const uint32_t c = chunkContig[g];
+        const uint32_t base = (g - b.tileStart[c]) * PROBE_CHUNK + lane * PROBE_NPT;
         const uint64_t src = static_cast<uint64_t>(g) * PROBE_CHUNK + lane * PROBE_NPT;
-        if (chunkSegN && chunkSegN[g]) {
-            // clean chunk (k_clean): at most one seed per lane, all on one diagonal and k1 apart; every maximal
-            // stretch of lanes with a seed leaves as one segment
-            const unsigned D = __ballot_sync(0xffffffffu, m != 0);
-            const unsigned S = D & ~(D << 1);
-            if ((S >> lane) & 1u) {
-                const uint32_t k = o + __popc(S & ((1u << lane) - 1u));
-                const int p = __ffs(m) - 1;
-                seedPos[k] = base + p;
-                seedEnc[k] = scratchEnc[src + p];
-                // consecutive lanes with a seed from here on (64-bit so that 32 ones give 32)
-                seedN[k] = static_cast<uint8_t>(__ffsll(static_cast<long long>(~static_cast<unsigned long long>(D >> lane))) - 1);
-            }
-            continue;
-        }
-        const uint32_t c = __popc(m);
-        uint32_t k = o + warp_incl_scan(c, lane) - c;
+        const uint32_t cnt = __popc(m);
+        uint32_t k = o + warp_incl_scan(cnt, lane) - cnt;
         while (m) {
             const int p = __ffs(m) - 1;
             m &= m - 1;
             seedPos[k] = base + p;
             seedEnc[k] = scratchEnc[src + p];
             seedN[k] = 1;
+            seedContig[k] = c;
             k++;
         }
     }
 }
 
-// head[j] = 1 iff seed j starts a run: first seed of its contig, or not (previous pos + k1, previous enc + step),
+// clean chunks (k_clean): one THREAD per chunk.  The chunk's seeds sit on one diagonal, k1 apart, at most one per
+// lane-sized group of 16 positions; D has a bit for every group with a seed, and every maximal stretch of set bits
+// leaves as one segment.
+__global__ void __launch_bounds__(256) k_compact_clean(BatchDesc b, const uint32_t* __restrict__ chunkContig,
+                                                       const uint32_t* __restrict__ chunkOff,
+                                                       const uint8_t* __restrict__ chunkSegN,
+                                                       const uint2* __restrict__ chunkSeg, uint32_t* __restrict__ seedPos,
+                                                       uint32_t* __restrict__ seedEnc, uint8_t* __restrict__ seedN,
+                                                       uint32_t* __restrict__ seedContig, uint32_t seedCap) {
+    if (chunkOff[b.nTiles] > seedCap) return;
+    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < b.nTiles; g += gridDim.x * blockDim.x) {
+        const uint32_t fl = chunkSegN[g];
+        if (!(fl & 0x80u)) continue;
+        const uint32_t pin = fl & 15u;
+        const uint2 sg = chunkSeg[g];  // .x = entry of group 0's seed, .y = D
+        const uint32_t c = chunkContig[g];
+        const uint32_t base = (g - b.tileStart[c]) * PROBE_CHUNK + pin;
+        uint32_t k = chunkOff[g];
+        unsigned D = sg.y;
+        while (D) {
+            const int l = __ffs(D) - 1;
+            // consecutive groups with a seed from l on (64-bit so that 32 ones give 32)
+            const int n = __ffsll(static_cast<long long>(~static_cast<unsigned long long>(D >> l))) - 1;
+            seedPos[k] = base + 16u * l;
+            seedEnc[k] = sg.x + l;
+            seedN[k] = static_cast<uint8_t>(n);
+            seedContig[k] = c;
+            k++;
+            D = l + n >= 32 ? 0u : D & (~0u << (l + n));
+        }
+    }
+}
+
+// head[j] = 1 iff segment j starts a run: first of its contig, or not (previous pos + k1, previous enc + step),
 // or a different window class (the class fixes the extension bounds tmpStart1/tmpEnd1, .cpp:221-222).
 // Seeds only collapse when their k-mers touch or overlap (k1 <= K); otherwise (protein profile: K = 12 < k1 = 16)
-// the bases between two seeds are unverified and every seed is its own run.
-__global__ void __launch_bounds__(256) k_heads(IndexState ix, BatchDesc b, const uint32_t* __restrict__ chunkContig,
-                                               const uint32_t* __restrict__ chunkOff,
+// the bases between two seeds are unverified and every seed is its own run.  One thread per segment.
+__global__ void __launch_bounds__(256) k_heads(IndexState ix, BatchDesc b, const uint32_t* __restrict__ chunkOff,
                                                const uint32_t* __restrict__ seedPos, const uint32_t* __restrict__ seedEnc,
-                                               const uint8_t* __restrict__ seedN, uint32_t* __restrict__ head,
-                                               const uint32_t* counters) {
+                                               const uint8_t* __restrict__ seedN, const uint32_t* __restrict__ seedContig,
+                                               uint32_t* __restrict__ head, const uint32_t* counters) {
     if (counters[3]) return;
-    const int lane = threadIdx.x & 31;
-    const uint32_t warpsTotal = gridDim.x * (blockDim.x >> 5);
+    const uint32_t nSeeds = chunkOff[b.nTiles];
     const uint32_t encStep = ix.k1ord >= 0 ? static_cast<uint32_t>(ix.k1 >> ix.k1ord) : static_cast<uint32_t>(ix.k1);
-    for (uint32_t g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); g < b.nTiles; g += warpsTotal) {
-        const uint32_t o = chunkOff[g], n = chunkOff[g + 1] - o;
-        if (n == 0) continue;
-        const uint32_t c = chunkContig[g];
-        const uint32_t contigFirst = chunkOff[b.tileStart[c]];
-        const uint64_t lock = b.contigLock ? b.contigLock[c] : NO_LOCK;
-        const uint64_t swStop = lock != NO_LOCK ? lock : ix.pos1;
-        for (uint32_t k = lane; k < n; k += 32) {
-            const uint32_t j = o + k;
-            uint32_t h = 1;
-            if (j != contigFirst) {
-                // last seed of the previous segment (a segment = seedN seeds, spacing k1, entries ascending)
-                const uint32_t nm1 = seedN[j - 1] - 1u;
-                const uint32_t e = seedEnc[j], ep = seedEnc[j - 1] + nm1 * encStep;
-                const uint32_t pp = seedPos[j - 1] + nm1 * static_cast<uint32_t>(ix.k1);
-                if (ix.k1 <= ix.K && seedPos[j] - pp == static_cast<uint32_t>(ix.k1) && e - ep == encStep) {
-                    int c0, c1;
-                    window_ok(decode_pos(e, ix.k1ord), ix.K, ix.pos1, swStop, c0);
-                    window_ok(decode_pos(ep, ix.k1ord), ix.K, ix.pos1, swStop, c1);
-                    h = c0 != c1;
-                }
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < nSeeds; j += gridDim.x * blockDim.x) {
+        uint32_t h = 1;
+        const uint32_t c = seedContig[j];
+        if (j != 0 && seedContig[j - 1] == c) {
+            // last seed of the previous segment (a segment = seedN seeds, spacing k1, entries ascending)
+            const uint32_t nm1 = seedN[j - 1] - 1u;
+            const uint32_t e = seedEnc[j], ep = seedEnc[j - 1] + nm1 * encStep;
+            const uint32_t pp = seedPos[j - 1] + nm1 * static_cast<uint32_t>(ix.k1);
+            if (ix.k1 <= ix.K && seedPos[j] - pp == static_cast<uint32_t>(ix.k1) && e - ep == encStep) {
+                const uint64_t lock = b.contigLock ? b.contigLock[c] : NO_LOCK;
+                const uint64_t swStop = lock != NO_LOCK ? lock : ix.pos1;
+                int c0, c1;
+                window_ok(decode_pos(e, ix.k1ord), ix.K, ix.pos1, swStop, c0);
+                window_ok(decode_pos(ep, ix.k1ord), ix.K, ix.pos1, swStop, c1);
+                h = c0 != c1;
             }
-            head[j] = h;
         }
+        head[j] = h;
     }
 }
 
@@ -867,9 +880,14 @@ int launch_compact_and_runs(const IndexState& ix, const BatchDesc& b, const Work
     // tileCount -> tileOff (in place), tileOff[nTiles] = nSeeds
     launches += scan_exclusive(w.tileCount, w.tileCount, nullptr, b.nTiles, b.nTiles, w.blockSums, nullptr, st);
     k_compact<<<sm * 8, 256, 0, st>>>(b, w.chunkContig, w.tileCount, w.seedMask, w.scratchEnc,
-                                      segments ? w.chunkSegN : nullptr, w.seedPos, w.seedEnc, w.seedN, w.seedCap,
-                                      w.counters);
-    k_heads<<<sm * 8, 256, 0, st>>>(ix, b, w.chunkContig, w.tileCount, w.seedPos, w.seedEnc, w.seedN, w.headScan,
+                                      segments ? w.workList : nullptr, segments ? w.counters + 5 : nullptr, w.seedPos,
+                                      w.seedEnc, w.seedN, w.seedContig, w.seedCap, w.counters);
+    if (segments) {
+        k_compact_clean<<<sm * 8, 256, 0, st>>>(b, w.chunkContig, w.tileCount, w.chunkSegN, w.chunkSeg, w.seedPos,
+                                                w.seedEnc, w.seedN, w.seedContig, w.seedCap);
+        launches += 1;
+    }
+    k_heads<<<sm * 8, 256, 0, st>>>(ix, b, w.tileCount, w.seedPos, w.seedEnc, w.seedN, w.seedContig, w.headScan,
                                     w.counters);
     launches += 2;
     // head flags -> exclusive scan in place; length lives on the device (tileOff[nTiles])
@@ -882,20 +900,22 @@ int launch_compact_and_runs(const IndexState& ix, const BatchDesc& b, const Work
 // ------------------------------------------------------------------------------------------------------
 // K4: extend  (.cpp:227-246 right, :257-259 / :278-280 raw left)
 //
-// One warp per seed run.  Inside a run every base is already known equal (overlapping verified k-mers), so
-// only the stretch left of the first seed and right of the last seed's k-mer is compared: 32 lanes x 8 bytes
-// per step, XOR + __clzll/__ffsll for the first differing byte, __ballot_sync for the first lane that stops.
+// Eight lanes per seed run (four runs per warp).  Inside a run every base is already known equal (overlapping
+// verified k-mers), so only the stretch left of the first seed and right of the last seed's k-mer is compared:
+// 8 lanes x 8 bytes per step, XOR + __clzll/__ffsll for the first differing byte, __ballot_sync for the first
+// lane that stops.  These stretches are short by construction (a run's seeds reach to within k1 + K bytes of the
+// mismatch that ends it), so one 64-byte step almost always finishes a side.
 // If the neighbouring run lies on the same diagonal (a sampled k-mer was overwritten in the table, so the seed
 // chain broke although the bases still match) the walk stops at the neighbour's verified span and the run is
-// marked linked; K5 resolves link chains, so no stretch of text is ever compared twice.
+// marked linked; k_links resolves link chains, so no stretch of text is ever compared twice.
 // ------------------------------------------------------------------------------------------------------
 struct ExtendArgs {
     IndexState ix;
     BatchDesc b;
-    const uint32_t* tileOff;
     const uint32_t* seedPos;
     const uint32_t* seedEnc;
     const uint8_t* seedN;
+    const uint32_t* seedContig;
     const uint32_t* runFirst;
     const uint32_t* runStart;
     RunRec* runs;
@@ -905,30 +925,32 @@ struct ExtendArgs {
 __global__ void __launch_bounds__(256) k_extend(const ExtendArgs a) {
     if (a.counters[3]) return;
     const uint32_t nRuns = a.counters[1];
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, sub = lane & 7, grp = lane >> 3;
     const uint32_t warpsTotal = gridDim.x * (blockDim.x >> 5);
     const int K = a.ix.K, k1 = a.ix.k1;
-    for (uint32_t r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < nRuns; r += warpsTotal) {
-        // contig of this run: largest c with runStart[c] <= r
-        const int c = upper_contig(a.runStart, a.b.nContigs + 1, r);
+    const uint32_t encStep = a.ix.k1ord >= 0 ? static_cast<uint32_t>(k1 >> a.ix.k1ord) : static_cast<uint32_t>(k1);
+    const uint8_t* R = a.ix.ref;
+    for (uint32_t rb = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 4; rb < nRuns; rb += warpsTotal * 4) {
+        const bool valid = rb + grp < nRuns;
+        const uint32_t r = valid ? rb + grp : nRuns - 1;
+        const uint32_t j0 = a.runFirst[r], j1 = a.runFirst[r + 1];
+        const uint32_t c = a.seedContig[j0];
+        const uint32_t firstPos = a.seedPos[j0], enc0 = a.seedEnc[j0];
+        const uint32_t lastPos = a.seedPos[j1 - 1] + (a.seedN[j1 - 1] - 1u) * static_cast<uint32_t>(k1);
+        const uint32_t rs = a.runStart[c], re = a.runStart[c + 1];
         const uint32_t N2 = a.b.contigLen[c];
         const uint8_t* T = a.b.text + a.b.contigOff[c];
         const uint64_t lock = a.b.contigLock ? a.b.contigLock[c] : NO_LOCK;
         const uint64_t swStop = lock != NO_LOCK ? lock : a.ix.pos1;
-        const uint32_t j0 = a.runFirst[r], j1 = a.runFirst[r + 1];
-        const uint32_t firstPos = a.seedPos[j0], enc0 = a.seedEnc[j0];
-        const uint32_t lastPos = a.seedPos[j1 - 1] + (a.seedN[j1 - 1] - 1u) * static_cast<uint32_t>(k1);
-        const uint32_t encStep = a.ix.k1ord >= 0 ? static_cast<uint32_t>(k1 >> a.ix.k1ord) : static_cast<uint32_t>(k1);
         const int64_t s0 = static_cast<int64_t>(decode_pos(enc0, a.ix.k1ord));
         const int64_t d = s0 - static_cast<int64_t>(firstPos);  // reference position = target position + d
         int cls;
         window_ok(static_cast<uint64_t>(s0), K, a.ix.pos1, swStop, cls);
-        const uint8_t* R = a.ix.ref;
 
-        // ---- left
+        // ---- bounds: the neighbour run's verified span when it continues this diagonal
         bool leftCand = false;
         int64_t stopL = d < 0 ? -d : 0;  // target position below which nothing is compared (ref index >= 0)
-        if (r > a.runStart[c]) {
+        if (r > rs) {
             const uint32_t nm1 = a.seedN[j0 - 1] - 1u;  // last seed of the previous segment
             const uint32_t pp = a.seedPos[j0 - 1] + nm1 * static_cast<uint32_t>(k1);
             const int64_t sp = static_cast<int64_t>(decode_pos(a.seedEnc[j0 - 1] + nm1 * encStep, a.ix.k1ord));
@@ -939,45 +961,11 @@ __global__ void __launch_bounds__(256) k_extend(const ExtendArgs a) {
                 stopL = static_cast<int64_t>(pp) + K;  // end of the previous run's verified span
             }
         }
-        int64_t hiEnd = firstPos;  // bytes [.., hiEnd) still to compare, walking left
-        int64_t mism = stopL - 1;  // position of the first mismatch (or the stop bound - 1)
-        bool dataMismatch = false;
-        while (hiEnd > stopL) {
-            const int64_t hi_l = hiEnd - 8 * lane, lo_l = hi_l - 8;
-            int64_t m = INT64_MIN;
-            bool isData = false;
-            if (hi_l > stopL) {
-                const uint64_t x = ld_u64_unaligned(T + lo_l) ^ ld_u64_unaligned(R + lo_l + d);
-                // bytes below stopL are outside the comparison: drop them from the diff
-                uint64_t diff = x;
-                if (lo_l < stopL) diff &= ~0ull << (8 * (stopL - lo_l));
-                if (diff) {
-                    m = lo_l + (63 - __clzll(diff)) / 8;
-                    isData = true;
-                } else if (lo_l <= stopL) {
-                    m = stopL - 1;
-                }
-            } else {
-                m = stopL - 1;
-            }
-            const unsigned bal = __ballot_sync(0xffffffffu, m != INT64_MIN);
-            if (bal) {
-                const int src = __ffs(bal) - 1;
-                mism = __shfl_sync(0xffffffffu, m, src);
-                dataMismatch = __shfl_sync(0xffffffffu, isData ? 1 : 0, src) != 0;
-                break;
-            }
-            hiEnd -= 256;
-        }
-        const bool leftLinked = leftCand && !dataMismatch;
-        const uint32_t aFree = static_cast<uint32_t>(mism + 1);
-
-        // ---- right
         const int64_t refCap = static_cast<int64_t>(a.ix.refLen);
         int64_t stopR = N2;  // exclusive target bound
         if (refCap - d < stopR) stopR = refCap - d;
         bool rightCand = false;
-        if (r + 1 < a.runStart[c + 1]) {
+        if (r + 1 < re) {
             const uint32_t np = a.seedPos[j1];
             const int64_t sn = static_cast<int64_t>(decode_pos(a.seedEnc[j1], a.ix.k1ord));
             int clsN;
@@ -987,44 +975,96 @@ __global__ void __launch_bounds__(256) k_extend(const ExtendArgs a) {
                 stopR = np;
             }
         }
+
+        // ---- left: bytes [stopL, firstPos), walking down from firstPos
+        int64_t hiEnd = firstPos;
+        int64_t mism = stopL - 1;  // position of the first mismatch (or the stop bound - 1)
+        bool dataMismatch = false;
+        bool act = valid && hiEnd > stopL;
+        while (__any_sync(0xffffffffu, act)) {
+            int64_t m = INT64_MIN;
+            int isData = 0;
+            if (act) {
+                const int64_t hi_l = hiEnd - 8 * sub, lo_l = hi_l - 8;
+                if (hi_l > stopL) {
+                    uint64_t diff = ld_u64_unaligned(T + lo_l) ^ ld_u64_unaligned(R + lo_l + d);
+                    // bytes below stopL are outside the comparison: drop them from the diff
+                    if (lo_l < stopL) diff &= ~0ull << (8 * (stopL - lo_l));
+                    if (diff) {
+                        m = lo_l + (63 - __clzll(diff)) / 8;
+                        isData = 1;
+                    } else if (lo_l <= stopL) {
+                        m = stopL - 1;
+                    }
+                } else {
+                    m = stopL - 1;
+                }
+            }
+            const unsigned bal = (__ballot_sync(0xffffffffu, m != INT64_MIN) >> (8 * grp)) & 0xffu;
+            const int src = bal ? 8 * grp + __ffs(bal) - 1 : lane;
+            const int64_t mS = __shfl_sync(0xffffffffu, m, src);
+            const int dS = __shfl_sync(0xffffffffu, isData, src);
+            if (act) {
+                if (bal) {
+                    mism = mS;
+                    dataMismatch = dS != 0;
+                    act = false;
+                } else {
+                    hiEnd -= 64;
+                    act = hiEnd > stopL;
+                }
+            }
+        }
+        const bool leftLinked = leftCand && !dataMismatch;
+        const uint32_t aFree = static_cast<uint32_t>(mism + 1);
+
+        // ---- right: bytes [lastPos + K, stopR)
         int64_t loBeg = static_cast<int64_t>(lastPos) + K;
         int64_t mismR = stopR;
         bool dataMismatchR = false;
-        while (loBeg < stopR) {
-            const int64_t lo_l = loBeg + 8 * lane, hi_l = lo_l + 8;
+        act = valid && loBeg < stopR;
+        while (__any_sync(0xffffffffu, act)) {
             int64_t m = INT64_MIN;
-            bool isData = false;
-            if (lo_l < stopR) {
-                const uint64_t x = ld_u64_unaligned(T + lo_l) ^ ld_u64_unaligned(R + lo_l + d);
-                uint64_t diff = x;
-                if (hi_l > stopR) diff &= ~0ull >> (8 * (hi_l - stopR));
-                if (diff) {
-                    m = lo_l + (__ffsll(static_cast<long long>(diff)) - 1) / 8;
-                    isData = true;
-                } else if (hi_l >= stopR) {
+            int isData = 0;
+            if (act) {
+                const int64_t lo_l = loBeg + 8 * sub, hi_l = lo_l + 8;
+                if (lo_l < stopR) {
+                    uint64_t diff = ld_u64_unaligned(T + lo_l) ^ ld_u64_unaligned(R + lo_l + d);
+                    if (hi_l > stopR) diff &= ~0ull >> (8 * (hi_l - stopR));
+                    if (diff) {
+                        m = lo_l + (__ffsll(static_cast<long long>(diff)) - 1) / 8;
+                        isData = 1;
+                    } else if (hi_l >= stopR) {
+                        m = stopR;
+                    }
+                } else {
                     m = stopR;
                 }
-            } else {
-                m = stopR;
             }
-            const unsigned bal = __ballot_sync(0xffffffffu, m != INT64_MIN);
-            if (bal) {
-                const int src = __ffs(bal) - 1;
-                mismR = __shfl_sync(0xffffffffu, m, src);
-                dataMismatchR = __shfl_sync(0xffffffffu, isData ? 1 : 0, src) != 0;
-                break;
+            const unsigned bal = (__ballot_sync(0xffffffffu, m != INT64_MIN) >> (8 * grp)) & 0xffu;
+            const int src = bal ? 8 * grp + __ffs(bal) - 1 : lane;
+            const int64_t mS = __shfl_sync(0xffffffffu, m, src);
+            const int dS = __shfl_sync(0xffffffffu, isData, src);
+            if (act) {
+                if (bal) {
+                    mismR = mS;
+                    dataMismatchR = dS != 0;
+                    act = false;
+                } else {
+                    loBeg += 64;
+                    act = loBeg < stopR;
+                }
             }
-            loBeg += 256;
         }
         const bool rightLinked = rightCand && !dataMismatchR;
-        if (lane == 0) {
+        if (valid && sub == 0) {
             RunRec rec;
             rec.firstPos = firstPos;
             rec.nSeeds = (lastPos - firstPos) / static_cast<uint32_t>(k1) + 1;
             rec.enc0 = enc0;
             rec.aFree = aFree;
             rec.bFree = static_cast<uint32_t>(mismR);
-            rec.flags = (leftLinked ? 1u : 0u) | (rightLinked ? 2u : 0u) | (static_cast<uint32_t>(c) << 2);
+            rec.flags = (leftLinked ? 1u : 0u) | (rightLinked ? 2u : 0u) | (c << 2);
             a.runs[r] = rec;
         }
     }
@@ -1052,7 +1092,7 @@ __global__ void __launch_bounds__(256) k_links(RunRec* __restrict__ runs, const 
 }
 
 int launch_extend(const IndexState& ix, const BatchDesc& b, const WorkBuffers& w, cudaStream_t st) {
-    ExtendArgs a{ix, b, w.tileCount, w.seedPos, w.seedEnc, w.seedN, w.runFirst, w.runStart, w.runs, w.counters};
+    ExtendArgs a{ix, b, w.seedPos, w.seedEnc, w.seedN, w.seedContig, w.runFirst, w.runStart, w.runs, w.counters};
     k_extend<<<device_sm_count() * 8, 256, 0, st>>>(a);
     k_links<<<device_sm_count() * 4, 256, 0, st>>>(w.runs, w.counters);
     return 2;
@@ -1370,7 +1410,7 @@ __global__ void __launch_bounds__(128) k_resolve(const ResolveArgs a) {
 // island lists -> one dense list; matchOffRun = exclusive scan of matchCountRun (matchOffRun[nRuns] = total)
 __global__ void __launch_bounds__(256) k_gather(const MatchRec* __restrict__ matches, const uint32_t* __restrict__ isHead,
                                                 const uint32_t* __restrict__ matchOffRun,
-                                                const uint32_t* __restrict__ runStart, MatchRec* __restrict__ dense,
+                                                const uint32_t* __restrict__ runStart, TextMatchRec* __restrict__ dense,
                                                 uint32_t* __restrict__ matchOff, int nContigs, uint32_t* counters) {
     if (counters[3]) return;
     const uint32_t nRuns = counters[1];
@@ -1378,7 +1418,15 @@ __global__ void __launch_bounds__(256) k_gather(const MatchRec* __restrict__ mat
     for (uint32_t r = gtid; r < nRuns; r += gsz) {
         if (!isHead[r]) continue;
         const uint32_t o = matchOffRun[r], n = matchOffRun[r + 1] - o;
-        for (uint32_t k = 0; k < n; k++) dense[o + k] = matches[r + k];
+        for (uint32_t k = 0; k < n; k++) {
+            const MatchRec m = matches[r + k];
+            TextMatchRec t;
+            t.posSrcText = m.src;
+            t.length = m.len;
+            t.posDestText = m.dst;
+            t.nextSrcRegionLoadingPos = 0;
+            dense[o + k] = t;
+        }
     }
     for (uint32_t c = gtid; c <= static_cast<uint32_t>(nContigs); c += gsz) matchOff[c] = matchOffRun[runStart[c]];
     if (gtid == 0) counters[2] = matchOffRun[nRuns];

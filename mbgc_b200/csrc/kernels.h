@@ -30,10 +30,14 @@ struct RunRec {          // one seed run = consecutive seeds on one diagonal, sp
     uint32_t flags;      // bit0 leftLinked (aFree = that of the previous run), bit1 rightLinked
 };
 
-struct MatchRec {        // 16 bytes, expanded to the 32-byte TextMatch on the host
+struct MatchRec {        // 16 bytes, device-internal
     uint64_t src;
     uint32_t dst;
     uint32_t len;
+};
+
+struct TextMatchRec {    // = PgTools::TextMatch (matching/TextMatchers.h:9-17), what the host receives
+    uint64_t posSrcText, length, posDestText, nextSrcRegionLoadingPos;
 };
 
 struct IndexState {      // frozen matcher state a match pass runs against
@@ -66,7 +70,8 @@ struct WorkBuffers {     // device scratch of one pass
     uint32_t* tileCount;     // [nChunks+1] seed segments per chunk -> exclusive scan in place (chunk offsets)
     uint32_t* chunkContig;   // [nChunks]
     unsigned long long* anchor;  // [nChunks] first verified seed among the first 16 positions: (pos in chunk << 32) | entry
-    uint8_t* chunkSegN;      // [nChunks] 1 = clean chunk (its entries are segments of k1-spaced seeds), 0 = plain seeds
+    uint8_t* chunkSegN;      // [nChunks] 0x80 | pin = clean chunk (pin = offset of its first grid position), 0 = full probe
+    uint2* chunkSeg;         // [nChunks] clean chunks: (table entry of group 0's seed, mask of 16-position groups with a seed)
     uint32_t* workList;      // [nChunks] chunks that need the full probe (fast path only)
     uint4* chunkDesc;        // [nChunks] text offset lo/hi, contig-local base position, nValid
     uint16_t* seedMask;      // [nChunks*32] per-lane 16-bit seed masks
@@ -74,15 +79,16 @@ struct WorkBuffers {     // device scratch of one pass
     uint32_t* seedPos;       // [seedCap] first target position of the segment
     uint32_t* seedEnc;       // [seedCap] table entry of its first seed
     uint8_t* seedN;          // [seedCap] seeds in the segment (spacing k1, entries ascending by k1 >> k1ord)
+    uint32_t* seedContig;    // [seedCap] contig (text) of the segment
     uint32_t* headScan;      // [seedCap+2] run-head flags -> scan; later the island-head flag of every run
     uint32_t* runFirst;      // [seedCap+2] first segment of every run; later matches per island -> scan
     RunRec* runs;            // [seedCap]
     uint32_t* runStart;      // [nContigs+1]
-    MatchRec* matches;       // [seedCap] per-contig regions at runStart[c]
+    MatchRec* matches;       // [seedCap] per-island regions at the island's first run
     unsigned long long* islandFwd;  // [seedCap/1024+2] per-tile carries of the island scans
     unsigned long long* islandBwd;
     uint32_t* matchOff;      // [nContigs+1]
-    MatchRec* matchesDense;  // [seedCap]
+    TextMatchRec* matchesDense;  // [seedCap] the pass's matches in text order, host layout
     uint32_t* blockSums;     // scan temporaries
     uint32_t* counters;      // [8]: 0 nSegments, 1 nRuns, 2 nMatches, 3 overflow flag, 5 work-list length
     uint32_t seedCap;

@@ -271,7 +271,7 @@ void B200SparseEMMatcher::matchTexts(std::vector<TextMatch>& resMatches, const c
         throw MatcherError(MBGCG_E_PARAM, "Source as destination and reverse-complement matching modes unsupported");
     std::vector<TextView> one{{destText, destLen}};
     matchBatch(one, &matchingLockPos, minMatchLength, false, nullptr, nullptr);
-    resMatches = resAll;
+    resMatches.assign(hMatches, hMatches + nMatchesAll);
 }
 
 void B200SparseEMMatcher::ensureWork(uint64_t textBytes, uint32_t nTiles, int nContigs, uint32_t seedCap) {
@@ -310,12 +310,14 @@ void B200SparseEMMatcher::ensureWork(uint64_t textBytes, uint32_t nTiles, int nC
     const uint64_t oAnchor = carve((static_cast<uint64_t>(nTiles) + 2) * 8);
     const uint64_t oChunkSegN = carve(static_cast<uint64_t>(nTiles) + 64);
     const uint64_t oWorkList = carve((static_cast<uint64_t>(nTiles) + 2) * 4);
+    const uint64_t oChunkSeg = carve((static_cast<uint64_t>(nTiles) + 2) * 8);
     const uint64_t oChunkDesc = carve((static_cast<uint64_t>(nTiles) + 2) * 16);
     const uint64_t oSeedMask = carve((static_cast<uint64_t>(nTiles) + 1) * 32 * 2);
     const uint64_t oScratchEnc = carve(scratchN * 4);
     const uint64_t oSeedPos = carve(static_cast<uint64_t>(seedCap) * 4);
     const uint64_t oSeedEnc = carve(static_cast<uint64_t>(seedCap) * 4);
     const uint64_t oSeedN = carve(static_cast<uint64_t>(seedCap) + 64);
+    const uint64_t oSeedContig = carve(static_cast<uint64_t>(seedCap) * 4);
     const uint64_t oHeadScan = carve((static_cast<uint64_t>(seedCap) + 2) * 4);
     const uint64_t oRunFirst = carve((static_cast<uint64_t>(seedCap) + 2) * 4);
     const uint64_t oRuns = carve(static_cast<uint64_t>(seedCap) * sizeof(RunRec));
@@ -324,7 +326,7 @@ void B200SparseEMMatcher::ensureWork(uint64_t textBytes, uint32_t nTiles, int nC
     const uint64_t oIslandFwd = carve((static_cast<uint64_t>(seedCap) / 1024 + 4) * 8);
     const uint64_t oIslandBwd = carve((static_cast<uint64_t>(seedCap) / 1024 + 4) * 8);
     const uint64_t oMatchOff = carve((static_cast<uint64_t>(nContigs) + 2) * 4);
-    const uint64_t oDense = carve(static_cast<uint64_t>(seedCap) * sizeof(MatchRec));
+    const uint64_t oDense = carve(static_cast<uint64_t>(seedCap) * sizeof(TextMatchRec));
     const uint64_t nScan = std::max<uint64_t>(nTiles, seedCap);
     const uint64_t oBlockSums = carve((nScan / 4096 + 8) * 4);
     const uint64_t oCounters = carve(64);
@@ -341,12 +343,14 @@ void B200SparseEMMatcher::ensureWork(uint64_t textBytes, uint32_t nTiles, int nC
     wb.anchor = reinterpret_cast<unsigned long long*>(dWork + oAnchor);
     wb.chunkSegN = dWork + oChunkSegN;
     wb.workList = reinterpret_cast<uint32_t*>(dWork + oWorkList);
+    wb.chunkSeg = reinterpret_cast<uint2*>(dWork + oChunkSeg);
     wb.chunkDesc = reinterpret_cast<uint4*>(dWork + oChunkDesc);
     wb.seedMask = reinterpret_cast<uint16_t*>(dWork + oSeedMask);
     wb.scratchEnc = reinterpret_cast<uint32_t*>(dWork + oScratchEnc);
     wb.seedPos = reinterpret_cast<uint32_t*>(dWork + oSeedPos);
     wb.seedEnc = reinterpret_cast<uint32_t*>(dWork + oSeedEnc);
     wb.seedN = dWork + oSeedN;
+    wb.seedContig = reinterpret_cast<uint32_t*>(dWork + oSeedContig);
     wb.headScan = reinterpret_cast<uint32_t*>(dWork + oHeadScan);
     wb.runFirst = reinterpret_cast<uint32_t*>(dWork + oRunFirst);
     wb.runs = reinterpret_cast<RunRec*>(dWork + oRuns);
@@ -355,7 +359,7 @@ void B200SparseEMMatcher::ensureWork(uint64_t textBytes, uint32_t nTiles, int nC
     wb.islandFwd = reinterpret_cast<unsigned long long*>(dWork + oIslandFwd);
     wb.islandBwd = reinterpret_cast<unsigned long long*>(dWork + oIslandBwd);
     wb.matchOff = reinterpret_cast<uint32_t*>(dWork + oMatchOff);
-    wb.matchesDense = reinterpret_cast<MatchRec*>(dWork + oDense);
+    wb.matchesDense = reinterpret_cast<TextMatchRec*>(dWork + oDense);
     wb.blockSums = reinterpret_cast<uint32_t*>(dWork + oBlockSums);
     wb.counters = reinterpret_cast<uint32_t*>(dWork + oCounters);
     wb.seedCap = seedCap;
@@ -463,7 +467,7 @@ void B200SparseEMMatcher::matchBatch(const std::vector<TextView>& texts, const u
     if (minMatchLength < static_cast<uint32_t>(K))
         throw MatcherError(MBGCG_E_PARAM, "Minimal matching length cannot be smaller than K (" +
                                               std::to_string(minMatchLength) + " < " + std::to_string(K) + ")");
-    resAll.clear();
+    nMatchesAll = 0;
     resCounts.assign(texts.size(), 0);
     for (auto& m : stageMs) m = 0;
     for (auto& c : lastCounters) c = 0;
@@ -581,29 +585,22 @@ void B200SparseEMMatcher::matchBatch(const std::vector<TextView>& texts, const u
                 continue;
             }
             const uint32_t total = hOffs[nC];
-            if (total > hMatchesCap) {
+            if (nMatchesAll + total > hMatchesCap) {  // grow the pinned result buffer, keeping earlier passes
+                const uint64_t cap = (nMatchesAll + total) + (nMatchesAll + total) / 2 + 4096;
+                TextMatch* grown = nullptr;
+                check(cudaHostAlloc(&grown, cap * sizeof(TextMatch), cudaHostAllocDefault), "cudaHostAlloc(matches)");
+                if (nMatchesAll) std::memcpy(grown, hMatches, nMatchesAll * sizeof(TextMatch));
                 if (hMatches) cudaFreeHost(hMatches);
-                hMatches = nullptr;
-                hMatchesCap = 0;
-                const uint64_t cap = static_cast<uint64_t>(total) + total / 2 + 4096;
-                check(cudaHostAlloc(&hMatches, cap * sizeof(MatchRec), cudaHostAllocDefault), "cudaHostAlloc(matches)");
+                hMatches = grown;
                 hMatchesCap = cap;
             }
-            if (total)
-                check(cudaMemcpyAsync(hMatches, wb.matchesDense, static_cast<uint64_t>(total) * sizeof(MatchRec),
+            TextMatch* passMatches = hMatches + nMatchesAll;
+            if (total)  // the gather kernel already wrote the host layout (TextMatch): no conversion on the host
+                check(cudaMemcpyAsync(passMatches, wb.matchesDense, static_cast<uint64_t>(total) * sizeof(TextMatch),
                                       cudaMemcpyDeviceToHost, stream), "D2H(matches)");
             check(cudaEventRecord(ev[6], stream), "event");
             check(cudaStreamSynchronize(stream), "D2H sync");
-
-            const size_t base = resAll.size();
-            resAll.resize(base + total);
-            for (uint32_t k = 0; k < total; k++) {
-                TextMatch& m = resAll[base + k];
-                m.posSrcText = hMatches[k].src;
-                m.length = hMatches[k].len;
-                m.posDestText = hMatches[k].dst;
-                m.nextSrcRegionLoadingPos = 0;
-            }
+            nMatchesAll += total;
             for (int c = 0; c < nC; c++) resCounts[first + c] = hOffs[c + 1] - hOffs[c];
             float ms;
             for (int s = 0; s < 6; s++) {
@@ -623,9 +620,10 @@ void B200SparseEMMatcher::matchBatch(const std::vector<TextView>& texts, const u
                 cleanEstimate = static_cast<double>(tiles - std::min(hCtr[5], tiles)) / tiles;
             } else if (positions) {
                 uint64_t covered = 0;
-                for (uint32_t k = 0; k < total; k++)
-                    if (hMatches[k].len >= 1024) covered += hMatches[k].len;
-                cleanEstimate = static_cast<double>(covered) / static_cast<double>(positions);
+                const uint32_t stride = total / 4096 + 1;  // a sample is enough for the policy
+                for (uint32_t k = 0; k < total; k += stride)
+                    if (passMatches[k].length >= 1024) covered += passMatches[k].length;
+                cleanEstimate = static_cast<double>(covered) * stride / static_cast<double>(positions);
             }
             lastCounters[6] += tiles;
             lastCounters[7] += useFast ? hCtr[5] : tiles;

@@ -81,7 +81,8 @@ public:
     // n texts against the same frozen state in one device pass; results concatenated in text order
     void matchBatch(const std::vector<TextView>& texts, const uint64_t* lockPos, uint32_t minMatchLength,
                     bool textsOnDevice, const void* dTextBase, const uint64_t* dOffsets);
-    const std::vector<TextMatch>& batchMatches() const { return resAll; }
+    const TextMatch* batchMatches() const { return hMatches; }   // pinned, valid until the next match call
+    uint64_t batchMatchCount() const { return nMatchesAll; }
     const std::vector<uint64_t>& batchCounts() const { return resCounts; }
 
     // inspection
@@ -138,9 +139,9 @@ private:
     uint8_t* dWork = nullptr; uint64_t dWorkCap = 0;
     WorkBuffers wb{};
     uint32_t wbTiles = 0; int wbContigs = 0;
-    MatchRec* hMatches = nullptr; uint64_t hMatchesCap = 0;  // pinned
+    TextMatch* hMatches = nullptr; uint64_t hMatchesCap = 0;  // pinned; all passes of the last call, text order
+    uint64_t nMatchesAll = 0;
     uint32_t* hCounts = nullptr; uint64_t hCountsCap = 0;    // pinned
-    std::vector<TextMatch> resAll;
     std::vector<uint64_t> resCounts;
 };
 

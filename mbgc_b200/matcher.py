@@ -146,8 +146,9 @@ class Matcher:
                                          C.byref(out), C.byref(n)))
         return self._matches(out, n.value)
 
-    def matchBatch(self, texts, minMatchLength=32, lockPos=None):
-        """list of texts -> list of (n_i, 3) arrays, all matched against the same frozen state."""
+    def matchBatch(self, texts, minMatchLength=32, lockPos=None, copy=True):
+        """list of texts -> list of (n_i, 3) arrays, all matched against the same frozen state.
+        copy=False returns views of the library's pinned result buffer (valid until the next match call)."""
         arrs = [_as_u8(t) for t in texts]
         n = len(arrs)
         ptrs = (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
@@ -156,9 +157,9 @@ class Matcher:
         out, counts = C.c_void_p(), C.c_void_p()
         self._check(self.lib.mbgcg_match_batch(self.h, n, ptrs, lens, minMatchLength, locks, C.byref(out),
                                                C.byref(counts)))
-        return self._split(out, counts, n)
+        return self._split(out, counts, n, copy)
 
-    def matchBatchDevice(self, dTextPtr, offsets, lens, minMatchLength=32, lockPos=None):
+    def matchBatchDevice(self, dTextPtr, offsets, lens, minMatchLength=32, lockPos=None, copy=True):
         """texts already resident in device memory (see mbgcg_match_batch_device for the layout rules)."""
         n = len(lens)
         offs = (C.c_uint64 * n)(*offsets)
@@ -167,7 +168,7 @@ class Matcher:
         out, counts = C.c_void_p(), C.c_void_p()
         self._check(self.lib.mbgcg_match_batch_device(self.h, dTextPtr, n, offs, ls, minMatchLength, locks,
                                                       C.byref(out), C.byref(counts)))
-        return self._split(out, counts, n)
+        return self._split(out, counts, n, copy)
 
     def acquireWorkerMatchingLockPos(self):
         return self.lib.mbgcg_acquire_lock(self.h)
@@ -231,17 +232,14 @@ class Matcher:
 
     # -- helpers -------------------------------------------------------------------------------------
     @staticmethod
-    def _matches(out, n):
+    def _matches(out, n, copy=True):
         if n == 0:
             return np.zeros((0, 3), dtype=np.uint64)
         a = np.ctypeslib.as_array(C.cast(out, u64p), shape=(n, 4))
-        return a[:, :3].copy()
+        return a[:, :3].copy() if copy else a[:, :3]
 
-    def _split(self, out, counts, n):
+    def _split(self, out, counts, n, copy=True):
         cnt = np.ctypeslib.as_array(C.cast(counts, u64p), shape=(n,)).copy() if n else np.zeros(0, np.uint64)
-        allm = self._matches(out, int(cnt.sum()))
-        res, o = [], 0
-        for c in cnt:
-            res.append(allm[o:o + int(c)])
-            o += int(c)
-        return res
+        allm = self._matches(out, int(cnt.sum()), copy)
+        ends = np.cumsum(cnt.astype(np.int64))
+        return [allm[int(e - c):int(e)] for c, e in zip(cnt, ends)]
