@@ -55,7 +55,9 @@ def parse_args():
     ap.add_argument("--tier", default="near", choices=list(TIERS))
     ap.add_argument("--mode", type=int, default=0, help="MBGC mode the matcher parameters come from (0..3)")
     ap.add_argument("--cpu-sample", type=int, default=100, help="genomes of the batch the CPU baseline is timed on")
+    ap.add_argument("--cpu-sample-other", type=int, default=32, help="same for the secondary tier")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-other-tier", action="store_true", help="skip the secondary similarity tier")
     return ap.parse_args()
 
 
@@ -81,9 +83,10 @@ def peaks():
 
 
 def probe_traffic():
-    """dram bytes per probe launch from the committed ncu capture, if one matches this workload"""
+    """measured DRAM bytes per target position of the main kernels (profiles/traffic.json, written from the
+    committed `ncu --set full` captures of this workload)"""
     try:
-        with open(os.path.join(ROOT, "profiles", "probe_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             return json.load(f)
     except Exception:
         return None
@@ -209,20 +212,38 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
-def run_b200(args, rank, world):
+# Algorithmic bytes per target position of each kernel group (DESIGN.md section 4 derives them).
+#   contract  SURVEY.md 8d: 6.0 B per target position for the whole match stage (probe every position)
+#   k_probe   the same 6.0 B, for the positions it actually probes (all of them without the fast path)
+#   k_clean   1 B text + (16 B descriptor + 8 B anchor + 16 B memo words + 13 B result) per 512-position chunk;
+#             the reference bytes on the diagonal are a second byte per position, served by L2 while the loaded
+#             reference fits it (10 MB here) and by HBM otherwise
+#   k_anchor  48 B text + 16 occupancy words + table slot + 32 B reference + 24 B descriptor/result per chunk
+STAGE_KERNELS = {"anchor": "k_anchor", "clean": "k_clean", "fullprobe": "k_probe",
+                 "compact": "k_compact + k_heads + k_runs + scans", "extend": "k_extend + k_links",
+                 "resolve": "k_island_* + k_resolve + k_gather"}
+
+
+def kernel_alg_bytes(group, counters, ref_bytes):
+    pos, chunks = counters["positions"], max(1, counters["chunks"])
+    if group == "fullprobe":
+        return ALG_BYTES_PER_POSITION * 512.0 * counters["chunks_full_probe"]
+    if group == "clean":
+        return pos * (1.0 + (0.0 if ref_bytes <= 100e6 else 1.0)) + chunks * 53.0
+    if group == "anchor":
+        return chunks * (48 + 64 + 8 + 32 + 24.0)
+    return None
+
+
+def measure_tier(args, tier, rank, world, dist, local):
+    """(line fragments for one tier) value / e2e / stage times / counters on this rank's batch"""
     import torch
     import mbgc_b200
     from mbgc_b200.dist import max_over_ranks
 
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist_mod
-        dist = dist_mod
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    base, targets = make_batch(args, rank)
+    targs = argparse.Namespace(**vars(args))
+    targs.tier = tier
+    base, targets = make_batch(targs, rank)
     n = len(targets)
     limit = mgmp_ref_limit(args.genomes * world + 1, base.size)
     sm = skip_margin_of(args.mode)
@@ -253,8 +274,8 @@ def run_b200(args, rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn):
-        for _ in range(args.warmup):
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
             fn()
         stage = {k: 0.0 for k in mbgc_b200.matcher.T_NAMES}
         launches0 = m.totalLaunches()
@@ -262,68 +283,132 @@ def run_b200(args, rank, world):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         res = None
-        for _ in range(args.steps):
+        for _ in range(steps):
             res = fn()
             for k, v in m.timing().items():
                 stage[k] += v
         e1.record(stream)
         barrier()
         ms = max_over_ranks(e0.elapsed_time(e1), "cuda")  # device time, max over ranks
-        return ms, stage, m.totalLaunches() - launches0, res
+        return ms, {k: v / steps for k, v in stage.items()}, m.totalLaunches() - launches0, res
+
+    steps, warmup = args.steps, args.warmup
+    ms_dev, stage_dev, launches, res = timed(
+        lambda: m.matchBatchDevice(dbuf.data_ptr(), offs, lens, 32, copy=False), steps, warmup)
+    n_matches = int(sum(len(r) for r in res))
+    counters = m.counters()
+    host_ptrs = [p.numpy() for p in pinned]
+    ms_e2e, stage_e2e, _, res2 = timed(lambda: m.matchBatch(host_ptrs, 32, copy=False), steps, warmup)
+    assert n_matches == int(sum(len(r) for r in res2)), "device-resident and host-buffer passes disagree"
+    state = m.state()
+    out = dict(base=base, targets=targets, limit=limit, sm=sm, n=n, lens=lens, fbytes=fbytes, index_s=index_s,
+               ms_dev=ms_dev, stage_dev=stage_dev, launches=launches, n_matches=n_matches, counters=counters,
+               ms_e2e=ms_e2e, stage_e2e=stage_e2e, table_slots=state["hashSize"], ref_bytes=int(state["pos1"]))
+    m.close()
+    del dbuf
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_b200(args, rank, world):
+    import torch
+
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     sampler = ClockSampler(local)
     sampler.start()
-    ms_dev, stage_dev, launches, res = timed(lambda: m.matchBatchDevice(dbuf.data_ptr(), offs, lens, 32, copy=False))
-    counters = m.counters()
-    host_ptrs = [p.numpy() for p in pinned]
-    ms_e2e, stage_e2e, _, res2 = timed(lambda: m.matchBatch(host_ptrs, 32, copy=False))
+    r = measure_tier(args, args.tier, rank, world, dist, local)
     sampler.stop_flag = True
     sampler.join(timeout=2)
-    n_matches = int(sum(len(r) for r in res))
-    assert n_matches == int(sum(len(r) for r in res2)), "device-resident and host-buffer passes disagree"
 
+    steps = args.steps
+    n, lens, fbytes, counters = r["n"], r["lens"], r["fbytes"], r["counters"]
+    stage_dev = r["stage_dev"]
     total_bytes = fbytes * world  # every rank has a batch of the same shape
-    value = total_bytes * args.steps / (ms_dev / 1e3) / 1e9
-    e2e = total_bytes * args.steps / (ms_e2e / 1e3) / 1e9
+    value = total_bytes * steps / (r["ms_dev"] / 1e3) / 1e9
+    e2e = total_bytes * steps / (r["ms_e2e"] / 1e3) / 1e9
     peak, peak_src = peaks()
-    probe_launches = max(1, counters["passes"])  # one k_probe launch per pass of at most 256 MiB of text
-    probe_ms = stage_dev["probe"] / args.steps / probe_launches
-    alg_bytes = ALG_BYTES_PER_POSITION * counters["positions"] / probe_launches
-    achieved = alg_bytes / (probe_ms / 1e3) / 1e9
-    kernels_ms = (stage_dev["probe"] + stage_dev["compact"] + stage_dev["extend"] + stage_dev["resolve"]) / args.steps
+    passes = max(1, counters["passes"])  # every kernel is launched once per pass (at most 1 GiB of text)
+    groups = ["anchor", "clean", "fullprobe", "compact", "extend", "resolve"]
+    kernels_ms = sum(stage_dev[g] for g in groups)
+    with_bytes = [g for g in groups if kernel_alg_bytes(g, counters, r["ref_bytes"])]
+    dom = max(with_bytes, key=lambda g: stage_dev[g])  # dominant kernel among those that stream the texts
+    dom_ms = stage_dev[dom] / passes
+    dom_bytes = kernel_alg_bytes(dom, counters, r["ref_bytes"]) / passes
+    achieved = dom_bytes / (dom_ms / 1e3) / 1e9
+    stage_achieved = ALG_BYTES_PER_POSITION * counters["positions"] / (kernels_ms / 1e3) / 1e9
     tr = probe_traffic()
+    traffic = None
+    if tr and STAGE_KERNELS[dom] in tr:
+        traffic = tr[STAGE_KERNELS[dom]]["dram_bytes_per_position"] * counters["positions"] / passes
     line = {
         "metric": "compression input GB/s (match stage)", "value": value, "unit": "GB/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+        "steps": steps, "warmup": args.warmup, "ms_per_step": r["ms_dev"] / steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": workload_name(args), "genomes_per_gpu": n, "bases_per_gpu": int(sum(lens)),
-                   "fasta_bytes_per_gpu": int(fbytes), "matches_per_gpu": n_matches, "seeds": counters["seeds"],
-                   "seed_runs": counters["runs"], "ref_limit": int(limit), "table_slots": m.state()["hashSize"],
-                   "skip_margin": sm, "l2": "inputs (>= 500 MB per step) exceed the 126 MB L2; no explicit flush",
-                   "index_build_s": index_s, "parallelism": f"targets sharded over {world} GPU(s), index replicated"},
-        "roofline": {"bound": "hbm", "kernel": "k_probe", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": tr["dram_bytes_per_launch"] if tr else None,
-                     "peak_source": peak_src, "alg_bytes_per_launch": alg_bytes, "launch_ms": probe_ms,
-                     "stage_frac": ALG_BYTES_PER_POSITION * counters["positions"] / (kernels_ms / 1e3) / 1e9 / peak,
-                     "stage_ms": {k: v / args.steps for k, v in stage_dev.items()}},
+                   "fasta_bytes_per_gpu": int(fbytes), "matches_per_gpu": r["n_matches"],
+                   "seed_segments": counters["seeds"], "seed_runs": counters["runs"], "chunks": counters["chunks"],
+                   "chunks_full_probe": counters["chunks_full_probe"], "ref_limit": int(r["limit"]),
+                   "table_slots": r["table_slots"], "skip_margin": r["sm"],
+                   "l2": "inputs (>= 500 MB per step) exceed the 126 MB L2; no explicit flush",
+                   "index_build_s": r["index_s"],
+                   "parallelism": f"targets sharded over {world} GPU(s), index replicated"},
+        "roofline": {"bound": "hbm", "kernel": STAGE_KERNELS[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "alg_bytes_per_launch": dom_bytes, "launch_ms": dom_ms, "launches_per_step": passes,
+                     "share_of_stage": stage_dev[dom] / kernels_ms,
+                     "stage": {"what": "all kernels of the match stage against the SURVEY 8d contract "
+                                       "(6.0 algorithmic bytes per target position)",
+                               "achieved": stage_achieved, "frac": stage_achieved / peak, "ms": kernels_ms},
+                     "stage_ms": stage_dev},
         "e2e": {"value": e2e, "unit": "GB/s", "h2d_bytes_per_step": int(sum(lens)),
-                "d2h_bytes_per_step": int(n_matches * 16 + (n + 9) * 4), "ms_per_step": ms_e2e / args.steps,
-                "stage_ms": {k: v / args.steps for k, v in stage_e2e.items()}},
-        "gpu_launches": int(launches),
+                "d2h_bytes_per_step": int(r["n_matches"] * 32 + (n + 9) * 4), "ms_per_step": r["ms_e2e"] / steps,
+                "stage_ms": r["stage_e2e"]},
+        "gpu_launches": int(r["launches"]),
         "clocks": sampler.summary(),
     }
     if rank == 0 and world == 1 and not args.no_cpu:
-        sample = targets[:max(1, min(args.cpu_sample, n))]
+        sample = r["targets"][:max(1, min(args.cpu_sample, n))]
         sbytes = sum(fasta_bytes(t.size, HEADER_LEN) for t in sample)
         threads = os.cpu_count() or 1
-        dt, kind, total, cores = cpu_match_stage(base, sample, limit, sm, threads)
-        line["cpu_baseline"] = {"value": sbytes / dt / 1e9, "unit": "GB/s", "cores": cores, "kind": kind,
+        reps, spent, total, kind, cores = 0, 0.0, 0, "port", 1
+        while reps < 3 or (spent < 2.0 and reps < 40):  # a pass is ~10 ms on the near tier: average a few
+            dt, kind, total, cores = cpu_match_stage(r["base"], sample, r["limit"], r["sm"], threads)
+            spent += dt
+            reps += 1
+        line["cpu_baseline"] = {"value": sbytes * reps / spent / 1e9, "unit": "GB/s", "cores": cores, "kind": kind,
                                 "sample": f"{len(sample)} of the {n} target genomes ({sbytes / 1e6:.0f} MB FASTA), "
-                                          f"one pass, matchTexts against the frozen G0+RC index, {dt:.2f} s",
+                                          f"{reps} passes of matchTexts against the frozen G0+RC index, "
+                                          f"{spent / reps * 1e3:.1f} ms each",
                                 "matches": total}
+    # the collection's other similarity tier (SURVEY.md 8d defines C2 with both), fewer steps
+    other = "div" if args.tier == "near" else "near"
+    if not args.no_other_tier:
+        oargs = argparse.Namespace(**vars(args))
+        oargs.steps, oargs.warmup = max(2, args.steps // 2), 3
+        o = measure_tier(oargs, other, rank, world, dist, local)
+        okern = sum(o["stage_dev"][g] for g in groups)
+        line["other_tier"] = {
+            "tier": other, "value": o["fbytes"] * world * oargs.steps / (o["ms_dev"] / 1e3) / 1e9,
+            "e2e": o["fbytes"] * world * oargs.steps / (o["ms_e2e"] / 1e3) / 1e9, "unit": "GB/s",
+            "ms_per_step": o["ms_dev"] / oargs.steps, "matches_per_gpu": o["n_matches"],
+            "chunks": o["counters"]["chunks"], "chunks_full_probe": o["counters"]["chunks_full_probe"],
+            "stage_frac": ALG_BYTES_PER_POSITION * o["counters"]["positions"] / (okern / 1e3) / 1e9 / peak,
+            "stage_ms": o["stage_dev"]}
+        if rank == 0 and world == 1 and not args.no_cpu:
+            sample = o["targets"][:max(1, min(args.cpu_sample_other, o["n"]))]
+            sbytes = sum(fasta_bytes(t.size, HEADER_LEN) for t in sample)
+            dt, kind, total, cores = cpu_match_stage(o["base"], sample, o["limit"], o["sm"], os.cpu_count() or 1)
+            line["other_tier"]["cpu_baseline"] = {"value": sbytes / dt / 1e9, "unit": "GB/s", "cores": cores,
+                                                  "kind": kind, "sample": f"{len(sample)} genomes, one pass, {dt:.2f} s"}
     if rank == 0:
         print(json.dumps(line), flush=True)
-    m.close()
     if dist is not None:
         dist.destroy_process_group()
 

@@ -455,8 +455,11 @@ __global__ void __launch_bounds__(FILTER ? PROBE_THREADS_FILTER : PROBE_THREADS_
 //           ("self-probe").  memoX has one bit per 16 reference positions: 0 = probing those 16 positions
 //           gives exactly the default answer -- one seed, at the sampled (16-aligned) position, pointing at
 //           itself; 1 = anything else (a repeat found elsewhere, an overwritten or unsampled slot).
-//   k_anchor  one LANE per chunk probes the chunk's first 16 positions in full; the first verified seed
-//           proposes the chunk's diagonal d (reference position - target position).
+//   k_anchor  one LANE per anchored chunk (every 8th chunk and the first chunk of a contig) probes the chunk's
+//           first 16 positions in full; the first verified seed proposes a diagonal d (reference position -
+//           target position) for that chunk and the chunks up to the next anchored one.  A proposal is only a
+//           guess -- k_clean verifies every byte -- so a wrong one (an indel in between) merely sends chunks
+//           to the full probe.
 //   k_clean   one WARP per chunk: if the chunk's 512 + K-1 bytes equal the reference on diagonal d, all
 //           covered memo bits are 0 and the window class is uniform, then the chunk's seeds are exactly the 32
 //           positions with (i + d) % 16 == 0 and entries (i + d) >> 4: it leaves as ONE 32-seed segment.
@@ -470,7 +473,18 @@ template <int KW>
 __global__ void __launch_bounds__(256) k_anchor(const ProbeArgs a) {
     constexpr int NPT = PROBE_NPT;
     constexpr int NWA = probe_words(KW);
-    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < a.b.nTiles; g += gridDim.x * blockDim.x) {
+    // anchored chunks: every ANCHOR_STRIDE-th chunk, and the first chunk of every contig
+    const uint32_t nStride = (a.b.nTiles + ANCHOR_STRIDE - 1) / ANCHOR_STRIDE;
+    const uint32_t nItems = nStride + static_cast<uint32_t>(a.b.nContigs);
+    for (uint32_t it = blockIdx.x * blockDim.x + threadIdx.x; it < nItems; it += gridDim.x * blockDim.x) {
+        uint32_t g;
+        if (it < nStride) {
+            g = it * ANCHOR_STRIDE;
+        } else {
+            const uint32_t c = it - nStride;
+            g = a.b.tileStart[c];
+            if (g == a.b.tileStart[c + 1] || g % ANCHOR_STRIDE == 0) continue;  // no chunk, or covered above
+        }
         const uint4 desc = __ldg(&a.chunkDesc[g]);
         const uint8_t* ctext = a.b.text + ((static_cast<uint64_t>(desc.y) << 32) | desc.x);
         const uint32_t base = desc.z, nValid = desc.w;
@@ -537,14 +551,17 @@ __global__ void __launch_bounds__(256) k_clean(const CleanArgs a) {
         const bool valid = gb + cg < nTiles;
         const uint32_t g = valid ? gb + cg : nTiles - 1;
         const uint4 desc = __ldg(&a.chunkDesc[g]);
-        const unsigned long long an = a.anchor[g];
+        const uint32_t base = desc.z, nValid = desc.w;
+        // diagonal proposal: the anchor of the nearest anchored chunk at or before this one in the same contig
+        const uint32_t back = min(g % ANCHOR_STRIDE, base / PROBE_CHUNK);
+        const unsigned long long an = a.anchor[g - back];
         uint64_t lock = NO_LOCK;
         if (a.b.contigLock) lock = __ldg(&a.b.contigLock[__ldg(&a.chunkContig[g])]);
-        const uint32_t base = desc.z, nValid = desc.w;
         const uint32_t enc = static_cast<uint32_t>(an);
         bool ok = valid && enc != 0 && base + PROBE_CHUNK <= nValid;
-        // reference position of the chunk start on the anchor's diagonal
-        const int64_t r0 = static_cast<int64_t>(decode_pos(enc, a.ix.k1ord)) - static_cast<int64_t>(an >> 32);
+        // reference position of the chunk start on the proposed diagonal
+        const int64_t r0 = static_cast<int64_t>(decode_pos(enc, a.ix.k1ord)) - static_cast<int64_t>(an >> 32) +
+                           static_cast<int64_t>(back) * PROBE_CHUNK;
         ok = ok && r0 >= 1 && static_cast<uint64_t>(r0) + PROBE_CHUNK + K - 1 <= a.memoLen;
         const uint32_t pin = (16u - (static_cast<uint32_t>(r0) & 15u)) & 15u;  // first position with (i + d) % 16 == 0
         if (ok) {
@@ -565,30 +582,34 @@ __global__ void __launch_bounds__(256) k_clean(const CleanArgs a) {
         const uint64_t xw = (static_cast<uint64_t>(__ldg(&a.memoX[wi + 1])) << 32 | __ldg(&a.memoX[wi])) >> ws;
         const uint64_t ew = (static_cast<uint64_t>(__ldg(&a.memoE[wi + 1])) << 32 | __ldg(&a.memoE[wi])) >> ws;
 
-        // 512 + K-1 bytes of text against the reference on the diagonal
+        // 512 + K-1 bytes of text against the reference on the diagonal.  The reference side is unaligned: three
+        // 8-byte loads cover a 16-byte piece (24-byte window from the 8-byte boundary below it), a select picks the
+        // 5 words the piece touches and a funnel shift per word removes the byte offset.  (Five 4-byte loads would
+        // make every lane group request the same sectors five times: L1TEX sector throughput was the limit.)
         const uintptr_t ra = reinterpret_cast<uintptr_t>(R + 16 * sub);
-        const uint32_t* rp = reinterpret_cast<const uint32_t*>(ra & ~static_cast<uintptr_t>(3));
+        const uint2* rp = reinterpret_cast<const uint2*>(ra & ~static_cast<uintptr_t>(7));
+        const bool hiHalf = (ra & 4) != 0;
         const uint32_t sh = static_cast<uint32_t>(ra & 3) * 8;
         const uint4* tp = reinterpret_cast<const uint4*>(T) + sub;
-        uint4 tw[4];
-        uint32_t rw[4][5];
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            tw[k] = __ldg(tp + 8 * k);
-#pragma unroll
-            for (int m = 0; m < 5; m++) rw[k][m] = __ldg(rp + 32 * k + m);
-        }
         uint32_t diff = 0;
 #pragma unroll
-        for (int k = 0; k < 4; k++)
-            diff |= (tw[k].x ^ __funnelshift_r(rw[k][0], rw[k][1], sh)) | (tw[k].y ^ __funnelshift_r(rw[k][1], rw[k][2], sh)) |
-                    (tw[k].z ^ __funnelshift_r(rw[k][2], rw[k][3], sh)) | (tw[k].w ^ __funnelshift_r(rw[k][3], rw[k][4], sh));
+        for (int k = 0; k < 4; k++) {
+            const uint4 tw = __ldg(tp + 8 * k);
+            const uint2 a0 = __ldg(rp + 16 * k), a1 = __ldg(rp + 16 * k + 1), a2 = __ldg(rp + 16 * k + 2);
+            const uint32_t w0 = hiHalf ? a0.y : a0.x, w1 = hiHalf ? a1.x : a0.y, w2 = hiHalf ? a1.y : a1.x,
+                           w3 = hiHalf ? a2.x : a1.y, w4 = hiHalf ? a2.y : a2.x;
+            diff |= (tw.x ^ __funnelshift_r(w0, w1, sh)) | (tw.y ^ __funnelshift_r(w1, w2, sh)) |
+                    (tw.z ^ __funnelshift_r(w2, w3, sh)) | (tw.w ^ __funnelshift_r(w3, w4, sh));
+        }
+        {
+            const uint32_t* rw = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(R) & ~static_cast<uintptr_t>(3));
 #pragma unroll
-        for (int w = 0; w < 2; w++) {  // tail: word sub, and word sub + 8 for K > 32
-            const int tl = sub + 8 * w;
-            if (tl < tailWords) {
-                const uint32_t* rt = rp - 4 * sub + PROBE_CHUNK / 4 + tl;  // R + PROBE_CHUNK + 4 tl, rounded down to a word
-                diff |= __ldg(reinterpret_cast<const uint32_t*>(T + PROBE_CHUNK) + tl) ^ __funnelshift_r(__ldg(rt), __ldg(rt + 1), sh);
+            for (int w = 0; w < 2; w++) {  // tail: word sub, and word sub + 8 for K > 32
+                const int tl = sub + 8 * w;
+                if (tl < tailWords) {
+                    const uint32_t* rt = rw + PROBE_CHUNK / 4 + tl;  // R + PROBE_CHUNK + 4 tl, rounded down to a word
+                    diff |= __ldg(reinterpret_cast<const uint32_t*>(T + PROBE_CHUNK) + tl) ^ __funnelshift_r(__ldg(rt), __ldg(rt + 1), sh);
+                }
             }
         }
         const unsigned bad = (__ballot_sync(0xffffffffu, diff != 0) >> (8 * cg)) & 0xffu;
@@ -670,8 +691,8 @@ __global__ void __launch_bounds__(256) k_chunk_contig(BatchDesc b, int K, uint32
 template <int KW>
 static void launch_probe_k(const ProbeArgs& a, bool useFilter, int mode, cudaStream_t st) {
     const int sm = device_sm_count();
-    if (mode == 1) {  // anchors: one lane per chunk
-        uint32_t blocks = (a.b.nTiles + 255) / 256;
+    if (mode == 1) {  // anchors: one lane per anchored chunk
+        uint32_t blocks = (a.b.nTiles / ANCHOR_STRIDE + a.b.nContigs + 256) / 256;
         const uint32_t cap = static_cast<uint32_t>(sm) * 8;
         if (blocks > cap) blocks = cap;
         k_anchor<KW><<<blocks, 256, 0, st>>>(a);

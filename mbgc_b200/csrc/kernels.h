@@ -19,6 +19,7 @@ constexpr int PROBE_THREADS_FILTER = 768;           // 1 CTA per SM next to the 
 constexpr int PROBE_THREADS_PLAIN = 512;
 constexpr uint32_t PROBE_FILTER_BYTES = 192 * 1024; // first-level filter, copied to shared memory by every CTA
 constexpr uint32_t PROBE_FILTER_BITS = PROBE_FILTER_BYTES * 8;
+constexpr uint32_t ANCHOR_STRIDE = 8;               // fast path: one diagonal proposal per 8 chunks (and per contig start)
 constexpr uint64_t NO_LOCK = UINT64_MAX;
 
 struct RunRec {          // one seed run = consecutive seeds on one diagonal, spacing k1 (24 bytes)

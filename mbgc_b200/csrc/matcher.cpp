@@ -478,7 +478,7 @@ void B200SparseEMMatcher::matchBatch(const std::vector<TextView>& texts, const u
     // split into passes of bounded size (work memory is ~26 bytes per target position)
     static const uint64_t maxPassBytes = [] {
         const char* e = std::getenv("MBGC_B200_MAX_PASS_BYTES");
-        return e ? std::strtoull(e, nullptr, 10) : (256ull << 20);
+        return e ? std::strtoull(e, nullptr, 10) : (1024ull << 20);
     }();
     size_t first = 0;
     while (first < texts.size()) {

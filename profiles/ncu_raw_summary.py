@@ -1,20 +1,32 @@
-"""Key metrics of an `ncu --page raw --csv` dump (first kernel row).  usage: python profiles/ncu_raw_summary.py raw.csv"""
+"""Key metrics of an `ncu --page raw --csv` dump (every kernel row).  usage: python profiles/ncu_raw_summary.py raw.csv"""
 import csv
 import sys
 
 WANT = ["Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
-        "launch__shared_mem_per_block_dynamic", "dram__bytes_read.sum", "dram__bytes_write.sum",
-        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sectors.sum", "lts__t_sector_hit_rate.pct",
-        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__t_sector_hit_rate.pct",
-        "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_lsu_wavefronts.sum",
+        "launch__shared_mem_per_block_dynamic", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "lts__t_sectors.sum", "lts__t_sector_hit_rate.pct", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__t_sector_hit_rate.pct", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum",
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
         "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
-        "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
         "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
-        "sm__cycles_active.avg"]
+        "sm__cycles_elapsed.avg"]
 rows = list(csv.reader(open(sys.argv[1])))
-hdr, units, first = rows[0], rows[1], rows[2]
-for w in WANT:
-    if w in hdr:
-        i = hdr.index(w)
-        print(f"{w:70s} {first[i]:>20s} {units[i]}")
+hdr, units = rows[0], rows[1]
+for r in rows[2:]:
+    for w in WANT:
+        if w in hdr:
+            i = hdr.index(w)
+            print(f"{w:75s} {r[i]:>22s} {units[i]}")
+    print("  warp stall reasons (warps per issue-active cycle, > 0.2):")
+    for i, h in enumerate(hdr):
+        if "smsp__average_warp" in h and "issue_stalled" in h and "_not_issued" not in h and h.endswith("ratio"):
+            try:
+                v = float(r[i])
+            except ValueError:
+                continue
+            if v > 0.2:
+                print(f"    {h.replace('smsp__average_warps_issue_stalled_', '').replace('_per_issue_active.ratio', ''):40s} {v:8.2f}")
+    print()
