@@ -134,6 +134,16 @@ int mbgcg_copy_table(mbgcg_t* h, uint32_t* out, uint64_t nSlots);
 /* Copies the device reference buffer [from, from+n) to host memory (to check it equals the mirror). */
 int mbgcg_copy_device_ref(mbgcg_t* h, uint64_t from, uint64_t n, char* out);
 
+/* Copies text `textIndex` of the last mbgcg_match / mbgcg_match_batch call back from the device, as the kernels
+ * saw it (host texts may travel 2-bit packed and are expanded on the device: this checks they arrive intact).
+ * Only meaningful for calls that fit one pass. */
+int mbgcg_copy_staged_text(mbgcg_t* h, uint64_t textIndex, char* out);
+
+/* Host-only self-test of the 2-bit text packer (no device needed): packs text[0..n) as the transfer path does and
+ * expands it again on the host into out[0..n).  Returns 0, or 1 if the text has too many non-ACGT bytes to be
+ * packed (such a block travels raw; out is then untouched). */
+int mbgcg_selftest_pack(const char* text, uint64_t n, char* out);
+
 /* Stage timings of the last match call, CUDA events on the handle's stream, milliseconds. */
 enum {
     MBGCG_T_H2D = 0,      /* host->device copy of the texts */

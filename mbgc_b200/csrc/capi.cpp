@@ -165,6 +165,21 @@ int mbgcg_copy_device_ref(mbgcg_t* h, uint64_t from, uint64_t n, char* out) {
     return guarded(h, [&] { h->m->copyDeviceRef(from, n, out); });
 }
 
+int mbgcg_copy_staged_text(mbgcg_t* h, uint64_t textIndex, char* out) {
+    return guarded(h, [&] { h->m->copyStagedText(textIndex, out); });
+}
+
+int mbgcg_selftest_pack(const char* text, uint64_t n, char* out) {
+    std::vector<mbgc_b200::ExcRun> runs;
+    std::vector<uint8_t> packed((n + 3) / 4 + 16);
+    if (!mbgc_b200::pack_block(reinterpret_cast<const uint8_t*>(text), n, packed.data(), 0, runs, n / 64 + 16)) return 1;
+    static const char lut[4] = {'A', 'C', 'T', 'G'};  // code = (c >> 1) & 3
+    for (uint64_t i = 0; i < n; i++) out[i] = lut[(packed[i >> 2] >> (2 * (i & 3))) & 3];
+    for (const auto& r : runs)
+        for (uint32_t k = 0; k < r.len; k++) out[r.off + k] = static_cast<char>(r.byte);
+    return 0;
+}
+
 void mbgcg_last_timing(const mbgcg_t* h, float ms[MBGCG_T_COUNT]) {
     for (int i = 0; i < MBGCG_T_COUNT; i++) ms[i] = h->m->stageMs[i];
 }

@@ -1,0 +1,170 @@
+// mbgc_b200/csrc/hostpack.cpp -- see hostpack.hpp.  Plain C++ (g++), AVX2 where the CPU has it.
+#include "hostpack.hpp"
+
+#include <immintrin.h>
+
+#include <cstring>
+
+namespace mbgc_b200 {
+
+namespace {
+
+inline bool is_acgt(uint8_t c) { return c == 'A' || c == 'C' || c == 'G' || c == 'T'; }
+
+// appends byte c at device offset off to the run list; false when the list is full
+inline bool add_exception(std::vector<ExcRun>& runs, size_t maxRuns, uint64_t off, uint8_t c) {
+    if (!runs.empty()) {
+        ExcRun& last = runs.back();
+        if (last.off + last.len == off && last.byte == c) {
+            last.len++;
+            return true;
+        }
+    }
+    if (runs.size() >= maxRuns) return false;
+    runs.push_back(ExcRun{off, 1u, c});
+    return true;
+}
+
+bool pack_scalar(const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t devOff, std::vector<ExcRun>& runs, size_t maxRuns,
+                 uint64_t from) {
+    // from is a multiple of 4
+    for (uint64_t i = from; i < n; i += 4) {
+        uint8_t b = 0;
+        for (uint64_t k = 0; k < 4 && i + k < n; k++) {
+            const uint8_t c = src[i + k];
+            b |= static_cast<uint8_t>(((c >> 1) & 3) << (2 * k));
+            if (!is_acgt(c) && !add_exception(runs, maxRuns, devOff + i + k, c)) return false;
+        }
+        dst[i >> 2] = b;
+    }
+    return true;
+}
+
+__attribute__((target("avx2"))) bool pack_avx2(const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t devOff,
+                                               std::vector<ExcRun>& runs, size_t maxRuns) {
+    // expected byte per low nibble: 'A' 0x41, 'C' 0x43, 'T' 0x54, 'G' 0x47; 0xFF where no base has that nibble
+    const __m256i lut = _mm256_setr_epi8(-1, 0x41, -1, 0x43, 0x54, -1, -1, 0x47, -1, -1, -1, -1, -1, -1, -1, -1,  //
+                                         -1, 0x41, -1, 0x43, 0x54, -1, -1, 0x47, -1, -1, -1, -1, -1, -1, -1, -1);
+    const __m256i lowNib = _mm256_set1_epi8(0x0f);
+    const __m256i three = _mm256_set1_epi8(3);
+    const __m256i w14 = _mm256_set1_epi16(0x0401);      // bytes (1, 4): c0 + 4 c1
+    const __m256i w116 = _mm256_set1_epi32(0x00100001);  // words (1, 16): (c0 + 4 c1) + 16 (c2 + 4 c3)
+    const __m256i gather = _mm256_setr_epi8(0, 4, 8, 12, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1,  //
+                                            0, 4, 8, 12, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1);
+    // 64 input bytes -> 16 packed bytes per iteration, written with a non-temporal store when dst is 16-byte aligned
+    // (it is, for the pinned staging buffer): the whole path is bound by host memory traffic, and a regular store
+    // would first read the destination line (read-for-ownership), a quarter more traffic for nothing.
+    const bool ntOk = (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
+    uint64_t i = 0;
+    for (; i + 64 <= n; i += 64) {
+        uint32_t out[4];
+        bool slow = false;
+#pragma GCC unroll 2
+        for (int h = 0; h < 2; h++) {
+            const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i + 32 * h));
+            const __m256i expect = _mm256_shuffle_epi8(lut, _mm256_and_si256(v, lowNib));
+            const uint32_t valid = static_cast<uint32_t>(_mm256_movemask_epi8(_mm256_cmpeq_epi8(expect, v)));
+            const __m256i codes = _mm256_and_si256(_mm256_srli_epi16(v, 1), three);
+            const __m256i p16 = _mm256_maddubs_epi16(codes, w14);
+            const __m256i p32 = _mm256_madd_epi16(p16, w116);
+            const __m256i pb = _mm256_shuffle_epi8(p32, gather);
+            out[2 * h] = static_cast<uint32_t>(_mm256_extract_epi32(pb, 0));
+            out[2 * h + 1] = static_cast<uint32_t>(_mm256_extract_epi32(pb, 4));
+            slow |= valid != 0xffffffffu;
+        }
+        const __m128i o = _mm_loadu_si128(reinterpret_cast<const __m128i*>(out));
+        if (ntOk)
+            _mm_stream_si128(reinterpret_cast<__m128i*>(dst + (i >> 2)), o);
+        else
+            _mm_storeu_si128(reinterpret_cast<__m128i*>(dst + (i >> 2)), o);
+        if (slow) {
+            for (int h = 0; h < 2; h++) {
+                const uint64_t at = i + 32 * h;
+                const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + at));
+                const __m256i expect = _mm256_shuffle_epi8(lut, _mm256_and_si256(v, lowNib));
+                uint32_t bad = ~static_cast<uint32_t>(_mm256_movemask_epi8(_mm256_cmpeq_epi8(expect, v)));
+                if (bad == 0xffffffffu && !runs.empty()) {  // inside a long run of one byte (N): extend it in one step
+                    ExcRun& last = runs.back();
+                    const __m256i same = _mm256_cmpeq_epi8(v, _mm256_set1_epi8(static_cast<char>(last.byte)));
+                    if (last.off + last.len == devOff + at && static_cast<uint32_t>(_mm256_movemask_epi8(same)) == 0xffffffffu) {
+                        last.len += 32;
+                        continue;
+                    }
+                }
+                while (bad) {
+                    const int k = __builtin_ctz(bad);
+                    bad &= bad - 1;
+                    if (!add_exception(runs, maxRuns, devOff + at + k, src[at + k])) return false;
+                }
+            }
+        }
+    }
+    if (ntOk) _mm_sfence();
+    return pack_scalar(src, n, dst, devOff, runs, maxRuns, i);
+}
+
+}  // namespace
+
+bool pack_block(const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t devOff, std::vector<ExcRun>& runs, size_t maxRuns) {
+    static const bool haveAvx2 = __builtin_cpu_supports("avx2");
+    if (haveAvx2) return pack_avx2(src, n, dst, devOff, runs, maxRuns);
+    return pack_scalar(src, n, dst, devOff, runs, maxRuns, 0);
+}
+
+// ---- worker pool ---------------------------------------------------------------------------------------
+
+WorkerPool::WorkerPool(int nThreads) {
+    if (nThreads < 1) nThreads = 1;
+    for (int t = 0; t < nThreads; t++) threads.emplace_back([this, t] { loop(t); });
+}
+
+WorkerPool::~WorkerPool() {
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        stop = true;
+    }
+    cvStart.notify_all();
+    for (auto& t : threads) t.join();
+}
+
+void WorkerPool::run(uint32_t n, std::function<void(uint32_t, int)> fn) {
+    wait();
+    std::lock_guard<std::mutex> lk(mu);
+    job = std::move(fn);
+    nItems = n;
+    if (doneFlags.size() < n) doneFlags = std::vector<std::atomic<uint8_t>>(n + n / 2 + 16);
+    for (uint32_t i = 0; i < n; i++) doneFlags[i].store(0, std::memory_order_relaxed);
+    next.store(0, std::memory_order_relaxed);
+    active = static_cast<int>(threads.size());
+    generation++;
+    cvStart.notify_all();
+}
+
+void WorkerPool::wait() {
+    std::unique_lock<std::mutex> lk(mu);
+    cvDone.wait(lk, [this] { return active == 0; });
+}
+
+void WorkerPool::loop(int worker) {
+    uint64_t seen = 0;
+    for (;;) {
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cvStart.wait(lk, [&] { return stop || generation != seen; });
+            if (stop) return;
+            seen = generation;
+        }
+        for (;;) {
+            const uint32_t i = next.fetch_add(1, std::memory_order_relaxed);
+            if (i >= nItems) break;
+            job(i, worker);
+            doneFlags[i].store(1, std::memory_order_release);
+        }
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            if (--active == 0) cvDone.notify_all();
+        }
+    }
+}
+
+}  // namespace mbgc_b200

@@ -674,6 +674,63 @@ int device_sm_count() {
     return g_smCount;
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Text transfer: blocks the host packed 4 bases per byte (hostpack.cpp) expand back to the exact ASCII bytes.
+// One thread per 16 output bytes = one packed 32-bit word; a byte permute maps four 2-bit codes to "ACTG"[code]
+// at once.  Bytes that are not A/C/G/T were sent as exception runs and are patched in afterwards.
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_unpack_blocks(const PackedBlock* __restrict__ blocks, uint32_t nBlocks,
+                                                       const uint8_t* __restrict__ packed, uint8_t* __restrict__ text) {
+    for (uint32_t b = blockIdx.x; b < nBlocks; b += gridDim.x) {
+        const PackedBlock pb = blocks[b];
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(packed + pb.srcOff);
+        uint8_t* dst = text + pb.dstOff;
+        const uint32_t groups = (pb.n + 15) / 16;
+        for (uint32_t g = threadIdx.x; g < groups; g += blockDim.x) {
+            const uint32_t w = __ldg(src + g);
+            uint32_t o[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t q = (w >> (8 * j)) & 0xffu;  // 4 codes, first base in the lowest bits
+                const uint32_t sel = (q & 3u) | ((q & 0xcu) << 2) | ((q & 0x30u) << 4) | ((q & 0xc0u) << 6);
+                o[j] = __byte_perm(0x47544341u, 0u, sel);   // code 0 'A', 1 'C', 2 'T', 3 'G'
+            }
+            if (g * 16 + 16 <= pb.n) {
+                reinterpret_cast<uint4*>(dst)[g] = make_uint4(o[0], o[1], o[2], o[3]);
+            } else {
+                for (uint32_t k = g * 16; k < pb.n; k++) dst[k] = static_cast<uint8_t>(o[(k & 15) >> 2] >> (8 * (k & 3)));
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_patch_exceptions(const ExcRunDev* __restrict__ runs, uint32_t nRuns,
+                                                          uint8_t* __restrict__ text) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warpsTotal = gridDim.x * (blockDim.x >> 5);
+    for (uint32_t r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < nRuns; r += warpsTotal) {
+        const ExcRunDev e = runs[r];
+        for (uint32_t k = lane; k < e.len; k += 32) text[e.off + k] = static_cast<uint8_t>(e.byte);
+    }
+}
+
+int launch_unpack(const PackedBlock* blocks, uint32_t nBlocks, const uint8_t* packed, const ExcRunDev* runs, uint32_t nRuns,
+                  uint8_t* text, cudaStream_t st) {
+    int launches = 0;
+    if (nBlocks) {
+        const uint32_t cap = static_cast<uint32_t>(device_sm_count()) * 8;
+        k_unpack_blocks<<<nBlocks < cap ? nBlocks : cap, 256, 0, st>>>(blocks, nBlocks, packed, text);
+        launches++;
+    }
+    if (nRuns) {
+        uint32_t blocksN = (nRuns + 7) / 8;
+        const uint32_t cap = static_cast<uint32_t>(device_sm_count()) * 8;
+        k_patch_exceptions<<<blocksN < cap ? blocksN : cap, 256, 0, st>>>(runs, nRuns, text);
+        launches++;
+    }
+    return launches;
+}
+
 // chunk -> contig table and self-contained chunk descriptors (one binary search per chunk, once per pass)
 __global__ void __launch_bounds__(256) k_chunk_contig(BatchDesc b, int K, uint32_t* __restrict__ chunkContig,
                                                       uint4* __restrict__ chunkDesc) {

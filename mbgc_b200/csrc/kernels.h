@@ -129,6 +129,21 @@ int launch_extend(const IndexState& ix, const BatchDesc& b, const WorkBuffers& w
 int launch_resolve(const IndexState& ix, const BatchDesc& b, const WorkBuffers& w, uint32_t minMatchLength,
                    cudaStream_t st);
 
+// ---- text transfer (host-packed blocks) ----
+struct PackedBlock {     // one block of a text that travelled 4 bases per byte
+    uint64_t dstOff;     // byte offset in the device text buffer (multiple of 16)
+    uint64_t srcOff;     // byte offset in the packed staging buffer (multiple of 16)
+    uint32_t n;          // bases
+    uint32_t pad;
+};
+struct ExcRunDev {       // = mbgc_b200::ExcRun (hostpack.hpp): a run of one non-ACGT byte
+    uint64_t off;
+    uint32_t len;
+    uint32_t byte;
+};
+int launch_unpack(const PackedBlock* blocks, uint32_t nBlocks, const uint8_t* packed, const ExcRunDev* runs, uint32_t nRuns,
+                  uint8_t* text, cudaStream_t st);
+
 bool probe_supports_K(int K);
 int device_sm_count();
 

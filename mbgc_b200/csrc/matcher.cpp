@@ -6,7 +6,9 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
+#include <thread>
 
 #include "../../include/mbgc_b200.h"
 
@@ -134,6 +136,11 @@ B200SparseEMMatcher::~B200SparseEMMatcher() {
     cudaFree(dOcc);
     cudaFree(dFilter);
     cudaFree(dMemoX);
+    delete pool;
+    if (hPacked) cudaFreeHost(hPacked);
+    if (hXferMeta) cudaFreeHost(hXferMeta);
+    cudaFree(dPacked);
+    cudaFree(dXferMeta);
     cudaFree(dText);
     cudaFree(dMeta);
     cudaFree(dWork);
@@ -461,6 +468,163 @@ bool B200SparseEMMatcher::useSharedFilter() const {
     return insertSeq < static_cast<uint64_t>(PROBE_FILTER_BITS) * 3 / 2 && !noFilterEnv;
 }
 
+void B200SparseEMMatcher::growPinned(void** p, uint64_t* cap, uint64_t need, const char* what) {
+    if (need <= *cap) return;
+    if (*p) cudaFreeHost(*p);
+    *p = nullptr;
+    *cap = 0;
+    const uint64_t c = align_up(need + need / 4, 1 << 20);
+    check(cudaHostAlloc(p, c, cudaHostAllocDefault), what);
+    *cap = c;
+}
+
+void B200SparseEMMatcher::growDevice(void** p, uint64_t* cap, uint64_t need, const char* what) {
+    if (need <= *cap) return;
+    cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    const uint64_t c = align_up(need + need / 4, 1 << 20);
+    check(cudaMalloc(p, c), what);
+    *cap = c;
+}
+
+// Host texts -> dText.  Small batches: one DMA per text.  Large ones: blocks of 256 KiB, a share of them DMA'd raw
+// from the caller's buffer (only when that buffer is pinned: a pageable source would be staged by the driver at a
+// fraction of the speed) while the worker pool packs the others 4:1 into pinned staging memory; packed blocks are
+// copied as they finish and expanded on the device.  See hostpack.hpp for why.
+//   MBGC_B200_PACK          0 = never pack; unset / 1 = pack batches of 8 MiB and more
+//   MBGC_B200_RAW_PERMILLE  share of the bytes that travels raw while the CPU packs the rest (default 300)
+//   MBGC_B200_PACK_THREADS  worker threads (default: hardware threads / LOCAL_WORLD_SIZE - 1)
+int B200SparseEMMatcher::stageTexts(const std::vector<TextView>& texts, size_t first, int nC,
+                                    const std::vector<uint64_t>& off) {
+    constexpr uint64_t BLK = 256 << 10;
+    uint64_t total = 0;
+    for (int c = 0; c < nC; c++) total += texts[first + c].len;
+    const char* envPack = std::getenv("MBGC_B200_PACK");
+    const bool pack = !(envPack && std::atoi(envPack) == 0) && total >= (8ull << 20);
+    if (!pack) {
+        for (int c = 0; c < nC; c++)
+            if (texts[first + c].len)
+                check(cudaMemcpyAsync(dText + off[c], texts[first + c].data, texts[first + c].len, cudaMemcpyHostToDevice,
+                                      stream), "H2D(text)");
+        return 0;
+    }
+    if (!pool) {
+        int n = static_cast<int>(std::thread::hardware_concurrency());
+        if (const char* lw = std::getenv("LOCAL_WORLD_SIZE")) n /= std::max(1, std::atoi(lw));
+        n -= 1;  // the calling thread feeds the copy engine
+        if (const char* e = std::getenv("MBGC_B200_PACK_THREADS")) n = std::atoi(e);
+        pool = new WorkerPool(std::max(1, std::min(n, 64)));
+    }
+    // Super-blocks of 4 MiB either travel raw (one DMA each: small copies cost ~5 us apiece in launch overhead alone)
+    // or are cut into 256 KiB blocks for the packers.
+    constexpr uint64_t SUPER = 4ull << 20;
+    struct Blk { const uint8_t* src; uint64_t dev; uint32_t n; uint64_t poff; bool raw; };
+    std::vector<Blk> blks;      // blocks to pack
+    std::vector<Blk> rawBlks;   // super-blocks that travel raw
+    bool pinnedSrc = true;
+    for (int c = 0; c < nC; c++) {
+        const TextView& t = texts[first + c];
+        if (!t.len) continue;
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, t.data) != cudaSuccess || attr.type != cudaMemoryTypeHost) {
+            cudaGetLastError();
+            pinnedSrc = false;
+        }
+    }
+    int rawPermille = 300;
+    if (const char* e = std::getenv("MBGC_B200_RAW_PERMILLE")) rawPermille = std::max(0, std::min(1000, std::atoi(e)));
+    if (!pinnedSrc) rawPermille = 0;
+    uint64_t seen = 0, rawBytes = 0, packedBytes = 0;
+    for (int c = 0; c < nC; c++) {
+        const TextView& t = texts[first + c];
+        for (uint64_t so = 0; so < t.len; so += SUPER) {
+            const uint64_t sn = std::min<uint64_t>(SUPER, t.len - so);
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(t.data) + so;
+            // keep the raw share of the bytes seen so far at rawPermille
+            if ((rawBytes + sn) * 1000 <= (seen + sn) * static_cast<uint64_t>(rawPermille)) {
+                rawBlks.push_back(Blk{src, off[c] + so, static_cast<uint32_t>(sn), 0, true});
+                rawBytes += sn;
+            } else {
+                for (uint64_t o = 0; o < sn; o += BLK) {
+                    const uint32_t n = static_cast<uint32_t>(std::min<uint64_t>(BLK, sn - o));
+                    blks.push_back(Blk{src + o, off[c] + so + o, n, packedBytes, false});
+                    packedBytes += align_up((n + 3) / 4, 16);
+                }
+            }
+            seen += sn;
+        }
+    }
+    const uint32_t nB = static_cast<uint32_t>(blks.size());
+    growPinned(&hPacked, &hPackedCap, packedBytes + 64, "cudaHostAlloc(packed)");
+    growDevice(&dPacked, &dPackedCap, packedBytes + 64, "cudaMalloc(packed)");
+    if (blockRuns.size() < nB) blockRuns.resize(nB);
+    std::vector<uint8_t> failed(nB, 0);
+    uint8_t* hp = static_cast<uint8_t*>(hPacked);
+    Blk* bp = blks.data();
+    uint8_t* fp = failed.data();
+    std::vector<std::vector<ExcRun>>* runsAll = &blockRuns;
+    pool->run(nB, [bp, hp, fp, runsAll](uint32_t b, int) {
+        std::vector<ExcRun>& runs = (*runsAll)[b];
+        runs.clear();
+        if (!pack_block(bp[b].src, bp[b].n, hp + bp[b].poff, bp[b].dev, runs, bp[b].n / 64 + 16)) {
+            fp[b] = 1;  // too many non-ACGT bytes: this block travels raw
+            runs.clear();
+        }
+    });
+    // feed the copy engine: packed blocks in order as they finish (merged into copies of up to 4 MiB), raw blocks
+    // whenever no packed block is ready
+    size_t ri = 0;
+    uint32_t pi = 0;
+    auto copyRaw = [&](const Blk& b) {
+        check(cudaMemcpyAsync(dText + b.dev, b.src, b.n, cudaMemcpyHostToDevice, stream), "H2D(raw block)");
+    };
+    while (ri < rawBlks.size() || pi < nB) {
+        if (pi < nB && pool->done(pi)) {
+            uint64_t lo = UINT64_MAX, hi = 0;
+            while (pi < nB && pool->done(pi) && (lo == UINT64_MAX || hi - lo < (4ull << 20))) {
+                const uint32_t b = pi++;
+                if (failed[b]) {
+                    copyRaw(blks[b]);
+                    continue;
+                }
+                lo = std::min(lo, blks[b].poff);
+                hi = blks[b].poff + align_up((blks[b].n + 3) / 4, 16);
+            }
+            if (lo != UINT64_MAX)
+                check(cudaMemcpyAsync(static_cast<uint8_t*>(dPacked) + lo, hp + lo, hi - lo, cudaMemcpyHostToDevice, stream),
+                      "H2D(packed blocks)");
+        } else if (ri < rawBlks.size()) {
+            copyRaw(rawBlks[ri++]);
+        } else {
+            std::this_thread::sleep_for(std::chrono::microseconds(20));  // leave the core to a packer
+        }
+    }
+    pool->wait();
+    // descriptors of the packed blocks + exception runs -> device, then expand
+    uint64_t nRuns = 0, nPacked = 0;
+    for (uint32_t b = 0; b < nB; b++)
+        if (!failed[b]) {
+            nPacked++;
+            nRuns += blockRuns[b].size();
+        }
+    const uint64_t metaBytes = nPacked * sizeof(PackedBlock) + nRuns * sizeof(ExcRunDev) + 64;
+    growPinned(&hXferMeta, &hXferMetaCap, metaBytes, "cudaHostAlloc(transfer meta)");
+    growDevice(&dXferMeta, &dXferMetaCap, metaBytes, "cudaMalloc(transfer meta)");
+    PackedBlock* hb = static_cast<PackedBlock*>(hXferMeta);
+    ExcRunDev* hr = reinterpret_cast<ExcRunDev*>(hb + nPacked);
+    uint64_t kb = 0, kr = 0;
+    for (uint32_t b = 0; b < nB; b++)
+        if (!failed[b]) {
+            hb[kb++] = PackedBlock{blks[b].dev, blks[b].poff, blks[b].n, 0};
+            for (const ExcRun& e : blockRuns[b]) hr[kr++] = ExcRunDev{e.off, e.len, e.byte};
+        }
+    check(cudaMemcpyAsync(dXferMeta, hXferMeta, metaBytes - 64, cudaMemcpyHostToDevice, stream), "H2D(transfer meta)");
+    const PackedBlock* db = static_cast<const PackedBlock*>(dXferMeta);
+    return launch_unpack(db, static_cast<uint32_t>(nPacked), static_cast<const uint8_t*>(dPacked),
+                         reinterpret_cast<const ExcRunDev*>(db + nPacked), static_cast<uint32_t>(nRuns), dText, stream);
+}
+
 void B200SparseEMMatcher::matchBatch(const std::vector<TextView>& texts, const uint64_t* lockPos, uint32_t minMatchLength,
                                      bool textsOnDevice, const void* dTextBase, const uint64_t* dOffsets) {
     check(cudaSetDevice(device), "cudaSetDevice");
@@ -529,10 +693,12 @@ void B200SparseEMMatcher::matchBatch(const std::vector<TextView>& texts, const u
             if (textsOnDevice) {
                 textBase = static_cast<const uint8_t*>(dTextBase);
             } else {
-                for (int c = 0; c < nC; c++)
-                    if (texts[first + c].len)
-                        check(cudaMemcpyAsync(dText + off[c], texts[first + c].data, texts[first + c].len,
-                                              cudaMemcpyHostToDevice, stream), "H2D(text)");
+                const int xl = stageTexts(texts, first, nC, off);
+                totalLaunches += static_cast<uint64_t>(xl);
+                lastCounters[4] += static_cast<uint64_t>(xl);
+                lastOffsets = off;
+                lastLens.resize(nC);
+                for (int c = 0; c < nC; c++) lastLens[c] = texts[first + c].len;
                 textBase = dText;
             }
             check(cudaMemsetAsync(wb.counters, 0, 32, stream), "memset(counters)");
@@ -649,6 +815,14 @@ void B200SparseEMMatcher::copyTableLow32(uint32_t* out, uint64_t nSlots) {
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
     cudaFree(d);
     check(e, "table copy");
+}
+
+void B200SparseEMMatcher::copyStagedText(uint64_t textIndex, char* out) {
+    check(cudaSetDevice(device), "cudaSetDevice");
+    if (textIndex >= lastOffsets.size()) throw MatcherError(MBGCG_E_PARAM, "no such text in the last host batch");
+    if (lastLens[textIndex] == 0) return;
+    check(cudaMemcpyAsync(out, dText + lastOffsets[textIndex], lastLens[textIndex], cudaMemcpyDeviceToHost, stream), "D2H(text)");
+    check(cudaStreamSynchronize(stream), "text copy sync");
 }
 
 void B200SparseEMMatcher::copyDeviceRef(uint64_t from, uint64_t n, char* out) {

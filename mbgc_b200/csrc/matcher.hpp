@@ -13,6 +13,7 @@
 #include <string>
 #include <vector>
 
+#include "hostpack.hpp"
 #include "kernels.h"
 
 constexpr int MBGCG_T_COUNT_ = 12;  // = MBGCG_T_COUNT of include/mbgc_b200.h (checked in capi.cpp)
@@ -88,6 +89,8 @@ public:
     // inspection
     void copyTableLow32(uint32_t* out, uint64_t nSlots);
     void copyDeviceRef(uint64_t from, uint64_t n, char* out);
+    // text i of the last host-buffer batch as it arrived on the device (single-pass batches; tests)
+    void copyStagedText(uint64_t textIndex, char* out);
     void* streamHandle() const { return stream; }
 
     // state (public like the C struct it is mirrored into)
@@ -111,6 +114,10 @@ private:
     void buildMemo();
     bool useSharedFilter() const;
     void fillIndexState(IndexState& ix) const;
+    // host texts -> device text buffer: raw DMA and / or host-packed blocks (hostpack.hpp); returns kernel launches
+    int stageTexts(const std::vector<TextView>& texts, size_t first, int nC, const std::vector<uint64_t>& off);
+    void growPinned(void** p, uint64_t* cap, uint64_t need, const char* what);
+    void growDevice(void** p, uint64_t* cap, uint64_t need, const char* what);
     void ensureWork(uint64_t textBytes, uint32_t nTiles, int nContigs, uint32_t seedCap);
     void check(cudaError_t e, const char* what);
 
@@ -131,6 +138,15 @@ private:
     uint64_t passesSinceInsert = 0;      // match passes since the index last changed
     double cleanEstimate = 0.5;          // expected fraction of clean chunks (updated from every pass)
     std::deque<uint64_t> workersSwEndPositions;
+
+    // text transfer (host-packed blocks)
+    WorkerPool* pool = nullptr;
+    void* hPacked = nullptr; uint64_t hPackedCap = 0;   // pinned: packed blocks
+    void* dPacked = nullptr; uint64_t dPackedCap = 0;
+    void* hXferMeta = nullptr; uint64_t hXferMetaCap = 0;  // pinned: block descriptors, then exception runs
+    void* dXferMeta = nullptr; uint64_t dXferMetaCap = 0;
+    std::vector<std::vector<ExcRun>> blockRuns;
+    std::vector<uint64_t> lastOffsets, lastLens;
 
     // per-pass device buffers (grown on demand)
     uint8_t* dText = nullptr; uint64_t dTextCap = 0;

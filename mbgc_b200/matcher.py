@@ -82,6 +82,10 @@ def load_library():
     L.mbgcg_copy_table.argtypes = [vp, vp, C.c_uint64]
     L.mbgcg_copy_device_ref.restype = C.c_int
     L.mbgcg_copy_device_ref.argtypes = [vp, C.c_uint64, C.c_uint64, vp]
+    L.mbgcg_copy_staged_text.restype = C.c_int
+    L.mbgcg_copy_staged_text.argtypes = [vp, C.c_uint64, vp]
+    L.mbgcg_selftest_pack.restype = C.c_int
+    L.mbgcg_selftest_pack.argtypes = [vp, C.c_uint64, vp]
     L.mbgcg_last_timing.argtypes = [vp, C.POINTER(C.c_float)]
     L.mbgcg_last_counters.argtypes = [vp, u64p]
     L.mbgcg_stream.restype = vp
@@ -210,6 +214,12 @@ class Matcher:
     def deviceRef(self, start, n):
         out = np.empty(n, dtype=np.uint8)
         self._check(self.lib.mbgcg_copy_device_ref(self.h, start, n, out.ctypes.data))
+        return out
+
+    def stagedText(self, index, n):
+        """text `index` of the last host-buffer batch as it arrived on the device (n = its length)"""
+        out = np.empty(n, dtype=np.uint8)
+        self._check(self.lib.mbgcg_copy_staged_text(self.h, index, out.ctypes.data))
         return out
 
     def timing(self):

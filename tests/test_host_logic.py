@@ -121,3 +121,30 @@ def test_rc_lut_matches_reference_quirks():
     lut = dst[::-1]
     assert bytes(lut[[ord(c) for c in "ACGTNacgtnUuYRKMBDHVWS"]]) == b"TGCANTGCANAARYMKVHDBSW"
     assert lut[0x7F] == 0 and lut[0] == 0 and lut[ord("X")] == ord("X") and lut[200] == 200
+
+
+def test_host_packer_round_trip():
+    """2-bit packing of the text transfer path (mbgc_b200/csrc/hostpack.cpp): exact ASCII comes back, including
+    N runs, IUPAC codes, lower case and lengths that are not multiples of 4 or 32; texts that are mostly
+    non-ACGT are refused (they travel raw)."""
+    import ctypes as C
+    lib = mbgc_b200.load_library()
+    rng = np.random.default_rng(5)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    for n in (0, 1, 3, 4, 5, 31, 32, 33, 63, 64, 65, 1000, 262_144, 262_147):
+        t = acgt[rng.integers(0, 4, n)].copy()
+        if n > 40:
+            t[7:19] = ord("N")
+            t[n // 2] = ord("R")
+            t[n - 1] = ord("n")
+            t[n - 3] = 0
+        if n > 100_000:
+            t[50_000:58_000] = ord("N")                 # long run: one exception entry
+            t[90_000:90_040] = np.frombuffer(b"acgtn" * 8, dtype=np.uint8)
+        out = np.zeros(n, dtype=np.uint8)
+        rc = lib.mbgcg_selftest_pack(t.ctypes.data, n, out.ctypes.data)
+        assert rc == 0
+        assert np.array_equal(out, t), f"length {n}"
+    lower = np.frombuffer(bytes(acgt[rng.integers(0, 4, 10_000)]).lower(), dtype=np.uint8).copy()
+    out = np.zeros(lower.size, dtype=np.uint8)
+    assert lib.mbgcg_selftest_pack(lower.ctypes.data, lower.size, out.ctypes.data) == 1
