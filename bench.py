@@ -227,7 +227,7 @@ STAGE_KERNELS = {"anchor": "k_anchor", "clean": "k_clean", "fullprobe": "k_probe
 def kernel_alg_bytes(group, counters, ref_bytes):
     pos, chunks = counters["positions"], max(1, counters["chunks"])
     if group == "fullprobe":
-        return ALG_BYTES_PER_POSITION * 512.0 * counters["chunks_full_probe"]
+        return ALG_BYTES_PER_POSITION * 16.0 * counters["lanes_full_probe"]
     if group == "clean":
         return pos * (1.0 + (0.0 if ref_bytes <= 100e6 else 1.0)) + chunks * 53.0
     if group == "anchor":
@@ -354,7 +354,7 @@ def run_b200(args, rank, world):
         "config": {"workload": workload_name(args), "genomes_per_gpu": n, "bases_per_gpu": int(sum(lens)),
                    "fasta_bytes_per_gpu": int(fbytes), "matches_per_gpu": r["n_matches"],
                    "seed_segments": counters["seeds"], "seed_runs": counters["runs"], "chunks": counters["chunks"],
-                   "chunks_full_probe": counters["chunks_full_probe"], "ref_limit": int(r["limit"]),
+                   "lanes_full_probe": counters["lanes_full_probe"], "ref_limit": int(r["limit"]),
                    "table_slots": r["table_slots"], "skip_margin": r["sm"],
                    "l2": "inputs (>= 500 MB per step) exceed the 126 MB L2; no explicit flush",
                    "index_build_s": r["index_s"],
@@ -398,7 +398,7 @@ def run_b200(args, rank, world):
             "tier": other, "value": o["fbytes"] * world * oargs.steps / (o["ms_dev"] / 1e3) / 1e9,
             "e2e": o["fbytes"] * world * oargs.steps / (o["ms_e2e"] / 1e3) / 1e9, "unit": "GB/s",
             "ms_per_step": o["ms_dev"] / oargs.steps, "matches_per_gpu": o["n_matches"],
-            "chunks": o["counters"]["chunks"], "chunks_full_probe": o["counters"]["chunks_full_probe"],
+            "chunks": o["counters"]["chunks"], "lanes_full_probe": o["counters"]["lanes_full_probe"],
             "stage_frac": ALG_BYTES_PER_POSITION * o["counters"]["positions"] / (okern / 1e3) / 1e9 / peak,
             "stage_ms": o["stage_dev"]}
         if rank == 0 and world == 1 and not args.no_cpu:

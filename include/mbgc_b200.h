@@ -162,7 +162,7 @@ enum {
 };
 void mbgcg_last_timing(const mbgcg_t* h, float ms[MBGCG_T_COUNT]);
 /* counters of the last match call: 0 positions, 1 seed segments, 2 seed runs, 3 matches, 4 kernel launches,
- * 5 passes, 6 chunks, 7 chunks that went through the full probe */
+ * 5 passes, 6 chunks (512 positions), 7 lanes (16 positions) that went through the full probe */
 void mbgcg_last_counters(const mbgcg_t* h, uint64_t out[8]);
 /* total kernel launches issued by this handle since creation */
 uint64_t mbgcg_total_launches(const mbgcg_t* h);

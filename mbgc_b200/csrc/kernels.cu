@@ -294,8 +294,8 @@ struct ProbeArgs {
     uint32_t* chunkCount;
     uint16_t* seedMask;
     uint32_t* scratchEnc;
-    const uint32_t* workList;    // nullptr: every chunk; else the chunks the fast path (k_clean) left over
-    const uint32_t* workCount;   // device-resident length of workList
+    const uint32_t* laneList;    // nullptr: every lane of every chunk; else the (chunk * 32 + lane) items k_clean left over
+    const uint32_t* laneCount;   // device-resident length of laneList
     unsigned long long* anchor;  // k_anchor output
 };
 
@@ -388,6 +388,9 @@ __device__ __forceinline__ uint32_t verify_candidate(const IndexState& ix, const
     return diff == 0 ? enc : 0;
 }
 
+// The unit of work is a LANE ITEM: 16 consecutive positions of one chunk (item = chunk * 32 + lane-in-chunk).
+// Without the fast path the items are simply 0 .. 32 nChunks - 1, so a warp still owns one chunk and its text
+// loads coalesce; with it, k_clean hands over only the items it could not prove identical to the reference.
 template <int KW, bool FILTER>
 __global__ void __launch_bounds__(FILTER ? PROBE_THREADS_FILTER : PROBE_THREADS_PLAIN, 1) k_probe(const ProbeArgs a) {
     constexpr int NPT = PROBE_NPT;
@@ -401,18 +404,20 @@ __global__ void __launch_bounds__(FILTER ? PROBE_THREADS_FILTER : PROBE_THREADS_
         __syncthreads();
     }
     const uint32_t warpsTotal = gridDim.x * (blockDim.x >> 5);
-    const uint32_t nWork = a.workList ? *a.workCount : a.b.nTiles;
-    for (uint32_t k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); k < nWork; k += warpsTotal) {
-        const uint32_t g = a.workList ? a.workList[k] : k;
+    const uint32_t nItems = a.laneList ? *a.laneCount : a.b.nTiles * 32u;
+    for (uint32_t kb = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32; kb < nItems; kb += warpsTotal * 32) {
+        const bool valid = kb + lane < nItems;
+        const uint32_t item = valid ? (a.laneList ? a.laneList[kb + lane] : kb + lane) : 0;
+        const uint32_t g = item >> 5, cl = item & 31u;  // chunk, lane within the chunk
         const uint4 desc = __ldg(&a.chunkDesc[g]);
         const uint8_t* ctext = a.b.text + ((static_cast<uint64_t>(desc.y) << 32) | desc.x);  // text of the chunk start
         const uint32_t base = desc.z;    // contig-local position of the chunk start
         const uint32_t nValid = desc.w;  // positions of the contig that can start a K-mer
-        const uint32_t p0 = base + lane * NPT;
+        const uint32_t p0 = base + cl * NPT;
 
         uint32_t A[NWA];
         {
-            const uint4* gp = reinterpret_cast<const uint4*>(ctext + lane * NPT);
+            const uint4* gp = reinterpret_cast<const uint4*>(ctext + cl * NPT);
 #pragma unroll
             for (int v = 0; v < NWA / 4; v++) {
                 const uint4 x = __ldg(gp + v);
@@ -423,6 +428,7 @@ __global__ void __launch_bounds__(FILTER ? PROBE_THREADS_FILTER : PROBE_THREADS_
         uint32_t hit = probe_lane16<KW, FILTER>(a.ix, sFilter, A, slots);
         // positions past the last valid one never probe (position p = bit 15 - p)
         if (p0 + NPT > nValid) hit &= p0 >= nValid ? 0u : (0xffffu << (p0 + NPT - nValid)) & 0xffffu;
+        if (!valid) hit = 0;
 
         uint32_t mask = 0;
         if (hit) {
@@ -434,16 +440,24 @@ __global__ void __launch_bounds__(FILTER ? PROBE_THREADS_FILTER : PROBE_THREADS_
                 const int p = 15 - bit;
                 const uint32_t enc = verify_candidate<KW>(a.ix, A, p, select16(slots, p), swStop);
                 if (enc) {
-                    a.scratchEnc[static_cast<uint64_t>(g) * PROBE_CHUNK + lane * NPT + p] = enc;
+                    a.scratchEnc[static_cast<uint64_t>(g) * PROBE_CHUNK + cl * NPT + p] = enc;
                     mask |= 1u << p;
                 }
             } while (hit);
         }
-        a.seedMask[static_cast<uint64_t>(g) * 32 + lane] = static_cast<uint16_t>(mask);
-        uint32_t cnt = __popc(mask);
+        if (valid) a.seedMask[static_cast<uint64_t>(g) * 32 + cl] = static_cast<uint16_t>(mask);
+        // seeds per chunk: one atomic per distinct chunk in the warp (all 32 lanes share it without the fast path)
+        const uint32_t cnt = __popc(mask);
+        const unsigned peers = __match_any_sync(0xffffffffu, valid ? g : 0xffffffffu);
+        uint32_t sum = cnt;
+        if (peers == 0xffffffffu) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-        if (lane == 0) a.chunkCount[g] = cnt;
+            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        } else {
+            sum = 0;
+            for (unsigned rest = peers; rest; rest &= rest - 1) sum += __shfl_sync(peers, cnt, __ffs(rest) - 1);
+        }
+        if (valid && sum && lane == __ffs(peers) - 1) atomicAdd(&a.chunkCount[g], sum);
     }
 }
 
@@ -533,7 +547,9 @@ struct CleanArgs {
     uint32_t* scratchEnc;
     uint8_t* chunkSegN;
     uint2* chunkSeg;
+    uint32_t* dirtyMask;
     uint32_t* workList;
+    uint32_t* laneList;
     uint32_t* counters;
 };
 
@@ -545,6 +561,8 @@ __global__ void __launch_bounds__(256) k_clean(const CleanArgs a) {
     const int lane = threadIdx.x & 31, sub = lane & 7, cg = lane >> 3;
     const int K = a.ix.K;
     const int tailWords = (K + 2) / 4;  // the K-1 bytes the chunk's last k-mers reach past it, rounded up to words
+    const int span = (K + 30) / 16;     // 16-byte pieces the 16 k-mers of a lane touch
+    const unsigned long long tailPieces = ((1ull << ((K + 14) / 16)) - 1ull) << 32;
     const uint32_t warpsTotal = gridDim.x * (blockDim.x >> 5);
     const uint32_t nTiles = a.b.nTiles;
     for (uint32_t gb = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 4; gb < nTiles; gb += warpsTotal * 4) {
@@ -591,15 +609,17 @@ __global__ void __launch_bounds__(256) k_clean(const CleanArgs a) {
         const bool hiHalf = (ra & 4) != 0;
         const uint32_t sh = static_cast<uint32_t>(ra & 3) * 8;
         const uint4* tp = reinterpret_cast<const uint4*>(T) + sub;
-        uint32_t diff = 0;
+        // which of the chunk's 32 + 2 sixteen-byte pieces differ: lane sub compares pieces sub, sub + 8, sub + 16, sub + 24
+        uint32_t pflags = 0, pt = 0;  // bit k of pflags: this lane's k-th piece differs
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             const uint4 tw = __ldg(tp + 8 * k);
             const uint2 a0 = __ldg(rp + 16 * k), a1 = __ldg(rp + 16 * k + 1), a2 = __ldg(rp + 16 * k + 2);
             const uint32_t w0 = hiHalf ? a0.y : a0.x, w1 = hiHalf ? a1.x : a0.y, w2 = hiHalf ? a1.y : a1.x,
                            w3 = hiHalf ? a2.x : a1.y, w4 = hiHalf ? a2.y : a2.x;
-            diff |= (tw.x ^ __funnelshift_r(w0, w1, sh)) | (tw.y ^ __funnelshift_r(w1, w2, sh)) |
-                    (tw.z ^ __funnelshift_r(w2, w3, sh)) | (tw.w ^ __funnelshift_r(w3, w4, sh));
+            const uint32_t pd = (tw.x ^ __funnelshift_r(w0, w1, sh)) | (tw.y ^ __funnelshift_r(w1, w2, sh)) |
+                                (tw.z ^ __funnelshift_r(w2, w3, sh)) | (tw.w ^ __funnelshift_r(w3, w4, sh));
+            pflags |= (pd != 0 ? 1u : 0u) << k;
         }
         {
             const uint32_t* rw = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(R) & ~static_cast<uintptr_t>(3));
@@ -608,24 +628,69 @@ __global__ void __launch_bounds__(256) k_clean(const CleanArgs a) {
                 const int tl = sub + 8 * w;
                 if (tl < tailWords) {
                     const uint32_t* rt = rw + PROBE_CHUNK / 4 + tl;  // R + PROBE_CHUNK + 4 tl, rounded down to a word
-                    diff |= __ldg(reinterpret_cast<const uint32_t*>(T + PROBE_CHUNK) + tl) ^ __funnelshift_r(__ldg(rt), __ldg(rt + 1), sh);
+                    pt |= __ldg(reinterpret_cast<const uint32_t*>(T + PROBE_CHUNK) + tl) ^ __funnelshift_r(__ldg(rt), __ldg(rt + 1), sh);
                 }
             }
         }
-        const unsigned bad = (__ballot_sync(0xffffffffu, diff != 0) >> (8 * cg)) & 0xffu;
-        const bool clean = ok && bad == 0 && static_cast<uint32_t>(xw >> 1) == 0 && !(pin && (xw & 1));
-        if (sub == 0 && valid) {
-            if (clean) {
-                // seeds = grid positions whose group is in the default state; maximal stretches leave as segments
-                // (k_compact_clean expands the mask D)
-                const uint32_t D = ~static_cast<uint32_t>(ew >> 1);
-                a.chunkCount[g] = __popc(D & ~(D << 1));
-                a.chunkSegN[g] = static_cast<uint8_t>(0x80u | pin);
-                a.chunkSeg[g] = make_uint2(static_cast<uint32_t>(grp0), D);
-            } else {
-                a.chunkSegN[g] = 0;
-                a.workList[atomicAdd(&a.counters[5], 1u)] = g;
+        // Most warps see no difference at all (on the near tier 3 of 4): one vote settles that, and everything that
+        // deals with dirty lanes is behind warp-uniform branches.
+        const uint32_t X1 = static_cast<uint32_t>(xw >> 1), X0 = static_cast<uint32_t>(xw);
+        uint32_t L = ok ? (X1 | (pin ? X0 : 0u)) : 0xffffffffu;  // dirty lanes: memo first (lane l overlaps the reference
+                                                                 // groups of bits l, before its grid position, and l + 1)
+        if (!valid) L = 0;
+        if (__any_sync(0xffffffffu, (pflags | pt) != 0)) {
+            unsigned long long pieces = 0;  // bit q = piece q differs (pieces 32.. = the K-1 bytes past the chunk)
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const unsigned bal = (__ballot_sync(0xffffffffu, (pflags >> k) & 1u) >> (8 * cg)) & 0xffu;
+                pieces |= static_cast<unsigned long long>(bal) << (8 * k);
             }
+            const unsigned balT = (__ballot_sync(0xffffffffu, pt != 0) >> (8 * cg)) & 0xffu;
+            if (balT) pieces |= tailPieces;  // any difference in the tail dirties all tail pieces (conservative)
+            // lane l of the chunk (positions 16 l .. 16 l + 15) reads bytes [16 l, 16 l + 15 + K): pieces l .. l + span - 1
+            unsigned long long dm = 0;
+            for (int j = 0; j < span; j++) dm |= pieces >> j;
+            if (valid) L |= static_cast<uint32_t>(dm);
+        }
+        if (__any_sync(0xffffffffu, L != 0)) {
+            // dirty lanes -> work items.  One 64-bit atomic per warp reserves the slots of its four chunks in both
+            // lists (counters 6 = chunks with dirty lanes, 7 = dirty lanes), then the eight lanes of a chunk write its
+            // items (4 bits of L each).
+            uint32_t laneBase = 0, chunkBase = 0, laneTot = 0, chunkTot = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t Lj = __shfl_sync(0xffffffffu, L, 8 * j);
+                if (j == cg) {
+                    laneBase = laneTot;
+                    chunkBase = chunkTot;
+                }
+                laneTot += __popc(Lj);
+                chunkTot += Lj ? 1u : 0u;
+            }
+            unsigned long long old = 0;
+            if (lane == 0)
+                old = atomicAdd(reinterpret_cast<unsigned long long*>(a.counters + 6),
+                                (static_cast<unsigned long long>(laneTot) << 32) | chunkTot);
+            old = __shfl_sync(0xffffffffu, old, 0);
+            if (L) {
+                if (sub == 0) a.workList[static_cast<uint32_t>(old) + chunkBase] = g;
+                uint32_t mine = (L >> (4 * sub)) & 0xfu;
+                uint32_t k = static_cast<uint32_t>(old >> 32) + laneBase + __popc(L & ((1u << (4 * sub)) - 1u));
+                while (mine) {
+                    a.laneList[k++] = g * 32u + 4 * sub + (__ffs(mine) - 1);
+                    mine &= mine - 1;
+                }
+            }
+        }
+        if (sub == 0 && valid) {
+            // seeds of the clean lanes = their grid position, where the memo group is in the default state
+            const uint32_t D = ~static_cast<uint32_t>(ew >> 1) & ~L;
+            a.dirtyMask[g] = L;
+            a.chunkSegN[g] = L == 0xffffffffu ? 0 : static_cast<uint8_t>(0x80u | pin);
+            a.chunkSeg[g] = make_uint2(static_cast<uint32_t>(grp0), D);
+            // clean chunk: maximal stretches of D leave as segments; mixed chunk: every seed on its own (k_probe adds
+            // the seeds of the dirty lanes)
+            a.chunkCount[g] = L == 0 ? __popc(D & ~(D << 1)) : __popc(D);
         }
     }
 }
@@ -733,10 +798,11 @@ int launch_unpack(const PackedBlock* blocks, uint32_t nBlocks, const uint8_t* pa
 
 // chunk -> contig table and self-contained chunk descriptors (one binary search per chunk, once per pass)
 __global__ void __launch_bounds__(256) k_chunk_contig(BatchDesc b, int K, uint32_t* __restrict__ chunkContig,
-                                                      uint4* __restrict__ chunkDesc) {
+                                                      uint4* __restrict__ chunkDesc, uint32_t* __restrict__ chunkCount) {
     for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < b.nTiles; g += gridDim.x * blockDim.x) {
         const uint32_t c = static_cast<uint32_t>(upper_contig(b.tileStart, b.nContigs, g));
         chunkContig[g] = c;
+        chunkCount[g] = 0;  // k_clean stores, k_probe adds
         const uint32_t base = (g - b.tileStart[c]) * PROBE_CHUNK;
         const uint64_t off = b.contigOff[c] + base;
         const uint32_t N2 = b.contigLen[c];
@@ -788,7 +854,7 @@ int launch_chunk_desc(const IndexState& ix, const BatchDesc& b, const WorkBuffer
         cudaMemsetAsync(w.tileCount, 0, sizeof(uint32_t), st);
         return 0;
     }
-    k_chunk_contig<<<device_sm_count() * 4, 256, 0, st>>>(b, ix.K, w.chunkContig, w.chunkDesc);
+    k_chunk_contig<<<device_sm_count() * 4, 256, 0, st>>>(b, ix.K, w.chunkContig, w.chunkDesc, w.tileCount);
     return 1;
 }
 
@@ -796,7 +862,7 @@ int launch_probe(const IndexState& ix, const BatchDesc& b, const WorkBuffers& w,
                  cudaStream_t st) {
     if (b.nTiles == 0) return 0;
     ProbeArgs a{ix, b, w.chunkDesc, w.chunkContig, w.tileCount, w.seedMask, w.scratchEnc,
-                useWorkList ? w.workList : nullptr, useWorkList ? w.counters + 5 : nullptr, w.anchor};
+                useWorkList ? w.laneList : nullptr, useWorkList ? w.counters + 7 : nullptr, w.anchor};
     return dispatch_probe(a, useFilter, 0, st);
 }
 
@@ -809,7 +875,7 @@ int launch_anchor(const IndexState& ix, const BatchDesc& b, const WorkBuffers& w
 int launch_clean(const IndexState& ix, const BatchDesc& b, const WorkBuffers& w, const MemoState& memo, cudaStream_t st) {
     if (b.nTiles == 0) return 0;
     CleanArgs a{ix, b, w.chunkDesc, w.chunkContig, w.anchor, memo.memoX, memo.memoE, memo.memoLen, w.tileCount,
-                w.seedMask, w.scratchEnc, w.chunkSegN, w.chunkSeg, w.workList, w.counters};
+                w.seedMask, w.scratchEnc, w.chunkSegN, w.chunkSeg, w.dirtyMask, w.workList, w.laneList, w.counters};
     k_clean<<<device_sm_count() * 8, 256, 0, st>>>(a);
     return 1;
 }
@@ -826,12 +892,16 @@ int launch_memo(const BatchDesc& b, const WorkBuffers& w, uint32_t nValid, uint3
 // ------------------------------------------------------------------------------------------------------
 
 // position-indexed seed staging -> dense, position-ordered segment arrays.  chunkOff = exclusive scan of the
-// chunk counts.  One warp per fully probed chunk (all chunks, or the fast path's work list).
+// chunk counts.  One warp per chunk that has probed lanes (all chunks, or the fast path's list of chunks with at
+// least one dirty lane).  In such a "mixed" chunk the clean lanes contribute their memo seed (k_clean: mask D, one
+// grid position per lane) and the dirty lanes what k_probe found; every seed leaves as its own segment.
 __global__ void __launch_bounds__(256) k_compact(BatchDesc b, const uint32_t* __restrict__ chunkContig,
                                                  const uint32_t* __restrict__ chunkOff,
                                                  const uint16_t* __restrict__ seedMask,
                                                  const uint32_t* __restrict__ scratchEnc,
                                                  const uint32_t* __restrict__ workList, const uint32_t* workCount,
+                                                 const uint32_t* __restrict__ dirtyMask,
+                                                 const uint8_t* __restrict__ chunkSegN, const uint2* __restrict__ chunkSeg,
                                                  uint32_t* __restrict__ seedPos, uint32_t* __restrict__ seedEnc,
                                                  uint8_t* __restrict__ seedN, uint32_t* __restrict__ seedContig,
                                                  uint32_t seedCap, uint32_t* counters) {
@@ -847,7 +917,15 @@ __global__ void __launch_bounds__(256) k_compact(BatchDesc b, const uint32_t* __
         const uint32_t g = workList ? workList[w] : w;
         const uint32_t o = chunkOff[g];
         if (chunkOff[g + 1] == o) continue;
-        uint32_t m = seedMask[static_cast<uint64_t>(g) * 32 + lane];
+        const bool dirty = workList ? ((dirtyMask[g] >> lane) & 1u) != 0 : true;
+        uint32_t m, memoEnc = 0;
+        if (dirty) {
+            m = seedMask[static_cast<uint64_t>(g) * 32 + lane];
+        } else {
+            const uint2 sg = chunkSeg[g];  // .x = entry of lane 0's grid position, .y = lanes whose grid position is a seed
+            m = ((sg.y >> lane) & 1u) << (chunkSegN[g] & 15u);
+            memoEnc = sg.x + lane;
+        }
         const uint32_t c = chunkContig[g];
         const uint32_t base = (g - b.tileStart[c]) * PROBE_CHUNK + lane * PROBE_NPT;
         const uint64_t src = static_cast<uint64_t>(g) * PROBE_CHUNK + lane * PROBE_NPT;
@@ -857,7 +935,7 @@ __global__ void __launch_bounds__(256) k_compact(BatchDesc b, const uint32_t* __
             const int p = __ffs(m) - 1;
             m &= m - 1;
             seedPos[k] = base + p;
-            seedEnc[k] = scratchEnc[src + p];
+            seedEnc[k] = dirty ? scratchEnc[src + p] : memoEnc;
             seedN[k] = 1;
             seedContig[k] = c;
             k++;
@@ -865,20 +943,20 @@ __global__ void __launch_bounds__(256) k_compact(BatchDesc b, const uint32_t* __
     }
 }
 
-// clean chunks (k_clean): one THREAD per chunk.  The chunk's seeds sit on one diagonal, k1 apart, at most one per
-// lane-sized group of 16 positions; D has a bit for every group with a seed, and every maximal stretch of set bits
-// leaves as one segment.
+// clean chunks (k_clean, no dirty lane): one THREAD per chunk.  The chunk's seeds sit on one diagonal, k1 apart, at
+// most one per lane-sized group of 16 positions; D has a bit for every group with a seed, and every maximal stretch
+// of set bits leaves as one segment.
 __global__ void __launch_bounds__(256) k_compact_clean(BatchDesc b, const uint32_t* __restrict__ chunkContig,
                                                        const uint32_t* __restrict__ chunkOff,
+                                                       const uint32_t* __restrict__ dirtyMask,
                                                        const uint8_t* __restrict__ chunkSegN,
                                                        const uint2* __restrict__ chunkSeg, uint32_t* __restrict__ seedPos,
                                                        uint32_t* __restrict__ seedEnc, uint8_t* __restrict__ seedN,
                                                        uint32_t* __restrict__ seedContig, uint32_t seedCap) {
     if (chunkOff[b.nTiles] > seedCap) return;
     for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < b.nTiles; g += gridDim.x * blockDim.x) {
-        const uint32_t fl = chunkSegN[g];
-        if (!(fl & 0x80u)) continue;
-        const uint32_t pin = fl & 15u;
+        if (dirtyMask[g]) continue;
+        const uint32_t pin = chunkSegN[g] & 15u;
         const uint2 sg = chunkSeg[g];  // .x = entry of group 0's seed, .y = D
         const uint32_t c = chunkContig[g];
         const uint32_t base = (g - b.tileStart[c]) * PROBE_CHUNK + pin;
@@ -958,11 +1036,12 @@ int launch_compact_and_runs(const IndexState& ix, const BatchDesc& b, const Work
     // tileCount -> tileOff (in place), tileOff[nTiles] = nSeeds
     launches += scan_exclusive(w.tileCount, w.tileCount, nullptr, b.nTiles, b.nTiles, w.blockSums, nullptr, st);
     k_compact<<<sm * 8, 256, 0, st>>>(b, w.chunkContig, w.tileCount, w.seedMask, w.scratchEnc,
-                                      segments ? w.workList : nullptr, segments ? w.counters + 5 : nullptr, w.seedPos,
-                                      w.seedEnc, w.seedN, w.seedContig, w.seedCap, w.counters);
+                                      segments ? w.workList : nullptr, segments ? w.counters + 6 : nullptr,
+                                      w.dirtyMask, w.chunkSegN, w.chunkSeg, w.seedPos, w.seedEnc, w.seedN,
+                                      w.seedContig, w.seedCap, w.counters);
     if (segments) {
-        k_compact_clean<<<sm * 8, 256, 0, st>>>(b, w.chunkContig, w.tileCount, w.chunkSegN, w.chunkSeg, w.seedPos,
-                                                w.seedEnc, w.seedN, w.seedContig, w.seedCap);
+        k_compact_clean<<<sm * 8, 256, 0, st>>>(b, w.chunkContig, w.tileCount, w.dirtyMask, w.chunkSegN, w.chunkSeg,
+                                                w.seedPos, w.seedEnc, w.seedN, w.seedContig, w.seedCap);
         launches += 1;
     }
     k_heads<<<sm * 8, 256, 0, st>>>(ix, b, w.tileCount, w.seedPos, w.seedEnc, w.seedN, w.seedContig, w.headScan,

@@ -71,9 +71,11 @@ struct WorkBuffers {     // device scratch of one pass
     uint32_t* tileCount;     // [nChunks+1] seed segments per chunk -> exclusive scan in place (chunk offsets)
     uint32_t* chunkContig;   // [nChunks]
     unsigned long long* anchor;  // [nChunks] first verified seed among the first 16 positions: (pos in chunk << 32) | entry
-    uint8_t* chunkSegN;      // [nChunks] 0x80 | pin = clean chunk (pin = offset of its first grid position), 0 = full probe
+    uint8_t* chunkSegN;      // [nChunks] 0x80 | pin = chunk with clean lanes (pin = offset of the grid position in a lane), 0 = none
     uint2* chunkSeg;         // [nChunks] clean chunks: (table entry of group 0's seed, mask of 16-position groups with a seed)
-    uint32_t* workList;      // [nChunks] chunks that need the full probe (fast path only)
+    uint32_t* workList;      // [nChunks] chunks with at least one dirty lane (fast path only)
+    uint32_t* dirtyMask;     // [nChunks] lanes (16-position groups) of the chunk that need the full probe
+    uint32_t* laneList;      // [nChunks*32] dirty lanes as items chunk * 32 + lane
     uint4* chunkDesc;        // [nChunks] text offset lo/hi, contig-local base position, nValid
     uint16_t* seedMask;      // [nChunks*32] per-lane 16-bit seed masks
     uint32_t* scratchEnc;    // [nChunks*PROBE_CHUNK] position-indexed table entries of the seeds
@@ -91,7 +93,7 @@ struct WorkBuffers {     // device scratch of one pass
     uint32_t* matchOff;      // [nContigs+1]
     TextMatchRec* matchesDense;  // [seedCap] the pass's matches in text order, host layout
     uint32_t* blockSums;     // scan temporaries
-    uint32_t* counters;      // [8]: 0 nSegments, 1 nRuns, 2 nMatches, 3 overflow flag, 5 work-list length
+    uint32_t* counters;      // [8]: 0 nSegments, 1 nRuns, 2 nMatches, 3 overflow flag, 6 chunks with dirty lanes, 7 dirty lanes (one 64-bit word)
     uint32_t seedCap;
 };
 
@@ -108,7 +110,7 @@ void launch_table_low32(const unsigned long long* ht, uint32_t* out, uint64_t n,
 // ---- match pass ----
 // returns the number of kernel launches issued
 int launch_chunk_desc(const IndexState& ix, const BatchDesc& b, const WorkBuffers& w, cudaStream_t st);
-// full probe of every chunk (useWorkList = false) or of the chunks the fast path could not prove clean
+// full probe of every chunk (useWorkList = false) or of the 16-position lanes the fast path could not prove clean
 int launch_probe(const IndexState& ix, const BatchDesc& b, const WorkBuffers& w, bool useFilter, bool useWorkList,
                  cudaStream_t st);
 // fast path for near-identical texts (needs the self-probe memo of the reference, see kernels.cu):

@@ -318,6 +318,8 @@ void B200SparseEMMatcher::ensureWork(uint64_t textBytes, uint32_t nTiles, int nC
     const uint64_t oChunkSegN = carve(static_cast<uint64_t>(nTiles) + 64);
     const uint64_t oWorkList = carve((static_cast<uint64_t>(nTiles) + 2) * 4);
     const uint64_t oChunkSeg = carve((static_cast<uint64_t>(nTiles) + 2) * 8);
+    const uint64_t oDirtyMask = carve((static_cast<uint64_t>(nTiles) + 2) * 4);
+    const uint64_t oLaneList = carve((static_cast<uint64_t>(nTiles) + 2) * 32 * 4);
     const uint64_t oChunkDesc = carve((static_cast<uint64_t>(nTiles) + 2) * 16);
     const uint64_t oSeedMask = carve((static_cast<uint64_t>(nTiles) + 1) * 32 * 2);
     const uint64_t oScratchEnc = carve(scratchN * 4);
@@ -351,6 +353,8 @@ void B200SparseEMMatcher::ensureWork(uint64_t textBytes, uint32_t nTiles, int nC
     wb.chunkSegN = dWork + oChunkSegN;
     wb.workList = reinterpret_cast<uint32_t*>(dWork + oWorkList);
     wb.chunkSeg = reinterpret_cast<uint2*>(dWork + oChunkSeg);
+    wb.dirtyMask = reinterpret_cast<uint32_t*>(dWork + oDirtyMask);
+    wb.laneList = reinterpret_cast<uint32_t*>(dWork + oLaneList);
     wb.chunkDesc = reinterpret_cast<uint4*>(dWork + oChunkDesc);
     wb.seedMask = reinterpret_cast<uint16_t*>(dWork + oSeedMask);
     wb.scratchEnc = reinterpret_cast<uint32_t*>(dWork + oScratchEnc);
@@ -400,7 +404,7 @@ bool B200SparseEMMatcher::wantMemo(uint64_t positions) {
     if (forced == 0 || k1 != 16 || k1ord != 4 || K < 16 || reachedRefLengthCount != 0) return false;
     if (pos1 <= static_cast<int64_t>(K) || static_cast<uint64_t>(pos1) >= (1ull << 32) - 65536) return false;
     if (forced == 1) return true;
-    if (cleanEstimate < 0.05) return false;
+    if (cleanEstimate < 0.6) return false;  // below that the anchor + compare passes cost more than they save
     if (memoSeq == insertSeq) return true;
     const double benefit = cleanEstimate * static_cast<double>(positions) *
                            static_cast<double>(std::max<uint64_t>(1, passesSinceInsert));
@@ -782,8 +786,8 @@ void B200SparseEMMatcher::matchBatch(const std::vector<TextView>& texts, const u
             check(cudaEventElapsedTime(&ms, ev[8], ev[2]), "event time");
             stageMs[MBGCG_T_FULLPROBE] += ms;
             // clean-fraction estimate for the fast-path policy (see wantMemo)
-            if (useFast && tiles) {
-                cleanEstimate = static_cast<double>(tiles - std::min(hCtr[5], tiles)) / tiles;
+            if (useFast && tiles) {  // share of the 16-position lanes that did not need the full probe
+                cleanEstimate = 1.0 - static_cast<double>(hCtr[7]) / (32.0 * tiles);
             } else if (positions) {
                 uint64_t covered = 0;
                 const uint32_t stride = total / 4096 + 1;  // a sample is enough for the policy
@@ -792,7 +796,7 @@ void B200SparseEMMatcher::matchBatch(const std::vector<TextView>& texts, const u
                 cleanEstimate = static_cast<double>(covered) * stride / static_cast<double>(positions);
             }
             lastCounters[6] += tiles;
-            lastCounters[7] += useFast ? hCtr[5] : tiles;
+            lastCounters[7] += useFast ? hCtr[7] : static_cast<uint64_t>(tiles) * 32;
             lastCounters[0] += positions;
             lastCounters[1] += hCtr[0];
             lastCounters[2] += hCtr[1];

@@ -136,7 +136,7 @@ private:
     uint64_t memoSeq = 0;                // insertSeq the memo was built at (0 = none)
     uint64_t memoLen = 0;                // reference positions covered
     uint64_t passesSinceInsert = 0;      // match passes since the index last changed
-    double cleanEstimate = 0.5;          // expected fraction of clean chunks (updated from every pass)
+    double cleanEstimate = 0.75;         // expected share of clean 16-position lanes (updated from every pass)
     std::deque<uint64_t> workersSwEndPositions;
 
     // text transfer (host-packed blocks)

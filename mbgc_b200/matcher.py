@@ -231,7 +231,7 @@ class Matcher:
         c = (C.c_uint64 * 8)()
         self.lib.mbgcg_last_counters(self.h, c)
         return {"positions": c[0], "seeds": c[1], "runs": c[2], "matches": c[3], "launches": c[4],
-                "passes": c[5], "chunks": c[6], "chunks_full_probe": c[7]}
+                "passes": c[5], "chunks": c[6], "lanes_full_probe": c[7]}
 
     def stream(self):
         """cudaStream_t (as int) all work of this matcher is issued on"""

