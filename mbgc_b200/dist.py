@@ -67,3 +67,84 @@ def gather_in_target_order(local_lists, n_targets, device="cpu"):
             out.append(flat[o:o + int(counts_h[t])])
             o += int(counts_h[t])
     return out
+
+
+# ------------------------------------------------------------------------------------------------------
+# The exchange step of the sharded path: reference extensions
+#
+# Index and reference are replicated.  When a target contig qualifies for reference extension
+# (MultipleGenomeMatchingProcessor.cpp:277-287, 389-398, 441) its bytes must reach every replica, and every
+# replica must apply the same loadRef calls in the same order: the index build is deterministic in that order
+# (insert sequence numbers), so the replicas stay bit-identical without exchanging table contents.
+# ------------------------------------------------------------------------------------------------------
+
+def broadcast_bytes(data, src, device="cpu"):
+    """Sends a uint8 array from rank `src` to every rank (two collectives: length, payload).  With the nccl backend
+    pass device="cuda": the payload travels GPU to GPU over NVLink; gloo uses host tensors."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return np.ascontiguousarray(data, dtype=np.uint8)
+    rank = dist.get_rank()
+    n = torch.tensor([len(data) if rank == src else 0], dtype=torch.int64, device=device)
+    dist.broadcast(n, src)
+    n = int(n.item())
+    if rank == src:
+        buf = torch.from_numpy(np.ascontiguousarray(data, dtype=np.uint8)).to(device)
+    else:
+        buf = torch.empty(n, dtype=torch.uint8, device=device)
+    if n:
+        dist.broadcast(buf, src)
+    return buf.cpu().numpy()
+
+
+def extend_reference_everywhere(matcher, text, owner, load_rc, device="cpu", separator=0):
+    """`owner` holds `text` (others pass None); afterwards every rank's matcher has loaded it (and its reverse
+    complement if load_rc), i.e. the replicas made the same loadRef call."""
+    data = broadcast_bytes(text, owner, device)
+    matcher.loadRef(data, load_rc, True, separator)
+    return data
+
+
+def match_speculative(matcher, texts, extension_rule, window, device="cpu", min_match_length=32):
+    """Sequential-equivalent matching of `texts` (in order) with a growing reference, sharded over the ranks by
+    optimistic batching.
+
+    The reference's sequential schedule is: match text i, decide from its match list whether it extends the
+    reference (and with its reverse complement), load it, go on to i + 1
+    (MultipleGenomeMatchingProcessor.cpp:274-287).  A text that does not extend the reference leaves the matcher
+    state untouched, so a whole window of texts can be matched in parallel against the frozen state; results are
+    committed in order up to and including the first text that extends the reference, that extension is applied on
+    every rank (broadcast from the rank that matched it), and the rest of the window is matched again.  On
+    near-identical collections nothing qualifies and every window commits whole; on divergent ones this
+    degenerates to one text per round.
+
+    Every rank passes the same `texts` (uint8 arrays).  extension_rule(text_len, matches) -> (extend, load_rc) must
+    be a pure function of its arguments (the reference's rule needs the unmatched-character count of
+    MBGC_Encoder::processMatches, which the caller supplies through this hook).  Returns the per-text match lists,
+    identical on every rank and identical to the one-text-at-a-time schedule, and the number of rounds."""
+    import torch.distributed as dist
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
+    n = len(texts)
+    out = [None] * n
+    done, rounds = 0, 0
+    while done < n:
+        hi = min(n, done + window)
+        spans = [shard_range(hi - done, r, world) for r in range(world)]
+        b, e = spans[rank]
+        mine = [texts[done + k] for k in range(b, e)]
+        local = matcher.matchBatch(mine, min_match_length) if mine else []
+        lists = gather_in_target_order(local, hi - done, device)
+        rounds += 1
+        committed = 0
+        for k, m in enumerate(lists):
+            out[done + k] = m
+            committed += 1
+            extend, load_rc = extension_rule(len(texts[done + k]), m)
+            if extend:
+                owner = next(r for r, (sb, se) in enumerate(spans) if sb <= k < se)  # the rank that matched it
+                extend_reference_everywhere(matcher, texts[done + k] if rank == owner else None, owner, load_rc, device)
+                break
+        done += committed
+    return out, rounds

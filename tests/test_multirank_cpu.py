@@ -70,3 +70,89 @@ def test_two_ranks_equal_single_process():
     assert len(got) == len(want) and total == sum(len(a) for a in want) and slow == 11.0
     for a, b in zip(got, want):
         assert np.array_equal(np.array(a, dtype=np.uint64).reshape(-1, 3), b)
+
+
+class _OracleAsMatcher:
+    """the CPU oracle behind the two Matcher methods match_speculative uses (tests only)"""
+
+    def __init__(self, limit):
+        from util import OracleMatcher
+        self.o = OracleMatcher(limit)
+        self.o.disable_sliding_window()
+
+    def loadRef(self, text, rc, add_sep=True, sep=0):
+        self.o.load_ref(np.asarray(text, dtype=np.uint8), rc=bool(rc))
+
+    def matchBatch(self, texts, min_len=32):
+        return [self.o.match(t, min_len) for t in texts]
+
+
+def _rule(n, m):
+    """stand-in for isContigProperForRefExtension (MGMP_Params.h:179-190): unmatched * 128 > length"""
+    matched = int(m[:, 1].sum()) if len(m) else 0
+    unmatched = n - matched
+    return unmatched * 128 > n, unmatched * 8 > n
+
+
+def _collection():
+    from mbgc_b200.synth import synth_base, synth_mutant
+    base = synth_base(80_000, 77)
+    other = synth_base(60_000, 78)
+    texts = []
+    for i in range(10):
+        src = base if i % 4 != 2 else other                       # every 4th text is novel: it extends the reference
+        texts.append(synth_mutant(src, 500 + i, 2e-4 if i % 3 else 2e-2, 1e-5))
+    return base, texts
+
+
+def _spec_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import torch.distributed as dist
+    from mbgc_b200.dist import match_speculative
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    base, texts = _collection()
+    m = _OracleAsMatcher(1 << 22)
+    m.loadRef(base, True)
+    lists, rounds = match_speculative(m, texts, _rule, window=4)
+    table = m.o.table()
+    dist.barrier()
+    q.put((rank, [a.tolist() for a in lists], rounds, int(table.astype(np.uint64).sum()), m.o.loading_position))
+    dist.destroy_process_group()
+
+
+def test_speculative_batching_equals_sequential_schedule():
+    """optimistic batching over 2 ranks with reference extensions broadcast between them gives the
+    match lists of the one-text-at-a-time schedule, and both replicas end with the same index"""
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_spec_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    base, texts = _collection()
+    m = _OracleAsMatcher(1 << 22)
+    m.loadRef(base, True)
+    want, extensions = [], 0
+    for t in texts:
+        a = m.o.match(t)
+        want.append(a)
+        ext, rc = _rule(len(t), a)
+        if ext:
+            m.loadRef(t, rc)
+            extensions += 1
+    assert 0 < extensions < len(texts)
+    for rank, lists, rounds, tsum, pos in res:
+        assert len(lists) == len(want)
+        for a, b in zip(lists, want):
+            assert np.array_equal(np.array(a, dtype=np.uint64).reshape(-1, 3), b)
+        assert tsum == int(m.o.table().astype(np.uint64).sum()) and pos == m.o.loading_position
+        assert rounds < len(texts)  # some windows committed more than one text
