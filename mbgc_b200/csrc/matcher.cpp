@@ -497,7 +497,8 @@ void B200SparseEMMatcher::growDevice(void** p, uint64_t* cap, uint64_t need, con
 // fraction of the speed) while the worker pool packs the others 4:1 into pinned staging memory; packed blocks are
 // copied as they finish and expanded on the device.  See hostpack.hpp for why.
 //   MBGC_B200_PACK          0 = never pack; unset / 1 = pack batches of 8 MiB and more
-//   MBGC_B200_RAW_PERMILLE  share of the bytes that travels raw while the CPU packs the rest (default 300)
+//   MBGC_B200_RAW_PERMILLE  share of the bytes that travels raw while the CPU packs the rest (default: from the
+//                           number of packer threads, 300 with 15 of them)
 //   MBGC_B200_PACK_THREADS  worker threads (default: hardware threads / LOCAL_WORLD_SIZE - 1)
 int B200SparseEMMatcher::stageTexts(const std::vector<TextView>& texts, size_t first, int nC,
                                     const std::vector<uint64_t>& off) {
@@ -536,7 +537,11 @@ int B200SparseEMMatcher::stageTexts(const std::vector<TextView>& texts, size_t f
             pinnedSrc = false;
         }
     }
-    int rawPermille = 300;
+    // raw share r that balances the copy engine ((r + (1 - r) / 4) bytes at ~52 GB/s) against the packers ((1 - r)
+    // bytes at ~4.8 GB/s per thread, measured on the B200 box): r = (c - 1/4) / (3/4 + c), c = 52 / (4.8 threads);
+    // 15 threads -> 0.32 (the sweep's optimum was 0.30), 5 threads (8 ranks on 48 cores) -> 0.66
+    const double cRatio = 52.0 / (4.8 * pool->size());
+    int rawPermille = static_cast<int>(1000.0 * std::max(0.3, std::min(1.0, (cRatio - 0.25) / (0.75 + cRatio))));
     if (const char* e = std::getenv("MBGC_B200_RAW_PERMILLE")) rawPermille = std::max(0, std::min(1000, std::atoi(e)));
     if (!pinnedSrc) rawPermille = 0;
     uint64_t seen = 0, rawBytes = 0, packedBytes = 0;
