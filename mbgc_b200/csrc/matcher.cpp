@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <chrono>
 #include <cstring>
@@ -79,10 +80,19 @@ void B200SparseEMMatcher::check(cudaError_t e, const char* what) {
 B200SparseEMMatcher::B200SparseEMMatcher(uint64_t refLengthLimit, uint32_t targetMatchLength, int _k1, int _k2,
                                          int _skipMargin, int dev)
     : maxRefLength(refLengthLimit), L(static_cast<int>(targetMatchLength)), skipMargin(_skipMargin), device(dev) {
+    const bool trace = std::getenv("MBGC_B200_TRACE") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (trace)
+            fprintf(stderr, "[mbgc_b200]   create: %-28s at %9.3f ms\n", what,
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    };
     int nDev = 0;
     if (cudaGetDeviceCount(&nDev) != cudaSuccess || nDev == 0)
         throw MatcherError(MBGCG_E_CUDA, "no CUDA device: the B200 matcher has no CPU fallback");
     check(cudaSetDevice(device), "cudaSetDevice");
+    check(cudaFree(nullptr), "context");
+    lap("CUDA context");
     if (targetMatchLength < 16)  // MIN_MATCH_LENGTH, .h:23 / .cpp:82-85
         throw MatcherError(MBGCG_E_PARAM, "Error: Minimal matching length too short!");
     if (maxRefLength < 2) throw MatcherError(MBGCG_E_PARAM, "reference length limit too small");
@@ -114,6 +124,7 @@ B200SparseEMMatcher::B200SparseEMMatcher(uint64_t refLengthLimit, uint32_t targe
 
     hostRef = static_cast<char*>(std::calloc(maxRefLength + PAD, 1));
     if (!hostRef) throw MatcherError(MBGCG_E_NOMEM, "host mirror allocation failed");
+    lap("host mirror");
     check(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate");
     for (auto& e : ev) check(cudaEventCreate(&e), "cudaEventCreate");
     check(cudaMalloc(&dRefAlloc, maxRefLength + PAD + REF_TAIL), "cudaMalloc(ref)");
@@ -126,6 +137,7 @@ B200SparseEMMatcher::B200SparseEMMatcher(uint64_t refLengthLimit, uint32_t targe
     check(cudaMalloc(&dFilter, PROBE_FILTER_BYTES), "cudaMalloc(filter)");
     check(cudaMemsetAsync(dFilter, 0, PROBE_FILTER_BYTES, stream), "memset(filter)");
     check(cudaStreamSynchronize(stream), "init sync");
+    lap("device buffers allocated + zeroed");
 }
 
 B200SparseEMMatcher::~B200SparseEMMatcher() {

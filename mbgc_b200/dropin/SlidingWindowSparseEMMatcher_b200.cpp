@@ -19,6 +19,7 @@
 // Errors keep the reference's behaviour: message on stderr, exit(EXIT_FAILURE).
 #include "SlidingWindowSparseEMMatcher.h"
 
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <mutex>
@@ -37,6 +38,23 @@ inline mbgcg_t* handle_of(uint64_t* slot) { return reinterpret_cast<mbgcg_t*>(sl
     fprintf(stderr, "%s\n\n", msg);
     exit(EXIT_FAILURE);
 }
+
+// MBGC_B200_TRACE=1: wall time of every call through the shim on stderr
+struct Trace {
+    const char* what;
+    size_t n;
+    std::chrono::steady_clock::time_point t0;
+    static bool on() {
+        static const bool v = std::getenv("MBGC_B200_TRACE") != nullptr;
+        return v;
+    }
+    Trace(const char* w, size_t bytes) : what(w), n(bytes), t0(std::chrono::steady_clock::now()) {}
+    ~Trace() {
+        if (on())
+            fprintf(stderr, "[mbgc_b200] %-14s %10zu bytes %9.3f ms\n", what, n,
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    }
+};
 
 int device_from_env() {
     const char* e = std::getenv("MBGC_B200_DEVICE");
@@ -75,6 +93,7 @@ SlidingWindowSparseEMMatcher::SlidingWindowSparseEMMatcher(const size_t refLengt
         : maxRefLength(refLengthLimit), L(targetMatchLength), skipMargin(skipMargin) {
     (void) minMatchLength;
     (void) skipHtInit;
+    Trace tr("create", refLengthLimit);
     mbgcg_t* h = nullptr;
     if (mbgcg_create(&h, refLengthLimit, targetMatchLength, _k1, _k2, skipMargin, device_from_env()) != MBGCG_OK)
         die(mbgcg_create_error());
@@ -125,6 +144,7 @@ SlidingWindowSparseEMMatcher::~SlidingWindowSparseEMMatcher() {
 // ref .cpp:453-458
 void SlidingWindowSparseEMMatcher::loadRef(const char* refText, size_t refLength, bool loadRCRef, bool addRegionSeparators,
                                            char regionSeparator) {
+    Trace tr("loadRef", refLength);
     std::lock_guard<std::mutex> g(g_lock);
     mbgcg_t* h = handle_of(ht64bit);
     MBGCG_PUSH_STATE(h);
@@ -167,6 +187,7 @@ void SlidingWindowSparseEMMatcher::matchTexts(vector<TextMatch>& resMatches, con
                                               size_t matchingLockPos) {
     if (destIsRef || revComplMatching)  // ref .cpp:185-188
         die("Source as destination and reverse-complement matching modes unsupported");
+    Trace tr("matchTexts", destLen);
     std::lock_guard<std::mutex> g(g_lock);
     mbgcg_t* h = handle_of(ht64bit);
     MBGCG_PUSH_STATE(h);
