@@ -181,6 +181,10 @@ int mbgcg_selftest_pack(const char* text, uint64_t n, char* out) {
 }
 
 void mbgcg_last_timing(const mbgcg_t* h, float ms[MBGCG_T_COUNT]) {
+    try {
+        h->m->collectTiming();
+    } catch (const std::exception&) {
+    }
     for (int i = 0; i < MBGCG_T_COUNT; i++) ms[i] = h->m->stageMs[i];
 }
 void mbgcg_last_counters(const mbgcg_t* h, uint64_t out[8]) {

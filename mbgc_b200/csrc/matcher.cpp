@@ -388,6 +388,25 @@ void B200SparseEMMatcher::ensureWork(uint64_t textBytes, uint32_t nTiles, int nC
     wb.seedCap = seedCap;
 }
 
+// stage times of the last pass from its events (lazily: ten cudaEventElapsedTime calls are not free)
+void B200SparseEMMatcher::collectTiming() {
+    if (!timingPending) return;
+    timingPending = false;
+    float ms;
+    for (int s = 0; s < 6; s++) {
+        check(cudaEventElapsedTime(&ms, ev[s], ev[s + 1]), "event time");
+        stageMs[s] += ms;
+    }
+    check(cudaEventElapsedTime(&ms, ev[0], ev[6]), "event time");
+    stageMs[MBGCG_T_TOTAL] += ms;
+    check(cudaEventElapsedTime(&ms, ev[1], ev[7]), "event time");
+    stageMs[MBGCG_T_ANCHOR] += ms;
+    check(cudaEventElapsedTime(&ms, ev[7], ev[8]), "event time");
+    stageMs[MBGCG_T_CLEAN] += ms;
+    check(cudaEventElapsedTime(&ms, ev[8], ev[2]), "event time");
+    stageMs[MBGCG_T_FULLPROBE] += ms;
+}
+
 void B200SparseEMMatcher::fillIndexState(IndexState& ix) const {
     ix.ref = dRef;
     ix.ht = dHt;
@@ -655,6 +674,7 @@ void B200SparseEMMatcher::matchBatch(const std::vector<TextView>& texts, const u
     nMatchesAll = 0;
     resCounts.assign(texts.size(), 0);
     for (auto& m : stageMs) m = 0;
+    timingPending = false;
     for (auto& c : lastCounters) c = 0;
     if (texts.empty()) return;
     for (const auto& t : texts)
@@ -765,6 +785,14 @@ void B200SparseEMMatcher::matchBatch(const std::vector<TextView>& texts, const u
             uint32_t* hCtr = hCounts + nC + 1;    // [8]
             check(cudaMemcpyAsync(hOffs, wb.matchOff, (static_cast<uint64_t>(nC) + 1) * 4, cudaMemcpyDeviceToHost, stream), "D2H(counts)");
             check(cudaMemcpyAsync(hCtr, wb.counters, 32, cudaMemcpyDeviceToHost, stream), "D2H(counters)");
+            // the match list itself: its length is only known after a sync, so a guess (last pass + 1.5 %) travels with
+            // the counts and a second copy fetches the rest if the guess was short -- one sync instead of two
+            uint64_t guess = std::min<uint64_t>(matchGuess, hMatchesCap > nMatchesAll ? hMatchesCap - nMatchesAll : 0);
+            guess = std::min<uint64_t>(guess, seedCap);
+            if (guess)
+                check(cudaMemcpyAsync(hMatches + nMatchesAll, wb.matchesDense, guess * sizeof(TextMatch),
+                                      cudaMemcpyDeviceToHost, stream), "D2H(matches, guessed)");
+            check(cudaEventRecord(ev[6], stream), "event");
             check(cudaStreamSynchronize(stream), "match pass sync");
             if (hCtr[3]) {  // seed capacity exceeded: rerun this pass with the worst-case capacity
                 if (attempt > 0) throw MatcherError(MBGCG_E_NOMEM, "seed buffer overflow after retry");
@@ -772,36 +800,28 @@ void B200SparseEMMatcher::matchBatch(const std::vector<TextView>& texts, const u
                 continue;
             }
             const uint32_t total = hOffs[nC];
+            matchGuess = static_cast<uint64_t>(total) + total / 64 + 1024;
             if (nMatchesAll + total > hMatchesCap) {  // grow the pinned result buffer, keeping earlier passes
                 const uint64_t cap = (nMatchesAll + total) + (nMatchesAll + total) / 2 + 4096;
                 TextMatch* grown = nullptr;
                 check(cudaHostAlloc(&grown, cap * sizeof(TextMatch), cudaHostAllocDefault), "cudaHostAlloc(matches)");
-                if (nMatchesAll) std::memcpy(grown, hMatches, nMatchesAll * sizeof(TextMatch));
+                if (nMatchesAll + guess) std::memcpy(grown, hMatches, (nMatchesAll + std::min<uint64_t>(guess, total)) * sizeof(TextMatch));
                 if (hMatches) cudaFreeHost(hMatches);
                 hMatches = grown;
                 hMatchesCap = cap;
             }
             TextMatch* passMatches = hMatches + nMatchesAll;
-            if (total)  // the gather kernel already wrote the host layout (TextMatch): no conversion on the host
-                check(cudaMemcpyAsync(passMatches, wb.matchesDense, static_cast<uint64_t>(total) * sizeof(TextMatch),
-                                      cudaMemcpyDeviceToHost, stream), "D2H(matches)");
-            check(cudaEventRecord(ev[6], stream), "event");
-            check(cudaStreamSynchronize(stream), "D2H sync");
+            if (total > guess) {  // the gather kernel already wrote the host layout (TextMatch): no conversion on the host
+                check(cudaMemcpyAsync(passMatches + guess, wb.matchesDense + guess,
+                                      (static_cast<uint64_t>(total) - guess) * sizeof(TextMatch), cudaMemcpyDeviceToHost,
+                                      stream), "D2H(matches)");
+                check(cudaEventRecord(ev[6], stream), "event");
+                check(cudaStreamSynchronize(stream), "D2H sync");
+            }
             nMatchesAll += total;
             for (int c = 0; c < nC; c++) resCounts[first + c] = hOffs[c + 1] - hOffs[c];
-            float ms;
-            for (int s = 0; s < 6; s++) {
-                check(cudaEventElapsedTime(&ms, ev[s], ev[s + 1]), "event time");
-                stageMs[s] += ms;
-            }
-            check(cudaEventElapsedTime(&ms, ev[0], ev[6]), "event time");
-            stageMs[MBGCG_T_TOTAL] += ms;
-            check(cudaEventElapsedTime(&ms, ev[1], ev[7]), "event time");
-            stageMs[MBGCG_T_ANCHOR] += ms;
-            check(cudaEventElapsedTime(&ms, ev[7], ev[8]), "event time");
-            stageMs[MBGCG_T_CLEAN] += ms;
-            check(cudaEventElapsedTime(&ms, ev[8], ev[2]), "event time");
-            stageMs[MBGCG_T_FULLPROBE] += ms;
+            timingPending = true;  // the events of this pass are read when somebody asks (collectTiming)
+            if (last < texts.size()) collectTiming();  // more passes follow and will reuse the events
             // clean-fraction estimate for the fast-path policy (see wantMemo)
             if (useFast && tiles) {  // share of the 16-position lanes that did not need the full probe
                 cleanEstimate = 1.0 - static_cast<double>(hCtr[7]) / (32.0 * tiles);

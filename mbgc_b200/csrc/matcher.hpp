@@ -103,7 +103,8 @@ public:
     uint32_t hashSize = 0;
     int L = 0, K = 0, k1 = 0, k2 = 0, skipMargin = 0, k1ord = -1;
 
-    float stageMs[MBGCG_T_COUNT_] = {0};
+    float stageMs[MBGCG_T_COUNT_] = {0};   // valid after collectTiming()
+    void collectTiming();
     uint64_t lastCounters[8] = {0};
     uint64_t totalLaunches = 0;
 
@@ -124,6 +125,7 @@ private:
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[12] = {};
+    bool timingPending = false;
     char* hostRef = nullptr;             // host mirror (getRef())
     uint8_t* dRefAlloc = nullptr;        // device reference buffer with padding
     uint8_t* dRef = nullptr;             // = dRefAlloc + PAD
@@ -157,6 +159,7 @@ private:
     uint32_t wbTiles = 0; int wbContigs = 0;
     TextMatch* hMatches = nullptr; uint64_t hMatchesCap = 0;  // pinned; all passes of the last call, text order
     uint64_t nMatchesAll = 0;
+    uint64_t matchGuess = 0;             // matches expected from the next pass (copied back before their count is known)
     uint32_t* hCounts = nullptr; uint64_t hCountsCap = 0;    // pinned
     std::vector<uint64_t> resCounts;
 };
