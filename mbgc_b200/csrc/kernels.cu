@@ -557,7 +557,7 @@ struct CleanArgs {
 // memo window) is a few dozen instructions that every lane of the chunk repeats, so fewer lanes per chunk means
 // fewer issue slots; each lane compares 4 x 16 bytes, the pieces interleaved so that the 8 lanes of a chunk read
 // 128 contiguous bytes per load instruction.
-__global__ void __launch_bounds__(256) k_clean(const CleanArgs a) {
+__global__ void __launch_bounds__(256, 8) k_clean(const CleanArgs a) {
     const int lane = threadIdx.x & 31, sub = lane & 7, cg = lane >> 3;
     const int K = a.ix.K;
     const int tailWords = (K + 2) / 4;  // the K-1 bytes the chunk's last k-mers reach past it, rounded up to words
