@@ -51,6 +51,35 @@ __device__ __forceinline__ uint64_t ld_u64_unaligned(const uint8_t* p) {
            (static_cast<uint64_t>(__funnelshift_r(w1, w2, sh)) << 32);
 }
 
+// ---- mbarrier / bulk-copy (TMA) primitives: Blackwell async proxy, inline PTX ----
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+
 // utils/Hashes.h:28-40 (maRushPrime1HashSimplified<K>): only the low 32 bits are ever used
 __device__ __forceinline__ uint32_t hash_step(uint32_t h, uint32_t w, uint32_t j) { return (h ^ (w + j)) * 171717u; }
 
@@ -395,13 +424,23 @@ template <int KW, bool FILTER>
 __global__ void __launch_bounds__(FILTER ? PROBE_THREADS_FILTER : PROBE_THREADS_PLAIN, 1) k_probe(const ProbeArgs a) {
     constexpr int NPT = PROBE_NPT;
     constexpr int NWA = probe_words(KW);
-    extern __shared__ uint32_t sFilter[];
+    extern __shared__ __align__(128) uint32_t sFilter[];  // [filter words][mbarrier]
     const int lane = threadIdx.x & 31;
+    // The first-level filter comes in by bulk copy (TMA): one thread queues the 192 KiB in 32 KiB pieces on an
+    // mbarrier and the CTA goes straight on to its first items' descriptor and text loads; the wait sits in front of
+    // the first filter lookup.
+    const uint32_t barAddr = smem_addr(sFilter + a.ix.filterWords);
+    bool filterPending = FILTER;
     if (FILTER) {
-        const uint4* src = reinterpret_cast<const uint4*>(a.ix.filter);
-        uint4* dst = reinterpret_cast<uint4*>(sFilter);
-        for (uint32_t k = threadIdx.x; k < a.ix.filterWords / 4; k += blockDim.x) dst[k] = src[k];
+        if (threadIdx.x == 0) mbar_init(barAddr, 1);
         __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint32_t bytes = a.ix.filterWords * 4;
+            mbar_arrive_expect_tx(barAddr, bytes);
+            for (uint32_t off = 0; off < bytes; off += 32768)
+                tma_load_1d(smem_addr(sFilter) + off, reinterpret_cast<const uint8_t*>(a.ix.filter) + off,
+                            min(32768u, bytes - off), barAddr);
+        }
     }
     const uint32_t warpsTotal = gridDim.x * (blockDim.x >> 5);
     const uint32_t nItems = a.laneList ? *a.laneCount : a.b.nTiles * 32u;
@@ -423,6 +462,10 @@ __global__ void __launch_bounds__(FILTER ? PROBE_THREADS_FILTER : PROBE_THREADS_
                 const uint4 x = __ldg(gp + v);
                 A[4 * v] = x.x; A[4 * v + 1] = x.y; A[4 * v + 2] = x.z; A[4 * v + 3] = x.w;
             }
+        }
+        if (filterPending) {
+            mbar_wait(barAddr, 0);
+            filterPending = false;
         }
         uint32_t slots[NPT];
         uint32_t hit = probe_lane16<KW, FILTER>(a.ix, sFilter, A, slots);
@@ -827,10 +870,10 @@ static void launch_probe_k(const ProbeArgs& a, bool useFilter, int mode, cudaStr
         return;
     }
     if (useFilter) {
-        const size_t smem = static_cast<size_t>(a.ix.filterWords) * 4;
+        const size_t smem = static_cast<size_t>(a.ix.filterWords) * 4 + 16;  // filter + mbarrier
         static bool attrSet = false;
         if (!attrSet) {
-            cudaFuncSetAttribute(k_probe<KW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(PROBE_FILTER_BYTES));
+            cudaFuncSetAttribute(k_probe<KW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(PROBE_FILTER_BYTES + 16));
             attrSet = true;
         }
         k_probe<KW, true><<<sm, PROBE_THREADS_FILTER, smem, st>>>(a);

@@ -681,10 +681,8 @@ void B200SparseEMMatcher::matchBatch(const std::vector<TextView>& texts, const u
         if (t.len >= (1ull << 32)) throw MatcherError(MBGCG_E_UNSUPPORTED, "target text of 4 GiB or more");
 
     // split into passes of bounded size (work memory is ~26 bytes per target position)
-    static const uint64_t maxPassBytes = [] {
-        const char* e = std::getenv("MBGC_B200_MAX_PASS_BYTES");
-        return e ? std::strtoull(e, nullptr, 10) : (1024ull << 20);
-    }();
+    uint64_t maxPassBytes = 1024ull << 20;
+    if (const char* e = std::getenv("MBGC_B200_MAX_PASS_BYTES")) maxPassBytes = std::max<uint64_t>(1, std::strtoull(e, nullptr, 10));
     size_t first = 0;
     while (first < texts.size()) {
         size_t last = first;

@@ -115,3 +115,27 @@ def test_sliding_window_classes(lock_mode, fastpath):
     finally:
         g.close()
         o.close()
+
+
+@pytest.mark.parametrize("pass_bytes", ["300000", "2500000"])
+def test_many_passes_equal_one(monkeypatch, pass_bytes):
+    """a batch cut into many passes (MBGC_B200_MAX_PASS_BYTES) gives the lists of the single pass: per-pass
+    buffers, the pinned result buffer that grows across passes and the guessed match copy are all exercised"""
+    monkeypatch.delenv("MBGC_B200_FASTPATH", raising=False)
+    gs = synth_collection(10, 600_000, 17, 1e-3, 1e-4)
+    ts = gs[1:] + [gs[1][:10], np.zeros(0, np.uint8), gs[2][:100_000]]
+    limit = mgmp_ref_limit(10, gs[0].size)
+    g = CudaFace(limit)
+    try:
+        g.disable_sliding_window()
+        g.load_ref(gs[0], rc=True)
+        one = g.match_batch(ts)
+        assert g.m.counters()["passes"] == 1
+        monkeypatch.setenv("MBGC_B200_MAX_PASS_BYTES", pass_bytes)
+        many = g.match_batch(ts)
+        assert g.m.counters()["passes"] > 2
+        again = g.match_batch(ts)
+        for a, b, c in zip(one, many, again):
+            assert np.array_equal(a, b) and np.array_equal(a, c)
+    finally:
+        g.close()
