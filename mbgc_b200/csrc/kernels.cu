@@ -950,9 +950,7 @@ __global__ void __launch_bounds__(256) k_compact(BatchDesc b, const uint32_t* __
                                                  const uint32_t* __restrict__ workList, const uint32_t* workCount,
                                                  const uint32_t* __restrict__ dirtyMask,
                                                  const uint8_t* __restrict__ chunkSegN, const uint2* __restrict__ chunkSeg,
-                                                 uint32_t* __restrict__ seedPos, uint32_t* __restrict__ seedEnc,
-                                                 uint8_t* __restrict__ seedN, uint32_t* __restrict__ seedContig,
-                                                 uint32_t seedCap, uint32_t* counters) {
+                                                 SeedRec* __restrict__ seeds, uint32_t seedCap, uint32_t* counters) {
     const uint32_t nSeeds = chunkOff[b.nTiles];
     if (nSeeds > seedCap) {
         if (blockIdx.x == 0 && threadIdx.x == 0) counters[3] = 1;  // overflow: host retries with more room
@@ -982,11 +980,12 @@ __global__ void __launch_bounds__(256) k_compact(BatchDesc b, const uint32_t* __
         while (m) {
             const int p = __ffs(m) - 1;
             m &= m - 1;
-            seedPos[k] = base + p;
-            seedEnc[k] = dirty ? scratchEnc[src + p] : memoEnc;
-            seedN[k] = 1;
-            seedContig[k] = c;
-            k++;
+            SeedRec rec;
+            rec.pos = base + p;
+            rec.enc = dirty ? scratchEnc[src + p] : memoEnc;
+            rec.n = 1;
+            rec.contig = c;
+            seeds[k++] = rec;
         }
     }
 }
@@ -998,9 +997,8 @@ __global__ void __launch_bounds__(256) k_compact_clean(BatchDesc b, const uint32
                                                        const uint32_t* __restrict__ chunkOff,
                                                        const uint32_t* __restrict__ dirtyMask,
                                                        const uint8_t* __restrict__ chunkSegN,
-                                                       const uint2* __restrict__ chunkSeg, uint32_t* __restrict__ seedPos,
-                                                       uint32_t* __restrict__ seedEnc, uint8_t* __restrict__ seedN,
-                                                       uint32_t* __restrict__ seedContig, uint32_t seedCap) {
+                                                       const uint2* __restrict__ chunkSeg, SeedRec* __restrict__ seeds,
+                                                       uint32_t seedCap) {
     if (chunkOff[b.nTiles] > seedCap) return;
     for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < b.nTiles; g += gridDim.x * blockDim.x) {
         if (dirtyMask[g]) continue;
@@ -1014,11 +1012,12 @@ __global__ void __launch_bounds__(256) k_compact_clean(BatchDesc b, const uint32
             const int l = __ffs(D) - 1;
             // consecutive groups with a seed from l on (64-bit so that 32 ones give 32)
             const int n = __ffsll(static_cast<long long>(~static_cast<unsigned long long>(D >> l))) - 1;
-            seedPos[k] = base + 16u * l;
-            seedEnc[k] = sg.x + l;
-            seedN[k] = static_cast<uint8_t>(n);
-            seedContig[k] = c;
-            k++;
+            SeedRec rec;
+            rec.pos = base + 16u * l;
+            rec.enc = sg.x + l;
+            rec.n = static_cast<uint32_t>(n);
+            rec.contig = c;
+            seeds[k++] = rec;
             D = l + n >= 32 ? 0u : D & (~0u << (l + n));
         }
     }
@@ -1029,21 +1028,22 @@ __global__ void __launch_bounds__(256) k_compact_clean(BatchDesc b, const uint32
 // Seeds only collapse when their k-mers touch or overlap (k1 <= K); otherwise (protein profile: K = 12 < k1 = 16)
 // the bases between two seeds are unverified and every seed is its own run.  One thread per segment.
 __global__ void __launch_bounds__(256) k_heads(IndexState ix, BatchDesc b, const uint32_t* __restrict__ chunkOff,
-                                               const uint32_t* __restrict__ seedPos, const uint32_t* __restrict__ seedEnc,
-                                               const uint8_t* __restrict__ seedN, const uint32_t* __restrict__ seedContig,
-                                               uint32_t* __restrict__ head, const uint32_t* counters) {
+                                               const SeedRec* __restrict__ seeds, uint32_t* __restrict__ head,
+                                               const uint32_t* counters) {
     if (counters[3]) return;
     const uint32_t nSeeds = chunkOff[b.nTiles];
     const uint32_t encStep = ix.k1ord >= 0 ? static_cast<uint32_t>(ix.k1 >> ix.k1ord) : static_cast<uint32_t>(ix.k1);
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < nSeeds; j += gridDim.x * blockDim.x) {
         uint32_t h = 1;
-        const uint32_t c = seedContig[j];
-        if (j != 0 && seedContig[j - 1] == c) {
-            // last seed of the previous segment (a segment = seedN seeds, spacing k1, entries ascending)
-            const uint32_t nm1 = seedN[j - 1] - 1u;
-            const uint32_t e = seedEnc[j], ep = seedEnc[j - 1] + nm1 * encStep;
-            const uint32_t pp = seedPos[j - 1] + nm1 * static_cast<uint32_t>(ix.k1);
-            if (ix.k1 <= ix.K && seedPos[j] - pp == static_cast<uint32_t>(ix.k1) && e - ep == encStep) {
+        const SeedRec cur = seeds[j];
+        const SeedRec prev = j ? seeds[j - 1] : cur;
+        const uint32_t c = cur.contig;
+        if (j != 0 && prev.contig == c) {
+            // last seed of the previous segment (a segment = n seeds, spacing k1, entries ascending)
+            const uint32_t nm1 = prev.n - 1u;
+            const uint32_t e = cur.enc, ep = prev.enc + nm1 * encStep;
+            const uint32_t pp = prev.pos + nm1 * static_cast<uint32_t>(ix.k1);
+            if (ix.k1 <= ix.K && cur.pos - pp == static_cast<uint32_t>(ix.k1) && e - ep == encStep) {
                 const uint64_t lock = b.contigLock ? b.contigLock[c] : NO_LOCK;
                 const uint64_t swStop = lock != NO_LOCK ? lock : ix.pos1;
                 int c0, c1;
@@ -1085,15 +1085,13 @@ int launch_compact_and_runs(const IndexState& ix, const BatchDesc& b, const Work
     launches += scan_exclusive(w.tileCount, w.tileCount, nullptr, b.nTiles, b.nTiles, w.blockSums, nullptr, st);
     k_compact<<<sm * 8, 256, 0, st>>>(b, w.chunkContig, w.tileCount, w.seedMask, w.scratchEnc,
                                       segments ? w.workList : nullptr, segments ? w.counters + 6 : nullptr,
-                                      w.dirtyMask, w.chunkSegN, w.chunkSeg, w.seedPos, w.seedEnc, w.seedN,
-                                      w.seedContig, w.seedCap, w.counters);
+                                      w.dirtyMask, w.chunkSegN, w.chunkSeg, w.seeds, w.seedCap, w.counters);
     if (segments) {
         k_compact_clean<<<sm * 8, 256, 0, st>>>(b, w.chunkContig, w.tileCount, w.dirtyMask, w.chunkSegN, w.chunkSeg,
-                                                w.seedPos, w.seedEnc, w.seedN, w.seedContig, w.seedCap);
+                                                w.seeds, w.seedCap);
         launches += 1;
     }
-    k_heads<<<sm * 8, 256, 0, st>>>(ix, b, w.tileCount, w.seedPos, w.seedEnc, w.seedN, w.seedContig, w.headScan,
-                                    w.counters);
+    k_heads<<<sm * 8, 256, 0, st>>>(ix, b, w.tileCount, w.seeds, w.headScan, w.counters);
     launches += 2;
     // head flags -> exclusive scan in place; length lives on the device (tileOff[nTiles])
     launches += scan_exclusive(w.headScan, w.headScan, w.tileCount + b.nTiles, 0, w.seedCap, w.blockSums, nullptr, st);
@@ -1117,10 +1115,7 @@ int launch_compact_and_runs(const IndexState& ix, const BatchDesc& b, const Work
 struct ExtendArgs {
     IndexState ix;
     BatchDesc b;
-    const uint32_t* seedPos;
-    const uint32_t* seedEnc;
-    const uint8_t* seedN;
-    const uint32_t* seedContig;
+    const SeedRec* seeds;
     const uint32_t* runFirst;
     const uint32_t* runStart;
     RunRec* runs;
@@ -1139,9 +1134,12 @@ __global__ void __launch_bounds__(256) k_extend(const ExtendArgs a) {
         const bool valid = rb + grp < nRuns;
         const uint32_t r = valid ? rb + grp : nRuns - 1;
         const uint32_t j0 = a.runFirst[r], j1 = a.runFirst[r + 1];
-        const uint32_t c = a.seedContig[j0];
-        const uint32_t firstPos = a.seedPos[j0], enc0 = a.seedEnc[j0];
-        const uint32_t lastPos = a.seedPos[j1 - 1] + (a.seedN[j1 - 1] - 1u) * static_cast<uint32_t>(k1);
+        // first / last segment of the run and their neighbours: four 128-bit loads, issued together
+        const SeedRec sFirst = a.seeds[j0], sLast = a.seeds[j1 - 1];
+        const SeedRec sPrev = a.seeds[j0 ? j0 - 1 : 0], sNext = a.seeds[j1];  // seeds[] has two spare entries at the end
+        const uint32_t c = sFirst.contig;
+        const uint32_t firstPos = sFirst.pos, enc0 = sFirst.enc;
+        const uint32_t lastPos = sLast.pos + (sLast.n - 1u) * static_cast<uint32_t>(k1);
         const uint32_t rs = a.runStart[c], re = a.runStart[c + 1];
         const uint32_t N2 = a.b.contigLen[c];
         const uint8_t* T = a.b.text + a.b.contigOff[c];
@@ -1156,9 +1154,9 @@ __global__ void __launch_bounds__(256) k_extend(const ExtendArgs a) {
         bool leftCand = false;
         int64_t stopL = d < 0 ? -d : 0;  // target position below which nothing is compared (ref index >= 0)
         if (r > rs) {
-            const uint32_t nm1 = a.seedN[j0 - 1] - 1u;  // last seed of the previous segment
-            const uint32_t pp = a.seedPos[j0 - 1] + nm1 * static_cast<uint32_t>(k1);
-            const int64_t sp = static_cast<int64_t>(decode_pos(a.seedEnc[j0 - 1] + nm1 * encStep, a.ix.k1ord));
+            const uint32_t nm1 = sPrev.n - 1u;  // last seed of the previous segment
+            const uint32_t pp = sPrev.pos + nm1 * static_cast<uint32_t>(k1);
+            const int64_t sp = static_cast<int64_t>(decode_pos(sPrev.enc + nm1 * encStep, a.ix.k1ord));
             int clsP;
             window_ok(static_cast<uint64_t>(sp), K, a.ix.pos1, swStop, clsP);
             if (sp - static_cast<int64_t>(pp) == d && clsP == cls) {
@@ -1171,8 +1169,8 @@ __global__ void __launch_bounds__(256) k_extend(const ExtendArgs a) {
         if (refCap - d < stopR) stopR = refCap - d;
         bool rightCand = false;
         if (r + 1 < re) {
-            const uint32_t np = a.seedPos[j1];
-            const int64_t sn = static_cast<int64_t>(decode_pos(a.seedEnc[j1], a.ix.k1ord));
+            const uint32_t np = sNext.pos;
+            const int64_t sn = static_cast<int64_t>(decode_pos(sNext.enc, a.ix.k1ord));
             int clsN;
             window_ok(static_cast<uint64_t>(sn), K, a.ix.pos1, swStop, clsN);
             if (sn - static_cast<int64_t>(np) == d && clsN == cls && static_cast<int64_t>(np) <= stopR) {
@@ -1297,7 +1295,7 @@ __global__ void __launch_bounds__(256) k_links(RunRec* __restrict__ runs, const 
 }
 
 int launch_extend(const IndexState& ix, const BatchDesc& b, const WorkBuffers& w, cudaStream_t st) {
-    ExtendArgs a{ix, b, w.seedPos, w.seedEnc, w.seedN, w.seedContig, w.runFirst, w.runStart, w.runs, w.counters};
+    ExtendArgs a{ix, b, w.seeds, w.runFirst, w.runStart, w.runs, w.counters};
     k_extend<<<device_sm_count() * 8, 256, 0, st>>>(a);
     k_links<<<device_sm_count() * 4, 256, 0, st>>>(w.runs, w.counters);
     return 2;

@@ -31,6 +31,13 @@ struct RunRec {          // one seed run = consecutive seeds on one diagonal, sp
     uint32_t flags;      // bit0 leftLinked (aFree = that of the previous run), bit1 rightLinked
 };
 
+struct alignas(16) SeedRec {  // one seed segment (16 bytes, read and written as one 128-bit word)
+    uint32_t pos;        // first target position of the segment
+    uint32_t enc;        // table entry of its first seed
+    uint32_t n;          // seeds in the segment (spacing k1, entries ascending by k1 >> k1ord)
+    uint32_t contig;     // contig (text) of the segment
+};
+
 struct MatchRec {        // 16 bytes, device-internal
     uint64_t src;
     uint32_t dst;
@@ -79,10 +86,7 @@ struct WorkBuffers {     // device scratch of one pass
     uint4* chunkDesc;        // [nChunks] text offset lo/hi, contig-local base position, nValid
     uint16_t* seedMask;      // [nChunks*32] per-lane 16-bit seed masks
     uint32_t* scratchEnc;    // [nChunks*PROBE_CHUNK] position-indexed table entries of the seeds
-    uint32_t* seedPos;       // [seedCap] first target position of the segment
-    uint32_t* seedEnc;       // [seedCap] table entry of its first seed
-    uint8_t* seedN;          // [seedCap] seeds in the segment (spacing k1, entries ascending by k1 >> k1ord)
-    uint32_t* seedContig;    // [seedCap] contig (text) of the segment
+    SeedRec* seeds;          // [seedCap] seed segments, position-ordered per contig
     uint32_t* headScan;      // [seedCap+2] run-head flags -> scan; later the island-head flag of every run
     uint32_t* runFirst;      // [seedCap+2] first segment of every run; later matches per island -> scan
     RunRec* runs;            // [seedCap]

@@ -335,10 +335,7 @@ void B200SparseEMMatcher::ensureWork(uint64_t textBytes, uint32_t nTiles, int nC
     const uint64_t oChunkDesc = carve((static_cast<uint64_t>(nTiles) + 2) * 16);
     const uint64_t oSeedMask = carve((static_cast<uint64_t>(nTiles) + 1) * 32 * 2);
     const uint64_t oScratchEnc = carve(scratchN * 4);
-    const uint64_t oSeedPos = carve(static_cast<uint64_t>(seedCap) * 4);
-    const uint64_t oSeedEnc = carve(static_cast<uint64_t>(seedCap) * 4);
-    const uint64_t oSeedN = carve(static_cast<uint64_t>(seedCap) + 64);
-    const uint64_t oSeedContig = carve(static_cast<uint64_t>(seedCap) * 4);
+    const uint64_t oSeeds = carve((static_cast<uint64_t>(seedCap) + 2) * sizeof(SeedRec));
     const uint64_t oHeadScan = carve((static_cast<uint64_t>(seedCap) + 2) * 4);
     const uint64_t oRunFirst = carve((static_cast<uint64_t>(seedCap) + 2) * 4);
     const uint64_t oRuns = carve(static_cast<uint64_t>(seedCap) * sizeof(RunRec));
@@ -370,10 +367,7 @@ void B200SparseEMMatcher::ensureWork(uint64_t textBytes, uint32_t nTiles, int nC
     wb.chunkDesc = reinterpret_cast<uint4*>(dWork + oChunkDesc);
     wb.seedMask = reinterpret_cast<uint16_t*>(dWork + oSeedMask);
     wb.scratchEnc = reinterpret_cast<uint32_t*>(dWork + oScratchEnc);
-    wb.seedPos = reinterpret_cast<uint32_t*>(dWork + oSeedPos);
-    wb.seedEnc = reinterpret_cast<uint32_t*>(dWork + oSeedEnc);
-    wb.seedN = dWork + oSeedN;
-    wb.seedContig = reinterpret_cast<uint32_t*>(dWork + oSeedContig);
+    wb.seeds = reinterpret_cast<SeedRec*>(dWork + oSeeds);
     wb.headScan = reinterpret_cast<uint32_t*>(dWork + oHeadScan);
     wb.runFirst = reinterpret_cast<uint32_t*>(dWork + oRunFirst);
     wb.runs = reinterpret_cast<RunRec*>(dWork + oRuns);

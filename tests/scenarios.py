@@ -89,18 +89,20 @@ def repeat_rich_near(seed=41, length=400_000, n=4):
     fast path's memo (which chunks may be declared clean) against repeats on and off the sampling grid."""
     r = _rng(seed)
     base = synth_base(length, seed).copy()
-    elem = base[50_000:56_000].copy()
-    for at in (120_003, 200_010, 300_007):      # copies at different phases of the 16-grid
-        base[at:at + elem.size] = elem
+    at = lambda x: x * length // 400_000              # positions are given for the default length
+    elem = base[at(50_000):at(50_000) + 6_000].copy()
+    for p in (120_003, 200_010, 300_007):       # copies at different phases of the 16-grid
+        base[at(p):at(p) + elem.size] = elem
     unit = _ACGT[r.integers(0, 4, 48)]           # tandem repeat, period 48 = 3 x 16
-    base[250_000:250_000 + 48 * 60] = np.tile(unit, 60)
-    base[20_000:21_500] = ord("A")
-    base[330_000:331_000] = ord("N")
-    base[350_000:352_000] = np.frombuffer(bytes(base[350_000:352_000]).lower(), dtype=np.uint8)
+    base[at(250_000):at(250_000) + 48 * 60] = np.tile(unit, 60)
+    base[at(20_000):at(20_000) + 1_500] = ord("A")
+    base[at(330_000):at(330_000) + 1_000] = ord("N")
+    lo = at(350_000)
+    base[lo:lo + 2_000] = np.frombuffer(bytes(base[lo:lo + 2_000]).lower(), dtype=np.uint8)
     ops = [("load", base, True)]
     texts = [synth_mutant(base, seed * 7919 + i, 2e-4, 2e-5) for i in range(1, n)]
     texts.append(base.copy())                                    # identical copy
-    texts.append(np.concatenate([base[77:150_000], base[10:90_000]]))  # rearranged, off-grid
+    texts.append(np.concatenate([base[77:at(150_000)], base[10:at(90_000)]]))  # rearranged, off-grid
     ops.append(("batch", texts))
     ops += [("sep",), ("match", texts[0], None), ("load", texts[1], True), ("match", texts[2], None), ("sep",),
             ("match", texts[0], None), ("batch", texts[:3])]

@@ -139,3 +139,25 @@ def test_many_passes_equal_one(monkeypatch, pass_bytes):
             assert np.array_equal(a, b) and np.array_equal(a, c)
     finally:
         g.close()
+
+
+@pytest.mark.parametrize("L,sm", [(20, 16), (24, 24), (32, 16), (40, 0), (48, 16), (56, 16), (64, 0), (120, 16)])
+def test_fast_path_other_kmer_lengths(monkeypatch, L, sm):
+    """k1 = 16 with K = 16 .. 56 (K-1 tail bytes of 15 .. 55, one or two tail words per lane, 2 .. 5 pieces per
+    lane): near-identical texts with repeats, fast path forced on, against the oracle"""
+    monkeypatch.setenv("MBGC_B200_FASTPATH", "1")
+    from scenarios import repeat_rich_near
+    sc = repeat_rich_near(seed=43, length=150_000, n=3)
+    o = OracleMatcher(sc["limit"], L, 16, 1, sm)
+    g = CudaFace(sc["limit"], L, 16, 1, sm)
+    try:
+        want, sw = replay(o, sc, min_len=L)
+        got, sg = replay(g, sc, min_len=L)
+        assert sg == sw
+        for k, (a, b) in enumerate(zip(got, want)):
+            assert np.array_equal(a, b), f"op {k}: cuda {len(a)} matches, oracle {len(b)}"
+        c = g.m.counters()
+        assert c["lanes_full_probe"] < 32 * c["chunks"], c  # the fast path did run
+    finally:
+        g.close()
+        o.close()
