@@ -521,7 +521,7 @@ void B200SparseEMMatcher::growDevice(void** p, uint64_t* cap, uint64_t need, con
 // from the caller's buffer (only when that buffer is pinned: a pageable source would be staged by the driver at a
 // fraction of the speed) while the worker pool packs the others 4:1 into pinned staging memory; packed blocks are
 // copied as they finish and expanded on the device.  See hostpack.hpp for why.
-//   MBGC_B200_PACK          0 = never pack; unset / 1 = pack batches of 8 MiB and more
+//   MBGC_B200_PACK          0 = never pack; unset / 1 = pack batches of MBGC_B200_PACK_MIN_BYTES (default 2 MiB) and more
 //   MBGC_B200_RAW_PERMILLE  share of the bytes that travels raw while the CPU packs the rest (default: from the
 //                           number of packer threads, 300 with 15 of them)
 //   MBGC_B200_PACK_THREADS  worker threads (default: hardware threads / LOCAL_WORLD_SIZE - 1)
@@ -531,7 +531,9 @@ int B200SparseEMMatcher::stageTexts(const std::vector<TextView>& texts, size_t f
     uint64_t total = 0;
     for (int c = 0; c < nC; c++) total += texts[first + c].len;
     const char* envPack = std::getenv("MBGC_B200_PACK");
-    const bool pack = !(envPack && std::atoi(envPack) == 0) && total >= (8ull << 20);
+    uint64_t packMin = 2ull << 20;
+    if (const char* e = std::getenv("MBGC_B200_PACK_MIN_BYTES")) packMin = std::strtoull(e, nullptr, 10);
+    const bool pack = !(envPack && std::atoi(envPack) == 0) && total >= packMin;
     if (!pack) {
         for (int c = 0; c < nC; c++)
             if (texts[first + c].len)
