@@ -15,7 +15,7 @@ namespace mbgc_b200 {
 
 constexpr int PROBE_NPT = 16;                       // positions per lane
 constexpr int PROBE_CHUNK = 32 * PROBE_NPT;         // positions per warp-chunk (512)
-constexpr int PROBE_THREADS_FILTER = 768;           // 1 CTA per SM next to the shared-memory filter
+constexpr int PROBE_THREADS_FILTER = 1024;          // 1 CTA per SM next to the shared-memory filter
 constexpr int PROBE_THREADS_PLAIN = 512;
 constexpr uint32_t PROBE_FILTER_BYTES = 192 * 1024; // first-level filter, copied to shared memory by every CTA
 constexpr uint32_t PROBE_FILTER_BITS = PROBE_FILTER_BYTES * 8;
