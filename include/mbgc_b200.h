@@ -112,6 +112,64 @@ int mbgcg_match_batch_device(mbgcg_t* h, const void* dText, int nTexts, const ui
                              uint32_t minMatchLength, const uint64_t* lockPos, const mbgcg_match_t** out,
                              const uint64_t** counts);
 
+/* ---- stream packing, K6 -------------------------------------------------------------------------------------
+ * Replaces MBGC_Encoder::processMatches with extendMatchLeft / extendMatchRight
+ * (/root/reference/mbgccoder/MBGC_Encoder.cpp:143-308, 373-427, 310-371) and
+ * ContextAwareMismatchesCoder::mismatch2code (coders/ContextAwareMismatchesCoder.cpp:22-27): the match list of a
+ * text becomes the bytes the reference appends to targetLiterals / targetMapOffDests / targetMapOff5thByte /
+ * targetMapLenDests / targetGapDeltas / targetGapMismatchesFlags, plus the list as pass 1 leaves it and the returned
+ * unmatched count.  The caller keeps what needs encoder state: the dissimilar-contig bail-out (:202-205, decided on
+ * the unmatched count returned here), processLiteral (:128-135, disabled by default) and the statistics counters. */
+
+/* the MBGC_Params members processMatches reads (mbgccoder/MBGC_Params.h:66-97); field names as in the reference */
+typedef struct {
+    int32_t enableExtensionsWithMismatches;
+    int32_t gapDepthOffsetEncoding;       /* 0..127 here (the reference allows 128) */
+    int32_t gapDepthMismatchesEncoding;   /* 0..2 here (larger values are a developer-build option of the reference) */
+    int32_t lazyDecompressionSupport;
+    int32_t frugal64bitLenEncoding;
+    int32_t enable40bitReference;
+    int32_t mismatchesWithExclusion;
+    int32_t mmsMismatchesInitialScore;
+    int32_t mmsMismatchesScoreThreshold;
+    int32_t mmsMismatchPenalty;
+    int32_t mmsMatchBonus;
+    int32_t reserved;
+    uint64_t gapBreakingMatchMinLength;
+} mbgcg_pack_params_t;
+
+enum {
+    MBGCG_S_LITERALS = 0,  /* targetLiterals: literals, mismatch codes, MATCH_MARK (MBGC_Params.h:45) */
+    MBGCG_S_MAPOFF = 1,    /* targetMapOffDests: u32 LE posSrcText of every unpaired match */
+    MBGCG_S_MAPOFF5 = 2,   /* targetMapOff5thByte (enable40bitReference) */
+    MBGCG_S_MAPLEN = 3,    /* targetMapLenDests: frugal u16/u32/u64 (utils/helper.cpp:237-246) or plain u32 */
+    MBGCG_S_GAPDELTA = 4,  /* targetGapDeltas */
+    MBGCG_S_GAPFLAGS = 5,  /* targetGapMismatchesFlags */
+    MBGCG_S_COUNT = 6
+};
+
+typedef struct {
+    const uint8_t* stream[MBGCG_S_COUNT];      /* all texts concatenated in text order; handle-owned, valid until the next pack call */
+    const uint64_t* streamOff[MBGCG_S_COUNT];  /* [nTexts+1]: text i owns stream[s][streamOff[s][i] .. streamOff[s][i+1]) */
+    const uint64_t* unmatched;                 /* [nTexts] processMatches' return value (unmatched chars before extension) */
+    const uint64_t* kept;                      /* [nTexts] matches left after pass 1 (gap-breaking matches removed) */
+} mbgcg_pack_result_t;
+
+/* processMatches(textMatches, destStart, destLen, targetIdx, matchingLockPos) for n texts in one device pass.
+ * texts / matches are HOST pointers; matches = all lists concatenated, counts[i] of them belong to text i.
+ * matches == NULL: pack the lists of the immediately preceding mbgcg_match / mbgcg_match_batch[_device] call on this
+ * handle (same texts, single pass) -- lists and texts are still on the device, nothing is uploaded again (texts may
+ * then be NULL too).  lockPos may be NULL (all SIZE_MAX).  loadedPosArr = refExtLoadedPosArr (MBGC_Encoder.h:47), read by
+ * the lazy-decompression pairing rule (:252-261). */
+int mbgcg_pack_batch(mbgcg_t* h, const mbgcg_pack_params_t* p, int nTexts, const char* const* texts, const uint64_t* lens,
+                     const mbgcg_match_t* matches, const uint64_t* counts, const uint64_t* lockPos,
+                     const uint64_t* loadedPosArr, uint64_t nLoadedPos, mbgcg_pack_result_t* out);
+/* textMatches as pass 1 of the last pack call left them (MBGC_Encoder.cpp:197), all texts concatenated (kept[] each) */
+int mbgcg_pack_kept_matches(mbgcg_t* h, const mbgcg_match_t** out, uint64_t* n);
+/* last pack call: ms[0..3] = input transfer, kernels, stream D2H, total (CUDA events); kernel launches; fixed-point
+ * sweeps used for (removal, pairing) */
+void mbgcg_pack_timing(const mbgcg_t* h, float ms[4], uint64_t* launches, int sweeps[2]);
+
 /* ---- sliding-window locks (ref .cpp:361-400) ------------------------------------------------------------ */
 uint64_t mbgcg_acquire_lock(mbgcg_t* h);
 int mbgcg_release_lock(mbgcg_t* h, uint64_t lockValue);

@@ -15,10 +15,12 @@ struct mbgcg {
     B200SparseEMMatcher* m = nullptr;
     std::string err;
     std::vector<TextMatch> single;
+    std::vector<TextMatch> kept;
 };
 
 static_assert(sizeof(mbgcg_match_t) == sizeof(TextMatch), "TextMatch layout");
 static_assert(MBGCG_T_COUNT == MBGCG_T_COUNT_, "timing slots");
+static_assert(MBGCG_S_COUNT == mbgc_b200::PACK_STREAMS, "stream ids");
 
 static thread_local std::string g_createError;
 
@@ -120,6 +122,56 @@ int mbgcg_match_batch_device(mbgcg_t* h, const void* dText, int nTexts, const ui
         *out = reinterpret_cast<const mbgcg_match_t*>(h->m->batchMatches());
         *counts = h->m->batchCounts().data();
     });
+}
+
+int mbgcg_pack_batch(mbgcg_t* h, const mbgcg_pack_params_t* p, int nTexts, const char* const* texts, const uint64_t* lens,
+                     const mbgcg_match_t* matches, const uint64_t* counts, const uint64_t* lockPos,
+                     const uint64_t* loadedPosArr, uint64_t nLoadedPos, mbgcg_pack_result_t* out) {
+    std::memset(out, 0, sizeof(*out));
+    return guarded(h, [&] {
+        if (matches && (!texts || !counts)) throw MatcherError(MBGCG_E_PARAM, "pack_batch: match lists without texts / counts");
+        mbgc_b200::PackParams pp{};
+        pp.enableExt = p->enableExtensionsWithMismatches;
+        pp.gapDepthOffset = p->gapDepthOffsetEncoding;
+        pp.gapDepthMismatches = p->gapDepthMismatchesEncoding;
+        pp.lazy = p->lazyDecompressionSupport;
+        pp.frugalLen = p->frugal64bitLenEncoding;
+        pp.enable40bit = p->enable40bitReference;
+        pp.withExclusion = p->mismatchesWithExclusion;
+        pp.initialScore = p->mmsMismatchesInitialScore;
+        pp.scoreThreshold = p->mmsMismatchesScoreThreshold;
+        pp.mismatchPenalty = p->mmsMismatchPenalty;
+        pp.matchBonus = p->mmsMatchBonus;
+        pp.gapBreakingMinLen = p->gapBreakingMatchMinLength;
+        std::vector<TextView> tv(static_cast<size_t>(nTexts));
+        for (int i = 0; i < nTexts; i++) tv[i] = TextView{texts ? texts[i] : nullptr, lens[i]};
+        h->m->packBatch(pp, tv, reinterpret_cast<const TextMatch*>(matches), counts, lockPos, loadedPosArr, nLoadedPos);
+        for (int s = 0; s < MBGCG_S_COUNT; s++) {
+            out->stream[s] = h->m->packStream(s);
+            out->streamOff[s] = h->m->packStreamOff(s).data();
+        }
+        out->unmatched = h->m->packUnmatched().data();
+        out->kept = h->m->packKept().data();
+    });
+}
+
+int mbgcg_pack_kept_matches(mbgcg_t* h, const mbgcg_match_t** out, uint64_t* n) {
+    *out = nullptr;
+    *n = 0;
+    return guarded(h, [&] {
+        h->m->packKeptMatches(h->kept);
+        *out = reinterpret_cast<const mbgcg_match_t*>(h->kept.data());
+        *n = h->kept.size();
+    });
+}
+
+void mbgcg_pack_timing(const mbgcg_t* h, float ms[4], uint64_t* launches, int sweeps[2]) {
+    for (int i = 0; i < 4; i++) ms[i] = h->m->packMs[i];
+    if (launches) *launches = h->m->packLaunches;
+    if (sweeps) {
+        sweeps[0] = h->m->packSweeps[0];
+        sweeps[1] = h->m->packSweeps[1];
+    }
 }
 
 uint64_t mbgcg_acquire_lock(mbgcg_t* h) { return h->m->acquireWorkerMatchingLockPos(); }

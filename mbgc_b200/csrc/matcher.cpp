@@ -159,6 +159,7 @@ B200SparseEMMatcher::~B200SparseEMMatcher() {
     if (hMeta) cudaFreeHost(hMeta);
     if (hMatches) cudaFreeHost(hMatches);
     if (hCounts) cudaFreeHost(hCounts);
+    releasePack();
     for (auto& e : ev) if (e) cudaEventDestroy(e);
     if (stream) cudaStreamDestroy(stream);
     std::free(hostRef);
@@ -668,6 +669,7 @@ void B200SparseEMMatcher::matchBatch(const std::vector<TextView>& texts, const u
         throw MatcherError(MBGCG_E_PARAM, "Minimal matching length cannot be smaller than K (" +
                                               std::to_string(minMatchLength) + " < " + std::to_string(K) + ")");
     nMatchesAll = 0;
+    resident.valid = false;
     resCounts.assign(texts.size(), 0);
     for (auto& m : stageMs) m = 0;
     timingPending = false;
@@ -833,6 +835,13 @@ void B200SparseEMMatcher::matchBatch(const std::vector<TextView>& texts, const u
             lastCounters[2] += hCtr[1];
             lastCounters[3] += total;
             lastCounters[5] += 1;  // passes
+            if (first == 0 && last == texts.size()) {  // texts + lists stay on the device for a resident packBatch
+                resident.valid = true;
+                resident.bd = bd;
+                resident.nMatches = total;
+                resident.lens.resize(nC);
+                for (int c = 0; c < nC; c++) resident.lens[c] = texts[c].len;
+            }
             break;
         }
         first = last;

@@ -15,6 +15,7 @@
 
 #include "hostpack.hpp"
 #include "kernels.h"
+#include "pack.h"
 
 constexpr int MBGCG_T_COUNT_ = 12;  // = MBGCG_T_COUNT of include/mbgc_b200.h (checked in capi.cpp)
 
@@ -85,6 +86,22 @@ public:
     const TextMatch* batchMatches() const { return hMatches; }   // pinned, valid until the next match call
     uint64_t batchMatchCount() const { return nMatchesAll; }
     const std::vector<uint64_t>& batchCounts() const { return resCounts; }
+
+    // K6, MBGC_Encoder::processMatches (mbgccoder/MBGC_Encoder.cpp:143-427) for n texts at once: match lists ->
+    // the six streams of the back-end coders.  matches == nullptr: pack the lists (and texts) of the immediately
+    // preceding single-pass matchBatch call, which are still on the device.  Results: packStream*/packUnmatched/
+    // packKept below, valid until the next pack call.  packer.cpp.
+    void packBatch(const PackParams& p, const std::vector<TextView>& texts, const TextMatch* matches, const uint64_t* counts,
+                   const uint64_t* lockPos, const uint64_t* loadedPosArr, uint64_t nLoadedPos);
+    const uint8_t* packStream(int s) const { return hPackOut[s]; }                    // pinned host memory
+    const std::vector<uint64_t>& packStreamOff(int s) const { return packOff[s]; }    // [nTexts+1] per stream
+    const std::vector<uint64_t>& packUnmatched() const { return packUnmatchedChars; } // processMatches' return value
+    const std::vector<uint64_t>& packKept() const { return packKeptCounts; }          // matches left after pass 1
+    // textMatches as pass 1 leaves them (MBGC_Encoder.cpp:197), all texts of the last pack call concatenated
+    void packKeptMatches(std::vector<TextMatch>& out);
+    float packMs[4] = {0, 0, 0, 0};       // last pack call: H2D, kernels, D2H, total (CUDA events)
+    uint64_t packLaunches = 0;            // kernel launches of the last pack call
+    int packSweeps[2] = {0, 0};           // fixed-point sweeps the last pack call needed (removal, pairing)
 
     // inspection
     void copyTableLow32(uint32_t* out, uint64_t nSlots);
@@ -162,6 +179,28 @@ private:
     uint64_t matchGuess = 0;             // matches expected from the next pass (copied back before their count is known)
     uint32_t* hCounts = nullptr; uint64_t hCountsCap = 0;    // pinned
     std::vector<uint64_t> resCounts;
+
+    // what the last matchBatch call left on the device (single-pass calls only): input of a resident packBatch
+    struct Resident {
+        bool valid = false;
+        BatchDesc bd{};
+        uint32_t nMatches = 0;
+        std::vector<uint64_t> lens;
+    } resident;
+
+    // K6 (packer.cpp)
+    void releasePack();
+    cudaEvent_t pkEv[4] = {};
+    uint8_t* dPackWork = nullptr; uint64_t dPackWorkCap = 0;
+    uint8_t* dPackIn = nullptr; uint64_t dPackInCap = 0;       // matches + meta + loaded positions of a host call
+    uint8_t* hPackIn = nullptr; uint64_t hPackInCap = 0;       // pinned staging of the same
+    uint8_t* hPackSum = nullptr; uint64_t hPackSumCap = 0;     // pinned: flags, totals, offsets, sums
+    uint8_t* hPackOut[PACK_STREAMS] = {}; uint64_t hPackOutCap[PACK_STREAMS] = {};
+    std::vector<uint64_t> packOff[PACK_STREAMS];
+    std::vector<uint64_t> packUnmatchedChars, packKeptCounts;
+    struct KeptSlice { const KeptRec* dev; uint32_t n; };  // kept list of the last pass (device) for packKeptMatches
+    std::vector<TextMatch> packKeptHost;                        // earlier passes of a multi-pass call
+    KeptSlice packKeptLast{nullptr, 0};
 };
 
 }  // namespace mbgc_b200

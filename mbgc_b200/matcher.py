@@ -31,6 +31,30 @@ class _State(C.Structure):
                 ("samplingPos", C.c_uint64), ("hashSize", C.c_uint32), ("K", C.c_int32)]
 
 
+STREAM_NAMES = ("literals", "mapOff", "mapOff5", "mapLen", "gapDelta", "gapFlags")  # MBGCG_S_*
+
+
+class PackParams(C.Structure):
+    """mbgcg_pack_params_t: the MBGC_Params members MBGC_Encoder::processMatches reads
+    (/root/reference/mbgccoder/MBGC_Params.h:66-97; presets :886-922)."""
+    _fields_ = [(n, C.c_int32) for n in (
+        "enableExtensionsWithMismatches", "gapDepthOffsetEncoding", "gapDepthMismatchesEncoding",
+        "lazyDecompressionSupport", "frugal64bitLenEncoding", "enable40bitReference", "mismatchesWithExclusion",
+        "mmsMismatchesInitialScore", "mmsMismatchesScoreThreshold", "mmsMismatchPenalty", "mmsMatchBonus",
+        "reserved")] + [("gapBreakingMatchMinLength", C.c_uint64)]
+
+    @staticmethod
+    def for_mode(mode, enable40bit=False, lazy=True):
+        """defaults of the reference for `mbgc c -m mode` (mode 0 writes plain u32 lengths, MBGC_Params.h:900)"""
+        return PackParams(1, 64, 2, 1 if lazy else 0, 0 if mode == 0 else 1, 1 if enable40bit else 0, 1,
+                          125, 500, 50, 50, 0, 256)
+
+
+class _PackResult(C.Structure):
+    _fields_ = [("stream", C.c_void_p * 6), ("streamOff", C.c_void_p * 6), ("unmatched", C.c_void_p),
+                ("kept", C.c_void_p)]
+
+
 def lib_path():
     return os.path.join(_HERE, "libmbgc_b200.so")
 
@@ -65,6 +89,12 @@ def load_library():
     L.mbgcg_match_batch.argtypes = [vp, C.c_int, C.POINTER(vp), u64p, C.c_uint32, u64p, C.POINTER(vp), C.POINTER(vp)]
     L.mbgcg_match_batch_device.restype = C.c_int
     L.mbgcg_match_batch_device.argtypes = [vp, vp, C.c_int, u64p, u64p, C.c_uint32, u64p, C.POINTER(vp), C.POINTER(vp)]
+    L.mbgcg_pack_batch.restype = C.c_int
+    L.mbgcg_pack_batch.argtypes = [vp, C.POINTER(PackParams), C.c_int, C.POINTER(vp), u64p, vp, u64p, u64p, u64p,
+                                   C.c_uint64, C.POINTER(_PackResult)]
+    L.mbgcg_pack_kept_matches.restype = C.c_int
+    L.mbgcg_pack_kept_matches.argtypes = [vp, C.POINTER(vp), u64p]
+    L.mbgcg_pack_timing.argtypes = [vp, C.POINTER(C.c_float), u64p, C.POINTER(C.c_int)]
     L.mbgcg_acquire_lock.restype = C.c_uint64
     L.mbgcg_acquire_lock.argtypes = [vp]
     L.mbgcg_release_lock.restype = C.c_int
@@ -173,6 +203,63 @@ class Matcher:
         self._check(self.lib.mbgcg_match_batch_device(self.h, dTextPtr, n, offs, ls, minMatchLength, locks,
                                                       C.byref(out), C.byref(counts)))
         return self._split(out, counts, n, copy)
+
+    def packBatch(self, params, texts, matches=None, lockPos=None, loadedPosArr=(), lens=None):
+        """MBGC_Encoder::processMatches for a list of texts (mbgcg_pack_batch).  matches: list of (n_i, 3) uint64
+        arrays (posSrcText, length, posDestText), or None to pack the lists of the immediately preceding match call
+        (still on the device; texts may then be None with lens given).  Returns a dict: per stream name a list of
+        bytes per text, plus "unmatched" and "kept" (arrays per text)."""
+        if texts is not None:
+            arrs = [_as_u8(t) for t in texts]
+            n = len(arrs)
+            ptrs = (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
+            ls = (C.c_uint64 * n)(*[a.size for a in arrs])
+        else:
+            n = len(lens)
+            ptrs = None
+            ls = (C.c_uint64 * n)(*lens)
+        if matches is not None:
+            cnt = (C.c_uint64 * n)(*[len(m) for m in matches])
+            tot = sum(len(m) for m in matches)
+            flat = np.zeros((max(tot, 1), 4), dtype=np.uint64)
+            at = 0
+            for m in matches:
+                if len(m):
+                    flat[at:at + len(m), :3] = np.asarray(m, dtype=np.uint64).reshape(-1, 3)
+                    at += len(m)
+            mptr = flat.ctypes.data
+        else:
+            cnt, mptr = None, None
+        locks = (C.c_uint64 * n)(*lockPos) if lockPos is not None else None
+        nl = len(loadedPosArr)
+        loaded = (C.c_uint64 * max(nl, 1))(*loadedPosArr)
+        res = _PackResult()
+        self._check(self.lib.mbgcg_pack_batch(self.h, C.byref(params), n, ptrs, ls, mptr, cnt, locks, loaded, nl,
+                                              C.byref(res)))
+        out = {}
+        for s, name in enumerate(STREAM_NAMES):
+            off = np.ctypeslib.as_array(C.cast(res.streamOff[s], u64p), shape=(n + 1,)).copy() if n else np.zeros(1, np.uint64)
+            total = int(off[-1])
+            data = bytes(np.ctypeslib.as_array(C.cast(res.stream[s], u8p), shape=(total,))) if total else b""
+            out[name] = [data[int(off[i]):int(off[i + 1])] for i in range(n)]
+        out["unmatched"] = np.ctypeslib.as_array(C.cast(res.unmatched, u64p), shape=(n,)).copy() if n else np.zeros(0, np.uint64)
+        out["kept"] = np.ctypeslib.as_array(C.cast(res.kept, u64p), shape=(n,)).copy() if n else np.zeros(0, np.uint64)
+        return out
+
+    def packKeptMatches(self):
+        """textMatches as pass 1 of the last packBatch left them (all texts concatenated), shape (n, 3)"""
+        out = C.c_void_p()
+        n = C.c_uint64()
+        self._check(self.lib.mbgcg_pack_kept_matches(self.h, C.byref(out), C.byref(n)))
+        return self._matches(out, n.value)
+
+    def packTiming(self):
+        ms = (C.c_float * 4)()
+        launches = C.c_uint64()
+        sweeps = (C.c_int * 2)()
+        self.lib.mbgcg_pack_timing(self.h, ms, C.byref(launches), sweeps)
+        return {"h2d": ms[0], "kernels": ms[1], "d2h": ms[2], "total": ms[3], "launches": launches.value,
+                "sweeps": (sweeps[0], sweeps[1])}
 
     def acquireWorkerMatchingLockPos(self):
         return self.lib.mbgcg_acquire_lock(self.h)
