@@ -177,6 +177,46 @@ def cpu_match_stage(base, targets, limit, skip_margin, threads):
     return dt, "port", int(total), 1
 
 
+def cpu_pack_stage(base, targets, lists, limit, skip_margin, mode):
+    """MBGC_Encoder::processMatches on one host core through the oracle port (oracle/mbgc_oracle.c:
+    mbo_process_matches; the reference's own function is a private member of its encoder and not reachable from
+    the matcher driver).  Returns (seconds, stream bytes)."""
+    subprocess.run(["make", "-s", "oracle"], cwd=os.path.join(ROOT, "oracle"), check=True)
+    L = C.CDLL(os.path.join(ROOT, "oracle", "libmbgc_oracle.so"))
+    L.mbo_create.restype = C.c_void_p
+    L.mbo_create.argtypes = [C.c_uint64, C.c_uint32, C.c_int, C.c_int, C.c_int]
+    L.mbo_disable_sliding_window.argtypes = [C.c_void_p]
+    L.mbo_load_ref.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_uint8]
+    L.mbo_loading_position.restype = C.c_uint64
+    L.mbo_loading_position.argtypes = [C.c_void_p]
+    L.mbo_destroy.argtypes = [C.c_void_p]
+    L.mbo_streams_create.restype = C.c_void_p
+    L.mbo_streams_destroy.argtypes = [C.c_void_p]
+    L.mbo_stream_size.restype = C.c_uint64
+    L.mbo_stream_size.argtypes = [C.c_void_p, C.c_int]
+    L.mbo_process_matches.restype = C.c_uint64
+    L.mbo_process_matches.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p,
+                                      C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64), C.c_uint64]
+    h = L.mbo_create(limit, 32, 16, 1, skip_margin)
+    L.mbo_disable_sliding_window(h)
+    L.mbo_load_ref(h, base.ctypes.data, base.size, 1, 1, 0)
+    # mbo_pack_params_t (oracle/mbgc_oracle.h): 14 ints, defaults of MBGC_Params.h:66-97
+    pp = (C.c_int * 14)(1, 256, 64, 2, 1, 0 if mode == 0 else 1, 0, 1, 125, 500, 50, 50, 32, 128)
+    loaded = (C.c_uint64 * 1)(L.mbo_loading_position(h))
+    st = L.mbo_streams_create()
+    copies = [np.ascontiguousarray(m, dtype=np.uint64).copy() for m in lists]  # the call edits its list in place
+    t0 = time.perf_counter()
+    for t, m in zip(targets, copies):
+        n = C.c_uint64(len(m))
+        L.mbo_process_matches(st, pp, h, m.ctypes.data if len(m) else None, C.byref(n), t.ctypes.data, t.size,
+                              2**64 - 1, loaded, 1)
+    dt = time.perf_counter() - t0
+    nbytes = sum(L.mbo_stream_size(st, i) for i in range(6))
+    L.mbo_streams_destroy(st)
+    L.mbo_destroy(h)
+    return dt, int(nbytes)
+
+
 def workload_name(args):
     return (f"synthetic {args.genomes}-genome E. coli-like collection per GPU ({args.length / 1e6:g} Mbp base + "
             f"SNP/indel mutants, tier {args.tier}), mode {args.mode} matcher parameters")
@@ -304,8 +344,38 @@ def measure_tier(args, tier, rank, world, dist, local):
     host_ptrs = [p.numpy() for p in pinned]
     ms_e2e, stage_e2e, _, res2 = timed(lambda: m.matchBatch(host_ptrs, 32, copy=False), steps, warmup)
     assert n_matches == int(sum(len(r) for r in res2)), "device-resident and host-buffer passes disagree"
+    # K6: match stage + stream packing with everything resident (the lists never leave the device between the two)
+    from mbgc_b200.matcher import PackParams
+    pd = PackParams.for_mode(args.mode)
+    loaded = [m.getLoadingPosition()]
+    pack_tm = {}
+
+    def match_and_pack():
+        m.matchBatchDevice(dbuf.data_ptr(), offs, lens, 32, copy=False)
+        return m.packBatch(pd, None, None, loadedPosArr=loaded, lens=lens, raw=True)
+
+    psteps = max(2, steps // 2)
+    for _ in range(2):
+        match_and_pack()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(psteps):
+        pres = match_and_pack()
+        for k, v in m.packTiming().items():
+            if k != "sweeps":
+                pack_tm[k] = pack_tm.get(k, 0.0) + v / psteps
+    e1.record(stream)
+    barrier()
+    ms_mp = max_over_ranks(e0.elapsed_time(e1), "cuda") / psteps
+    pack = {"match_plus_pack_ms_per_step": ms_mp, "pack_ms": pack_tm, "sweeps": list(m.packTiming()["sweeps"]),
+            "stream_bytes": pres["stream_bytes"],
+            "kept_matches": int(pres["kept"].sum()), "unmatched_chars": int(pres["unmatched"].sum())}
+    ks = max(1, min(16, n))
+    lists_sample = m.matchBatchDevice(dbuf.data_ptr(), offs[:ks], lens[:ks], 32)  # copies, for the CPU pack baseline
     state = m.state()
-    out = dict(base=base, targets=targets, limit=limit, sm=sm, n=n, lens=lens, fbytes=fbytes, index_s=index_s,
+    out = dict(base=base, targets=targets, limit=limit, sm=sm, n=n, lens=lens, fbytes=fbytes, index_s=index_s, pack=pack,
+               lists_sample=lists_sample,
                ms_dev=ms_dev, stage_dev=stage_dev, launches=launches, n_matches=n_matches, counters=counters,
                ms_e2e=ms_e2e, stage_e2e=stage_e2e, table_slots=state["hashSize"], ref_bytes=int(state["pos1"]))
     m.close()
@@ -377,6 +447,21 @@ def run_b200(args, rank, world):
         "gpu_launches": int(r["launches"]),
         "clocks": sampler.summary(),
     }
+    def pack_report(t, world_):
+        p = dict(t["pack"])
+        p["what"] = ("MBGC_Encoder::processMatches on the device (K6, pack.cu) right after the match stage, lists and "
+                     "texts resident; the six streams copied to the host inside the timed region")
+        p["match_plus_pack_value"] = t["fbytes"] * world_ / (p["match_plus_pack_ms_per_step"] / 1e3) / 1e9
+        p["unit"] = "GB/s"
+        return p
+
+    line["pack"] = pack_report(r, world)
+    if rank == 0 and world == 1 and not args.no_cpu and r["lists_sample"]:
+        k = len(r["lists_sample"])
+        dt, nb = cpu_pack_stage(r["base"], r["targets"][:k], r["lists_sample"], r["limit"], r["sm"], args.mode)
+        sb = sum(fasta_bytes(t.size, HEADER_LEN) for t in r["targets"][:k])
+        line["pack"]["cpu_baseline"] = {"value": sb / dt / 1e9, "unit": "GB/s", "cores": 1, "kind": "port",
+                                        "sample": f"{k} genomes, mbo_process_matches, {dt * 1e3:.1f} ms, {nb} stream bytes"}
     if rank == 0 and world == 1 and not args.no_cpu:
         sample = r["targets"][:max(1, min(args.cpu_sample, n))]
         sbytes = sum(fasta_bytes(t.size, HEADER_LEN) for t in sample)
@@ -404,7 +489,14 @@ def run_b200(args, rank, world):
             "ms_per_step": o["ms_dev"] / oargs.steps, "matches_per_gpu": o["n_matches"],
             "chunks": o["counters"]["chunks"], "lanes_full_probe": o["counters"]["lanes_full_probe"],
             "stage_frac": ALG_BYTES_PER_POSITION * o["counters"]["positions"] / (okern / 1e3) / 1e9 / peak,
-            "stage_ms": o["stage_dev"]}
+            "stage_ms": o["stage_dev"], "pack": pack_report(o, world)}
+        if rank == 0 and world == 1 and not args.no_cpu and o["lists_sample"]:
+            k = min(4, len(o["lists_sample"]))
+            dt, nb = cpu_pack_stage(o["base"], o["targets"][:k], o["lists_sample"][:k], o["limit"], o["sm"], args.mode)
+            sb = sum(fasta_bytes(t.size, HEADER_LEN) for t in o["targets"][:k])
+            line["other_tier"]["pack"]["cpu_baseline"] = {
+                "value": sb / dt / 1e9, "unit": "GB/s", "cores": 1, "kind": "port",
+                "sample": f"{k} genomes, mbo_process_matches, {dt * 1e3:.1f} ms, {nb} stream bytes"}
         if rank == 0 and world == 1 and not args.no_cpu:
             sample = o["targets"][:max(1, min(args.cpu_sample_other, o["n"]))]
             sbytes = sum(fasta_bytes(t.size, HEADER_LEN) for t in sample)

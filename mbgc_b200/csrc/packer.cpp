@@ -104,6 +104,11 @@ void B200SparseEMMatcher::packBatch(const PackParams& p, const std::vector<TextV
             b.matches = wb.matchesDense;
             b.matchOff = wb.matchOff;
             for (int c = 0; c < nC; c++) textBytes += texts[first + c].len;
+            if (lockPos) {  // the caller's lock positions win over those of the match call
+                const uint64_t oLock = place(nC * 8ull);
+                std::memcpy(hPackIn + oLock, lockPos, nC * 8ull);
+                b.contigLock = reinterpret_cast<const uint64_t*>(dPackIn + oLock);
+            }
         } else {
             resident.valid = false;  // the device text buffer is about to be overwritten
             const uint64_t oM = place(static_cast<uint64_t>(nM) * sizeof(TextMatch));

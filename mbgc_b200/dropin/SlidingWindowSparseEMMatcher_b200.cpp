@@ -25,8 +25,12 @@
 #include <mutex>
 
 #include "mbgc_b200.h"
+#include "dropin_shared.h"
 
 namespace {
+
+// the text and list of the most recent matchTexts call (under g_lock): the packer may still find both on the device
+mbgc_b200_dropin::LastMatch g_lastMatch{nullptr, nullptr, 0, 0};
 
 // The reference's parallel mode enters matchTexts from several OpenMP threads while another one runs loadRef
 // (SURVEY.md 8b "Threading").  A handle is not thread-safe; serialising is a legal schedule of that mode.
@@ -199,7 +203,40 @@ void SlidingWindowSparseEMMatcher::matchTexts(vector<TextMatch>& resMatches, con
     resMatches.reserve(n);
     for (uint64_t i = 0; i < n; i++)
         resMatches.push_back(TextMatch(out[i].posSrcText, out[i].length, out[i].posDestText));
+    g_lastMatch = mbgc_b200_dropin::LastMatch{this, destText, destLen, n};
 }
+
+// ---- hooks for the other drop-in translation unit (MBGC_Encoder_processMatches_b200.cpp) ----------------------
+namespace mbgc_b200_dropin {
+
+// protected members of the reference class, reached through pointers to members named in a derived class
+struct Access : SlidingWindowSparseEMMatcher {
+    static uint64_t* SlidingWindowSparseEMMatcher::* ht() { return &Access::ht64bit; }
+    static void push(SlidingWindowSparseEMMatcher* m, mbgcg_t* h) {
+        mbgcg_state_t st;
+        mbgcg_get_state(h, &st);
+        st.pos1 = m->*(&Access::pos1);
+        st.reachedRefLengthCount = m->*(&Access::reachedRefLengthCount);
+        st.circularBuffer = m->*(&Access::circularBuffer) ? 1 : 0;
+        st.swSize = m->*(&Access::swSize);
+        st.swEnd = m->*(&Access::swEnd);
+        st.samplingPos = m->*(&Access::samplingPos);
+        mbgcg_set_state(h, &st);
+    }
+};
+
+std::mutex& handle_lock() { return g_lock; }
+
+mbgcg_t* synced_handle(SlidingWindowSparseEMMatcher* m) {
+    mbgcg_t* h = handle_of(m->*Access::ht());
+    Access::push(m, h);
+    return h;
+}
+
+LastMatch last_match() { return g_lastMatch; }
+void forget_last_match() { g_lastMatch = LastMatch{nullptr, nullptr, 0, 0}; }
+
+}  // namespace mbgc_b200_dropin
 
 // ref .cpp:470-475
 void SlidingWindowSparseEMMatcher::matchTexts(vector<TextMatch>& resMatches, const string& destText, bool destIsRef,

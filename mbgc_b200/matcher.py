@@ -204,11 +204,12 @@ class Matcher:
                                                       C.byref(out), C.byref(counts)))
         return self._split(out, counts, n, copy)
 
-    def packBatch(self, params, texts, matches=None, lockPos=None, loadedPosArr=(), lens=None):
+    def packBatch(self, params, texts, matches=None, lockPos=None, loadedPosArr=(), lens=None, raw=False):
         """MBGC_Encoder::processMatches for a list of texts (mbgcg_pack_batch).  matches: list of (n_i, 3) uint64
         arrays (posSrcText, length, posDestText), or None to pack the lists of the immediately preceding match call
         (still on the device; texts may then be None with lens given).  Returns a dict: per stream name a list of
-        bytes per text, plus "unmatched" and "kept" (arrays per text)."""
+        bytes per text, plus "unmatched" and "kept" (arrays per text).  raw=True skips the per-text slicing and
+        returns {"stream_bytes": {name: total}, "unmatched", "kept"} (the streams stay in the library's pinned buffers)."""
         if texts is not None:
             arrs = [_as_u8(t) for t in texts]
             n = len(arrs)
@@ -237,7 +238,10 @@ class Matcher:
         self._check(self.lib.mbgcg_pack_batch(self.h, C.byref(params), n, ptrs, ls, mptr, cnt, locks, loaded, nl,
                                               C.byref(res)))
         out = {}
-        for s, name in enumerate(STREAM_NAMES):
+        if raw:
+            out["stream_bytes"] = {name: int(C.cast(res.streamOff[s], u64p)[n]) if n else 0
+                                   for s, name in enumerate(STREAM_NAMES)}
+        for s, name in enumerate(STREAM_NAMES if not raw else ()):
             off = np.ctypeslib.as_array(C.cast(res.streamOff[s], u64p), shape=(n + 1,)).copy() if n else np.zeros(1, np.uint64)
             total = int(off[-1])
             data = bytes(np.ctypeslib.as_array(C.cast(res.stream[s], u8p), shape=(total,))) if total else b""
