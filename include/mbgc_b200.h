@@ -100,7 +100,10 @@ int mbgcg_match(mbgcg_t* h, const char* text, uint64_t len, uint32_t minMatchLen
 
 /* n independent matchTexts calls against the SAME frozen matcher state, in one device pass (the unit the
  * multi-GPU sharding and the speculative sequential schedule work in).  lockPos may be NULL (no locks).
- * out: all lists concatenated in text order; counts[i] = matches of text i. */
+ * out: all lists concatenated in text order; counts[i] = matches of text i.
+ * out == NULL (here and in mbgcg_match_batch_device): the lists stay on the device -- only the counts come back --
+ * for an mbgcg_pack_batch(matches = NULL) call right after; a caller that only wants the packed streams never pays
+ * the 32 bytes per match of the device->host copy. */
 int mbgcg_match_batch(mbgcg_t* h, int nTexts, const char* const* texts, const uint64_t* lens, uint32_t minMatchLength,
                       const uint64_t* lockPos, const mbgcg_match_t** out, const uint64_t** counts);
 

@@ -96,13 +96,20 @@ int mbgcg_match(mbgcg_t* h, const char* text, uint64_t len, uint32_t minMatchLen
 
 int mbgcg_match_batch(mbgcg_t* h, int nTexts, const char* const* texts, const uint64_t* lens, uint32_t minMatchLength,
                       const uint64_t* lockPos, const mbgcg_match_t** out, const uint64_t** counts) {
-    *out = nullptr;
+    if (out) *out = nullptr;
     *counts = nullptr;
     return guarded(h, [&] {
         std::vector<TextView> tv(static_cast<size_t>(nTexts));
         for (int i = 0; i < nTexts; i++) tv[i] = TextView{texts[i], lens[i]};
-        h->m->matchBatch(tv, lockPos, minMatchLength, false, nullptr, nullptr);
-        *out = reinterpret_cast<const mbgcg_match_t*>(h->m->batchMatches());
+        h->m->listsStayOnDevice = out == nullptr;
+        try {
+            h->m->matchBatch(tv, lockPos, minMatchLength, false, nullptr, nullptr);
+        } catch (...) {
+            h->m->listsStayOnDevice = false;
+            throw;
+        }
+        h->m->listsStayOnDevice = false;
+        if (out) *out = reinterpret_cast<const mbgcg_match_t*>(h->m->batchMatches());
         *counts = h->m->batchCounts().data();
     });
 }
@@ -110,7 +117,7 @@ int mbgcg_match_batch(mbgcg_t* h, int nTexts, const char* const* texts, const ui
 int mbgcg_match_batch_device(mbgcg_t* h, const void* dText, int nTexts, const uint64_t* offsets, const uint64_t* lens,
                              uint32_t minMatchLength, const uint64_t* lockPos, const mbgcg_match_t** out,
                              const uint64_t** counts) {
-    *out = nullptr;
+    if (out) *out = nullptr;
     *counts = nullptr;
     return guarded(h, [&] {
         std::vector<TextView> tv(static_cast<size_t>(nTexts));
@@ -118,8 +125,15 @@ int mbgcg_match_batch_device(mbgcg_t* h, const void* dText, int nTexts, const ui
             if (offsets[i] % 16) throw MatcherError(MBGCG_E_PARAM, "device text offsets must be multiples of 16");
             tv[i] = TextView{nullptr, lens[i]};
         }
-        h->m->matchBatch(tv, lockPos, minMatchLength, true, dText, offsets);
-        *out = reinterpret_cast<const mbgcg_match_t*>(h->m->batchMatches());
+        h->m->listsStayOnDevice = out == nullptr;
+        try {
+            h->m->matchBatch(tv, lockPos, minMatchLength, true, dText, offsets);
+        } catch (...) {
+            h->m->listsStayOnDevice = false;
+            throw;
+        }
+        h->m->listsStayOnDevice = false;
+        if (out) *out = reinterpret_cast<const mbgcg_match_t*>(h->m->batchMatches());
         *counts = h->m->batchCounts().data();
     });
 }

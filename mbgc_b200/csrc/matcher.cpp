@@ -785,6 +785,8 @@ void B200SparseEMMatcher::matchBatch(const std::vector<TextView>& texts, const u
             // the counts and a second copy fetches the rest if the guess was short -- one sync instead of two
             uint64_t guess = std::min<uint64_t>(matchGuess, hMatchesCap > nMatchesAll ? hMatchesCap - nMatchesAll : 0);
             guess = std::min<uint64_t>(guess, seedCap);
+            // lists wanted on the device only (a packBatch follows): fetch just a prefix, for the fast-path policy below
+            if (listsStayOnDevice) guess = std::min<uint64_t>(guess, 4096);
             if (guess)
                 check(cudaMemcpyAsync(hMatches + nMatchesAll, wb.matchesDense, guess * sizeof(TextMatch),
                                       cudaMemcpyDeviceToHost, stream), "D2H(matches, guessed)");
@@ -796,7 +798,8 @@ void B200SparseEMMatcher::matchBatch(const std::vector<TextView>& texts, const u
                 continue;
             }
             const uint32_t total = hOffs[nC];
-            matchGuess = static_cast<uint64_t>(total) + total / 64 + 1024;
+            if (!listsStayOnDevice) matchGuess = static_cast<uint64_t>(total) + total / 64 + 1024;
+            const uint32_t fetched = listsStayOnDevice ? static_cast<uint32_t>(std::min<uint64_t>(guess, total)) : total;
             if (nMatchesAll + total > hMatchesCap) {  // grow the pinned result buffer, keeping earlier passes
                 const uint64_t cap = (nMatchesAll + total) + (nMatchesAll + total) / 2 + 4096;
                 TextMatch* grown = nullptr;
@@ -807,7 +810,7 @@ void B200SparseEMMatcher::matchBatch(const std::vector<TextView>& texts, const u
                 hMatchesCap = cap;
             }
             TextMatch* passMatches = hMatches + nMatchesAll;
-            if (total > guess) {  // the gather kernel already wrote the host layout (TextMatch): no conversion on the host
+            if (total > guess && !listsStayOnDevice) {  // the gather kernel already wrote the host layout (TextMatch): no conversion on the host
                 check(cudaMemcpyAsync(passMatches + guess, wb.matchesDense + guess,
                                       (static_cast<uint64_t>(total) - guess) * sizeof(TextMatch), cudaMemcpyDeviceToHost,
                                       stream), "D2H(matches)");
@@ -823,10 +826,12 @@ void B200SparseEMMatcher::matchBatch(const std::vector<TextView>& texts, const u
                 cleanEstimate = 1.0 - static_cast<double>(hCtr[7]) / (32.0 * tiles);
             } else if (positions) {
                 uint64_t covered = 0;
-                const uint32_t stride = total / 4096 + 1;  // a sample is enough for the policy
-                for (uint32_t k = 0; k < total; k += stride)
+                const uint32_t stride = fetched / 4096 + 1;  // a sample is enough for the policy
+                for (uint32_t k = 0; k < fetched; k += stride)
                     if (passMatches[k].length >= 1024) covered += passMatches[k].length;
-                cleanEstimate = static_cast<double>(covered) * stride / static_cast<double>(positions);
+                // (with the lists left on the device only a prefix was fetched: scale it to the whole list)
+                const double scale = fetched ? static_cast<double>(total) / fetched : 0.0;
+                cleanEstimate = static_cast<double>(covered) * stride * scale / static_cast<double>(positions);
             }
             lastCounters[6] += tiles;
             lastCounters[7] += useFast ? hCtr[7] : static_cast<uint64_t>(tiles) * 32;

@@ -49,14 +49,15 @@ __device__ __forceinline__ uint32_t warp_incl_scan_u32(uint32_t v, int lane) {
     return v;
 }
 
-// exclusive scan over the block (PK_THREADS threads); *total = block sum
+// exclusive scan over the block (THREADS threads, at most 1024); *total = block sum
+template <int THREADS = PK_THREADS>
 __device__ __forceinline__ uint32_t block_excl_scan_u32(uint32_t v, uint32_t* total, uint32_t* sWarp) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t inc = warp_incl_scan_u32(v, lane);
     if (lane == 31) sWarp[warp] = inc;
     __syncthreads();
     if (warp == 0) {
-        const uint32_t w = lane < (PK_THREADS >> 5) ? sWarp[lane] : 0;
+        const uint32_t w = lane < (THREADS >> 5) ? sWarp[lane] : 0;
         const uint32_t wi = warp_incl_scan_u32(w, lane);
         sWarp[lane] = wi - w;
         if (lane == 31) sWarp[32] = wi;
@@ -142,28 +143,31 @@ __global__ void __launch_bounds__(PK_THREADS) k_pk_kept_tot(uint32_t nM, const u
     if (threadIdx.x == 0) blockTot[blockIdx.x] = total;
 }
 
-// exclusive scan of per-block totals, COLS interleaved columns, one CTA; totals land at row nBlocks
+// exclusive scan of per-block totals, COLS interleaved columns, one CTA of 1024 threads per column (4 values per
+// thread and round); totals land at row nBlocks
 template <int COLS>
-__global__ void __launch_bounds__(PK_THREADS) k_pk_partials(uint32_t* __restrict__ blockTot, uint32_t nBlocks) {
+__global__ void __launch_bounds__(1024) k_pk_partials(uint32_t* __restrict__ blockTot, uint32_t nBlocks) {
     __shared__ uint32_t sWarp[33];
-    uint32_t carry[COLS];
+    const int k = blockIdx.x;
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < nBlocks; base += 4096) {
+        const uint32_t i0 = base + threadIdx.x * 4;
+        uint32_t v[4], sum = 0;
 #pragma unroll
-    for (int k = 0; k < COLS; k++) carry[k] = 0;
-    for (uint32_t base = 0; base < nBlocks; base += PK_THREADS) {
-        const uint32_t i = base + threadIdx.x;
-#pragma unroll
-        for (int k = 0; k < COLS; k++) {
-            const uint32_t v = i < nBlocks ? blockTot[static_cast<uint64_t>(i) * COLS + k] : 0;
-            uint32_t total;
-            const uint32_t ex = block_excl_scan_u32(v, &total, sWarp);
-            if (i < nBlocks) blockTot[static_cast<uint64_t>(i) * COLS + k] = ex + carry[k];
-            carry[k] += total;
+        for (int q = 0; q < 4; q++) {
+            v[q] = i0 + q < nBlocks ? blockTot[static_cast<uint64_t>(i0 + q) * COLS + k] : 0;
+            sum += v[q];
         }
-    }
-    if (threadIdx.x == 0) {
+        uint32_t total;
+        uint32_t ex = block_excl_scan_u32<1024>(sum, &total, sWarp) + carry;
 #pragma unroll
-        for (int k = 0; k < COLS; k++) blockTot[static_cast<uint64_t>(nBlocks) * COLS + k] = carry[k];
+        for (int q = 0; q < 4; q++) {
+            if (i0 + q < nBlocks) blockTot[static_cast<uint64_t>(i0 + q) * COLS + k] = ex;
+            ex += v[q];
+        }
+        carry += total;
     }
+    if (threadIdx.x == 0) blockTot[static_cast<uint64_t>(nBlocks) * COLS + k] = carry;
 }
 
 __global__ void __launch_bounds__(PK_THREADS) k_pk_compact(PackState s, PackBatch b, PackWork w,
@@ -195,6 +199,7 @@ __global__ void __launch_bounds__(PK_THREADS) k_pk_compact(PackState s, PackBatc
         }
         w.kept[idx] = r;
         w.kContig[idx] = c;
+        w.kDiag[idx] = static_cast<uint32_t>(r.src) - r.dst;
         w.claim[idx] = 0;
         w.delta[idx] = 0;
         len = r.len;
@@ -269,29 +274,33 @@ __global__ void __launch_bounds__(PK_THREADS) k_pk_claim_sweep(PackParams p, Pac
         const uint32_t literalsLeft = (j + 1 < n ? w.kept[m + 1].dst : b.contigLen[c]) - end;
         const bool special = !p.lazy && !active && literalsLeft == 0;  // :247
         const uint64_t diag = me.src - me.dst;
+        const uint32_t diag32 = static_cast<uint32_t>(diag);
         const int side = me.src > lock ? 1 : (me.src < lock ? -1 : 0);  // TextMatchers.h:46-50
-        int reduce = 0;
-        for (int g = 1; g <= gCnt; g++) {
-            const uint32_t k = m + static_cast<uint32_t>(g);
-            if (w.claimedBy[k] < m || (special && g == 1)) {
-                reduce++;
-                continue;
-            }
-            const KeptRec kr = w.kept[k];
-            if (kr.src - kr.dst != diag || side == 0) continue;
-            if ((kr.src > lock ? 1 : (kr.src < lock ? -1 : 0)) != side) continue;
-            if (p.lazy) {  // :252-261
-                if (!haveNl) {
-                    const uint32_t cb = w.claimedBy[m];
-                    myNl = cb != PK_NONE ? w.nl[cb] : next_region_loading_pos(s, me.src);
-                    haveNl = true;
+        // Only a candidate on the same diagonal can end the scan, so the scan itself reads 4 bytes per candidate;
+        // the claimed / skipped ones before the hit (`reduce`, :247-250) are counted once the hit is known.
+        if (side != 0)
+            for (int g = 1; g <= gCnt; g++) {
+                const uint32_t k = m + static_cast<uint32_t>(g);
+                if (w.kDiag[k] != diag32) continue;
+                if (w.claimedBy[k] < m || (special && g == 1)) continue;
+                const KeptRec kr = w.kept[k];
+                if (kr.src - kr.dst != diag) continue;
+                if ((kr.src > lock ? 1 : (kr.src < lock ? -1 : 0)) != side) continue;
+                if (p.lazy) {  // :252-261
+                    if (!haveNl) {
+                        const uint32_t cb = w.claimedBy[m];
+                        myNl = cb != PK_NONE ? w.nl[cb] : next_region_loading_pos(s, me.src);
+                        haveNl = true;
+                    }
+                    if (loaded_pos(s, kr.src) >= myNl) continue;
                 }
-                if (loaded_pos(s, kr.src) >= myNl) continue;
+                int reduce = 0;
+                for (int q = 1; q < g; q++)
+                    if (w.claimedBy[m + static_cast<uint32_t>(q)] < m || (special && q == 1)) reduce++;
+                newClaim = static_cast<uint8_t>(g);
+                newDelta = static_cast<uint8_t>(g - reduce);
+                break;
             }
-            newClaim = static_cast<uint8_t>(g);
-            newDelta = static_cast<uint8_t>(g - reduce);
-            break;
-        }
     }
     bool ch = false;
     if (haveNl && w.nl[m] != myNl) {
@@ -584,7 +593,7 @@ __device__ __forceinline__ bool locate_gap(const PackBatch& b, const uint32_t* _
 }
 
 __global__ void __launch_bounds__(PK_THREADS) k_pk_count(PackParams p, PackState s, PackBatch b, PackWork w) {
-    __shared__ uint32_t sWarp[33];
+    __shared__ uint32_t sTot[PACK_STREAMS];
     const uint32_t gi = blockIdx.x * PK_THREADS + threadIdx.x;
     GapOut cnt;
 #pragma unroll
@@ -599,25 +608,40 @@ __global__ void __launch_bounds__(PK_THREADS) k_pk_count(PackParams p, PackState
 #pragma unroll
         for (int k = 0; k < PACK_STREAMS; k++) w.gapCnt[static_cast<uint64_t>(gi) * PACK_STREAMS + k] = cnt.n[k];
     }
+    // per-block totals of the six columns: one hardware warp reduction each, then 8 warps x 6 shared atomics
+    if (threadIdx.x < PACK_STREAMS) sTot[threadIdx.x] = 0;
+    __syncthreads();
 #pragma unroll
     for (int k = 0; k < PACK_STREAMS; k++) {
-        uint32_t total;
-        block_excl_scan_u32(cnt.n[k], &total, sWarp);
-        if (threadIdx.x == 0) w.blockTot[static_cast<uint64_t>(blockIdx.x) * PACK_STREAMS + k] = total;
+        const uint32_t t = __reduce_add_sync(0xFFFFFFFFu, cnt.n[k]);
+        if ((threadIdx.x & 31) == 0 && t) atomicAdd(&sTot[k], t);
     }
+    __syncthreads();
+    if (threadIdx.x < PACK_STREAMS) w.blockTot[static_cast<uint64_t>(blockIdx.x) * PACK_STREAMS + threadIdx.x] = sTot[threadIdx.x];
 }
 
 __global__ void __launch_bounds__(PK_THREADS) k_pk_emit(PackParams p, PackState s, PackBatch b, PackWork w) {
-    __shared__ uint32_t sWarp[33];
+    __shared__ uint32_t sWarpTot[PK_THREADS / 32][PACK_STREAMS];
     const uint32_t gi = blockIdx.x * PK_THREADS + threadIdx.x;
     uint32_t c = 0, j = 0, n = 0;
     const bool live = locate_gap(b, w.kOff, gi, c, j, n);
     GapOut at;
+    {   // exclusive scan of the six columns over the block: warp scans, then the (8 x 6) warp totals
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-    for (int k = 0; k < PACK_STREAMS; k++) {
-        const uint32_t v = live ? w.gapCnt[static_cast<uint64_t>(gi) * PACK_STREAMS + k] : 0;
-        uint32_t total;
-        at.n[k] = block_excl_scan_u32(v, &total, sWarp) + w.blockTot[static_cast<uint64_t>(blockIdx.x) * PACK_STREAMS + k];
+        for (int k = 0; k < PACK_STREAMS; k++) {
+            const uint32_t v = live ? w.gapCnt[static_cast<uint64_t>(gi) * PACK_STREAMS + k] : 0;
+            const uint32_t inc = warp_incl_scan_u32(v, lane);
+            at.n[k] = inc - v;
+            if (lane == 31) sWarpTot[warp][k] = inc;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < PACK_STREAMS; k++) {
+            uint32_t before = w.blockTot[static_cast<uint64_t>(blockIdx.x) * PACK_STREAMS + k];
+            for (int q = 0; q < warp; q++) before += sWarpTot[q][k];
+            at.n[k] += before;
+        }
     }
     const uint8_t* plainSrc = nullptr;
     uint8_t* plainDst = nullptr;
@@ -701,7 +725,7 @@ int launch_pack_pass1(const PackParams& p, const PackState& s, const PackBatch& 
             launches++;
         }
     k_pk_kept_tot<<<blocks, PK_THREADS, 0, st>>>(nM, w.removed, w.blockTot);
-    k_pk_partials<1><<<1, PK_THREADS, 0, st>>>(w.blockTot, blocks);
+    k_pk_partials<1><<<1, 1024, 0, st>>>(w.blockTot, blocks);
     k_pk_compact<<<blocks, PK_THREADS, 0, st>>>(s, b, w, w.blockTot);
     k_pk_koff<<<blocks_for(static_cast<uint64_t>(b.nContigs) + 1), PK_THREADS, 0, st>>>(b, w.keptScan, w.kOff);
     return launches + 4;
@@ -735,7 +759,7 @@ int launch_pack_claims(const PackParams& p, const PackState& s, const PackBatch&
 int launch_pack_count(const PackParams& p, const PackState& s, const PackBatch& b, const PackWork& w, cudaStream_t st) {
     const uint32_t blocks = blocks_for(static_cast<uint64_t>(b.nMatches) + b.nContigs);
     k_pk_count<<<blocks, PK_THREADS, 0, st>>>(p, s, b, w);
-    k_pk_partials<PACK_STREAMS><<<1, PK_THREADS, 0, st>>>(w.blockTot, blocks);
+    k_pk_partials<PACK_STREAMS><<<PACK_STREAMS, 1024, 0, st>>>(w.blockTot, blocks);
     return 2;
 }
 

@@ -70,6 +70,7 @@ struct PackWork {
     uint32_t* keptScan;        // [nM+1] exclusive scan of !removed
     KeptRec* kept;             // [nM]
     uint32_t* kContig;         // [nM]
+    uint32_t* kDiag;           // [nM] low 32 bits of posSrcText - posDestText (quick reject in the pairing scan)
     uint32_t* kOff;            // [nC+1] first kept match of every text
     unsigned long long* sumLen;// [nC] sum of kept lengths (unmatched = destLen - sum)
     uint8_t* claim;            // [nM] g of the later match this one pairs with (0 = none)

@@ -177,6 +177,7 @@ void B200SparseEMMatcher::packBatch(const PackParams& p, const std::vector<TextV
         const uint64_t oKeptScan = carve((nM + 1ull) * 4);
         const uint64_t oKept = carve(nM * sizeof(KeptRec));
         const uint64_t oKContig = carve(nM * 4ull);
+        const uint64_t oKDiag = carve(nM * 4ull);
         const uint64_t oKOff = carve((nC + 1ull) * 4);
         const uint64_t oClaim = carve(nM);
         const uint64_t oDelta = carve(nM);
@@ -206,6 +207,7 @@ void B200SparseEMMatcher::packBatch(const PackParams& p, const std::vector<TextV
         w.keptScan = reinterpret_cast<uint32_t*>(dPackWork + oKeptScan);
         w.kept = reinterpret_cast<KeptRec*>(dPackWork + oKept);
         w.kContig = reinterpret_cast<uint32_t*>(dPackWork + oKContig);
+        w.kDiag = reinterpret_cast<uint32_t*>(dPackWork + oKDiag);
         w.kOff = reinterpret_cast<uint32_t*>(dPackWork + oKOff);
         w.claim = dPackWork + oClaim;
         w.delta = dPackWork + oDelta;

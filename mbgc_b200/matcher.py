@@ -180,7 +180,7 @@ class Matcher:
                                          C.byref(out), C.byref(n)))
         return self._matches(out, n.value)
 
-    def matchBatch(self, texts, minMatchLength=32, lockPos=None, copy=True):
+    def matchBatch(self, texts, minMatchLength=32, lockPos=None, copy=True, fetch=True):
         """list of texts -> list of (n_i, 3) arrays, all matched against the same frozen state.
         copy=False returns views of the library's pinned result buffer (valid until the next match call)."""
         arrs = [_as_u8(t) for t in texts]
@@ -189,19 +189,24 @@ class Matcher:
         lens = (C.c_uint64 * n)(*[a.size for a in arrs])
         locks = (C.c_uint64 * n)(*lockPos) if lockPos is not None else None
         out, counts = C.c_void_p(), C.c_void_p()
-        self._check(self.lib.mbgcg_match_batch(self.h, n, ptrs, lens, minMatchLength, locks, C.byref(out),
-                                               C.byref(counts)))
+        self._check(self.lib.mbgcg_match_batch(self.h, n, ptrs, lens, minMatchLength, locks,
+                                               C.byref(out) if fetch else None, C.byref(counts)))
+        if not fetch:  # lists stay on the device for packBatch(matches=None)
+            return np.ctypeslib.as_array(C.cast(counts, u64p), shape=(n,)).copy()
         return self._split(out, counts, n, copy)
 
-    def matchBatchDevice(self, dTextPtr, offsets, lens, minMatchLength=32, lockPos=None, copy=True):
-        """texts already resident in device memory (see mbgcg_match_batch_device for the layout rules)."""
+    def matchBatchDevice(self, dTextPtr, offsets, lens, minMatchLength=32, lockPos=None, copy=True, fetch=True):
+        """texts already resident in device memory (see mbgcg_match_batch_device for the layout rules).
+        fetch=False leaves the lists on the device for a packBatch(matches=None) call and returns the counts."""
         n = len(lens)
         offs = (C.c_uint64 * n)(*offsets)
         ls = (C.c_uint64 * n)(*lens)
         locks = (C.c_uint64 * n)(*lockPos) if lockPos is not None else None
         out, counts = C.c_void_p(), C.c_void_p()
         self._check(self.lib.mbgcg_match_batch_device(self.h, dTextPtr, n, offs, ls, minMatchLength, locks,
-                                                      C.byref(out), C.byref(counts)))
+                                                      C.byref(out) if fetch else None, C.byref(counts)))
+        if not fetch:
+            return np.ctypeslib.as_array(C.cast(counts, u64p), shape=(n,)).copy()
         return self._split(out, counts, n, copy)
 
     def packBatch(self, params, texts, matches=None, lockPos=None, loadedPosArr=(), lens=None, raw=False):

@@ -103,6 +103,11 @@ def _run_all_routes(pr, texts, po, pd, locks=None, loaded=(), tag=""):
         assert np.array_equal(a, b), tag + " match lists differ (matcher parity)"
     got = g.packBatch(pd, texts, None, lockPos=locks, loadedPosArr=loaded)
     _check(got, want, tag + " resident")
+    # (b') the same with the lists never leaving the device (out == NULL in the match call)
+    cnts = g.matchBatch(texts, 32, locks, fetch=False)
+    assert [int(c) for c in cnts] == [len(m) for m in lists]
+    got = g.packBatch(pd, texts, None, lockPos=locks, loadedPosArr=loaded)
+    _check(got, want, tag + " resident, lists on the device only")
     # (c) one call per text
     for i, t in enumerate(texts[:6]):
         got = g.packBatch(pd, [t], [lists[i]], lockPos=[lk[i]] if locks is not None else None, loadedPosArr=loaded)
