@@ -148,3 +148,135 @@ def match_speculative(matcher, texts, extension_rule, window, device="cpu", min_
                 break
         done += committed
     return out, rounds
+
+
+# ------------------------------------------------------------------------------------------------------
+# The whole hot path sharded: match stage + stream packing (K6), reference extensions decided by the reference's
+# own rule on the packer's unmatched count.
+# ------------------------------------------------------------------------------------------------------
+
+STREAM_NAMES = ("literals", "mapOff", "mapOff5", "mapLen", "gapDelta", "gapFlags")
+SEQ_SEPARATOR_MARK = (ord('"') + 128) & 0xFF   # mbgccoder/MBGC_Params.h:46
+FILE_SEPARATOR_MARK = (ord(';') + 128) & 0xFF  # mbgccoder/MBGC_Params.h:47
+
+
+def _gather_packed(local, n_items, device="cpu"):
+    """local: this rank's per-text results [(unmatched, [six bytes objects])] for its shard of n_items texts.
+    Returns the same for all n_items texts, in text order, on every rank (sizes by all_reduce, payload by all_gather)."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return list(local)
+    world, rank = dist.get_world_size(), dist.get_rank()
+    meta = torch.zeros((n_items, 7), dtype=torch.int64, device=device)  # unmatched + six stream sizes per text
+    b, e = shard_range(n_items, rank, world)
+    assert e - b == len(local)
+    for k, (unmatched, segs) in enumerate(local):
+        meta[b + k, 0] = int(unmatched)
+        for s_, seg in enumerate(segs):
+            meta[b + k, 1 + s_] = len(seg)
+    dist.all_reduce(meta, op=dist.ReduceOp.SUM)
+    meta_h = meta.cpu().numpy()
+    per_rank = [int(meta_h[slice(*shard_range(n_items, r, world)), 1:].sum()) for r in range(world)]
+    width = max(per_rank) if per_rank else 0
+    mine = np.zeros(width, dtype=np.uint8)
+    flat = b"".join(seg for _, segs in local for seg in segs)
+    mine[:len(flat)] = np.frombuffer(flat, dtype=np.uint8)
+    bufs = [torch.zeros(width, dtype=torch.uint8, device=device) for _ in range(world)]
+    dist.all_gather(bufs, torch.from_numpy(mine).to(device))
+    out = []
+    for r in range(world):
+        rb, re_ = shard_range(n_items, r, world)
+        data = bufs[r].cpu().numpy().tobytes()
+        o = 0
+        for t in range(rb, re_):
+            segs = []
+            for s_ in range(6):
+                n = int(meta_h[t, 1 + s_])
+                segs.append(data[o:o + n])
+                o += n
+            out.append((int(meta_h[t, 0]), segs))
+    return out
+
+
+def compress_speculative(matcher, files, pack_params, window, device="cpu", min_match_length=32,
+                         unmatched_fraction_factor=128, unmatched_fraction_rc_factor=8):
+    """The reference's sequential (-t 1) encoder schedule over `files` (a list of files, each a list of contig texts),
+    with both stages of the hot path on the matcher's device and the contigs of a window sharded over the ranks
+    (optimistic batching):
+
+        per contig   matchTexts -> processMatches -> if unmatched * factor > length: loadRef(contig [, +RC])
+                     (MultipleGenomeMatchingProcessor.cpp:274-287; MGMP_Params.h:179-196)
+        per file     FILE_SEPARATOR_MARK in the flag stream, loadSeparator, refExtLoadedPosArr grows
+                     (mbgccoder/MBGC_Encoder.cpp:493-509)
+
+    A contig that does not extend the reference leaves index and reference untouched, and the one-byte separators
+    appended between files only move the loading cursor over bytes that are zero anyway, so a window of contigs
+    (across file boundaries) is matched AND packed in parallel against the frozen state; results are committed in
+    order up to and including the first contig that extends the reference; the extension is broadcast and applied on
+    every replica and the rest of the window is processed again.  Every rank passes the same `files`.
+
+    Returns ({stream name: bytes}, stats) -- identical on every rank and byte-identical to the sequential schedule
+    (tests/seq_schedule.py::encode_streams, which reproduces the reference's own stream dumps).  The literal stream
+    does not include the G0 bootstrap the encoder writes before the first target (MBGC_Encoder.cpp:34-37)."""
+    import torch.distributed as dist
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
+    flat = [(fi, ci) for fi, f in enumerate(files) for ci in range(len(f))]
+    last_of_file = {(fi, len(f) - 1) for fi, f in enumerate(files) if len(f)}
+    out = {n: [] for n in STREAM_NAMES}
+    loaded = [matcher.getLoadingPosition()]
+    file_start = matcher.getLoadedRefLength()
+    stats = dict(rounds=0, extensions=0, unmatched=0, contigs=len(flat), repacked=0)
+    # files without contigs still close with a separator
+    def close_file():
+        nonlocal file_start
+        if pack_params.enableExtensionsWithMismatches:
+            out["gapFlags"].append(bytes([FILE_SEPARATOR_MARK]))
+        matcher.loadSeparator(0)
+        loaded.append(loaded[-1] + (matcher.getLoadedRefLength() - file_start))
+        file_start = matcher.getLoadedRefLength()
+
+    next_file = 0
+    done = 0
+    while done < len(flat):
+        hi = min(len(flat), done + window)
+        spans = [shard_range(hi - done, r, world) for r in range(world)]
+        b, e = spans[rank]
+        mine = [files[fi][ci] for fi, ci in flat[done + b:done + e]]
+        local = []
+        if mine:
+            matcher.matchBatch(mine, min_match_length, fetch=False)      # lists stay on the device
+            res = matcher.packBatch(pack_params, mine, None, loadedPosArr=loaded)
+            local = [(int(res["unmatched"][k]), [res[n][k] for n in STREAM_NAMES]) for k in range(len(mine))]
+        packed = _gather_packed(local, hi - done, device)
+        stats["rounds"] += 1
+        committed = 0
+        for k, (unmatched, segs) in enumerate(packed):
+            fi, ci = flat[done + k]
+            while next_file < fi:          # (empty files in between)
+                close_file()
+                next_file += 1
+            text = files[fi][ci]
+            for n, seg in zip(STREAM_NAMES, segs):
+                out[n].append(seg)
+            out["literals"].append(bytes([SEQ_SEPARATOR_MARK]))
+            stats["unmatched"] += unmatched
+            committed += 1
+            extend = unmatched * unmatched_fraction_factor > len(text)
+            if extend:
+                owner = next(r for r, (sb, se) in enumerate(spans) if sb <= k < se)
+                extend_reference_everywhere(matcher, text if rank == owner else None, owner,
+                                            unmatched * unmatched_fraction_rc_factor > len(text), device)
+                stats["extensions"] += 1
+            if (fi, ci) in last_of_file:
+                close_file()
+                next_file = fi + 1
+            if extend:
+                break
+        stats["repacked"] += (hi - done) - committed
+        done += committed
+    while next_file < len(files):
+        close_file()
+        next_file += 1
+    return {n: b"".join(v) for n, v in out.items()}, stats

@@ -9,7 +9,7 @@ import sys
 import numpy as np
 import pytest
 
-from test_multirank_cpu import _OracleAsMatcher, _collection, _rule
+from test_multirank_cpu import _OracleAsMatcher, _collection, _compress_files, _rule, _write_files
 
 pytestmark = pytest.mark.gpu
 
@@ -64,3 +64,52 @@ def test_speculative_batching_two_ranks_gpu():
             assert np.array_equal(np.array(a, dtype=np.uint64).reshape(-1, 3), b)
         assert tsum == int(o.o.table().astype(np.uint64).sum()) and pos == o.o.loading_position
         assert rounds < len(texts)
+
+
+def _compress_worker(rank, world, port, q, limit):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import torch.distributed as dist
+    import mbgc_b200
+    from mbgc_b200.dist import compress_speculative
+    from mbgc_b200.matcher import PackParams
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    files = _compress_files()
+    m = mbgc_b200.Matcher(limit, 32, 16, 1, 16, device=0)
+    m.disableSlidingWindow()
+    m.loadRef(files[0][0], True, True, 0)
+    streams, stats = compress_speculative(m, files, PackParams.for_mode(1), window=5)
+    pos = m.getLoadingPosition()
+    dist.barrier()
+    q.put((rank, streams, stats, pos))
+    m.close()
+    dist.destroy_process_group()
+
+
+def test_sharded_compress_two_ranks_gpu(tmp_path):
+    """both stages of the hot path (match + K6 pack) on real matchers, contigs sharded over two ranks, reference
+    extensions by the reference's rule on the packer's unmatched count: the six streams of the sequential schedule"""
+    import torch.multiprocessing as mp
+    from seq_schedule import SEQ_SEPARATOR_MARK, encode_streams
+    files = _compress_files()
+    paths = _write_files(str(tmp_path), files)
+    want, wstats = encode_streams(paths, 1)
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_compress_worker, args=(r, 2, port, q, wstats["limit"])) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=600) for _ in range(2)), key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    boot = bytes(files[0][0]) + bytes([SEQ_SEPARATOR_MARK])
+    for rank, streams, stats, pos in res:
+        assert 0 < stats["extensions"] < stats["contigs"] and stats["rounds"] < stats["contigs"]
+        for name, data in want.items():
+            got = (boot if name == "literals" else b"") + streams[name]
+            assert got == data, f"rank {rank} stream {name} differs ({len(got)} vs {len(data)} bytes)"

@@ -156,3 +156,130 @@ def test_speculative_batching_equals_sequential_schedule():
             assert np.array_equal(np.array(a, dtype=np.uint64).reshape(-1, 3), b)
         assert tsum == int(m.o.table().astype(np.uint64).sum()) and pos == m.o.loading_position
         assert rounds < len(texts)  # some windows committed more than one text
+
+
+# ------------------------------------------------------------------------------------------------------
+# the whole hot path sharded: match + pack + the reference's extension rule (mbgc_b200.dist.compress_speculative)
+# ------------------------------------------------------------------------------------------------------
+
+class _OracleAsCompressor(_OracleAsMatcher):
+    """the CPU oracle behind the Matcher methods compress_speculative uses (tests only): match lists stay inside the
+    adapter between matchBatch(fetch=False) and packBatch(matches=None), like they stay on the device"""
+
+    def getLoadingPosition(self):
+        return self.o.loading_position
+
+    def getLoadedRefLength(self):
+        return self.o.loaded_ref_length
+
+    def loadSeparator(self, sep=0):
+        self.o.load_separator(sep)
+
+    def matchBatch(self, texts, min_len=32, fetch=True):
+        self._lists = [self.o.match(t, min_len) for t in texts]
+        return self._lists if fetch else np.array([len(a) for a in self._lists], dtype=np.uint64)
+
+    def packBatch(self, pd, texts, matches=None, lockPos=None, loadedPosArr=(), lens=None):
+        import ctypes as C
+        from util import PackParams, oracle_lib, u8p
+        assert matches is None
+        lib = oracle_lib()
+        po = PackParams(pd.enableExtensionsWithMismatches, pd.gapBreakingMatchMinLength, pd.gapDepthOffsetEncoding,
+                        pd.gapDepthMismatchesEncoding, pd.lazyDecompressionSupport, pd.frugal64bitLenEncoding,
+                        pd.enable40bitReference, pd.mismatchesWithExclusion, pd.mmsMismatchesInitialScore,
+                        pd.mmsMismatchesScoreThreshold, pd.mmsMismatchPenalty, pd.mmsMatchBonus, 32, 128)
+        names = ("literals", "mapOff", "mapOff5", "mapLen", "gapDelta", "gapFlags")
+        out = {n: [] for n in names}
+        out["unmatched"], out["kept"] = [], []
+        arr = (C.c_uint64 * max(1, len(loadedPosArr)))(*loadedPosArr)
+        for t, mt in zip(texts, self._lists):
+            st = lib.mbo_streams_create()
+            a = np.ascontiguousarray(t, dtype=np.uint8)
+            buf = np.ascontiguousarray(mt, dtype=np.uint64).copy() if len(mt) else np.zeros((1, 3), dtype=np.uint64)
+            n = C.c_uint64(len(mt))
+            unmatched = lib.mbo_process_matches(st, C.byref(po), self.o.h, buf.ctypes.data_as(C.c_void_p), C.byref(n),
+                                                a.ctypes.data_as(u8p), a.size, 2**64 - 1, arr, len(loadedPosArr))
+            for i, name in enumerate(names):
+                k = lib.mbo_stream_size(st, i)
+                ptr = lib.mbo_stream_data(st, i)
+                out[name].append(bytes(np.ctypeslib.as_array(C.cast(ptr, u8p), shape=(k,))) if k else b"")
+            out["unmatched"].append(unmatched)
+            out["kept"].append(n.value)
+            lib.mbo_streams_destroy(st)
+        return out
+
+
+def _compress_files():
+    """6 files x 1..3 contigs: near-identical ones (never extend), a divergent and two novel ones (extend, with and
+    without the reverse complement), a tiny contig"""
+    from mbgc_b200.synth import synth_base, synth_mutant
+    base = synth_base(70_000, 177)
+    other = synth_base(40_000, 178)
+    files = [[base],
+             [synth_mutant(base, 601, 2e-4, 1e-5), synth_mutant(other, 602, 1e-4, 1e-5)],
+             [synth_mutant(base, 603, 3e-4, 2e-5)],
+             [synth_mutant(base, 604, 3e-2, 1e-3), synth_mutant(base, 605, 1e-4, 1e-5)[:31], synth_mutant(other, 606, 2e-4, 1e-5)],
+             [synth_mutant(base, 607, 1e-4, 1e-5), synth_mutant(base, 608, 2e-4, 0)],
+             [synth_mutant(synth_base(30_000, 179), 609, 0, 0), synth_mutant(base, 610, 5e-4, 1e-5)]]
+    return files
+
+
+def _write_files(d, files):
+    from util import write_fasta
+    paths = []
+    for i, f in enumerate(files):
+        path = os.path.join(d, f"f{i:03d}.fna")
+        with open(path, "wb") as fh:
+            for j, c in enumerate(f):
+                fh.write(f">file{i} contig{j}\n".encode())
+                seq = bytes(c)
+                for k in range(0, len(seq), 80):
+                    fh.write(seq[k:k + 80] + b"\n")
+        paths.append(path)
+    return paths
+
+
+def _compress_worker(rank, world, port, q, limit):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import torch.distributed as dist
+    from mbgc_b200.dist import compress_speculative
+    from mbgc_b200.matcher import PackParams
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    files = _compress_files()
+    m = _OracleAsCompressor(limit)
+    m.loadRef(files[0][0], True)
+    streams, stats = compress_speculative(m, files, PackParams.for_mode(1), window=5)
+    dist.barrier()
+    q.put((rank, streams, stats, m.o.loading_position))
+    dist.destroy_process_group()
+
+
+def test_sharded_compress_equals_sequential_streams(tmp_path):
+    """match + pack sharded over 2 ranks with speculative windows across file boundaries == the six streams of the
+    sequential (-t 1) schedule (tests/seq_schedule.py, pinned against the reference's stream dumps)"""
+    import torch.multiprocessing as mp
+    from seq_schedule import SEQ_SEPARATOR_MARK, encode_streams
+    files = _compress_files()
+    paths = _write_files(str(tmp_path), files)
+    want, wstats = encode_streams(paths, 1)
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_compress_worker, args=(r, 2, port, q, wstats["limit"])) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=300) for _ in range(2)), key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    boot = bytes(files[0][0]) + bytes([SEQ_SEPARATOR_MARK])
+    for rank, streams, stats, pos in res:
+        assert 0 < stats["extensions"] < stats["contigs"] and stats["rounds"] < stats["contigs"]
+        assert stats["unmatched"] == wstats["unmatched"]
+        for name, data in want.items():
+            got = (boot if name == "literals" else b"") + streams[name]
+            assert got == data, f"rank {rank} stream {name} differs ({len(got)} vs {len(data)} bytes)"
