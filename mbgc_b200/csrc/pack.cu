@@ -353,11 +353,77 @@ struct Sink {
         if (W) flg[nFlg] = v;
         nFlg++;
     }
+    // `n` flags at once: byte i of mm has bit 7 set where position i mismatches
+    __device__ __forceinline__ void putFlags(uint64_t mm, int n) {
+        if (W)
+            for (int i = 0; i < n; i++) flg[nFlg + i] = static_cast<uint8_t>((mm >> (8 * i + 7)) & 1);
+        nFlg += n;
+    }
 };
 
 __device__ __forceinline__ uint8_t ref_at(const PackState& s, int64_t i) {
     const int64_t hi = static_cast<int64_t>(s.maxRefLength + REF_READ_SLACK);
     return __ldg(s.ref + (i < hi ? i : hi));  // memory safety only: the reference never reads there in a valid run
+}
+
+// 8 bytes at an arbitrary address (little endian: byte i = p[i]) from three aligned words
+__device__ __forceinline__ uint64_t load8(const uint8_t* p) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~static_cast<uintptr_t>(3));
+    const uint32_t sh = static_cast<uint32_t>(a & 3) * 8;
+    const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
+    return static_cast<uint64_t>(__funnelshift_r(w0, w1, sh)) | (static_cast<uint64_t>(__funnelshift_r(w1, w2, sh)) << 32);
+}
+__device__ __forceinline__ uint64_t load8_ref(const PackState& s, int64_t i) {
+    if (i + 12 <= static_cast<int64_t>(s.maxRefLength + REF_READ_SLACK)) return load8(s.ref + i);
+    uint64_t v = 0;
+    for (int k = 0; k < 8; k++) v |= static_cast<uint64_t>(ref_at(s, i + k)) << (8 * k);
+    return v;
+}
+__device__ __forceinline__ uint64_t bswap64(uint64_t x) {
+    return (static_cast<uint64_t>(__byte_perm(static_cast<uint32_t>(x), 0, 0x0123)) << 32) |
+           __byte_perm(static_cast<uint32_t>(x >> 32), 0, 0x0123);
+}
+// bit 7 of every byte that is non-zero
+__device__ __forceinline__ uint64_t nonzero_bytes(uint64_t x) {
+    return (((x & 0x7F7F7F7F7F7F7F7Full) + 0x7F7F7F7F7F7F7F7Full) | x) & 0x8080808080808080ull;
+}
+__device__ __forceinline__ uint64_t low_bytes(uint64_t x, int n) { return n >= 8 ? x : x & ((1ull << (8 * n)) - 1); }
+
+// The score automaton of both extensions over up to 8 positions held in registers (rw = reference bytes, tw = text
+// bytes, byte i = i-th position in walking order, `nb` of them in range).  Emits a flag per position walked and a
+// literal per mismatch; returns how many positions it walked.  `limited`: the walk also ends where the score has
+// reached the threshold (checked before every position, as the loop conditions of :346 and :397 do).
+template <bool W>
+__device__ __forceinline__ int walk_word(const PackParams& p, uint64_t rw, uint64_t tw, int nb, bool limited, int& score,
+                                         Sink<W>& out) {
+    uint64_t mm = low_bytes(nonzero_bytes(rw ^ tw), nb);
+    int done = nb;
+    if (limited) {
+        if (mm == 0) {  // all equal: the score only falls (floor 0), no stop inside
+            score -= nb * p.matchBonus;
+            if (score < 0) score = 0;
+        } else {
+            for (done = 0; done < nb; done++) {
+                if (score >= p.scoreThreshold) break;
+                if ((mm >> (8 * done + 7)) & 1)
+                    score += p.mismatchPenalty;
+                else {
+                    score -= p.matchBonus;
+                    if (score < 0) score = 0;
+                }
+            }
+            mm = low_bytes(mm, done);
+        }
+    }
+    out.putFlags(mm, done);
+    while (mm) {
+        const int i = (__ffsll(static_cast<long long>(mm)) - 1) >> 3;
+        mm &= mm - 1;
+        const uint8_t r = static_cast<uint8_t>(rw >> (8 * i)), t = static_cast<uint8_t>(tw >> (8 * i));
+        out.putLit(p.withExclusion ? mismatch2code(r, t) : t);
+    }
+    return done;
 }
 
 // MBGC_Encoder.cpp:310-371.  T = text of the contig, gapPos = first byte after `match`, srcStart = reference
@@ -386,20 +452,29 @@ __device__ uint32_t extend_right(const PackParams& p, const PackState& s, const 
     } else
         srcPtr--;
     int score = p.initialScore;
-    while (++srcPtr < validGuard && (isGap || score < p.scoreThreshold)) {
-        const uint8_t r = ref_at(s, srcPtr);
-        if (p.lazy && r == REF_REGION_SEPARATOR) break;
-        const uint8_t t = __ldg(T + gp);
-        const bool mismatch = t != r;
-        out.putFlag(mismatch ? 1 : 0);
-        if (mismatch) {
-            score += p.mismatchPenalty;
-            out.putLit(p.withExclusion ? mismatch2code(r, t) : t);
-        } else {
-            score -= p.matchBonus;
-            if (score < 0) score = 0;
+    // :346-361, eight positions per step.  The loop leaves srcPtr at the first position it did not walk: the guard, a
+    // region separator (lazy mode) or, outside a gap, where the score reached the threshold.
+    ++srcPtr;
+    for (;;) {
+        const int64_t avail = validGuard - srcPtr;
+        if (avail <= 0 || (!isGap && score >= p.scoreThreshold)) break;
+        int nb = avail < 8 ? static_cast<int>(avail) : 8;
+        const uint64_t rw = load8_ref(s, srcPtr), tw = load8(T + gp);
+        bool sep = false;
+        if (p.lazy) {
+            const uint64_t z = ~nonzero_bytes(rw) & 0x8080808080808080ull;
+            if (z) {
+                const int zi = (__ffsll(static_cast<long long>(z)) - 1) >> 3;
+                if (zi < nb) {
+                    nb = zi;
+                    sep = true;
+                }
+            }
         }
-        gp++;
+        const int done = walk_word<W>(p, rw, tw, nb, !isGap, score, out);
+        srcPtr += done;
+        gp += static_cast<uint32_t>(done);
+        if (done < nb || sep) break;
     }
     while (srcPtr++ < srcGuard && (isGap || score < p.scoreThreshold)) {
         out.putFlag(1);
@@ -435,6 +510,29 @@ __device__ uint32_t extend_left(const PackParams& p, const PackState& s, const u
         out.putLit(p.withExclusion && validSrc ? mismatch2code(r, t) : t);
     }
     int score = p.initialScore;
+    // :397-415, eight positions per step while both buffers have eight bytes to the left (walking order = descending
+    // addresses, hence the byte swap); the byte-wise loop below finishes near the buffer starts
+    while (validSrc && srcPtr - srcGuard >= 1 && score < p.scoreThreshold && gp >= 8 && srcPtr >= 8) {
+        const int64_t avail = srcPtr - srcGuard;
+        int nb = avail < 8 ? static_cast<int>(avail) : 8;
+        const uint64_t rw = bswap64(load8_ref(s, srcPtr - 8)), tw = bswap64(load8(T + gp - 8));
+        bool sep = false;
+        if (p.lazy) {
+            const uint64_t z = ~nonzero_bytes(rw) & 0x8080808080808080ull;
+            if (z) {
+                const int zi = (__ffsll(static_cast<long long>(z)) - 1) >> 3;
+                if (zi < nb) {
+                    nb = zi;
+                    sep = true;
+                }
+            }
+        }
+        const int done = walk_word<W>(p, rw, tw, nb, true, score, out);
+        srcPtr -= done;
+        gp -= done;
+        if (done == nb && sep) validSrc = false;  // the next position is a separator: :399-404
+        if (done < nb || sep) break;
+    }
     while (validSrc && srcPtr > srcGuard && score < p.scoreThreshold) {
         --gp;
         --srcPtr;
