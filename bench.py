@@ -307,6 +307,7 @@ def measure_tier(args, tier, rank, world, dist, local):
     torch.cuda.synchronize()
     lens = [t.size for t in targets]
     fbytes = sum(fasta_bytes(x, HEADER_LEN) for x in lens)
+    offs_a, lens_a = np.array(offs, dtype=np.uint64), np.array(lens, dtype=np.uint64)  # handed to the C ABI as they are
     stream = torch.cuda.ExternalStream(m.stream())
 
     def barrier():
@@ -338,7 +339,7 @@ def measure_tier(args, tier, rank, world, dist, local):
 
     steps, warmup = args.steps, args.warmup
     ms_dev, stage_dev, launches, res = timed(
-        lambda: m.matchBatchDevice(dbuf.data_ptr(), offs, lens, 32, copy=False), steps, warmup)
+        lambda: m.matchBatchDevice(dbuf.data_ptr(), offs_a, lens_a, 32, copy=False), steps, warmup)
     n_matches = int(sum(len(r) for r in res))
     counters = m.counters()
     host_ptrs = [p.numpy() for p in pinned]
@@ -351,8 +352,8 @@ def measure_tier(args, tier, rank, world, dist, local):
     pack_tm = {}
 
     def match_and_pack():
-        m.matchBatchDevice(dbuf.data_ptr(), offs, lens, 32, fetch=False)  # lists stay in HBM, only counts come back
-        return m.packBatch(pd, None, None, loadedPosArr=loaded, lens=lens, raw=True)
+        m.matchBatchDevice(dbuf.data_ptr(), offs_a, lens_a, 32, fetch=False)  # lists stay in HBM, only counts come back
+        return m.packBatch(pd, None, None, loadedPosArr=loaded, lens=lens_a, raw=True)
 
     psteps = max(2, steps // 2)
     for _ in range(2):

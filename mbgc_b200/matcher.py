@@ -124,6 +124,13 @@ def load_library():
     return L
 
 
+def _u64_array(v):
+    """ctypes view of a sequence of uint64 for the C ABI; a C-contiguous uint64 numpy array is passed as is"""
+    if isinstance(v, np.ndarray) and v.dtype == np.uint64 and v.flags.c_contiguous:
+        return v.ctypes.data_as(u64p)
+    return (C.c_uint64 * len(v))(*v)
+
+
 def _as_u8(buf):
     if isinstance(buf, np.ndarray):
         return np.ascontiguousarray(buf, dtype=np.uint8)
@@ -199,9 +206,8 @@ class Matcher:
         """texts already resident in device memory (see mbgcg_match_batch_device for the layout rules).
         fetch=False leaves the lists on the device for a packBatch(matches=None) call and returns the counts."""
         n = len(lens)
-        offs = (C.c_uint64 * n)(*offsets)
-        ls = (C.c_uint64 * n)(*lens)
-        locks = (C.c_uint64 * n)(*lockPos) if lockPos is not None else None
+        offs, ls = _u64_array(offsets), _u64_array(lens)   # uint64 numpy arrays pass through without a copy
+        locks = _u64_array(lockPos) if lockPos is not None else None
         out, counts = C.c_void_p(), C.c_void_p()
         self._check(self.lib.mbgcg_match_batch_device(self.h, dTextPtr, n, offs, ls, minMatchLength, locks,
                                                       C.byref(out) if fetch else None, C.byref(counts)))
@@ -223,7 +229,7 @@ class Matcher:
         else:
             n = len(lens)
             ptrs = None
-            ls = (C.c_uint64 * n)(*lens)
+            ls = _u64_array(lens)
         if matches is not None:
             cnt = (C.c_uint64 * n)(*[len(m) for m in matches])
             tot = sum(len(m) for m in matches)
