@@ -339,12 +339,12 @@ def measure_tier(args, tier, rank, world, dist, local):
 
     steps, warmup = args.steps, args.warmup
     ms_dev, stage_dev, launches, res = timed(
-        lambda: m.matchBatchDevice(dbuf.data_ptr(), offs_a, lens_a, 32, copy=False), steps, warmup)
-    n_matches = int(sum(len(r) for r in res))
+        lambda: m.matchBatchDevice(dbuf.data_ptr(), offs_a, lens_a, 32, copy=False, split=False), steps, warmup)
+    n_matches = int(len(res[0]))
     counters = m.counters()
     host_ptrs = [p.numpy() for p in pinned]
-    ms_e2e, stage_e2e, _, res2 = timed(lambda: m.matchBatch(host_ptrs, 32, copy=False), steps, warmup)
-    assert n_matches == int(sum(len(r) for r in res2)), "device-resident and host-buffer passes disagree"
+    ms_e2e, stage_e2e, _, res2 = timed(lambda: m.matchBatch(host_ptrs, 32, copy=False, split=False), steps, warmup)
+    assert n_matches == int(len(res2[0])), "device-resident and host-buffer passes disagree"
     # K6: match stage + stream packing with everything resident (the lists never leave the device between the two)
     from mbgc_b200.matcher import PackParams
     pd = PackParams.for_mode(args.mode)

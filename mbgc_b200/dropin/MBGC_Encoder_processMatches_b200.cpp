@@ -50,6 +50,7 @@ size_t MBGC_Encoder::processMatches(vector<PgTools::TextMatch>& textMatches, cha
     pp.mmsMatchBonus = params->mmsMatchBonus;
     pp.gapBreakingMatchMinLength = params->gapBreakingMatchMinLength;
 
+    mbgc_b200_dropin::Trace tr("processMatches", destLen);
     const uint64_t n0 = textMatches.size();
     uint64_t unmatchedChars = 0, kept = 0;
     {

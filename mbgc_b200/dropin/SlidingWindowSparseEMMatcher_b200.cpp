@@ -43,22 +43,7 @@ inline mbgcg_t* handle_of(uint64_t* slot) { return reinterpret_cast<mbgcg_t*>(sl
     exit(EXIT_FAILURE);
 }
 
-// MBGC_B200_TRACE=1: wall time of every call through the shim on stderr
-struct Trace {
-    const char* what;
-    size_t n;
-    std::chrono::steady_clock::time_point t0;
-    static bool on() {
-        static const bool v = std::getenv("MBGC_B200_TRACE") != nullptr;
-        return v;
-    }
-    Trace(const char* w, size_t bytes) : what(w), n(bytes), t0(std::chrono::steady_clock::now()) {}
-    ~Trace() {
-        if (on())
-            fprintf(stderr, "[mbgc_b200] %-14s %10zu bytes %9.3f ms\n", what, n,
-                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
-    }
-};
+using mbgc_b200_dropin::Trace;
 
 int device_from_env() {
     const char* e = std::getenv("MBGC_B200_DEVICE");

@@ -1,8 +1,11 @@
 // mbgc_b200/dropin/dropin_shared.h -- what the two drop-in translation units share: the handle behind a reference
 // matcher object, the mutex that serialises calls on it, and the identity of the last matchTexts call.
 #pragma once
+#include <chrono>
 #include <cstddef>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <mutex>
 
 #include "mbgc_b200.h"
@@ -10,6 +13,23 @@
 class SlidingWindowSparseEMMatcher;
 
 namespace mbgc_b200_dropin {
+
+// MBGC_B200_TRACE=1: wall time of every call through the shims on stderr
+struct Trace {
+    const char* what;
+    size_t n;
+    std::chrono::steady_clock::time_point t0;
+    static bool on() {
+        static const bool v = std::getenv("MBGC_B200_TRACE") != nullptr;
+        return v;
+    }
+    Trace(const char* w, size_t bytes) : what(w), n(bytes), t0(std::chrono::steady_clock::now()) {}
+    ~Trace() {
+        if (on())
+            fprintf(stderr, "[mbgc_b200] %-14s %10zu bytes %9.3f ms\n", what, n,
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    }
+};
 
 struct LastMatch {
     const SlidingWindowSparseEMMatcher* matcher;

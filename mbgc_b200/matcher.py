@@ -187,7 +187,7 @@ class Matcher:
                                          C.byref(out), C.byref(n)))
         return self._matches(out, n.value)
 
-    def matchBatch(self, texts, minMatchLength=32, lockPos=None, copy=True, fetch=True):
+    def matchBatch(self, texts, minMatchLength=32, lockPos=None, copy=True, fetch=True, split=True):
         """list of texts -> list of (n_i, 3) arrays, all matched against the same frozen state.
         copy=False returns views of the library's pinned result buffer (valid until the next match call)."""
         arrs = [_as_u8(t) for t in texts]
@@ -200,11 +200,13 @@ class Matcher:
                                                C.byref(out) if fetch else None, C.byref(counts)))
         if not fetch:  # lists stay on the device for packBatch(matches=None)
             return np.ctypeslib.as_array(C.cast(counts, u64p), shape=(n,)).copy()
-        return self._split(out, counts, n, copy)
+        return self._split(out, counts, n, copy, split)
 
-    def matchBatchDevice(self, dTextPtr, offsets, lens, minMatchLength=32, lockPos=None, copy=True, fetch=True):
+    def matchBatchDevice(self, dTextPtr, offsets, lens, minMatchLength=32, lockPos=None, copy=True, fetch=True,
+                         split=True):
         """texts already resident in device memory (see mbgcg_match_batch_device for the layout rules).
-        fetch=False leaves the lists on the device for a packBatch(matches=None) call and returns the counts."""
+        fetch=False leaves the lists on the device for a packBatch(matches=None) call and returns the counts.
+        split=False returns (all lists concatenated, counts per text) instead of one array per text."""
         n = len(lens)
         offs, ls = _u64_array(offsets), _u64_array(lens)   # uint64 numpy arrays pass through without a copy
         locks = _u64_array(lockPos) if lockPos is not None else None
@@ -213,7 +215,7 @@ class Matcher:
                                                       C.byref(out) if fetch else None, C.byref(counts)))
         if not fetch:
             return np.ctypeslib.as_array(C.cast(counts, u64p), shape=(n,)).copy()
-        return self._split(out, counts, n, copy)
+        return self._split(out, counts, n, copy, split)
 
     def packBatch(self, params, texts, matches=None, lockPos=None, loadedPosArr=(), lens=None, raw=False):
         """MBGC_Encoder::processMatches for a list of texts (mbgcg_pack_batch).  matches: list of (n_i, 3) uint64
@@ -350,8 +352,10 @@ class Matcher:
         a = np.ctypeslib.as_array(C.cast(out, u64p), shape=(n, 4))
         return a[:, :3].copy() if copy else a[:, :3]
 
-    def _split(self, out, counts, n, copy=True):
+    def _split(self, out, counts, n, copy=True, split=True):
         cnt = np.ctypeslib.as_array(C.cast(counts, u64p), shape=(n,)).copy() if n else np.zeros(0, np.uint64)
         allm = self._matches(out, int(cnt.sum()), copy)
+        if not split:
+            return allm, cnt
         ends = np.cumsum(cnt.astype(np.int64))
         return [allm[int(e - c):int(e)] for c, e in zip(cnt, ends)]

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Full-size drop-in check (BASELINE.json configs[1] shape): the reference CLI with our matcher linked in
-(oracle/_ref/mbgc_b200) against the stock CLI (oracle/_ref/mbgc), both `c -t 1 -m M`, on the synthetic
+(oracle/_ref/mbgc_b200; and oracle/_ref/mbgc_b200_full with the stream packer on the GPU as well) against the stock CLI (oracle/_ref/mbgc), both `c -t 1 -m M`, on the synthetic
 100 x 5 Mbp collection.  Prints archive md5s (must be equal), wall times and the reference's own timing lines.
 
     python tools/full_size_dropin.py [--genomes 100] [--length 5000000] [--tier near|div] [--mode 0] [--dir /tmp/c2]
@@ -44,7 +44,8 @@ def main():
     env = dict(os.environ)
     env.pop("OMP_NUM_THREADS", None)
     out = {"fasta_bytes": total, "genomes": a.genomes, "tier": a.tier, "mode": a.mode}
-    for tag, binary in (("reference", "mbgc"), ("b200_dropin", "mbgc_b200")):
+    # mbgc_b200 = our matcher behind the reference CLI; mbgc_b200_full = matcher and MBGC_Encoder::processMatches (K6)
+    for tag, binary in (("reference", "mbgc"), ("b200_dropin", "mbgc_b200"), ("b200_dropin_full", "mbgc_b200_full")):
         arch = os.path.join(a.dir, f"{tag}.mbgc")
         if os.path.exists(arch):
             os.remove(arch)
@@ -58,7 +59,7 @@ def main():
         timing = [l.strip() for l in (r.stdout + r.stderr).splitlines() if "time" in l.lower() or "finished" in l.lower()]
         out[tag] = {"wall_s": dt, "GB_per_s": total / dt / 1e9, "archive_bytes": os.path.getsize(arch),
                     "md5": hashlib.md5(open(arch, "rb").read()).hexdigest(), "log": timing[-4:]}
-    out["byte_identical"] = out["reference"]["md5"] == out["b200_dropin"]["md5"]
+    out["byte_identical"] = out["reference"]["md5"] == out["b200_dropin"]["md5"] == out["b200_dropin_full"]["md5"]
     print(json.dumps(out, indent=1))
     if not out["byte_identical"]:
         raise SystemExit("archives differ")
