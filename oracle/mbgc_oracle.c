@@ -731,3 +731,66 @@ uint64_t mbo_process_matches(mbo_streams* out, const mbo_pack_params_t* p, const
     free(nextLoad);
     return (uint64_t) unmatched;
 }
+
+/* ---- FASTA ingest ------------------------------------------------------------------------------------------- */
+
+/* utils/kseq.h:233-274.  The stream functions (ks_getc :61-72, ks_getuntil2 :100-149 with KS_SEP_LINE and
+ * loosy = false: a line ends at '\n' only, '\r' is data) are restated on a cursor into the buffer. */
+uint64_t mbo_fasta_parse(const uint8_t* buf, uint64_t n, mbo_fasta_rec_t* recs, uint64_t recCap, uint8_t* seqOut,
+                         uint64_t* dnaLineLenOut, uint64_t* maxLastOut, int* status) {
+    uint64_t pos = 0, nrec = 0, outl = 0;
+    uint64_t dna = 0 /* DNA_LINE_LENGTH_UNKNOWN */, maxLast = 0;
+    int last_char = 0;
+    *status = -1;
+    for (;;) {
+        if (last_char == 0) { /* :238-242 */
+            if (pos >= n) { *status = -1; break; }
+            int c = buf[pos++];
+            if (c != '>') { *status = -3; break; }
+            last_char = c;
+        }
+        /* :244 ks_getuntil(KS_SEP_LINE, name): nothing left -> -1 */
+        if (pos >= n) { *status = -1; break; }
+        const uint64_t hdrOff = pos;
+        const uint8_t* e = (const uint8_t*) memchr(buf + pos, '\n', n - pos);
+        const uint64_t hdrEnd = e ? (uint64_t) (e - buf) : n;
+        pos = e ? hdrEnd + 1 : n;
+        uint64_t seql = 0, b = 0;
+        int c = -1;
+        while (pos < n) { /* :250-259; ks_getc at the end of the buffer returns -1 and ends the loop */
+            c = buf[pos++];
+            if (c == '>') break;
+            if (c == '\n') { dna = MBO_DNA_NOT_WELLFORMED; c = -1; continue; }
+            if (seql > b) {
+                const uint64_t d = seql - b;
+                dna = dna == 0 ? d : (dna == d ? d : MBO_DNA_NOT_WELLFORMED);
+            }
+            b = seql;
+            seqOut[outl + seql++] = (uint8_t) c;
+            const uint8_t* le = (const uint8_t*) memchr(buf + pos, '\n', n - pos);
+            const uint64_t lineEnd = le ? (uint64_t) (le - buf) : n;
+            memcpy(seqOut + outl + seql, buf + pos, lineEnd - pos);
+            seql += lineEnd - pos;
+            pos = le ? lineEnd + 1 : n;
+            c = -1;
+        }
+        if (seql > b) { /* :260-263 */
+            const uint64_t d = seql - b;
+            if (d > maxLast) maxLast = d;
+        }
+        dna = (!dna || dna >= maxLast) ? dna : MBO_DNA_NOT_WELLFORMED; /* :264 */
+        if (dna == MBO_DNA_NOT_WELLFORMED) { *status = -4; break; }
+        if (c == '>') last_char = c; /* :266; otherwise it keeps the '>' of this record and the next call ends at :244 */
+        if (nrec < recCap) {
+            recs[nrec].hdrOff = hdrOff;
+            recs[nrec].hdrLen = hdrEnd - hdrOff;
+            recs[nrec].seqOff = outl;
+            recs[nrec].seqLen = seql;
+        }
+        nrec++;
+        outl += seql;
+    }
+    *dnaLineLenOut = dna;
+    *maxLastOut = maxLast;
+    return nrec;
+}

@@ -128,6 +128,23 @@ uint64_t mbo_process_matches(mbo_streams* out, const mbo_pack_params_t* p, const
 /* coders/ContextAwareMismatchesCoder.cpp:22-27 */
 uint8_t mbo_mismatch2code(uint8_t actual, uint8_t mismatch);
 
+/* ---- FASTA ingest: utils/kseq.h:233-274 (kseq_read_lossless_fasta), the reader MBGC uses by default
+ * (matching/MultipleGenomeMatchingProcessor.cpp:9-14) -------------------------------------------------------- */
+
+typedef struct {
+    uint64_t hdrOff, hdrLen; /* the header line in the input, without '>' and without the line end */
+    uint64_t seqOff, seqLen; /* the sequence (line ends removed) in seqOut */
+} mbo_fasta_rec_t;
+
+#define MBO_DNA_NOT_WELLFORMED UINT64_MAX /* DNA_NOT_WELLFORMED (-1) in the uint64 member, utils/kseq.h:35,340 */
+
+/* Calls the reader on an in-memory file until it returns a negative value.  Returns the number of records read
+ * successfully (recs[0..], sequences concatenated in seqOut, which must hold n bytes); *status = the final negative
+ * return value (-1 end of file, -3 not FASTA, -4 DNA not well-formed); *dnaLineLen / *maxLastDnaLineLen = the reader's
+ * state after the last call (KSEQ_DNA_LINE_LENGTH reads the former, MultipleGenomeMatchingProcessor.cpp:12-14). */
+uint64_t mbo_fasta_parse(const uint8_t* buf, uint64_t n, mbo_fasta_rec_t* recs, uint64_t recCap, uint8_t* seqOut,
+                         uint64_t* dnaLineLen, uint64_t* maxLastDnaLineLen, int* status);
+
 #ifdef __cplusplus
 }
 #endif
