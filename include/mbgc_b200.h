@@ -173,6 +173,30 @@ int mbgcg_pack_kept_matches(mbgcg_t* h, const mbgcg_match_t** out, uint64_t* n);
  * sweeps used for (removal, pairing) */
 void mbgcg_pack_timing(const mbgcg_t* h, float ms[4], uint64_t* launches, int sweeps[2]);
 
+/* ---- FASTA ingest ---------------------------------------------------------------------------------------------
+ * Replaces the loop over the reference's FASTA reader for one file: kseq_read_lossless_fasta
+ * (/root/reference/utils/kseq.h:233-274; called at matching/MultipleGenomeMatchingProcessor.cpp:9-14, 126-139,
+ * 400-406): record splitting at every '>' that starts a line, the header line, the sequence with its line ends
+ * removed, the DNA line length detection with its "not well-formed" exits.  The file image goes to the device as it is
+ * on disk (gzip stays with libdeflate on the host); the sequences stay there as a batch of texts. */
+typedef struct {
+    uint64_t hdrOff, hdrLen;   /* seq->name: the header line inside `bytes`, without '>' and without the '\n' */
+    uint64_t textOff, seqLen;  /* seq->seq: the sequence inside the device buffer returned in *dTexts */
+} mbgcg_fasta_rec_t;
+
+#define MBGCG_DNA_NOT_WELLFORMED UINT64_MAX /* DNA_NOT_WELLFORMED in the reader's uint64 member, utils/kseq.h:35,340 */
+
+/* bytes = the whole (decompressed) file, HOST pointer.  *recs / *nRecs: the records every successful call of the reader
+ * would have returned, in file order (handle-owned, valid until the next ingest).  *status: the negative value that ends
+ * the reader's loop (-1 end of file, -3 not FASTA, -4 DNA not well-formed -- MBGC exits on the last two,
+ * MultipleGenomeMatchingProcessor.cpp:17-30).  *dnaLineLen: seq->dnaLineLen after the last call (what KSEQ_DNA_LINE_LENGTH
+ * reads).  *dTexts: device buffer holding the sequences at textOff (multiples of 16, >= 64 zero bytes between them,
+ * 8 KiB behind the last): pass it with textOff / seqLen to mbgcg_match_batch_device. */
+int mbgcg_ingest_fasta(mbgcg_t* h, const char* bytes, uint64_t n, const mbgcg_fasta_rec_t** recs, uint64_t* nRecs,
+                       const void** dTexts, uint64_t* dnaLineLen, int* status);
+/* copies sequence `record` of the last ingest to host memory (seqLen bytes) */
+int mbgcg_copy_ingested(mbgcg_t* h, uint64_t record, char* out);
+
 /* ---- sliding-window locks (ref .cpp:361-400) ------------------------------------------------------------ */
 uint64_t mbgcg_acquire_lock(mbgcg_t* h);
 int mbgcg_release_lock(mbgcg_t* h, uint64_t lockValue);

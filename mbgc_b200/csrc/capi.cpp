@@ -188,6 +188,25 @@ void mbgcg_pack_timing(const mbgcg_t* h, float ms[4], uint64_t* launches, int sw
     }
 }
 
+int mbgcg_ingest_fasta(mbgcg_t* h, const char* bytes, uint64_t n, const mbgcg_fasta_rec_t** recs, uint64_t* nRecs,
+                       const void** dTexts, uint64_t* dnaLineLen, int* status) {
+    *recs = nullptr;
+    *nRecs = 0;
+    return guarded(h, [&] {
+        static_assert(sizeof(mbgcg_fasta_rec_t) == sizeof(mbgc_b200::FastaRecord), "FastaRecord layout");
+        h->m->ingestFasta(bytes, n);
+        *recs = reinterpret_cast<const mbgcg_fasta_rec_t*>(h->m->ingestedRecords().data());
+        *nRecs = h->m->ingestedRecords().size();
+        if (dTexts) *dTexts = h->m->ingestedTexts();
+        if (dnaLineLen) *dnaLineLen = h->m->ingestDnaLineLen();
+        if (status) *status = h->m->ingestStatus();
+    });
+}
+
+int mbgcg_copy_ingested(mbgcg_t* h, uint64_t record, char* out) {
+    return guarded(h, [&] { h->m->copyIngested(record, out); });
+}
+
 uint64_t mbgcg_acquire_lock(mbgcg_t* h) { return h->m->acquireWorkerMatchingLockPos(); }
 int mbgcg_release_lock(mbgcg_t* h, uint64_t lockValue) {
     return guarded(h, [&] { h->m->releaseWorkerMatchingLockPos(lockValue); });

@@ -1,0 +1,255 @@
+// mbgc_b200/csrc/ingest.cu -- FASTA ingest on the device (sm_100a): a file image as it is on disk -> contiguous texts.
+//
+// Replaces the per-character loop of the reference's reader, kseq_read_lossless_fasta
+// (/root/reference/utils/kseq.h:233-274), which MBGC runs on one thread per file
+// (matching/MultipleGenomeMatchingProcessor.cpp:9-14, 126-139, 400-406).  The reader is sequential only in how it is
+// written; what it computes is local:
+//
+//   records        a record starts at every '>' that is the first byte of a line (:250: the loop looks at the first
+//                  character of every line); its header is the rest of that line (:244, KS_SEP_LINE, '\r' is data)
+//   sequence       the lines up to the next record start, line ends removed (:250-259)
+//   line length    every line but a record's last must have the file's line length (set by the first such line, :253-256),
+//                  no line may be empty (:251), no last line may be longer (:260-264)  -- otherwise "DNA not well-formed"
+//
+// So: k_fa_count / k_fa_starts find the record starts in file order (block counts, scan, ranks); k_fa_records (a warp
+// per record) finds the end of the header and of the first line; k_fa_check (a thread per 16 input bytes) verifies
+// that every line end of a record sits exactly where its first line's length puts it -- which makes the sequence a pure
+// index transformation, out[k] = in[seqStart + k + k / lineLen], done by k_fa_gather with 16-byte stores.  The one
+// genuinely sequential piece, the file-wide line-length state across records, is a loop over the per-record
+// summaries on the host (ingest.cpp).  All byte work, HBM-bound: the input is read three times, the output written once.
+#include "ingest.h"
+
+namespace mbgc_b200 {
+
+namespace {
+
+__device__ __forceinline__ uint32_t fa_warp_incl_scan(uint32_t v, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, v, d);
+        if (lane >= d) v += t;
+    }
+    return v;
+}
+
+template <int THREADS>
+__device__ __forceinline__ uint32_t fa_block_excl_scan(uint32_t v, uint32_t* total, uint32_t* sWarp) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t inc = fa_warp_incl_scan(v, lane);
+    if (lane == 31) sWarp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t w = lane < (THREADS >> 5) ? sWarp[lane] : 0;
+        const uint32_t wi = fa_warp_incl_scan(w, lane);
+        sWarp[lane] = wi - w;
+        if (lane == 31) sWarp[32] = wi;
+    }
+    __syncthreads();
+    const uint32_t res = inc - v + sWarp[warp];
+    *total = sWarp[32];
+    __syncthreads();
+    return res;
+}
+
+// The 16 bytes at i0 (a multiple of 16; the buffer is 16-byte aligned with a '\n' in front of byte 0 and zeros behind
+// byte n-1) -> bit k set where byte k starts a record.
+__device__ __forceinline__ uint32_t start_mask(const uint8_t* __restrict__ in, uint64_t n, uint64_t i0) {
+    const uint4 v = *reinterpret_cast<const uint4*>(in + i0);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint8_t prev = in[static_cast<int64_t>(i0) - 1];
+    uint32_t m = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const uint8_t b = static_cast<uint8_t>(w[k >> 2] >> (8 * (k & 3)));
+        if (b == '>' && prev == '\n' && i0 + k < n) m |= 1u << k;
+        prev = b;
+    }
+    return m;
+}
+
+__global__ void __launch_bounds__(FA_THREADS) k_fa_count(const uint8_t* __restrict__ in, uint64_t n, uint32_t* __restrict__ blockCnt) {
+    __shared__ uint32_t sTot;
+    if (threadIdx.x == 0) sTot = 0;
+    __syncthreads();
+    const uint64_t i0 = (static_cast<uint64_t>(blockIdx.x) * FA_THREADS + threadIdx.x) * FA_CHUNK;
+    const uint32_t c = i0 < n ? __popc(start_mask(in, n, i0)) : 0;
+    const uint32_t t = __reduce_add_sync(0xFFFFFFFFu, c);
+    if ((threadIdx.x & 31) == 0 && t) atomicAdd(&sTot, t);
+    __syncthreads();
+    if (threadIdx.x == 0) blockCnt[blockIdx.x] = sTot;
+}
+
+// exclusive scan in place, one CTA of 1024 threads, 4 values per thread and round; total at [nBlocks]
+__global__ void __launch_bounds__(1024) k_fa_scan(uint32_t* __restrict__ blockCnt, uint32_t nBlocks) {
+    __shared__ uint32_t sWarp[33];
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < nBlocks; base += 4096) {
+        const uint32_t i0 = base + threadIdx.x * 4;
+        uint32_t v[4], sum = 0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            v[q] = i0 + q < nBlocks ? blockCnt[i0 + q] : 0;
+            sum += v[q];
+        }
+        uint32_t total;
+        uint32_t ex = fa_block_excl_scan<1024>(sum, &total, sWarp) + carry;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            if (i0 + q < nBlocks) blockCnt[i0 + q] = ex;
+            ex += v[q];
+        }
+        carry += total;
+    }
+    if (threadIdx.x == 0) blockCnt[nBlocks] = carry;
+}
+
+__global__ void __launch_bounds__(FA_THREADS) k_fa_starts(const uint8_t* __restrict__ in, uint64_t n,
+                                                          const uint32_t* __restrict__ blockOff, uint64_t* __restrict__ starts) {
+    __shared__ uint32_t sWarp[33];
+    const uint64_t i0 = (static_cast<uint64_t>(blockIdx.x) * FA_THREADS + threadIdx.x) * FA_CHUNK;
+    uint32_t m = i0 < n ? start_mask(in, n, i0) : 0;
+    uint32_t total;
+    uint32_t at = fa_block_excl_scan<FA_THREADS>(__popc(m), &total, sWarp) + blockOff[blockIdx.x];
+    while (m) {
+        const int k = __ffs(m) - 1;
+        m &= m - 1;
+        starts[at++] = i0 + k;
+    }
+}
+
+// first '\n' in [from, to) found by the whole warp, or `to`
+__device__ __forceinline__ uint64_t warp_find_nl(const uint8_t* __restrict__ in, uint64_t from, uint64_t to, int lane) {
+    for (uint64_t base = from; base < to; base += 32) {
+        const uint64_t i = base + lane;
+        const bool hit = i < to && in[i] == '\n';
+        const unsigned b = __ballot_sync(0xFFFFFFFFu, hit);
+        if (b) return base + (__ffs(b) - 1);
+    }
+    return to;
+}
+
+__global__ void __launch_bounds__(FA_THREADS) k_fa_records(const uint8_t* __restrict__ in, uint64_t n,
+                                                           const uint64_t* __restrict__ starts, uint32_t nRecs,
+                                                           FaRecord* __restrict__ recs) {
+    const uint32_t r = (blockIdx.x * FA_THREADS + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (r >= nRecs) return;
+    const uint64_t start = starts[r];
+    const uint64_t regionEnd = r + 1 < nRecs ? starts[r + 1] : n;
+    const uint64_t hdrEnd = warp_find_nl(in, start + 1, regionEnd, lane);  // the header line cannot reach the next record
+    const uint64_t seqStart = hdrEnd + 1 < regionEnd ? hdrEnd + 1 : regionEnd;
+    const uint64_t firstNl = warp_find_nl(in, seqStart, regionEnd, lane);
+    if (lane == 0) {
+        FaRecord rec;
+        rec.start = start;
+        rec.hdrEnd = hdrEnd;
+        rec.regionEnd = regionEnd;
+        rec.firstLine = firstNl - seqStart;
+        rec.endsWithNl = regionEnd > seqStart && in[regionEnd - 1] == '\n';
+        rec.bad = regionEnd > seqStart && firstNl == seqStart;  // the record begins with an empty line (:251)
+        recs[r] = rec;
+    }
+}
+
+// Every byte of a record's sequence region against the layout its first line dictates: a '\n' exactly after every
+// `firstLine` bytes; the last line may be shorter (not empty) and may lack its '\n'.
+__global__ void __launch_bounds__(FA_THREADS) k_fa_check(const uint8_t* __restrict__ in, uint64_t n,
+                                                         const uint64_t* __restrict__ starts, uint32_t nRecs,
+                                                         FaRecord* __restrict__ recs) {
+    const uint64_t i0 = (static_cast<uint64_t>(blockIdx.x) * FA_THREADS + threadIdx.x) * FA_CHUNK;
+    if (i0 >= n) return;
+    uint32_t lo = 0, hi = nRecs;  // starts[lo] <= i0 < starts[hi] (starts[0] == 0)
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (starts[mid] <= i0) lo = mid; else hi = mid;
+    }
+    uint32_t r = lo;
+    const uint4 v = *reinterpret_cast<const uint4*>(in + i0);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint64_t seqStart = 0, len = 0, line = 0, next = 0, m = 0;
+    bool loaded = false, bad = false;
+    for (int k = 0; k < 16 && i0 + k < n; k++) {
+        const uint64_t i = i0 + k;
+        if (loaded && i >= next) {
+            if (bad) recs[r].bad = 1;
+            bad = false;
+            loaded = false;
+            r++;
+        }
+        if (!loaded) {
+            const FaRecord rec = recs[r];
+            seqStart = rec.hdrEnd + 1;
+            next = rec.regionEnd;
+            len = next > seqStart ? next - seqStart : 0;
+            line = rec.firstLine;
+            loaded = true;
+            m = i >= seqStart ? (i - seqStart) % (line + 1) : 0;
+        }
+        if (i < seqStart) continue;
+        const bool nl = static_cast<uint8_t>(w[k >> 2] >> (8 * (k & 3))) == '\n';
+        const bool expect = m == line;
+        const uint64_t o = i - seqStart;
+        if (nl != expect && !(nl && o == len - 1 && m != 0)) bad = true;
+        m = expect ? 0 : m + 1;
+    }
+    if (bad) recs[r].bad = 1;
+}
+
+// out[outOff + k] = in[seqStart + k + k / lineLen]: a thread per 16 output bytes, one 16-byte store
+__global__ void __launch_bounds__(FA_THREADS) k_fa_gather(const uint8_t* __restrict__ in, const FaGather* __restrict__ g,
+                                                          uint32_t nRecs, uint64_t nChunks, uint8_t* __restrict__ out) {
+    const uint64_t c = static_cast<uint64_t>(blockIdx.x) * FA_THREADS + threadIdx.x;
+    if (c >= nChunks) return;
+    uint32_t lo = 0, hi = nRecs;  // g[lo].chunkStart <= c < g[hi].chunkStart
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (g[mid].chunkStart <= c) lo = mid; else hi = mid;
+    }
+    const FaGather rec = g[lo];
+    const uint64_t k0 = (c - rec.chunkStart) * 16;
+    uint64_t q = rec.lineLen ? k0 / rec.lineLen : 0, rem = rec.lineLen ? k0 % rec.lineLen : 0;
+    const uint8_t* src = in + rec.seqStart;
+    uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        if (k0 + j < rec.seqLen) {
+            w[j >> 2] |= static_cast<uint32_t>(src[k0 + j + q]) << (8 * (j & 3));
+            if (++rem == rec.lineLen) {
+                rem = 0;
+                q++;
+            }
+        }
+    }
+    *reinterpret_cast<uint4*>(out + rec.outOff + k0) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+inline uint32_t fa_blocks(uint64_t n) { return static_cast<uint32_t>((n + FA_BLOCK_BYTES - 1) / FA_BLOCK_BYTES); }
+
+}  // namespace
+
+int launch_fa_count(const uint8_t* in, uint64_t n, uint32_t* blockCnt, cudaStream_t st) {
+    const uint32_t blocks = fa_blocks(n);
+    k_fa_count<<<blocks, FA_THREADS, 0, st>>>(in, n, blockCnt);
+    k_fa_scan<<<1, 1024, 0, st>>>(blockCnt, blocks);
+    return 2;
+}
+
+int launch_fa_starts(const uint8_t* in, uint64_t n, const uint32_t* blockOff, uint64_t* starts, cudaStream_t st) {
+    k_fa_starts<<<fa_blocks(n), FA_THREADS, 0, st>>>(in, n, blockOff, starts);
+    return 1;
+}
+
+int launch_fa_records(const uint8_t* in, uint64_t n, const uint64_t* starts, uint32_t nRecs, FaRecord* recs, cudaStream_t st) {
+    const uint32_t warpsPerBlock = FA_THREADS / 32;
+    k_fa_records<<<(nRecs + warpsPerBlock - 1) / warpsPerBlock, FA_THREADS, 0, st>>>(in, n, starts, nRecs, recs);
+    k_fa_check<<<fa_blocks(n), FA_THREADS, 0, st>>>(in, n, starts, nRecs, recs);
+    return 2;
+}
+
+int launch_fa_gather(const uint8_t* in, const FaGather* g, uint32_t nRecs, uint64_t nChunks, uint8_t* out, cudaStream_t st) {
+    if (nChunks == 0) return 0;
+    k_fa_gather<<<static_cast<uint32_t>((nChunks + FA_THREADS - 1) / FA_THREADS), FA_THREADS, 0, st>>>(in, g, nRecs, nChunks, out);
+    return 1;
+}
+
+}  // namespace mbgc_b200

@@ -160,6 +160,7 @@ B200SparseEMMatcher::~B200SparseEMMatcher() {
     if (hMatches) cudaFreeHost(hMatches);
     if (hCounts) cudaFreeHost(hCounts);
     releasePack();
+    releaseIngest();
     for (auto& e : ev) if (e) cudaEventDestroy(e);
     if (stream) cudaStreamDestroy(stream);
     std::free(hostRef);

@@ -16,6 +16,7 @@
 #include "hostpack.hpp"
 #include "kernels.h"
 #include "pack.h"
+#include "ingest.h"
 
 constexpr int MBGCG_T_COUNT_ = 12;  // = MBGCG_T_COUNT of include/mbgc_b200.h (checked in capi.cpp)
 
@@ -28,6 +29,11 @@ struct MatcherError : public std::runtime_error {
 
 struct TextMatch {  // = PgTools::TextMatch, matching/TextMatchers.h:9-17
     uint64_t posSrcText, length, posDestText, nextSrcRegionLoadingPos;
+};
+
+struct FastaRecord {  // one record of an ingested FASTA file (= mbgcg_fasta_rec_t)
+    uint64_t hdrOff, hdrLen;   // header line in the file image, without '>' and without the line end
+    uint64_t textOff, seqLen;  // the sequence in the device text buffer of the ingest
 };
 
 struct TextView {   // one target text (contig / block) of a batch
@@ -104,6 +110,18 @@ public:
     float packMs[4] = {0, 0, 0, 0};       // last pack call: H2D, kernels, D2H, total (CUDA events)
     uint64_t packLaunches = 0;            // kernel launches of the last pack call
     int packSweeps[2] = {0, 0};           // fixed-point sweeps the last pack call needed (removal, pairing)
+
+    // FASTA ingest, kseq_read_lossless_fasta (utils/kseq.h:233-274) for a whole file image: records + DNA line length +
+    // final status, the sequences as a batch of texts in device memory (ingestedTexts(), valid until the next ingest).
+    // ingest.cpp / ingest.cu.
+    void ingestFasta(const char* bytes, uint64_t n);
+    const std::vector<FastaRecord>& ingestedRecords() const { return faRecords; }
+    const void* ingestedTexts() const { return dFaText; }
+    int ingestStatus() const { return faStatus; }                 // -1 end of file, -3 not FASTA, -4 DNA not well-formed
+    uint64_t ingestDnaLineLen() const { return faDnaLineLen; }    // seq->dnaLineLen (UINT64_MAX = DNA_NOT_WELLFORMED)
+    uint64_t ingestMaxLastLineLen() const { return faMaxLastLineLen; }
+    uint64_t ingestLaunches() const { return faLaunches; }
+    void copyIngested(uint64_t record, char* out);                // one sequence back to the host (tests)
 
     // inspection
     void copyTableLow32(uint32_t* out, uint64_t nSlots);
@@ -189,6 +207,16 @@ private:
         uint32_t nMatches = 0;
         std::vector<uint64_t> lens;
     } resident;
+
+    // FASTA ingest (ingest.cpp)
+    void releaseIngest();
+    uint8_t* dFaIn = nullptr; uint64_t dFaInCap = 0;       // file image (16 bytes of padding in front)
+    uint8_t* dFaWork = nullptr; uint64_t dFaWorkCap = 0;   // block counts, record starts, records, gather descriptors
+    uint8_t* dFaText = nullptr; uint64_t dFaTextCap = 0;   // the sequences, batch layout
+    uint8_t* hFaWork = nullptr; uint64_t hFaWorkCap = 0;   // pinned
+    std::vector<FastaRecord> faRecords;
+    int faStatus = -1;
+    uint64_t faDnaLineLen = 0, faMaxLastLineLen = 0, faLaunches = 0;
 
     // K6 (packer.cpp)
     void releasePack();

@@ -95,6 +95,10 @@ def load_library():
     L.mbgcg_pack_kept_matches.restype = C.c_int
     L.mbgcg_pack_kept_matches.argtypes = [vp, C.POINTER(vp), u64p]
     L.mbgcg_pack_timing.argtypes = [vp, C.POINTER(C.c_float), u64p, C.POINTER(C.c_int)]
+    L.mbgcg_ingest_fasta.restype = C.c_int
+    L.mbgcg_ingest_fasta.argtypes = [vp, vp, C.c_uint64, C.POINTER(vp), u64p, C.POINTER(vp), u64p, C.POINTER(C.c_int)]
+    L.mbgcg_copy_ingested.restype = C.c_int
+    L.mbgcg_copy_ingested.argtypes = [vp, C.c_uint64, vp]
     L.mbgcg_acquire_lock.restype = C.c_uint64
     L.mbgcg_acquire_lock.argtypes = [vp]
     L.mbgcg_release_lock.restype = C.c_int
@@ -277,6 +281,26 @@ class Matcher:
         self.lib.mbgcg_pack_timing(self.h, ms, C.byref(launches), sweeps)
         return {"h2d": ms[0], "kernels": ms[1], "d2h": ms[2], "total": ms[3], "launches": launches.value,
                 "sweeps": (sweeps[0], sweeps[1])}
+
+    def ingestFasta(self, data):
+        """kseq_read_lossless_fasta (/root/reference/utils/kseq.h:233-274) over a whole file image on the device
+        (mbgcg_ingest_fasta).  Returns a dict: records = (n, 4) uint64 array (hdrOff, hdrLen, textOff, seqLen), status
+        (-1 end of file, -3 not FASTA, -4 DNA not well-formed), dnaLineLen, dTexts (device pointer of the sequences: pass
+        it with textOff / seqLen to matchBatchDevice)."""
+        a = _as_u8(data)
+        recs, n, dtexts = C.c_void_p(), C.c_uint64(), C.c_void_p()
+        dna, status = C.c_uint64(), C.c_int()
+        self._check(self.lib.mbgcg_ingest_fasta(self.h, a.ctypes.data if a.size else None, a.size, C.byref(recs), C.byref(n),
+                                                C.byref(dtexts), C.byref(dna), C.byref(status)))
+        r = (np.ctypeslib.as_array(C.cast(recs, u64p), shape=(n.value, 4)).copy() if n.value
+             else np.zeros((0, 4), dtype=np.uint64))
+        return {"records": r, "status": status.value, "dnaLineLen": dna.value, "dTexts": dtexts.value}
+
+    def copyIngested(self, record, seqLen):
+        out = np.empty(int(seqLen), dtype=np.uint8)
+        if seqLen:
+            self._check(self.lib.mbgcg_copy_ingested(self.h, record, out.ctypes.data))
+        return out
 
     def acquireWorkerMatchingLockPos(self):
         return self.lib.mbgcg_acquire_lock(self.h)
