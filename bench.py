@@ -56,6 +56,7 @@ def parse_args():
     ap.add_argument("--mode", type=int, default=0, help="MBGC mode the matcher parameters come from (0..3)")
     ap.add_argument("--cpu-sample", type=int, default=100, help="genomes of the batch the CPU baseline is timed on")
     ap.add_argument("--cpu-sample-other", type=int, default=32, help="same for the secondary tier")
+    ap.add_argument("--ingest-genomes", type=int, default=100, help="genomes in the multi-FASTA image of the ingest measurement")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-other-tier", action="store_true", help="skip the secondary similarity tier")
     return ap.parse_args()
@@ -217,6 +218,51 @@ def cpu_pack_stage(base, targets, lists, limit, skip_margin, mode):
     return dt, int(nbytes)
 
 
+def fasta_image(targets, first_index):
+    """the targets as one multi-FASTA file image (80-column lines, the headers of SURVEY.md 8d)"""
+    parts = []
+    for k, t in enumerate(targets):
+        i = first_index + k
+        parts.append(np.frombuffer(f">syn_{i:04d} synthetic E. coli-like genome {i}\n".encode(), dtype=np.uint8))
+        full = t.size // 80 * 80
+        body = np.empty((full // 80, 81), dtype=np.uint8)
+        body[:, :80] = t[:full].reshape(-1, 80)
+        body[:, 80] = 10
+        parts.append(body.reshape(-1))
+        if t.size > full:
+            parts.append(np.concatenate([t[full:], np.array([10], dtype=np.uint8)]))
+    return np.concatenate(parts)
+
+
+def cpu_fasta_reader(image):
+    """the reference's own reader (utils/kseq.h through oracle/_ref/libref_kseq.so; else the oracle port) on one host
+    core over the same file image.  Returns (seconds, kind, records)."""
+    n = image.size
+    ref_so = os.path.join(ROOT, "oracle", "_ref", "libref_kseq.so")
+    cap = 4096
+    recs = np.zeros((cap, 4), dtype=np.uint64)
+    seq = np.empty(n, dtype=np.uint8)
+    dna, mx, st = C.c_uint64(), C.c_uint64(), C.c_int()
+    if os.path.exists(ref_so):
+        L = C.CDLL(ref_so)
+        L.refk_fasta_parse.restype = C.c_uint64
+        L.refk_fasta_parse.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p,
+                                       C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int)]
+        hdr = np.empty(1 << 20, dtype=np.uint8)
+        t0 = time.perf_counter()
+        k = L.refk_fasta_parse(image.ctypes.data, n, recs.ctypes.data, cap, seq.ctypes.data, hdr.ctypes.data,
+                               C.byref(dna), C.byref(mx), C.byref(st))
+        return time.perf_counter() - t0, "reference", int(k)
+    subprocess.run(["make", "-s", "oracle"], cwd=os.path.join(ROOT, "oracle"), check=True)
+    L = C.CDLL(os.path.join(ROOT, "oracle", "libmbgc_oracle.so"))
+    L.mbo_fasta_parse.restype = C.c_uint64
+    L.mbo_fasta_parse.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(C.c_uint64),
+                                  C.POINTER(C.c_uint64), C.POINTER(C.c_int)]
+    t0 = time.perf_counter()
+    k = L.mbo_fasta_parse(image.ctypes.data, n, recs.ctypes.data, cap, seq.ctypes.data, C.byref(dna), C.byref(mx), C.byref(st))
+    return time.perf_counter() - t0, "port", int(k)
+
+
 def workload_name(args):
     return (f"synthetic {args.genomes}-genome E. coli-like collection per GPU ({args.length / 1e6:g} Mbp base + "
             f"SNP/indel mutants, tier {args.tier}), mode {args.mode} matcher parameters")
@@ -372,10 +418,61 @@ def measure_tier(args, tier, rank, world, dist, local):
     pack = {"match_plus_pack_ms_per_step": ms_mp, "pack_ms": pack_tm, "sweeps": list(m.packTiming()["sweeps"]),
             "stream_bytes": pres["stream_bytes"],
             "kept_matches": int(pres["kept"].sum()), "unmatched_chars": int(pres["unmatched"].sum())}
+    # FASTA ingest: the same genomes as one multi-FASTA file image in pinned host memory -> device texts
+    ingest = None
+    if tier == args.tier:
+        ki = max(1, min(args.ingest_genomes, n))
+        image = torch.from_numpy(fasta_image(targets[:ki], 1 + rank * args.genomes)).pin_memory()
+        img = image.numpy()
+        for _ in range(2):
+            m.ingestFasta(img)
+        isteps, tm = max(2, steps // 2), {}
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(isteps):
+            ing = m.ingestFasta(img)
+            for k, v in m.ingestTiming().items():
+                tm[k] = tm.get(k, 0.0) + v / isteps
+        e1.record(stream)
+        barrier()
+        ms_ing = max_over_ranks(e0.elapsed_time(e1), "cuda") / isteps
+        assert ing["status"] == -1 and len(ing["records"]) == ki and ing["dnaLineLen"] == 80
+        assert int(ing["records"][:, 3].sum()) == int(sum(lens[:ki]))
+        ingest = {"what": "kseq_read_lossless_fasta for a whole multi-FASTA file image on the device (ingest.cu): image in "
+                          "pinned host memory -> records + sequences as device texts; H2D of the image inside the timed region",
+                  "genomes": ki, "image_bytes": int(img.size), "ms_per_file": ms_ing, "ms": tm,
+                  "value": img.size * world / (ms_ing / 1e3) / 1e9, "kernels_value": img.size / (tm["kernels"] / 1e3) / 1e9,
+                  "unit": "GB/s", "image": img if rank == 0 else None}
+
+        # the whole hot path from the file image: ingest -> match stage -> stream packing, nothing but the image goes
+        # up and nothing but the six streams (and counts) comes back
+        def pipeline():
+            g = m.ingestFasta(img)
+            recs = g["records"]
+            m.matchBatchDevice(g["dTexts"], recs[:, 2].copy(), recs[:, 3].copy(), 32, fetch=False)
+            return m.packBatch(pd, None, None, loadedPosArr=loaded, lens=recs[:, 3].copy(), raw=True)
+
+        for _ in range(2):
+            pipeline()
+        barrier()
+        e0.record(stream)
+        for _ in range(isteps):
+            pp_res = pipeline()
+        e1.record(stream)
+        barrier()
+        ms_pipe = max_over_ranks(e0.elapsed_time(e1), "cuda") / isteps
+        ingest["pipeline"] = {
+            "what": "file image (pinned host memory) -> FASTA ingest -> match stage -> stream packing -> six streams on the "
+                    "host: the reference's compression path between file read and back-end coder, all on the device",
+            "ms_per_step": ms_pipe, "value": img.size * world / (ms_pipe / 1e3) / 1e9, "unit": "GB/s",
+            "h2d_bytes_per_step": int(img.size), "d2h_bytes_per_step": int(sum(pp_res["stream_bytes"].values())),
+            "kept_matches": int(pp_res["kept"].sum())}
     ks = max(1, min(16, n))
     lists_sample = m.matchBatchDevice(dbuf.data_ptr(), offs[:ks], lens[:ks], 32)  # copies, for the CPU pack baseline
     state = m.state()
     out = dict(base=base, targets=targets, limit=limit, sm=sm, n=n, lens=lens, fbytes=fbytes, index_s=index_s, pack=pack,
+               ingest=ingest,
                lists_sample=lists_sample,
                ms_dev=ms_dev, stage_dev=stage_dev, launches=launches, n_matches=n_matches, counters=counters,
                ms_e2e=ms_e2e, stage_e2e=stage_e2e, table_slots=state["hashSize"], ref_bytes=int(state["pos1"]))
@@ -457,6 +554,13 @@ def run_b200(args, rank, world):
         return p
 
     line["pack"] = pack_report(r, world)
+    if r["ingest"]:
+        image = r["ingest"].pop("image")
+        line["ingest"] = r["ingest"]
+        if rank == 0 and world == 1 and not args.no_cpu:
+            dt, kind, nrec = cpu_fasta_reader(image)
+            line["ingest"]["cpu_baseline"] = {"value": image.size / dt / 1e9, "unit": "GB/s", "cores": 1, "kind": kind,
+                                              "sample": f"the same {image.size / 1e6:.0f} MB image, {nrec} records, {dt * 1e3:.0f} ms"}
     if rank == 0 and world == 1 and not args.no_cpu and r["lists_sample"]:
         k = len(r["lists_sample"])
         dt, nb = cpu_pack_stage(r["base"], r["targets"][:k], r["lists_sample"], r["limit"], r["sm"], args.mode)

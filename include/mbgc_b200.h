@@ -196,6 +196,9 @@ int mbgcg_ingest_fasta(mbgcg_t* h, const char* bytes, uint64_t n, const mbgcg_fa
                        const void** dTexts, uint64_t* dnaLineLen, int* status);
 /* copies sequence `record` of the last ingest to host memory (seqLen bytes) */
 int mbgcg_copy_ingested(mbgcg_t* h, uint64_t record, char* out);
+/* last ingest: ms[0..2] = file image host -> device, kernels (incl. two small host round trips), total (CUDA events);
+ * kernel launches */
+void mbgcg_ingest_timing(const mbgcg_t* h, float ms[3], uint64_t* launches);
 
 /* ---- sliding-window locks (ref .cpp:361-400) ------------------------------------------------------------ */
 uint64_t mbgcg_acquire_lock(mbgcg_t* h);

@@ -207,6 +207,11 @@ int mbgcg_copy_ingested(mbgcg_t* h, uint64_t record, char* out) {
     return guarded(h, [&] { h->m->copyIngested(record, out); });
 }
 
+void mbgcg_ingest_timing(const mbgcg_t* h, float ms[3], uint64_t* launches) {
+    for (int i = 0; i < 3; i++) ms[i] = h->m->faMs[i];
+    if (launches) *launches = h->m->ingestLaunches();
+}
+
 uint64_t mbgcg_acquire_lock(mbgcg_t* h) { return h->m->acquireWorkerMatchingLockPos(); }
 int mbgcg_release_lock(mbgcg_t* h, uint64_t lockValue) {
     return guarded(h, [&] { h->m->releaseWorkerMatchingLockPos(lockValue); });

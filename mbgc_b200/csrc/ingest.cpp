@@ -23,6 +23,8 @@ void B200SparseEMMatcher::releaseIngest() {
     cudaFree(dFaWork);
     cudaFree(dFaText);
     if (hFaWork) cudaFreeHost(hFaWork);
+    for (auto& e : faEv)
+        if (e) cudaEventDestroy(e);
 }
 
 void B200SparseEMMatcher::ingestFasta(const char* bytes, uint64_t n) {
@@ -39,14 +41,19 @@ void B200SparseEMMatcher::ingestFasta(const char* bytes, uint64_t n) {
         return;
     }
     if (n >= (1ull << 40)) throw MatcherError(MBGCG_E_UNSUPPORTED, "FASTA image of 1 TiB or more");
+    if (!faEv[0])
+        for (auto& e : faEv) check(cudaEventCreate(&e), "cudaEventCreate");
+    faMs[0] = faMs[1] = faMs[2] = 0;
 
     // ---- the file image -> device: 16 bytes in front (a '\n' right before byte 0), zeros behind ----
     const uint64_t inBytes = 16 + align_up(n, 16) + 64;
     growDevice(reinterpret_cast<void**>(&dFaIn), &dFaInCap, inBytes, "cudaMalloc(fasta image)");
     uint8_t* in = dFaIn + 16;
+    check(cudaEventRecord(faEv[0], stream), "event");
     check(cudaMemsetAsync(dFaIn, '\n', 16, stream), "memset");
     check(cudaMemsetAsync(in + n, 0, inBytes - 16 - n, stream), "memset");
     check(cudaMemcpyAsync(in, bytes, n, cudaMemcpyHostToDevice, stream), "H2D(fasta image)");
+    check(cudaEventRecord(faEv[1], stream), "event");
 
     // ---- record starts ----
     const uint32_t blocks = static_cast<uint32_t>((n + FA_BLOCK_BYTES - 1) / FA_BLOCK_BYTES);
@@ -134,7 +141,11 @@ void B200SparseEMMatcher::ingestFasta(const char* bytes, uint64_t n) {
         launches += launch_fa_gather(in, dGather, accepted, chunks, dFaText, stream);
     }
     check(cudaGetLastError(), "ingest launch");
+    check(cudaEventRecord(faEv[2], stream), "event");
     check(cudaStreamSynchronize(stream), "ingest sync");
+    check(cudaEventElapsedTime(&faMs[0], faEv[0], faEv[1]), "event time");  // image host -> device
+    check(cudaEventElapsedTime(&faMs[1], faEv[1], faEv[2]), "event time");  // kernels (with the two small host round trips)
+    check(cudaEventElapsedTime(&faMs[2], faEv[0], faEv[2]), "event time");
     faLaunches = static_cast<uint64_t>(launches);
     totalLaunches += faLaunches;
 }

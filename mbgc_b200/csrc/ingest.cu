@@ -51,20 +51,24 @@ __device__ __forceinline__ uint32_t fa_block_excl_scan(uint32_t v, uint32_t* tot
     return res;
 }
 
+// bit k set where byte k of the four equals c (SIMD-in-register compare, then one bit per byte)
+__device__ __forceinline__ uint32_t eq_mask4(uint32_t x, uint32_t c4) {
+    const uint32_t r = __vcmpeq4(x, c4);  // 0xFF per equal byte
+    return (r & 1u) | ((r >> 7) & 2u) | ((r >> 14) & 4u) | ((r >> 21) & 8u);
+}
+__device__ __forceinline__ uint32_t eq_mask16(const uint4& v, uint32_t c4) {
+    return eq_mask4(v.x, c4) | (eq_mask4(v.y, c4) << 4) | (eq_mask4(v.z, c4) << 8) | (eq_mask4(v.w, c4) << 12);
+}
+
 // The 16 bytes at i0 (a multiple of 16; the buffer is 16-byte aligned with a '\n' in front of byte 0 and zeros behind
-// byte n-1) -> bit k set where byte k starts a record.
+// byte n-1) -> bit k set where byte k starts a record: a '>' whose predecessor is a '\n'.
 __device__ __forceinline__ uint32_t start_mask(const uint8_t* __restrict__ in, uint64_t n, uint64_t i0) {
     const uint4 v = *reinterpret_cast<const uint4*>(in + i0);
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-    uint8_t prev = in[static_cast<int64_t>(i0) - 1];
-    uint32_t m = 0;
-#pragma unroll
-    for (int k = 0; k < 16; k++) {
-        const uint8_t b = static_cast<uint8_t>(w[k >> 2] >> (8 * (k & 3)));
-        if (b == '>' && prev == '\n' && i0 + k < n) m |= 1u << k;
-        prev = b;
-    }
-    return m;
+    const uint32_t gt = eq_mask16(v, 0x3E3E3E3Eu);
+    if (gt == 0) return 0;
+    const uint32_t nl = eq_mask16(v, 0x0A0A0A0Au);
+    const uint32_t prevNl = in[static_cast<int64_t>(i0) - 1] == '\n' ? 1u : 0u;
+    return gt & ((nl << 1) | prevNl) & 0xFFFFu;  // (bytes behind n-1 are zeros, never '>')
 }
 
 __global__ void __launch_bounds__(FA_THREADS) k_fa_count(const uint8_t* __restrict__ in, uint64_t n, uint32_t* __restrict__ blockCnt) {
@@ -165,6 +169,18 @@ __global__ void __launch_bounds__(FA_THREADS) k_fa_check(const uint8_t* __restri
     }
     uint32_t r = lo;
     const uint4 v = *reinterpret_cast<const uint4*>(in + i0);
+    {   // the whole chunk inside one record's sequence, lines of 16 bytes or more, the region's last byte not in it:
+        // at most one line end is due in these 16 bytes, compare the masks
+        const FaRecord rec = recs[r];
+        const uint64_t seqStart = rec.hdrEnd + 1;
+        if (i0 >= seqStart && i0 + 16 < rec.regionEnd && rec.firstLine >= 16) {
+            const uint64_t o = i0 - seqStart, period = rec.firstLine + 1;
+            const uint64_t m0 = (o | period) >> 32 ? o % period : static_cast<uint32_t>(o) % static_cast<uint32_t>(period);
+            const uint64_t due = rec.firstLine - m0;
+            if (eq_mask16(v, 0x0A0A0A0Au) != (due < 16 ? 1u << due : 0u)) recs[r].bad = 1;
+            return;
+        }
+    }
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
     uint64_t seqStart = 0, len = 0, line = 0, next = 0, m = 0;
     bool loaded = false, bad = false;
@@ -206,17 +222,20 @@ __global__ void __launch_bounds__(FA_THREADS) k_fa_gather(const uint8_t* __restr
         if (g[mid].chunkStart <= c) lo = mid; else hi = mid;
     }
     const FaGather rec = g[lo];
-    const uint64_t k0 = (c - rec.chunkStart) * 16;
-    uint64_t q = rec.lineLen ? k0 / rec.lineLen : 0, rem = rec.lineLen ? k0 % rec.lineLen : 0;
-    const uint8_t* src = in + rec.seqStart;
+    // sequences are shorter than 4 GiB (checked on the host): 32-bit index arithmetic
+    const uint32_t k0 = static_cast<uint32_t>(c - rec.chunkStart) * 16u;
+    const uint32_t lineLen = static_cast<uint32_t>(rec.lineLen), seqLen = static_cast<uint32_t>(rec.seqLen);
+    uint32_t q = lineLen ? k0 / lineLen : 0, rem = lineLen ? k0 - q * lineLen : 0;
+    const uint8_t* src = in + rec.seqStart + k0 + q;
     uint32_t w[4] = {0, 0, 0, 0};
+    uint32_t skip = 0;  // line ends passed inside this chunk
 #pragma unroll
     for (int j = 0; j < 16; j++) {
-        if (k0 + j < rec.seqLen) {
-            w[j >> 2] |= static_cast<uint32_t>(src[k0 + j + q]) << (8 * (j & 3));
-            if (++rem == rec.lineLen) {
+        if (k0 + j < seqLen) {
+            w[j >> 2] |= static_cast<uint32_t>(src[j + skip]) << (8 * (j & 3));
+            if (++rem == lineLen) {
                 rem = 0;
-                q++;
+                skip++;
             }
         }
     }

@@ -121,6 +121,7 @@ public:
     uint64_t ingestDnaLineLen() const { return faDnaLineLen; }    // seq->dnaLineLen (UINT64_MAX = DNA_NOT_WELLFORMED)
     uint64_t ingestMaxLastLineLen() const { return faMaxLastLineLen; }
     uint64_t ingestLaunches() const { return faLaunches; }
+    float faMs[3] = {0, 0, 0};                                     // last ingest: image H2D, kernels, total (CUDA events)
     void copyIngested(uint64_t record, char* out);                // one sequence back to the host (tests)
 
     // inspection
@@ -215,6 +216,7 @@ private:
     uint8_t* dFaText = nullptr; uint64_t dFaTextCap = 0;   // the sequences, batch layout
     uint8_t* hFaWork = nullptr; uint64_t hFaWorkCap = 0;   // pinned
     std::vector<FastaRecord> faRecords;
+    cudaEvent_t faEv[3] = {};
     int faStatus = -1;
     uint64_t faDnaLineLen = 0, faMaxLastLineLen = 0, faLaunches = 0;
 

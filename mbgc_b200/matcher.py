@@ -97,6 +97,7 @@ def load_library():
     L.mbgcg_pack_timing.argtypes = [vp, C.POINTER(C.c_float), u64p, C.POINTER(C.c_int)]
     L.mbgcg_ingest_fasta.restype = C.c_int
     L.mbgcg_ingest_fasta.argtypes = [vp, vp, C.c_uint64, C.POINTER(vp), u64p, C.POINTER(vp), u64p, C.POINTER(C.c_int)]
+    L.mbgcg_ingest_timing.argtypes = [vp, C.POINTER(C.c_float), u64p]
     L.mbgcg_copy_ingested.restype = C.c_int
     L.mbgcg_copy_ingested.argtypes = [vp, C.c_uint64, vp]
     L.mbgcg_acquire_lock.restype = C.c_uint64
@@ -295,6 +296,12 @@ class Matcher:
         r = (np.ctypeslib.as_array(C.cast(recs, u64p), shape=(n.value, 4)).copy() if n.value
              else np.zeros((0, 4), dtype=np.uint64))
         return {"records": r, "status": status.value, "dnaLineLen": dna.value, "dTexts": dtexts.value}
+
+    def ingestTiming(self):
+        ms = (C.c_float * 3)()
+        launches = C.c_uint64()
+        self.lib.mbgcg_ingest_timing(self.h, ms, C.byref(launches))
+        return {"h2d": ms[0], "kernels": ms[1], "total": ms[2], "launches": launches.value}
 
     def copyIngested(self, record, seqLen):
         out = np.empty(int(seqLen), dtype=np.uint8)
