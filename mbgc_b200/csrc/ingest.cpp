@@ -125,8 +125,9 @@ void B200SparseEMMatcher::ingestFasta(const char* bytes, uint64_t n) {
         if (seqLen >= (1ull << 32)) throw MatcherError(MBGCG_E_UNSUPPORTED, "sequence of 4 GiB or more");
         hGather[accepted] = FaGather{seqStart, cursor, seqLen, seqLen ? line : 0, chunks};
         faRecords.push_back(FastaRecord{rec.start + 1, std::min(rec.hdrEnd, n) - (rec.start + 1), cursor, seqLen});
-        cursor = align_up(cursor + seqLen + TEXT_GAP, 16);
-        chunks += (seqLen + 15) / 16;
+        const uint64_t next = align_up(cursor + seqLen + TEXT_GAP, 16);
+        chunks += (next - cursor) / 16;  // the text and the zero gap behind it: the gather writes both
+        cursor = next;
         accepted++;
     }
     faDnaLineLen = dna;
@@ -135,7 +136,8 @@ void B200SparseEMMatcher::ingestFasta(const char* bytes, uint64_t n) {
     // ---- sequences -> texts ----
     const uint64_t textBytes = cursor + TEXT_TAIL;
     growDevice(reinterpret_cast<void**>(&dFaText), &dFaTextCap, textBytes, "cudaMalloc(ingested texts)");
-    check(cudaMemsetAsync(dFaText, 0, textBytes, stream), "memset(ingested texts)");
+    check(cudaMemsetAsync(dFaText, 0, PAD, stream), "memset(ingested texts, head)");
+    check(cudaMemsetAsync(dFaText + cursor, 0, TEXT_TAIL, stream), "memset(ingested texts, tail)");
     if (accepted) {
         check(cudaMemcpyAsync(dGather, hGather, accepted * sizeof(FaGather), cudaMemcpyHostToDevice, stream), "H2D(gather)");
         launches += launch_fa_gather(in, dGather, accepted, chunks, dFaText, stream);

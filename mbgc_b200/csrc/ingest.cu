@@ -75,8 +75,13 @@ __global__ void __launch_bounds__(FA_THREADS) k_fa_count(const uint8_t* __restri
     __shared__ uint32_t sTot;
     if (threadIdx.x == 0) sTot = 0;
     __syncthreads();
-    const uint64_t i0 = (static_cast<uint64_t>(blockIdx.x) * FA_THREADS + threadIdx.x) * FA_CHUNK;
-    const uint32_t c = i0 < n ? __popc(start_mask(in, n, i0)) : 0;
+    const uint64_t b0 = static_cast<uint64_t>(blockIdx.x) * FA_BLOCK_BYTES;
+    uint32_t c = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < FA_PER_THREAD; k++) {
+        const uint64_t i0 = b0 + (k * FA_THREADS + threadIdx.x) * FA_CHUNK;
+        if (i0 < n) c += __popc(start_mask(in, n, i0));
+    }
     const uint32_t t = __reduce_add_sync(0xFFFFFFFFu, c);
     if ((threadIdx.x & 31) == 0 && t) atomicAdd(&sTot, t);
     __syncthreads();
@@ -110,40 +115,57 @@ __global__ void __launch_bounds__(1024) k_fa_scan(uint32_t* __restrict__ blockCn
 __global__ void __launch_bounds__(FA_THREADS) k_fa_starts(const uint8_t* __restrict__ in, uint64_t n,
                                                           const uint32_t* __restrict__ blockOff, uint64_t* __restrict__ starts) {
     __shared__ uint32_t sWarp[33];
-    const uint64_t i0 = (static_cast<uint64_t>(blockIdx.x) * FA_THREADS + threadIdx.x) * FA_CHUNK;
-    uint32_t m = i0 < n ? start_mask(in, n, i0) : 0;
-    uint32_t total;
-    uint32_t at = fa_block_excl_scan<FA_THREADS>(__popc(m), &total, sWarp) + blockOff[blockIdx.x];
-    while (m) {
-        const int k = __ffs(m) - 1;
-        m &= m - 1;
-        starts[at++] = i0 + k;
+    uint32_t at0 = blockOff[blockIdx.x];
+    if (blockOff[blockIdx.x + 1] == at0) return;  // no record starts in this 16 KiB: nearly every CTA ends here
+    const uint64_t b0 = static_cast<uint64_t>(blockIdx.x) * FA_BLOCK_BYTES;
+    for (uint32_t k = 0; k < FA_PER_THREAD; k++) {  // file order = round k, then thread
+        const uint64_t i0 = b0 + (k * FA_THREADS + threadIdx.x) * FA_CHUNK;
+        uint32_t m = i0 < n ? start_mask(in, n, i0) : 0;
+        uint32_t total;
+        uint32_t at = fa_block_excl_scan<FA_THREADS>(__popc(m), &total, sWarp) + at0;
+        while (m) {
+            const int b = __ffs(m) - 1;
+            m &= m - 1;
+            starts[at++] = i0 + b;
+        }
+        at0 += total;
     }
 }
 
-// first '\n' in [from, to) found by the whole warp, or `to`
-__device__ __forceinline__ uint64_t warp_find_nl(const uint8_t* __restrict__ in, uint64_t from, uint64_t to, int lane) {
-    for (uint64_t base = from; base < to; base += 32) {
-        const uint64_t i = base + lane;
-        const bool hit = i < to && in[i] == '\n';
-        const unsigned b = __ballot_sync(0xFFFFFFFFu, hit);
-        if (b) return base + (__ffs(b) - 1);
+// first '\n' in [from, to) found by the whole CTA (16 bytes per thread and round, 4 KiB per round), or `to`
+__device__ __forceinline__ uint64_t block_find_nl(const uint8_t* __restrict__ in, uint64_t from, uint64_t to,
+                                                  unsigned long long* sPos) {
+    if (threadIdx.x == 0) *sPos = to;
+    __syncthreads();
+    for (uint64_t base = from & ~static_cast<uint64_t>(15); base < to; base += FA_THREADS * FA_CHUNK) {
+        const uint64_t i0 = base + threadIdx.x * FA_CHUNK;
+        uint32_t m = 0;
+        if (i0 < to) {
+            m = eq_mask16(*reinterpret_cast<const uint4*>(in + i0), 0x0A0A0A0Au);
+            if (i0 < from) m &= 0xFFFFu << (from - i0);
+            if (i0 + 16 > to) m &= (1u << (to - i0)) - 1;
+        }
+        if (m) atomicMin(sPos, static_cast<unsigned long long>(i0 + (__ffs(m) - 1)));
+        if (__syncthreads_or(m != 0)) break;
     }
-    return to;
+    __syncthreads();
+    const uint64_t r = *sPos;
+    __syncthreads();
+    return r;
 }
 
+// a CTA per record (a header or a first line can be a whole unwrapped chromosome)
 __global__ void __launch_bounds__(FA_THREADS) k_fa_records(const uint8_t* __restrict__ in, uint64_t n,
                                                            const uint64_t* __restrict__ starts, uint32_t nRecs,
                                                            FaRecord* __restrict__ recs) {
-    const uint32_t r = (blockIdx.x * FA_THREADS + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (r >= nRecs) return;
+    __shared__ unsigned long long sPos;
+    const uint32_t r = blockIdx.x;
     const uint64_t start = starts[r];
     const uint64_t regionEnd = r + 1 < nRecs ? starts[r + 1] : n;
-    const uint64_t hdrEnd = warp_find_nl(in, start + 1, regionEnd, lane);  // the header line cannot reach the next record
+    const uint64_t hdrEnd = block_find_nl(in, start + 1, regionEnd, &sPos);  // the header line cannot reach the next record
     const uint64_t seqStart = hdrEnd + 1 < regionEnd ? hdrEnd + 1 : regionEnd;
-    const uint64_t firstNl = warp_find_nl(in, seqStart, regionEnd, lane);
-    if (lane == 0) {
+    const uint64_t firstNl = block_find_nl(in, seqStart, regionEnd, &sPos);
+    if (threadIdx.x == 0) {
         FaRecord rec;
         rec.start = start;
         rec.hdrEnd = hdrEnd;
@@ -155,19 +177,21 @@ __global__ void __launch_bounds__(FA_THREADS) k_fa_records(const uint8_t* __rest
     }
 }
 
-// Every byte of a record's sequence region against the layout its first line dictates: a '\n' exactly after every
-// `firstLine` bytes; the last line may be shorter (not empty) and may lack its '\n'.
-__global__ void __launch_bounds__(FA_THREADS) k_fa_check(const uint8_t* __restrict__ in, uint64_t n,
-                                                         const uint64_t* __restrict__ starts, uint32_t nRecs,
-                                                         FaRecord* __restrict__ recs) {
-    const uint64_t i0 = (static_cast<uint64_t>(blockIdx.x) * FA_THREADS + threadIdx.x) * FA_CHUNK;
-    if (i0 >= n) return;
-    uint32_t lo = 0, hi = nRecs;  // starts[lo] <= i0 < starts[hi] (starts[0] == 0)
+// index r with key[r] <= x < key[r + 1] (key ascending, key[0] <= x), keys read through `get`
+template <typename F>
+__device__ __forceinline__ uint32_t fa_segment(uint32_t nRecs, uint64_t x, F get) {
+    uint32_t lo = 0, hi = nRecs;
     while (hi - lo > 1) {
         const uint32_t mid = (lo + hi) >> 1;
-        if (starts[mid] <= i0) lo = mid; else hi = mid;
+        if (get(mid) <= x) lo = mid; else hi = mid;
     }
-    uint32_t r = lo;
+    return lo;
+}
+
+// Every byte of a record's sequence region against the layout its first line dictates: a '\n' exactly after every
+// `firstLine` bytes; the last line may be shorter (not empty) and may lack its '\n'.
+__device__ __forceinline__ void check_chunk(const uint8_t* __restrict__ in, uint64_t n, uint64_t i0, uint32_t r,
+                                            FaRecord* __restrict__ recs) {
     const uint4 v = *reinterpret_cast<const uint4*>(in + i0);
     {   // the whole chunk inside one record's sequence, lines of 16 bytes or more, the region's last byte not in it:
         // at most one line end is due in these 16 bytes, compare the masks
@@ -211,35 +235,93 @@ __global__ void __launch_bounds__(FA_THREADS) k_fa_check(const uint8_t* __restri
     if (bad) recs[r].bad = 1;
 }
 
-// out[outOff + k] = in[seqStart + k + k / lineLen]: a thread per 16 output bytes, one 16-byte store
-__global__ void __launch_bounds__(FA_THREADS) k_fa_gather(const uint8_t* __restrict__ in, const FaGather* __restrict__ g,
-                                                          uint32_t nRecs, uint64_t nChunks, uint8_t* __restrict__ out) {
-    const uint64_t c = static_cast<uint64_t>(blockIdx.x) * FA_THREADS + threadIdx.x;
-    if (c >= nChunks) return;
-    uint32_t lo = 0, hi = nRecs;  // g[lo].chunkStart <= c < g[hi].chunkStart
-    while (hi - lo > 1) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (g[mid].chunkStart <= c) lo = mid; else hi = mid;
-    }
-    const FaGather rec = g[lo];
-    // sequences are shorter than 4 GiB (checked on the host): 32-bit index arithmetic
-    const uint32_t k0 = static_cast<uint32_t>(c - rec.chunkStart) * 16u;
-    const uint32_t lineLen = static_cast<uint32_t>(rec.lineLen), seqLen = static_cast<uint32_t>(rec.seqLen);
-    uint32_t q = lineLen ? k0 / lineLen : 0, rem = lineLen ? k0 - q * lineLen : 0;
-    const uint8_t* src = in + rec.seqStart + k0 + q;
-    uint32_t w[4] = {0, 0, 0, 0};
-    uint32_t skip = 0;  // line ends passed inside this chunk
+__global__ void __launch_bounds__(FA_THREADS) k_fa_check(const uint8_t* __restrict__ in, uint64_t n,
+                                                         const uint64_t* __restrict__ starts, uint32_t nRecs,
+                                                         FaRecord* __restrict__ recs) {
+    const uint64_t b0 = static_cast<uint64_t>(blockIdx.x) * FA_BLOCK_BYTES;
+    if (b0 >= n) return;
+    // one search for the CTA's 16 KiB; records are far longer than that, so usually all of it is one record
+    const uint32_t rb = fa_segment(nRecs, b0, [&](uint32_t k) { return starts[k]; });
+    const bool oneRecord = rb + 1 >= nRecs || starts[rb + 1] >= b0 + FA_BLOCK_BYTES;
 #pragma unroll
-    for (int j = 0; j < 16; j++) {
-        if (k0 + j < seqLen) {
+    for (uint32_t k = 0; k < FA_PER_THREAD; k++) {
+        const uint64_t i0 = b0 + (k * FA_THREADS + threadIdx.x) * FA_CHUNK;
+        if (i0 >= n) break;
+        const uint32_t r = oneRecord ? rb : fa_segment(nRecs, i0, [&](uint32_t q) { return starts[q]; });
+        check_chunk(in, n, i0, r, recs);
+    }
+}
+
+// 16 output bytes of a validated record: out[k] = in[seqStart + k + k / lineLen] for k = k0 .. k0 + 15
+__device__ __forceinline__ uint4 gather_chunk(const uint8_t* __restrict__ in, const FaGather& rec, uint32_t k0) {
+    // sequences are shorter than 4 GiB (checked on the host): 32-bit index arithmetic
+    const uint32_t lineLen = static_cast<uint32_t>(rec.lineLen), seqLen = static_cast<uint32_t>(rec.seqLen);
+    const uint32_t q = lineLen ? k0 / lineLen : 0, rem = lineLen ? k0 - q * lineLen : 0;
+    const uint8_t* src = in + rec.seqStart + k0 + q;
+    const uint32_t valid = k0 >= seqLen ? 0 : (seqLen - k0 < 16 ? seqLen - k0 : 16);
+    uint32_t w[4] = {0, 0, 0, 0};
+    if (valid == 0) return make_uint4(0, 0, 0, 0);  // the zero gap behind a text (its chunks belong to the record too)
+    if (lineLen >= 16) {
+        // at most one line end falls inside the chunk: after `e` output bytes the source skips one byte.  24 source bytes
+        // from six aligned words, F = bytes 0.., G = bytes 1..; every output word is F, G or a byte-wise mix of the two.
+        const uintptr_t a = reinterpret_cast<uintptr_t>(src);
+        const uint32_t* p = reinterpret_cast<const uint32_t*>(a & ~static_cast<uintptr_t>(3));
+        const uint32_t sh = static_cast<uint32_t>(a & 3) * 8;
+        uint32_t x[6];
+#pragma unroll
+        for (int i = 0; i < 6; i++) x[i] = __ldg(p + i);
+        uint32_t F[5];
+#pragma unroll
+        for (int i = 0; i < 5; i++) F[i] = __funnelshift_r(x[i], x[i + 1], sh);
+        const uint32_t e = lineLen - rem;  // output bytes before the line end (>= 16: none inside)
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint32_t G = __funnelshift_r(F[i], F[i + 1], 8);
+            const uint32_t lo = 4u * i;
+            if (e >= lo + 4) w[i] = F[i];
+            else if (e <= lo) w[i] = G;
+            else {
+                const uint32_t keep = (1u << (8 * (e - lo))) - 1;
+                w[i] = (F[i] & keep) | (G & ~keep);
+            }
+        }
+        if (valid < 16) {  // the record's last chunk: zeros behind the sequence
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const uint32_t lo = 4u * i;
+                if (valid <= lo) w[i] = 0;
+                else if (valid < lo + 4) w[i] &= (1u << (8 * (valid - lo))) - 1;
+            }
+        }
+    } else {  // short lines: byte by byte
+        uint32_t r2 = rem, skip = 0;
+        for (uint32_t j = 0; j < valid; j++) {
             w[j >> 2] |= static_cast<uint32_t>(src[j + skip]) << (8 * (j & 3));
-            if (++rem == lineLen) {
-                rem = 0;
+            if (++r2 == lineLen) {
+                r2 = 0;
                 skip++;
             }
         }
     }
-    *reinterpret_cast<uint4*>(out + rec.outOff + k0) = make_uint4(w[0], w[1], w[2], w[3]);
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// a thread per 4 x 16 output bytes, 16-byte stores into the batch layout
+__global__ void __launch_bounds__(FA_THREADS) k_fa_gather(const uint8_t* __restrict__ in, const FaGather* __restrict__ g,
+                                                          uint32_t nRecs, uint64_t nChunks, uint8_t* __restrict__ out) {
+    const uint64_t c0 = static_cast<uint64_t>(blockIdx.x) * (FA_THREADS * FA_PER_THREAD);
+    if (c0 >= nChunks) return;
+    const uint32_t rb = fa_segment(nRecs, c0, [&](uint32_t k) { return g[k].chunkStart; });
+    const bool oneRecord = rb + 1 >= nRecs || g[rb + 1].chunkStart >= c0 + FA_THREADS * FA_PER_THREAD;
+    FaGather rec = g[rb];
+#pragma unroll
+    for (uint32_t k = 0; k < FA_PER_THREAD; k++) {
+        const uint64_t c = c0 + k * FA_THREADS + threadIdx.x;
+        if (c >= nChunks) break;
+        if (!oneRecord) rec = g[fa_segment(nRecs, c, [&](uint32_t q) { return g[q].chunkStart; })];
+        const uint32_t k0 = static_cast<uint32_t>(c - rec.chunkStart) * 16u;
+        *reinterpret_cast<uint4*>(out + rec.outOff + k0) = gather_chunk(in, rec, k0);
+    }
 }
 
 inline uint32_t fa_blocks(uint64_t n) { return static_cast<uint32_t>((n + FA_BLOCK_BYTES - 1) / FA_BLOCK_BYTES); }
@@ -259,15 +341,15 @@ int launch_fa_starts(const uint8_t* in, uint64_t n, const uint32_t* blockOff, ui
 }
 
 int launch_fa_records(const uint8_t* in, uint64_t n, const uint64_t* starts, uint32_t nRecs, FaRecord* recs, cudaStream_t st) {
-    const uint32_t warpsPerBlock = FA_THREADS / 32;
-    k_fa_records<<<(nRecs + warpsPerBlock - 1) / warpsPerBlock, FA_THREADS, 0, st>>>(in, n, starts, nRecs, recs);
+    k_fa_records<<<nRecs, FA_THREADS, 0, st>>>(in, n, starts, nRecs, recs);
     k_fa_check<<<fa_blocks(n), FA_THREADS, 0, st>>>(in, n, starts, nRecs, recs);
     return 2;
 }
 
 int launch_fa_gather(const uint8_t* in, const FaGather* g, uint32_t nRecs, uint64_t nChunks, uint8_t* out, cudaStream_t st) {
     if (nChunks == 0) return 0;
-    k_fa_gather<<<static_cast<uint32_t>((nChunks + FA_THREADS - 1) / FA_THREADS), FA_THREADS, 0, st>>>(in, g, nRecs, nChunks, out);
+    const uint64_t perBlock = static_cast<uint64_t>(FA_THREADS) * FA_PER_THREAD;
+    k_fa_gather<<<static_cast<uint32_t>((nChunks + perBlock - 1) / perBlock), FA_THREADS, 0, st>>>(in, g, nRecs, nChunks, out);
     return 1;
 }
 

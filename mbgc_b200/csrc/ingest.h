@@ -11,8 +11,9 @@
 namespace mbgc_b200 {
 
 constexpr int FA_THREADS = 256;
-constexpr uint32_t FA_CHUNK = 16;                       // input bytes per thread
-constexpr uint32_t FA_BLOCK_BYTES = FA_THREADS * FA_CHUNK;
+constexpr uint32_t FA_CHUNK = 16;                       // bytes per load / store
+constexpr uint32_t FA_PER_THREAD = 4;                   // chunks per thread, FA_THREADS * FA_CHUNK apart (coalesced)
+constexpr uint32_t FA_BLOCK_BYTES = FA_THREADS * FA_CHUNK * FA_PER_THREAD;  // 16 KiB of the file per CTA
 
 struct FaRecord {          // per record, filled by k_fa_records / k_fa_check (device) and read by the host
     uint64_t start;        // position of '>'

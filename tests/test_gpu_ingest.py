@@ -83,3 +83,17 @@ def test_big_file_roundtrip(matcher):
     for k, s in enumerate(seqs):
         assert int(got["records"][k][3]) == len(s)
         assert bytes(matcher.copyIngested(k, len(s))) == s
+
+
+def test_unwrapped_records(matcher):
+    """single-line (unwrapped) sequences of a few MB and a very long header: the record scan is a CTA-wide search"""
+    rng = np.random.default_rng(6)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    seqs = [bytes(acgt[rng.integers(0, 4, n)]) for n in (3_000_001, 17, 2_500_000)]
+    hdrs = [b"h" * 70_000, b"short", b""]
+    data = b"".join(b">" + h + b"\n" + s + b"\n" for h, s in zip(hdrs, seqs))[:-1]   # no trailing newline
+    want, wdna, _, wstatus = oracle_parse(data)
+    got = matcher.ingestFasta(data)
+    assert (got["status"], got["dnaLineLen"], len(got["records"])) == (wstatus, wdna, len(want)) == (-1, 0, 3)
+    for k, ((h_off, h_len, _, s_len), (whdr, wseq)) in enumerate(zip(got["records"], want)):
+        assert data[int(h_off):int(h_off + h_len)] == whdr and bytes(matcher.copyIngested(k, s_len)) == wseq
