@@ -1119,6 +1119,7 @@ struct ExtendArgs {
     const uint32_t* runFirst;
     const uint32_t* runStart;
     RunRec* runs;
+    uint8_t* runLink;
     const uint32_t* counters;
 };
 
@@ -1150,32 +1151,46 @@ __global__ void __launch_bounds__(256) k_extend(const ExtendArgs a) {
         int cls;
         window_ok(static_cast<uint64_t>(s0), K, a.ix.pos1, swStop, cls);
 
-        // ---- bounds: the neighbour run's verified span when it continues this diagonal
+        // ---- bounds: the verified span of the nearest run (within LINK_WINDOW) that continues this diagonal.  When the
+        // reference holds several similar copies of a region, seeds of their diagonals interleave in position order and
+        // the neighbour on the same diagonal is a few runs away, not adjacent; without it every run would walk the whole
+        // equal interval again.
         bool leftCand = false;
+        uint32_t linkBack = 0, linkAhead = 0;
         int64_t stopL = d < 0 ? -d : 0;  // target position below which nothing is compared (ref index >= 0)
-        if (r > rs) {
-            const uint32_t nm1 = sPrev.n - 1u;  // last seed of the previous segment
-            const uint32_t pp = sPrev.pos + nm1 * static_cast<uint32_t>(k1);
-            const int64_t sp = static_cast<int64_t>(decode_pos(sPrev.enc + nm1 * encStep, a.ix.k1ord));
+        for (uint32_t k = 1; k <= LINK_WINDOW && r >= rs + k; k++) {
+            const SeedRec sp_ = k == 1 ? sPrev : a.seeds[a.runFirst[r - k + 1] - 1];  // last segment of run r - k
+            const uint32_t nm1 = sp_.n - 1u;  // its last seed
+            const uint32_t pp = sp_.pos + nm1 * static_cast<uint32_t>(k1);
+            const int64_t sp = static_cast<int64_t>(decode_pos(sp_.enc + nm1 * encStep, a.ix.k1ord));
+            if (sp - static_cast<int64_t>(pp) != d) continue;
             int clsP;
             window_ok(static_cast<uint64_t>(sp), K, a.ix.pos1, swStop, clsP);
-            if (sp - static_cast<int64_t>(pp) == d && clsP == cls) {
+            if (clsP == cls) {
                 leftCand = true;
-                stopL = static_cast<int64_t>(pp) + K;  // end of the previous run's verified span
+                linkBack = k;
+                stopL = static_cast<int64_t>(pp) + K;  // end of that run's verified span
+                break;
             }
         }
         const int64_t refCap = static_cast<int64_t>(a.ix.refLen);
         int64_t stopR = N2;  // exclusive target bound
         if (refCap - d < stopR) stopR = refCap - d;
         bool rightCand = false;
-        if (r + 1 < re) {
-            const uint32_t np = sNext.pos;
-            const int64_t sn = static_cast<int64_t>(decode_pos(sNext.enc, a.ix.k1ord));
+        for (uint32_t k = 1; k <= LINK_WINDOW && r + k < re; k++) {
+            const SeedRec sn_ = k == 1 ? sNext : a.seeds[a.runFirst[r + k]];  // first segment of run r + k
+            const uint32_t np = sn_.pos;
+            const int64_t sn = static_cast<int64_t>(decode_pos(sn_.enc, a.ix.k1ord));
+            if (sn - static_cast<int64_t>(np) != d) continue;
             int clsN;
             window_ok(static_cast<uint64_t>(sn), K, a.ix.pos1, swStop, clsN);
-            if (sn - static_cast<int64_t>(np) == d && clsN == cls && static_cast<int64_t>(np) <= stopR) {
-                rightCand = true;
-                stopR = np;
+            if (clsN == cls) {
+                if (static_cast<int64_t>(np) <= stopR) {
+                    rightCand = true;
+                    linkAhead = k;
+                    stopR = np;
+                }
+                break;
             }
         }
 
@@ -1269,6 +1284,7 @@ __global__ void __launch_bounds__(256) k_extend(const ExtendArgs a) {
             rec.bFree = static_cast<uint32_t>(mismR);
             rec.flags = (leftLinked ? 1u : 0u) | (rightLinked ? 2u : 0u) | (c << 2);
             a.runs[r] = rec;
+            a.runLink[r] = static_cast<uint8_t>((leftLinked ? linkBack : 0u) | ((rightLinked ? linkAhead : 0u) << 4));
         }
     }
 }
@@ -1276,28 +1292,38 @@ __global__ void __launch_bounds__(256) k_extend(const ExtendArgs a) {
 // Link chains (adjacent runs on one diagonal whose gap compared equal) share one maximal interval: copy the
 // chain's left end forward and its right end backward so that K5 reads final values.  Every run belongs to
 // exactly one chain and only the thread of the chain end (start) walks it: no races.
-__global__ void __launch_bounds__(256) k_links(RunRec* __restrict__ runs, const uint32_t* counters) {
+__global__ void __launch_bounds__(256) k_links(RunRec* __restrict__ runs, const uint8_t* __restrict__ runLink,
+                                               const uint32_t* counters) {
     if (counters[3]) return;
     const uint32_t nRuns = counters[1];
     for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < nRuns; r += gridDim.x * blockDim.x) {
-        const uint32_t fl = runs[r].flags;
-        if (!(fl & 2u) && (fl & 1u)) {  // chain end (chains have >= 2 runs): push bFree backward
+        const uint32_t lk = runLink[r];
+        const uint32_t back = lk & 15u, ahead = lk >> 4;
+        if (!ahead && back) {  // chain end (chains have >= 2 runs): push bFree backward
             const uint32_t b = runs[r].bFree;
-            uint32_t q = r;
-            while (runs[q].flags & 1u) runs[--q].bFree = b;  // a left-linked run always has a predecessor
+            uint32_t q = r, step = back;
+            while (step) {  // a left-linked run always has its predecessor `step` runs back
+                q -= step;
+                runs[q].bFree = b;
+                step = runLink[q] & 15u;
+            }
         }
-        if (!(fl & 1u) && (fl & 2u)) {  // chain start: push aFree forward
+        if (!back && ahead) {  // chain start: push aFree forward
             const uint32_t a = runs[r].aFree;
-            uint32_t q = r;
-            while (runs[q].flags & 2u) runs[++q].aFree = a;
+            uint32_t q = r, step = ahead;
+            while (step) {
+                q += step;
+                runs[q].aFree = a;
+                step = runLink[q] >> 4;
+            }
         }
     }
 }
 
 int launch_extend(const IndexState& ix, const BatchDesc& b, const WorkBuffers& w, cudaStream_t st) {
-    ExtendArgs a{ix, b, w.seeds, w.runFirst, w.runStart, w.runs, w.counters};
+    ExtendArgs a{ix, b, w.seeds, w.runFirst, w.runStart, w.runs, w.runLink, w.counters};
     k_extend<<<device_sm_count() * 8, 256, 0, st>>>(a);
-    k_links<<<device_sm_count() * 4, 256, 0, st>>>(w.runs, w.counters);
+    k_links<<<device_sm_count() * 4, 256, 0, st>>>(w.runs, w.runLink, w.counters);
     return 2;
 }
 
@@ -1540,6 +1566,21 @@ __global__ void __launch_bounds__(128) k_resolve(const ResolveArgs a) {
             const int64_t aRes = run.aFree;  // link chains already resolved by k_links
             const int64_t firstPos = run.firstPos;
             const int64_t lastPos = firstPos + static_cast<int64_t>(run.nSeeds - 1) * k1;
+            if (lastPos < cur) {
+                // Behind the cursor (inside the match just accepted).  With several similar copies in the reference an
+                // island holds thousands of such runs: look at sixteen at a time, their loads in flight together.
+                while (r + 16 < re) {
+                    bool ahead = false;
+#pragma unroll
+                    for (int k = 1; k <= 16; k++) {
+                        const RunRec& q = a.runs[r + k];
+                        ahead |= static_cast<int64_t>(q.firstPos) + static_cast<int64_t>(q.nSeeds - 1) * k1 >= cur;
+                    }
+                    if (ahead) break;
+                    r += 16;
+                }
+                continue;
+            }
             while (lastPos >= cur) {
                 int64_t i = firstPos;
                 if (cur > i) {  // first seed of the run at or after the cursor (32-bit math: targets are < 4 GiB)

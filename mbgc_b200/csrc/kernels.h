@@ -21,6 +21,7 @@ constexpr uint32_t PROBE_FILTER_BYTES = 192 * 1024; // first-level filter, copie
 constexpr uint32_t PROBE_FILTER_BITS = PROBE_FILTER_BYTES * 8;
 constexpr uint32_t ANCHOR_STRIDE = 8;               // fast path: one diagonal proposal per 8 chunks (and per contig start)
 constexpr uint64_t NO_LOCK = UINT64_MAX;
+constexpr uint32_t LINK_WINDOW = 12;                // K4 looks this many runs back / ahead for the same diagonal (< 16)
 
 struct RunRec {          // one seed run = consecutive seeds on one diagonal, spacing k1 (24 bytes)
     uint32_t firstPos;   // target position of the first seed
@@ -90,6 +91,7 @@ struct WorkBuffers {     // device scratch of one pass
     uint32_t* headScan;      // [seedCap+2] run-head flags -> scan; later the island-head flag of every run
     uint32_t* runFirst;      // [seedCap+2] first segment of every run; later matches per island -> scan
     RunRec* runs;            // [seedCap]
+    uint8_t* runLink;        // [seedCap] distance to the linked run on the same diagonal: low nibble back, high nibble ahead
     uint32_t* runStart;      // [nContigs+1]
     MatchRec* matches;       // [seedCap] per-island regions at the island's first run
     unsigned long long* islandFwd;  // [seedCap/1024+2] per-tile carries of the island scans

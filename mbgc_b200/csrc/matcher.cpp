@@ -341,6 +341,7 @@ void B200SparseEMMatcher::ensureWork(uint64_t textBytes, uint32_t nTiles, int nC
     const uint64_t oHeadScan = carve((static_cast<uint64_t>(seedCap) + 2) * 4);
     const uint64_t oRunFirst = carve((static_cast<uint64_t>(seedCap) + 2) * 4);
     const uint64_t oRuns = carve(static_cast<uint64_t>(seedCap) * sizeof(RunRec));
+    const uint64_t oRunLink = carve(static_cast<uint64_t>(seedCap) + 16);
     const uint64_t oRunStart = carve((static_cast<uint64_t>(nContigs) + 2) * 4);
     const uint64_t oMatches = carve(static_cast<uint64_t>(seedCap) * sizeof(MatchRec));
     const uint64_t oIslandFwd = carve((static_cast<uint64_t>(seedCap) / 1024 + 4) * 8);
@@ -373,6 +374,7 @@ void B200SparseEMMatcher::ensureWork(uint64_t textBytes, uint32_t nTiles, int nC
     wb.headScan = reinterpret_cast<uint32_t*>(dWork + oHeadScan);
     wb.runFirst = reinterpret_cast<uint32_t*>(dWork + oRunFirst);
     wb.runs = reinterpret_cast<RunRec*>(dWork + oRuns);
+    wb.runLink = dWork + oRunLink;
     wb.runStart = reinterpret_cast<uint32_t*>(dWork + oRunStart);
     wb.matches = reinterpret_cast<MatchRec*>(dWork + oMatches);
     wb.islandFwd = reinterpret_cast<unsigned long long*>(dWork + oIslandFwd);
