@@ -214,7 +214,9 @@ def compress_speculative(matcher, files, pack_params, window, device="cpu", min_
     appended between files only move the loading cursor over bytes that are zero anyway, so a window of contigs
     (across file boundaries) is matched AND packed in parallel against the frozen state; results are committed in
     order up to and including the first contig that extends the reference; the extension is broadcast and applied on
-    every replica and the rest of the window is processed again.  Every rank passes the same `files`.
+    every replica and the rest of the window is processed again.  Every rank passes the same `files`.  `window` is the
+    largest number of contigs matched speculatively; the actual window follows the commit rate, so a divergent
+    collection (every contig extends the reference) costs a few contigs per round instead of the whole window.
 
     Returns ({stream name: bytes}, stats) -- identical on every rank and byte-identical to the sequential schedule
     (tests/seq_schedule.py::encode_streams, which reproduces the reference's own stream dumps).  The literal stream
@@ -239,8 +241,9 @@ def compress_speculative(matcher, files, pack_params, window, device="cpu", min_
 
     next_file = 0
     done = 0
+    cur_window = window
     while done < len(flat):
-        hi = min(len(flat), done + window)
+        hi = min(len(flat), done + cur_window)
         spans = [shard_range(hi - done, r, world) for r in range(world)]
         b, e = spans[rank]
         mine = [files[fi][ci] for fi, ci in flat[done + b:done + e]]
@@ -276,6 +279,9 @@ def compress_speculative(matcher, files, pack_params, window, device="cpu", min_
                 break
         stats["repacked"] += (hi - done) - committed
         done += committed
+        # speculation that fails is wasted work: follow the commit rate (twice what the last round committed, at least
+        # one contig per rank, at most the caller's window); identical on every rank, so the schedule stays in lock step
+        cur_window = max(world, min(window, 2 * committed))
     while next_file < len(files):
         close_file()
         next_file += 1
