@@ -232,6 +232,11 @@ int mbgcg_copy_staged_text(mbgcg_t* h, uint64_t textIndex, char* out);
  * packed (such a block travels raw; out is then untouched). */
 int mbgcg_selftest_pack(const char* text, uint64_t n, char* out);
 
+/* Host-only self-test of the reverse complement mbgcg_load_ref writes for loadRC (no device needed):
+ * out[n - 1 - i] = complement(text[i]) with the table of /root/reference/utils/helper.cpp:312-358 (upper-casing, IUPAC,
+ * everything else unchanged, 0x7F -> 0), i.e. upperReverseComplement (:405-410). */
+void mbgcg_selftest_revcomp(const char* text, uint64_t n, char* out);
+
 /* Stage timings of the last match call, CUDA events on the handle's stream, milliseconds. */
 enum {
     MBGCG_T_H2D = 0,      /* host->device copy of the texts */

@@ -259,6 +259,10 @@ int mbgcg_copy_staged_text(mbgcg_t* h, uint64_t textIndex, char* out) {
     return guarded(h, [&] { h->m->copyStagedText(textIndex, out); });
 }
 
+void mbgcg_selftest_revcomp(const char* text, uint64_t n, char* out) {
+    B200SparseEMMatcher::selftestReverseComplement(reinterpret_cast<const uint8_t*>(text), n, reinterpret_cast<uint8_t*>(out));
+}
+
 int mbgcg_selftest_pack(const char* text, uint64_t n, char* out) {
     std::vector<mbgc_b200::ExcRun> runs;
     std::vector<uint8_t> packed((n + 3) / 4 + 16);

@@ -111,6 +111,67 @@ bool pack_block(const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t devOff, s
     return pack_scalar(src, n, dst, devOff, runs, maxRuns, 0);
 }
 
+// ---- reverse complement ----------------------------------------------------------------------------------
+
+namespace {
+
+// letters[i] = what 0x40 + i and 0x60 + i map to (0 = both stay as they are); false if the table is not of that shape
+bool letter_table(const uint8_t lut[256], uint8_t letters[32]) {
+    for (int i = 0; i < 256; i++) {
+        const bool letterRange = (i & 0xC0) == 0x40;
+        if (!letterRange && lut[i] != i) return false;
+    }
+    for (int i = 0; i < 32; i++) {
+        const int up = 0x40 + i, lo = 0x60 + i;
+        if (lo == 0x7F) {  // the table's hole: 0x7F -> 0 (handled separately); its upper partner must be identity
+            if (lut[lo] != 0 || lut[up] != up) return false;
+            letters[i] = 0;
+            continue;
+        }
+        if (lut[up] == up && lut[lo] == lo) letters[i] = 0;
+        else if (lut[up] == lut[lo] && lut[up] != 0) letters[i] = lut[up];
+        else return false;
+    }
+    return true;
+}
+
+__attribute__((target("avx2"))) void revcomp_avx2(const uint8_t* src, uint64_t n, uint8_t* dst, const uint8_t lut[256],
+                                                  const uint8_t letters[32]) {
+    const __m256i tblLo = _mm256_broadcastsi128_si256(_mm_loadu_si128(reinterpret_cast<const __m128i*>(letters)));
+    const __m256i tblHi = _mm256_broadcastsi128_si256(_mm_loadu_si128(reinterpret_cast<const __m128i*>(letters + 16)));
+    const __m256i rev = _mm256_setr_epi8(15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1, 0,  //
+                                         15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1, 0);
+    const __m256i c40 = _mm256_set1_epi8(0x40), cC0 = _mm256_set1_epi8(static_cast<char>(0xC0));
+    const __m256i c0F = _mm256_set1_epi8(0x0F), c7F = _mm256_set1_epi8(0x7F), zero = _mm256_setzero_si256();
+    uint64_t i = 0;
+    for (; i + 32 <= n; i += 32) {
+        const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i));
+        const __m256i inRange = _mm256_cmpeq_epi8(_mm256_and_si256(v, cC0), c40);
+        const __m256i nib = _mm256_and_si256(v, c0F);
+        const __m256i lo = _mm256_shuffle_epi8(tblLo, nib), hi = _mm256_shuffle_epi8(tblHi, nib);
+        const __m256i t = _mm256_blendv_epi8(lo, hi, _mm256_slli_epi16(v, 3));  // bit 4 of the byte -> bit 7: upper half
+        const __m256i use = _mm256_andnot_si256(_mm256_cmpeq_epi8(t, zero), inRange);
+        __m256i c = _mm256_blendv_epi8(v, t, use);
+        c = _mm256_andnot_si256(_mm256_cmpeq_epi8(v, c7F), c);  // 0x7F -> 0
+        c = _mm256_shuffle_epi8(c, rev);
+        c = _mm256_permute2x128_si256(c, c, 1);
+        _mm256_storeu_si256(reinterpret_cast<__m256i*>(dst + (n - 32 - i)), c);
+    }
+    for (; i < n; i++) dst[n - 1 - i] = lut[src[i]];
+}
+
+}  // namespace
+
+void reverse_complement(const uint8_t* src, uint64_t n, uint8_t* dst, const uint8_t lut[256]) {
+    static const bool haveAvx2 = __builtin_cpu_supports("avx2");
+    uint8_t letters[32];
+    if (haveAvx2 && n >= 64 && letter_table(lut, letters)) {
+        revcomp_avx2(src, n, dst, lut, letters);
+        return;
+    }
+    for (uint64_t i = 0; i < n; i++) dst[n - 1 - i] = lut[src[i]];
+}
+
 // ---- worker pool ---------------------------------------------------------------------------------------
 
 WorkerPool::WorkerPool(int nThreads) {

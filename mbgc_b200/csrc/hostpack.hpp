@@ -31,6 +31,12 @@ struct ExcRun {          // a run of identical non-ACGT bytes, device layout (16
 // then undefined -- as soon as more than maxRuns runs would be needed.
 bool pack_block(const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t devOff, std::vector<ExcRun>& runs, size_t maxRuns);
 
+// dst[n - 1 - i] = lut[src[i]]: the reverse complement the reference computes with upperReverseComplement
+// (utils/helper.cpp:405-410) through its 256-entry table (:312-358).  AVX2 where the CPU has it and the table has the
+// shape of that LUT (identity except letters, both cases of a letter mapping to one upper-case letter, 0x7F); plain loop
+// otherwise.  src and dst must not overlap.
+void reverse_complement(const uint8_t* src, uint64_t n, uint8_t* dst, const uint8_t lut[256]);
+
 // Minimal persistent worker pool: run(nItems, fn) calls fn(item, worker) for every item, items handed out in
 // index order; returns immediately, wait() blocks until all items are done.  done(i) tells whether item i is.
 class WorkerPool {

@@ -1528,7 +1528,7 @@ struct ResolveArgs {
     const uint32_t* isHead;
     MatchRec* matches;
     uint32_t* matchCountRun;  // [nRuns+1] matches of the island starting at this run (0 for other runs)
-    const uint32_t* counters;
+    uint32_t* counters;          // 1 nRuns, 3 overflow (read); 4 longest island, 5 islands (diagnostics, written)
     uint32_t minMatchLength;
 };
 
@@ -1551,8 +1551,21 @@ __global__ void __launch_bounds__(128) k_resolve(const ResolveArgs a) {
             a.matchCountRun[rs] = 0;
             continue;
         }
-        uint32_t re = rs + 1;  // island = runs [rs, re)
-        while (re < nRuns && !a.isHead[re]) re++;
+        uint32_t re = rs + 1;  // island = runs [rs, re): up to the next head, sixteen flags per step (loads in flight together)
+        while (re < nRuns) {
+            uint32_t heads = 0;
+#pragma unroll
+            for (int k = 0; k < 16; k++)
+                if (re + k < nRuns && a.isHead[re + k]) heads |= 1u << k;
+            if (heads) {
+                re += __ffs(heads) - 1;
+                break;
+            }
+            re += 16;
+        }
+        if (re > nRuns) re = nRuns;
+        atomicAdd(&a.counters[5], 1u);              // islands of the pass, and the longest one (diagnostics)
+        atomicMax(&a.counters[4], re - rs);
         const uint32_t c = a.runs[rs].flags >> 2;
         const uint64_t lock = a.b.contigLock ? a.b.contigLock[c] : NO_LOCK;
         const int64_t swStop = lock != NO_LOCK ? static_cast<int64_t>(lock) : pos1;

@@ -72,6 +72,10 @@ void calc_coprimes(int L, int K, int& k1, int& k2) {
 
 }  // namespace
 
+void B200SparseEMMatcher::selftestReverseComplement(const uint8_t* src, uint64_t n, uint8_t* dst) {
+    reverse_complement(src, n, dst, g_lut.t);
+}
+
 void B200SparseEMMatcher::check(cudaError_t e, const char* what) {
     if (e != cudaSuccess)
         throw MatcherError(MBGCG_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
@@ -207,7 +211,7 @@ void B200SparseEMMatcher::loadSegment(const char* text, uint64_t len, bool rc, b
         char* dst = hostRef + pos1;
         if (rc) {
             const uint8_t* src = reinterpret_cast<const uint8_t*>(text) + len - tmpLen;
-            for (uint64_t i = 0; i < tmpLen; i++) dst[tmpLen - 1 - i] = static_cast<char>(g_lut.t[src[i]]);
+            reverse_complement(src, tmpLen, reinterpret_cast<uint8_t*>(dst), g_lut.t);
         } else
             std::memcpy(dst, text, tmpLen);
         const bool sepHit = addSep && static_cast<uint64_t>(pos1) + tmpLen == swEnd;
@@ -800,6 +804,8 @@ void B200SparseEMMatcher::matchBatch(const std::vector<TextView>& texts, const u
                 seedCap = static_cast<uint32_t>(std::min<uint64_t>(positions + 65536, 0xFFFFFFF0ull));
                 continue;
             }
+            if (std::getenv("MBGC_B200_TRACE_ISLANDS"))
+                fprintf(stderr, "[mbgc_b200] pass: %u runs, %u islands, longest %u runs\n", hCtr[1], hCtr[5], hCtr[4]);
             const uint32_t total = hOffs[nC];
             if (!listsStayOnDevice) matchGuess = static_cast<uint64_t>(total) + total / 64 + 1024;
             const uint32_t fetched = listsStayOnDevice ? static_cast<uint32_t>(std::min<uint64_t>(guess, total)) : total;

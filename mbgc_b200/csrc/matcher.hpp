@@ -124,6 +124,9 @@ public:
     float faMs[3] = {0, 0, 0};                                     // last ingest: image H2D, kernels, total (CUDA events)
     void copyIngested(uint64_t record, char* out);                // one sequence back to the host (tests)
 
+    // host-only: the reverse complement loadRef writes for loadRCRef (utils/helper.cpp:405-410 with the table of :312-358)
+    static void selftestReverseComplement(const uint8_t* src, uint64_t n, uint8_t* dst);
+
     // inspection
     void copyTableLow32(uint32_t* out, uint64_t nSlots);
     void copyDeviceRef(uint64_t from, uint64_t n, char* out);

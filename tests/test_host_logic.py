@@ -123,6 +123,30 @@ def test_rc_lut_matches_reference_quirks():
     assert lut[0x7F] == 0 and lut[0] == 0 and lut[ord("X")] == ord("X") and lut[200] == 200
 
 
+def test_vector_reverse_complement_equals_oracle():
+    """the AVX2 reverse complement loadRef uses (mbgc_b200/csrc/hostpack.cpp) against the oracle's restatement of
+    upperReverseComplement (utils/helper.cpp:405-410, table :312-358) -- every byte value, lengths around the 32-byte
+    blocks, random texts with lower case / IUPAC / N / 0x7F"""
+    import ctypes as C
+    from util import oracle_lib
+    lib = mbgc_b200.load_library()
+    lib.mbgcg_selftest_revcomp.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+    o = oracle_lib()
+    rng = np.random.default_rng(8)
+    alphabet = np.frombuffer(b"ACGTNacgtnUuYyRrKkMmBbDdHhVvWwSsXx*-\x7f\x00\xff", dtype=np.uint8)
+    cases = [np.arange(256, dtype=np.uint8), np.tile(np.arange(256, dtype=np.uint8), 3)[5:]]
+    for n in (0, 1, 31, 32, 33, 63, 64, 65, 95, 96, 97, 1000, 100_003):
+        cases.append(alphabet[rng.integers(0, alphabet.size, n)].copy())
+        cases.append(rng.integers(0, 256, n).astype(np.uint8))
+    for src in cases:
+        want = np.zeros(max(1, src.size), dtype=np.uint8)
+        got = np.full(max(1, src.size), 0xEE, dtype=np.uint8)
+        if src.size:
+            o.mbo_upper_reverse_complement(src.ctypes.data_as(C.POINTER(C.c_uint8)), src.size, want.ctypes.data_as(C.POINTER(C.c_uint8)))
+        lib.mbgcg_selftest_revcomp(src.ctypes.data, src.size, got.ctypes.data)
+        assert np.array_equal(got[:src.size], want[:src.size]), f"length {src.size}"
+
+
 def test_host_packer_round_trip():
     """2-bit packing of the text transfer path (mbgc_b200/csrc/hostpack.cpp): exact ASCII comes back, including
     N runs, IUPAC codes, lower case and lengths that are not multiples of 4 or 32; texts that are mostly
