@@ -1528,8 +1528,9 @@ struct ResolveArgs {
     const uint32_t* isHead;
     MatchRec* matches;
     uint32_t* matchCountRun;  // [nRuns+1] matches of the island starting at this run (0 for other runs)
-    uint32_t* counters;          // 1 nRuns, 3 overflow (read); 4 longest island, 5 islands (diagnostics, written)
+    uint32_t* counters;          // 1 nRuns, 3 overflow (read); 4 longest island, 5 / 8 long islands (diagnostics, work list)
     uint32_t minMatchLength;
+    uint32_t* bigList;           // first runs of the long islands (k_resolve -> k_resolve_big)
 };
 
 __device__ __forceinline__ int64_t max3(int64_t a, int64_t b, int64_t c) {
@@ -1537,22 +1538,125 @@ __device__ __forceinline__ int64_t max3(int64_t a, int64_t b, int64_t c) {
     return m > c ? m : c;
 }
 
+// State of one island replay: the cursor and the stack of accepted matches (top kept in registers).
+struct ReplayState {
+    int64_t cur = 0;
+    uint32_t nOut = 0;
+    MatchRec top{0, 0, 0};
+};
+
+struct ReplayConst {
+    int K, k1, M, k1Shift;
+    bool k1Pow2;
+    int64_t pos1, refLen, swStop;
+    uint32_t cap;  // runs of the island = capacity of its output region
+};
+
+// Everything the reference does with the seeds of ONE run that lie at or after the cursor (.cpp:250-315).
+__device__ __forceinline__ void replay_run(const ResolveArgs& a, const ReplayConst& rc, const RunRec& run, MatchRec* out,
+                                           ReplayState& st) {
+    const int K = rc.K, k1 = rc.k1, M = rc.M, k1Shift = rc.k1Shift;
+    const bool k1Pow2 = rc.k1Pow2;
+    const int64_t OVERLAP_MATCH_MAX_LENGTH = 1 << 13;  // SlidingWindowSparseEMMatcher.h:18
+    const int64_t pos1 = rc.pos1, refLen = rc.refLen, swStop = rc.swStop;
+    const uint32_t rs = 0, re = rc.cap;  // (the bound of the output region is written as re - rs below)
+    int64_t& cur = st.cur;
+    uint32_t& nOut = st.nOut;
+    MatchRec& top = st.top;
+    const int64_t aRes = run.aFree;  // link chains already resolved by k_links
+    const int64_t firstPos = run.firstPos;
+    const int64_t lastPos = firstPos + static_cast<int64_t>(run.nSeeds - 1) * k1;
+    while (lastPos >= cur) {
+        int64_t i = firstPos;
+        if (cur > i) {  // first seed of the run at or after the cursor (32-bit math: targets are < 4 GiB)
+            const uint32_t gap = static_cast<uint32_t>(cur - i) + static_cast<uint32_t>(k1) - 1;
+            i += k1Pow2 ? ((gap >> k1Shift) << k1Shift) : (gap / static_cast<uint32_t>(k1)) * static_cast<uint32_t>(k1);
+        }
+        const int64_t s = static_cast<int64_t>(decode_pos(run.enc0, a.ix.k1ord)) + (i - firstPos);
+        const int64_t d = s - i;
+        const bool endsBefore = s + K < pos1;
+        const bool startsBefore = s < swStop;
+        const int64_t hi = endsBefore ? pos1 : refLen;  // tmpEnd1
+        const int64_t lo = startsBefore ? 0 : swStop;   // tmpStart1
+        int64_t right1 = static_cast<int64_t>(run.bFree) + d;
+        if (hi < right1) right1 = hi;
+
+        // left edge with overlap resolution (.cpp:251-291); p2 = inclusive matched cursor,
+        // e = exclusive cursor (the reference's final p2)
+        int64_t p2 = i, e = 0;
+        uint32_t idx = nOut;
+        bool broke = false;
+        while (idx > 0) {
+            const MatchRec last = idx == nOut ? top : out[idx - 1];
+            const int64_t lastDst = last.dst, lastEnd = lastDst + last.len;
+            if (lastEnd < p2) {
+                const int64_t stop = max3(aRes - 1, lo - d, lastEnd - 1);
+                if (stop > lastEnd - 1) {
+                    e = stop;
+                    broke = true;
+                    break;
+                }
+                p2 = lastEnd;
+            }
+            const int64_t lastDelta = p2 - lastDst;
+            if ((p2 + d) - lo < lastDelta || static_cast<int64_t>(last.len) > OVERLAP_MATCH_MAX_LENGTH ||
+                aRes > lastDst) {
+                e = p2 - 1;
+                broke = true;
+                break;
+            }
+            p2 = lastDst;
+            idx--;
+        }
+        if (!broke) {
+            e = max3(aRes - 1, lo - d, -1);
+        } else {
+            const MatchRec keep = idx == nOut ? top : out[idx - 1];
+            const int64_t overlap = static_cast<int64_t>(keep.dst) + keep.len - (e + 1);
+            if (overlap > 0) e += overlap;
+        }
+        const int64_t len = right1 - (e + d) - 1;
+        if (len >= static_cast<int64_t>(a.minMatchLength) && idx < re - rs) {
+            nOut = idx;
+            MatchRec mr;
+            mr.src = static_cast<uint64_t>(e + d + 1);
+            mr.dst = static_cast<uint32_t>(e + 1);
+            mr.len = static_cast<uint32_t>(len);
+            out[nOut++] = mr;
+            top = mr;
+            int64_t skip = (e + 1 + len) - i;
+            skip -= skip > M ? M : skip;
+            cur = i + (skip ? skip : 1);
+        } else {
+            cur = i + 1;
+        }
+    }
+}
+
+constexpr uint32_t BIG_ISLAND = 256;  // islands longer than this go to the warp-cooperative kernel
+
 __global__ void __launch_bounds__(128) k_resolve(const ResolveArgs a) {
     if (a.counters[3]) return;
     const uint32_t nRuns = a.counters[1];
-    const int K = a.ix.K, k1 = a.ix.k1, M = a.ix.skipMargin;
-    const bool k1Pow2 = (k1 & (k1 - 1)) == 0;
-    const int k1Shift = 31 - __clz(k1);
-    const int64_t OVERLAP_MATCH_MAX_LENGTH = 1 << 13;  // SlidingWindowSparseEMMatcher.h:18
-    const int64_t pos1 = static_cast<int64_t>(a.ix.pos1);
-    const int64_t refLen = static_cast<int64_t>(a.ix.refLen);
+    ReplayConst rc;
+    rc.K = a.ix.K;
+    rc.k1 = a.ix.k1;
+    rc.M = a.ix.skipMargin;
+    rc.k1Pow2 = (rc.k1 & (rc.k1 - 1)) == 0;
+    rc.k1Shift = 31 - __clz(rc.k1);
+    rc.pos1 = static_cast<int64_t>(a.ix.pos1);
+    rc.refLen = static_cast<int64_t>(a.ix.refLen);
+    const int k1 = rc.k1;
     for (uint32_t rs = blockIdx.x * blockDim.x + threadIdx.x; rs < nRuns; rs += gridDim.x * blockDim.x) {
         if (!a.isHead[rs]) {
             a.matchCountRun[rs] = 0;
             continue;
         }
-        uint32_t re = rs + 1;  // island = runs [rs, re): up to the next head, sixteen flags per step (loads in flight together)
-        while (re < nRuns) {
+        uint32_t re = rs + 1;  // island = runs [rs, re): up to the next head
+        bool big = false;
+        // most islands are one or two runs: look at the next flag alone first, then sixteen per step (loads in flight together)
+        if (re < nRuns && !a.isHead[re]) re++;
+        while (re > rs + 1 && re < nRuns) {
             uint32_t heads = 0;
 #pragma unroll
             for (int k = 0; k < 16; k++)
@@ -1562,105 +1666,90 @@ __global__ void __launch_bounds__(128) k_resolve(const ResolveArgs a) {
                 break;
             }
             re += 16;
+            if (re - rs > BIG_ISLAND) {  // a long island (several similar copies in the reference): a whole warp takes it
+                big = true;
+                break;
+            }
+        }
+        if (big) {
+            a.bigList[atomicAdd(&a.counters[8], 1u)] = rs;
+            continue;
         }
         if (re > nRuns) re = nRuns;
-        atomicAdd(&a.counters[5], 1u);              // islands of the pass, and the longest one (diagnostics)
-        atomicMax(&a.counters[4], re - rs);
         const uint32_t c = a.runs[rs].flags >> 2;
         const uint64_t lock = a.b.contigLock ? a.b.contigLock[c] : NO_LOCK;
-        const int64_t swStop = lock != NO_LOCK ? static_cast<int64_t>(lock) : pos1;
+        rc.swStop = lock != NO_LOCK ? static_cast<int64_t>(lock) : rc.pos1;
+        rc.cap = re - rs;
         MatchRec* out = a.matches + rs;
-        MatchRec top;  // = out[nOut - 1], kept in registers: the common case never re-reads global memory
-        top.src = 0; top.dst = 0; top.len = 0;
-        uint32_t nOut = 0;
-        int64_t cur = 0;
+        ReplayState st;
         for (uint32_t r = rs; r < re; r++) {
             const RunRec run = a.runs[r];
-            const int64_t aRes = run.aFree;  // link chains already resolved by k_links
-            const int64_t firstPos = run.firstPos;
-            const int64_t lastPos = firstPos + static_cast<int64_t>(run.nSeeds - 1) * k1;
-            if (lastPos < cur) {
-                // Behind the cursor (inside the match just accepted).  With several similar copies in the reference an
-                // island holds thousands of such runs: look at sixteen at a time, their loads in flight together.
-                while (r + 16 < re) {
-                    bool ahead = false;
-#pragma unroll
-                    for (int k = 1; k <= 16; k++) {
-                        const RunRec& q = a.runs[r + k];
-                        ahead |= static_cast<int64_t>(q.firstPos) + static_cast<int64_t>(q.nSeeds - 1) * k1 >= cur;
-                    }
-                    if (ahead) break;
-                    r += 16;
-                }
+            const int64_t lastPos = static_cast<int64_t>(run.firstPos) + static_cast<int64_t>(run.nSeeds - 1) * k1;
+            if (lastPos < st.cur) continue;  // behind the cursor (inside the match just accepted)
+            replay_run(a, rc, run, out, st);
+        }
+        a.matchCountRun[rs] = st.nOut;
+    }
+}
+
+// Long islands, a warp each: lane 0 replays, all 32 lanes find the island's end and the next run that is not behind
+// the cursor (a ballot over 32 runs per step instead of one dependent load per run).
+__global__ void __launch_bounds__(128) k_resolve_big(const ResolveArgs a) {
+    if (a.counters[3]) return;
+    const uint32_t nRuns = a.counters[1], nBig = a.counters[8];
+    const int lane = threadIdx.x & 31;
+    ReplayConst rc;
+    rc.K = a.ix.K;
+    rc.k1 = a.ix.k1;
+    rc.M = a.ix.skipMargin;
+    rc.k1Pow2 = (rc.k1 & (rc.k1 - 1)) == 0;
+    rc.k1Shift = 31 - __clz(rc.k1);
+    rc.pos1 = static_cast<int64_t>(a.ix.pos1);
+    rc.refLen = static_cast<int64_t>(a.ix.refLen);
+    const int k1 = rc.k1;
+    const uint32_t warps = gridDim.x * (blockDim.x >> 5);
+    for (uint32_t w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < nBig; w += warps) {
+        const uint32_t rs = a.bigList[w];
+        uint32_t re = rs + 1;
+        while (re < nRuns) {
+            const uint32_t q = re + lane;
+            const unsigned heads = __ballot_sync(0xffffffffu, q < nRuns && a.isHead[q] != 0);
+            if (heads) {
+                re += __ffs(heads) - 1;
+                break;
+            }
+            re += 32;
+        }
+        if (re > nRuns) re = nRuns;
+        const uint32_t c = a.runs[rs].flags >> 2;
+        const uint64_t lock = a.b.contigLock ? a.b.contigLock[c] : NO_LOCK;
+        rc.swStop = lock != NO_LOCK ? static_cast<int64_t>(lock) : rc.pos1;
+        rc.cap = re - rs;
+        MatchRec* out = a.matches + rs;
+        ReplayState st;
+        uint32_t r = rs;
+        while (r < re) {
+            const uint32_t q = r + lane;
+            bool ahead = false;
+            if (q < re) {
+                const RunRec& rr = a.runs[q];
+                ahead = static_cast<int64_t>(rr.firstPos) + static_cast<int64_t>(rr.nSeeds - 1) * k1 >= st.cur;
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, ahead);
+            if (!bal) {
+                r += 32;
                 continue;
             }
-            while (lastPos >= cur) {
-                int64_t i = firstPos;
-                if (cur > i) {  // first seed of the run at or after the cursor (32-bit math: targets are < 4 GiB)
-                    const uint32_t gap = static_cast<uint32_t>(cur - i) + static_cast<uint32_t>(k1) - 1;
-                    i += k1Pow2 ? ((gap >> k1Shift) << k1Shift) : (gap / static_cast<uint32_t>(k1)) * static_cast<uint32_t>(k1);
-                }
-                const int64_t s = static_cast<int64_t>(decode_pos(run.enc0, a.ix.k1ord)) + (i - firstPos);
-                const int64_t d = s - i;
-                const bool endsBefore = s + K < pos1;
-                const bool startsBefore = s < swStop;
-                const int64_t hi = endsBefore ? pos1 : refLen;  // tmpEnd1
-                const int64_t lo = startsBefore ? 0 : swStop;   // tmpStart1
-                int64_t right1 = static_cast<int64_t>(run.bFree) + d;
-                if (hi < right1) right1 = hi;
-
-                // left edge with overlap resolution (.cpp:251-291); p2 = inclusive matched cursor,
-                // e = exclusive cursor (the reference's final p2)
-                int64_t p2 = i, e = 0;
-                uint32_t idx = nOut;
-                bool broke = false;
-                while (idx > 0) {
-                    const MatchRec last = idx == nOut ? top : out[idx - 1];
-                    const int64_t lastDst = last.dst, lastEnd = lastDst + last.len;
-                    if (lastEnd < p2) {
-                        const int64_t stop = max3(aRes - 1, lo - d, lastEnd - 1);
-                        if (stop > lastEnd - 1) {
-                            e = stop;
-                            broke = true;
-                            break;
-                        }
-                        p2 = lastEnd;
-                    }
-                    const int64_t lastDelta = p2 - lastDst;
-                    if ((p2 + d) - lo < lastDelta || static_cast<int64_t>(last.len) > OVERLAP_MATCH_MAX_LENGTH ||
-                        aRes > lastDst) {
-                        e = p2 - 1;
-                        broke = true;
-                        break;
-                    }
-                    p2 = lastDst;
-                    idx--;
-                }
-                if (!broke) {
-                    e = max3(aRes - 1, lo - d, -1);
-                } else {
-                    const MatchRec keep = idx == nOut ? top : out[idx - 1];
-                    const int64_t overlap = static_cast<int64_t>(keep.dst) + keep.len - (e + 1);
-                    if (overlap > 0) e += overlap;
-                }
-                const int64_t len = right1 - (e + d) - 1;
-                if (len >= static_cast<int64_t>(a.minMatchLength) && idx < re - rs) {
-                    nOut = idx;
-                    MatchRec mr;
-                    mr.src = static_cast<uint64_t>(e + d + 1);
-                    mr.dst = static_cast<uint32_t>(e + 1);
-                    mr.len = static_cast<uint32_t>(len);
-                    out[nOut++] = mr;
-                    top = mr;
-                    int64_t skip = (e + 1 + len) - i;
-                    skip -= skip > M ? M : skip;
-                    cur = i + (skip ? skip : 1);
-                } else {
-                    cur = i + 1;
-                }
-            }
+            r += __ffs(bal) - 1;
+            if (lane == 0) replay_run(a, rc, a.runs[r], out, st);
+            st.cur = __shfl_sync(0xffffffffu, st.cur, 0);
+            r++;
         }
-        a.matchCountRun[rs] = nOut;
+        if (lane == 0) {
+            a.matchCountRun[rs] = st.nOut;
+            atomicAdd(&a.counters[5], 1u);
+            atomicMax(&a.counters[4], re - rs);
+        }
     }
 }
 
@@ -1699,9 +1788,11 @@ int launch_resolve(const IndexState& ix, const BatchDesc& b, const WorkBuffers& 
     k_island_heads<<<sm * 4, ISL_THREADS, 0, st>>>(w.runs, w.counters, w.islandFwd, w.islandBwd, w.headScan);
     launches += 3;
     // runFirst (free after k_extend) takes the per-island match counts, then their exclusive scan
-    ResolveArgs a{ix, b, w.runs, w.runStart, w.headScan, w.matches, w.runFirst, w.counters, minMatchLength};
+    // scratchEnc (position-indexed seed staging, free since the compaction) holds the list of long islands
+    ResolveArgs a{ix, b, w.runs, w.runStart, w.headScan, w.matches, w.runFirst, w.counters, minMatchLength, w.scratchEnc};
     k_resolve<<<sm * 16, 128, 0, st>>>(a);
-    launches += 1;
+    k_resolve_big<<<sm * 4, 128, 0, st>>>(a);
+    launches += 2;
     launches += scan_exclusive(w.runFirst, w.runFirst, w.counters + 1, 0, w.seedCap, w.blockSums, nullptr, st);
     k_gather<<<sm * 8, 256, 0, st>>>(w.matches, w.headScan, w.runFirst, w.runStart, w.matchesDense, w.matchOff,
                                      b.nContigs, w.counters);

@@ -745,7 +745,7 @@ void B200SparseEMMatcher::matchBatch(const std::vector<TextView>& texts, const u
                 for (int c = 0; c < nC; c++) lastLens[c] = texts[first + c].len;
                 textBase = dText;
             }
-            check(cudaMemsetAsync(wb.counters, 0, 32, stream), "memset(counters)");
+            check(cudaMemsetAsync(wb.counters, 0, 64, stream), "memset(counters)");
             check(cudaEventRecord(ev[1], stream), "event");
 
             BatchDesc bd;
@@ -805,7 +805,7 @@ void B200SparseEMMatcher::matchBatch(const std::vector<TextView>& texts, const u
                 continue;
             }
             if (std::getenv("MBGC_B200_TRACE_ISLANDS"))
-                fprintf(stderr, "[mbgc_b200] pass: %u runs, %u islands, longest %u runs\n", hCtr[1], hCtr[5], hCtr[4]);
+                fprintf(stderr, "[mbgc_b200] pass: %u runs, %u islands of more than 256 runs, longest %u runs\n", hCtr[1], hCtr[5], hCtr[4]);
             const uint32_t total = hOffs[nC];
             if (!listsStayOnDevice) matchGuess = static_cast<uint64_t>(total) + total / 64 + 1024;
             const uint32_t fetched = listsStayOnDevice ? static_cast<uint32_t>(std::min<uint64_t>(guess, total)) : total;
