@@ -159,3 +159,38 @@ def test_synthetic_100x_near_batch():
     finally:
         g.close()
         o.close()
+
+
+def test_grown_reference_long_islands():
+    """A reference that holds several similar copies of the genome (G0 + two divergent genomes, each with its reverse
+    complement): seeds of the copies' diagonals interleave, every run is a single seed linked to a run a few places
+    away (LINK_WINDOW), and the islands between two mismatches of a near-identical target hold thousands of runs
+    (k_resolve_big).  Match lists against the oracle, one text at a time and as a batch, with and without the fast path."""
+    import os
+    base = synth_base(400_000, 77)
+    copies = [synth_mutant(base, 7000 + i, 1e-2, 1e-4) for i in range(2)]
+    targets = [synth_mutant(base, 7100 + i, p, q) for i, (p, q) in enumerate(((1e-4, 1e-5), (3e-5, 0), (1e-3, 1e-4)))]
+    targets.append(synth_mutant(copies[0], 7200, 1e-4, 1e-5))   # near-identical to one of the appended copies
+    limit = mgmp_ref_limit(8, base.size)
+    for fast in ("0", "1"):
+        os.environ["MBGC_B200_FASTPATH"] = fast
+        o = OracleMatcher(limit, 32, 16, 1, 16)
+        g = CudaFace(limit, 32, 16, 1, 16)
+        try:
+            for m in (o, g):
+                m.disable_sliding_window()
+                m.load_ref(base, rc=True)
+                for c in copies:
+                    m.load_ref(c, rc=True)
+                    m.load_separator(0)
+            want = [o.match(t) for t in targets]
+            assert max(len(w) for w in want) > 10
+            for t, w in zip(targets, want):
+                got = g.match(t)
+                assert np.array_equal(got, w), _diff(got, w)
+            for got, w in zip(g.match_batch(targets), want):
+                assert np.array_equal(got, w), _diff(got, w)
+        finally:
+            os.environ.pop("MBGC_B200_FASTPATH", None)
+            g.close()
+            o.close()
