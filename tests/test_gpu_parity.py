@@ -4,7 +4,8 @@ import numpy as np
 import pytest
 
 from scenarios import CudaFace, all_scenarios, replay
-from util import (FIXTURES, OracleMatcher, have_fixtures, mgmp_ref_limit, read_fasta, synth_collection)
+from util import (FIXTURES, OracleMatcher, have_fixtures, mgmp_ref_limit, read_fasta, synth_base, synth_collection,
+                  synth_mutant)
 
 pytestmark = pytest.mark.gpu
 
