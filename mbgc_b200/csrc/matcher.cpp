@@ -688,6 +688,15 @@ void B200SparseEMMatcher::matchBatch(const std::vector<TextView>& texts, const u
     // split into passes of bounded size (work memory is ~26 bytes per target position)
     uint64_t maxPassBytes = 1024ull << 20;
     if (const char* e = std::getenv("MBGC_B200_MAX_PASS_BYTES")) maxPassBytes = std::max<uint64_t>(1, std::strtoull(e, nullptr, 10));
+    if (listsStayOnDevice) {  // only one pass can leave its lists behind: refuse before doing any work
+        uint64_t bytes = 0;
+        for (size_t i = 0; i < texts.size(); i++) {
+            if (i && bytes + texts[i].len > maxPassBytes)
+                throw MatcherError(MBGCG_E_PARAM, "match lists can only stay on the device for a batch that fits one pass (" +
+                                                      std::to_string(maxPassBytes) + " bytes of text, MBGC_B200_MAX_PASS_BYTES)");
+            bytes += texts[i].len;
+        }
+    }
     size_t first = 0;
     while (first < texts.size()) {
         size_t last = first;

@@ -200,7 +200,7 @@ def _gather_packed(local, n_items, device="cpu"):
 
 
 def compress_speculative(matcher, files, pack_params, window, device="cpu", min_match_length=32,
-                         unmatched_fraction_factor=128, unmatched_fraction_rc_factor=8):
+                         unmatched_fraction_factor=128, unmatched_fraction_rc_factor=8, max_pass_bytes=512 << 20):
     """The reference's sequential (-t 1) encoder schedule over `files` (a list of files, each a list of contig texts),
     with both stages of the hot path on the matcher's device and the contigs of a window sharded over the ranks
     (optimistic batching):
@@ -248,10 +248,17 @@ def compress_speculative(matcher, files, pack_params, window, device="cpu", min_
         b, e = spans[rank]
         mine = [files[fi][ci] for fi, ci in flat[done + b:done + e]]
         local = []
-        if mine:
-            matcher.matchBatch(mine, min_match_length, fetch=False)      # lists stay on the device
-            res = matcher.packBatch(pack_params, mine, None, loadedPosArr=loaded)
-            local = [(int(res["unmatched"][k]), [res[n][k] for n in STREAM_NAMES]) for k in range(len(mine))]
+        at = 0
+        while at < len(mine):   # sub-batches that fit one device pass (the lists stay on the device between the two calls)
+            end, nbytes = at, 0
+            while end < len(mine) and (end == at or nbytes + len(mine[end]) <= max_pass_bytes):
+                nbytes += len(mine[end])
+                end += 1
+            part = mine[at:end]
+            matcher.matchBatch(part, min_match_length, fetch=False)
+            res = matcher.packBatch(pack_params, part, None, loadedPosArr=loaded)
+            local += [(int(res["unmatched"][k]), [res[n][k] for n in STREAM_NAMES]) for k in range(len(part))]
+            at = end
         packed = _gather_packed(local, hi - done, device)
         stats["rounds"] += 1
         committed = 0

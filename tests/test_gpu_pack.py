@@ -290,3 +290,42 @@ def test_pack_listeria_sequential_schedule():
                 assert removed == 1418  # SURVEY.md 8c dev counter of the reference
         finally:
             g.close()
+
+
+def test_pack_error_paths(monkeypatch):
+    """what the device packer refuses, and how: parameters outside its scope (MBGCG_E_UNSUPPORTED), a resident call
+    without the match call it refers to (MBGCG_E_PARAM), lists asked to stay on the device for a multi-pass batch"""
+    import mbgc_b200
+    from mbgc_b200.matcher import MatcherError
+    base, texts = _collection(404, 3, 60_000, 1e-3, 1e-4)
+    pr = Pair(1 << 22)
+    try:
+        pr.load(base)
+        g = pr.g
+        _, pd = _params(gdepth=3)
+        with pytest.raises(MatcherError) as e:
+            g.packBatch(pd, texts, [g.matchTexts(t) for t in texts])
+        assert e.value.code == -3
+        _, pd = _params(depth=128)
+        with pytest.raises(MatcherError) as e:
+            g.packBatch(pd, texts, [g.matchTexts(t) for t in texts])
+        assert e.value.code == -3
+        _, pd = _params()
+        g.matchBatch(texts, 32)
+        with pytest.raises(MatcherError) as e:          # other texts than those of the match call
+            g.packBatch(pd, texts[:1], None)
+        assert e.value.code == -2
+        g.packBatch(pd, texts, [g.matchTexts(t) for t in texts])   # a host-route call overwrites the device texts ...
+        with pytest.raises(MatcherError) as e:                      # ... so nothing is resident any more
+            g.packBatch(pd, texts, None)
+        assert e.value.code == -2
+        monkeypatch.setenv("MBGC_B200_MAX_PASS_BYTES", "70000")
+        with pytest.raises(MatcherError) as e:
+            g.matchBatch(texts, 32, fetch=False)
+        assert e.value.code == -2
+        lists = g.matchBatch(texts, 32)                              # with the lists fetched, two passes are fine
+        monkeypatch.delenv("MBGC_B200_MAX_PASS_BYTES")
+        for a, t in zip(lists, texts):
+            assert np.array_equal(a, pr.o.match(t))
+    finally:
+        pr.close()
