@@ -60,10 +60,19 @@ __device__ __forceinline__ uint32_t eq_mask16(const uint4& v, uint32_t c4) {
     return eq_mask4(v.x, c4) | (eq_mask4(v.y, c4) << 4) | (eq_mask4(v.z, c4) << 8) | (eq_mask4(v.w, c4) << 12);
 }
 
+// bit 7 of every byte of x that equals the byte replicated in c4 (exact: no carries between bytes)
+__device__ __forceinline__ uint32_t eq_bytes(uint32_t x, uint32_t c4) {
+    const uint32_t y = x ^ c4;
+    return ~(((y & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | y) & 0x80808080u;
+}
+
 // The 16 bytes at i0 (a multiple of 16; the buffer is 16-byte aligned with a '\n' in front of byte 0 and zeros behind
 // byte n-1) -> bit k set where byte k starts a record: a '>' whose predecessor is a '\n'.
 __device__ __forceinline__ uint32_t start_mask(const uint8_t* __restrict__ in, uint64_t n, uint64_t i0) {
     const uint4 v = *reinterpret_cast<const uint4*>(in + i0);
+    // sequence lines hold no '>' at all: one cheap test per word rejects nearly every chunk
+    if ((eq_bytes(v.x, 0x3E3E3E3Eu) | eq_bytes(v.y, 0x3E3E3E3Eu) | eq_bytes(v.z, 0x3E3E3E3Eu) | eq_bytes(v.w, 0x3E3E3E3Eu)) == 0)
+        return 0;
     const uint32_t gt = eq_mask16(v, 0x3E3E3E3Eu);
     if (gt == 0) return 0;
     const uint32_t nl = eq_mask16(v, 0x0A0A0A0Au);
@@ -200,8 +209,16 @@ __device__ __forceinline__ void check_chunk(const uint8_t* __restrict__ in, uint
         if (i0 >= seqStart && i0 + 16 < rec.regionEnd && rec.firstLine >= 16) {
             const uint64_t o = i0 - seqStart, period = rec.firstLine + 1;
             const uint64_t m0 = (o | period) >> 32 ? o % period : static_cast<uint32_t>(o) % static_cast<uint32_t>(period);
-            const uint64_t due = rec.firstLine - m0;
-            if (eq_mask16(v, 0x0A0A0A0Au) != (due < 16 ? 1u << due : 0u)) recs[r].bad = 1;
+            const uint32_t due = static_cast<uint32_t>(rec.firstLine - m0 < 16 ? rec.firstLine - m0 : 16);  // 16: none
+            // line ends as bit 7 per byte, word by word, against the one that is due
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+            bool ok = true;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const uint32_t want = (due >> 2) == static_cast<uint32_t>(q) ? 0x80u << (8 * (due & 3)) : 0u;
+                ok &= eq_bytes(w[q], 0x0A0A0A0Au) == want;
+            }
+            if (!ok) recs[r].bad = 1;
             return;
         }
     }
