@@ -329,3 +329,22 @@ def test_pack_error_paths(monkeypatch):
             assert np.array_equal(a, pr.o.match(t))
     finally:
         pr.close()
+
+
+def test_pack_fixed_point_rerun_path(monkeypatch):
+    """starting with a single sweep leaves the convergence flag set whenever anything pairs or is removed: the host must
+    notice, run again with more sweeps, and arrive at the same streams"""
+    base, texts = _collection(505, 4, 150_000, 5e-3, 5e-4)
+    pr = Pair(1 << 22)
+    try:
+        pr.load(base)
+        po, pd = _params()
+        lists = [pr.o.match(t) for t in texts]
+        want = [_oracle_pack(pr.o, po, t, m, NO_LOCK, [pr.o.loading_position]) for t, m in zip(texts, lists)]
+        monkeypatch.setenv("MBGC_B200_PACK_SWEEPS", "1")
+        got = pr.g.packBatch(pd, texts, lists, loadedPosArr=[pr.o.loading_position])
+        _check(got, want, "one sweep first")
+        assert pr.g.packTiming()["sweeps"][1] >= 2
+        monkeypatch.delenv("MBGC_B200_PACK_SWEEPS")
+    finally:
+        pr.close()
