@@ -185,6 +185,29 @@ void launch_table_low32(const unsigned long long* ht, uint32_t* out, uint64_t n,
 }
 
 // ------------------------------------------------------------------------------------------------------
+// reference segments from the staged text of a loadRef call (.cpp:420-424): a straight copy, or the upper-casing
+// reverse complement of utils/helper.cpp:405-410 through its 256-entry table (:312-358)
+// ------------------------------------------------------------------------------------------------------
+__constant__ uint8_t c_complement[256];
+
+__global__ void __launch_bounds__(256) k_ref_segment(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uint64_t n,
+                                                     int reverseComplement) {
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+        dst[i] = reverseComplement ? c_complement[src[n - 1 - i]] : src[i];
+}
+
+void upload_complement_table(const uint8_t table[256]) { cudaMemcpyToSymbol(c_complement, table, 256); }
+
+void launch_ref_segment(const uint8_t* src, uint8_t* dst, uint64_t n, bool reverseComplement, cudaStream_t st) {
+    if (n == 0) return;
+    uint64_t blocks = (n + 256 * 16 - 1) / (256 * 16);
+    const uint64_t cap = static_cast<uint64_t>(device_sm_count()) * 16;
+    if (blocks > cap) blocks = cap;
+    k_ref_segment<<<static_cast<unsigned>(blocks), 256, 0, st>>>(src, dst, n, reverseComplement ? 1 : 0);
+}
+
+// ------------------------------------------------------------------------------------------------------
 // exclusive scan of a uint32 array whose length may live in device memory (no host sync between stages)
 // ------------------------------------------------------------------------------------------------------
 constexpr int SCAN_THREADS = 1024;

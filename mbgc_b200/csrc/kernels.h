@@ -112,6 +112,10 @@ struct InsertRange {
 void launch_index_insert(const uint8_t* ref, unsigned long long* ht, uint32_t* occ, uint32_t* filter, uint32_t filterBits,
                          uint32_t hashMask, int K, int k1, int k1ord, InsertRange r0, InsertRange r1, cudaStream_t st);
 void launch_table_low32(const unsigned long long* ht, uint32_t* out, uint64_t n, cudaStream_t st);
+// reference segment from the staged text of a loadRef call: copy or upper-casing reverse complement (table uploaded once
+// per process with upload_complement_table)
+void upload_complement_table(const uint8_t table[256]);
+void launch_ref_segment(const uint8_t* src, uint8_t* dst, uint64_t n, bool reverseComplement, cudaStream_t st);
 
 // ---- match pass ----
 // returns the number of kernel launches issued

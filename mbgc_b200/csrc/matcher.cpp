@@ -126,6 +126,7 @@ B200SparseEMMatcher::B200SparseEMMatcher(uint64_t refLengthLimit, uint32_t targe
             throw MatcherError(MBGCG_E_UNSUPPORTED, "reference needs the 64-bit table (ref .cpp:347-350)");
     }
 
+    upload_complement_table(g_lut.t);
     hostRef = static_cast<char*>(std::calloc(maxRefLength + PAD, 1));
     if (!hostRef) throw MatcherError(MBGCG_E_NOMEM, "host mirror allocation failed");
     lap("host mirror");
@@ -152,6 +153,8 @@ B200SparseEMMatcher::~B200SparseEMMatcher() {
     cudaFree(dOcc);
     cudaFree(dFilter);
     cudaFree(dMemoX);
+    cudaFree(dStage);
+    if (hStage) cudaFreeHost(hStage);
     delete pool;
     if (hPacked) cudaFreeHost(hPacked);
     if (hXferMeta) cudaFreeHost(hXferMeta);
@@ -197,7 +200,9 @@ void B200SparseEMMatcher::indexPass() {
 }
 
 // .cpp:402-437 (tail recursion written as a loop)
-void B200SparseEMMatcher::loadSegment(const char* text, uint64_t len, bool rc, bool addSep, char sep) {
+// `text` is also on the device at dStage + stageOff (staged once per loadRef call): the device reference gets its bytes
+// from there (copy / reverse-complement kernel) while the host cores write the mirror
+void B200SparseEMMatcher::loadSegment(const char* text, uint64_t len, bool rc, bool addSep, char sep, uint64_t stageOff) {
     while (len != 0) {
         if (static_cast<uint64_t>(pos1) == maxRefLength && swEnd != maxRefLength) {
             reachedRefLengthCount++;
@@ -216,13 +221,19 @@ void B200SparseEMMatcher::loadSegment(const char* text, uint64_t len, bool rc, b
             std::memcpy(dst, text, tmpLen);
         const bool sepHit = addSep && static_cast<uint64_t>(pos1) + tmpLen == swEnd;
         if (sepHit) hostRef[swEnd - 1] = sep;
-        if (tmpLen)
-            check(cudaMemcpyAsync(dRef + pos1, dst, tmpLen, cudaMemcpyHostToDevice, stream), "H2D(ref segment)");
-        else if (sepHit)
+        if (tmpLen) {
+            launch_ref_segment(dStage + stageOff + (rc ? len - tmpLen : 0), dRef + pos1, tmpLen, rc, stream);
+            totalLaunches++;
+            if (sepHit)  // the separator replaced the segment's last byte in the mirror: same on the device
+                check(cudaMemcpyAsync(dRef + swEnd - 1, hostRef + swEnd - 1, 1, cudaMemcpyHostToDevice, stream), "H2D(sep)");
+        } else if (sepHit)
             check(cudaMemcpyAsync(dRef + swEnd - 1, hostRef + swEnd - 1, 1, cudaMemcpyHostToDevice, stream), "H2D(sep)");
         pos1 += static_cast<int64_t>(tmpLen);
         indexPass();
-        if (!rc) text += tmpLen;
+        if (!rc) {
+            text += tmpLen;
+            stageOff += tmpLen;
+        }
         len = (static_cast<uint64_t>(pos1) == tmpEnd) ? 0 : len - tmpLen;
     }
 }
@@ -230,8 +241,14 @@ void B200SparseEMMatcher::loadSegment(const char* text, uint64_t len, bool rc, b
 void B200SparseEMMatcher::loadRef(const char* refText, uint64_t refLength, bool loadRCRef, bool addRegionSeparators,
                                   char regionSeparator) {
     check(cudaSetDevice(device), "cudaSetDevice");
-    loadSegment(refText, refLength, false, addRegionSeparators, regionSeparator);
-    if (loadRCRef) loadSegment(refText, refLength, true, addRegionSeparators, regionSeparator);
+    if (refLength) {  // the text goes up once, through pinned staging (a pageable source would be staged by the driver)
+        growPinned(reinterpret_cast<void**>(&hStage), &hStageCap, refLength, "cudaHostAlloc(ref staging)");
+        growDevice(reinterpret_cast<void**>(&dStage), &dStageCap, refLength + 64, "cudaMalloc(ref staging)");
+        std::memcpy(hStage, refText, refLength);
+        check(cudaMemcpyAsync(dStage, hStage, refLength, cudaMemcpyHostToDevice, stream), "H2D(ref text)");
+    }
+    loadSegment(refText, refLength, false, addRegionSeparators, regionSeparator, 0);
+    if (loadRCRef) loadSegment(refText, refLength, true, addRegionSeparators, regionSeparator, 0);
     // the caller may free refText right after the call; pageable copies are staged before returning, but
     // keep the ordering explicit
     check(cudaStreamSynchronize(stream), "loadRef sync");

@@ -150,7 +150,7 @@ public:
     uint64_t totalLaunches = 0;
 
 private:
-    void loadSegment(const char* text, uint64_t len, bool rc, bool addSep, char sep);
+    void loadSegment(const char* text, uint64_t len, bool rc, bool addSep, char sep, uint64_t stageOff);
     void indexPass();
     bool wantMemo(uint64_t positions);
     void buildMemo();
@@ -170,6 +170,8 @@ private:
     char* hostRef = nullptr;             // host mirror (getRef())
     uint8_t* dRefAlloc = nullptr;        // device reference buffer with padding
     uint8_t* dRef = nullptr;             // = dRefAlloc + PAD
+    uint8_t* dStage = nullptr; uint64_t dStageCap = 0;   // the text of the current loadRef call on the device
+    uint8_t* hStage = nullptr; uint64_t hStageCap = 0;   // pinned staging of the same
     unsigned long long* dHt = nullptr;
     uint32_t* dOcc = nullptr;
     uint32_t* dFilter = nullptr;         // first-level probe filter (copied to shared memory by the probe kernel)
