@@ -11,6 +11,8 @@
 #include <cstring>
 #include <thread>
 
+#include <sys/mman.h>
+
 #include "../../include/mbgc_b200.h"
 
 namespace mbgc_b200 {
@@ -127,8 +129,13 @@ B200SparseEMMatcher::B200SparseEMMatcher(uint64_t refLengthLimit, uint32_t targe
     }
 
     upload_complement_table(g_lut.t);
-    hostRef = static_cast<char*>(std::calloc(maxRefLength + PAD, 1));
-    if (!hostRef) throw MatcherError(MBGCG_E_NOMEM, "host mirror allocation failed");
+    // anonymous mapping (zero pages, like calloc) with transparent huge pages asked for: the mirror is written once,
+    // front to back, and with 4 KiB pages every loadRef call would spend most of its time in first-touch page faults
+    hostRefBytes = align_up(maxRefLength + PAD, 2ull << 20);
+    void* mem = mmap(nullptr, hostRefBytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (mem == MAP_FAILED) throw MatcherError(MBGCG_E_NOMEM, "host mirror allocation failed");
+    madvise(mem, hostRefBytes, MADV_HUGEPAGE);
+    hostRef = static_cast<char*>(mem);
     lap("host mirror");
     check(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate");
     for (auto& e : ev) check(cudaEventCreate(&e), "cudaEventCreate");
@@ -170,7 +177,7 @@ B200SparseEMMatcher::~B200SparseEMMatcher() {
     releaseIngest();
     for (auto& e : ev) if (e) cudaEventDestroy(e);
     if (stream) cudaStreamDestroy(stream);
-    std::free(hostRef);
+    if (hostRef) munmap(hostRef, hostRefBytes);
 }
 
 // ---- index build ---------------------------------------------------------------------------------------
@@ -241,17 +248,28 @@ void B200SparseEMMatcher::loadSegment(const char* text, uint64_t len, bool rc, b
 void B200SparseEMMatcher::loadRef(const char* refText, uint64_t refLength, bool loadRCRef, bool addRegionSeparators,
                                   char regionSeparator) {
     check(cudaSetDevice(device), "cudaSetDevice");
+    static const bool trace = std::getenv("MBGC_B200_TRACE") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (trace)
+            fprintf(stderr, "[mbgc_b200]   loadRef: %-22s at %8.3f ms\n", what,
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    };
     if (refLength) {  // the text goes up once, through pinned staging (a pageable source would be staged by the driver)
         growPinned(reinterpret_cast<void**>(&hStage), &hStageCap, refLength, "cudaHostAlloc(ref staging)");
         growDevice(reinterpret_cast<void**>(&dStage), &dStageCap, refLength + 64, "cudaMalloc(ref staging)");
         std::memcpy(hStage, refText, refLength);
         check(cudaMemcpyAsync(dStage, hStage, refLength, cudaMemcpyHostToDevice, stream), "H2D(ref text)");
     }
+    lap("text staged");
     loadSegment(refText, refLength, false, addRegionSeparators, regionSeparator, 0);
+    lap("forward segment");
     if (loadRCRef) loadSegment(refText, refLength, true, addRegionSeparators, regionSeparator, 0);
+    lap("reverse complement");
     // the caller may free refText right after the call; pageable copies are staged before returning, but
     // keep the ordering explicit
     check(cudaStreamSynchronize(stream), "loadRef sync");
+    lap("device done");
 }
 
 void B200SparseEMMatcher::loadSeparator(char regionSeparator) {

@@ -168,6 +168,7 @@ private:
     cudaEvent_t ev[12] = {};
     bool timingPending = false;
     char* hostRef = nullptr;             // host mirror (getRef())
+    uint64_t hostRefBytes = 0;           // size of its mapping
     uint8_t* dRefAlloc = nullptr;        // device reference buffer with padding
     uint8_t* dRef = nullptr;             // = dRefAlloc + PAD
     uint8_t* dStage = nullptr; uint64_t dStageCap = 0;   // the text of the current loadRef call on the device
