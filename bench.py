@@ -493,11 +493,13 @@ def run_b200(args, rank, world):
         dist = dist_mod
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler = ClockSampler(local)  # rank 0 reports its GPU's clocks; nvidia-smi from every rank would only disturb the timing
+    if rank == 0:
+        sampler.start()
     r = measure_tier(args, args.tier, rank, world, dist, local)
     sampler.stop_flag = True
-    sampler.join(timeout=2)
+    if rank == 0:
+        sampler.join(timeout=2)
 
     steps = args.steps
     n, lens, fbytes, counters = r["n"], r["lens"], r["fbytes"], r["counters"]
