@@ -101,14 +101,7 @@ int mbgcg_match_batch(mbgcg_t* h, int nTexts, const char* const* texts, const ui
     return guarded(h, [&] {
         std::vector<TextView> tv(static_cast<size_t>(nTexts));
         for (int i = 0; i < nTexts; i++) tv[i] = TextView{texts[i], lens[i]};
-        h->m->listsStayOnDevice = out == nullptr;
-        try {
-            h->m->matchBatch(tv, lockPos, minMatchLength, false, nullptr, nullptr);
-        } catch (...) {
-            h->m->listsStayOnDevice = false;
-            throw;
-        }
-        h->m->listsStayOnDevice = false;
+        h->m->matchBatch(tv, lockPos, minMatchLength, false, nullptr, nullptr, out == nullptr);
         if (out) *out = reinterpret_cast<const mbgcg_match_t*>(h->m->batchMatches());
         *counts = h->m->batchCounts().data();
     });
@@ -125,14 +118,7 @@ int mbgcg_match_batch_device(mbgcg_t* h, const void* dText, int nTexts, const ui
             if (offsets[i] % 16) throw MatcherError(MBGCG_E_PARAM, "device text offsets must be multiples of 16");
             tv[i] = TextView{nullptr, lens[i]};
         }
-        h->m->listsStayOnDevice = out == nullptr;
-        try {
-            h->m->matchBatch(tv, lockPos, minMatchLength, true, dText, offsets);
-        } catch (...) {
-            h->m->listsStayOnDevice = false;
-            throw;
-        }
-        h->m->listsStayOnDevice = false;
+        h->m->matchBatch(tv, lockPos, minMatchLength, true, dText, offsets, out == nullptr);
         if (out) *out = reinterpret_cast<const mbgcg_match_t*>(h->m->batchMatches());
         *counts = h->m->batchCounts().data();
     });

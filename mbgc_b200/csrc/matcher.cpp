@@ -705,7 +705,8 @@ int B200SparseEMMatcher::stageTexts(const std::vector<TextView>& texts, size_t f
 }
 
 void B200SparseEMMatcher::matchBatch(const std::vector<TextView>& texts, const uint64_t* lockPos, uint32_t minMatchLength,
-                                     bool textsOnDevice, const void* dTextBase, const uint64_t* dOffsets) {
+                                     bool textsOnDevice, const void* dTextBase, const uint64_t* dOffsets,
+                                     bool listsStayOnDevice) {
     check(cudaSetDevice(device), "cudaSetDevice");
     if (minMatchLength < static_cast<uint32_t>(K))
         throw MatcherError(MBGCG_E_PARAM, "Minimal matching length cannot be smaller than K (" +

@@ -87,10 +87,9 @@ public:
                     bool revComplMatching, uint32_t minMatchLength, uint64_t matchingLockPos = SW_END_ERASED_FLAG);
 
     // n texts against the same frozen state in one device pass; results concatenated in text order
+    // listsStayOnDevice: the match lists are not copied to the host (the counts are) -- for a resident packBatch
     void matchBatch(const std::vector<TextView>& texts, const uint64_t* lockPos, uint32_t minMatchLength,
-                    bool textsOnDevice, const void* dTextBase, const uint64_t* dOffsets);
-    // true: the next matchBatch leaves its match lists on the device (counts still come back) for a resident packBatch
-    bool listsStayOnDevice = false;
+                    bool textsOnDevice, const void* dTextBase, const uint64_t* dOffsets, bool listsStayOnDevice = false);
     const TextMatch* batchMatches() const { return hMatches; }   // pinned, valid until the next match call
     uint64_t batchMatchCount() const { return nMatchesAll; }
     const std::vector<uint64_t>& batchCounts() const { return resCounts; }
