@@ -172,3 +172,18 @@ def test_host_packer_round_trip():
     lower = np.frombuffer(bytes(acgt[rng.integers(0, 4, 10_000)]).lower(), dtype=np.uint8).copy()
     out = np.zeros(lower.size, dtype=np.uint8)
     assert lib.mbgcg_selftest_pack(lower.ctypes.data, lower.size, out.ctypes.data) == 1
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/mbgc_b200.h is the drop-in boundary for any host language: it must compile as C99 on its own"""
+    import os
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc") or "/usr/bin/gcc"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "mbgc_b200.h"\nint main(void) { mbgcg_pack_params_t p; mbgcg_pack_result_t r; mbgcg_fasta_rec_t f; '
+                   'mbgcg_match_t m; mbgcg_state_t s; (void) p; (void) r; (void) f; (void) m; (void) s; return MBGCG_OK; }\n')
+    res = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"),
+                          "-c", str(src), "-o", str(tmp_path / "hdr.o")], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
