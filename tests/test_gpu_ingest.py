@@ -58,6 +58,18 @@ def test_ingested_texts_feed_the_match_stage():
         lists = g.matchBatchDevice(ing["dTexts"], recs[:, 2].copy(), recs[:, 3].copy(), 32)
         for c, got in zip(contigs, lists):
             assert np.array_equal(got, o.match(c))
+        # ... and, with the lists left on the device, the packer: file image -> six streams without the texts or the
+        # lists ever visiting the host
+        from test_gpu_pack import STREAMS, _oracle_pack, _params
+        po, pd = _params()
+        loaded = [o.loading_position]
+        g.matchBatchDevice(ing["dTexts"], recs[:, 2].copy(), recs[:, 3].copy(), 32, fetch=False)
+        out = g.packBatch(pd, None, None, loadedPosArr=loaded, lens=recs[:, 3].copy())
+        for i, c in enumerate(contigs):
+            ws, wk, wu = _oracle_pack(o, po, c, o.match(c), loaded=loaded)
+            for name in STREAMS:
+                assert out[name][i] == ws[name], f"record {i} stream {name}"
+            assert int(out["unmatched"][i]) == wu and int(out["kept"][i]) == len(wk)
     finally:
         g.close()
         o.close()
