@@ -1185,6 +1185,9 @@ __global__ void __launch_bounds__(256) k_extend(const ExtendArgs a) {
             const SeedRec sp_ = k == 1 ? sPrev : a.seeds[a.runFirst[r - k + 1] - 1];  // last segment of run r - k
             const uint32_t nm1 = sp_.n - 1u;  // its last seed
             const uint32_t pp = sp_.pos + nm1 * static_cast<uint32_t>(k1);
+            // interleaved diagonals sit within k1 positions of each other; a run further back than 2 k1 (and all before
+            // it: the list is in position order) belongs to another stretch of the text -- stop looking
+            if (k > 1 && static_cast<int64_t>(pp) + 2 * k1 < static_cast<int64_t>(firstPos)) break;
             const int64_t sp = static_cast<int64_t>(decode_pos(sp_.enc + nm1 * encStep, a.ix.k1ord));
             if (sp - static_cast<int64_t>(pp) != d) continue;
             int clsP;
@@ -1203,6 +1206,7 @@ __global__ void __launch_bounds__(256) k_extend(const ExtendArgs a) {
         for (uint32_t k = 1; k <= LINK_WINDOW && r + k < re; k++) {
             const SeedRec sn_ = k == 1 ? sNext : a.seeds[a.runFirst[r + k]];  // first segment of run r + k
             const uint32_t np = sn_.pos;
+            if (k > 1 && static_cast<int64_t>(np) > static_cast<int64_t>(lastPos) + 2 * k1) break;
             const int64_t sn = static_cast<int64_t>(decode_pos(sn_.enc, a.ix.k1ord));
             if (sn - static_cast<int64_t>(np) != d) continue;
             int clsN;
