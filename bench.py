@@ -47,7 +47,7 @@ ALG_BYTES_PER_POSITION = 6.0  # 1 ASCII + .25 + .25 packed + 4 tab
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--genomes", type=int, default=100, help="target genomes per rank")
