@@ -129,6 +129,7 @@ int mbgcg_pack_batch(mbgcg_t* h, const mbgcg_pack_params_t* p, int nTexts, const
                      const uint64_t* loadedPosArr, uint64_t nLoadedPos, mbgcg_pack_result_t* out) {
     std::memset(out, 0, sizeof(*out));
     return guarded(h, [&] {
+        if (!p || (nTexts > 0 && !lens)) throw MatcherError(MBGCG_E_PARAM, "pack_batch: parameters and text lengths are required");
         if (matches && (!texts || !counts)) throw MatcherError(MBGCG_E_PARAM, "pack_batch: match lists without texts / counts");
         mbgc_b200::PackParams pp{};
         pp.enableExt = p->enableExtensionsWithMismatches;
@@ -180,6 +181,7 @@ int mbgcg_ingest_fasta(mbgcg_t* h, const char* bytes, uint64_t n, const mbgcg_fa
     *nRecs = 0;
     return guarded(h, [&] {
         static_assert(sizeof(mbgcg_fasta_rec_t) == sizeof(mbgc_b200::FastaRecord), "FastaRecord layout");
+        if (n && !bytes) throw MatcherError(MBGCG_E_PARAM, "ingest_fasta: no file image");
         h->m->ingestFasta(bytes, n);
         *recs = reinterpret_cast<const mbgcg_fasta_rec_t*>(h->m->ingestedRecords().data());
         *nRecs = h->m->ingestedRecords().size();
