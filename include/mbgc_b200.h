@@ -254,6 +254,9 @@ enum {
     MBGCG_T_COUNT = 12
 };
 void mbgcg_last_timing(const mbgcg_t* h, float ms[MBGCG_T_COUNT]);
+/* on = 0: match calls stop recording their stage events (mbgcg_last_timing then returns zeros): a dozen event records
+ * less per call on the stream and on the calling thread.  Default: on. */
+void mbgcg_set_stage_timing(mbgcg_t* h, int on);
 /* counters of the last match call: 0 positions, 1 seed segments, 2 seed runs, 3 matches, 4 kernel launches,
  * 5 passes, 6 chunks (512 positions), 7 lanes (16 positions) that went through the full probe */
 void mbgcg_last_counters(const mbgcg_t* h, uint64_t out[8]);

@@ -262,6 +262,8 @@ int mbgcg_selftest_pack(const char* text, uint64_t n, char* out) {
     return 0;
 }
 
+void mbgcg_set_stage_timing(mbgcg_t* h, int on) { h->m->stageTiming = on != 0; }
+
 void mbgcg_last_timing(const mbgcg_t* h, float ms[MBGCG_T_COUNT]) {
     try {
         h->m->collectTiming();

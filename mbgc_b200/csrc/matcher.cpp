@@ -708,6 +708,10 @@ void B200SparseEMMatcher::matchBatch(const std::vector<TextView>& texts, const u
                                      bool textsOnDevice, const void* dTextBase, const uint64_t* dOffsets,
                                      bool listsStayOnDevice) {
     check(cudaSetDevice(device), "cudaSetDevice");
+    // stage boundaries for mbgcg_last_timing; switched off (stageTiming) the stream carries nothing but the work itself
+    auto mark = [&](int e) {
+        if (stageTiming) check(cudaEventRecord(ev[e], stream), "event");
+    };
     if (minMatchLength < static_cast<uint32_t>(K))
         throw MatcherError(MBGCG_E_PARAM, "Minimal matching length cannot be smaller than K (" +
                                               std::to_string(minMatchLength) + " < " + std::to_string(K) + ")");
@@ -776,7 +780,7 @@ void B200SparseEMMatcher::matchBatch(const std::vector<TextView>& texts, const u
             }
             hTile[nC] = tileStart[nC];
             const uint64_t metaUsed = static_cast<uint64_t>(nC) * 24 + 4;
-            check(cudaEventRecord(ev[0], stream), "event");
+            mark(0);
             check(cudaMemcpyAsync(dMeta, hMeta, metaUsed, cudaMemcpyHostToDevice, stream), "H2D(meta)");
             const uint8_t* textBase;
             if (textsOnDevice) {
@@ -791,7 +795,7 @@ void B200SparseEMMatcher::matchBatch(const std::vector<TextView>& texts, const u
                 textBase = dText;
             }
             check(cudaMemsetAsync(wb.counters, 0, 64, stream), "memset(counters)");
-            check(cudaEventRecord(ev[1], stream), "event");
+            mark(1);
 
             BatchDesc bd;
             bd.text = textBase;
@@ -809,21 +813,21 @@ void B200SparseEMMatcher::matchBatch(const std::vector<TextView>& texts, const u
             launches += launch_chunk_desc(ix, bd, wb, stream);
             if (useFast) {
                 launches += launch_anchor(ix, bd, wb, stream);
-                check(cudaEventRecord(ev[7], stream), "event");
+                mark(7);
                 launches += launch_clean(ix, bd, wb, MemoState{dMemoX, dMemoX + memoCapWords, memoLen}, stream);
-                check(cudaEventRecord(ev[8], stream), "event");
+                mark(8);
             } else {
-                check(cudaEventRecord(ev[7], stream), "event");
-                check(cudaEventRecord(ev[8], stream), "event");
+                mark(7);
+                mark(8);
             }
             launches += launch_probe(ix, bd, wb, useSharedFilter(), useFast, stream);
-            check(cudaEventRecord(ev[2], stream), "event");
+            mark(2);
             launches += launch_compact_and_runs(ix, bd, wb, useFast, stream);
-            check(cudaEventRecord(ev[3], stream), "event");
+            mark(3);
             launches += launch_extend(ix, bd, wb, stream);
-            check(cudaEventRecord(ev[4], stream), "event");
+            mark(4);
             launches += launch_resolve(ix, bd, wb, minMatchLength, stream);
-            check(cudaEventRecord(ev[5], stream), "event");
+            mark(5);
             check(cudaGetLastError(), "match pass launch");
             totalLaunches += static_cast<uint64_t>(launches);
             lastCounters[4] += static_cast<uint64_t>(launches);
@@ -842,7 +846,7 @@ void B200SparseEMMatcher::matchBatch(const std::vector<TextView>& texts, const u
             if (guess)
                 check(cudaMemcpyAsync(hMatches + nMatchesAll, wb.matchesDense, guess * sizeof(TextMatch),
                                       cudaMemcpyDeviceToHost, stream), "D2H(matches, guessed)");
-            check(cudaEventRecord(ev[6], stream), "event");
+            mark(6);
             check(cudaStreamSynchronize(stream), "match pass sync");
             if (hCtr[3]) {  // seed capacity exceeded: rerun this pass with the worst-case capacity
                 if (attempt > 0) throw MatcherError(MBGCG_E_NOMEM, "seed buffer overflow after retry");
@@ -868,12 +872,12 @@ void B200SparseEMMatcher::matchBatch(const std::vector<TextView>& texts, const u
                 check(cudaMemcpyAsync(passMatches + guess, wb.matchesDense + guess,
                                       (static_cast<uint64_t>(total) - guess) * sizeof(TextMatch), cudaMemcpyDeviceToHost,
                                       stream), "D2H(matches)");
-                check(cudaEventRecord(ev[6], stream), "event");
+                mark(6);
                 check(cudaStreamSynchronize(stream), "D2H sync");
             }
             nMatchesAll += total;
             for (int c = 0; c < nC; c++) resCounts[first + c] = hOffs[c + 1] - hOffs[c];
-            timingPending = true;  // the events of this pass are read when somebody asks (collectTiming)
+            timingPending = stageTiming;  // the events of this pass are read when somebody asks (collectTiming)
             if (last < texts.size()) collectTiming();  // more passes follow and will reuse the events
             // clean-fraction estimate for the fast-path policy (see wantMemo)
             if (useFast && tiles) {  // share of the 16-position lanes that did not need the full probe

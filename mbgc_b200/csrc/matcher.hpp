@@ -143,6 +143,7 @@ public:
     uint32_t hashSize = 0;
     int L = 0, K = 0, k1 = 0, k2 = 0, skipMargin = 0, k1ord = -1;
 
+    bool stageTiming = true;               // record the stage events of match calls (mbgcg_set_stage_timing)
     float stageMs[MBGCG_T_COUNT_] = {0};   // valid after collectTiming()
     void collectTiming();
     uint64_t lastCounters[8] = {0};

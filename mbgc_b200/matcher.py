@@ -122,6 +122,7 @@ def load_library():
     L.mbgcg_selftest_pack.restype = C.c_int
     L.mbgcg_selftest_pack.argtypes = [vp, C.c_uint64, vp]
     L.mbgcg_last_timing.argtypes = [vp, C.POINTER(C.c_float)]
+    L.mbgcg_set_stage_timing.argtypes = [vp, C.c_int]
     L.mbgcg_last_counters.argtypes = [vp, u64p]
     L.mbgcg_stream.restype = vp
     L.mbgcg_stream.argtypes = [vp]
@@ -356,6 +357,10 @@ class Matcher:
         out = np.empty(n, dtype=np.uint8)
         self._check(self.lib.mbgcg_copy_staged_text(self.h, index, out.ctypes.data))
         return out
+
+    def setStageTiming(self, on):
+        """switch the per-stage CUDA events of match calls off / on (timing() returns zeros while off)"""
+        self.lib.mbgcg_set_stage_timing(self.h, int(bool(on)))
 
     def timing(self):
         ms = (C.c_float * 12)()
