@@ -71,6 +71,15 @@ typedef struct {
  * occupancy bitmap; plus a host mirror of the reference buffer for getRef(). */
 int mbgcg_create(mbgcg_t** out, uint64_t refLengthLimit, uint32_t targetMatchLength, int k1, int k2, int skipMargin,
                  int device);
+/* The same matcher replicated on `ndev` devices: every replica holds the whole reference buffer and
+ * index; every state-changing call below (window configuration, load_ref, load_separator, locks, set_state,
+ * set_position) is applied to all of them in the same order, so the replicas stay bit-identical without any table
+ * contents travelling.  Single-text calls (mbgcg_match, mbgcg_match_batch*, mbgcg_pack_batch, mbgcg_ingest_fasta) and
+ * all getters use replica 0; the collection pass (mbgcg_seq_*) shards its windows over all replicas.
+ * mbgcg_create(..., device) == mbgcg_create_multi(..., &device, 1). */
+int mbgcg_create_multi(mbgcg_t** out, uint64_t refLengthLimit, uint32_t targetMatchLength, int k1, int k2, int skipMargin,
+                       const int* devices, int ndev);
+int mbgcg_device_count(const mbgcg_t* h);
 /* ~SlidingWindowSparseEMMatcher (ref .cpp:460-467) */
 void mbgcg_destroy(mbgcg_t* h);
 const char* mbgcg_last_error(const mbgcg_t* h);
@@ -199,6 +208,90 @@ int mbgcg_copy_ingested(mbgcg_t* h, uint64_t record, char* out);
 /* last ingest: ms[0..2] = file image host -> device, kernels (incl. two small host round trips), total (CUDA events);
  * kernel launches */
 void mbgcg_ingest_timing(const mbgcg_t* h, float ms[3], uint64_t* launches);
+
+/* ---- the collection pass: row a9 of SURVEY.md 8 -----------------------------------------------------------------
+ * Replaces the target loop of the reference's sequential schedule,
+ * MultipleGenomeMatchingProcessor::processTargetsWithParallelIO
+ * (/root/reference/matching/MultipleGenomeMatchingProcessor.cpp:232-313: per contig matchTexts :274 -> processMatches :276
+ * -> isContigProperForRefExtension / ...RCExtension :277-285 (MGMP_Params.h:179-196) -> loadRef :286; per file
+ * processTargetMeta :297 and the hook processAfterTargetWithParallelIO, mbgccoder/MBGC_Encoder.cpp:493-509: loadSeparator,
+ * refExtSize, acquire/releaseWorkerMatchingLockPos), batched and sharded over the handle's devices:
+ *
+ *   file images (as on disk, after gunzip) are pushed in target order; groups of them go to the replicas in turn, where
+ *   the FASTA ingest, the match stage (lists stay on the device) and the stream packer run for a whole window of contigs
+ *   against the frozen matcher state; results are committed in target order up to and including the first contig that
+ *   extends the reference; the extension reaches every replica device-to-device and the rest of the window runs again.
+ *
+ * What comes out is byte-identical to the one-contig-at-a-time schedule (`mbgc -t 1`).  The caller keeps what belongs to
+ * the encoder: headers, stream concatenation, separator marks, meta streams.  While a pass is in progress no other call
+ * may be made on the handle; the host mirror behind mbgcg_host_ref is switched off by mbgcg_seq_begin (extensions come
+ * from device memory). */
+typedef struct {
+    mbgcg_pack_params_t pack;
+    uint32_t minMatchLength;            /* params->k (MultipleGenomeMatchingProcessor.cpp:274) */
+    int32_t unmatchedFractionFactor;    /* currentUnmatchedFractionFactor (MGMP_Params.h:41,179-187) */
+    int32_t unmatchedFractionRCFactor;  /* unmatchedFractionRCFactor (MGMP_Params.h:42,189-191) */
+    int32_t rcInReferenceDisabled;      /* isRCinReferenceDisabled() (MGMP_Params.h:82-84) */
+    int32_t refRegionSeparators;        /* params->refRegionSeparators */
+    int32_t separatorPerFile;           /* lazyDecompressionSupport: loadSeparator + a refExtLoadedPosArr entry per file */
+    char regionSeparator;               /* MGMP_Params::REF_REGION_SEPARATOR */
+    uint64_t chunkBytes;                /* file-image bytes per ingest slot; 0 = default (64 MiB) */
+    uint32_t maxWindowContigs;          /* speculation window; 0 = default */
+} mbgcg_seq_config_t;
+
+enum { MBGCG_EV_CONTIG = 1, MBGCG_EV_FILE_END = 2, MBGCG_EV_NEED_INPUT = 3, MBGCG_EV_DONE = 4 };
+
+typedef struct {
+    int32_t type;
+    int32_t status;          /* FILE_END: what ended the reader's loop for this file: -1 end of file, -3 not FASTA, -4 DNA
+                              * not well-formed (MBGC exits on the last two, MultipleGenomeMatchingProcessor.cpp:17-30) */
+    uint64_t file;           /* index of the file in push order */
+    /* CONTIG: one committed contig, in target order */
+    const char* hdr;         /* the header line (seq->name of the lossless reader), valid until the next call */
+    uint64_t hdrLen;
+    uint64_t seqLen;
+    uint64_t nMatches;       /* resMatches.size() */
+    uint64_t kept;           /* matches left after pass 1 of processMatches */
+    uint64_t unmatched;      /* processMatches' return value */
+    int32_t extended;        /* the contig was loaded into the reference ... */
+    int32_t extendedRC;      /* ... and its reverse complement */
+    const uint8_t* seg[MBGCG_S_COUNT];   /* what processMatches appends to the six streams; valid until the next call */
+    uint64_t segLen[MBGCG_S_COUNT];
+    /* FILE_END */
+    uint64_t nContigs;       /* seqCounter */
+    uint64_t dnaLineLen;     /* KSEQ_DNA_LINE_LENGTH(seq) */
+    uint64_t refExtSize;     /* getLoadedRefLength() - startPos after the separator (MBGC_Encoder.cpp:502) */
+    uint64_t lockPos;        /* the value appended to locksPosStream (MBGC_Encoder.cpp:506-508) */
+    uint64_t loadedRefLength;/* getLoadedRefLength() afterwards (also in DONE) */
+} mbgcg_seq_event_t;
+
+typedef struct {
+    uint64_t files, contigs, windows, runs, rerunContigs, extensions;
+    uint64_t imageBytes, textBytes, pageableBytes, launches, chunks;
+    double ingestMs, matchMs, packMs, loadRefMs, waitStageMs;  /* host wall time inside the respective calls */
+} mbgcg_seq_stats_t;
+
+/* loadedPosArr = refExtLoadedPosArr as it stands (MBGC_Encoder.cpp:786-791); the pass appends to its own copy */
+int mbgcg_seq_begin(mbgcg_t* h, const mbgcg_seq_config_t* cfg, const uint64_t* loadedPosArr, uint64_t nLoadedPos);
+/* next file image, HOST pointer.  Memory from mbgcg_image_alloc now belongs to the pass (it is released as soon as the
+ * image is on the device); any other memory must stay valid until the file's FILE_END event has been returned. */
+int mbgcg_seq_push_file(mbgcg_t* h, const char* bytes, uint64_t n);
+int mbgcg_seq_finish_input(mbgcg_t* h);
+/* 1 while the pass can use more images to keep the devices busy (about two windows ahead of the commit cursor) */
+int mbgcg_seq_wants_input(mbgcg_t* h);
+/* next event in target order; MBGCG_EV_NEED_INPUT = nothing can be committed before another file (or finish_input) */
+int mbgcg_seq_next(mbgcg_t* h, mbgcg_seq_event_t* ev);
+int mbgcg_seq_end(mbgcg_t* h, mbgcg_seq_stats_t* stats);
+
+/* Pinned host memory for file images, cut from large slabs (cudaHostAlloc costs ~0.5 ms per MiB): DMA reads it at PCIe
+ * speed, pageable images travel through bounce buffers at ~1/4 of that.  NULL when the arena is full -- use any other
+ * memory then.  mbgcg_image_free only for images that were never pushed. */
+void* mbgcg_image_alloc(mbgcg_t* h, uint64_t n);
+int mbgcg_image_free(mbgcg_t* h, const void* p);
+
+/* switches the host mirror behind mbgcg_host_ref off / on (only the reference's own CPU packer reads it,
+ * MBGC_Encoder.cpp:181,318-330,376-380); while it is off mbgcg_load_ref skips the host-side copy */
+void mbgcg_set_host_mirror(mbgcg_t* h, int on);
 
 /* ---- sliding-window locks (ref .cpp:361-400) ------------------------------------------------------------ */
 uint64_t mbgcg_acquire_lock(mbgcg_t* h);

@@ -6,6 +6,6 @@ SlidingWindowSparseEMMatcher (/root/reference/matching/SlidingWindowSparseEMMatc
 method through ctypes.  There is no CPU fallback: importing works anywhere, but creating a Matcher needs the
 built library and a CUDA device and fails loudly otherwise.
 """
-from .matcher import Matcher, MatcherError, NO_LOCK, lib_path, load_library  # noqa: F401
+from .matcher import Matcher, MatcherError, NO_LOCK, PackParams, SeqConfig, lib_path, load_library  # noqa: F401
 
-__all__ = ["Matcher", "MatcherError", "NO_LOCK", "lib_path", "load_library"]
+__all__ = ["Matcher", "MatcherError", "NO_LOCK", "PackParams", "SeqConfig", "lib_path", "load_library"]

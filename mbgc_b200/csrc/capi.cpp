@@ -4,15 +4,20 @@
 #include <vector>
 
 #include "../../include/mbgc_b200.h"
+#include "collection.hpp"
 #include "matcher.hpp"
 
 using mbgc_b200::B200SparseEMMatcher;
+using mbgc_b200::ReplicaSet;
+using mbgc_b200::SequentialPass;
 using mbgc_b200::MatcherError;
 using mbgc_b200::TextMatch;
 using mbgc_b200::TextView;
 
 struct mbgcg {
+    ReplicaSet* rs = nullptr;            // the replicas (one per device); m = replica 0
     B200SparseEMMatcher* m = nullptr;
+    SequentialPass* pass = nullptr;      // the collection pass in progress, if any
     std::string err;
     std::vector<TextMatch> single;
     std::vector<TextMatch> kept;
@@ -40,13 +45,16 @@ static int guarded(mbgcg_t* h, F&& f) {
 
 extern "C" {
 
-int mbgcg_create(mbgcg_t** out, uint64_t refLengthLimit, uint32_t targetMatchLength, int k1, int k2, int skipMargin,
-                 int device) {
+int mbgcg_create_multi(mbgcg_t** out, uint64_t refLengthLimit, uint32_t targetMatchLength, int k1, int k2, int skipMargin,
+                       const int* devices, int ndev) {
+    if (!out) return MBGCG_E_PARAM;
     *out = nullptr;
     try {
+        if (!devices || ndev < 1) throw MatcherError(MBGCG_E_PARAM, "mbgcg_create_multi: no devices");
         mbgcg_t* h = new mbgcg();
         try {
-            h->m = new B200SparseEMMatcher(refLengthLimit, targetMatchLength, k1, k2, skipMargin, device);
+            h->rs = new ReplicaSet(refLengthLimit, targetMatchLength, k1, k2, skipMargin, devices, ndev);
+            h->m = h->rs->primary();
         } catch (...) {
             delete h;
             throw;
@@ -62,26 +70,46 @@ int mbgcg_create(mbgcg_t** out, uint64_t refLengthLimit, uint32_t targetMatchLen
     }
 }
 
+int mbgcg_create(mbgcg_t** out, uint64_t refLengthLimit, uint32_t targetMatchLength, int k1, int k2, int skipMargin,
+                 int device) {
+    return mbgcg_create_multi(out, refLengthLimit, targetMatchLength, k1, k2, skipMargin, &device, 1);
+}
+
+int mbgcg_device_count(const mbgcg_t* h) { return h->rs->size(); }
+
 void mbgcg_destroy(mbgcg_t* h) {
     if (!h) return;
-    delete h->m;
+    delete h->pass;
+    delete h->rs;   // owns the matchers
     delete h;
 }
 
 const char* mbgcg_last_error(const mbgcg_t* h) { return h ? h->err.c_str() : ""; }
 const char* mbgcg_create_error(void) { return g_createError.c_str(); }
 
-void mbgcg_disable_sliding_window(mbgcg_t* h) { h->m->disableSlidingWindow(); }
-void mbgcg_disable_circular_buffer(mbgcg_t* h) { h->m->disableCircularBuffer(); }
-void mbgcg_set_sliding_window_size(mbgcg_t* h, int factor) { h->m->setSlidingWindowSize(static_cast<uint8_t>(factor)); }
+// state-changing calls reach every replica: each does the identical host bookkeeping and the identical ordered inserts
+void mbgcg_disable_sliding_window(mbgcg_t* h) {
+    for (int r = 0; r < h->rs->size(); r++) h->rs->at(r)->disableSlidingWindow();
+}
+void mbgcg_disable_circular_buffer(mbgcg_t* h) {
+    for (int r = 0; r < h->rs->size(); r++) h->rs->at(r)->disableCircularBuffer();
+}
+void mbgcg_set_sliding_window_size(mbgcg_t* h, int factor) {
+    for (int r = 0; r < h->rs->size(); r++) h->rs->at(r)->setSlidingWindowSize(static_cast<uint8_t>(factor));
+}
 
 int mbgcg_load_ref(mbgcg_t* h, const char* text, uint64_t len, int loadRC, int addSeparators, char separator) {
-    return guarded(h, [&] { h->m->loadRef(text, len, loadRC != 0, addSeparators != 0, separator); });
+    return guarded(h, [&] {
+        if (len && !text) throw MatcherError(MBGCG_E_PARAM, "load_ref: no text");
+        h->rs->loadRef(text, len, loadRC != 0, addSeparators != 0, separator);
+    });
 }
 
 int mbgcg_load_separator(mbgcg_t* h, char separator) {
-    return guarded(h, [&] { h->m->loadSeparator(separator); });
+    return guarded(h, [&] { h->rs->loadSeparator(separator); });
 }
+
+void mbgcg_set_host_mirror(mbgcg_t* h, int on) { h->rs->setHostMirror(on != 0); }
 
 int mbgcg_match(mbgcg_t* h, const char* text, uint64_t len, uint32_t minMatchLength, uint64_t lockPos,
                 const mbgcg_match_t** out, uint64_t* n) {
@@ -97,8 +125,10 @@ int mbgcg_match(mbgcg_t* h, const char* text, uint64_t len, uint32_t minMatchLen
 int mbgcg_match_batch(mbgcg_t* h, int nTexts, const char* const* texts, const uint64_t* lens, uint32_t minMatchLength,
                       const uint64_t* lockPos, const mbgcg_match_t** out, const uint64_t** counts) {
     if (out) *out = nullptr;
+    if (!counts) return MBGCG_E_PARAM;
     *counts = nullptr;
     return guarded(h, [&] {
+        if (nTexts < 0 || (nTexts > 0 && (!texts || !lens))) throw MatcherError(MBGCG_E_PARAM, "match_batch: texts and lengths are required");
         std::vector<TextView> tv(static_cast<size_t>(nTexts));
         for (int i = 0; i < nTexts; i++) tv[i] = TextView{texts[i], lens[i]};
         h->m->matchBatch(tv, lockPos, minMatchLength, false, nullptr, nullptr, out == nullptr);
@@ -111,8 +141,13 @@ int mbgcg_match_batch_device(mbgcg_t* h, const void* dText, int nTexts, const ui
                              uint32_t minMatchLength, const uint64_t* lockPos, const mbgcg_match_t** out,
                              const uint64_t** counts) {
     if (out) *out = nullptr;
+    if (!counts) return MBGCG_E_PARAM;
     *counts = nullptr;
     return guarded(h, [&] {
+        if (nTexts < 0 || (nTexts > 0 && (!dText || !offsets || !lens)))
+            throw MatcherError(MBGCG_E_PARAM, "match_batch_device: device text, offsets and lengths are required");
+        if (reinterpret_cast<uintptr_t>(dText) % 16)
+            throw MatcherError(MBGCG_E_PARAM, "match_batch_device: the device text buffer must be 16-byte aligned");
         std::vector<TextView> tv(static_cast<size_t>(nTexts));
         for (int i = 0; i < nTexts; i++) {
             if (offsets[i] % 16) throw MatcherError(MBGCG_E_PARAM, "device text offsets must be multiples of 16");
@@ -127,6 +162,7 @@ int mbgcg_match_batch_device(mbgcg_t* h, const void* dText, int nTexts, const ui
 int mbgcg_pack_batch(mbgcg_t* h, const mbgcg_pack_params_t* p, int nTexts, const char* const* texts, const uint64_t* lens,
                      const mbgcg_match_t* matches, const uint64_t* counts, const uint64_t* lockPos,
                      const uint64_t* loadedPosArr, uint64_t nLoadedPos, mbgcg_pack_result_t* out) {
+    if (!out) return MBGCG_E_PARAM;
     std::memset(out, 0, sizeof(*out));
     return guarded(h, [&] {
         if (!p || (nTexts > 0 && !lens)) throw MatcherError(MBGCG_E_PARAM, "pack_batch: parameters and text lengths are required");
@@ -200,9 +236,9 @@ void mbgcg_ingest_timing(const mbgcg_t* h, float ms[3], uint64_t* launches) {
     if (launches) *launches = h->m->ingestLaunches();
 }
 
-uint64_t mbgcg_acquire_lock(mbgcg_t* h) { return h->m->acquireWorkerMatchingLockPos(); }
+uint64_t mbgcg_acquire_lock(mbgcg_t* h) { return h->rs->acquireLock(); }
 int mbgcg_release_lock(mbgcg_t* h, uint64_t lockValue) {
-    return guarded(h, [&] { h->m->releaseWorkerMatchingLockPos(lockValue); });
+    return guarded(h, [&] { h->rs->releaseLock(lockValue); });
 }
 
 const char* mbgcg_host_ref(const mbgcg_t* h) { return h->m->getRef(); }
@@ -210,7 +246,9 @@ uint64_t mbgcg_max_ref_length(const mbgcg_t* h) { return h->m->getMaxRefLength()
 uint64_t mbgcg_ref_length(const mbgcg_t* h) { return h->m->getRefLength(); }
 uint64_t mbgcg_loading_position(const mbgcg_t* h) { return h->m->getLoadingPosition(); }
 uint64_t mbgcg_loaded_ref_length(const mbgcg_t* h) { return h->m->getLoadedRefLength(); }
-void mbgcg_set_position(mbgcg_t* h, uint64_t refPos, int reached) { h->m->setPosition(refPos, reached); }
+void mbgcg_set_position(mbgcg_t* h, uint64_t refPos, int reached) {
+    for (int r = 0; r < h->rs->size(); r++) h->rs->at(r)->setPosition(refPos, reached);
+}
 
 void mbgcg_get_state(const mbgcg_t* h, mbgcg_state_t* out) {
     const B200SparseEMMatcher* m = h->m;
@@ -234,6 +272,7 @@ void mbgcg_set_state(mbgcg_t* h, const mbgcg_state_t* in) {
     m->swSize = in->swSize;
     m->swEnd = in->swEnd;
     m->samplingPos = in->samplingPos;
+    if (h->rs->size() > 1) h->rs->syncStateFromPrimary();
 }
 
 int mbgcg_copy_table(mbgcg_t* h, uint32_t* out, uint64_t nSlots) {
@@ -276,5 +315,122 @@ void mbgcg_last_counters(const mbgcg_t* h, uint64_t out[8]) {
 }
 uint64_t mbgcg_total_launches(const mbgcg_t* h) { return h->m->totalLaunches; }
 void* mbgcg_stream(const mbgcg_t* h) { return h->m->streamHandle(); }
+
+// ---- pinned host memory for file images -----------------------------------------------------------------------------
+void* mbgcg_image_alloc(mbgcg_t* h, uint64_t n) {
+    try {
+        return h->rs->arena().alloc(n);
+    } catch (...) {
+        return nullptr;
+    }
+}
+int mbgcg_image_free(mbgcg_t* h, const void* p) { return h->rs->arena().release(p) ? MBGCG_OK : MBGCG_E_PARAM; }
+
+// ---- the sequential schedule over a collection, batched and sharded over the handle's devices ---------------------------
+int mbgcg_seq_begin(mbgcg_t* h, const mbgcg_seq_config_t* c, const uint64_t* loadedPosArr, uint64_t nLoadedPos) {
+    return guarded(h, [&] {
+        if (!c) throw MatcherError(MBGCG_E_PARAM, "seq_begin: no configuration");
+        if (h->pass) throw MatcherError(MBGCG_E_PARAM, "seq_begin: a pass is already in progress on this handle");
+        mbgc_b200::SeqConfig sc;
+        const mbgcg_pack_params_t* p = &c->pack;
+        sc.pack.enableExt = p->enableExtensionsWithMismatches;
+        sc.pack.gapDepthOffset = p->gapDepthOffsetEncoding;
+        sc.pack.gapDepthMismatches = p->gapDepthMismatchesEncoding;
+        sc.pack.lazy = p->lazyDecompressionSupport;
+        sc.pack.frugalLen = p->frugal64bitLenEncoding;
+        sc.pack.enable40bit = p->enable40bitReference;
+        sc.pack.withExclusion = p->mismatchesWithExclusion;
+        sc.pack.initialScore = p->mmsMismatchesInitialScore;
+        sc.pack.scoreThreshold = p->mmsMismatchesScoreThreshold;
+        sc.pack.mismatchPenalty = p->mmsMismatchPenalty;
+        sc.pack.matchBonus = p->mmsMatchBonus;
+        sc.pack.gapBreakingMinLen = p->gapBreakingMatchMinLength;
+        sc.minMatchLength = c->minMatchLength;
+        sc.unmatchedFractionFactor = c->unmatchedFractionFactor;
+        sc.unmatchedFractionRCFactor = c->unmatchedFractionRCFactor;
+        sc.rcDisabled = c->rcInReferenceDisabled != 0;
+        sc.refRegionSeparators = c->refRegionSeparators != 0;
+        sc.separator = c->regionSeparator;
+        sc.separatorPerFile = c->separatorPerFile != 0;
+        if (c->chunkBytes) sc.chunkBytes = c->chunkBytes;
+        if (c->maxWindowContigs) sc.maxWindowContigs = c->maxWindowContigs;
+        if (nLoadedPos && !loadedPosArr) throw MatcherError(MBGCG_E_PARAM, "seq_begin: loaded positions missing");
+        h->pass = new SequentialPass(*h->rs, sc, loadedPosArr, nLoadedPos);
+    });
+}
+
+int mbgcg_seq_push_file(mbgcg_t* h, const char* bytes, uint64_t n) {
+    return guarded(h, [&] {
+        if (!h->pass) throw MatcherError(MBGCG_E_PARAM, "seq_push_file: no pass in progress");
+        if (n && !bytes) throw MatcherError(MBGCG_E_PARAM, "seq_push_file: no file image");
+        h->pass->pushFile(bytes, n);
+    });
+}
+
+int mbgcg_seq_finish_input(mbgcg_t* h) {
+    return guarded(h, [&] {
+        if (!h->pass) throw MatcherError(MBGCG_E_PARAM, "seq_finish_input: no pass in progress");
+        h->pass->finishInput();
+    });
+}
+
+int mbgcg_seq_wants_input(mbgcg_t* h) { return h->pass && h->pass->wantsInput() ? 1 : 0; }
+
+int mbgcg_seq_next(mbgcg_t* h, mbgcg_seq_event_t* ev) {
+    if (!ev) return MBGCG_E_PARAM;
+    std::memset(ev, 0, sizeof(*ev));
+    return guarded(h, [&] {
+        if (!h->pass) throw MatcherError(MBGCG_E_PARAM, "seq_next: no pass in progress");
+        mbgc_b200::SeqEvent e;
+        h->pass->next(e);
+        ev->type = e.type;
+        ev->status = e.status;
+        ev->file = e.file;
+        ev->hdr = e.hdr;
+        ev->hdrLen = e.hdrLen;
+        ev->seqLen = e.seqLen;
+        ev->nMatches = e.nMatches;
+        ev->kept = e.kept;
+        ev->unmatched = e.unmatched;
+        ev->extended = e.extended;
+        ev->extendedRC = e.extendedRC;
+        for (int s = 0; s < MBGCG_S_COUNT; s++) {
+            ev->seg[s] = e.seg[s];
+            ev->segLen[s] = e.segLen[s];
+        }
+        ev->nContigs = e.nContigs;
+        ev->dnaLineLen = e.dnaLineLen;
+        ev->refExtSize = e.refExtSize;
+        ev->lockPos = e.lockPos;
+        ev->loadedRefLength = e.loadedRefLength;
+    });
+}
+
+int mbgcg_seq_end(mbgcg_t* h, mbgcg_seq_stats_t* stats) {
+    return guarded(h, [&] {
+        if (!h->pass) throw MatcherError(MBGCG_E_PARAM, "seq_end: no pass in progress");
+        if (stats) {
+            const mbgc_b200::SeqStats& s = h->pass->stats();
+            stats->files = s.files;
+            stats->contigs = s.contigs;
+            stats->windows = s.windows;
+            stats->runs = s.runs;
+            stats->rerunContigs = s.rerunContigs;
+            stats->extensions = s.extensions;
+            stats->imageBytes = s.imageBytes;
+            stats->textBytes = s.textBytes;
+            stats->pageableBytes = s.pageableBytes;
+            stats->launches = s.launches + s.ingestLaunches;
+            stats->chunks = s.chunks;
+            stats->ingestMs = s.ingestMs;
+            stats->matchMs = s.matchMs;
+            stats->packMs = s.packMs;
+            stats->loadRefMs = s.loadRefMs;
+            stats->waitStageMs = s.waitStageMs;
+        }
+        delete h->pass;
+        h->pass = nullptr;
+    });
+}
 
 }  // extern "C"

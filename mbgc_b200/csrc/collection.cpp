@@ -1,0 +1,849 @@
+// mbgc_b200/csrc/collection.cpp -- see collection.hpp.
+#include "collection.hpp"
+
+#include <algorithm>
+#include <chrono>
+#include <cstdlib>
+#include <cstring>
+
+#include "../../include/mbgc_b200.h"
+
+namespace mbgc_b200 {
+
+namespace {
+constexpr uint64_t PAD = 64, TEXT_GAP = 64, TEXT_TAIL = 8192;  // = matcher.cpp
+constexpr uint64_t BOUNCE_BYTES = 8ull << 20;
+inline uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
+inline double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+bool is_pinned(const void* p) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return attr.type == cudaMemoryTypeHost;
+}
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------------
+// FastaBatchIngest
+// ---------------------------------------------------------------------------------------------------------------------
+
+void FastaBatchIngest::check(cudaError_t e, const char* what) {
+    if (e != cudaSuccess) throw MatcherError(MBGCG_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+void FastaBatchIngest::grow(uint8_t** p, uint64_t* cap, uint64_t need, const char* what) {
+    if (need <= *cap) return;
+    cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    const uint64_t c = align_up(need + need / 8, 1 << 20);
+    check(cudaMalloc(p, c), what);
+    *cap = c;
+}
+
+FastaBatchIngest::FastaBatchIngest(int dev) : device(dev) {
+    check(cudaSetDevice(device), "cudaSetDevice");
+    check(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate");
+    for (auto& e : ev) check(cudaEventCreate(&e), "cudaEventCreate");
+    for (auto& e : bounceEv) check(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
+}
+
+FastaBatchIngest::~FastaBatchIngest() {
+    cudaSetDevice(device);
+    if (stream) cudaStreamSynchronize(stream);
+    cudaFree(dIn);
+    cudaFree(dWork);
+    cudaFree(dText);
+    if (hWork) cudaFreeHost(hWork);
+    for (auto& b : hBounce)
+        if (b) cudaFreeHost(b);
+    for (auto& e : ev)
+        if (e) cudaEventDestroy(e);
+    for (auto& e : bounceEv)
+        if (e) cudaEventDestroy(e);
+    if (stream) cudaStreamDestroy(stream);
+}
+
+// The per-file loop of ingest.cpp (B200SparseEMMatcher::ingestFasta) for a batch of images in one device buffer: image f
+// sits at a 16-byte aligned offset with 16 '\n' in front of it; a record ends at its file's end (k_fa_records clamps).
+void FastaBatchIngest::run(const HostImage* images, int nFiles) {
+    check(cudaSetDevice(device), "cudaSetDevice");
+    files.assign(static_cast<size_t>(nFiles), IngestedFile{});
+    contigs.clear();
+    launches = 0;
+    imageBytes = textBytes = wireBytes = 0;
+    ms[0] = ms[1] = ms[2] = 0;
+
+    // layout: only images that can hold a record travel (the others are decided here: kseq.h:239-240)
+    std::vector<int> live;
+    std::vector<uint64_t> spans;  // start, end per live image (offsets behind the 16 leading bytes)
+    uint64_t cursor = 0;
+    for (int f = 0; f < nFiles; f++) {
+        const HostImage& im = images[f];
+        if (im.n == 0) continue;                       // end of file before the first header: status -1, no records
+        if (im.bytes[0] != '>') {                      // not FASTA
+            files[f].status = -3;
+            continue;
+        }
+        if (im.n >= (1ull << 40)) throw MatcherError(MBGCG_E_UNSUPPORTED, "FASTA image of 1 TiB or more");
+        live.push_back(f);
+        spans.push_back(cursor);
+        spans.push_back(cursor + im.n);
+        cursor = align_up(cursor + im.n, 16) + 16;
+        imageBytes += im.n;
+    }
+    const uint32_t nLive = static_cast<uint32_t>(live.size());
+    if (nLive == 0) {
+        grow(&dText, &dTextCap, PAD + TEXT_TAIL, "cudaMalloc(ingested texts)");
+        return;
+    }
+    const uint64_t n = spans.back();                   // end of the last image
+    const uint64_t inBytes = 16 + align_up(n, 16) + 64;
+    grow(&dIn, &dInCap, inBytes, "cudaMalloc(fasta images)");
+    uint8_t* in = dIn + 16;
+
+    // ---- images -> device ----
+    check(cudaEventRecord(ev[0], stream), "event");
+    int bounceUse = 0;
+    for (uint32_t k = 0; k < nLive; k++) {
+        const HostImage& im = images[live[k]];
+        uint8_t* dst = in + spans[2 * k];
+        if (is_pinned(im.bytes)) {
+            check(cudaMemcpyAsync(dst, im.bytes, im.n, cudaMemcpyHostToDevice, stream), "H2D(fasta image)");
+        } else {  // pageable: through the pinned bounce buffers, one being filled while the other is on the wire
+            for (uint64_t o = 0; o < im.n; o += BOUNCE_BYTES) {
+                const uint64_t m = std::min<uint64_t>(BOUNCE_BYTES, im.n - o);
+                const int b = bounceUse & 1;
+                if (!hBounce[b]) check(cudaHostAlloc(reinterpret_cast<void**>(&hBounce[b]), BOUNCE_BYTES, cudaHostAllocDefault), "cudaHostAlloc(bounce)");
+                else if (bounceUse >= 2) check(cudaEventSynchronize(bounceEv[b]), "bounce sync");
+                std::memcpy(hBounce[b], im.bytes + o, m);
+                check(cudaMemcpyAsync(dst + o, hBounce[b], m, cudaMemcpyHostToDevice, stream), "H2D(fasta image)");
+                check(cudaEventRecord(bounceEv[b], stream), "event");
+                bounceUse++;
+            }
+        }
+        wireBytes += im.n;
+    }
+    // descriptors: spans, then file ends
+    const uint32_t blocks = static_cast<uint32_t>((n + FA_BLOCK_BYTES - 1) / FA_BLOCK_BYTES);
+    const uint64_t oSpans = 0;
+    const uint64_t oEnds = align_up(oSpans + nLive * 16ull, 256);
+    const uint64_t oCnt = align_up(oEnds + nLive * 8ull, 256);
+    const uint64_t cntBytes = align_up((blocks + 2ull) * 4, 256);
+    const uint64_t fixedBytes = oCnt + cntBytes;
+    grow(&dWork, &dWorkCap, fixedBytes + (1 << 20), "cudaMalloc(fasta work)");
+    auto growHost = [&](uint64_t need) {
+        if (need <= hWorkCap) return;
+        if (hWork) cudaFreeHost(hWork);
+        hWork = nullptr;
+        hWorkCap = 0;
+        const uint64_t c = align_up(need + need / 4, 1 << 16);
+        check(cudaHostAlloc(reinterpret_cast<void**>(&hWork), c, cudaHostAllocDefault), "cudaHostAlloc(fasta work)");
+        hWorkCap = c;
+    };
+    growHost(oCnt + 64);
+    std::memcpy(hWork + oSpans, spans.data(), nLive * 16ull);
+    uint64_t* hEnds = reinterpret_cast<uint64_t*>(hWork + oEnds);
+    for (uint32_t k = 0; k < nLive; k++) hEnds[k] = spans[2 * k + 1];
+    check(cudaMemcpyAsync(dWork, hWork, oEnds + nLive * 8ull, cudaMemcpyHostToDevice, stream), "H2D(fasta descriptors)");
+    const uint64_t* dSpans = reinterpret_cast<const uint64_t*>(dWork + oSpans);
+    const uint64_t* dEnds = reinterpret_cast<const uint64_t*>(dWork + oEnds);
+    int nl = launch_fa_filler(in, dSpans, nLive, inBytes - 16, stream);
+    check(cudaEventRecord(ev[1], stream), "event");
+
+    // ---- record starts ----
+    uint32_t* dCnt = reinterpret_cast<uint32_t*>(dWork + oCnt);
+    nl += launch_fa_count(in, n, dCnt, stream);
+    uint32_t* hN = reinterpret_cast<uint32_t*>(hWork + oCnt);
+    check(cudaMemcpyAsync(hN, dCnt + blocks, 4, cudaMemcpyDeviceToHost, stream), "D2H(record count)");
+    check(cudaStreamSynchronize(stream), "ingest sync");
+    const uint32_t nRecs = *hN;
+    if (nRecs < nLive) throw MatcherError(MBGCG_E_CUDA, "FASTA ingest found fewer record starts than files");
+
+    const uint64_t oStarts = fixedBytes;
+    const uint64_t oRecs = align_up(oStarts + nRecs * 8ull, 256);
+    const uint64_t oGather = align_up(oRecs + nRecs * sizeof(FaRecord), 256);
+    const uint64_t workBytes = oGather + nRecs * sizeof(FaGather) + 256;
+    if (workBytes > dWorkCap) {  // grow, keeping descriptors and block offsets
+        uint8_t* grown = nullptr;
+        const uint64_t cap = align_up(workBytes + workBytes / 4, 1 << 20);
+        check(cudaMalloc(reinterpret_cast<void**>(&grown), cap), "cudaMalloc(fasta work)");
+        check(cudaMemcpyAsync(grown, dWork, fixedBytes, cudaMemcpyDeviceToDevice, stream), "D2D(fasta work)");
+        check(cudaStreamSynchronize(stream), "ingest sync");
+        cudaFree(dWork);
+        dWork = grown;
+        dWorkCap = cap;
+        dCnt = reinterpret_cast<uint32_t*>(dWork + oCnt);
+        dSpans = reinterpret_cast<const uint64_t*>(dWork + oSpans);
+        dEnds = reinterpret_cast<const uint64_t*>(dWork + oEnds);
+    }
+    uint64_t* dStarts = reinterpret_cast<uint64_t*>(dWork + oStarts);
+    FaRecord* dRecs = reinterpret_cast<FaRecord*>(dWork + oRecs);
+    FaGather* dGather = reinterpret_cast<FaGather*>(dWork + oGather);
+    nl += launch_fa_starts(in, n, dCnt, dStarts, stream);
+    nl += launch_fa_records(in, n, dStarts, nRecs, dRecs, stream, dEnds, nLive);
+    growHost(nRecs * (sizeof(FaRecord) + sizeof(FaGather)) + 64);
+    FaRecord* hRecs = reinterpret_cast<FaRecord*>(hWork);
+    FaGather* hGather = reinterpret_cast<FaGather*>(hRecs + nRecs);
+    check(cudaMemcpyAsync(hRecs, dRecs, nRecs * sizeof(FaRecord), cudaMemcpyDeviceToHost, stream), "D2H(records)");
+    check(cudaStreamSynchronize(stream), "ingest sync");
+
+    // ---- the reader's file-wide state, file by file, record by record (kseq.h:253-256, 260-265) ----
+    uint64_t outCursor = PAD, chunks = 0;
+    uint32_t accepted = 0, r = 0;
+    for (uint32_t k = 0; k < nLive; k++) {
+        const int f = live[k];
+        IngestedFile& fi = files[f];
+        const uint64_t fStart = spans[2 * k], fEnd = spans[2 * k + 1];
+        fi.firstContig = static_cast<uint32_t>(contigs.size());
+        uint64_t dna = 0, maxLast = 0;
+        bool stopped = false;
+        while (r < nRecs && hRecs[r].start < fEnd) {
+            const FaRecord& rec = hRecs[r++];
+            if (stopped) continue;
+            if (rec.start + 1 >= fEnd) {  // '>' is the file's last byte: kseq.h:244 returns end of file, the record does not exist
+                stopped = true;
+                continue;
+            }
+            const uint64_t seqStart = rec.hdrEnd + 1;
+            const uint64_t len = rec.regionEnd > seqStart ? rec.regionEnd - seqStart : 0;
+            const uint64_t body = len - (rec.endsWithNl ? 1 : 0);
+            const uint64_t line = rec.firstLine;
+            bool bad = rec.bad != 0;
+            uint64_t seqLen = 0, lastLen = 0;
+            if (!bad && body) {
+                const uint64_t fullLines = body / (line + 1);
+                seqLen = body - fullLines;
+                lastLen = body - fullLines * (line + 1);
+                if (fullLines) {
+                    if (dna == 0) dna = line;
+                    else if (dna != line) bad = true;
+                }
+            }
+            if (lastLen > maxLast) maxLast = lastLen;
+            if (!bad && dna && dna < maxLast) bad = true;
+            if (bad) {
+                dna = UINT64_MAX;
+                fi.status = -4;
+                stopped = true;
+                continue;
+            }
+            if (seqLen >= (1ull << 32)) throw MatcherError(MBGCG_E_UNSUPPORTED, "sequence of 4 GiB or more");
+            hGather[accepted] = FaGather{seqStart, outCursor, seqLen, seqLen ? line : 0, chunks};
+            contigs.push_back(IngestedContig{static_cast<uint32_t>(f), rec.start + 1 - fStart,
+                                             std::min(rec.hdrEnd, fEnd) - (rec.start + 1), outCursor, seqLen});
+            const uint64_t next = align_up(outCursor + seqLen + TEXT_GAP, 16);
+            chunks += (next - outCursor) / 16;
+            outCursor = next;
+            accepted++;
+        }
+        fi.dnaLineLen = dna;
+        fi.maxLastLineLen = maxLast;
+        fi.nContigs = static_cast<uint32_t>(contigs.size()) - fi.firstContig;
+    }
+    for (int f = 0; f < nFiles; f++)   // files that did not travel sit between their neighbours
+        if (files[f].nContigs == 0) {
+            uint32_t at = 0;
+            for (int g = f - 1; g >= 0; g--)
+                if (files[g].nContigs) { at = files[g].firstContig + files[g].nContigs; break; }
+            files[f].firstContig = at;
+        }
+
+    // ---- sequences -> texts ----
+    textBytes = outCursor + TEXT_TAIL;
+    grow(&dText, &dTextCap, textBytes, "cudaMalloc(ingested texts)");
+    check(cudaMemsetAsync(dText, 0, PAD, stream), "memset(ingested texts, head)");
+    check(cudaMemsetAsync(dText + outCursor, 0, TEXT_TAIL, stream), "memset(ingested texts, tail)");
+    if (accepted) {
+        check(cudaMemcpyAsync(dGather, hGather, accepted * sizeof(FaGather), cudaMemcpyHostToDevice, stream), "H2D(gather)");
+        nl += launch_fa_gather(in, dGather, accepted, chunks, dText, stream);
+    }
+    check(cudaGetLastError(), "ingest launch");
+    check(cudaEventRecord(ev[2], stream), "event");
+    check(cudaStreamSynchronize(stream), "ingest sync");
+    check(cudaEventElapsedTime(&ms[0], ev[0], ev[1]), "event time");
+    check(cudaEventElapsedTime(&ms[1], ev[1], ev[2]), "event time");
+    check(cudaEventElapsedTime(&ms[2], ev[0], ev[2]), "event time");
+    launches = static_cast<uint64_t>(nl);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// PinnedArena
+// ---------------------------------------------------------------------------------------------------------------------
+
+PinnedArena::~PinnedArena() {
+    for (auto& s : slabs)
+        if (s.base) cudaFreeHost(s.base);
+}
+
+void* PinnedArena::alloc(uint64_t n) {
+    n = align_up(std::max<uint64_t>(n, 1), 256);
+    if (n > slabBytes) return nullptr;
+    std::lock_guard<std::mutex> g(mu);
+    for (auto& s : slabs)
+        if (s.open && s.used + n <= slabBytes) {
+            void* p = s.base + s.used;
+            s.used += n;
+            s.live++;
+            return p;
+        }
+    for (auto& s : slabs)          // the open slab is full: close it; an empty closed slab starts over
+        if (s.open) s.open = false;
+    for (auto& s : slabs)
+        if (!s.open && s.live == 0) {
+            s.open = true;
+            s.used = n;
+            s.live = 1;
+            return s.base;
+        }
+    if (static_cast<int>(slabs.size()) >= maxSlabs) return nullptr;
+    uint8_t* base = nullptr;
+    if (cudaHostAlloc(reinterpret_cast<void**>(&base), slabBytes, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    slabs.push_back(Slab{base, n, 1, true});
+    return base;
+}
+
+bool PinnedArena::owns(const void* p) {
+    std::lock_guard<std::mutex> g(mu);
+    const uint8_t* q = static_cast<const uint8_t*>(p);
+    for (auto& s : slabs)
+        if (q >= s.base && q < s.base + slabBytes) return true;
+    return false;
+}
+
+bool PinnedArena::release(const void* p) {
+    std::lock_guard<std::mutex> g(mu);
+    const uint8_t* q = static_cast<const uint8_t*>(p);
+    for (auto& s : slabs)
+        if (q >= s.base && q < s.base + slabBytes) {
+            if (s.live > 0) s.live--;
+            if (s.live == 0 && !s.open) s.used = 0;
+            return true;
+        }
+    return false;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// ReplicaSet
+// ---------------------------------------------------------------------------------------------------------------------
+
+ReplicaSet::ReplicaSet(uint64_t refLengthLimit, uint32_t targetMatchLength, int k1, int k2, int skipMargin, const int* devices,
+                       int ndev) {
+    if (ndev < 1 || ndev > 64) throw MatcherError(MBGCG_E_PARAM, "between 1 and 64 devices");
+    for (int i = 0; i < ndev; i++)
+        for (int j = 0; j < i; j++)
+            if (devices[i] == devices[j]) throw MatcherError(MBGCG_E_PARAM, "a device may hold one replica only");
+    rep.resize(static_cast<size_t>(ndev), nullptr);
+    workers.resize(static_cast<size_t>(ndev));
+    try {
+        // contexts and the gigabytes of reference / table come up on all devices at once
+        std::vector<std::thread> th;
+        std::vector<std::exception_ptr> errs(static_cast<size_t>(ndev));
+        for (int r = 0; r < ndev; r++)
+            th.emplace_back([&, r] {
+                try {
+                    rep[r] = new B200SparseEMMatcher(refLengthLimit, targetMatchLength, k1, k2, skipMargin, devices[r]);
+                } catch (...) {
+                    errs[r] = std::current_exception();
+                }
+            });
+        for (auto& t : th) t.join();
+        for (auto& e : errs)
+            if (e) std::rethrow_exception(e);
+        for (int r = 0; r < ndev; r++)   // peers read each other's resident texts (extension broadcast)
+            for (int q = 0; q < ndev; q++) {
+                if (q == r) continue;
+                int can = 0;
+                cudaDeviceCanAccessPeer(&can, devices[r], devices[q]);
+                if (can) {
+                    cudaSetDevice(devices[r]);
+                    if (cudaDeviceEnablePeerAccess(devices[q], 0) != cudaSuccess) cudaGetLastError();
+                }
+            }
+        for (int r = 0; r < ndev; r++) {
+            workers[r].reset(new Worker());
+            workers[r]->th = std::thread([this, r] { workerLoop(r); });
+        }
+    } catch (...) {
+        for (auto& w : workers)
+            if (w && w->th.joinable()) {
+                { std::lock_guard<std::mutex> g(w->mu); w->quit = true; }
+                w->cv.notify_all();
+                w->th.join();
+            }
+        for (auto* m : rep) delete m;
+        throw;
+    }
+}
+
+ReplicaSet::~ReplicaSet() {
+    for (auto& w : workers)
+        if (w && w->th.joinable()) {
+            { std::lock_guard<std::mutex> g(w->mu); w->quit = true; }
+            w->cv.notify_all();
+            w->th.join();
+        }
+    pinned.reset();
+    for (auto* m : rep) delete m;
+}
+
+void ReplicaSet::workerLoop(int r) {
+    Worker& w = *workers[r];
+    cudaSetDevice(rep[r]->deviceIndex());
+    std::unique_lock<std::mutex> lk(w.mu);
+    for (;;) {
+        w.cv.wait(lk, [&] { return w.quit || w.job; });
+        if (w.quit) return;
+        std::function<void()> job = std::move(w.job);
+        w.job = nullptr;
+        lk.unlock();
+        std::exception_ptr err;
+        try {
+            job();
+        } catch (...) {
+            err = std::current_exception();
+        }
+        lk.lock();
+        w.err = err;
+        w.busy = false;
+        w.cv.notify_all();
+    }
+}
+
+void ReplicaSet::parallel(uint64_t which, const std::function<void(int)>& f) {
+    const int n = size();
+    int only = -1, cnt = 0;
+    for (int r = 0; r < n; r++)
+        if (which >> r & 1) { only = r; cnt++; }
+    if (cnt == 0) return;
+    if (cnt == 1) {  // nothing to overlap: run on the calling thread
+        f(only);
+        return;
+    }
+    for (int r = 0; r < n; r++) {
+        if (!(which >> r & 1)) continue;
+        Worker& w = *workers[r];
+        std::lock_guard<std::mutex> g(w.mu);
+        w.busy = true;
+        w.err = nullptr;
+        w.job = [&f, r] { f(r); };
+        w.cv.notify_all();
+    }
+    std::exception_ptr first;
+    for (int r = 0; r < n; r++) {
+        if (!(which >> r & 1)) continue;
+        Worker& w = *workers[r];
+        std::unique_lock<std::mutex> lk(w.mu);
+        w.cv.wait(lk, [&] { return !w.busy; });
+        if (w.err && !first) first = w.err;
+    }
+    if (first) std::rethrow_exception(first);
+}
+
+void ReplicaSet::loadRef(const char* text, uint64_t len, bool rc, bool addSep, char sep) {
+    parallel((size() >= 64 ? ~0ull : (1ull << size()) - 1), [&](int r) { rep[r]->loadRef(text, len, rc, addSep, sep); });
+}
+
+void ReplicaSet::loadRefFromReplica(int owner, const void* dText, uint64_t len, bool rc, bool addSep, char sep) {
+    parallel((size() >= 64 ? ~0ull : (1ull << size()) - 1), [&](int r) {
+        B200SparseEMMatcher* m = rep[r];
+        if (m->hostMirror() && len) throw MatcherError(MBGCG_E_PARAM, "extensions from device memory need the host mirror off");
+        if (r == owner || len == 0) {
+            m->loadRefDevice(dText, nullptr, len, rc, addSep, sep);
+            return;
+        }
+        void* stage = m->refStaging(len);
+        cudaError_t e = cudaMemcpyPeerAsync(stage, m->deviceIndex(), dText, rep[owner]->deviceIndex(), len,
+                                            static_cast<cudaStream_t>(m->streamHandle()));
+        if (e != cudaSuccess) throw MatcherError(MBGCG_E_CUDA, std::string("peer copy of a reference extension: ") + cudaGetErrorString(e));
+        m->loadRefDevice(stage, nullptr, len, rc, addSep, sep);
+    });
+}
+
+void ReplicaSet::loadSeparator(char sep) {
+    for (auto* m : rep) m->loadSeparator(sep);
+}
+
+uint64_t ReplicaSet::acquireLock() {
+    uint64_t v = 0;
+    for (size_t r = 0; r < rep.size(); r++) {
+        const uint64_t x = rep[r]->acquireWorkerMatchingLockPos();
+        if (r == 0) v = x;
+    }
+    return v;
+}
+
+void ReplicaSet::releaseLock(uint64_t v) {
+    for (auto* m : rep) m->releaseWorkerMatchingLockPos(v);
+}
+
+void ReplicaSet::setHostMirror(bool on) {
+    for (auto* m : rep) m->setHostMirror(on);
+}
+
+void ReplicaSet::syncStateFromPrimary() {
+    const B200SparseEMMatcher* p = rep[0];
+    for (size_t r = 1; r < rep.size(); r++) {
+        B200SparseEMMatcher* m = rep[r];
+        if (m->pos1 != p->pos1 || m->reachedRefLengthCount != p->reachedRefLengthCount) m->invalidateMemo();
+        m->pos1 = p->pos1;
+        m->reachedRefLengthCount = p->reachedRefLengthCount;
+        m->circularBuffer = p->circularBuffer;
+        m->swSize = p->swSize;
+        m->swEnd = p->swEnd;
+        m->samplingPos = p->samplingPos;
+    }
+}
+
+PinnedArena& ReplicaSet::arena() {
+    std::lock_guard<std::mutex> g(arenaMu);
+    if (!pinned) {
+        uint64_t slab = 64ull << 20;
+        int maxSlabs = 4 * size() + 2;
+        if (const char* e = std::getenv("MBGC_B200_ARENA_SLAB_MB")) slab = std::max<uint64_t>(1, std::strtoull(e, nullptr, 10)) << 20;
+        if (const char* e = std::getenv("MBGC_B200_ARENA_SLABS")) maxSlabs = std::max(0, std::atoi(e));
+        pinned.reset(new PinnedArena(slab, maxSlabs));
+    }
+    return *pinned;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// SequentialPass
+// ---------------------------------------------------------------------------------------------------------------------
+
+SequentialPass::SequentialPass(ReplicaSet& rs_, const SeqConfig& c, const uint64_t* loadedPosArr, uint64_t nLoaded)
+    : rs(rs_), cfg(c), loaded(loadedPosArr, loadedPosArr + nLoaded) {
+    const int nd = rs.size();
+    if (const char* e = std::getenv("MBGC_B200_CHUNK_MB")) cfg.chunkBytes = std::max<uint64_t>(1, std::strtoull(e, nullptr, 10)) << 20;
+    if (const char* e = std::getenv("MBGC_B200_WINDOW")) cfg.maxWindowContigs = static_cast<uint32_t>(std::max(1, std::atoi(e)));
+    rs.setHostMirror(false);  // extensions come from device memory; nothing on this path reads getRef()
+    slots.resize(static_cast<size_t>(nd) * 2);
+    slotFree.assign(static_cast<size_t>(nd) * 2, true);
+    stageQ.resize(static_cast<size_t>(nd));
+    runState.resize(static_cast<size_t>(nd));
+    curWindow = cfg.maxWindowContigs;
+    for (int r = 0; r < nd; r++) stagers.emplace_back([this, r] { stagerLoop(r); });
+}
+
+SequentialPass::~SequentialPass() {
+    {
+        std::lock_guard<std::mutex> g(mu);
+        quit = true;
+    }
+    cv.notify_all();
+    for (auto& t : stagers) t.join();
+    // whatever was pushed but never consumed: arena images go back
+    for (auto& im : pending) rs.arena().release(im.bytes);
+    slots.clear();
+}
+
+void SequentialPass::pushFile(const char* bytes, uint64_t n) {
+    std::lock_guard<std::mutex> g(mu);
+    if (inputDone) throw MatcherError(MBGCG_E_PARAM, "pushFile after finishInput");
+    pending.push_back(HostImage{bytes, n});
+    pendingBytes += n;
+    pushedFiles++;
+    formChunks();
+}
+
+void SequentialPass::finishInput() {
+    std::lock_guard<std::mutex> g(mu);
+    inputDone = true;
+    formChunks();
+}
+
+bool SequentialPass::wantsInput() {
+    std::lock_guard<std::mutex> g(mu);
+    if (inputDone) return false;
+    // keep about two windows of images ahead of the commit cursor
+    uint64_t inFlight = pendingBytes;
+    for (auto& c : staged)
+        for (auto& im : c->images) inFlight += im.n;
+    return inFlight < 3 * cfg.chunkBytes * static_cast<uint64_t>(rs.size());
+}
+
+// (mu held) pending files -> chunks, as long as the next replica in turn has a free slot
+void SequentialPass::formChunks() {
+    for (;;) {
+        if (pending.empty()) return;
+        if (pendingBytes < cfg.chunkBytes && !inputDone) return;
+        const int r = static_cast<int>(chunkSeq % static_cast<uint64_t>(rs.size()));
+        int slot = -1;
+        for (int s = 0; s < 2; s++)
+            if (slotFree[r * 2 + s]) { slot = s; break; }
+        if (slot < 0) return;
+        auto c = std::make_shared<Chunk>();
+        c->replica = r;
+        c->slot = slot;
+        c->firstFile = dispatchedFiles;
+        uint64_t bytes = 0;
+        while (!pending.empty() && (bytes == 0 || bytes + pending.front().n <= cfg.chunkBytes + cfg.chunkBytes / 4)) {
+            bytes += pending.front().n;
+            c->images.push_back(pending.front());
+            pending.pop_front();
+            if (bytes >= cfg.chunkBytes) break;
+        }
+        pendingBytes -= bytes;
+        dispatchedFiles += c->images.size();
+        slotFree[r * 2 + slot] = false;
+        chunkSeq++;
+        staged.push_back(c);
+        stageQ[r].push_back(c);
+        cv.notify_all();
+    }
+}
+
+void SequentialPass::stagerLoop(int r) {
+    cudaSetDevice(rs.at(r)->deviceIndex());
+    for (;;) {
+        std::shared_ptr<Chunk> c;
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return quit || !stageQ[r].empty(); });
+            if (quit) return;
+            c = stageQ[r].front();
+            stageQ[r].pop_front();
+        }
+        try {
+            auto& slot = slots[r * 2 + c->slot];
+            if (!slot) slot.reset(new FastaBatchIngest(rs.at(r)->deviceIndex()));
+            const double t0 = now_ms();
+            slot->run(c->images.data(), static_cast<int>(c->images.size()));
+            c->headers.resize(slot->contigs.size());
+            for (size_t k = 0; k < slot->contigs.size(); k++) {
+                const IngestedContig& ic = slot->contigs[k];
+                c->headers[k].assign(c->images[ic.file].bytes + ic.hdrOff, ic.hdrLen);
+            }
+            uint64_t pageable = 0;
+            for (auto& im : c->images) {  // arena images are ours to give back now; others stay with the caller
+                if (!rs.arena().release(im.bytes)) pageable += im.n;
+            }
+            std::lock_guard<std::mutex> g(mu);
+            st.ingestMs += now_ms() - t0;
+            st.imageBytes += slot->imageBytes;
+            st.textBytes += slot->textBytes;
+            st.ingestLaunches += slot->launches;
+            st.pageableBytes += pageable;
+            st.chunks++;
+        } catch (...) {
+            c->err = std::current_exception();
+        }
+        {
+            std::lock_guard<std::mutex> g(mu);
+            c->ready = true;
+        }
+        cv.notify_all();
+    }
+}
+
+// next window = the next (up to) one chunk per replica, in file order
+bool SequentialPass::startWindow() {
+    std::unique_lock<std::mutex> lk(mu);
+    if (staged.empty()) return false;
+    win.clear();
+    const size_t take = std::min<size_t>(staged.size(), static_cast<size_t>(rs.size()));
+    const double t0 = now_ms();
+    for (size_t k = 0; k < take; k++) {
+        std::shared_ptr<Chunk> c = staged.front();
+        cv.wait(lk, [&] { return c->ready; });
+        staged.pop_front();
+        win.push_back(c);
+    }
+    st.waitStageMs += now_ms() - t0;
+    lk.unlock();
+    for (auto& c : win)
+        if (c->err) std::rethrow_exception(c->err);
+    items.clear();
+    for (size_t w = 0; w < win.size(); w++) {
+        FastaBatchIngest& ing = *slots[win[w]->replica * 2 + win[w]->slot];
+        for (size_t f = 0; f < ing.files.size(); f++) {
+            const IngestedFile& fi = ing.files[f];
+            for (uint32_t k = 0; k < fi.nContigs; k++) items.push_back(Item{false, static_cast<int>(w), fi.firstContig + k});
+            items.push_back(Item{true, static_cast<int>(w), static_cast<uint32_t>(f)});
+        }
+    }
+    cursor = 0;
+    winActive = true;
+    st.windows++;
+    return true;
+}
+
+void SequentialPass::releaseWindow() {
+    std::lock_guard<std::mutex> g(mu);
+    for (auto& c : win) slotFree[c->replica * 2 + c->slot] = true;
+    win.clear();
+    items.clear();
+    winActive = false;
+    formChunks();
+}
+
+// match + pack the not yet valid contigs items[from ...) against the current state, at most curWindow of them and at
+// most one pass of text per replica; every replica works on its own chunk
+void SequentialPass::runFrom(size_t from) {
+    uint64_t maxPassBytes = 1024ull << 20;
+    if (const char* e = std::getenv("MBGC_B200_MAX_PASS_BYTES")) maxPassBytes = std::max<uint64_t>(1, std::strtoull(e, nullptr, 10));
+    const int nd = rs.size();
+    for (auto& rsn : runState) { rsn.texts.clear(); rsn.offs.clear(); }
+    std::vector<uint64_t> bytes(static_cast<size_t>(nd), 0);
+    uint32_t taken = 0;
+    uint64_t which = 0;
+    for (size_t i = from; i < items.size() && taken < curWindow; i++) {
+        Item& it = items[i];
+        if (it.fileEnd) continue;
+        const int r = win[it.chunk]->replica;
+        FastaBatchIngest& ing = *slots[r * 2 + win[it.chunk]->slot];
+        const IngestedContig& ic = ing.contigs[it.contig];
+        if (!runState[r].texts.empty() && bytes[r] + ic.seqLen > maxPassBytes) break;
+        bytes[r] += ic.seqLen;
+        it.resIndex = static_cast<uint32_t>(runState[r].texts.size());
+        it.valid = true;
+        runState[r].texts.push_back(TextView{nullptr, ic.seqLen});
+        runState[r].offs.push_back(ic.textOff);
+        which |= 1ull << r;
+        taken++;
+    }
+    std::vector<double> tm(static_cast<size_t>(nd) * 2, 0.0);
+    std::vector<uint64_t> launches(static_cast<size_t>(nd), 0);
+    rs.parallel(which, [&](int r) {
+        B200SparseEMMatcher* m = rs.at(r);
+        // the window's contigs of this replica all live in one ingest slot (one chunk per replica and window)
+        int slot = -1;
+        for (auto& c : win)
+            if (c->replica == r) slot = c->slot;
+        FastaBatchIngest& ing = *slots[r * 2 + slot];
+        const uint64_t l0 = m->totalLaunches;
+        const double t0 = now_ms();
+        m->matchBatch(runState[r].texts, nullptr, cfg.minMatchLength, true, ing.dTexts(), runState[r].offs.data(), true);
+        const double t1 = now_ms();
+        m->packBatch(cfg.pack, runState[r].texts, nullptr, nullptr, nullptr, loaded.data(), loaded.size());
+        tm[r * 2] = t1 - t0;
+        tm[r * 2 + 1] = now_ms() - t1;
+        launches[r] = m->totalLaunches - l0;
+    });
+    double mMax = 0, pMax = 0;
+    for (int r = 0; r < nd; r++) {
+        mMax = std::max(mMax, tm[r * 2]);
+        pMax = std::max(pMax, tm[r * 2 + 1]);
+        st.launches += launches[r];
+    }
+    st.matchMs += mMax;
+    st.packMs += pMax;
+    st.runs++;
+    committedThisRun = 0;
+}
+
+void SequentialPass::next(SeqEvent& ev) {
+    for (;;) {
+        if (!evQ.empty()) {
+            ev = evQ.front();
+            evQ.pop_front();
+            return;
+        }
+        if (!winActive) {
+            if (!startWindow()) {
+                std::lock_guard<std::mutex> g(mu);
+                ev = SeqEvent{};
+                if (inputDone && pending.empty() && staged.empty()) {
+                    ev.type = SeqEvent::DONE;
+                    ev.loadedRefLength = rs.primary()->getLoadedRefLength();
+                } else
+                    ev.type = SeqEvent::NEED_INPUT;
+                return;
+            }
+            continue;
+        }
+        if (cursor >= items.size()) {
+            releaseWindow();
+            continue;
+        }
+        Item& it = items[cursor];
+        Chunk& ch = *win[it.chunk];
+        FastaBatchIngest& ing = *slots[ch.replica * 2 + ch.slot];
+        B200SparseEMMatcher* pm = rs.primary();
+        if (it.fileEnd) {
+            // processTargetMeta + processAfterTargetWithParallelIO (MBGC_Encoder.cpp:493-509): separator, the size of this
+            // file's reference extension, and the sliding-window position the decoder will replay
+            const IngestedFile& fi = ing.files[it.contig];
+            if (!fileOpen) fileStartLoaded = pm->getLoadedRefLength();  // a file without contigs
+            SeqEvent e{};
+            e.type = SeqEvent::FILE_END;
+            e.file = ch.firstFile + it.contig;
+            e.status = fi.status;
+            e.nContigs = fi.nContigs;
+            e.dnaLineLen = fi.dnaLineLen == UINT64_MAX ? 0 : fi.dnaLineLen;  // KSEQ_DNA_LINE_LENGTH, MGMP.cpp:12-14
+            if (fi.status >= -2) {
+                if (cfg.separatorPerFile) {
+                    rs.loadSeparator(cfg.separator);
+                    e.refExtSize = pm->getLoadedRefLength() - fileStartLoaded;
+                    loaded.push_back((loaded.empty() ? 0 : loaded.back()) + e.refExtSize);
+                }
+                e.lockPos = rs.acquireLock();
+                rs.releaseLock(e.lockPos);
+            }
+            e.loadedRefLength = pm->getLoadedRefLength();
+            fileOpen = false;
+            st.files++;
+            evQ.push_back(e);
+            cursor++;
+            continue;
+        }
+        if (!it.valid) {
+            runFrom(cursor);
+            continue;
+        }
+        // ---- commit one contig (MultipleGenomeMatchingProcessor.cpp:274-287) ----
+        if (!fileOpen) {
+            fileStartLoaded = pm->getLoadedRefLength();
+            fileOpen = true;
+        }
+        const IngestedContig& ic = ing.contigs[it.contig];
+        B200SparseEMMatcher* m = rs.at(ch.replica);
+        SeqEvent e{};
+        e.type = SeqEvent::CONTIG;
+        e.file = ch.firstFile + ic.file;
+        e.hdr = ch.headers[it.contig].data();
+        e.hdrLen = ch.headers[it.contig].size();
+        e.seqLen = ic.seqLen;
+        e.nMatches = m->batchCounts()[it.resIndex];
+        e.kept = m->packKept()[it.resIndex];
+        e.unmatched = m->packUnmatched()[it.resIndex];
+        for (int s = 0; s < PACK_STREAMS; s++) {
+            const auto& off = m->packStreamOff(s);
+            e.seg[s] = m->packStream(s) + off[it.resIndex];
+            e.segLen[s] = off[it.resIndex + 1] - off[it.resIndex];
+        }
+        const bool extend = e.unmatched * static_cast<uint64_t>(cfg.unmatchedFractionFactor) > ic.seqLen;      // MGMP_Params.h:179-187
+        const bool extendRC = !cfg.rcDisabled && e.unmatched * static_cast<uint64_t>(cfg.unmatchedFractionRCFactor) > ic.seqLen;  // :189-191
+        e.extended = extend;
+        e.extendedRC = extend && extendRC;
+        st.contigs++;
+        committedThisRun++;
+        cursor++;
+        evQ.push_back(e);
+        if (extend) {
+            const double t0 = now_ms();
+            rs.loadRefFromReplica(ch.replica, ing.dTexts() + ic.textOff, ic.seqLen, extendRC, cfg.refRegionSeparators, cfg.separator);
+            st.loadRefMs += now_ms() - t0;
+            st.extensions++;
+            // everything matched against the old state and not yet committed runs again; speculation that fails is wasted
+            // work, so the window follows the commit rate (as mbgc_b200/dist.py does)
+            for (size_t i = cursor; i < items.size(); i++)
+                if (!items[i].fileEnd && items[i].valid) {
+                    items[i].valid = false;
+                    st.rerunContigs++;
+                }
+            curWindow = std::max<uint32_t>(static_cast<uint32_t>(rs.size()), std::min<uint32_t>(cfg.maxWindowContigs, 2 * committedThisRun));
+        } else if (cursor < items.size() && !items[cursor].fileEnd && !items[cursor].valid && committedThisRun >= curWindow) {
+            curWindow = std::min<uint32_t>(cfg.maxWindowContigs, 2 * curWindow);  // a whole run committed: speculate further
+        }
+    }
+}
+
+}  // namespace mbgc_b200

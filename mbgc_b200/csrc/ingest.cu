@@ -164,13 +164,24 @@ __device__ __forceinline__ uint64_t block_find_nl(const uint8_t* __restrict__ in
 }
 
 // a CTA per record (a header or a first line can be a whole unwrapped chromosome)
+// fileEnds (batched ingest, several file images in one buffer): ascending end offsets of the images; a record ends where
+// its file ends even if the next record start lies further on (the bytes between two images are filler)
 __global__ void __launch_bounds__(FA_THREADS) k_fa_records(const uint8_t* __restrict__ in, uint64_t n,
                                                            const uint64_t* __restrict__ starts, uint32_t nRecs,
-                                                           FaRecord* __restrict__ recs) {
+                                                           FaRecord* __restrict__ recs,
+                                                           const uint64_t* __restrict__ fileEnds, uint32_t nFiles) {
     __shared__ unsigned long long sPos;
     const uint32_t r = blockIdx.x;
     const uint64_t start = starts[r];
-    const uint64_t regionEnd = r + 1 < nRecs ? starts[r + 1] : n;
+    uint64_t regionEnd = r + 1 < nRecs ? starts[r + 1] : n;
+    if (fileEnds) {  // first file end behind `start`
+        uint32_t lo = 0, hi = nFiles;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (fileEnds[mid] > start) hi = mid; else lo = mid + 1;
+        }
+        if (lo < nFiles && fileEnds[lo] < regionEnd) regionEnd = fileEnds[lo];
+    }
     const uint64_t hdrEnd = block_find_nl(in, start + 1, regionEnd, &sPos);  // the header line cannot reach the next record
     const uint64_t seqStart = hdrEnd + 1 < regionEnd ? hdrEnd + 1 : regionEnd;
     const uint64_t firstNl = block_find_nl(in, seqStart, regionEnd, &sPos);
@@ -357,8 +368,26 @@ int launch_fa_starts(const uint8_t* in, uint64_t n, const uint32_t* blockOff, ui
     return 1;
 }
 
-int launch_fa_records(const uint8_t* in, uint64_t n, const uint64_t* starts, uint32_t nRecs, FaRecord* recs, cudaStream_t st) {
-    k_fa_records<<<nRecs, FA_THREADS, 0, st>>>(in, n, starts, nRecs, recs);
+// the filler between the images of a batched ingest: 16 x '\n' in front of every image (so that its first byte starts a
+// line), zeros from an image's end to the next filler.  spans[2f], spans[2f+1] = start and end offset of image f.
+__global__ void k_fa_filler(uint8_t* __restrict__ in, const uint64_t* __restrict__ spans, uint32_t nFiles, uint64_t bufEnd) {
+    const uint32_t f = blockIdx.x;
+    const uint64_t end = spans[2 * f + 1];
+    const uint64_t nextStart = f + 1 < nFiles ? spans[2 * f + 2] : bufEnd + 16;
+    for (uint64_t i = end + threadIdx.x; i < nextStart - 16; i += blockDim.x) in[i] = 0;
+    if (f + 1 < nFiles && threadIdx.x < 16) in[nextStart - 16 + threadIdx.x] = '\n';
+    if (f == 0 && threadIdx.x < 16) in[static_cast<int64_t>(spans[0]) - 16 + threadIdx.x] = '\n';
+}
+
+int launch_fa_filler(uint8_t* in, const uint64_t* spans, uint32_t nFiles, uint64_t bufEnd, cudaStream_t st) {
+    if (nFiles == 0) return 0;
+    k_fa_filler<<<nFiles, 64, 0, st>>>(in, spans, nFiles, bufEnd);
+    return 1;
+}
+
+int launch_fa_records(const uint8_t* in, uint64_t n, const uint64_t* starts, uint32_t nRecs, FaRecord* recs, cudaStream_t st,
+                      const uint64_t* fileEnds, uint32_t nFiles) {
+    k_fa_records<<<nRecs, FA_THREADS, 0, st>>>(in, n, starts, nRecs, recs, fileEnds, nFiles);
     k_fa_check<<<fa_blocks(n), FA_THREADS, 0, st>>>(in, n, starts, nRecs, recs);
     return 2;
 }

@@ -36,7 +36,12 @@ struct FaGather {          // per accepted record, written by the host
 // total; returns kernel launches.
 int launch_fa_count(const uint8_t* in, uint64_t n, uint32_t* blockCnt, cudaStream_t st);   // + scan in place, total at [nBlocks]
 int launch_fa_starts(const uint8_t* in, uint64_t n, const uint32_t* blockOff, uint64_t* starts, cudaStream_t st);
-int launch_fa_records(const uint8_t* in, uint64_t n, const uint64_t* starts, uint32_t nRecs, FaRecord* recs, cudaStream_t st);
+// fileEnds != nullptr: `in` holds several file images (batched ingest); fileEnds[f] = end offset of image f, ascending
+int launch_fa_records(const uint8_t* in, uint64_t n, const uint64_t* starts, uint32_t nRecs, FaRecord* recs, cudaStream_t st,
+                      const uint64_t* fileEnds = nullptr, uint32_t nFiles = 0);
+// filler bytes around the images of a batched ingest (spans[2f], spans[2f+1] = start / end offset of image f; the buffer
+// has 16 bytes in front of spans[0] and extends to bufEnd)
+int launch_fa_filler(uint8_t* in, const uint64_t* spans, uint32_t nFiles, uint64_t bufEnd, cudaStream_t st);
 int launch_fa_gather(const uint8_t* in, const FaGather* g, uint32_t nRecs, uint64_t nChunks, uint8_t* out, cudaStream_t st);
 
 }  // namespace mbgc_b200

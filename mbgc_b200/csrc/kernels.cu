@@ -20,6 +20,8 @@
 //   k_gather          per-contig match lists -> one dense list for the device->host copy
 #include "kernels.h"
 
+#include <atomic>
+
 #include <cstdio>
 
 namespace mbgc_b200 {
@@ -799,15 +801,19 @@ bool probe_supports_K(int K) {
     }
 }
 
-static int g_smCount = 0;
+// per device: one process may hold matchers on several GPUs (mbgcg_create_multi), each driven by its own host thread
+static std::atomic<int> g_smCount[64];
 int device_sm_count() {
-    if (g_smCount == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_smCount, cudaDevAttrMultiProcessorCount, dev);
-        if (g_smCount <= 0) g_smCount = 148;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int slot = dev & 63;
+    int n = g_smCount[slot].load(std::memory_order_relaxed);
+    if (n == 0) {
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+        g_smCount[slot].store(n, std::memory_order_relaxed);
     }
-    return g_smCount;
+    return n;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -894,10 +900,14 @@ static void launch_probe_k(const ProbeArgs& a, bool useFilter, int mode, cudaStr
     }
     if (useFilter) {
         const size_t smem = static_cast<size_t>(a.ix.filterWords) * 4 + 16;  // filter + mbarrier
-        static bool attrSet = false;
-        if (!attrSet) {
+        // the opt-in applies to the device that is current when it is made: once per (device, instantiation)
+        static std::atomic<uint64_t> attrSet{0};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        const uint64_t bit = 1ull << (dev & 63);
+        if (!(attrSet.load(std::memory_order_acquire) & bit)) {
             cudaFuncSetAttribute(k_probe<KW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(PROBE_FILTER_BYTES + 16));
-            attrSet = true;
+            attrSet.fetch_or(bit, std::memory_order_release);
         }
         k_probe<KW, true><<<sm, PROBE_THREADS_FILTER, smem, st>>>(a);
     } else {

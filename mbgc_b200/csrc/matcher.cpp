@@ -207,9 +207,10 @@ void B200SparseEMMatcher::indexPass() {
 }
 
 // .cpp:402-437 (tail recursion written as a loop)
-// `text` is also on the device at dStage + stageOff (staged once per loadRef call): the device reference gets its bytes
-// from there (copy / reverse-complement kernel) while the host cores write the mirror
-void B200SparseEMMatcher::loadSegment(const char* text, uint64_t len, bool rc, bool addSep, char sep, uint64_t stageOff) {
+// The bytes of `text` are on the device at dSrc (staged once per loadRef call, or the resident text of an ingested
+// contig): the device reference gets its bytes from there (copy / reverse-complement kernel) while the host cores write
+// the mirror -- unless the mirror is switched off (text may then be null).
+void B200SparseEMMatcher::loadSegment(const char* text, const uint8_t* dSrc, uint64_t len, bool rc, bool addSep, char sep) {
     while (len != 0) {
         if (static_cast<uint64_t>(pos1) == maxRefLength && swEnd != maxRefLength) {
             reachedRefLengthCount++;
@@ -220,26 +221,28 @@ void B200SparseEMMatcher::loadSegment(const char* text, uint64_t len, bool rc, b
         uint64_t tmpLen = len;
         const uint64_t tmpMax = tmpEnd < static_cast<uint64_t>(pos1) ? maxRefLength : tmpEnd;
         if (static_cast<uint64_t>(pos1) + tmpLen > tmpMax) tmpLen = tmpMax - static_cast<uint64_t>(pos1);
-        char* dst = hostRef + pos1;
-        if (rc) {
-            const uint8_t* src = reinterpret_cast<const uint8_t*>(text) + len - tmpLen;
-            reverse_complement(src, tmpLen, reinterpret_cast<uint8_t*>(dst), g_lut.t);
-        } else
-            std::memcpy(dst, text, tmpLen);
+        const bool mirror = mirrorEnabled && text != nullptr;
+        if (mirror) {
+            char* dst = hostRef + pos1;
+            if (rc) {
+                const uint8_t* src = reinterpret_cast<const uint8_t*>(text) + len - tmpLen;
+                reverse_complement(src, tmpLen, reinterpret_cast<uint8_t*>(dst), g_lut.t);
+            } else
+                std::memcpy(dst, text, tmpLen);
+        }
         const bool sepHit = addSep && static_cast<uint64_t>(pos1) + tmpLen == swEnd;
-        if (sepHit) hostRef[swEnd - 1] = sep;
+        if (sepHit && mirrorEnabled) hostRef[swEnd - 1] = sep;
         if (tmpLen) {
-            launch_ref_segment(dStage + stageOff + (rc ? len - tmpLen : 0), dRef + pos1, tmpLen, rc, stream);
+            launch_ref_segment(dSrc + (rc ? len - tmpLen : 0), dRef + pos1, tmpLen, rc, stream);
             totalLaunches++;
-            if (sepHit)  // the separator replaced the segment's last byte in the mirror: same on the device
-                check(cudaMemcpyAsync(dRef + swEnd - 1, hostRef + swEnd - 1, 1, cudaMemcpyHostToDevice, stream), "H2D(sep)");
-        } else if (sepHit)
-            check(cudaMemcpyAsync(dRef + swEnd - 1, hostRef + swEnd - 1, 1, cudaMemcpyHostToDevice, stream), "H2D(sep)");
+        }
+        if (sepHit)  // the separator replaces the segment's last byte
+            check(cudaMemsetAsync(dRef + swEnd - 1, static_cast<unsigned char>(sep), 1, stream), "memset(sep)");
         pos1 += static_cast<int64_t>(tmpLen);
         indexPass();
         if (!rc) {
-            text += tmpLen;
-            stageOff += tmpLen;
+            if (text) text += tmpLen;
+            dSrc += tmpLen;
         }
         len = (static_cast<uint64_t>(pos1) == tmpEnd) ? 0 : len - tmpLen;
     }
@@ -262,14 +265,34 @@ void B200SparseEMMatcher::loadRef(const char* refText, uint64_t refLength, bool 
         check(cudaMemcpyAsync(dStage, hStage, refLength, cudaMemcpyHostToDevice, stream), "H2D(ref text)");
     }
     lap("text staged");
-    loadSegment(refText, refLength, false, addRegionSeparators, regionSeparator, 0);
+    loadSegment(refText, dStage, refLength, false, addRegionSeparators, regionSeparator);
     lap("forward segment");
-    if (loadRCRef) loadSegment(refText, refLength, true, addRegionSeparators, regionSeparator, 0);
+    if (loadRCRef) loadSegment(refText, dStage, refLength, true, addRegionSeparators, regionSeparator);
     lap("reverse complement");
     // the caller may free refText right after the call; pageable copies are staged before returning, but
     // keep the ordering explicit
     check(cudaStreamSynchronize(stream), "loadRef sync");
     lap("device done");
+}
+
+// loadRef whose text is already in this device's memory (an ingested contig, or a peer copy of one): nothing crosses
+// PCIe.  hostText, when given, feeds the host mirror; without it the mirror must be off (setHostMirror(false)).
+void B200SparseEMMatcher::loadRefDevice(const void* dText, const char* hostText, uint64_t refLength, bool loadRCRef,
+                                        bool addRegionSeparators, char regionSeparator) {
+    check(cudaSetDevice(device), "cudaSetDevice");
+    if (mirrorEnabled && !hostText && refLength)
+        throw MatcherError(MBGCG_E_PARAM, "loadRef from device memory needs the host text too while the host mirror is on");
+    const uint8_t* src = static_cast<const uint8_t*>(dText);
+    loadSegment(hostText, src, refLength, false, addRegionSeparators, regionSeparator);
+    if (loadRCRef) loadSegment(hostText, src, refLength, true, addRegionSeparators, regionSeparator);
+    check(cudaStreamSynchronize(stream), "loadRef sync");
+}
+
+// staging buffer of at least n bytes on this device (the target of a peer copy before loadRefDevice)
+void* B200SparseEMMatcher::refStaging(uint64_t n) {
+    check(cudaSetDevice(device), "cudaSetDevice");
+    growDevice(reinterpret_cast<void**>(&dStage), &dStageCap, n + 64, "cudaMalloc(ref staging)");
+    return dStage;
 }
 
 void B200SparseEMMatcher::loadSeparator(char regionSeparator) {
@@ -285,9 +308,9 @@ void B200SparseEMMatcher::loadSeparator(char regionSeparator) {
         at = static_cast<uint64_t>(pos1) - 1;
     else
         at = static_cast<uint64_t>(pos1++);
-    hostRef[at] = regionSeparator;
-    check(cudaMemcpyAsync(dRef + at, hostRef + at, 1, cudaMemcpyHostToDevice, stream), "H2D(sep)");
-    check(cudaStreamSynchronize(stream), "loadSeparator sync");
+    if (mirrorEnabled) hostRef[at] = regionSeparator;
+    // (no sync: every later use of the reference is ordered behind this on the handle's stream)
+    check(cudaMemsetAsync(dRef + at, static_cast<unsigned char>(regionSeparator), 1, stream), "memset(sep)");
 }
 
 // ---- locks: .cpp:361-400 -------------------------------------------------------------------------------

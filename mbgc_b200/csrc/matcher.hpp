@@ -61,6 +61,16 @@ public:
     void loadRef(const char* refText, uint64_t refLength, bool loadRCRef, bool addRegionSeparators, char regionSeparator);
     // ref .cpp:439-451
     void loadSeparator(char regionSeparator);
+    // loadRef with the text already in this device's memory (dText; stays valid until the call returns)
+    void loadRefDevice(const void* dText, const char* hostText, uint64_t refLength, bool loadRCRef, bool addRegionSeparators,
+                       char regionSeparator);
+    void* refStaging(uint64_t n);
+    // the host mirror behind getRef() is only read by the reference's own CPU packer (MBGC_Encoder.cpp:181,318-330,
+    // 376-380); with K6 on the device nobody needs it and loadRef stops filling it
+    void setHostMirror(bool on) { mirrorEnabled = on; }
+    bool hostMirror() const { return mirrorEnabled; }
+    int deviceIndex() const { return device; }
+    const uint8_t* deviceRef() const { return dRef; }
 
     // ref .h:104-113
     const char* getRef() const { return hostRef; }
@@ -150,7 +160,7 @@ public:
     uint64_t totalLaunches = 0;
 
 private:
-    void loadSegment(const char* text, uint64_t len, bool rc, bool addSep, char sep, uint64_t stageOff);
+    void loadSegment(const char* text, const uint8_t* dSrc, uint64_t len, bool rc, bool addSep, char sep);
     void indexPass();
     bool wantMemo(uint64_t positions);
     void buildMemo();
@@ -164,6 +174,7 @@ private:
     void check(cudaError_t e, const char* what);
 
     int device = 0;
+    bool mirrorEnabled = true;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[12] = {};
     bool timingPending = false;

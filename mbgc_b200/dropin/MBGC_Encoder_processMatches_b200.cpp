@@ -34,6 +34,38 @@ namespace {
 
 size_t MBGC_Encoder::processMatches(vector<PgTools::TextMatch>& textMatches, char* destStart, size_t destLen, int targetIdx,
                                     size_t matchingLockPos) {
+    // ---- the batched target loop (MGMP_processTargets_b200.cpp) on the line ----
+    if (mbgc_b200_dropin::EncoderState* es = mbgc_b200_dropin::encoder_state_request()) {
+        static_assert(sizeof(size_t) == sizeof(uint64_t), "size_t");
+        es->loadedPosArr = reinterpret_cast<const uint64_t*>(refExtLoadedPosArr.data());
+        es->nLoadedPos = refExtLoadedPosArr.size();
+        return 0;
+    }
+    if (const mbgcg_seq_event_t* ev = mbgc_b200_dropin::prepacked_event()) {
+        // a committed contig of the collection pass: its streams were packed on the device against exactly the state the
+        // stock loop would have had; append them where the stock function does (:225-287) and keep the counters (:289-302)
+        auto seg = [&](int s) { return reinterpret_cast<const char*>(ev->seg[s]); };
+        auto len = [&](int s) { return static_cast<size_t>(ev->segLen[s]); };
+        if (len(MBGCG_S_LITERALS)) targetLiterals[targetIdx].append(seg(MBGCG_S_LITERALS), len(MBGCG_S_LITERALS));
+        if (len(MBGCG_S_MAPOFF))
+            targetMapOffDests[targetIdx].write(seg(MBGCG_S_MAPOFF), static_cast<std::streamsize>(len(MBGCG_S_MAPOFF)));
+        if (len(MBGCG_S_MAPOFF5)) targetMapOff5thByte[targetIdx].append(seg(MBGCG_S_MAPOFF5), len(MBGCG_S_MAPOFF5));
+        if (len(MBGCG_S_MAPLEN))
+            targetMapLenDests[targetIdx].write(seg(MBGCG_S_MAPLEN), static_cast<std::streamsize>(len(MBGCG_S_MAPLEN)));
+        if (len(MBGCG_S_GAPDELTA)) targetGapDeltas[targetIdx].append(seg(MBGCG_S_GAPDELTA), len(MBGCG_S_GAPDELTA));
+        size_t extMatched = 0;
+        if (len(MBGCG_S_GAPFLAGS)) {
+            targetGapMismatchesFlags[targetIdx].append(seg(MBGCG_S_GAPFLAGS), len(MBGCG_S_GAPFLAGS));
+            const char* f = seg(MBGCG_S_GAPFLAGS);
+            for (size_t i = 0, e = len(MBGCG_S_GAPFLAGS); i < e; i++) extMatched += f[i] == 0;
+        }
+        extensionsMatchedCharsAll += extMatched;
+        unmatchedCharsAll += ev->unmatched;
+        totalMatchedAll += ev->seqLen - ev->unmatched;
+        totalDestLenAll += ev->seqLen;
+        removedGapBreakingMatchesAll += ev->nMatches - ev->kept;
+        return ev->unmatched;
+    }
     if (params->refLiteralMinimalLengthExt != SIZE_MAX)
         die("mbgc_b200: literal-based reference extension (refLiteralMinimalLengthExt) is not part of the device packer");
     mbgcg_pack_params_t pp{};

@@ -23,6 +23,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <mutex>
+#include <vector>
 
 #include "mbgc_b200.h"
 #include "dropin_shared.h"
@@ -31,6 +32,12 @@ namespace {
 
 // the text and list of the most recent matchTexts call (under g_lock): the packer may still find both on the device
 mbgc_b200_dropin::LastMatch g_lastMatch{nullptr, nullptr, 0, 0};
+
+// batched target loop: see dropin_shared.h
+const mbgcg_seq_event_t* g_prepacked = nullptr;
+mbgc_b200_dropin::EncoderState* g_encoderStateRequest = nullptr;
+bool g_replay = false;
+uint64_t g_replayLock = 0;
 
 // The reference's parallel mode enters matchTexts from several OpenMP threads while another one runs loadRef
 // (SURVEY.md 8b "Threading").  A handle is not thread-safe; serialising is a legal schedule of that mode.
@@ -45,9 +52,24 @@ inline mbgcg_t* handle_of(uint64_t* slot) { return reinterpret_cast<mbgcg_t*>(sl
 
 using mbgc_b200_dropin::Trace;
 
-int device_from_env() {
-    const char* e = std::getenv("MBGC_B200_DEVICE");
-    return e ? std::atoi(e) : 0;
+// MBGC_B200_DEVICES = "0,1,2,3": the matcher is replicated on these devices (mbgcg_create_multi); the batched target loop
+// shards its windows over them.  MBGC_B200_DEVICE = one device (default 0).
+std::vector<int> devices_from_env() {
+    std::vector<int> d;
+    if (const char* e = std::getenv("MBGC_B200_DEVICES")) {
+        for (const char* p = e; *p;) {
+            char* end = nullptr;
+            const long v = std::strtol(p, &end, 10);
+            if (end == p) break;
+            d.push_back(static_cast<int>(v));
+            p = *end == ',' ? end + 1 : end;
+        }
+    }
+    if (d.empty()) {
+        const char* e = std::getenv("MBGC_B200_DEVICE");
+        d.push_back(e ? std::atoi(e) : 0);
+    }
+    return d;
 }
 
 }  // namespace
@@ -84,7 +106,8 @@ SlidingWindowSparseEMMatcher::SlidingWindowSparseEMMatcher(const size_t refLengt
     (void) skipHtInit;
     Trace tr("create", refLengthLimit);
     mbgcg_t* h = nullptr;
-    if (mbgcg_create(&h, refLengthLimit, targetMatchLength, _k1, _k2, skipMargin, device_from_env()) != MBGCG_OK)
+    const std::vector<int> devs = devices_from_env();
+    if (mbgcg_create_multi(&h, refLengthLimit, targetMatchLength, _k1, _k2, skipMargin, devs.data(), static_cast<int>(devs.size())) != MBGCG_OK)
         die(mbgcg_create_error());
     ht64bit = reinterpret_cast<std::uint64_t*>(h);
     ht32bit = nullptr;
@@ -145,6 +168,7 @@ void SlidingWindowSparseEMMatcher::loadRef(const char* refText, size_t refLength
 // ref .cpp:439-451
 void SlidingWindowSparseEMMatcher::loadSeparator(char regionSeparator) {
     std::lock_guard<std::mutex> g(g_lock);
+    if (g_replay) return;  // the collection pass wrote the separator on every replica; the members already show it
     mbgcg_t* h = handle_of(ht64bit);
     MBGCG_PUSH_STATE(h);
     if (mbgcg_load_separator(h, regionSeparator) != MBGCG_OK) die(mbgcg_last_error(h));
@@ -154,6 +178,7 @@ void SlidingWindowSparseEMMatcher::loadSeparator(char regionSeparator) {
 // ref .cpp:361-378
 size_t SlidingWindowSparseEMMatcher::acquireWorkerMatchingLockPos() {
     std::lock_guard<std::mutex> g(g_lock);
+    if (g_replay) return g_replayLock;
     mbgcg_t* h = handle_of(ht64bit);
     MBGCG_PUSH_STATE(h);
     const size_t v = mbgcg_acquire_lock(h);
@@ -164,6 +189,7 @@ size_t SlidingWindowSparseEMMatcher::acquireWorkerMatchingLockPos() {
 // ref .cpp:380-400
 void SlidingWindowSparseEMMatcher::releaseWorkerMatchingLockPos(size_t lockValue) {
     std::lock_guard<std::mutex> g(g_lock);
+    if (g_replay) return;
     mbgcg_t* h = handle_of(ht64bit);
     MBGCG_PUSH_STATE(h);
     if (mbgcg_release_lock(h, lockValue) != MBGCG_OK) die(mbgcg_last_error(h));
@@ -208,6 +234,14 @@ struct Access : SlidingWindowSparseEMMatcher {
         st.samplingPos = m->*(&Access::samplingPos);
         mbgcg_set_state(h, &st);
     }
+    static void pull(SlidingWindowSparseEMMatcher* m, mbgcg_t* h) {
+        mbgcg_state_t st;
+        mbgcg_get_state(h, &st);
+        m->*(&Access::pos1) = st.pos1;
+        m->*(&Access::reachedRefLengthCount) = st.reachedRefLengthCount;
+        m->*(&Access::swEnd) = st.swEnd;
+        m->*(&Access::samplingPos) = st.samplingPos;
+    }
 };
 
 std::mutex& handle_lock() { return g_lock; }
@@ -216,6 +250,19 @@ mbgcg_t* synced_handle(SlidingWindowSparseEMMatcher* m) {
     mbgcg_t* h = handle_of(m->*Access::ht());
     Access::push(m, h);
     return h;
+}
+
+void pull_state(SlidingWindowSparseEMMatcher* m) { Access::pull(m, handle_of(m->*Access::ht())); }
+
+void set_prepacked(const mbgcg_seq_event_t* ev, EncoderState* es) {
+    g_prepacked = ev;
+    g_encoderStateRequest = es;
+}
+const mbgcg_seq_event_t* prepacked_event() { return g_prepacked; }
+EncoderState* encoder_state_request() { return g_encoderStateRequest; }
+void set_replay(bool on, uint64_t lockPos) {
+    g_replay = on;
+    g_replayLock = lockPos;
 }
 
 LastMatch last_match() { return g_lastMatch; }

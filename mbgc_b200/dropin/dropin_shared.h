@@ -38,6 +38,23 @@ struct LastMatch {
     uint64_t n;
 };
 
+// ---- hand-over between the batched target loop (MGMP_processTargets_b200.cpp) and the two shims -------------------
+// What the loop cannot reach itself because it is private to MBGC_Encoder: asked for through processMatches.
+struct EncoderState {
+    const uint64_t* loadedPosArr;   // refExtLoadedPosArr
+    uint64_t nLoadedPos;
+};
+// ev != nullptr: the next processMatches call appends the ready-made stream segments of this committed contig instead
+// of packing anything; es != nullptr: the next processMatches call only fills *es.
+void set_prepacked(const mbgcg_seq_event_t* ev, EncoderState* es);
+const mbgcg_seq_event_t* prepacked_event();
+EncoderState* encoder_state_request();
+// replay: the collection pass has already applied loadSeparator and the lock acquire / release to every replica; while
+// this is on, the matcher shim answers those calls of the encoder's per-file hook from the event (take handle_lock()).
+void set_replay(bool on, uint64_t lockPos);
+// members of the reference matcher object <- the handle (take handle_lock() first)
+void pull_state(SlidingWindowSparseEMMatcher* m);
+
 std::mutex& handle_lock();
 // the C-ABI handle of a matcher built by the shim, after pushing the members the reference header's inline
 // setters may have changed (take handle_lock() first)

@@ -50,6 +50,41 @@ class PackParams(C.Structure):
                           125, 500, 50, 50, 0, 256)
 
 
+class SeqConfig(C.Structure):
+    """mbgcg_seq_config_t: what the sequential target schedule reads from MGMP_Params / MBGC_Params"""
+    _fields_ = [("pack", PackParams), ("minMatchLength", C.c_uint32), ("unmatchedFractionFactor", C.c_int32),
+                ("unmatchedFractionRCFactor", C.c_int32), ("rcInReferenceDisabled", C.c_int32),
+                ("refRegionSeparators", C.c_int32), ("separatorPerFile", C.c_int32), ("regionSeparator", C.c_char),
+                ("chunkBytes", C.c_uint64), ("maxWindowContigs", C.c_uint32)]
+
+    @staticmethod
+    def for_mode(mode, chunk_bytes=0, max_window=0, lazy=True):
+        """`mbgc c -m mode` defaults: extension when unmatched * 128 > length, its reverse complement too when
+        unmatched * 8 > length (modes 2/3: * 128), MGMP_Params.h:41-42, MBGC_Params.h:906-909"""
+        return SeqConfig(PackParams.for_mode(mode, lazy=lazy), 32, 128, 128 if mode >= 2 else 8, 0, 1, 1 if lazy else 0,
+                         b"\0", chunk_bytes, max_window)
+
+
+class SeqEvent(C.Structure):
+    _fields_ = [("type", C.c_int32), ("status", C.c_int32), ("file", C.c_uint64), ("hdr", C.c_void_p),
+                ("hdrLen", C.c_uint64), ("seqLen", C.c_uint64), ("nMatches", C.c_uint64), ("kept", C.c_uint64),
+                ("unmatched", C.c_uint64), ("extended", C.c_int32), ("extendedRC", C.c_int32),
+                ("seg", C.c_void_p * 6), ("segLen", C.c_uint64 * 6), ("nContigs", C.c_uint64),
+                ("dnaLineLen", C.c_uint64), ("refExtSize", C.c_uint64), ("lockPos", C.c_uint64),
+                ("loadedRefLength", C.c_uint64)]
+
+
+class SeqStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("files", "contigs", "windows", "runs", "rerunContigs", "extensions",
+                                          "imageBytes", "textBytes", "pageableBytes", "launches", "chunks")] + \
+               [(n, C.c_double) for n in ("ingestMs", "matchMs", "packMs", "loadRefMs", "waitStageMs")]
+
+
+EV_CONTIG, EV_FILE_END, EV_NEED_INPUT, EV_DONE = 1, 2, 3, 4
+SEQ_SEPARATOR_MARK = (ord('"') + 128) & 0xFF   # mbgccoder/MBGC_Params.h:46
+FILE_SEPARATOR_MARK = (ord(';') + 128) & 0xFF  # mbgccoder/MBGC_Params.h:47
+
+
 class _PackResult(C.Structure):
     _fields_ = [("stream", C.c_void_p * 6), ("streamOff", C.c_void_p * 6), ("unmatched", C.c_void_p),
                 ("kept", C.c_void_p)]
@@ -72,6 +107,27 @@ def load_library():
     vp = C.c_void_p
     L.mbgcg_create.restype = C.c_int
     L.mbgcg_create.argtypes = [C.POINTER(vp), C.c_uint64, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.mbgcg_create_multi.restype = C.c_int
+    L.mbgcg_create_multi.argtypes = [C.POINTER(vp), C.c_uint64, C.c_uint32, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int]
+    L.mbgcg_device_count.restype = C.c_int
+    L.mbgcg_device_count.argtypes = [vp]
+    L.mbgcg_seq_begin.restype = C.c_int
+    L.mbgcg_seq_begin.argtypes = [vp, C.POINTER(SeqConfig), u64p, C.c_uint64]
+    L.mbgcg_seq_push_file.restype = C.c_int
+    L.mbgcg_seq_push_file.argtypes = [vp, vp, C.c_uint64]
+    L.mbgcg_seq_finish_input.restype = C.c_int
+    L.mbgcg_seq_finish_input.argtypes = [vp]
+    L.mbgcg_seq_wants_input.restype = C.c_int
+    L.mbgcg_seq_wants_input.argtypes = [vp]
+    L.mbgcg_seq_next.restype = C.c_int
+    L.mbgcg_seq_next.argtypes = [vp, C.POINTER(SeqEvent)]
+    L.mbgcg_seq_end.restype = C.c_int
+    L.mbgcg_seq_end.argtypes = [vp, C.POINTER(SeqStats)]
+    L.mbgcg_image_alloc.restype = vp
+    L.mbgcg_image_alloc.argtypes = [vp, C.c_uint64]
+    L.mbgcg_image_free.restype = C.c_int
+    L.mbgcg_image_free.argtypes = [vp, vp]
+    L.mbgcg_set_host_mirror.argtypes = [vp, C.c_int]
     L.mbgcg_destroy.argtypes = [vp]
     L.mbgcg_last_error.restype = C.c_char_p
     L.mbgcg_last_error.argtypes = [vp]
@@ -147,13 +203,90 @@ class Matcher:
     """SlidingWindowSparseEMMatcher on a B200.  Match lists come back as uint64 arrays of shape (n, 3) with
     columns (posSrcText, length, posDestText) -- the TextMatch fields of matching/TextMatchers.h:9-17."""
 
-    def __init__(self, ref_length_limit, L=32, k1=16, k2=1, skip_margin=16, device=0):
+    def __init__(self, ref_length_limit, L=32, k1=16, k2=1, skip_margin=16, device=0, devices=None):
+        """devices: a list of CUDA device indices -> the same matcher replicated on each (mbgcg_create_multi); the
+        collection pass (compressSequential) shards its windows over them, everything else runs on the first."""
         self.lib = load_library()
         h = C.c_void_p()
-        rc = self.lib.mbgcg_create(C.byref(h), ref_length_limit, L, k1, k2, skip_margin, device)
+        if devices is None:
+            rc = self.lib.mbgcg_create(C.byref(h), ref_length_limit, L, k1, k2, skip_margin, device)
+        else:
+            devs = (C.c_int * len(devices))(*devices)
+            rc = self.lib.mbgcg_create_multi(C.byref(h), ref_length_limit, L, k1, k2, skip_margin, devs, len(devices))
         if rc != 0:
             raise MatcherError(rc, self.lib.mbgcg_create_error().decode())
         self.h = h
+
+    def deviceCount(self):
+        return self.lib.mbgcg_device_count(self.h)
+
+    def setHostMirror(self, on):
+        self.lib.mbgcg_set_host_mirror(self.h, int(bool(on)))
+
+    def compressSequential(self, images, cfg, loadedPosArr=None, pinned=True, on_event=None):
+        """The reference's sequential (-t 1) target schedule over file images (bytes objects, in target order) through
+        mbgcg_seq_*: MultipleGenomeMatchingProcessor::processTargetsWithParallelIO
+        (/root/reference/matching/MultipleGenomeMatchingProcessor.cpp:232-313) with the encoder's hooks
+        (mbgccoder/MBGC_Encoder.cpp:489-509) applied to the committed events.  Returns ({stream: bytes}, info) where the
+        streams are what the encoder holds after the last target (the literal stream without the G0 bootstrap of
+        MBGC_Encoder.cpp:34-37) and info has per-file meta data, headers, lock positions and the pass statistics."""
+        loaded = list(loadedPosArr) if loadedPosArr is not None else [self.getLoadingPosition()]
+        arr = (C.c_uint64 * len(loaded))(*loaded)
+        self._check(self.lib.mbgcg_seq_begin(self.h, C.byref(cfg), arr, len(loaded)))
+        out = {n: [] for n in STREAM_NAMES}
+        info = dict(headers=[], seqCounts=[], dnaLineLens=[], refExtSizes=[], lockPos=[], unmatched=0, matches=0,
+                    extensions=0, status=[])
+        keep = []
+        nxt = 0
+        ev = SeqEvent()
+        try:
+            while True:
+                while nxt < len(images) and self.lib.mbgcg_seq_wants_input(self.h):
+                    a = _as_u8(images[nxt])
+                    p = self.lib.mbgcg_image_alloc(self.h, a.size) if (pinned and a.size) else None
+                    if p:
+                        C.memmove(p, a.ctypes.data, a.size)
+                        self._check(self.lib.mbgcg_seq_push_file(self.h, p, a.size))
+                    else:
+                        keep.append(a)
+                        self._check(self.lib.mbgcg_seq_push_file(self.h, a.ctypes.data if a.size else None, a.size))
+                    nxt += 1
+                    if nxt == len(images):
+                        self._check(self.lib.mbgcg_seq_finish_input(self.h))
+                if not images and nxt == 0:
+                    self._check(self.lib.mbgcg_seq_finish_input(self.h))
+                    nxt = -1
+                self._check(self.lib.mbgcg_seq_next(self.h, C.byref(ev)))
+                if on_event is not None:
+                    on_event(ev)
+                if ev.type == EV_DONE:
+                    break
+                if ev.type == EV_NEED_INPUT:
+                    if nxt >= len(images) or nxt < 0:
+                        raise MatcherError(-2, "the pass asks for input after finish_input")
+                    continue
+                if ev.type == EV_CONTIG:
+                    for s, name in enumerate(STREAM_NAMES):
+                        if ev.segLen[s]:
+                            out[name].append(C.string_at(ev.seg[s], ev.segLen[s]))
+                    out["literals"].append(bytes([SEQ_SEPARATOR_MARK]))          # processAfterSequence
+                    info["headers"].append((int(ev.file), C.string_at(ev.hdr, ev.hdrLen) if ev.hdrLen else b""))
+                    info["unmatched"] += int(ev.unmatched)
+                    info["matches"] += int(ev.nMatches)
+                    info["extensions"] += int(ev.extended)
+                elif ev.type == EV_FILE_END:
+                    if cfg.pack.enableExtensionsWithMismatches:                   # processAfterTarget
+                        out["gapFlags"].append(bytes([FILE_SEPARATOR_MARK]))
+                    info["seqCounts"].append(int(ev.nContigs))
+                    info["dnaLineLens"].append(int(ev.dnaLineLen))
+                    info["refExtSizes"].append(int(ev.refExtSize))
+                    info["lockPos"].append(int(ev.lockPos))
+                    info["status"].append(int(ev.status))
+        finally:
+            st = SeqStats()
+            self.lib.mbgcg_seq_end(self.h, C.byref(st))
+        info["stats"] = {n: getattr(st, n) for n, _ in SeqStats._fields_}
+        return {n: b"".join(v) for n, v in out.items()}, info
 
     def close(self):
         if getattr(self, "h", None):

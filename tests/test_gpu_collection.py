@@ -1,0 +1,146 @@
+"""The collection pass (mbgcg_seq_*, row a9 of SURVEY.md 8): the reference's sequential (-t 1) target schedule run over
+speculative windows on 1..N devices must produce the SAME six streams, meta data and matcher state as the
+one-contig-at-a-time schedule -- here the oracle's emulation of it (tests/seq_schedule.py), which reproduces the stream
+dumps of the stock `mbgc-dev v -Q -D` (tests/test_oracle_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+
+import mbgc_b200
+from mbgc_b200.matcher import SeqConfig
+from mbgc_b200.synth import synth_collection, write_fasta
+from seq_schedule import STREAMS, encode_streams, reference_factor
+from util import FIXTURES, have_fixtures, read_fasta
+
+pytestmark = pytest.mark.gpu
+
+
+def n_devices():
+    import torch
+    return torch.cuda.device_count()
+
+
+def gpu_streams(paths, mode, devices, chunk_bytes, pinned=True, max_window=0):
+    """the GPU side of seq_schedule.encode_streams: same initial reference, then the pass over the file images"""
+    recs0 = read_fasta(paths[0])
+    c0 = recs0[0][1]
+    basic = max(os.path.getsize(paths[0]), 1 << 21)
+    limit = min(reference_factor(len(paths)) * basic * 2, 2**32 - 1)
+    limit = max(limit, len(c0))
+    g = mbgc_b200.Matcher(limit, 32, 16, 1, 24 if mode >= 2 else 16, devices=devices)
+    try:
+        g.disableSlidingWindow()
+        g.loadRef(c0, True, True, 0)
+        images = [open(p, "rb").read() for p in paths]
+        out, info = g.compressSequential(images, SeqConfig.for_mode(mode, chunk_bytes, max_window), pinned=pinned)
+        info["ref_length"] = g.getRefLength()
+        info["loaded"] = g.getLoadedRefLength()
+        info["table"] = g.table()
+        return out, info
+    finally:
+        g.close()
+
+
+def check_against_oracle(paths, mode, devices, chunk_bytes, **kw):
+    want, wstats = encode_streams(paths, mode)
+    got, info = gpu_streams(paths, mode, devices, chunk_bytes, **kw)
+    lit0 = read_fasta(paths[0])[0][1]
+    assert want["literals"][:len(lit0)] == lit0
+    want = dict(want)
+    want["literals"] = want["literals"][len(lit0) + 1:]  # the G0 bootstrap (contig + SEQ mark) is the encoder's
+    for name in STREAMS:
+        assert got[name] == want[name], f"stream {name} differs ({len(got[name])} vs {len(want[name])} bytes)"
+    assert info["unmatched"] == wstats["unmatched"]
+    assert info["matches"] == wstats["matches"]
+    assert info["ref_length"] == wstats["ref_length"]
+    recs = [read_fasta(p) for p in paths]
+    assert info["seqCounts"] == [len(r) for r in recs]
+    assert [h.decode() for _, h in info["headers"]] == [h for r in recs for h, _ in r]
+    assert all(s == -1 for s in info["status"])
+    return info
+
+
+@pytest.fixture(scope="module")
+def mixed_dir(tmp_path_factory):
+    """divergent genomes (every contig extends the reference), then near-identical ones (nothing does), some files with
+    several contigs, one with a short last line and one tiny contig"""
+    d = tmp_path_factory.mktemp("coll")
+    gs = synth_collection(7, 300_000, 4321, 1e-2, 1e-4)
+    gs += synth_collection(9, 300_000, 4321, 1e-4, 1e-5, first=40)[1:]
+    paths = []
+    for i, g in enumerate(gs):
+        p = os.path.join(d, f"g{i:04d}.fna")
+        if i % 4 == 1:  # three contigs
+            a, b = g.size // 3, 2 * g.size // 3
+            with open(p, "wb") as f:
+                for k, part in enumerate((g[:a], g[a:b], g[b:])):
+                    tmp = os.path.join(d, "part.tmp")
+                    write_fasta(tmp, f"syn_{i:04d}.{k} contig {k}", part, width=70)
+                    f.write(open(tmp, "rb").read())
+        elif i % 4 == 2:
+            with open(p, "wb") as f:
+                tmp = os.path.join(d, "part.tmp")
+                write_fasta(tmp, f"syn_{i:04d} main", g, width=80)
+                f.write(open(tmp, "rb").read())
+                f.write(b">tiny\nACGTACGTAC\n")
+        else:
+            write_fasta(p, f"syn_{i:04d} synthetic E. coli-like genome {i}", g)
+        paths.append(p)
+    return paths
+
+
+@pytest.mark.parametrize("mode", [0, 1, 3])
+def test_streams_equal_sequential_schedule(mixed_dir, mode):
+    info = check_against_oracle(mixed_dir, mode, [0], 1 << 20)
+    st = info["stats"]
+    assert st["extensions"] > 0 and st["windows"] > 1 and st["launches"] > 0
+    assert st["pageableBytes"] == 0, "images from mbgcg_image_alloc must travel by DMA from pinned memory"
+
+
+def test_one_big_window_and_pageable_images(mixed_dir):
+    info = check_against_oracle(mixed_dir, 1, [0], 1 << 30, pinned=False)
+    assert info["stats"]["windows"] == 1 and info["stats"]["pageableBytes"] > 0
+
+
+def test_small_speculation_window(mixed_dir):
+    check_against_oracle(mixed_dir, 1, [0], 2 << 20, max_window=2)
+
+
+@pytest.mark.skipif(not have_fixtures(), reason="reference fixtures not present")
+@pytest.mark.parametrize("mode", [1, 2])
+def test_listeria_streams(mode):
+    paths = [os.path.join(FIXTURES, l.strip()) for l in open(os.path.join(FIXTURES, "seqlist.txt"))]
+    check_against_oracle(paths, mode, [0], 2 << 20)
+
+
+def test_two_replicas_same_streams(mixed_dir):
+    if n_devices() < 2:
+        pytest.skip("needs two CUDA devices")
+    info = check_against_oracle(mixed_dir, 1, [0, 1], 1 << 20)
+    assert info["stats"]["extensions"] > 0
+
+
+def test_replicas_hold_identical_tables(mixed_dir):
+    """after a pass with extensions every replica's index equals the single-device one (ordered inserts everywhere)"""
+    if n_devices() < 2:
+        pytest.skip("needs two CUDA devices")
+    _, one = gpu_streams(mixed_dir[:6], 1, [0], 1 << 20)
+    _, two = gpu_streams(mixed_dir[:6], 1, [1, 0], 1 << 20)  # replica 0 on device 1
+    assert np.array_equal(one["table"], two["table"])
+    assert one["loaded"] == two["loaded"]
+
+
+def test_bad_files_report_the_readers_status(tmp_path):
+    good = tmp_path / "a.fna"
+    write_fasta(str(good), "a", synth_collection(1, 50_000, 9, 0, 0)[0])
+    g = mbgc_b200.Matcher(1 << 23, 32, 16, 1, 16, device=0)
+    try:
+        g.disableSlidingWindow()
+        g.loadRef(read_fasta(str(good))[0][1], True, True, 0)
+        images = [open(good, "rb").read(), b"", b"not fasta\n", b">x\nACGT\n\nAC\n"]
+        _, info = g.compressSequential(images, SeqConfig.for_mode(1, 1 << 20))
+        assert info["status"] == [-1, -1, -3, -4]
+        assert info["seqCounts"][:2] == [1, 0]
+    finally:
+        g.close()
