@@ -245,7 +245,10 @@ __device__ __forceinline__ void check_chunk(const uint8_t* __restrict__ in, uint
             r++;
         }
         if (!loaded) {
-            const FaRecord rec = recs[r];
+            FaRecord rec = recs[r];
+            // batched ingest: the chunk starts in the filler behind record r's file image -- the next record owns the
+            // rest of it (i < n = end of the last image, so there is one)
+            if (i >= rec.regionEnd) rec = recs[++r];
             seqStart = rec.hdrEnd + 1;
             next = rec.regionEnd;
             len = next > seqStart ? next - seqStart : 0;
