@@ -287,6 +287,8 @@ int mbgcg_seq_end(mbgcg_t* h, mbgcg_seq_stats_t* stats);
  * speed, pageable images travel through bounce buffers at ~1/4 of that.  NULL when the arena is full -- use any other
  * memory then.  mbgcg_image_free only for images that were never pushed. */
 void* mbgcg_image_alloc(mbgcg_t* h, uint64_t n);
+/* the largest image the arena can hold in one piece (larger requests always return NULL) */
+uint64_t mbgcg_image_max(mbgcg_t* h);
 int mbgcg_image_free(mbgcg_t* h, const void* p);
 
 /* switches the host mirror behind mbgcg_host_ref off / on (only the reference's own CPU packer reads it,

@@ -324,6 +324,7 @@ void* mbgcg_image_alloc(mbgcg_t* h, uint64_t n) {
         return nullptr;
     }
 }
+uint64_t mbgcg_image_max(mbgcg_t* h) { return h->rs->arena().maxPiece(); }
 int mbgcg_image_free(mbgcg_t* h, const void* p) { return h->rs->arena().release(p) ? MBGCG_OK : MBGCG_E_PARAM; }
 
 // ---- the sequential schedule over a collection, batched and sharded over the handle's devices ---------------------------

@@ -13,6 +13,7 @@ namespace mbgc_b200 {
 namespace {
 constexpr uint64_t PAD = 64, TEXT_GAP = 64, TEXT_TAIL = 8192;  // = matcher.cpp
 constexpr uint64_t BOUNCE_BYTES = 8ull << 20;
+constexpr int NSLOT = 3;  // ingest slots per replica: one in the window, one being ingested, one receiving images
 inline uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
 inline double now_ms() {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -35,13 +36,17 @@ void FastaBatchIngest::check(cudaError_t e, const char* what) {
     if (e != cudaSuccess) throw MatcherError(MBGCG_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
 }
 
-void FastaBatchIngest::grow(uint8_t** p, uint64_t* cap, uint64_t need, const char* what) {
+void FastaBatchIngest::grow(uint8_t** p, uint64_t* cap, uint64_t need, const char* what, bool keep, uint64_t keepBytes) {
     if (need <= *cap) return;
-    cudaFree(*p);
-    *p = nullptr;
-    *cap = 0;
     const uint64_t c = align_up(need + need / 8, 1 << 20);
-    check(cudaMalloc(p, c), what);
+    uint8_t* grown = nullptr;
+    check(cudaMalloc(&grown, c), what);
+    if (keep && *p && keepBytes) {
+        check(cudaMemcpyAsync(grown, *p, keepBytes, cudaMemcpyDeviceToDevice, stream), what);
+        check(cudaStreamSynchronize(stream), what);
+    }
+    cudaFree(*p);
+    *p = grown;
     *cap = c;
 }
 
@@ -58,7 +63,9 @@ FastaBatchIngest::~FastaBatchIngest() {
     cudaFree(dIn);
     cudaFree(dWork);
     cudaFree(dText);
+    cudaFree(dHdr);
     if (hWork) cudaFreeHost(hWork);
+    if (hHdr) cudaFreeHost(hHdr);
     for (auto& b : hBounce)
         if (b) cudaFreeHost(b);
     for (auto& e : ev)
@@ -70,32 +77,64 @@ FastaBatchIngest::~FastaBatchIngest() {
 
 // The per-file loop of ingest.cpp (B200SparseEMMatcher::ingestFasta) for a batch of images in one device buffer: image f
 // sits at a 16-byte aligned offset with 16 '\n' in front of it; a record ends at its file's end (k_fa_records clamps).
-void FastaBatchIngest::run(const HostImage* images, int nFiles) {
+void FastaBatchIngest::begin(uint64_t expectedBytes) {
     check(cudaSetDevice(device), "cudaSetDevice");
-    files.assign(static_cast<size_t>(nFiles), IngestedFile{});
+    files.clear();
     contigs.clear();
+    fileBytes.clear();
+    hdrAt.clear();
+    live.clear();
+    spans.clear();
+    cursor = 0;
     launches = 0;
-    imageBytes = textBytes = wireBytes = 0;
-    ms[0] = ms[1] = ms[2] = 0;
+    imageBytes = textBytes = pageableBytes = 0;
+    ms[0] = ms[1] = 0;
+    bounceUse = 0;
+    grow(&dIn, &dInCap, 16 + expectedBytes + expectedBytes / 8 + 4096, "cudaMalloc(fasta images)");
+    check(cudaEventRecord(ev[0], stream), "event");
+}
 
-    // layout: only images that can hold a record travel (the others are decided here: kseq.h:239-240)
-    std::vector<int> live;
-    std::vector<uint64_t> spans;  // start, end per live image (offsets behind the 16 leading bytes)
-    uint64_t cursor = 0;
-    for (int f = 0; f < nFiles; f++) {
-        const HostImage& im = images[f];
-        if (im.n == 0) continue;                       // end of file before the first header: status -1, no records
-        if (im.bytes[0] != '>') {                      // not FASTA
-            files[f].status = -3;
-            continue;
-        }
-        if (im.n >= (1ull << 40)) throw MatcherError(MBGCG_E_UNSUPPORTED, "FASTA image of 1 TiB or more");
-        live.push_back(f);
-        spans.push_back(cursor);
-        spans.push_back(cursor + im.n);
-        cursor = align_up(cursor + im.n, 16) + 16;
-        imageBytes += im.n;
+void FastaBatchIngest::add(const HostImage& im) {
+    check(cudaSetDevice(device), "cudaSetDevice");
+    const int f = static_cast<int>(files.size());
+    files.push_back(IngestedFile{});
+    fileBytes.push_back(im.n);
+    // only images that can hold a record travel (the others are decided here: kseq.h:239-240)
+    if (im.n == 0) return;                         // end of file before the first header: status -1, no records
+    if (im.bytes[0] != '>') {                      // not FASTA
+        files[f].status = -3;
+        return;
     }
+    if (im.n >= (1ull << 40)) throw MatcherError(MBGCG_E_UNSUPPORTED, "FASTA image of 1 TiB or more");
+    const uint64_t end = cursor + im.n;
+    grow(&dIn, &dInCap, 16 + align_up(end, 16) + 16 + 64, "cudaMalloc(fasta images)", true, 16 + cursor);
+    uint8_t* dst = dIn + 16 + cursor;
+    if (is_pinned(im.bytes)) {
+        check(cudaMemcpyAsync(dst, im.bytes, im.n, cudaMemcpyHostToDevice, stream), "H2D(fasta image)");
+    } else {  // pageable: through the pinned bounce buffers, one being filled while the other is on the wire
+        for (uint64_t o = 0; o < im.n; o += BOUNCE_BYTES) {
+            const uint64_t m = std::min<uint64_t>(BOUNCE_BYTES, im.n - o);
+            const int b = bounceUse & 1;
+            if (!hBounce[b]) check(cudaHostAlloc(reinterpret_cast<void**>(&hBounce[b]), BOUNCE_BYTES, cudaHostAllocDefault), "cudaHostAlloc(bounce)");
+            else if (bounceUse >= 2) check(cudaEventSynchronize(bounceEv[b]), "bounce sync");
+            std::memcpy(hBounce[b], im.bytes + o, m);
+            check(cudaMemcpyAsync(dst + o, hBounce[b], m, cudaMemcpyHostToDevice, stream), "H2D(fasta image)");
+            check(cudaEventRecord(bounceEv[b], stream), "event");
+            bounceUse++;
+        }
+        pageableBytes += im.n;
+    }
+    live.push_back(f);
+    spans.push_back(cursor);
+    spans.push_back(end);
+    cursor = align_up(end, 16) + 16;
+    imageBytes += im.n;
+    check(cudaStreamSynchronize(stream), "H2D(fasta image) sync");  // the caller gets its memory back
+}
+
+void FastaBatchIngest::finish() {
+    check(cudaSetDevice(device), "cudaSetDevice");
+    const int nFiles = static_cast<int>(files.size());
     const uint32_t nLive = static_cast<uint32_t>(live.size());
     if (nLive == 0) {
         grow(&dText, &dTextCap, PAD + TEXT_TAIL, "cudaMalloc(ingested texts)");
@@ -103,31 +142,9 @@ void FastaBatchIngest::run(const HostImage* images, int nFiles) {
     }
     const uint64_t n = spans.back();                   // end of the last image
     const uint64_t inBytes = 16 + align_up(n, 16) + 64;
-    grow(&dIn, &dInCap, inBytes, "cudaMalloc(fasta images)");
+    grow(&dIn, &dInCap, inBytes, "cudaMalloc(fasta images)", true, 16 + n);
     uint8_t* in = dIn + 16;
 
-    // ---- images -> device ----
-    check(cudaEventRecord(ev[0], stream), "event");
-    int bounceUse = 0;
-    for (uint32_t k = 0; k < nLive; k++) {
-        const HostImage& im = images[live[k]];
-        uint8_t* dst = in + spans[2 * k];
-        if (is_pinned(im.bytes)) {
-            check(cudaMemcpyAsync(dst, im.bytes, im.n, cudaMemcpyHostToDevice, stream), "H2D(fasta image)");
-        } else {  // pageable: through the pinned bounce buffers, one being filled while the other is on the wire
-            for (uint64_t o = 0; o < im.n; o += BOUNCE_BYTES) {
-                const uint64_t m = std::min<uint64_t>(BOUNCE_BYTES, im.n - o);
-                const int b = bounceUse & 1;
-                if (!hBounce[b]) check(cudaHostAlloc(reinterpret_cast<void**>(&hBounce[b]), BOUNCE_BYTES, cudaHostAllocDefault), "cudaHostAlloc(bounce)");
-                else if (bounceUse >= 2) check(cudaEventSynchronize(bounceEv[b]), "bounce sync");
-                std::memcpy(hBounce[b], im.bytes + o, m);
-                check(cudaMemcpyAsync(dst + o, hBounce[b], m, cudaMemcpyHostToDevice, stream), "H2D(fasta image)");
-                check(cudaEventRecord(bounceEv[b], stream), "event");
-                bounceUse++;
-            }
-        }
-        wireBytes += im.n;
-    }
     // descriptors: spans, then file ends
     const uint32_t blocks = static_cast<uint32_t>((n + FA_BLOCK_BYTES - 1) / FA_BLOCK_BYTES);
     const uint64_t oSpans = 0;
@@ -136,24 +153,24 @@ void FastaBatchIngest::run(const HostImage* images, int nFiles) {
     const uint64_t cntBytes = align_up((blocks + 2ull) * 4, 256);
     const uint64_t fixedBytes = oCnt + cntBytes;
     grow(&dWork, &dWorkCap, fixedBytes + (1 << 20), "cudaMalloc(fasta work)");
-    auto growHost = [&](uint64_t need) {
-        if (need <= hWorkCap) return;
-        if (hWork) cudaFreeHost(hWork);
-        hWork = nullptr;
-        hWorkCap = 0;
+    auto growHost = [&](uint8_t** p, uint64_t* cap, uint64_t need) {
+        if (need <= *cap) return;
+        if (*p) cudaFreeHost(*p);
+        *p = nullptr;
+        *cap = 0;
         const uint64_t c = align_up(need + need / 4, 1 << 16);
-        check(cudaHostAlloc(reinterpret_cast<void**>(&hWork), c, cudaHostAllocDefault), "cudaHostAlloc(fasta work)");
-        hWorkCap = c;
+        check(cudaHostAlloc(reinterpret_cast<void**>(p), c, cudaHostAllocDefault), "cudaHostAlloc(fasta work)");
+        *cap = c;
     };
-    growHost(oCnt + 64);
+    growHost(&hWork, &hWorkCap, oCnt + 64);
     std::memcpy(hWork + oSpans, spans.data(), nLive * 16ull);
     uint64_t* hEnds = reinterpret_cast<uint64_t*>(hWork + oEnds);
     for (uint32_t k = 0; k < nLive; k++) hEnds[k] = spans[2 * k + 1];
+    check(cudaEventRecord(ev[1], stream), "event");
     check(cudaMemcpyAsync(dWork, hWork, oEnds + nLive * 8ull, cudaMemcpyHostToDevice, stream), "H2D(fasta descriptors)");
     const uint64_t* dSpans = reinterpret_cast<const uint64_t*>(dWork + oSpans);
     const uint64_t* dEnds = reinterpret_cast<const uint64_t*>(dWork + oEnds);
     int nl = launch_fa_filler(in, dSpans, nLive, inBytes - 16, stream);
-    check(cudaEventRecord(ev[1], stream), "event");
 
     // ---- record starts ----
     uint32_t* dCnt = reinterpret_cast<uint32_t*>(dWork + oCnt);
@@ -167,33 +184,27 @@ void FastaBatchIngest::run(const HostImage* images, int nFiles) {
     const uint64_t oStarts = fixedBytes;
     const uint64_t oRecs = align_up(oStarts + nRecs * 8ull, 256);
     const uint64_t oGather = align_up(oRecs + nRecs * sizeof(FaRecord), 256);
-    const uint64_t workBytes = oGather + nRecs * sizeof(FaGather) + 256;
-    if (workBytes > dWorkCap) {  // grow, keeping descriptors and block offsets
-        uint8_t* grown = nullptr;
-        const uint64_t cap = align_up(workBytes + workBytes / 4, 1 << 20);
-        check(cudaMalloc(reinterpret_cast<void**>(&grown), cap), "cudaMalloc(fasta work)");
-        check(cudaMemcpyAsync(grown, dWork, fixedBytes, cudaMemcpyDeviceToDevice, stream), "D2D(fasta work)");
-        check(cudaStreamSynchronize(stream), "ingest sync");
-        cudaFree(dWork);
-        dWork = grown;
-        dWorkCap = cap;
-        dCnt = reinterpret_cast<uint32_t*>(dWork + oCnt);
-        dSpans = reinterpret_cast<const uint64_t*>(dWork + oSpans);
-        dEnds = reinterpret_cast<const uint64_t*>(dWork + oEnds);
-    }
+    const uint64_t oHdr = align_up(oGather + nRecs * sizeof(FaGather), 256);
+    const uint64_t workBytes = oHdr + nRecs * 24ull + 256;
+    grow(&dWork, &dWorkCap, workBytes, "cudaMalloc(fasta work)", true, fixedBytes);
+    dCnt = reinterpret_cast<uint32_t*>(dWork + oCnt);
+    dSpans = reinterpret_cast<const uint64_t*>(dWork + oSpans);
+    dEnds = reinterpret_cast<const uint64_t*>(dWork + oEnds);
     uint64_t* dStarts = reinterpret_cast<uint64_t*>(dWork + oStarts);
     FaRecord* dRecs = reinterpret_cast<FaRecord*>(dWork + oRecs);
     FaGather* dGather = reinterpret_cast<FaGather*>(dWork + oGather);
+    uint64_t* dHdrDesc = reinterpret_cast<uint64_t*>(dWork + oHdr);
     nl += launch_fa_starts(in, n, dCnt, dStarts, stream);
     nl += launch_fa_records(in, n, dStarts, nRecs, dRecs, stream, dEnds, nLive);
-    growHost(nRecs * (sizeof(FaRecord) + sizeof(FaGather)) + 64);
+    growHost(&hWork, &hWorkCap, nRecs * (sizeof(FaRecord) + sizeof(FaGather) + 24) + 64);
     FaRecord* hRecs = reinterpret_cast<FaRecord*>(hWork);
     FaGather* hGather = reinterpret_cast<FaGather*>(hRecs + nRecs);
+    uint64_t* hHdrDesc = reinterpret_cast<uint64_t*>(hGather + nRecs);
     check(cudaMemcpyAsync(hRecs, dRecs, nRecs * sizeof(FaRecord), cudaMemcpyDeviceToHost, stream), "D2H(records)");
     check(cudaStreamSynchronize(stream), "ingest sync");
 
     // ---- the reader's file-wide state, file by file, record by record (kseq.h:253-256, 260-265) ----
-    uint64_t outCursor = PAD, chunks = 0;
+    uint64_t outCursor = PAD, chunks = 0, hdrBytes = 0;
     uint32_t accepted = 0, r = 0;
     for (uint32_t k = 0; k < nLive; k++) {
         const int f = live[k];
@@ -234,8 +245,13 @@ void FastaBatchIngest::run(const HostImage* images, int nFiles) {
             }
             if (seqLen >= (1ull << 32)) throw MatcherError(MBGCG_E_UNSUPPORTED, "sequence of 4 GiB or more");
             hGather[accepted] = FaGather{seqStart, outCursor, seqLen, seqLen ? line : 0, chunks};
-            contigs.push_back(IngestedContig{static_cast<uint32_t>(f), rec.start + 1 - fStart,
-                                             std::min(rec.hdrEnd, fEnd) - (rec.start + 1), outCursor, seqLen});
+            const uint64_t hdrLen = std::min(rec.hdrEnd, fEnd) - (rec.start + 1);
+            hHdrDesc[3 * accepted] = rec.start + 1;
+            hHdrDesc[3 * accepted + 1] = hdrLen;
+            hHdrDesc[3 * accepted + 2] = hdrBytes;
+            hdrAt.push_back(hdrBytes);
+            hdrBytes += hdrLen;
+            contigs.push_back(IngestedContig{static_cast<uint32_t>(f), rec.start + 1 - fStart, hdrLen, outCursor, seqLen});
             const uint64_t next = align_up(outCursor + seqLen + TEXT_GAP, 16);
             chunks += (next - outCursor) / 16;
             outCursor = next;
@@ -253,21 +269,26 @@ void FastaBatchIngest::run(const HostImage* images, int nFiles) {
             files[f].firstContig = at;
         }
 
-    // ---- sequences -> texts ----
+    // ---- sequences -> texts, header lines -> host ----
     textBytes = outCursor + TEXT_TAIL;
     grow(&dText, &dTextCap, textBytes, "cudaMalloc(ingested texts)");
     check(cudaMemsetAsync(dText, 0, PAD, stream), "memset(ingested texts, head)");
     check(cudaMemsetAsync(dText + outCursor, 0, TEXT_TAIL, stream), "memset(ingested texts, tail)");
     if (accepted) {
         check(cudaMemcpyAsync(dGather, hGather, accepted * sizeof(FaGather), cudaMemcpyHostToDevice, stream), "H2D(gather)");
+        check(cudaMemcpyAsync(dHdrDesc, hHdrDesc, accepted * 24ull, cudaMemcpyHostToDevice, stream), "H2D(header descriptors)");
         nl += launch_fa_gather(in, dGather, accepted, chunks, dText, stream);
-    }
+        grow(&dHdr, &dHdrCap, hdrBytes + 64, "cudaMalloc(headers)");
+        growHost(&hHdr, &hHdrCap, hdrBytes + 64);
+        nl += launch_fa_headers(in, dHdrDesc, accepted, dHdr, stream);
+        if (hdrBytes) check(cudaMemcpyAsync(hHdr, dHdr, hdrBytes, cudaMemcpyDeviceToHost, stream), "D2H(headers)");
+    } else
+        growHost(&hHdr, &hHdrCap, 64);
     check(cudaGetLastError(), "ingest launch");
     check(cudaEventRecord(ev[2], stream), "event");
     check(cudaStreamSynchronize(stream), "ingest sync");
-    check(cudaEventElapsedTime(&ms[0], ev[0], ev[1]), "event time");
-    check(cudaEventElapsedTime(&ms[1], ev[1], ev[2]), "event time");
-    check(cudaEventElapsedTime(&ms[2], ev[0], ev[2]), "event time");
+    check(cudaEventElapsedTime(&ms[0], ev[1], ev[2]), "event time");
+    check(cudaEventElapsedTime(&ms[1], ev[0], ev[2]), "event time");
     launches = static_cast<uint64_t>(nl);
 }
 
@@ -505,8 +526,8 @@ void ReplicaSet::syncStateFromPrimary() {
 PinnedArena& ReplicaSet::arena() {
     std::lock_guard<std::mutex> g(arenaMu);
     if (!pinned) {
-        uint64_t slab = 64ull << 20;
-        int maxSlabs = 4 * size() + 2;
+        uint64_t slab = 16ull << 20;
+        int maxSlabs = 2 * size() + 6;
         if (const char* e = std::getenv("MBGC_B200_ARENA_SLAB_MB")) slab = std::max<uint64_t>(1, std::strtoull(e, nullptr, 10)) << 20;
         if (const char* e = std::getenv("MBGC_B200_ARENA_SLABS")) maxSlabs = std::max(0, std::atoi(e));
         pinned.reset(new PinnedArena(slab, maxSlabs));
@@ -524,12 +545,12 @@ SequentialPass::SequentialPass(ReplicaSet& rs_, const SeqConfig& c, const uint64
     if (const char* e = std::getenv("MBGC_B200_CHUNK_MB")) cfg.chunkBytes = std::max<uint64_t>(1, std::strtoull(e, nullptr, 10)) << 20;
     if (const char* e = std::getenv("MBGC_B200_WINDOW")) cfg.maxWindowContigs = static_cast<uint32_t>(std::max(1, std::atoi(e)));
     rs.setHostMirror(false);  // extensions come from device memory; nothing on this path reads getRef()
-    slots.resize(static_cast<size_t>(nd) * 2);
-    slotFree.assign(static_cast<size_t>(nd) * 2, true);
-    stageQ.resize(static_cast<size_t>(nd));
+    slots.resize(static_cast<size_t>(nd) * NSLOT);
+    slotFree.assign(static_cast<size_t>(nd) * NSLOT, true);
+    stageQ.resize(static_cast<size_t>(nd) * NSLOT);
     runState.resize(static_cast<size_t>(nd));
     curWindow = cfg.maxWindowContigs;
-    for (int r = 0; r < nd; r++) stagers.emplace_back([this, r] { stagerLoop(r); });
+    for (int q = 0; q < nd * NSLOT; q++) stagers.emplace_back([this, q] { stagerLoop(q); });  // one per ingest slot
 }
 
 SequentialPass::~SequentialPass() {
@@ -550,105 +571,121 @@ void SequentialPass::pushFile(const char* bytes, uint64_t n) {
     pending.push_back(HostImage{bytes, n});
     pendingBytes += n;
     pushedFiles++;
-    formChunks();
+    dispatch();
 }
 
 void SequentialPass::finishInput() {
     std::lock_guard<std::mutex> g(mu);
     inputDone = true;
-    formChunks();
+    dispatch();
 }
 
 bool SequentialPass::wantsInput() {
     std::lock_guard<std::mutex> g(mu);
     if (inputDone) return false;
     // keep about two windows of images ahead of the commit cursor
-    uint64_t inFlight = pendingBytes;
-    for (auto& c : staged)
-        for (auto& im : c->images) inFlight += im.n;
-    return inFlight < 3 * cfg.chunkBytes * static_cast<uint64_t>(rs.size());
+    return pendingBytes + stagedBytes < 3 * cfg.chunkBytes * static_cast<uint64_t>(rs.size());
 }
 
-// (mu held) pending files -> chunks, as long as the next replica in turn has a free slot
-void SequentialPass::formChunks() {
-    for (;;) {
-        if (pending.empty()) return;
-        if (pendingBytes < cfg.chunkBytes && !inputDone) return;
-        const int r = static_cast<int>(chunkSeq % static_cast<uint64_t>(rs.size()));
-        int slot = -1;
-        for (int s = 0; s < 2; s++)
-            if (slotFree[r * 2 + s]) { slot = s; break; }
-        if (slot < 0) return;
-        auto c = std::make_shared<Chunk>();
-        c->replica = r;
-        c->slot = slot;
-        c->firstFile = dispatchedFiles;
-        uint64_t bytes = 0;
-        while (!pending.empty() && (bytes == 0 || bytes + pending.front().n <= cfg.chunkBytes + cfg.chunkBytes / 4)) {
-            bytes += pending.front().n;
-            c->images.push_back(pending.front());
-            pending.pop_front();
-            if (bytes >= cfg.chunkBytes) break;
+// (mu held) pending files -> the chunk being formed on the replica whose turn it is; every file starts its trip to the
+// device at once, the chunk's kernels run when it is full
+void SequentialPass::dispatch() {
+    while (!pending.empty()) {
+        if (!forming) {
+            const int r = static_cast<int>(chunkSeq % static_cast<uint64_t>(rs.size()));
+            int slot = -1;
+            for (int s = 0; s < NSLOT; s++)
+                if (slotFree[r * NSLOT + s]) { slot = s; break; }
+            if (slot < 0) break;
+            forming = std::make_shared<Chunk>();
+            forming->replica = r;
+            forming->slot = slot;
+            forming->firstFile = dispatchedFiles;
+            slotFree[r * NSLOT + slot] = false;
+            chunkSeq++;
+            staged.push_back(forming);
+            stageQ[r * NSLOT + slot].push_back(StageMsg{StageMsg::BEGIN, forming, HostImage{nullptr, cfg.chunkBytes}});
         }
-        pendingBytes -= bytes;
-        dispatchedFiles += c->images.size();
-        slotFree[r * 2 + slot] = false;
-        chunkSeq++;
-        staged.push_back(c);
-        stageQ[r].push_back(c);
-        cv.notify_all();
+        const HostImage im = pending.front();
+        pending.pop_front();
+        pendingBytes -= im.n;
+        stagedBytes += im.n;
+        forming->nFiles++;
+        forming->bytes += im.n;
+        dispatchedFiles++;
+        stageQ[forming->replica * NSLOT + forming->slot].push_back(StageMsg{StageMsg::ADD, forming, im});
+        if (forming->bytes >= cfg.chunkBytes) {
+            forming->closed = true;
+            stageQ[forming->replica * NSLOT + forming->slot].push_back(StageMsg{StageMsg::FINISH, forming, HostImage{nullptr, 0}});
+            forming.reset();
+        }
     }
+    if (inputDone && forming && pending.empty()) {
+        forming->closed = true;
+        stageQ[forming->replica * NSLOT + forming->slot].push_back(StageMsg{StageMsg::FINISH, forming, HostImage{nullptr, 0}});
+        forming.reset();
+    }
+    cv.notify_all();
 }
 
-void SequentialPass::stagerLoop(int r) {
+// one thread per ingest slot: while one slot's chunk runs its kernels and host round trips (finish), the replica's other
+// slot already receives the images of the next chunk
+void SequentialPass::stagerLoop(int q) {
+    const int r = q / NSLOT;
     cudaSetDevice(rs.at(r)->deviceIndex());
     for (;;) {
-        std::shared_ptr<Chunk> c;
+        StageMsg msg;
         {
             std::unique_lock<std::mutex> lk(mu);
-            cv.wait(lk, [&] { return quit || !stageQ[r].empty(); });
-            if (quit) return;
-            c = stageQ[r].front();
-            stageQ[r].pop_front();
+            cv.wait(lk, [&] { return quit || !stageQ[q].empty(); });
+            if (quit) {
+                for (auto& m : stageQ[q])
+                    if (m.type == StageMsg::ADD) rs.arena().release(m.image.bytes);
+                return;
+            }
+            msg = stageQ[q].front();
+            stageQ[q].pop_front();
         }
+        Chunk& c = *msg.chunk;
+        const double t0 = now_ms();
         try {
-            auto& slot = slots[r * 2 + c->slot];
+            auto& slot = slots[r * NSLOT + c.slot];
             if (!slot) slot.reset(new FastaBatchIngest(rs.at(r)->deviceIndex()));
-            const double t0 = now_ms();
-            slot->run(c->images.data(), static_cast<int>(c->images.size()));
-            c->headers.resize(slot->contigs.size());
-            for (size_t k = 0; k < slot->contigs.size(); k++) {
-                const IngestedContig& ic = slot->contigs[k];
-                c->headers[k].assign(c->images[ic.file].bytes + ic.hdrOff, ic.hdrLen);
+            if (msg.type == StageMsg::BEGIN) {
+                slot->begin(msg.image.n);
+            } else if (msg.type == StageMsg::ADD) {
+                if (!c.err) slot->add(msg.image);
+            } else if (!c.err) {
+                slot->finish();
             }
-            uint64_t pageable = 0;
-            for (auto& im : c->images) {  // arena images are ours to give back now; others stay with the caller
-                if (!rs.arena().release(im.bytes)) pageable += im.n;
-            }
-            std::lock_guard<std::mutex> g(mu);
-            st.ingestMs += now_ms() - t0;
-            st.imageBytes += slot->imageBytes;
-            st.textBytes += slot->textBytes;
-            st.ingestLaunches += slot->launches;
-            st.pageableBytes += pageable;
-            st.chunks++;
         } catch (...) {
-            c->err = std::current_exception();
+            if (!c.err) c.err = std::current_exception();
         }
-        {
-            std::lock_guard<std::mutex> g(mu);
-            c->ready = true;
+        if (msg.type == StageMsg::ADD) rs.arena().release(msg.image.bytes);  // arena images are ours to give back; others stay with the caller
+        std::lock_guard<std::mutex> g(mu);
+        st.ingestMs += now_ms() - t0;
+        if (msg.type == StageMsg::FINISH) {
+            if (!c.err) {
+                auto& slot = slots[r * NSLOT + c.slot];
+                st.imageBytes += slot->imageBytes;
+                st.textBytes += slot->textBytes;
+                st.ingestLaunches += slot->launches;
+                st.pageableBytes += slot->pageableBytes;
+            }
+            st.chunks++;
+            c.ready = true;
+            cv.notify_all();
         }
-        cv.notify_all();
     }
 }
 
 // next window = the next (up to) one chunk per replica, in file order
 bool SequentialPass::startWindow() {
     std::unique_lock<std::mutex> lk(mu);
-    if (staged.empty()) return false;
+    size_t take = 0;
+    while (take < staged.size() && take < static_cast<size_t>(rs.size()) && staged[take]->closed) take++;
+    if (take == 0) return false;
     win.clear();
-    const size_t take = std::min<size_t>(staged.size(), static_cast<size_t>(rs.size()));
     const double t0 = now_ms();
     for (size_t k = 0; k < take; k++) {
         std::shared_ptr<Chunk> c = staged.front();
@@ -662,7 +699,7 @@ bool SequentialPass::startWindow() {
         if (c->err) std::rethrow_exception(c->err);
     items.clear();
     for (size_t w = 0; w < win.size(); w++) {
-        FastaBatchIngest& ing = *slots[win[w]->replica * 2 + win[w]->slot];
+        FastaBatchIngest& ing = *slots[win[w]->replica * NSLOT + win[w]->slot];
         for (size_t f = 0; f < ing.files.size(); f++) {
             const IngestedFile& fi = ing.files[f];
             for (uint32_t k = 0; k < fi.nContigs; k++) items.push_back(Item{false, static_cast<int>(w), fi.firstContig + k});
@@ -677,11 +714,14 @@ bool SequentialPass::startWindow() {
 
 void SequentialPass::releaseWindow() {
     std::lock_guard<std::mutex> g(mu);
-    for (auto& c : win) slotFree[c->replica * 2 + c->slot] = true;
+    for (auto& c : win) {
+        slotFree[c->replica * NSLOT + c->slot] = true;
+        stagedBytes -= c->bytes;
+    }
     win.clear();
     items.clear();
     winActive = false;
-    formChunks();
+    dispatch();
 }
 
 // match + pack the not yet valid contigs items[from ...) against the current state, at most curWindow of them and at
@@ -698,7 +738,7 @@ void SequentialPass::runFrom(size_t from) {
         Item& it = items[i];
         if (it.fileEnd) continue;
         const int r = win[it.chunk]->replica;
-        FastaBatchIngest& ing = *slots[r * 2 + win[it.chunk]->slot];
+        FastaBatchIngest& ing = *slots[r * NSLOT + win[it.chunk]->slot];
         const IngestedContig& ic = ing.contigs[it.contig];
         if (!runState[r].texts.empty() && bytes[r] + ic.seqLen > maxPassBytes) break;
         bytes[r] += ic.seqLen;
@@ -717,7 +757,7 @@ void SequentialPass::runFrom(size_t from) {
         int slot = -1;
         for (auto& c : win)
             if (c->replica == r) slot = c->slot;
-        FastaBatchIngest& ing = *slots[r * 2 + slot];
+        FastaBatchIngest& ing = *slots[r * NSLOT + slot];
         const uint64_t l0 = m->totalLaunches;
         const double t0 = now_ms();
         m->matchBatch(runState[r].texts, nullptr, cfg.minMatchLength, true, ing.dTexts(), runState[r].offs.data(), true);
@@ -750,7 +790,7 @@ void SequentialPass::next(SeqEvent& ev) {
             if (!startWindow()) {
                 std::lock_guard<std::mutex> g(mu);
                 ev = SeqEvent{};
-                if (inputDone && pending.empty() && staged.empty()) {
+                if (inputDone && pending.empty() && staged.empty() && !forming) {
                     ev.type = SeqEvent::DONE;
                     ev.loadedRefLength = rs.primary()->getLoadedRefLength();
                 } else
@@ -765,7 +805,7 @@ void SequentialPass::next(SeqEvent& ev) {
         }
         Item& it = items[cursor];
         Chunk& ch = *win[it.chunk];
-        FastaBatchIngest& ing = *slots[ch.replica * 2 + ch.slot];
+        FastaBatchIngest& ing = *slots[ch.replica * NSLOT + ch.slot];
         B200SparseEMMatcher* pm = rs.primary();
         if (it.fileEnd) {
             // processTargetMeta + processAfterTargetWithParallelIO (MBGC_Encoder.cpp:493-509): separator, the size of this
@@ -808,8 +848,8 @@ void SequentialPass::next(SeqEvent& ev) {
         SeqEvent e{};
         e.type = SeqEvent::CONTIG;
         e.file = ch.firstFile + ic.file;
-        e.hdr = ch.headers[it.contig].data();
-        e.hdrLen = ch.headers[it.contig].size();
+        e.hdr = ing.header(it.contig);
+        e.hdrLen = ic.hdrLen;
         e.seqLen = ic.seqLen;
         e.nMatches = m->batchCounts()[it.resIndex];
         e.kept = m->packKept()[it.resIndex];

@@ -51,6 +51,7 @@ struct IngestedContig {
 // One ingest slot: the images of a batch of files -> device, record splitting / validation / line joining for all of
 // them in one set of launches (ingest.cu), the sequences left on the device in the batch-text layout of the match stage.
 // Owns its stream, so that a slot can be filled while the matcher's stream works on another one.
+//   begin();  add(image) ...;  finish();      add() returns when the image is on the device (its memory is free again)
 class FastaBatchIngest {
 public:
     explicit FastaBatchIngest(int device);
@@ -58,29 +59,48 @@ public:
     FastaBatchIngest(const FastaBatchIngest&) = delete;
     FastaBatchIngest& operator=(const FastaBatchIngest&) = delete;
 
-    // blocking; afterwards files / contigs / dTexts() describe the batch.  Pinned images are copied by DMA straight from
-    // the caller's memory, pageable ones through this slot's pinned bounce buffers.
-    void run(const HostImage* images, int nFiles);
+    void begin(uint64_t expectedBytes);
+    // Pinned images are copied by DMA straight from the caller's memory, pageable ones through this slot's pinned bounce
+    // buffers.  Blocking: the image may be released when the call returns.
+    void add(const HostImage& image);
+    // blocking; afterwards files / contigs / headers / dTexts() describe the batch
+    void finish();
+    void run(const HostImage* images, int nFiles) {
+        uint64_t b = 0;
+        for (int i = 0; i < nFiles; i++) b += images[i].n;
+        begin(b);
+        for (int i = 0; i < nFiles; i++) add(images[i]);
+        finish();
+    }
     const uint8_t* dTexts() const { return dText; }
     std::vector<IngestedFile> files;
     std::vector<IngestedContig> contigs;
-    uint64_t launches = 0;         // kernel launches of the last run
-    uint64_t imageBytes = 0, textBytes = 0, wireBytes = 0;
-    float ms[3] = {0, 0, 0};       // last run: images host -> device, kernels (incl. the two host round trips), total
+    std::vector<uint64_t> fileBytes;   // image size per file
+    const char* header(size_t contig) const { return reinterpret_cast<const char*>(hHdr) + hdrAt[contig]; }
+    uint64_t launches = 0;         // kernel launches of the last batch
+    uint64_t imageBytes = 0, textBytes = 0, pageableBytes = 0;
+    float ms[2] = {0, 0};          // last batch: kernels (incl. the two host round trips) of finish(); begin -> end of finish
     int deviceIndex() const { return device; }
 
 private:
     void check(cudaError_t e, const char* what);
-    void grow(uint8_t** p, uint64_t* cap, uint64_t need, const char* what);
+    void grow(uint8_t** p, uint64_t* cap, uint64_t need, const char* what, bool keep = false, uint64_t keepBytes = 0);
     int device;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[3] = {};
     cudaEvent_t bounceEv[2] = {};
     uint8_t* hBounce[2] = {nullptr, nullptr};
+    int bounceUse = 0;
     uint8_t* dIn = nullptr; uint64_t dInCap = 0;
     uint8_t* dWork = nullptr; uint64_t dWorkCap = 0;
     uint8_t* dText = nullptr; uint64_t dTextCap = 0;
+    uint8_t* dHdr = nullptr; uint64_t dHdrCap = 0;
     uint8_t* hWork = nullptr; uint64_t hWorkCap = 0;   // pinned
+    uint8_t* hHdr = nullptr; uint64_t hHdrCap = 0;     // pinned: the header lines of the batch
+    std::vector<uint64_t> hdrAt;
+    std::vector<int> live;             // files that travelled
+    std::vector<uint64_t> spans;       // start, end per live image
+    uint64_t cursor = 0;               // next image offset (behind the 16 leading bytes)
 };
 
 // Pinned host memory in large slabs, handed out in pieces (file images).  cudaHostAlloc costs ~0.3 ms per MiB, far too
@@ -92,6 +112,7 @@ public:
     void* alloc(uint64_t n);       // nullptr when the arena is full (the caller falls back to pageable memory)
     bool release(const void* p);   // false if p is not from this arena
     bool owns(const void* p);
+    uint64_t maxPiece() const { return slabBytes; }
 private:
     struct Slab { uint8_t* base; uint64_t used; int live; bool open; };
     std::mutex mu;
@@ -188,11 +209,15 @@ public:
 private:
     struct Chunk {
         int replica = 0, slot = 0;
-        uint64_t firstFile = 0;
-        std::vector<HostImage> images;
-        std::vector<std::string> headers;   // copied at ingest time (the images of arena memory are gone by commit time)
-        bool ready = false;
+        uint64_t firstFile = 0, nFiles = 0, bytes = 0;
+        bool closed = false;       // no more files will join (FINISH is queued)
+        bool ready = false;        // ingested
         std::exception_ptr err;
+    };
+    struct StageMsg {
+        enum Type { BEGIN, ADD, FINISH } type;
+        std::shared_ptr<Chunk> chunk;
+        HostImage image;
     };
     struct Item {                  // one step of the committed order
         bool fileEnd;
@@ -201,8 +226,8 @@ private:
         bool valid = false;
         uint32_t resIndex = 0;     // position in its replica's last run
     };
-    void formChunks();
-    void stagerLoop(int r);
+    void dispatch();
+    void stagerLoop(int q);
     bool startWindow();
     void runFrom(size_t from);
     void releaseWindow();
@@ -218,14 +243,15 @@ private:
     std::mutex mu;
     std::condition_variable cv;
     std::deque<HostImage> pending;
-    uint64_t pendingBytes = 0, pushedFiles = 0, dispatchedFiles = 0;
+    std::shared_ptr<Chunk> forming;
+    uint64_t pendingBytes = 0, stagedBytes = 0, pushedFiles = 0, dispatchedFiles = 0;
     bool inputDone = false;
     uint64_t chunkSeq = 0;
 
-    // staging: two ingest slots per replica, one stager thread per replica
-    std::vector<std::unique_ptr<FastaBatchIngest>> slots;   // [replica * 2 + slot]
+    // staging: NSLOT ingest slots per replica, one stager thread per slot
+    std::vector<std::unique_ptr<FastaBatchIngest>> slots;   // [replica * NSLOT + slot]
     std::vector<bool> slotFree;
-    std::vector<std::deque<std::shared_ptr<Chunk>>> stageQ;  // per replica
+    std::vector<std::deque<StageMsg>> stageQ;                // per ingest slot
     std::vector<std::thread> stagers;
     std::deque<std::shared_ptr<Chunk>> staged;               // dispatched chunks in file order
     bool quit = false;

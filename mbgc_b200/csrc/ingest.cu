@@ -395,6 +395,24 @@ int launch_fa_records(const uint8_t* in, uint64_t n, const uint64_t* starts, uin
     return 2;
 }
 
+// header lines of the accepted records -> one contiguous buffer (a warp per header; they go back to the host in one copy)
+__global__ void __launch_bounds__(256) k_fa_headers(const uint8_t* __restrict__ in, const uint64_t* __restrict__ hdr, uint32_t nRecs,
+                                                    uint8_t* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warpsTotal = gridDim.x * (blockDim.x >> 5);
+    for (uint32_t r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < nRecs; r += warpsTotal) {
+        const uint64_t src = hdr[3 * r], len = hdr[3 * r + 1], dst = hdr[3 * r + 2];
+        for (uint64_t k = lane; k < len; k += 32) out[dst + k] = in[src + k];
+    }
+}
+
+int launch_fa_headers(const uint8_t* in, const uint64_t* hdr, uint32_t nRecs, uint8_t* out, cudaStream_t st) {
+    if (nRecs == 0) return 0;
+    const uint32_t blocks = (nRecs + 7) / 8;
+    k_fa_headers<<<blocks < 1024 ? blocks : 1024, 256, 0, st>>>(in, hdr, nRecs, out);
+    return 1;
+}
+
 int launch_fa_gather(const uint8_t* in, const FaGather* g, uint32_t nRecs, uint64_t nChunks, uint8_t* out, cudaStream_t st) {
     if (nChunks == 0) return 0;
     const uint64_t perBlock = static_cast<uint64_t>(FA_THREADS) * FA_PER_THREAD;

@@ -42,6 +42,8 @@ int launch_fa_records(const uint8_t* in, uint64_t n, const uint64_t* starts, uin
 // filler bytes around the images of a batched ingest (spans[2f], spans[2f+1] = start / end offset of image f; the buffer
 // has 16 bytes in front of spans[0] and extends to bufEnd)
 int launch_fa_filler(uint8_t* in, const uint64_t* spans, uint32_t nFiles, uint64_t bufEnd, cudaStream_t st);
+// hdr[3r], hdr[3r+1], hdr[3r+2] = offset of header r in `in`, its length, its offset in `out`
+int launch_fa_headers(const uint8_t* in, const uint64_t* hdr, uint32_t nRecs, uint8_t* out, cudaStream_t st);
 int launch_fa_gather(const uint8_t* in, const FaGather* g, uint32_t nRecs, uint64_t nChunks, uint8_t* out, cudaStream_t st);
 
 }  // namespace mbgc_b200

@@ -26,6 +26,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
@@ -123,8 +124,17 @@ void MultipleGenomeMatchingProcessor::processTargetsWithParallelIO() {
     if (const char* e = std::getenv("MBGC_B200_READERS")) nReaders = std::atoi(e);
     nReaders = std::max(1, std::min(nReaders, std::min(nFiles, 32)));
     if (iterableDecoder) nReaders = 1;      // the decoder iterator hands out files in order, from one thread
+    int allocTurn = 0;                      // next file that may ask for pinned memory (under mu)
+    std::vector<char> turnDone(static_cast<size_t>(nFiles), 0);
+    auto passTurn = [&](int i) {            // (mu held) file i has had its turn, or does not need one
+        turnDone[i] = 1;
+        while (allocTurn < nFiles && turnDone[allocTurn]) allocTurn++;
+        cv.notify_all();
+    };
+    const uint64_t arenaMax = mbgcg_image_max(h);
     auto readOne = [&](int i) {
         Image im;
+        bool turnTaken = false;
         if (i == 0 && firstFpIsFirstTarget) {  // the file loadG0Ref already holds (mgmpInReset, :247)
             mgmpInReset(firstFp);
             im.bytes = reinterpret_cast<const char*>(firstFp.out);
@@ -136,7 +146,22 @@ void MultipleGenomeMatchingProcessor::processTargetsWithParallelIO() {
             bool done = false;
             if (fd >= 0 && fstat(fd, &sb) == 0 && S_ISREG(sb.st_mode) && sb.st_size >= 2) {
                 const size_t n = static_cast<size_t>(sb.st_size);
-                char* buf = static_cast<char*>(mbgcg_image_alloc(h, n));
+                // Pinned memory goes out in file order: a file whose turn it is waits for room (earlier files are on their
+                // way to the device and give theirs back), later files wait for their turn -- so the arena can be small
+                // without ever blocking the file the pass is waiting for.
+                char* buf = nullptr;
+                {
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv.wait(lk, [&] { return allocTurn == i; });
+                }
+                if (n <= arenaMax)
+                    for (int spin = 0; !(buf = static_cast<char*>(mbgcg_image_alloc(h, n))) && spin < 20000; spin++)
+                        std::this_thread::sleep_for(std::chrono::microseconds(50));
+                {
+                    std::lock_guard<std::mutex> g(mu);
+                    passTurn(i);
+                }
+                turnTaken = true;
                 const bool arena = buf != nullptr;
                 if (!buf) buf = static_cast<char*>(malloc(n));
                 size_t got = 0;
@@ -164,6 +189,7 @@ void MultipleGenomeMatchingProcessor::processTargetsWithParallelIO() {
             }
         }
         std::lock_guard<std::mutex> g(mu);
+        if (!turnTaken) passTurn(i);  // a file that never asked for pinned memory still passes the turn on
         im.ready = true;
         images[i] = im;
         cv.notify_all();

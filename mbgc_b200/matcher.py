@@ -125,6 +125,8 @@ def load_library():
     L.mbgcg_seq_end.argtypes = [vp, C.POINTER(SeqStats)]
     L.mbgcg_image_alloc.restype = vp
     L.mbgcg_image_alloc.argtypes = [vp, C.c_uint64]
+    L.mbgcg_image_max.restype = C.c_uint64
+    L.mbgcg_image_max.argtypes = [vp]
     L.mbgcg_image_free.restype = C.c_int
     L.mbgcg_image_free.argtypes = [vp, vp]
     L.mbgcg_set_host_mirror.argtypes = [vp, C.c_int]

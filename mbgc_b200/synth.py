@@ -76,3 +76,39 @@ def mgmp_ref_limit(n_files, basic_len, rc=True):
     tmp = 5 if tmp < 5 else (12 if tmp > 12 else tmp)
     lim = (1 << tmp) * max(basic_len, 1 << 21) * (2 if rc else 1)
     return min(lim, 2**32 - 1)
+
+
+def _write_one(args):
+    d, i, length, seed, p_snp, p_indel = args
+    base = synth_base(length, seed)
+    g = base if i == 0 else synth_mutant(base, seed * 1000003 + i, p_snp, p_indel)
+    name = f"g{i:04d}.fna"
+    path = f"{d}/{name}"
+    write_fasta(path, f"syn_{i:04d} synthetic E. coli-like genome {i}", g)
+    import os
+    return name, os.path.getsize(path)
+
+
+def write_collection(d, n, length, seed, p_snp, p_indel, workers=None):
+    """the collection of SURVEY.md 8d as files: g0000.fna = base, g%04d.fna = mutant i (80-column lines, one record per
+    file), plus list.txt in index order.  Returns (names, total FASTA bytes).  Files that already exist with the right
+    count are kept (the generator is deterministic)."""
+    import os
+    from concurrent.futures import ProcessPoolExecutor
+    os.makedirs(d, exist_ok=True)
+    stamp = os.path.join(d, f".done_{n}_{length}_{seed}_{p_snp}_{p_indel}")
+    names = [f"g{i:04d}.fna" for i in range(n)]
+    if not os.path.exists(stamp):
+        workers = workers or min(32, os.cpu_count() or 1)
+        jobs = [(d, i, length, seed, p_snp, p_indel) for i in range(n)]
+        if workers > 1 and n > 4:
+            with ProcessPoolExecutor(workers) as ex:
+                list(ex.map(_write_one, jobs, chunksize=max(1, n // (workers * 4))))
+        else:
+            for j in jobs:
+                _write_one(j)
+        with open(os.path.join(d, "list.txt"), "w") as f:
+            f.write("\n".join(names) + "\n")
+        open(stamp, "w").close()
+    total = sum(os.path.getsize(os.path.join(d, x)) for x in names)
+    return names, total
