@@ -283,6 +283,31 @@ int mbgcg_seq_wants_input(mbgcg_t* h);
 int mbgcg_seq_next(mbgcg_t* h, mbgcg_seq_event_t* ev);
 int mbgcg_seq_end(mbgcg_t* h, mbgcg_seq_stats_t* stats);
 
+/* The same pass run to its end in one call, for callers that want the encoder's view of the result rather than the
+ * events: the six streams as MBGC_Encoder holds them after the last target -- every contig's segments in target order,
+ * SEQ_SEPARATOR_MARK behind each contig's literals (processAfterSequence, MBGC_Encoder.cpp:489-491), FILE_SEPARATOR_MARK
+ * behind each file's mismatch flags (processAfterTarget, :493-496) -- plus the per-file meta data and the header lines.
+ * next_image is called from the calling thread whenever the pass can use another file: return 1 with *bytes / *n set,
+ * 0 if none is ready yet (only allowed when block == 0), -1 when there are no more files. */
+typedef int (*mbgcg_next_image_fn)(void* user, int block, const char** bytes, uint64_t* n);
+typedef struct {
+    const uint8_t* stream[MBGCG_S_COUNT];
+    uint64_t streamLen[MBGCG_S_COUNT];
+    uint64_t nFiles, nContigs;
+    const uint64_t* seqCounts;     /* [nFiles] processTargetMeta's first argument */
+    const uint64_t* dnaLineLens;   /* [nFiles] ... and its second */
+    const uint64_t* refExtSizes;   /* [nFiles] what goes to refExtSizeDest (lazy decompression support) */
+    const uint64_t* lockPos;       /* [nFiles] what goes to locksPosStream */
+    const int32_t* status;         /* [nFiles] the reader's final status per file */
+    const char* headers;           /* all header lines, each followed by '\n', in target order */
+    uint64_t headersLen;
+    uint64_t matches, unmatched, extensions;
+    uint64_t digest;               /* sum over the contigs of a 64-bit FNV-1a hash of their stream segments: independent
+                                    * of how the files were split over windows, devices or ranks */
+} mbgcg_seq_result_t;
+/* call between mbgcg_seq_begin and mbgcg_seq_end; *out stays valid until mbgcg_seq_end */
+int mbgcg_seq_run(mbgcg_t* h, mbgcg_next_image_fn next_image, void* user, int keepStreams, mbgcg_seq_result_t* out);
+
 /* Pinned host memory for file images, cut from large slabs (cudaHostAlloc costs ~0.5 ms per MiB): DMA reads it at PCIe
  * speed, pageable images travel through bounce buffers at ~1/4 of that.  NULL when the arena is full -- use any other
  * memory then.  mbgcg_image_free only for images that were never pushed. */
@@ -355,6 +380,12 @@ void mbgcg_set_stage_timing(mbgcg_t* h, int on);
 /* counters of the last match call: 0 positions, 1 seed segments, 2 seed runs, 3 matches, 4 kernel launches,
  * 5 passes, 6 chunks (512 positions), 7 lanes (16 positions) that went through the full probe */
 void mbgcg_last_counters(const mbgcg_t* h, uint64_t out[8]);
+/* last match call: bytes that crossed PCIe, out[0] host -> device (texts raw or 2-bit packed, descriptors), out[1]
+ * device -> host (counts + match lists) */
+void mbgcg_last_wire_bytes(const mbgcg_t* h, uint64_t out[2]);
+/* last mbgcg_load_ref: ms[0] device time of the call (staging copy, segment kernels, index inserts; CUDA events),
+ * ms[1] host wall time; *appended = reference bytes it appended (text + reverse complement + separators) */
+void mbgcg_load_ref_timing(const mbgcg_t* h, float ms[2], uint64_t* appended);
 /* total kernel launches issued by this handle since creation */
 uint64_t mbgcg_total_launches(const mbgcg_t* h);
 /* the cudaStream_t every kernel and copy of this handle is issued on (to bracket calls with CUDA events) */

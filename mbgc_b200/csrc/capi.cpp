@@ -18,6 +18,12 @@ struct mbgcg {
     ReplicaSet* rs = nullptr;            // the replicas (one per device); m = replica 0
     B200SparseEMMatcher* m = nullptr;
     SequentialPass* pass = nullptr;      // the collection pass in progress, if any
+    struct RunResult {                    // what mbgcg_seq_run accumulates (valid until mbgcg_seq_end)
+        std::string stream[MBGCG_S_COUNT];
+        std::vector<uint64_t> seqCounts, dnaLineLens, refExtSizes, lockPos;
+        std::vector<int32_t> status;
+        std::string headers;
+    } run;
     std::string err;
     std::vector<TextMatch> single;
     std::vector<TextMatch> kept;
@@ -314,6 +320,15 @@ void mbgcg_last_counters(const mbgcg_t* h, uint64_t out[8]) {
     for (int i = 0; i < 8; i++) out[i] = h->m->lastCounters[i];
 }
 uint64_t mbgcg_total_launches(const mbgcg_t* h) { return h->m->totalLaunches; }
+void mbgcg_last_wire_bytes(const mbgcg_t* h, uint64_t out[2]) {
+    out[0] = h->m->lastWire[0];
+    out[1] = h->m->lastWire[1];
+}
+void mbgcg_load_ref_timing(const mbgcg_t* h, float ms[2], uint64_t* appended) {
+    ms[0] = h->m->lastLoadRefMs[0];
+    ms[1] = h->m->lastLoadRefMs[1];
+    if (appended) *appended = h->m->lastLoadRefBases;
+}
 void* mbgcg_stream(const mbgcg_t* h) { return h->m->streamHandle(); }
 
 // ---- pinned host memory for file images -----------------------------------------------------------------------------
@@ -404,6 +419,89 @@ int mbgcg_seq_next(mbgcg_t* h, mbgcg_seq_event_t* ev) {
         ev->refExtSize = e.refExtSize;
         ev->lockPos = e.lockPos;
         ev->loadedRefLength = e.loadedRefLength;
+    });
+}
+
+int mbgcg_seq_run(mbgcg_t* h, mbgcg_next_image_fn next_image, void* user, int keepStreams, mbgcg_seq_result_t* out) {
+    if (!out) return MBGCG_E_PARAM;
+    std::memset(out, 0, sizeof(*out));
+    return guarded(h, [&] {
+        if (!h->pass) throw MatcherError(MBGCG_E_PARAM, "seq_run: no pass in progress");
+        if (!next_image) throw MatcherError(MBGCG_E_PARAM, "seq_run: no image source");
+        h->run = mbgcg::RunResult();
+        auto& R = h->run;
+        bool finished = false;
+        auto feed = [&](bool block) {   // returns false when nothing was pushed
+            const char* bytes = nullptr;
+            uint64_t n = 0;
+            const int rc = next_image(user, block ? 1 : 0, &bytes, &n);
+            if (rc > 0) {
+                h->pass->pushFile(bytes, n);
+                return true;
+            }
+            if (rc < 0) {
+                h->pass->finishInput();
+                finished = true;
+                return true;
+            }
+            if (block) throw MatcherError(MBGCG_E_PARAM, "seq_run: the image source returned nothing to a blocking request");
+            return false;
+        };
+        const char SEQ_MARK = static_cast<char>(0xA2), FILE_MARK = static_cast<char>(0xBB);  // MBGC_Params.h:46-47
+        uint64_t contigs = 0, matches = 0, unmatched = 0, extensions = 0, digest = 0;
+        mbgc_b200::SeqEvent e;
+        for (;;) {
+            while (!finished && h->pass->wantsInput() && feed(false)) {}
+            h->pass->next(e);
+            if (e.type == mbgc_b200::SeqEvent::DONE) break;
+            if (e.type == mbgc_b200::SeqEvent::NEED_INPUT) {
+                if (finished) throw MatcherError(MBGCG_E_PARAM, "seq_run: the pass asks for input after the last file");
+                feed(true);
+                continue;
+            }
+            if (e.type == mbgc_b200::SeqEvent::CONTIG) {
+                uint64_t hsh = 1469598103934665603ull;
+                for (int s = 0; s < MBGCG_S_COUNT; s++) {
+                    for (uint64_t k = 0; k < e.segLen[s]; k++) hsh = (hsh ^ e.seg[s][k]) * 1099511628211ull;
+                    hsh = (hsh ^ 0xFF) * 1099511628211ull;
+                    if (keepStreams && e.segLen[s]) R.stream[s].append(reinterpret_cast<const char*>(e.seg[s]), e.segLen[s]);
+                }
+                digest += hsh;
+                if (keepStreams) {
+                    R.stream[MBGCG_S_LITERALS].push_back(SEQ_MARK);
+                    R.headers.append(e.hdr, e.hdrLen);
+                    R.headers.push_back('\n');
+                }
+                contigs++;
+                matches += e.nMatches;
+                unmatched += e.unmatched;
+                extensions += e.extended ? 1 : 0;
+            } else {
+                if (keepStreams && h->pass->config().pack.enableExt) R.stream[MBGCG_S_GAPFLAGS].push_back(FILE_MARK);
+                R.seqCounts.push_back(e.nContigs);
+                R.dnaLineLens.push_back(e.dnaLineLen);
+                R.refExtSizes.push_back(e.refExtSize);
+                R.lockPos.push_back(e.lockPos);
+                R.status.push_back(e.status);
+            }
+        }
+        for (int s = 0; s < MBGCG_S_COUNT; s++) {
+            out->stream[s] = reinterpret_cast<const uint8_t*>(R.stream[s].data());
+            out->streamLen[s] = R.stream[s].size();
+        }
+        out->nFiles = R.seqCounts.size();
+        out->nContigs = contigs;
+        out->seqCounts = R.seqCounts.data();
+        out->dnaLineLens = R.dnaLineLens.data();
+        out->refExtSizes = R.refExtSizes.data();
+        out->lockPos = R.lockPos.data();
+        out->status = R.status.data();
+        out->headers = R.headers.data();
+        out->headersLen = R.headers.size();
+        out->matches = matches;
+        out->unmatched = unmatched;
+        out->extensions = extensions;
+        out->digest = digest;
     });
 }
 

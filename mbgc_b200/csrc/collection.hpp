@@ -205,6 +205,7 @@ public:
     bool wantsInput();
     void next(SeqEvent& ev);       // pointers in ev stay valid until the next call
     const SeqStats& stats() const { return st; }
+    const SeqConfig& config() const { return cfg; }
 
 private:
     struct Chunk {

@@ -258,6 +258,8 @@ void B200SparseEMMatcher::loadRef(const char* refText, uint64_t refLength, bool 
             fprintf(stderr, "[mbgc_b200]   loadRef: %-22s at %8.3f ms\n", what,
                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
     };
+    const uint64_t loaded0 = getLoadedRefLength();
+    check(cudaEventRecord(ev[10], stream), "event");
     if (refLength) {  // the text goes up once, through pinned staging (a pageable source would be staged by the driver)
         growPinned(reinterpret_cast<void**>(&hStage), &hStageCap, refLength, "cudaHostAlloc(ref staging)");
         growDevice(reinterpret_cast<void**>(&dStage), &dStageCap, refLength + 64, "cudaMalloc(ref staging)");
@@ -271,8 +273,12 @@ void B200SparseEMMatcher::loadRef(const char* refText, uint64_t refLength, bool 
     lap("reverse complement");
     // the caller may free refText right after the call; pageable copies are staged before returning, but
     // keep the ordering explicit
+    check(cudaEventRecord(ev[11], stream), "event");
     check(cudaStreamSynchronize(stream), "loadRef sync");
     lap("device done");
+    check(cudaEventElapsedTime(&lastLoadRefMs[0], ev[10], ev[11]), "event time");
+    lastLoadRefMs[1] = static_cast<float>(std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    lastLoadRefBases = getLoadedRefLength() - loaded0;
 }
 
 // loadRef whose text is already in this device's memory (an ingested contig, or a peer copy of one): nothing crosses
@@ -283,9 +289,16 @@ void B200SparseEMMatcher::loadRefDevice(const void* dText, const char* hostText,
     if (mirrorEnabled && !hostText && refLength)
         throw MatcherError(MBGCG_E_PARAM, "loadRef from device memory needs the host text too while the host mirror is on");
     const uint8_t* src = static_cast<const uint8_t*>(dText);
+    const auto t0 = std::chrono::steady_clock::now();
+    const uint64_t loaded0 = getLoadedRefLength();
+    check(cudaEventRecord(ev[10], stream), "event");
     loadSegment(hostText, src, refLength, false, addRegionSeparators, regionSeparator);
     if (loadRCRef) loadSegment(hostText, src, refLength, true, addRegionSeparators, regionSeparator);
+    check(cudaEventRecord(ev[11], stream), "event");
     check(cudaStreamSynchronize(stream), "loadRef sync");
+    check(cudaEventElapsedTime(&lastLoadRefMs[0], ev[10], ev[11]), "event time");
+    lastLoadRefMs[1] = static_cast<float>(std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    lastLoadRefBases = getLoadedRefLength() - loaded0;
 }
 
 // staging buffer of at least n bytes on this device (the target of a peer copy before loadRefDevice)
@@ -605,6 +618,7 @@ int B200SparseEMMatcher::stageTexts(const std::vector<TextView>& texts, size_t f
             if (texts[first + c].len)
                 check(cudaMemcpyAsync(dText + off[c], texts[first + c].data, texts[first + c].len, cudaMemcpyHostToDevice,
                                       stream), "H2D(text)");
+        lastWire[0] += total;
         return 0;
     }
     if (!pool) {
@@ -680,6 +694,7 @@ int B200SparseEMMatcher::stageTexts(const std::vector<TextView>& texts, size_t f
     uint32_t pi = 0;
     auto copyRaw = [&](const Blk& b) {
         check(cudaMemcpyAsync(dText + b.dev, b.src, b.n, cudaMemcpyHostToDevice, stream), "H2D(raw block)");
+        lastWire[0] += b.n;
     };
     while (ri < rawBlks.size() || pi < nB) {
         if (pi < nB && pool->done(pi)) {
@@ -693,9 +708,11 @@ int B200SparseEMMatcher::stageTexts(const std::vector<TextView>& texts, size_t f
                 lo = std::min(lo, blks[b].poff);
                 hi = blks[b].poff + align_up((blks[b].n + 3) / 4, 16);
             }
-            if (lo != UINT64_MAX)
+            if (lo != UINT64_MAX) {
                 check(cudaMemcpyAsync(static_cast<uint8_t*>(dPacked) + lo, hp + lo, hi - lo, cudaMemcpyHostToDevice, stream),
                       "H2D(packed blocks)");
+                lastWire[0] += hi - lo;
+            }
         } else if (ri < rawBlks.size()) {
             copyRaw(rawBlks[ri++]);
         } else {
@@ -722,6 +739,7 @@ int B200SparseEMMatcher::stageTexts(const std::vector<TextView>& texts, size_t f
             for (const ExcRun& e : blockRuns[b]) hr[kr++] = ExcRunDev{e.off, e.len, e.byte};
         }
     check(cudaMemcpyAsync(dXferMeta, hXferMeta, metaBytes - 64, cudaMemcpyHostToDevice, stream), "H2D(transfer meta)");
+    lastWire[0] += metaBytes - 64;
     const PackedBlock* db = static_cast<const PackedBlock*>(dXferMeta);
     return launch_unpack(db, static_cast<uint32_t>(nPacked), static_cast<const uint8_t*>(dPacked),
                          reinterpret_cast<const ExcRunDev*>(db + nPacked), static_cast<uint32_t>(nRuns), dText, stream);
@@ -744,6 +762,7 @@ void B200SparseEMMatcher::matchBatch(const std::vector<TextView>& texts, const u
     for (auto& m : stageMs) m = 0;
     timingPending = false;
     for (auto& c : lastCounters) c = 0;
+    lastWire[0] = lastWire[1] = 0;
     if (texts.empty()) return;
     for (const auto& t : texts)
         if (t.len >= (1ull << 32)) throw MatcherError(MBGCG_E_UNSUPPORTED, "target text of 4 GiB or more");
@@ -805,6 +824,7 @@ void B200SparseEMMatcher::matchBatch(const std::vector<TextView>& texts, const u
             const uint64_t metaUsed = static_cast<uint64_t>(nC) * 24 + 4;
             mark(0);
             check(cudaMemcpyAsync(dMeta, hMeta, metaUsed, cudaMemcpyHostToDevice, stream), "H2D(meta)");
+            lastWire[0] += metaUsed;
             const uint8_t* textBase;
             if (textsOnDevice) {
                 textBase = static_cast<const uint8_t*>(dTextBase);
@@ -899,6 +919,8 @@ void B200SparseEMMatcher::matchBatch(const std::vector<TextView>& texts, const u
                 check(cudaStreamSynchronize(stream), "D2H sync");
             }
             nMatchesAll += total;
+            lastWire[1] += (static_cast<uint64_t>(nC) + 1) * 4 + 32 +
+                           (listsStayOnDevice ? guess : std::max<uint64_t>(guess, total)) * sizeof(TextMatch);
             for (int c = 0; c < nC; c++) resCounts[first + c] = hOffs[c + 1] - hOffs[c];
             timingPending = stageTiming;  // the events of this pass are read when somebody asks (collectTiming)
             if (last < texts.size()) collectTiming();  // more passes follow and will reuse the events

@@ -157,6 +157,9 @@ public:
     float stageMs[MBGCG_T_COUNT_] = {0};   // valid after collectTiming()
     void collectTiming();
     uint64_t lastCounters[8] = {0};
+    uint64_t lastWire[2] = {0, 0};         // last match call: bytes that crossed PCIe host -> device, device -> host
+    float lastLoadRefMs[2] = {0, 0};       // last loadRef / loadRefDevice: device time (CUDA events), host wall time
+    uint64_t lastLoadRefBases = 0;         // reference bytes it appended (forward + reverse complement)
     uint64_t totalLaunches = 0;
 
 private:

@@ -293,3 +293,48 @@ def compress_speculative(matcher, files, pack_params, window, device="cpu", min_
         close_file()
         next_file += 1
     return {n: b"".join(v) for n, v in out.items()}, stats
+
+
+# ------------------------------------------------------------------------------------------------------
+# The collection pass (mbgcg_seq_*, C++: mbgc_b200/csrc/collection.cpp) sharded over ranks: every rank reads ONLY its
+# own files and keeps its stream bytes; what travels is one integer per rank.
+# ------------------------------------------------------------------------------------------------------
+
+class SpeculationFailed(RuntimeError):
+    """a rank other than the last extended the reference: the shards behind it were matched against a stale state"""
+
+
+def compress_sharded_files(matcher, paths, cfg, device="cpu", readers=None, keep_streams=True):
+    """The sequential (-t 1) schedule of `paths` (files in target order; every rank passes the same list) with the files
+    split into one contiguous shard per rank.  Rank r runs the collection pass on its shard against the state the
+    sequential schedule has after the files in front of it PROVIDED none of them extends the reference: one region
+    separator per file (mbgccoder/MBGC_Encoder.cpp:498-505) and nothing else.  That speculation is checked afterwards
+    with one all_gather of the per-rank extension counts; it holds for near-identical collections (the README's
+    1k-E.-coli regime) and raises SpeculationFailed otherwise (use compress_speculative, or one process
+    with mbgcg_create_multi, for divergent collections).
+
+    Returns (streams of this rank's shard, info, extensions per rank).  The sequential schedule's streams are the
+    per-rank streams concatenated in rank order; nothing but the counts is exchanged."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
+    a, b = shard_range(len(paths), rank, world)
+    loaded = [matcher.getLoadingPosition()]
+    if cfg.separatorPerFile:
+        start = matcher.getLoadedRefLength()
+        for _ in range(a):
+            matcher.loadSeparator(0)
+            now = matcher.getLoadedRefLength()
+            loaded.append(loaded[-1] + (now - start))
+            start = now
+    streams, info = matcher.compressFiles(paths[a:b], cfg, loadedPosArr=loaded, readers=readers, keep_streams=keep_streams)
+    ext = [info["extensions"]]
+    if world > 1:
+        t = torch.zeros(world, dtype=torch.int64, device=device)
+        t[rank] = info["extensions"]
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        ext = [int(x) for x in t.cpu().tolist()]
+    if any(ext[:-1]):
+        raise SpeculationFailed(f"reference extensions per rank {ext}: shards behind the first extending rank are stale")
+    return streams, info, ext

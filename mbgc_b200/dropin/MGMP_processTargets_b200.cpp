@@ -212,6 +212,7 @@ void MultipleGenomeMatchingProcessor::processTargetsWithParallelIO() {
     int pushed = 0, openFile = -1, seqCounter = 0;
     size_t fileStartPos = matcher->getLoadedRefLength();
     uint64_t contigsTotal = 0;
+    double tWaitReaders = 0, tNext = 0, tHooks = 0;
     mbgcg_seq_event_t ev;
     auto pushReady = [&](bool block) {
         for (;;) {
@@ -222,7 +223,9 @@ void MultipleGenomeMatchingProcessor::processTargetsWithParallelIO() {
                 std::unique_lock<std::mutex> lk(mu);
                 if (!images[pushed].ready) {
                     if (!block) return;
+                    const double w0 = now_ms();
                     cv.wait(lk, [&] { return images[pushed].ready; });
+                    tWaitReaders += now_ms() - w0;
                 }
                 im = images[pushed];
             }
@@ -244,7 +247,10 @@ void MultipleGenomeMatchingProcessor::processTargetsWithParallelIO() {
     if (nFiles == 0 && mbgcg_seq_finish_input(h) != MBGCG_OK) die(mbgcg_last_error(h));
     for (;;) {
         pushReady(false);
+        const double n0 = now_ms();
         if (mbgcg_seq_next(h, &ev) != MBGCG_OK) die(mbgcg_last_error(h));
+        const double n1 = now_ms();
+        tNext += n1 - n0;
         if (ev.type == MBGCG_EV_DONE) break;
         if (ev.type == MBGCG_EV_NEED_INPUT) {
             pushReady(true);
@@ -296,6 +302,7 @@ void MultipleGenomeMatchingProcessor::processTargetsWithParallelIO() {
             else if (im.mallocd) free(const_cast<char*>(im.bytes));
             openFile = -1;
         }
+        tHooks += now_ms() - n1;
     }
     for (auto& t : readers) t.join();
     mbgcg_seq_stats_t st;
@@ -309,9 +316,10 @@ void MultipleGenomeMatchingProcessor::processTargetsWithParallelIO() {
         fprintf(stderr,
                 "[mbgc_b200] batched pass: %d files, %llu contigs, %d devices, %llu windows, %llu runs, %llu extensions, %llu contigs re-run; "
                 "%.1f MB images (%.1f MB pageable), %llu launches; ingest %.1f ms, match %.1f ms, pack %.1f ms, loadRef %.1f ms, "
-                "waiting for staging %.1f ms; whole loop %.1f ms\n",
+                "waiting for staging %.1f ms; main thread: waiting for readers %.1f ms, in seq_next %.1f ms, encoder hooks %.1f ms; "
+                "%d reader threads; whole loop %.1f ms\n",
                 nFiles, (unsigned long long) contigsTotal, mbgcg_device_count(h), (unsigned long long) st.windows,
                 (unsigned long long) st.runs, (unsigned long long) st.extensions, (unsigned long long) st.rerunContigs,
                 st.imageBytes / 1e6, st.pageableBytes / 1e6, (unsigned long long) st.launches, st.ingestMs, st.matchMs, st.packMs,
-                st.loadRefMs, st.waitStageMs, now_ms() - tStart);
+                st.loadRefMs, st.waitStageMs, tWaitReaders, tNext, tHooks, nReaders, now_ms() - tStart);
 }

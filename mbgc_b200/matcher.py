@@ -5,6 +5,7 @@ Reference interface mirrored: /root/reference/matching/SlidingWindowSparseEMMatc
 """
 import ctypes as C
 import os
+import time
 
 import numpy as np
 
@@ -80,6 +81,14 @@ class SeqStats(C.Structure):
                [(n, C.c_double) for n in ("ingestMs", "matchMs", "packMs", "loadRefMs", "waitStageMs")]
 
 
+class SeqResult(C.Structure):
+    _fields_ = [("stream", C.c_void_p * 6), ("streamLen", C.c_uint64 * 6), ("nFiles", C.c_uint64), ("nContigs", C.c_uint64),
+                ("seqCounts", C.c_void_p), ("dnaLineLens", C.c_void_p), ("refExtSizes", C.c_void_p), ("lockPos", C.c_void_p),
+                ("status", C.c_void_p), ("headers", C.c_void_p), ("headersLen", C.c_uint64), ("matches", C.c_uint64),
+                ("unmatched", C.c_uint64), ("extensions", C.c_uint64), ("digest", C.c_uint64)]
+
+
+NEXT_IMAGE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64))
 EV_CONTIG, EV_FILE_END, EV_NEED_INPUT, EV_DONE = 1, 2, 3, 4
 SEQ_SEPARATOR_MARK = (ord('"') + 128) & 0xFF   # mbgccoder/MBGC_Params.h:46
 FILE_SEPARATOR_MARK = (ord(';') + 128) & 0xFF  # mbgccoder/MBGC_Params.h:47
@@ -121,6 +130,8 @@ def load_library():
     L.mbgcg_seq_wants_input.argtypes = [vp]
     L.mbgcg_seq_next.restype = C.c_int
     L.mbgcg_seq_next.argtypes = [vp, C.POINTER(SeqEvent)]
+    L.mbgcg_seq_run.restype = C.c_int
+    L.mbgcg_seq_run.argtypes = [vp, NEXT_IMAGE_FN, vp, C.c_int, C.POINTER(SeqResult)]
     L.mbgcg_seq_end.restype = C.c_int
     L.mbgcg_seq_end.argtypes = [vp, C.POINTER(SeqStats)]
     L.mbgcg_image_alloc.restype = vp
@@ -182,6 +193,8 @@ def load_library():
     L.mbgcg_last_timing.argtypes = [vp, C.POINTER(C.c_float)]
     L.mbgcg_set_stage_timing.argtypes = [vp, C.c_int]
     L.mbgcg_last_counters.argtypes = [vp, u64p]
+    L.mbgcg_last_wire_bytes.argtypes = [vp, u64p]
+    L.mbgcg_load_ref_timing.argtypes = [vp, C.POINTER(C.c_float), u64p]
     L.mbgcg_stream.restype = vp
     L.mbgcg_stream.argtypes = [vp]
     _LIB = L
@@ -225,70 +238,239 @@ class Matcher:
     def setHostMirror(self, on):
         self.lib.mbgcg_set_host_mirror(self.h, int(bool(on)))
 
-    def compressSequential(self, images, cfg, loadedPosArr=None, pinned=True, on_event=None):
+    def compressSequential(self, images, cfg, loadedPosArr=None, pinned=True, on_event=None, keep_streams=True):
         """The reference's sequential (-t 1) target schedule over file images (bytes objects, in target order) through
         mbgcg_seq_*: MultipleGenomeMatchingProcessor::processTargetsWithParallelIO
         (/root/reference/matching/MultipleGenomeMatchingProcessor.cpp:232-313) with the encoder's hooks
         (mbgccoder/MBGC_Encoder.cpp:489-509) applied to the committed events.  Returns ({stream: bytes}, info) where the
         streams are what the encoder holds after the last target (the literal stream without the G0 bootstrap of
         MBGC_Encoder.cpp:34-37) and info has per-file meta data, headers, lock positions and the pass statistics."""
+        keep = []
+
+        def provider(i):
+            a = _as_u8(images[i])
+            p = self.lib.mbgcg_image_alloc(self.h, a.size) if (pinned and a.size) else None
+            if p:
+                C.memmove(p, a.ctypes.data, a.size)
+                return p, a.size
+            keep.append(a)
+            return (a.ctypes.data if a.size else None), a.size
+
+        return self._run_pass(len(images), provider, None, cfg, loadedPosArr, on_event, keep_streams)
+
+    def compressFiles(self, paths, cfg, loadedPosArr=None, readers=None, on_event=None, keep_streams=True):
+        """compressSequential for files on disk: `readers` threads read them (ahead of the pass, in order of need) straight
+        into pinned memory of the handle's arena, pageable memory when that is full.  gzip is not handled here (the
+        reference's own reader does that in the drop-in)."""
+        import threading
+        n = len(paths)
+        readers = max(1, min(readers or (os.cpu_count() or 1), 32, max(n, 1)))
+        ready = [None] * n
+        cond = threading.Condition()
+        state = {"next": 0, "turn": 0, "consumed": 0, "stop": False}
+        arena_max = self.lib.mbgcg_image_max(self.h)
+        keep = {}
+
+        def work():
+            while True:
+                with cond:
+                    i = state["next"]
+                    if i >= n or state["stop"]:
+                        return
+                    state["next"] = i + 1
+                    cond.wait_for(lambda: i < state["consumed"] + 64 or state["stop"])
+                    cond.wait_for(lambda: state["turn"] == i or state["stop"])   # pinned memory goes out in file order
+                    if state["stop"]:
+                        return
+                size = os.path.getsize(paths[i])
+                p = None
+                if 0 < size <= arena_max:
+                    for _ in range(20000):
+                        p = self.lib.mbgcg_image_alloc(self.h, size)
+                        if p or state["stop"]:
+                            break
+                        time.sleep(50e-6)
+                with cond:
+                    state["turn"] = i + 1
+                    cond.notify_all()
+                if p:
+                    buf = (C.c_char * size).from_address(p)
+                else:
+                    arr = np.empty(size, dtype=np.uint8)
+                    keep[i] = arr
+                    buf = memoryview(arr)
+                    p = arr.ctypes.data if size else None
+                with open(paths[i], "rb", buffering=0) as f:
+                    got = 0
+                    mv = memoryview(buf).cast("B")
+                    while got < size:
+                        k = f.readinto(mv[got:])
+                        if not k:
+                            raise IOError(f"short read on {paths[i]}")
+                        got += k
+                with cond:
+                    ready[i] = (p, size)
+                    cond.notify_all()
+
+        threads = [threading.Thread(target=work, daemon=True) for _ in range(readers)]
+        for t in threads:
+            t.start()
+
+        def provider(i, block):
+            with cond:
+                if ready[i] is None:
+                    if not block:
+                        return None
+                    cond.wait_for(lambda: ready[i] is not None)
+                return ready[i]
+
+        def consumed(i, drop=True):
+            with cond:
+                state["consumed"] = max(state["consumed"], i + 1)
+                if drop:   # only once the file's FILE_END has been seen: a pageable image must stay valid until then
+                    keep.pop(i, None)
+                cond.notify_all()
+
+        try:
+            return self._run_pass(n, None, (provider, consumed), cfg, loadedPosArr, on_event, keep_streams)
+        finally:
+            with cond:
+                state["stop"] = True
+                cond.notify_all()
+            for t in threads:
+                t.join()
+
+    def _run_pass(self, n, provider, async_provider, cfg, loadedPosArr, on_event, keep_streams):
         loaded = list(loadedPosArr) if loadedPosArr is not None else [self.getLoadingPosition()]
         arr = (C.c_uint64 * len(loaded))(*loaded)
         self._check(self.lib.mbgcg_seq_begin(self.h, C.byref(cfg), arr, len(loaded)))
-        out = {n: [] for n in STREAM_NAMES}
+        if on_event is None:
+            return self._run_pass_to_end(n, provider, async_provider, keep_streams)
+        return self._run_pass_events(n, provider, async_provider, cfg, on_event, keep_streams)
+
+    def _run_pass_to_end(self, n, provider, async_provider, keep_streams):
+        """mbgcg_seq_run: the whole pass inside the library, images pulled through a callback"""
+        state = {"next": 0, "err": None}
+
+        def next_image(user, block, bytes_out, n_out):
+            try:
+                i = state["next"]
+                if i >= n:
+                    return -1
+                if provider is not None:
+                    p, size = provider(i)
+                else:
+                    got = async_provider[0](i, bool(block))
+                    if got is None:
+                        return 0
+                    p, size = got
+                    async_provider[1](i - 1, False)   # read-ahead window follows the pushes; pageable images stay until the end
+                bytes_out[0] = p
+                n_out[0] = size
+                state["next"] = i + 1
+                return 1
+            except BaseException as e:  # noqa: BLE001 -- must not propagate through the C frame
+                state["err"] = e
+                return -1
+
+        cb = NEXT_IMAGE_FN(next_image)
+        res = SeqResult()
+        st = SeqStats()
+        try:
+            rc = self.lib.mbgcg_seq_run(self.h, cb, None, int(bool(keep_streams)), C.byref(res))
+            if state["err"] is not None:
+                raise state["err"]
+            self._check(rc)
+            nf = int(res.nFiles)
+
+            def arr64(p):
+                return np.ctypeslib.as_array(C.cast(p, u64p), shape=(nf,)).astype(np.int64).tolist() if nf else []
+            out = {name: (C.string_at(res.stream[s], res.streamLen[s]) if res.streamLen[s] else b"")
+                   for s, name in enumerate(STREAM_NAMES)}
+            hdrs = C.string_at(res.headers, res.headersLen).split(b"\n")[:-1] if res.headersLen else []
+            counts = arr64(res.seqCounts)
+            files_of = [f for f, c in enumerate(counts) for _ in range(c)]
+            info = dict(headers=list(zip(files_of, hdrs)), seqCounts=counts, dnaLineLens=arr64(res.dnaLineLens),
+                        refExtSizes=arr64(res.refExtSizes), lockPos=[int(x) & (2**64 - 1) for x in arr64(res.lockPos)],
+                        unmatched=int(res.unmatched), matches=int(res.matches), extensions=int(res.extensions),
+                        status=(np.ctypeslib.as_array(C.cast(res.status, C.POINTER(C.c_int32)), shape=(nf,)).tolist() if nf else []),
+                        contigs=int(res.nContigs), digest=int(res.digest),
+                        stream_bytes={name: int(res.streamLen[s]) for s, name in enumerate(STREAM_NAMES)})
+        finally:
+            self.lib.mbgcg_seq_end(self.h, C.byref(st))
+        info["stats"] = {name: getattr(st, name) for name, _ in SeqStats._fields_}
+        return out, info
+
+    def _run_pass_events(self, n, provider, async_provider, cfg, on_event, keep_streams):
+        out = {name: [] for name in STREAM_NAMES}
+        sizes = {name: 0 for name in STREAM_NAMES}
         info = dict(headers=[], seqCounts=[], dnaLineLens=[], refExtSizes=[], lockPos=[], unmatched=0, matches=0,
-                    extensions=0, status=[])
-        keep = []
+                    extensions=0, status=[], contigs=0)
         nxt = 0
+        finished = False
         ev = SeqEvent()
         try:
             while True:
-                while nxt < len(images) and self.lib.mbgcg_seq_wants_input(self.h):
-                    a = _as_u8(images[nxt])
-                    p = self.lib.mbgcg_image_alloc(self.h, a.size) if (pinned and a.size) else None
-                    if p:
-                        C.memmove(p, a.ctypes.data, a.size)
-                        self._check(self.lib.mbgcg_seq_push_file(self.h, p, a.size))
+                while nxt < n and self.lib.mbgcg_seq_wants_input(self.h):
+                    if provider is not None:
+                        p, size = provider(nxt)
                     else:
-                        keep.append(a)
-                        self._check(self.lib.mbgcg_seq_push_file(self.h, a.ctypes.data if a.size else None, a.size))
+                        got = async_provider[0](nxt, False)
+                        if got is None:
+                            break
+                        p, size = got
+                    self._check(self.lib.mbgcg_seq_push_file(self.h, p, size))
                     nxt += 1
-                    if nxt == len(images):
-                        self._check(self.lib.mbgcg_seq_finish_input(self.h))
-                if not images and nxt == 0:
+                if nxt == n and not finished:
                     self._check(self.lib.mbgcg_seq_finish_input(self.h))
-                    nxt = -1
+                    finished = True
                 self._check(self.lib.mbgcg_seq_next(self.h, C.byref(ev)))
                 if on_event is not None:
                     on_event(ev)
                 if ev.type == EV_DONE:
                     break
                 if ev.type == EV_NEED_INPUT:
-                    if nxt >= len(images) or nxt < 0:
+                    if finished:
                         raise MatcherError(-2, "the pass asks for input after finish_input")
+                    if provider is not None:
+                        p, size = provider(nxt)
+                    else:
+                        p, size = async_provider[0](nxt, True)
+                    self._check(self.lib.mbgcg_seq_push_file(self.h, p, size))
+                    nxt += 1
                     continue
                 if ev.type == EV_CONTIG:
                     for s, name in enumerate(STREAM_NAMES):
                         if ev.segLen[s]:
-                            out[name].append(C.string_at(ev.seg[s], ev.segLen[s]))
-                    out["literals"].append(bytes([SEQ_SEPARATOR_MARK]))          # processAfterSequence
-                    info["headers"].append((int(ev.file), C.string_at(ev.hdr, ev.hdrLen) if ev.hdrLen else b""))
+                            sizes[name] += int(ev.segLen[s])
+                            if keep_streams:
+                                out[name].append(C.string_at(ev.seg[s], ev.segLen[s]))
+                    sizes["literals"] += 1
+                    if keep_streams:
+                        out["literals"].append(bytes([SEQ_SEPARATOR_MARK]))          # processAfterSequence
+                        info["headers"].append((int(ev.file), C.string_at(ev.hdr, ev.hdrLen) if ev.hdrLen else b""))
                     info["unmatched"] += int(ev.unmatched)
                     info["matches"] += int(ev.nMatches)
                     info["extensions"] += int(ev.extended)
+                    info["contigs"] += 1
                 elif ev.type == EV_FILE_END:
                     if cfg.pack.enableExtensionsWithMismatches:                   # processAfterTarget
-                        out["gapFlags"].append(bytes([FILE_SEPARATOR_MARK]))
+                        sizes["gapFlags"] += 1
+                        if keep_streams:
+                            out["gapFlags"].append(bytes([FILE_SEPARATOR_MARK]))
                     info["seqCounts"].append(int(ev.nContigs))
                     info["dnaLineLens"].append(int(ev.dnaLineLen))
                     info["refExtSizes"].append(int(ev.refExtSize))
                     info["lockPos"].append(int(ev.lockPos))
                     info["status"].append(int(ev.status))
+                    if async_provider is not None:
+                        async_provider[1](int(ev.file))
         finally:
             st = SeqStats()
             self.lib.mbgcg_seq_end(self.h, C.byref(st))
-        info["stats"] = {n: getattr(st, n) for n, _ in SeqStats._fields_}
-        return {n: b"".join(v) for n, v in out.items()}, info
+        info["stats"] = {name: getattr(st, name) for name, _ in SeqStats._fields_}
+        info["stream_bytes"] = sizes
+        return {name: b"".join(v) for name, v in out.items()}, info
 
     def close(self):
         if getattr(self, "h", None):
@@ -507,6 +689,19 @@ class Matcher:
         self.lib.mbgcg_last_counters(self.h, c)
         return {"positions": c[0], "seeds": c[1], "runs": c[2], "matches": c[3], "launches": c[4],
                 "passes": c[5], "chunks": c[6], "lanes_full_probe": c[7]}
+
+    def wireBytes(self):
+        """bytes the last match call moved over PCIe: (host -> device, device -> host)"""
+        w = (C.c_uint64 * 2)()
+        self.lib.mbgcg_last_wire_bytes(self.h, w)
+        return int(w[0]), int(w[1])
+
+    def loadRefTiming(self):
+        """last loadRef: device ms (CUDA events), host wall ms, reference bytes appended"""
+        ms = (C.c_float * 2)()
+        n = C.c_uint64()
+        self.lib.mbgcg_load_ref_timing(self.h, ms, C.byref(n))
+        return {"device_ms": ms[0], "wall_ms": ms[1], "appended": int(n.value)}
 
     def stream(self):
         """cudaStream_t (as int) all work of this matcher is issued on"""
