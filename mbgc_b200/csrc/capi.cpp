@@ -449,6 +449,7 @@ int mbgcg_seq_run(mbgcg_t* h, mbgcg_next_image_fn next_image, void* user, int ke
         };
         const char SEQ_MARK = static_cast<char>(0xA2), FILE_MARK = static_cast<char>(0xBB);  // MBGC_Params.h:46-47
         uint64_t contigs = 0, matches = 0, unmatched = 0, extensions = 0, digest = 0;
+        uint64_t sizes[MBGCG_S_COUNT] = {0, 0, 0, 0, 0, 0};
         mbgc_b200::SeqEvent e;
         for (;;) {
             while (!finished && h->pass->wantsInput() && feed(false)) {}
@@ -464,9 +465,11 @@ int mbgcg_seq_run(mbgcg_t* h, mbgcg_next_image_fn next_image, void* user, int ke
                 for (int s = 0; s < MBGCG_S_COUNT; s++) {
                     for (uint64_t k = 0; k < e.segLen[s]; k++) hsh = (hsh ^ e.seg[s][k]) * 1099511628211ull;
                     hsh = (hsh ^ 0xFF) * 1099511628211ull;
+                    sizes[s] += e.segLen[s];
                     if (keepStreams && e.segLen[s]) R.stream[s].append(reinterpret_cast<const char*>(e.seg[s]), e.segLen[s]);
                 }
                 digest += hsh;
+                sizes[MBGCG_S_LITERALS]++;
                 if (keepStreams) {
                     R.stream[MBGCG_S_LITERALS].push_back(SEQ_MARK);
                     R.headers.append(e.hdr, e.hdrLen);
@@ -477,7 +480,10 @@ int mbgcg_seq_run(mbgcg_t* h, mbgcg_next_image_fn next_image, void* user, int ke
                 unmatched += e.unmatched;
                 extensions += e.extended ? 1 : 0;
             } else {
-                if (keepStreams && h->pass->config().pack.enableExt) R.stream[MBGCG_S_GAPFLAGS].push_back(FILE_MARK);
+                if (h->pass->config().pack.enableExt) {
+                    sizes[MBGCG_S_GAPFLAGS]++;
+                    if (keepStreams) R.stream[MBGCG_S_GAPFLAGS].push_back(FILE_MARK);
+                }
                 R.seqCounts.push_back(e.nContigs);
                 R.dnaLineLens.push_back(e.dnaLineLen);
                 R.refExtSizes.push_back(e.refExtSize);
@@ -487,7 +493,7 @@ int mbgcg_seq_run(mbgcg_t* h, mbgcg_next_image_fn next_image, void* user, int ke
         }
         for (int s = 0; s < MBGCG_S_COUNT; s++) {
             out->stream[s] = reinterpret_cast<const uint8_t*>(R.stream[s].data());
-            out->streamLen[s] = R.stream[s].size();
+            out->streamLen[s] = sizes[s];   // (the bytes themselves only with keepStreams)
         }
         out->nFiles = R.seqCounts.size();
         out->nContigs = contigs;

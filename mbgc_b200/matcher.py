@@ -385,7 +385,7 @@ class Matcher:
 
             def arr64(p):
                 return np.ctypeslib.as_array(C.cast(p, u64p), shape=(nf,)).astype(np.int64).tolist() if nf else []
-            out = {name: (C.string_at(res.stream[s], res.streamLen[s]) if res.streamLen[s] else b"")
+            out = {name: (C.string_at(res.stream[s], res.streamLen[s]) if (keep_streams and res.streamLen[s]) else b"")
                    for s, name in enumerate(STREAM_NAMES)}
             hdrs = C.string_at(res.headers, res.headersLen).split(b"\n")[:-1] if res.headersLen else []
             counts = arr64(res.seqCounts)

@@ -62,6 +62,46 @@ def md5(p):
     return hashlib.md5(open(p, "rb").read()).hexdigest()
 
 
+def measure(d, total, mode, gpus, stock_runs=3, skip_t1=False):
+    """d: directory with the FASTA files and list.txt.  Returns the report dictionary."""
+    out = {"fasta_bytes": total, "mode": mode, "host_cores": os.cpu_count()}
+    m = ["c", "-m", str(mode), "-f"]
+    arch = lambda tag: os.path.join(d, f"{tag}.mbgc")
+    out["stock_default_threads"] = [run("mbgc", m + ["list.txt", arch("stock")], d) for _ in range(stock_runs)]
+    if not skip_t1:
+        out["stock_t1"] = run("mbgc", m + ["-t", "1", "list.txt", arch("stock_t1")], d)
+        out["stock_t1"]["md5"] = md5(arch("stock_t1"))
+    for g in gpus:
+        env = {"MBGC_B200_DEVICES": ",".join(str(i) for i in range(g)), "MBGC_B200_TRACE": "1"}
+        key = f"batched_{g}gpu"
+        out[key] = {}
+        if not skip_t1:
+            r = run("mbgc_b200_batched", m + ["-t", "1", "list.txt", arch(key + "_t1")], d, env)
+            r["md5"] = md5(arch(key + "_t1"))
+            r["byte_identical_to_stock_t1"] = r["md5"] == out["stock_t1"]["md5"]
+            out[key]["t1"] = r
+        runs = [run("mbgc_b200_batched", m + ["-Q", "list.txt", arch(key + "_Q")], d, env) for _ in range(3)]
+        out[key]["Q_default_threads"] = runs
+        if not skip_t1:  # same archive but for the thread-count bytes of the header (1-based bytes 10, 11)
+            x, y = open(arch(key + "_Q"), "rb").read(), open(arch(key + "_t1"), "rb").read()
+            diff = [i for i in range(min(len(x), len(y))) if x[i] != y[i]] if len(x) == len(y) else None
+            out[key]["Q_vs_t1_differing_bytes"] = diff if diff is None or len(diff) < 8 else len(diff)
+    best = min(out["stock_default_threads"], key=lambda r: r["wall_s"])
+    out["summary"] = {"cpu_cli": {"what": "stock `mbgc c` with default threads, best of the runs", "wall_s": best["wall_s"],
+                                  "GB_per_s": round(total / best["wall_s"] / 1e9, 3),
+                                  "match_phase_ms": (best["matching_finished_ms"] or 0) - (best["loaded_reference_ms"] or 0),
+                                  "encoding_time_ms": best["encoding_time_ms"], "cores": os.cpu_count()}}
+    for g in gpus:
+        b = min(out[f"batched_{g}gpu"]["Q_default_threads"], key=lambda r: r["wall_s"])
+        ctx = b.get("cuda_context_ms") or 0.0
+        out["summary"][f"batched_{g}gpu"] = {
+            "wall_s": b["wall_s"], "GB_per_s": round(total / b["wall_s"] / 1e9, 3),
+            "match_phase_ms": (b["matching_finished_ms"] or 0) - (b["loaded_reference_ms"] or 0),
+            "encoding_time_ms": b["encoding_time_ms"], "cuda_context_ms": ctx,
+            "encoding_time_without_context_ms": (b["encoding_time_ms"] or 0) - ctx}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", default="c2near", choices=list(CONFIGS))
@@ -77,35 +117,8 @@ def main():
     d = os.path.join(a.dir, f"{a.config}_{n}")
     t0 = time.perf_counter()
     names, total = write_collection(d, n, length, seed, p_snp, p_indel)
-    out = {"config": a.config, "genomes": n, "fasta_bytes": total, "mode": mode, "host_cores": os.cpu_count(),
-           "generate_s": round(time.perf_counter() - t0, 1)}
-    m = ["c", "-m", str(mode), "-f"]
-    arch = lambda tag: os.path.join(d, f"{tag}.mbgc")
-    out["stock_default_threads"] = [run("mbgc", m + ["list.txt", arch("stock")], d) for _ in range(a.stock_runs)]
-    if not a.skip_t1:
-        out["stock_t1"] = run("mbgc", m + ["-t", "1", "list.txt", arch("stock_t1")], d)
-        out["stock_t1"]["md5"] = md5(arch("stock_t1"))
-    for g in [int(x) for x in a.gpus.split(",")]:
-        env = {"MBGC_B200_DEVICES": ",".join(str(i) for i in range(g)), "MBGC_B200_TRACE": "1"}
-        key = f"batched_{g}gpu"
-        out[key] = {}
-        if not a.skip_t1:
-            r = run("mbgc_b200_batched", m + ["-t", "1", "list.txt", arch(key + "_t1")], d, env)
-            r["md5"] = md5(arch(key + "_t1"))
-            r["byte_identical_to_stock_t1"] = r["md5"] == out["stock_t1"]["md5"]
-            out[key]["t1"] = r
-        runs = [run("mbgc_b200_batched", m + ["-Q", "list.txt", arch(key + "_Q")], d, env) for _ in range(2)]
-        out[key]["Q_default_threads"] = runs
-        if not a.skip_t1:  # same archive but for the thread-count bytes of the header (1-based bytes 10, 11)
-            x, y = open(arch(key + "_Q"), "rb").read(), open(arch(key + "_t1"), "rb").read()
-            diff = [i for i in range(min(len(x), len(y))) if x[i] != y[i]] if len(x) == len(y) else None
-            out[key]["Q_vs_t1_differing_bytes"] = diff if diff is None or len(diff) < 8 else len(diff)
-    best_stock = min(r["wall_s"] for r in out["stock_default_threads"])
-    out["summary"] = {"stock_default_best_wall_s": best_stock, "stock_GB_per_s": round(total / best_stock / 1e9, 3)}
-    for g in [int(x) for x in a.gpus.split(",")]:
-        w = min(r["wall_s"] for r in out[f"batched_{g}gpu"]["Q_default_threads"])
-        out["summary"][f"batched_{g}gpu_best_wall_s"] = w
-        out["summary"][f"batched_{g}gpu_GB_per_s"] = round(total / w / 1e9, 3)
+    out = {"config": a.config, "genomes": n, "generate_s": round(time.perf_counter() - t0, 1)}
+    out.update(measure(d, total, mode, [int(x) for x in a.gpus.split(",")], a.stock_runs, a.skip_t1))
     print(json.dumps(out, indent=1))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", f"whole_pipeline_{a.config}_{n}.json"), "w") as f:
