@@ -308,16 +308,93 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_final(const uint32_t* in,
     }
 }
 
+// Single-pass exclusive scan (decoupled look-back): one launch instead of three.  Every 4096-element tile publishes its
+// aggregate, then its inclusive prefix, in one 64-bit word of `state` ((flag << 32) | value; flag 1 = aggregate, 2 =
+// inclusive prefix, 0 = nothing yet -- `state` is zeroed together with the pass counters; its last word is the tile
+// ticket).  Tiles are handed out by ticket, so every predecessor of a tile belongs to a CTA that is already running: no
+// CTA can wait for one that has not been scheduled.  The first warp of a tile looks back 32 predecessors at a time
+// until it meets an inclusive prefix.  out may alias in.  out[n] receives the grand total.
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_lookback(const uint32_t* in, uint32_t* out, const uint32_t* nPtr,
+                                                                uint32_t nConst, uint32_t nMax,
+                                                                unsigned long long* state, uint32_t stateWords,
+                                                                uint32_t* totalOut) {
+    __shared__ uint32_t sWarp[33];
+    __shared__ uint32_t sPrefix, sTile;
+    const uint32_t n = scan_len(nPtr, nConst, nMax);
+    const uint32_t nBlocks = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    if (nBlocks == 0) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            out[0] = 0;
+            if (totalOut) *totalOut = 0;
+        }
+        return;
+    }
+    volatile unsigned long long* vs = state;
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(state + stateWords - 1);
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        if (threadIdx.x == 0) sTile = atomicAdd(ticket, 1u);
+        __syncthreads();
+        const uint32_t b = sTile;
+        if (b >= nBlocks) break;
+        uint32_t v[SCAN_ITEMS];
+        uint32_t s = 0;
+        const uint32_t i0 = b * SCAN_BLOCK + threadIdx.x * SCAN_ITEMS;
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k++) {
+            v[k] = (i0 + k < n) ? in[i0 + k] : 0;
+            s += v[k];
+        }
+        uint32_t total;
+        uint32_t ex = block_excl_scan(s, &total, sWarp);
+        if (threadIdx.x < 32) {
+            uint32_t prefix = 0;
+            if (b == 0) {
+                if (lane == 0) vs[0] = (2ull << 32) | total;
+            } else {
+                if (lane == 0) vs[b] = (1ull << 32) | total;
+                for (int64_t base = static_cast<int64_t>(b) - 1;; base -= 32) {
+                    const int64_t j = base - lane;
+                    unsigned long long w = 2ull << 32;  // in front of tile 0: an inclusive prefix of 0
+                    if (j >= 0) {
+                        do {
+                            w = vs[j];
+                        } while ((w >> 32) == 0);
+                    }
+                    const uint32_t incl = __ballot_sync(0xFFFFFFFFu, (w >> 32) == 2);
+                    const int first = incl ? __ffs(incl) - 1 : 31;  // nearest predecessor that knows its inclusive prefix
+                    prefix += __reduce_add_sync(0xFFFFFFFFu, lane <= first ? static_cast<uint32_t>(w) : 0u);
+                    if (incl) break;
+                }
+                if (lane == 0) vs[b] = (2ull << 32) | static_cast<uint32_t>(prefix + total);
+            }
+            if (lane == 0) {
+                sPrefix = prefix;
+                if (b == nBlocks - 1) {
+                    out[n] = prefix + total;
+                    if (totalOut) *totalOut = prefix + total;
+                }
+            }
+        }
+        __syncthreads();
+        ex += sPrefix;
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k++) {
+            if (i0 + k < n) out[i0 + k] = ex;
+            ex += v[k];
+        }
+        __syncthreads();  // sTile / sPrefix are rewritten in the next round
+    }
+}
+
 static int scan_exclusive(const uint32_t* in, uint32_t* out, const uint32_t* nPtr, uint32_t nConst, uint32_t nMax,
-                          uint32_t* blockSums, uint32_t* totalOut, cudaStream_t st) {
+                          unsigned long long* state, uint32_t stateWords, uint32_t* totalOut, cudaStream_t st) {
     uint32_t blocks = (nMax + SCAN_BLOCK - 1) / SCAN_BLOCK;
     const uint32_t cap = static_cast<uint32_t>(device_sm_count()) * 2;
     if (blocks > cap) blocks = cap;
     if (blocks == 0) blocks = 1;
-    k_scan_reduce<<<blocks, SCAN_THREADS, 0, st>>>(in, nPtr, nConst, nMax, blockSums);
-    k_scan_partials<<<1, SCAN_THREADS, 0, st>>>(blockSums, nPtr, nConst, nMax);
-    k_scan_final<<<blocks, SCAN_THREADS, 0, st>>>(in, out, nPtr, nConst, nMax, blockSums, totalOut);
-    return 3;
+    k_scan_lookback<<<blocks, SCAN_THREADS, 0, st>>>(in, out, nPtr, nConst, nMax, state, stateWords, totalOut);
+    return 1;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -1115,7 +1192,7 @@ int launch_compact_and_runs(const IndexState& ix, const BatchDesc& b, const Work
     int launches = 0;
     const int sm = device_sm_count();
     // tileCount -> tileOff (in place), tileOff[nTiles] = nSeeds
-    launches += scan_exclusive(w.tileCount, w.tileCount, nullptr, b.nTiles, b.nTiles, w.blockSums, nullptr, st);
+    launches += scan_exclusive(w.tileCount, w.tileCount, nullptr, b.nTiles, b.nTiles, w.scanState, w.scanStride, nullptr, st);
     k_compact<<<sm * 8, 256, 0, st>>>(b, w.chunkContig, w.tileCount, w.seedMask, w.scratchEnc,
                                       segments ? w.workList : nullptr, segments ? w.counters + 6 : nullptr,
                                       w.dirtyMask, w.chunkSegN, w.chunkSeg, w.seeds, w.seedCap, w.counters);
@@ -1127,7 +1204,7 @@ int launch_compact_and_runs(const IndexState& ix, const BatchDesc& b, const Work
     k_heads<<<sm * 8, 256, 0, st>>>(ix, b, w.tileCount, w.seeds, w.headScan, w.counters);
     launches += 2;
     // head flags -> exclusive scan in place; length lives on the device (tileOff[nTiles])
-    launches += scan_exclusive(w.headScan, w.headScan, w.tileCount + b.nTiles, 0, w.seedCap, w.blockSums, nullptr, st);
+    launches += scan_exclusive(w.headScan, w.headScan, w.tileCount + b.nTiles, 0, w.seedCap, w.scanState + w.scanStride, w.scanStride, nullptr, st);
     k_runs<<<sm * 8, 256, 0, st>>>(b, w.tileCount, w.headScan, w.runFirst, w.runStart, w.counters);
     launches += 1;
     return launches;
@@ -1830,7 +1907,7 @@ int launch_resolve(const IndexState& ix, const BatchDesc& b, const WorkBuffers& 
     k_resolve<<<sm * 16, 128, 0, st>>>(a);
     k_resolve_big<<<sm * 4, 128, 0, st>>>(a);
     launches += 2;
-    launches += scan_exclusive(w.runFirst, w.runFirst, w.counters + 1, 0, w.seedCap, w.blockSums, nullptr, st);
+    launches += scan_exclusive(w.runFirst, w.runFirst, w.counters + 1, 0, w.seedCap, w.scanState + 2 * w.scanStride, w.scanStride, nullptr, st);
     k_gather<<<sm * 8, 256, 0, st>>>(w.matches, w.headScan, w.runFirst, w.runStart, w.matchesDense, w.matchOff,
                                      b.nContigs, w.counters);
     launches += 1;

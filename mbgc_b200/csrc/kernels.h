@@ -99,6 +99,9 @@ struct WorkBuffers {     // device scratch of one pass
     uint32_t* matchOff;      // [nContigs+1]
     TextMatchRec* matchesDense;  // [seedCap] the pass's matches in text order, host layout
     uint32_t* blockSums;     // scan temporaries
+    unsigned long long* scanState;  // look-back state of the three scans of a pass (scanStride words each), zeroed with the counters
+    uint32_t scanStride;
+    uint32_t zeroBytes;      // counters + scanState: one memset at the start of a pass
     uint32_t* counters;      // [16]: 0 nSegments, 1 nRuns, 2 nMatches, 3 overflow flag, 4 longest island, 5 islands, 6 chunks with dirty lanes, 7 dirty lanes (one 64-bit word), 8 long islands
     uint32_t seedCap;
 };

@@ -425,7 +425,9 @@ void B200SparseEMMatcher::ensureWork(uint64_t textBytes, uint32_t nTiles, int nC
     const uint64_t oDense = carve(static_cast<uint64_t>(seedCap) * sizeof(TextMatchRec));
     const uint64_t nScan = std::max<uint64_t>(nTiles, seedCap);
     const uint64_t oBlockSums = carve((nScan / 4096 + 8) * 4);
-    const uint64_t oCounters = carve(64);
+    const uint64_t oCounters = carve(256);
+    const uint64_t scanStride = nScan / 4096 + 8;
+    const uint64_t oScanState = carve(3 * scanStride * 8);
     if (off > dWorkCap) {
         cudaFree(dWork);
         dWork = nullptr;
@@ -458,6 +460,9 @@ void B200SparseEMMatcher::ensureWork(uint64_t textBytes, uint32_t nTiles, int nC
     wb.matchesDense = reinterpret_cast<TextMatchRec*>(dWork + oDense);
     wb.blockSums = reinterpret_cast<uint32_t*>(dWork + oBlockSums);
     wb.counters = reinterpret_cast<uint32_t*>(dWork + oCounters);
+    wb.scanState = reinterpret_cast<unsigned long long*>(dWork + oScanState);
+    wb.scanStride = static_cast<uint32_t>(scanStride);
+    wb.zeroBytes = static_cast<uint32_t>(oScanState + 3 * scanStride * 8 - oCounters);
     wb.seedCap = seedCap;
 }
 
@@ -837,7 +842,7 @@ void B200SparseEMMatcher::matchBatch(const std::vector<TextView>& texts, const u
                 for (int c = 0; c < nC; c++) lastLens[c] = texts[first + c].len;
                 textBase = dText;
             }
-            check(cudaMemsetAsync(wb.counters, 0, 64, stream), "memset(counters)");
+            check(cudaMemsetAsync(wb.counters, 0, wb.zeroBytes, stream), "memset(counters + scan state)");
             mark(1);
 
             BatchDesc bd;
