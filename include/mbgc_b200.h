@@ -237,6 +237,21 @@ typedef struct {
     char regionSeparator;               /* MGMP_Params::REF_REGION_SEPARATOR */
     uint64_t chunkBytes;                /* file-image bytes per ingest slot; 0 = default (64 MiB) */
     uint32_t maxWindowContigs;          /* speculation window; 0 = default */
+    /* 1: the batch-frozen schedule of the reference's PARALLEL mode instead of the sequential one
+     * (processTargetsParallel / processTarget / finalizeParallelProcessingOfTarget,
+     * MultipleGenomeMatchingProcessor.cpp:340-468, 520-555): every target (file) of a window is matched under its own
+     * sliding-window lock against the matcher state at the window's start; its qualifying contigs -- each followed by its
+     * reverse complement when contigsIndividuallyReversed (:389-398) -- extend the reference as ONE text when the target is
+     * finalized, in target order (:441).  No result is ever redone except for the dissimilar-contig rule
+     * (MBGC_Encoder.cpp:202-205).  Any such schedule yields a legal archive; this one is deterministic.
+     * Events: CONTIG carries contigLock; FILE_END carries the lock in lockPos and refExtSize measured across the
+     * extension and the separator. */
+    int32_t parallelSchedule;
+    int32_t contigsIndividuallyReversed;                       /* MGMP_Params.h:75 */
+    int32_t allowedTargetsOutrun;                              /* targets per window: matcherWorkingThreads * allowedTargetsOutrunFactor */
+    int32_t allowedTargetsOutrunForDissimilarContigs;          /* MGMP_Params.h:78 */
+    int32_t unmatchedFractionFactorTweakForDissimilarContigs;  /* MGMP_Params.h:80 */
+    uint64_t minimalLengthForDissimilarContigs;                /* MGMP_Params.h:79 */
 } mbgcg_seq_config_t;
 
 enum { MBGCG_EV_CONTIG = 1, MBGCG_EV_FILE_END = 2, MBGCG_EV_NEED_INPUT = 3, MBGCG_EV_DONE = 4 };
@@ -253,8 +268,10 @@ typedef struct {
     uint64_t nMatches;       /* resMatches.size() */
     uint64_t kept;           /* matches left after pass 1 of processMatches */
     uint64_t unmatched;      /* processMatches' return value */
-    int32_t extended;        /* the contig was loaded into the reference ... */
+    int32_t extended;        /* the contig was loaded into the reference (parallel schedule: will be, with its target) ... */
     int32_t extendedRC;      /* ... and its reverse complement */
+    uint64_t contigLock;     /* parallel schedule: the matchingLockPos the contig was matched and packed under */
+    uint64_t window;         /* running number of the window (group of files ingested together) the file belongs to */
     const uint8_t* seg[MBGCG_S_COUNT];   /* what processMatches appends to the six streams; valid until the next call */
     uint64_t segLen[MBGCG_S_COUNT];
     /* FILE_END */

@@ -370,6 +370,15 @@ int mbgcg_seq_begin(mbgcg_t* h, const mbgcg_seq_config_t* c, const uint64_t* loa
         sc.separatorPerFile = c->separatorPerFile != 0;
         if (c->chunkBytes) sc.chunkBytes = c->chunkBytes;
         if (c->maxWindowContigs) sc.maxWindowContigs = c->maxWindowContigs;
+        sc.parallelSchedule = c->parallelSchedule != 0;
+        if (sc.parallelSchedule) {
+            sc.contigsIndividuallyReversed = c->contigsIndividuallyReversed != 0;
+            if (c->allowedTargetsOutrun > 0) sc.allowedTargetsOutrun = c->allowedTargetsOutrun;
+            sc.allowedTargetsOutrunForDissimilarContigs = c->allowedTargetsOutrunForDissimilarContigs;
+            if (c->unmatchedFractionFactorTweakForDissimilarContigs > 0)
+                sc.unmatchedFractionFactorTweakForDissimilarContigs = c->unmatchedFractionFactorTweakForDissimilarContigs;
+            sc.minimalLengthForDissimilarContigs = c->minimalLengthForDissimilarContigs;
+        }
         if (nLoadedPos && !loadedPosArr) throw MatcherError(MBGCG_E_PARAM, "seq_begin: loaded positions missing");
         h->pass = new SequentialPass(*h->rs, sc, loadedPosArr, nLoadedPos);
     });
@@ -410,6 +419,8 @@ int mbgcg_seq_next(mbgcg_t* h, mbgcg_seq_event_t* ev) {
         ev->unmatched = e.unmatched;
         ev->extended = e.extended;
         ev->extendedRC = e.extendedRC;
+        ev->contigLock = e.contigLock;
+        ev->window = e.window;
         for (int s = 0; s < MBGCG_S_COUNT; s++) {
             ev->seg[s] = e.seg[s];
             ev->segLen[s] = e.segLen[s];

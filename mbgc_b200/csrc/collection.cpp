@@ -488,6 +488,25 @@ void ReplicaSet::loadRefFromReplica(int owner, const void* dText, uint64_t len, 
     });
 }
 
+void ReplicaSet::loadRefConcatFromReplica(int owner, const B200SparseEMMatcher::StagePiece* pieces, size_t n, bool rc,
+                                          bool addSep, char sep) {
+    uint64_t total = 0;
+    void* src = rep[owner]->stageConcat(pieces, n, &total);
+    parallel((size() >= 64 ? ~0ull : (1ull << size()) - 1), [&](int r) {
+        B200SparseEMMatcher* m = rep[r];
+        if (m->hostMirror() && total) throw MatcherError(MBGCG_E_PARAM, "extensions from device memory need the host mirror off");
+        if (r == owner || total == 0) {
+            m->loadRefDevice(src, nullptr, total, rc, addSep, sep);
+            return;
+        }
+        void* stage = m->refStaging(total);
+        cudaError_t e = cudaMemcpyPeerAsync(stage, m->deviceIndex(), src, rep[owner]->deviceIndex(), total,
+                                            static_cast<cudaStream_t>(m->streamHandle()));
+        if (e != cudaSuccess) throw MatcherError(MBGCG_E_CUDA, std::string("peer copy of a reference extension: ") + cudaGetErrorString(e));
+        m->loadRefDevice(stage, nullptr, total, rc, addSep, sep);
+    });
+}
+
 void ReplicaSet::loadSeparator(char sep) {
     for (auto* m : rep) m->loadSeparator(sep);
 }
@@ -614,7 +633,9 @@ void SequentialPass::dispatch() {
         forming->bytes += im.n;
         dispatchedFiles++;
         stageQ[forming->replica * NSLOT + forming->slot].push_back(StageMsg{StageMsg::ADD, forming, im});
-        if (forming->bytes >= cfg.chunkBytes) {
+        const uint64_t maxFiles = cfg.parallelSchedule
+            ? static_cast<uint64_t>(std::max(1, cfg.allowedTargetsOutrun / rs.size())) : UINT64_MAX;
+        if (forming->bytes >= cfg.chunkBytes || forming->nFiles >= maxFiles) {
             forming->closed = true;
             stageQ[forming->replica * NSLOT + forming->slot].push_back(StageMsg{StageMsg::FINISH, forming, HostImage{nullptr, 0}});
             forming.reset();
@@ -706,6 +727,14 @@ bool SequentialPass::startWindow() {
             items.push_back(Item{true, static_cast<int>(w), static_cast<uint32_t>(f)});
         }
     }
+    if (cfg.parallelSchedule) {  // every target takes its lock at the state it is matched against (MGMP.cpp:353-358)
+        for (auto& c : win) {
+            FastaBatchIngest& ing = *slots[c->replica * NSLOT + c->slot];
+            c->locks.assign(ing.files.size(), 0);
+            for (size_t f = 0; f < ing.files.size(); f++) c->locks[f] = rs.acquireLock();
+        }
+        windowFirstTarget = st.files;
+    }
     cursor = 0;
     winActive = true;
     st.windows++;
@@ -730,7 +759,7 @@ void SequentialPass::runFrom(size_t from) {
     uint64_t maxPassBytes = 1024ull << 20;
     if (const char* e = std::getenv("MBGC_B200_MAX_PASS_BYTES")) maxPassBytes = std::max<uint64_t>(1, std::strtoull(e, nullptr, 10));
     const int nd = rs.size();
-    for (auto& rsn : runState) { rsn.texts.clear(); rsn.offs.clear(); }
+    for (auto& rsn : runState) { rsn.texts.clear(); rsn.offs.clear(); rsn.locks.clear(); }
     std::vector<uint64_t> bytes(static_cast<size_t>(nd), 0);
     uint32_t taken = 0;
     uint64_t which = 0;
@@ -746,6 +775,7 @@ void SequentialPass::runFrom(size_t from) {
         it.valid = true;
         runState[r].texts.push_back(TextView{nullptr, ic.seqLen});
         runState[r].offs.push_back(ic.textOff);
+        if (cfg.parallelSchedule) runState[r].locks.push_back(win[it.chunk]->locks[ic.file]);
         which |= 1ull << r;
         taken++;
     }
@@ -760,9 +790,10 @@ void SequentialPass::runFrom(size_t from) {
         FastaBatchIngest& ing = *slots[r * NSLOT + slot];
         const uint64_t l0 = m->totalLaunches;
         const double t0 = now_ms();
-        m->matchBatch(runState[r].texts, nullptr, cfg.minMatchLength, true, ing.dTexts(), runState[r].offs.data(), true);
+        const uint64_t* locks = cfg.parallelSchedule ? runState[r].locks.data() : nullptr;
+        m->matchBatch(runState[r].texts, locks, cfg.minMatchLength, true, ing.dTexts(), runState[r].offs.data(), true);
         const double t1 = now_ms();
-        m->packBatch(cfg.pack, runState[r].texts, nullptr, nullptr, nullptr, loaded.data(), loaded.size());
+        m->packBatch(cfg.pack, runState[r].texts, nullptr, nullptr, locks, loaded.data(), loaded.size());
         tm[r * 2] = t1 - t0;
         tm[r * 2 + 1] = now_ms() - t1;
         launches[r] = m->totalLaunches - l0;
@@ -777,6 +808,7 @@ void SequentialPass::runFrom(size_t from) {
     st.packMs += pMax;
     st.runs++;
     committedThisRun = 0;
+    if (cfg.parallelSchedule) windowFirstTarget = st.files;   // these results saw every target finalized so far
 }
 
 void SequentialPass::next(SeqEvent& ev) {
@@ -808,24 +840,48 @@ void SequentialPass::next(SeqEvent& ev) {
         FastaBatchIngest& ing = *slots[ch.replica * NSLOT + ch.slot];
         B200SparseEMMatcher* pm = rs.primary();
         if (it.fileEnd) {
-            // processTargetMeta + processAfterTargetWithParallelIO (MBGC_Encoder.cpp:493-509): separator, the size of this
-            // file's reference extension, and the sliding-window position the decoder will replay
             const IngestedFile& fi = ing.files[it.contig];
-            if (!fileOpen) fileStartLoaded = pm->getLoadedRefLength();  // a file without contigs
             SeqEvent e{};
             e.type = SeqEvent::FILE_END;
+            e.window = st.windows;
             e.file = ch.firstFile + it.contig;
             e.status = fi.status;
             e.nContigs = fi.nContigs;
             e.dnaLineLen = fi.dnaLineLen == UINT64_MAX ? 0 : fi.dnaLineLen;  // KSEQ_DNA_LINE_LENGTH, MGMP.cpp:12-14
-            if (fi.status >= -2) {
-                if (cfg.separatorPerFile) {
-                    rs.loadSeparator(cfg.separator);
-                    e.refExtSize = pm->getLoadedRefLength() - fileStartLoaded;
-                    loaded.push_back((loaded.empty() ? 0 : loaded.back()) + e.refExtSize);
+            if (cfg.parallelSchedule) {
+                // finalizeParallelProcessingOfTarget (MGMP.cpp:433-468 with the encoder's hook, MBGC_Encoder.cpp:542-564):
+                // the target's extension goes into the reference as ONE text, then separator, extension size, lock release
+                const uint64_t lock = ch.locks[it.contig];
+                if (fi.status >= -2) {
+                    const uint64_t start = pm->getLoadedRefLength();
+                    if (!fileExt.empty()) {
+                        const double t0 = now_ms();
+                        loadRefPieces(ch.replica, fileExt, !cfg.rcDisabled && !cfg.contigsIndividuallyReversed);
+                        st.loadRefMs += now_ms() - t0;
+                        st.extensions++;
+                    }
+                    if (cfg.separatorPerFile) {
+                        rs.loadSeparator(cfg.separator);
+                        e.refExtSize = pm->getLoadedRefLength() - start;
+                        loaded.push_back(pm->getLoadedRefLength());
+                    }
                 }
-                e.lockPos = rs.acquireLock();
-                rs.releaseLock(e.lockPos);
+                e.lockPos = lock;
+                rs.releaseLock(lock);
+                fileExt.clear();
+            } else {
+                // processTargetMeta + processAfterTargetWithParallelIO (MBGC_Encoder.cpp:493-509): separator, the size of
+                // this file's reference extension, and the sliding-window position the decoder will replay
+                if (!fileOpen) fileStartLoaded = pm->getLoadedRefLength();  // a file without contigs
+                if (fi.status >= -2) {
+                    if (cfg.separatorPerFile) {
+                        rs.loadSeparator(cfg.separator);
+                        e.refExtSize = pm->getLoadedRefLength() - fileStartLoaded;
+                        loaded.push_back((loaded.empty() ? 0 : loaded.back()) + e.refExtSize);
+                    }
+                    e.lockPos = rs.acquireLock();
+                    rs.releaseLock(e.lockPos);
+                }
             }
             e.loadedRefLength = pm->getLoadedRefLength();
             fileOpen = false;
@@ -838,22 +894,42 @@ void SequentialPass::next(SeqEvent& ev) {
             runFrom(cursor);
             continue;
         }
-        // ---- commit one contig (MultipleGenomeMatchingProcessor.cpp:274-287) ----
+        const IngestedContig& ic = ing.contigs[it.contig];
+        B200SparseEMMatcher* m = rs.at(ch.replica);
+        const uint64_t unmatched = m->packUnmatched()[it.resIndex];
+        if (cfg.parallelSchedule) {
+            // the dissimilar-contig rule of MBGC_Encoder::processMatches (:202-205; MGMP_Params.h:193-196): a contig that
+            // looks dissimilar against a state more than allowedTargetsOutrunForDissimilarContigs targets old is matched
+            // again once the targets in front of it are finalized (MGMP.cpp:382-388) -- here: now, they all are
+            const uint64_t target = ch.firstFile + ic.file;
+            const int factor = cfg.unmatchedFractionFactor / std::max(1, cfg.unmatchedFractionFactorTweakForDissimilarContigs);
+            if (windowFirstTarget + static_cast<uint64_t>(cfg.allowedTargetsOutrunForDissimilarContigs) < target &&
+                ic.seqLen > cfg.minimalLengthForDissimilarContigs && unmatched * static_cast<uint64_t>(factor) > ic.seqLen) {
+                for (size_t i = cursor; i < items.size(); i++)
+                    if (!items[i].fileEnd && items[i].valid) {
+                        items[i].valid = false;
+                        st.rerunContigs++;
+                    }
+                runFrom(cursor);
+                continue;
+            }
+        }
+        // ---- commit one contig (MultipleGenomeMatchingProcessor.cpp:274-287 / :379-398) ----
         if (!fileOpen) {
             fileStartLoaded = pm->getLoadedRefLength();
             fileOpen = true;
         }
-        const IngestedContig& ic = ing.contigs[it.contig];
-        B200SparseEMMatcher* m = rs.at(ch.replica);
         SeqEvent e{};
         e.type = SeqEvent::CONTIG;
+        e.window = st.windows;
         e.file = ch.firstFile + ic.file;
         e.hdr = ing.header(it.contig);
         e.hdrLen = ic.hdrLen;
         e.seqLen = ic.seqLen;
         e.nMatches = m->batchCounts()[it.resIndex];
         e.kept = m->packKept()[it.resIndex];
-        e.unmatched = m->packUnmatched()[it.resIndex];
+        e.unmatched = unmatched;
+        e.contigLock = cfg.parallelSchedule ? ch.locks[ic.file] : UINT64_MAX;
         for (int s = 0; s < PACK_STREAMS; s++) {
             const auto& off = m->packStreamOff(s);
             e.seg[s] = m->packStream(s) + off[it.resIndex];
@@ -867,6 +943,12 @@ void SequentialPass::next(SeqEvent& ev) {
         committedThisRun++;
         cursor++;
         evQ.push_back(e);
+        if (cfg.parallelSchedule) {
+            // targetRefExtensions[i]: the contig, and right behind it its reverse complement (MGMP.cpp:389-398)
+            if (extend) fileExt.push_back(ExtPiece{ing.dTexts() + ic.textOff, ic.seqLen, false});
+            if (extend && extendRC && cfg.contigsIndividuallyReversed) fileExt.push_back(ExtPiece{ing.dTexts() + ic.textOff, ic.seqLen, true});
+            continue;
+        }
         if (extend) {
             const double t0 = now_ms();
             rs.loadRefFromReplica(ch.replica, ing.dTexts() + ic.textOff, ic.seqLen, extendRC, cfg.refRegionSeparators, cfg.separator);
@@ -884,6 +966,13 @@ void SequentialPass::next(SeqEvent& ev) {
             curWindow = std::min<uint32_t>(cfg.maxWindowContigs, 2 * curWindow);  // a whole run committed: speculate further
         }
     }
+}
+
+void SequentialPass::loadRefPieces(int owner, const std::vector<ExtPiece>& pieces, bool rc) {
+    std::vector<B200SparseEMMatcher::StagePiece> sp;
+    sp.reserve(pieces.size());
+    for (const auto& p : pieces) sp.push_back(B200SparseEMMatcher::StagePiece{p.dText, p.len, p.rc});
+    rs.loadRefConcatFromReplica(owner, sp.data(), sp.size(), rc, cfg.refRegionSeparators, cfg.separator);
 }
 
 }  // namespace mbgc_b200

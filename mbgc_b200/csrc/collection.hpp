@@ -134,6 +134,8 @@ public:
     void loadRef(const char* text, uint64_t len, bool rc, bool addSep, char sep);
     // the text is resident on replica `owner` at dText: peers fetch it device-to-device (NVLink), nothing crosses PCIe
     void loadRefFromReplica(int owner, const void* dText, uint64_t len, bool rc, bool addSep, char sep);
+    // the same for a text that is the concatenation of several pieces resident on `owner` (a whole target's extension)
+    void loadRefConcatFromReplica(int owner, const B200SparseEMMatcher::StagePiece* pieces, size_t n, bool rc, bool addSep, char sep);
     void loadSeparator(char sep);
     uint64_t acquireLock();
     void releaseLock(uint64_t v);
@@ -170,6 +172,18 @@ struct SeqConfig {                 // what the sequential schedule reads from MG
     bool refRegionSeparators = true;        // params->refRegionSeparators
     char separator = 0;                     // MGMP_Params::REF_REGION_SEPARATOR
     bool separatorPerFile = true;           // lazyDecompressionSupport: loadSeparator + refExtLoadedPosArr per file
+    // The batch-frozen schedule of the reference's PARALLEL mode instead (processTargetsParallel / processTarget /
+    // finalizeParallelProcessingOfTarget, MultipleGenomeMatchingProcessor.cpp:340-468, 520-555): every target (file) of a
+    // window is matched under its own sliding-window lock against the state at the window's start; a target's qualifying
+    // contigs (each followed by its reverse complement when contigsIndividuallyReversed) extend the reference when the
+    // target is finalized, in target order.  Any such schedule is legal (the decoder replays the reference growth from
+    // the lock positions); this one is deterministic.
+    bool parallelSchedule = false;
+    bool contigsIndividuallyReversed = true;          // MGMP_Params.h:75
+    int allowedTargetsOutrun = 64;                    // matcherWorkingThreads * allowedTargetsOutrunFactor: targets per window
+    int allowedTargetsOutrunForDissimilarContigs = 1; // MGMP_Params.h:78
+    uint64_t minimalLengthForDissimilarContigs = 0;   // MGMP_Params.h:79
+    int unmatchedFractionFactorTweakForDissimilarContigs = 16;  // MGMP_Params.h:80
     uint64_t chunkBytes = 64ull << 20;      // file images per ingest slot
     uint32_t maxWindowContigs = 1u << 20;   // speculation window (contigs); follows the commit rate below this
 };
@@ -182,6 +196,8 @@ struct SeqEvent {
     const char* hdr = nullptr; uint64_t hdrLen = 0;
     uint64_t seqLen = 0, nMatches = 0, kept = 0, unmatched = 0;
     int extended = 0, extendedRC = 0;
+    uint64_t contigLock = 0;       // parallel schedule: the lock position the contig was matched under
+    uint64_t window = 0;
     const uint8_t* seg[PACK_STREAMS] = {}; uint64_t segLen[PACK_STREAMS] = {};
     uint64_t nContigs = 0, dnaLineLen = 0, refExtSize = 0, lockPos = 0, loadedRefLength = 0;
 };
@@ -211,6 +227,7 @@ private:
     struct Chunk {
         int replica = 0, slot = 0;
         uint64_t firstFile = 0, nFiles = 0, bytes = 0;
+        std::vector<uint64_t> locks;   // parallel schedule: the sliding-window lock of every file
         bool closed = false;       // no more files will join (FINISH is queued)
         bool ready = false;        // ingested
         std::exception_ptr err;
@@ -239,6 +256,10 @@ private:
     std::vector<uint64_t> loaded;              // refExtLoadedPosArr as the schedule maintains it
     uint64_t fileStartLoaded = 0;              // getLoadedRefLength() when the current file began
     bool fileOpen = false;
+    uint64_t windowFirstTarget = 0;            // parallel schedule: processedTargetsCount when the current results were matched
+    struct ExtPiece { const uint8_t* dText; uint64_t len; bool rc; };
+    std::vector<ExtPiece> fileExt;             // parallel schedule: the open target's reference extension (device pieces)
+    void loadRefPieces(int owner, const std::vector<ExtPiece>& pieces, bool rc);
 
     // input
     std::mutex mu;
@@ -266,7 +287,7 @@ private:
     uint32_t committedThisRun = 0;
     std::deque<SeqEvent> evQ;
     // per replica: the contigs of its last run (texts for packBatch) and where each landed
-    struct RunState { std::vector<TextView> texts; std::vector<uint64_t> offs; };
+    struct RunState { std::vector<TextView> texts; std::vector<uint64_t> offs, locks; };
     std::vector<RunState> runState;
 };
 

@@ -301,6 +301,25 @@ void B200SparseEMMatcher::loadRefDevice(const void* dText, const char* hostText,
     lastLoadRefBases = getLoadedRefLength() - loaded0;
 }
 
+void* B200SparseEMMatcher::stageConcat(const StagePiece* pieces, size_t n, uint64_t* total) {
+    check(cudaSetDevice(device), "cudaSetDevice");
+    uint64_t sum = 0;
+    for (size_t i = 0; i < n; i++) sum += pieces[i].len;
+    growDevice(reinterpret_cast<void**>(&dStage), &dStageCap, sum + 64, "cudaMalloc(ref staging)");
+    uint64_t at = 0;
+    for (size_t i = 0; i < n; i++) {
+        if (pieces[i].len) {
+            launch_ref_segment(static_cast<const uint8_t*>(pieces[i].dText), dStage + at, pieces[i].len, pieces[i].rc, stream);
+            totalLaunches++;
+        }
+        at += pieces[i].len;
+    }
+    check(cudaGetLastError(), "ref_segment launch");
+    check(cudaStreamSynchronize(stream), "stageConcat sync");  // peers are about to read it through their own streams
+    if (total) *total = sum;
+    return dStage;
+}
+
 // staging buffer of at least n bytes on this device (the target of a peer copy before loadRefDevice)
 void* B200SparseEMMatcher::refStaging(uint64_t n) {
     check(cudaSetDevice(device), "cudaSetDevice");

@@ -65,6 +65,10 @@ public:
     void loadRefDevice(const void* dText, const char* hostText, uint64_t refLength, bool loadRCRef, bool addRegionSeparators,
                        char regionSeparator);
     void* refStaging(uint64_t n);
+    // pieces of this device's memory concatenated into the staging buffer (a piece with rc = true goes in as its upper-casing
+    // reverse complement): the reference extension of a whole target file, MultipleGenomeMatchingProcessor.cpp:389-398
+    struct StagePiece { const void* dText; uint64_t len; bool rc; };
+    void* stageConcat(const StagePiece* pieces, size_t n, uint64_t* total);
     // the host mirror behind getRef() is only read by the reference's own CPU packer (MBGC_Encoder.cpp:181,318-330,
     // 376-380); with K6 on the device nobody needs it and loadRef stops filling it
     void setHostMirror(bool on) { mirrorEnabled = on; }

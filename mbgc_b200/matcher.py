@@ -56,20 +56,27 @@ class SeqConfig(C.Structure):
     _fields_ = [("pack", PackParams), ("minMatchLength", C.c_uint32), ("unmatchedFractionFactor", C.c_int32),
                 ("unmatchedFractionRCFactor", C.c_int32), ("rcInReferenceDisabled", C.c_int32),
                 ("refRegionSeparators", C.c_int32), ("separatorPerFile", C.c_int32), ("regionSeparator", C.c_char),
-                ("chunkBytes", C.c_uint64), ("maxWindowContigs", C.c_uint32)]
+                ("chunkBytes", C.c_uint64), ("maxWindowContigs", C.c_uint32), ("parallelSchedule", C.c_int32),
+                ("contigsIndividuallyReversed", C.c_int32), ("allowedTargetsOutrun", C.c_int32),
+                ("allowedTargetsOutrunForDissimilarContigs", C.c_int32),
+                ("unmatchedFractionFactorTweakForDissimilarContigs", C.c_int32),
+                ("minimalLengthForDissimilarContigs", C.c_uint64)]
 
     @staticmethod
-    def for_mode(mode, chunk_bytes=0, max_window=0, lazy=True):
+    def for_mode(mode, chunk_bytes=0, max_window=0, lazy=True, parallel=False, outrun=64):
         """`mbgc c -m mode` defaults: extension when unmatched * 128 > length, its reverse complement too when
-        unmatched * 8 > length (modes 2/3: * 128), MGMP_Params.h:41-42, MBGC_Params.h:906-909"""
+        unmatched * 8 > length (modes 2/3: * 128), MGMP_Params.h:41-42, MBGC_Params.h:906-909.  parallel=True: the
+        batch-frozen schedule of the reference's parallel mode with the mode's dissimilar-contig settings
+        (MGMP_Params.h:57-63, MBGC_Params.h:893-905)."""
+        dis_outrun, tweak = {0: (4, 32), 2: (0, 2)}.get(mode, (1, 16))
         return SeqConfig(PackParams.for_mode(mode, lazy=lazy), 32, 128, 128 if mode >= 2 else 8, 0, 1, 1 if lazy else 0,
-                         b"\0", chunk_bytes, max_window)
+                         b"\0", chunk_bytes, max_window, 1 if parallel else 0, 1, outrun, dis_outrun, tweak, 1024)
 
 
 class SeqEvent(C.Structure):
     _fields_ = [("type", C.c_int32), ("status", C.c_int32), ("file", C.c_uint64), ("hdr", C.c_void_p),
                 ("hdrLen", C.c_uint64), ("seqLen", C.c_uint64), ("nMatches", C.c_uint64), ("kept", C.c_uint64),
-                ("unmatched", C.c_uint64), ("extended", C.c_int32), ("extendedRC", C.c_int32),
+                ("unmatched", C.c_uint64), ("extended", C.c_int32), ("extendedRC", C.c_int32), ("contigLock", C.c_uint64), ("window", C.c_uint64),
                 ("seg", C.c_void_p * 6), ("segLen", C.c_uint64 * 6), ("nContigs", C.c_uint64),
                 ("dnaLineLen", C.c_uint64), ("refExtSize", C.c_uint64), ("lockPos", C.c_uint64),
                 ("loadedRefLength", C.c_uint64)]

@@ -144,3 +144,49 @@ def test_bad_files_report_the_readers_status(tmp_path):
         assert info["seqCounts"][:2] == [1, 0]
     finally:
         g.close()
+
+
+# ---- the batch-frozen schedule of the reference's parallel mode ---------------------------------------------------------
+
+def check_parallel_schedule(paths, mode, devices, chunk_bytes, outrun):
+    from par_schedule import encode_streams_parallel
+    from mbgc_b200.matcher import EV_FILE_END
+    recs0 = read_fasta(paths[0])
+    basic = max(os.path.getsize(paths[0]), 1 << 21)
+    limit = max(min(reference_factor(len(paths)) * basic * 2, 2**32 - 1), len(recs0[0][1]))
+    g = mbgc_b200.Matcher(limit, 32, 16, 1, 24 if mode >= 2 else 16, devices=devices)
+    try:
+        g.disableSlidingWindow()
+        g.loadRef(recs0[0][1], True, True, 0)
+        cfg = SeqConfig.for_mode(mode, chunk_bytes, parallel=True, outrun=outrun)
+        windows = {}
+
+        def on_event(ev):
+            if ev.type == EV_FILE_END:
+                windows.setdefault(int(ev.window), []).append(int(ev.file))
+
+        got, info = g.compressSequential([open(p, "rb").read() for p in paths], cfg, on_event=on_event)
+        ref_length = g.getRefLength()
+    finally:
+        g.close()
+    wins = [windows[k] for k in sorted(windows)]
+    want, st = encode_streams_parallel(paths, mode, limit, wins, cfg.allowedTargetsOutrunForDissimilarContigs,
+                                       cfg.unmatchedFractionFactorTweakForDissimilarContigs)
+    for name in STREAMS:
+        assert got[name] == want[name], f"stream {name} differs ({len(got[name])} vs {len(want[name])} bytes)"
+    assert info["unmatched"] == st["unmatched"] and info["matches"] == st["matches"]
+    assert info["lockPos"] == st["locks"] and info["refExtSizes"] == st["ref_ext"]
+    assert ref_length == st["ref_length"]
+    return info, wins, st
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_parallel_schedule_streams(mixed_dir, mode):
+    info, wins, st = check_parallel_schedule(mixed_dir, mode, [0], 1 << 20, outrun=4)
+    assert len(wins) > 2 and max(len(w) for w in wins) > 1 and info["extensions"] > 0
+
+
+def test_parallel_schedule_two_replicas(mixed_dir):
+    if n_devices() < 2:
+        pytest.skip("needs two CUDA devices")
+    check_parallel_schedule(mixed_dir, 1, [0, 1], 1 << 20, outrun=6)
