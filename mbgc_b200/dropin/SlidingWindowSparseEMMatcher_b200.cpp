@@ -23,6 +23,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <mutex>
+#include <string>
 #include <vector>
 
 #include "mbgc_b200.h"
@@ -68,6 +69,15 @@ std::vector<int> devices_from_env() {
     if (d.empty()) {
         const char* e = std::getenv("MBGC_B200_DEVICE");
         d.push_back(e ? std::atoi(e) : 0);
+    }
+    // CUDA initialises every VISIBLE device when the first context is created (~0.5-0.8 s apiece on a multi-GPU box):
+    // unless the user has set the mask already, show the runtime only the devices this run uses.  This is the first
+    // CUDA-related thing the process does, so the mask takes effect.
+    if (!std::getenv("CUDA_VISIBLE_DEVICES") && !std::getenv("MBGC_B200_KEEP_VISIBLE")) {
+        std::string mask;
+        for (size_t i = 0; i < d.size(); i++) mask += (i ? "," : "") + std::to_string(d[i]);
+        setenv("CUDA_VISIBLE_DEVICES", mask.c_str(), 1);
+        for (size_t i = 0; i < d.size(); i++) d[i] = static_cast<int>(i);
     }
     return d;
 }

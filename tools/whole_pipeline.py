@@ -62,7 +62,19 @@ def md5(p):
     return hashlib.md5(open(p, "rb").read()).hexdigest()
 
 
-def measure(d, total, mode, gpus, stock_runs=3, skip_t1=False):
+def decodes(archive, d, names):
+    """the stock decoder (sequential, `d -Q`) restores every file byte for byte"""
+    import shutil
+    out = os.path.join(d, "_decoded")
+    shutil.rmtree(out, ignore_errors=True)
+    os.makedirs(out)
+    run("mbgc", ["d", "-Q", archive, out], d)
+    ok = all(open(os.path.join(d, n), "rb").read() == open(os.path.join(out, n), "rb").read() for n in names)
+    shutil.rmtree(out, ignore_errors=True)
+    return ok
+
+
+def measure(d, total, mode, gpus, stock_runs=3, skip_t1=False, parallel=False, names=None):
     """d: directory with the FASTA files and list.txt.  Returns the report dictionary."""
     out = {"fasta_bytes": total, "mode": mode, "host_cores": os.cpu_count()}
     m = ["c", "-m", str(mode), "-f"]
@@ -86,6 +98,16 @@ def measure(d, total, mode, gpus, stock_runs=3, skip_t1=False):
             x, y = open(arch(key + "_Q"), "rb").read(), open(arch(key + "_t1"), "rb").read()
             diff = [i for i in range(min(len(x), len(y))) if x[i] != y[i]] if len(x) == len(y) else None
             out[key]["Q_vs_t1_differing_bytes"] = diff if diff is None or len(diff) < 8 else len(diff)
+    if parallel:  # the drop-in in the reference's default (parallel) mode: the pass's batch-frozen schedule
+        out["stock_default_threads"][-1]["archive_bytes"] = os.path.getsize(arch("stock"))
+        for g in gpus:
+            env = {"MBGC_B200_DEVICES": ",".join(str(i) for i in range(g)), "MBGC_B200_TRACE": "1"}
+            key = f"batched_{g}gpu"
+            runs = [run("mbgc_b200_batched", m + ["list.txt", arch(key + "_par")], d, env) for _ in range(2)]
+            out[key]["default_mode"] = {"runs": runs, "archive_bytes": os.path.getsize(arch(key + "_par")),
+                                        "md5": md5(arch(key + "_par"))}
+            if names:
+                out[key]["default_mode"]["decodes_with_stock_decoder"] = decodes(arch(key + "_par"), d, names)
     best = min(out["stock_default_threads"], key=lambda r: r["wall_s"])
     out["summary"] = {"cpu_cli": {"what": "stock `mbgc c` with default threads, best of the runs", "wall_s": best["wall_s"],
                                   "GB_per_s": round(total / best["wall_s"] / 1e9, 3),
@@ -99,6 +121,11 @@ def measure(d, total, mode, gpus, stock_runs=3, skip_t1=False):
             "match_phase_ms": (b["matching_finished_ms"] or 0) - (b["loaded_reference_ms"] or 0),
             "encoding_time_ms": b["encoding_time_ms"], "cuda_context_ms": ctx,
             "encoding_time_without_context_ms": (b["encoding_time_ms"] or 0) - ctx}
+        if parallel:
+            p = min(out[f"batched_{g}gpu"]["default_mode"]["runs"], key=lambda r: r["wall_s"])
+            out["summary"][f"batched_{g}gpu"]["default_mode"] = {
+                "wall_s": p["wall_s"], "match_phase_ms": (p["matching_finished_ms"] or 0) - (p["loaded_reference_ms"] or 0),
+                "encoding_time_ms": p["encoding_time_ms"], "cuda_context_ms": p.get("cuda_context_ms")}
     return out
 
 
@@ -110,6 +137,7 @@ def main():
     ap.add_argument("--dir", default="/dev/shm/mbgc_wp")
     ap.add_argument("--stock-runs", type=int, default=3)
     ap.add_argument("--skip-t1", action="store_true", help="skip the two -t 1 runs (archive identity)")
+    ap.add_argument("--parallel", action="store_true", help="also run the drop-in in the default (parallel) mode and decode its archive")
     a = ap.parse_args()
     n, length, seed, p_snp, p_indel, mode = CONFIGS[a.config]
     if a.genomes:
@@ -118,7 +146,7 @@ def main():
     t0 = time.perf_counter()
     names, total = write_collection(d, n, length, seed, p_snp, p_indel)
     out = {"config": a.config, "genomes": n, "generate_s": round(time.perf_counter() - t0, 1)}
-    out.update(measure(d, total, mode, [int(x) for x in a.gpus.split(",")], a.stock_runs, a.skip_t1))
+    out.update(measure(d, total, mode, [int(x) for x in a.gpus.split(",")], a.stock_runs, a.skip_t1, a.parallel, names))
     print(json.dumps(out, indent=1))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", f"whole_pipeline_{a.config}_{n}.json"), "w") as f:
