@@ -337,6 +337,23 @@ int mbgcg_image_free(mbgcg_t* h, const void* p);
  * MBGC_Encoder.cpp:181,318-330,376-380); while it is off mbgcg_load_ref skips the host-side copy */
 void mbgcg_set_host_mirror(mbgcg_t* h, int on);
 
+/* ---- the two legacy symbol packers the reference carries (row a14 of SURVEY.md 8; no live call site in MBGC) ----
+ * SymbolsPackingFacility::packSequence (/root/reference/coders/SymbolsPackingFacility.cpp:123-139, packSuffixSymbols
+ * :149-159): symbols of an alphabet of nSymbols letters (`symbols`, in order), as many per byte as fit -- 4 for ACGT,
+ * 3 for ACGNT -- first symbol most significant, a short tail padded with zeros.  dst needs ceil(n / perByte) bytes.
+ * A byte that is not in the alphabet is an error (the reference's validateSymbol ends the program). */
+int mbgcg_symbols_pack(mbgcg_t* h, const char* symbols, int nSymbols, const char* src, uint64_t n, uint8_t* dst, uint64_t* nOut);
+/* SymbolsPackingFacility::reverseSequence(sequence, pos, length, destPtr) (:190-215): symbols pos .. pos+length-1 */
+int mbgcg_symbols_unpack(mbgcg_t* h, const char* symbols, int nSymbols, const uint8_t* packed, uint64_t pos, uint64_t length, char* dst);
+/* VarLenDNACoder::encode (/root/reference/coders/VarLenDNACoder.cpp:55-112) for a code book given as the reference reads
+ * it (initUsing :10-36: up to 256 words of 1..4 symbols separated by '\n', the first a single symbol; writeBook :41-52
+ * produces it): greedy longest-first parse, one output byte per word.  The three static books of the reference are data
+ * of the reference; pass any of them, or your own.  n < 4 takes the tail rule of :89-111 only (the reference's main loop
+ * underflows there). */
+int mbgcg_varlen_encode(mbgcg_t* h, const char* codeBook, const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t dstCap, uint64_t* nOut);
+/* VarLenDNACoder::decode (:114-128): every code byte expands to its word; fails unless exactly expLen symbols come out */
+int mbgcg_varlen_decode(mbgcg_t* h, const char* codeBook, const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t expLen);
+
 /* ---- sliding-window locks (ref .cpp:361-400) ------------------------------------------------------------ */
 uint64_t mbgcg_acquire_lock(mbgcg_t* h);
 int mbgcg_release_lock(mbgcg_t* h, uint64_t lockValue);

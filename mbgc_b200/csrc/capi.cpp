@@ -14,6 +14,13 @@ using mbgc_b200::MatcherError;
 using mbgc_b200::TextMatch;
 using mbgc_b200::TextView;
 
+namespace mbgc_b200 {  // coders.cpp
+uint64_t symbols_pack(B200SparseEMMatcher* m, const char* symbols, int nSymbols, const char* src, uint64_t n, uint8_t* dst);
+void symbols_unpack(B200SparseEMMatcher* m, const char* symbols, int nSymbols, const uint8_t* packed, uint64_t pos, uint64_t length, char* dst);
+uint64_t varlen_encode(B200SparseEMMatcher* m, const char* codeBook, const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t dstCap);
+void varlen_decode(B200SparseEMMatcher* m, const char* codeBook, const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t expLen);
+}
+
 struct mbgcg {
     ReplicaSet* rs = nullptr;            // the replicas (one per device); m = replica 0
     B200SparseEMMatcher* m = nullptr;
@@ -330,6 +337,32 @@ void mbgcg_load_ref_timing(const mbgcg_t* h, float ms[2], uint64_t* appended) {
     if (appended) *appended = h->m->lastLoadRefBases;
 }
 void* mbgcg_stream(const mbgcg_t* h) { return h->m->streamHandle(); }
+
+// ---- the two legacy symbol packers (row a14) ---------------------------------------------------------------------------
+int mbgcg_symbols_pack(mbgcg_t* h, const char* symbols, int nSymbols, const char* src, uint64_t n, uint8_t* dst, uint64_t* nOut) {
+    return guarded(h, [&] {
+        if (!symbols || (n && (!src || !dst)) || !nOut) throw MatcherError(MBGCG_E_PARAM, "symbols_pack: null argument");
+        *nOut = mbgc_b200::symbols_pack(h->m, symbols, nSymbols, src, n, dst);
+    });
+}
+int mbgcg_symbols_unpack(mbgcg_t* h, const char* symbols, int nSymbols, const uint8_t* packed, uint64_t pos, uint64_t length, char* dst) {
+    return guarded(h, [&] {
+        if (!symbols || (length && (!packed || !dst))) throw MatcherError(MBGCG_E_PARAM, "symbols_unpack: null argument");
+        mbgc_b200::symbols_unpack(h->m, symbols, nSymbols, packed, pos, length, dst);
+    });
+}
+int mbgcg_varlen_encode(mbgcg_t* h, const char* codeBook, const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t dstCap, uint64_t* nOut) {
+    return guarded(h, [&] {
+        if (!codeBook || (n && !src) || !dst || !nOut) throw MatcherError(MBGCG_E_PARAM, "varlen_encode: null argument");
+        *nOut = mbgc_b200::varlen_encode(h->m, codeBook, src, n, dst, dstCap);
+    });
+}
+int mbgcg_varlen_decode(mbgcg_t* h, const char* codeBook, const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t expLen) {
+    return guarded(h, [&] {
+        if (!codeBook || (n && !src) || (expLen && !dst)) throw MatcherError(MBGCG_E_PARAM, "varlen_decode: null argument");
+        mbgc_b200::varlen_decode(h->m, codeBook, src, n, dst, expLen);
+    });
+}
 
 // ---- pinned host memory for file images -----------------------------------------------------------------------------
 void* mbgcg_image_alloc(mbgcg_t* h, uint64_t n) {

@@ -148,6 +148,14 @@ def load_library():
     L.mbgcg_image_free.restype = C.c_int
     L.mbgcg_image_free.argtypes = [vp, vp]
     L.mbgcg_set_host_mirror.argtypes = [vp, C.c_int]
+    L.mbgcg_symbols_pack.restype = C.c_int
+    L.mbgcg_symbols_pack.argtypes = [vp, C.c_char_p, C.c_int, vp, C.c_uint64, vp, u64p]
+    L.mbgcg_symbols_unpack.restype = C.c_int
+    L.mbgcg_symbols_unpack.argtypes = [vp, C.c_char_p, C.c_int, vp, C.c_uint64, C.c_uint64, vp]
+    L.mbgcg_varlen_encode.restype = C.c_int
+    L.mbgcg_varlen_encode.argtypes = [vp, C.c_char_p, vp, C.c_uint64, vp, C.c_uint64, u64p]
+    L.mbgcg_varlen_decode.restype = C.c_int
+    L.mbgcg_varlen_decode.argtypes = [vp, C.c_char_p, vp, C.c_uint64, vp, C.c_uint64]
     L.mbgcg_destroy.argtypes = [vp]
     L.mbgcg_last_error.restype = C.c_char_p
     L.mbgcg_last_error.argtypes = [vp]
@@ -238,6 +246,39 @@ class Matcher:
         if rc != 0:
             raise MatcherError(rc, self.lib.mbgcg_create_error().decode())
         self.h = h
+
+    # -- row a14: the reference's legacy symbol packers (coders/SymbolsPackingFacility.cpp, coders/VarLenDNACoder.cpp) ------
+    def packSymbols(self, symbols, src):
+        """SymbolsPackingFacility(symbols).packSequence(src)"""
+        a = _as_u8(src)
+        out = np.empty(a.size + 8, dtype=np.uint8)
+        n = C.c_uint64()
+        self._check(self.lib.mbgcg_symbols_pack(self.h, bytes(symbols), len(symbols), a.ctypes.data, a.size, out.ctypes.data, C.byref(n)))
+        return out[:n.value].copy()
+
+    def unpackSymbols(self, symbols, packed, pos, length):
+        """SymbolsPackingFacility(symbols).reverseSequence(packed, pos, length)"""
+        p = _as_u8(packed)
+        out = np.empty(max(length, 1), dtype=np.uint8)
+        self._check(self.lib.mbgcg_symbols_unpack(self.h, bytes(symbols), len(symbols), p.ctypes.data, pos, length, out.ctypes.data))
+        return out[:length].copy()
+
+    def varLenEncode(self, book, src):
+        """VarLenDNACoder(book).encode(src); book = the words separated by newlines"""
+        a = _as_u8(src)
+        out = np.empty(a.size + 8, dtype=np.uint8)
+        n = C.c_uint64()
+        self._check(self.lib.mbgcg_varlen_encode(self.h, book.encode("latin-1"), a.ctypes.data if a.size else None, a.size,
+                                                 out.ctypes.data, out.size, C.byref(n)))
+        return out[:n.value].copy()
+
+    def varLenDecode(self, book, codes, expected_len):
+        """VarLenDNACoder(book).decode(codes) -> exactly expected_len symbols"""
+        c = _as_u8(codes)
+        out = np.empty(max(expected_len, 1), dtype=np.uint8)
+        self._check(self.lib.mbgcg_varlen_decode(self.h, book.encode("latin-1"), c.ctypes.data if c.size else None, c.size,
+                                                 out.ctypes.data, expected_len))
+        return out[:expected_len].copy()
 
     def deviceCount(self):
         return self.lib.mbgcg_device_count(self.h)

@@ -794,3 +794,136 @@ uint64_t mbo_fasta_parse(const uint8_t* buf, uint64_t n, mbo_fasta_rec_t* recs, 
     *maxLastOut = maxLast;
     return nrec;
 }
+
+/* =====================================================================================================================
+ * Row a14: the two legacy symbol packers.  Restated from /root/reference/coders/SymbolsPackingFacility.cpp and
+ * coders/VarLenDNACoder.cpp; pinned against the reference's own classes by tests/test_coders_oracle.py
+ * (oracle/_ref/libref_coders.so) and golden digests.
+ * ===================================================================================================================== */
+
+/* SymbolsPackingFacility::maxSymbolsPerElement, SymbolsPackingFacility.cpp:102-111 */
+int mbo_symbols_per_element(int nSymbols) {
+    int k = 0;
+    uint64_t pw = 1;
+    while (pw * (uint64_t) nSymbols <= 256) {
+        pw *= (uint64_t) nSymbols;
+        k++;
+    }
+    return k;
+}
+
+/* packSequence :123-139 with packSymbols :161-166 (= the positional value for symbols of the alphabet) and
+ * packSuffixSymbols :149-159.  Returns the packed length, or UINT64_MAX for a symbol outside the alphabet. */
+uint64_t mbo_symbols_pack(const char* symbols, int nSymbols, const uint8_t* src, uint64_t n, uint8_t* dst) {
+    int order[256];
+    for (int i = 0; i < 256; i++) order[i] = -1;
+    for (int i = 0; i < nSymbols; i++) order[(uint8_t) symbols[i]] = i;
+    const int per = mbo_symbols_per_element(nSymbols);
+    uint64_t o = 0;
+    for (uint64_t i = 0; i < n; i += (uint64_t) per) {
+        unsigned v = 0;
+        for (int j = 0; j < per; j++) {
+            v *= (unsigned) nSymbols;
+            if (i + (uint64_t) j < n) {
+                const int k = order[src[i + (uint64_t) j]];
+                if (k < 0) return UINT64_MAX;
+                v += (unsigned) k;
+            }
+        }
+        dst[o++] = (uint8_t) v;
+    }
+    return o;
+}
+
+/* reverseSequence(sequence, pos, length, destPtr) :190-215 */
+void mbo_symbols_unpack(const char* symbols, int nSymbols, const uint8_t* packed, uint64_t pos, uint64_t length, uint8_t* dst) {
+    const int per = mbo_symbols_per_element(nSymbols);
+    for (uint64_t k = 0; k < length; k++) {
+        const uint64_t p = pos + k;
+        unsigned v = packed[p / (uint64_t) per];
+        const int j = (int) (p % (uint64_t) per);
+        for (int t = per - 1; t > j; t--) v /= (unsigned) nSymbols;
+        dst[k] = (uint8_t) symbols[v % (unsigned) nSymbols];
+    }
+}
+
+static uint32_t mbo_vl_idx(uint32_t v) { /* getLUTidx, VarLenDNACoder.h:40-43 */
+    return (v & 0x3Fu) | ((v & 0x3F00u) >> 2) | ((v & 0x3F0000u) >> 4) | ((v & 0x3F000000u) >> 6);
+}
+
+/* initUsing :10-36 -> book[256][5] and the 2^24-entry table (caller frees *lutOut).  Returns the number of words or -1. */
+static int mbo_vl_init(const char* codes, char book[256][5], uint8_t** lutOut) {
+    memset(book, 0, 256 * 5);
+    int counter = 0;
+    const char* p = codes;
+    for (;;) {
+        const char* nl = strchr(p, '\n');
+        const size_t len = nl ? (size_t) (nl - p) : strlen(p);
+        if (counter > 255 || len > 4) return -1;
+        memcpy(book[counter++], p, len);
+        if (!nl) break;
+        p = nl + 1;
+    }
+    if (strlen(book[0]) != 1) return -1;
+    uint8_t* lut = (uint8_t*) calloc(1u << 24, 1);
+    for (int i = 0; i < counter; i++) {
+        uint32_t t = 0;
+        memcpy(&t, book[i], 4);
+        lut[mbo_vl_idx(t)] = (uint8_t) i;
+    }
+    *lutOut = lut;
+    return counter;
+}
+
+/* encode :55-112.  Returns the number of codes, UINT64_MAX for an unexpected symbol or a bad book.  n < 4: the tail loop
+ * only (the reference's `pos <= srcLen - 4` wraps around there). */
+uint64_t mbo_varlen_encode(const char* codes, const uint8_t* src, uint64_t n, uint8_t* dst) {
+    char book[256][5];
+    uint8_t* lut = NULL;
+    if (mbo_vl_init(codes, book, &lut) < 0) return UINT64_MAX;
+    uint64_t out = 0, pos = 0;
+    while (n >= 4 && pos <= n - 4) {
+        uint32_t t = 0;
+        memcpy(&t, src + pos, 4);
+        t = mbo_vl_idx(t);
+        if (lut[t] != 0) { dst[out++] = lut[t]; pos += 4; continue; }
+        t &= 0x0003FFFFu;
+        if (lut[t] != 0) { dst[out++] = lut[t]; pos += 3; continue; }
+        t &= 0x00000FFFu;
+        if (lut[t] != 0) { dst[out++] = lut[t]; pos += 2; continue; }
+        t &= 0x0000003Fu;
+        if (lut[t] == 0 && t != (65u & 0x3Fu)) { free(lut); return UINT64_MAX; }
+        dst[out++] = lut[t];
+        pos++;
+    }
+    while (pos < n) {
+        uint32_t t = 0;
+        memcpy(&t, src + pos, (size_t) (n - pos));
+        t = mbo_vl_idx(t);
+        t &= 0x0003FFFFu;
+        if (n - pos >= 3 && lut[t] != 0) { dst[out++] = lut[t]; pos += 3; continue; }
+        t &= 0x00000FFFu;
+        if (n - pos >= 2 && lut[t] != 0) { dst[out++] = lut[t]; pos += 2; continue; }
+        t &= 0x0000003Fu;
+        if (lut[t] == 0 && t != (65u & 0x3Fu)) { free(lut); return UINT64_MAX; }
+        dst[out++] = lut[t];
+        pos++;
+    }
+    free(lut);
+    return out;
+}
+
+/* decode :114-128.  Returns the decoded length (the caller compares it with the expected one), UINT64_MAX for a bad book. */
+uint64_t mbo_varlen_decode(const char* codes, const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t dstCap) {
+    char book[256][5];
+    uint8_t* lut = NULL;
+    if (mbo_vl_init(codes, book, &lut) < 0) return UINT64_MAX;
+    free(lut);
+    uint64_t out = 0;
+    for (uint64_t i = 0; i < n; i++)
+        for (const char* w = book[src[i]]; *w; w++) {
+            if (out < dstCap) dst[out] = (uint8_t) *w;
+            out++;
+        }
+    return out;
+}

@@ -145,6 +145,13 @@ typedef struct {
 uint64_t mbo_fasta_parse(const uint8_t* buf, uint64_t n, mbo_fasta_rec_t* recs, uint64_t recCap, uint8_t* seqOut,
                          uint64_t* dnaLineLen, uint64_t* maxLastDnaLineLen, int* status);
 
+/* ---- row a14: SymbolsPackingFacility / VarLenDNACoder (coders/SymbolsPackingFacility.cpp, coders/VarLenDNACoder.cpp) ---- */
+int mbo_symbols_per_element(int nSymbols);
+uint64_t mbo_symbols_pack(const char* symbols, int nSymbols, const uint8_t* src, uint64_t n, uint8_t* dst);
+void mbo_symbols_unpack(const char* symbols, int nSymbols, const uint8_t* packed, uint64_t pos, uint64_t length, uint8_t* dst);
+uint64_t mbo_varlen_encode(const char* codes, const uint8_t* src, uint64_t n, uint8_t* dst);
+uint64_t mbo_varlen_decode(const char* codes, const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t dstCap);
+
 #ifdef __cplusplus
 }
 #endif

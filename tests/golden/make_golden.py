@@ -67,7 +67,35 @@ def stream_digests(d, list_name, mode):
     return out
 
 
+def coders_golden():
+    """row a14: digests of what the reference's own SymbolsPackingFacility / VarLenDNACoder produce
+    (oracle/_ref/libref_coders.so) for the seeded inputs of tests/coders_cases.py"""
+    from coders_cases import OWN_BOOK, SYMBOL_CASES, VARLEN_SIZES, random_symbols, ref_coders
+    L = ref_coders()
+    sha = lambda a: hashlib.sha1(bytes(a)).hexdigest()[:16]
+    out = {"symbols": {}, "varlen_own_book": {}}
+    for symbols, n, seed in SYMBOL_CASES:
+        src = random_symbols(symbols, n, seed)
+        dst = np.zeros(n + 8, dtype=np.uint8)
+        k = L.refc_symbols_pack(symbols, len(symbols), src.ctypes.data, n, dst.ctypes.data)
+        out["symbols"][f"{symbols.decode()}:{n}:{seed}"] = sha(dst[:k])
+    for n in VARLEN_SIZES:
+        src = random_symbols(b"ACGTN", n, 7 * n)
+        dst = np.zeros(n + 8, dtype=np.uint8)
+        k = L.refc_varlen_encode(OWN_BOOK.encode(), src.ctypes.data, n, dst.ctypes.data)
+        out["varlen_own_book"][str(n)] = sha(dst[:k])
+    return out
+
+
 def main():
+    if "--only-coders" in sys.argv:   # refresh one section, keep the rest
+        path = os.path.join(HERE, "golden.json")
+        g = json.load(open(path))
+        g["coders"] = coders_golden()
+        with open(path, "w") as f:
+            json.dump(g, f, indent=1, sort_keys=True)
+        print("updated coders section of", path)
+        return
     g = {"scenarios": {}, "streams": {}, "hash": [], "listeria": {}}
     # 1. match lists / table / cursor state of every scenario, from the reference class
     for sm in (16, 24):
@@ -101,6 +129,7 @@ def main():
     nz = np.nonzero(tab)[0]
     g["hash"] = {"text_seed": 5, "text_len": int(text.size), "slots": [[int(s), int(tab[s])] for s in nz]}
     r.close()
+    g["coders"] = coders_golden()
     with open(os.path.join(HERE, "golden.json"), "w") as f:
         json.dump(g, f, indent=1, sort_keys=True)
     print("wrote", os.path.join(HERE, "golden.json"))
