@@ -10,6 +10,7 @@
  */
 #include "mbgc_oracle.h"
 
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -926,4 +927,261 @@ uint64_t mbo_varlen_decode(const char* codes, const uint8_t* src, uint64_t n, ui
             out++;
         }
     return out;
+}
+
+/* =====================================================================================================================
+ * Row f3: the reverse-complement redundancy pass of mode 3.  SimpleSequenceMatcher::rcMatchSequence
+ * (/root/reference/matching/SimpleSequenceMatcher.cpp:165-176 -> markAndRemoveExactMatches :69-148 ->
+ * exactMatchSequence :24-56, resolveMappingCollisionsInTheSameText :150-163) over CopMEMMatcher
+ * (matching/copmem/CopMEMMatcher.cpp: initParams :63-93, calcCoprimes :108-137, genCumm / processRef :139-227 -- the
+ * single-threaded build, i.e. `-t 1` -- and processExactMatchQueryTight :332-484) with the hash
+ * maRushPrime1HashSparsified (utils/Hashes.h:43-66).  32-bit case only (sequence < 4 GiB).
+ * The l / r 4-byte prefilter of the query loop (:388-393, :449-452) is left out: a match of at least minMatchLength that
+ * contains the K-mer extends by LK2 = (L - K) / 2 on one side, so the prefilter never rejects an accepted match, and a
+ * candidate it lets through wrongly fails the length / K-mer test anyway (pinned against the reference's own classes,
+ * tests/test_rcmatch_oracle.py).
+ * ===================================================================================================================== */
+
+static uint32_t mbo_hash_sparsified(const uint8_t* s, int K) { /* utils/Hashes.h:43-66 */
+    uint64_t h = (uint64_t) K;
+    uint32_t j = 0, k;
+    while (j < 3) {
+        memcpy(&k, s, 4);
+        k &= 0x00FFFFFFu;
+        k += j++;
+        h ^= k;
+        h *= 171717;
+        s += 4;
+    }
+    while (j < (uint32_t) K / 4) {
+        memcpy(&k, s, 4);
+        k &= 0x0000FFFFu;
+        k += j++;
+        h ^= k;
+        h *= 171717;
+        s += 4;
+    }
+    return (uint32_t) h;
+}
+
+/* PgHelpers::reverseComplement (utils/helper.cpp:412-417) with the case-preserving table of :312-358 */
+static void mbo_complement_lut(uint8_t lut[256]) {
+    for (int i = 0; i < 256; i++) lut[i] = (uint8_t) i;
+    lut[0x7F] = 0; /* the reference fills CHAR_MIN .. CHAR_MAX - 1 only */
+    const char* from = "ACGTNYRKMBDHVWS";
+    const char* to = "TGCANRYMKVHDBSW";
+    for (int i = 0; from[i]; i++) {
+        lut[(uint8_t) from[i]] = (uint8_t) to[i];
+        lut[(uint8_t) (from[i] + 32)] = (uint8_t) (to[i] + 32);
+    }
+    lut['U'] = 'U';
+    lut['u'] = 'u';
+}
+
+void mbo_reverse_complement(const uint8_t* src, uint64_t n, uint8_t* dst) {
+    uint8_t lut[256];
+    mbo_complement_lut(lut);
+    for (uint64_t i = 0; i < n; i++) dst[n - 1 - i] = lut[src[i]];
+}
+
+/* CopMEMMatcher::initParams / calcCoprimes.  Returns 0, or -1 for "Minimal matching length too short" / L-K mismatch. */
+int mbo_copmem_params(uint64_t N, uint32_t L, uint32_t minMatchLength, int* K, int* k1, int* k2, uint32_t* hashSize) {
+    if (minMatchLength > L) minMatchLength = L;
+    int k;
+    if (L > 110) k = 56;
+    else if (L > 62) k = 44;
+    else if (L > 53) k = 40;
+    else if (L > 46) k = 36;
+    else if (L > 42) k = 32;
+    else if (L > 32) k = 28;
+    else k = ((int) L / 4 - 1) * 4;
+    if (minMatchLength < 24) return -1;
+    const int kmm = ((int) minMatchLength / 4 - 1) * 4;
+    if (kmm < k) k = kmm;
+    const int t = (int) L - k + 1;
+    if (t <= 0) return -1;
+    if (t >= 20) {
+        *k1 = (int) pow((double) t, 0.5) + 1;
+        *k2 = *k1 - 1;
+        if (*k1 * *k2 > t) { --*k2; --*k1; }
+    } else if (t >= 15) { *k1 = 5; *k2 = 3; }
+    else if (t >= 12) { *k1 = 4; *k2 = 3; }
+    else if (t >= 10) { *k1 = 5; *k2 = 2; }
+    else if (t >= 6) { *k1 = 3; *k2 = 2; }
+    else { *k1 = t; *k2 = 1; }
+    *K = k;
+    uint8_t i = 24;
+    uint32_t hs;
+    do {
+        hs = ((uint32_t) 1) << (i++);
+    } while (i <= 31 && hs < N / (uint64_t) *k1);
+    *hashSize = hs;
+    return 0;
+}
+
+static int mbo_rcm_cmp(const void* a, const void* b) { /* TextMatch::operator< (matching/TextMatchers.h:30-40): dest, src, length */
+    const mbo_rcm_t* x = (const mbo_rcm_t*) a;
+    const mbo_rcm_t* y = (const mbo_rcm_t*) b;
+    if (x->dst != y->dst) return x->dst < y->dst ? -1 : 1;
+    if (x->src != y->src) return x->src < y->src ? -1 : 1;
+    if (x->len != y->len) return x->len < y->len ? -1 : 1;
+    return 0;
+}
+
+static uint64_t mbo_frugal_bytes(uint8_t* dst, uint64_t at, uint64_t v) { /* writeUIntByteFrugal, utils/helper.cpp:217-225 */
+    while (v >= 128) {
+        dst[at++] = (uint8_t) (128 + v % 128);
+        v /= 128;
+    }
+    dst[at++] = (uint8_t) v;
+    return at;
+}
+
+/* The raw match list of CopMEMMatcher::matchTexts(resMatches, reverseComplement(seq), destIsSrc = true, revComplMatching =
+ * true, minMatchLength) as the query loop pushes it (positions in the reverse-complemented text).  Caller frees *out. */
+int64_t mbo_copmem_rc_matches(const uint8_t* seq, uint64_t N, uint32_t L, uint32_t minMatchLength, mbo_rcm_t** out) {
+    *out = NULL;
+    if (N >= (1ull << 32)) return -2;
+    int K, k1, k2;
+    uint32_t hashSize;
+    if (minMatchLength > L) minMatchLength = L;
+    if (mbo_copmem_params(N, L, minMatchLength, &K, &k1, &k2, &hashSize) < 0) return -1;
+    if (minMatchLength < (uint32_t) K) return -1;
+    const uint32_t mask = hashSize - 1;
+    /* ---- genCumm + processRef, single-threaded (:139-227) ---- */
+    uint32_t* cumm = (uint32_t*) calloc((size_t) hashSize + 2, 4);
+    uint8_t* skipped = (uint8_t*) calloc((size_t) (N / (uint64_t) k1 + 2), 1);
+    for (uint64_t i = 0, s = 0; i + (uint64_t) K <= N; i += (uint64_t) k1, s++) {
+        const uint32_t h = (mbo_hash_sparsified(seq + i, K) & mask) + 2;
+        if (cumm[h] <= 12) ++cumm[h];
+        else skipped[s] = 1;
+    }
+    for (uint64_t x = 1; x < (uint64_t) hashSize + 2; x++) cumm[x] += cumm[x - 1];
+    const uint32_t hashCount = cumm[hashSize + 1];
+    uint32_t* sampled = (uint32_t*) malloc(((size_t) hashCount + 2) * 4);
+    for (uint64_t i = 0, s = 0; i + (uint64_t) K <= N; i += (uint64_t) k1, s++) {
+        if (skipped[s]) continue;
+        const uint32_t h = (mbo_hash_sparsified(seq + i, K) & mask) + 1;
+        sampled[cumm[h]++] = (uint32_t) i;
+    }
+    free(skipped);
+    /* ---- the query: reverseComplement(seq) against the index of seq (:332-484) ---- */
+    uint8_t* q = (uint8_t*) malloc((size_t) N + 8);
+    mbo_reverse_complement(seq, N, q);
+    const uint64_t N2 = N;
+    const int skip = K / k1 - 1;
+    const uint64_t MULTI = 256, k2MULTI = (uint64_t) k2 * MULTI;
+    uint64_t cap = 1024, n = 0;
+    mbo_rcm_t* res = (mbo_rcm_t*) malloc(cap * sizeof(mbo_rcm_t));
+    /* one query position: returns 1 when the walk skips ahead (a push, or a seed inside the last match) */
+#define MBO_RC_QUERY(POS, HIT)                                                                                          \
+    do {                                                                                                                \
+        const uint64_t pos_ = (POS);                                                                                    \
+        const uint32_t h_ = mbo_hash_sparsified(q + pos_, K) & mask;                                                    \
+        HIT = 0;                                                                                                        \
+        for (uint32_t j = cumm[h_]; j < cumm[h_ + 1]; j++) {                                                            \
+            const uint64_t src_ = sampled[j];                                                                           \
+            if (N2 - src_ < pos_) continue;                                                                             \
+            if (n > 0 && pos_ - src_ == res[n - 1].dst - res[n - 1].src && pos_ + (uint64_t) K < res[n - 1].dst + res[n - 1].len) { \
+                HIT = 1;                                                                                                \
+                break;                                                                                                  \
+            }                                                                                                           \
+            uint64_t p1 = src_ + (uint64_t) K - 1, p2 = pos_ + (uint64_t) K - 1;                                        \
+            while (++p1 != N && ++p2 != N2 && seq[p1] == q[p2]) {}                                                      \
+            const uint64_t right = p1;                                                                                  \
+            int64_t a = (int64_t) src_, b = (int64_t) pos_;                                                             \
+            while (a != 0 && b != 0 && seq[a] == q[b]) { a--; b--; }                                                    \
+            if ((int64_t) right - a > (int64_t) minMatchLength && memcmp(seq + src_, q + pos_, (size_t) K) == 0) {      \
+                if (n == cap) { cap *= 2; res = (mbo_rcm_t*) realloc(res, cap * sizeof(mbo_rcm_t)); }                   \
+                res[n].src = (uint64_t) (a + 1);                                                                        \
+                res[n].len = (uint64_t) ((int64_t) right - a - 1);                                                      \
+                res[n].dst = (uint64_t) (b + 1);                                                                        \
+                n++;                                                                                                    \
+                HIT = 1;                                                                                                \
+                break;                                                                                                  \
+            }                                                                                                           \
+        }                                                                                                               \
+    } while (0)
+    uint64_t i1 = 0;
+    for (i1 = 0; i1 + (uint64_t) K + k2MULTI < N2 + 1; i1 += k2MULTI) {
+        for (uint64_t i2 = 0; i2 < MULTI; ++i2) {
+            int hit;
+            MBO_RC_QUERY(i1 + i2 * (uint64_t) k2, hit);
+            if (hit) i2 += (uint64_t) skip;
+        }
+    }
+    for (; i1 + (uint64_t) K < N2 + 1; i1 += (uint64_t) k2) {
+        int hit;
+        MBO_RC_QUERY(i1, hit);
+        if (hit) i1 += (uint64_t) skip * (uint64_t) k2;
+    }
+#undef MBO_RC_QUERY
+    free(q);
+    free(sampled);
+    free(cumm);
+    *out = res;
+    return (int64_t) n;
+}
+
+/* rcMatchSequence.  seq (n bytes) is rewritten in place; returns its new length.  mapOff needs 4 bytes per match, mapLen
+ * up to 10 bytes per match + 10.  Returns UINT64_MAX on a parameter error (the reference exits). */
+uint64_t mbo_rc_match_sequence(uint8_t* seq, uint64_t N, uint32_t targetMatchLength, uint32_t minMatchLength, uint8_t* mapOff,
+                               uint64_t* mapOffLen, uint8_t* mapLen, uint64_t* mapLenLen, uint64_t* nMatchesRaw) {
+    *mapOffLen = *mapLenLen = 0;
+    if (nMatchesRaw) *nMatchesRaw = 0;
+    if (N < targetMatchLength) return N; /* no matcher: both maps stay empty (SimpleSequenceMatcher.cpp:17-19, 72-76) */
+    mbo_rcm_t* m = NULL;
+    const int64_t nm = mbo_copmem_rc_matches(seq, N, targetMatchLength, minMatchLength, &m);
+    if (nm < 0) return UINT64_MAX;
+    if (minMatchLength == UINT32_MAX) minMatchLength = targetMatchLength;
+    if (nMatchesRaw) *nMatchesRaw = (uint64_t) nm;
+    uint64_t n = (uint64_t) nm;
+    for (uint64_t i = 0; i < n; i++) { /* correctDestPositionDueToRevComplMatching :58-61, resolveMappingCollisions :150-163 */
+        m[i].dst = N - (m[i].dst + m[i].len);
+        if (m[i].src > m[i].dst) {
+            const uint64_t t = m[i].src;
+            m[i].src = m[i].dst;
+            m[i].dst = t;
+        }
+        if (m[i].src + m[i].len > m[i].dst) {
+            const uint64_t margin = (m[i].src + m[i].len - m[i].dst + 1) / 2;
+            m[i].len -= margin;
+            m[i].dst += margin;
+        }
+    }
+    uint64_t lo = mbo_frugal_bytes(mapLen, 0, minMatchLength);
+    qsort(m, (size_t) n, sizeof(mbo_rcm_t), mbo_rcm_cmp);
+    uint64_t u = 0;
+    for (uint64_t i = 0; i < n; i++)
+        if (u == 0 || mbo_rcm_cmp(&m[i], &m[u - 1]) != 0) m[u++] = m[i];
+    n = u;
+    uint64_t pos = 0, nPos = 0, oo = 0;
+    for (uint64_t i = 0; i < n; i++) { /* :99-125 */
+        mbo_rcm_t* t = &m[i];
+        if (t->dst < pos) {
+            const uint64_t overflow = pos - t->dst;
+            if (overflow >= t->len) {
+                t->len = 0;
+                continue;
+            }
+            t->len -= overflow;
+            t->dst += overflow; /* revComplMatching: posSrcText stays */
+        }
+        if (t->len < minMatchLength) continue;
+        const uint64_t length = t->dst - pos;
+        memmove(seq + nPos, seq + pos, (size_t) length);
+        nPos += length;
+        seq[nPos++] = (uint8_t) ('$' + 128); /* RC_MATCH_MARK, mbgccoder/MBGC_Params.h:48 */
+        const uint32_t src32 = (uint32_t) t->src;
+        memcpy(mapOff + oo, &src32, 4);
+        oo += 4;
+        lo = mbo_frugal_bytes(mapLen, lo, t->len - minMatchLength);
+        pos = t->dst + t->len;
+    }
+    memmove(seq + nPos, seq + pos, (size_t) (N - pos));
+    nPos += N - pos;
+    free(m);
+    *mapOffLen = oo;
+    *mapLenLen = lo;
+    return nPos;
 }

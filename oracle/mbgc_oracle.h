@@ -152,6 +152,16 @@ void mbo_symbols_unpack(const char* symbols, int nSymbols, const uint8_t* packed
 uint64_t mbo_varlen_encode(const char* codes, const uint8_t* src, uint64_t n, uint8_t* dst);
 uint64_t mbo_varlen_decode(const char* codes, const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t dstCap);
 
+/* ---- row f3: SimpleSequenceMatcher::rcMatchSequence over CopMEMMatcher (matching/SimpleSequenceMatcher.cpp:165-176,
+ * matching/copmem/CopMEMMatcher.cpp), single-threaded index build (-t 1) ---- */
+void mbo_reverse_complement(const uint8_t* src, uint64_t n, uint8_t* dst);
+int mbo_copmem_params(uint64_t N, uint32_t L, uint32_t minMatchLength, int* K, int* k1, int* k2, uint32_t* hashSize);
+typedef struct { uint64_t src, len, dst; } mbo_rcm_t;   /* TextMatch(posSrcText, length, posDestText) */
+/* the list CopMEMMatcher::matchTexts(reverseComplement(seq), destIsSrc, revComplMatching) pushes, in push order; *out is malloc'ed */
+int64_t mbo_copmem_rc_matches(const uint8_t* seq, uint64_t N, uint32_t L, uint32_t minMatchLength, mbo_rcm_t** out);
+uint64_t mbo_rc_match_sequence(uint8_t* seq, uint64_t N, uint32_t targetMatchLength, uint32_t minMatchLength, uint8_t* mapOff,
+                               uint64_t* mapOffLen, uint8_t* mapLen, uint64_t* mapLenLen, uint64_t* nMatchesRaw);
+
 #ifdef __cplusplus
 }
 #endif

@@ -87,7 +87,32 @@ def coders_golden():
     return out
 
 
+def rcmatch_golden():
+    """row f3: digests of what the reference's own SimpleSequenceMatcher::rcMatchSequence produces
+    (oracle/_ref/libref_copmem.so, single-threaded index build) for the seeded inputs of tests/rcmatch_cases.py"""
+    from rcmatch_cases import RC_CASES, r_rc_match, rc_sequence, ref_copmem
+    L = ref_copmem()
+    out = {}
+    for n, seed in RC_CASES:
+        for tl in (55, 32):
+            s, off, ln = r_rc_match(L, rc_sequence(n, seed), tl)
+            h = hashlib.sha1()
+            for a in (s, off, ln):
+                h.update(bytes(a))
+                h.update(b"|")
+            out[f"{n}:{seed}:{tl}"] = h.hexdigest()[:16]
+    return out
+
+
 def main():
+    if "--only-rcmatch" in sys.argv:
+        path = os.path.join(HERE, "golden.json")
+        g = json.load(open(path))
+        g["rcmatch"] = rcmatch_golden()
+        with open(path, "w") as f:
+            json.dump(g, f, indent=1, sort_keys=True)
+        print("updated rcmatch section of", path)
+        return
     if "--only-coders" in sys.argv:   # refresh one section, keep the rest
         path = os.path.join(HERE, "golden.json")
         g = json.load(open(path))
@@ -130,6 +155,7 @@ def main():
     g["hash"] = {"text_seed": 5, "text_len": int(text.size), "slots": [[int(s), int(tab[s])] for s in nz]}
     r.close()
     g["coders"] = coders_golden()
+    g["rcmatch"] = rcmatch_golden()
     with open(os.path.join(HERE, "golden.json"), "w") as f:
         json.dump(g, f, indent=1, sort_keys=True)
     print("wrote", os.path.join(HERE, "golden.json"))
