@@ -337,6 +337,18 @@ int mbgcg_image_free(mbgcg_t* h, const void* p);
  * MBGC_Encoder.cpp:181,318-330,376-380); while it is off mbgcg_load_ref skips the host-side copy */
 void mbgcg_set_host_mirror(mbgcg_t* h, int on);
 
+/* ---- the reverse-complement redundancy pass of mode 3 (row f3 of SURVEY.md 8) ------------------------------------
+ * SimpleSequenceMatcher::rcMatchSequence(sequence, rcMapOff, rcMapLen, targetMatchLength, minMatchLength)
+ * (/root/reference/matching/SimpleSequenceMatcher.cpp:165-176; called on the literal stream at
+ * mbgccoder/MBGC_Encoder.cpp:637-638) over CopMEMMatcher (matching/copmem/CopMEMMatcher.cpp) with the single-threaded
+ * (`-t 1`) index build: stretches of `seq` that are the reverse complement of an earlier stretch are cut out and replaced by
+ * RC_MATCH_MARK; mapOff gets their source positions (u32 each), mapLen the frugal-byte lengths (first entry: the minimal
+ * match length).  seq (HOST, n bytes) is rewritten in place, *newLen = its new length.  mapOff needs 4 and mapLen 10 bytes
+ * per (n / minMatchLength + 2) matches.  minMatchLength = UINT32_MAX means targetMatchLength, as in the reference.
+ * deviceMs (may be NULL): [0] index build, [1] query, CUDA events. */
+int mbgcg_rc_match_sequence(mbgcg_t* h, uint8_t* seq, uint64_t n, uint32_t targetMatchLength, uint32_t minMatchLength, uint64_t* newLen,
+                            uint8_t* mapOff, uint64_t* mapOffLen, uint8_t* mapLen, uint64_t* mapLenLen, float deviceMs[2]);
+
 /* ---- the two legacy symbol packers the reference carries (row a14 of SURVEY.md 8; no live call site in MBGC) ----
  * SymbolsPackingFacility::packSequence (/root/reference/coders/SymbolsPackingFacility.cpp:123-139, packSuffixSymbols
  * :149-159): symbols of an alphabet of nSymbols letters (`symbols`, in order), as many per byte as fit -- 4 for ACGT,

@@ -19,6 +19,10 @@ uint64_t symbols_pack(B200SparseEMMatcher* m, const char* symbols, int nSymbols,
 void symbols_unpack(B200SparseEMMatcher* m, const char* symbols, int nSymbols, const uint8_t* packed, uint64_t pos, uint64_t length, char* dst);
 uint64_t varlen_encode(B200SparseEMMatcher* m, const char* codeBook, const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t dstCap);
 void varlen_decode(B200SparseEMMatcher* m, const char* codeBook, const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t expLen);
+// rcmatch.cpp
+uint64_t rc_match_sequence(B200SparseEMMatcher* m, uint8_t* seq, uint64_t N, uint32_t targetMatchLength, uint32_t minMatchLength,
+                           uint8_t* mapOff, uint64_t* mapOffLen, uint8_t* mapLen, uint64_t* mapLenLen, float deviceMs[2],
+                           uint64_t* launches);
 }
 
 struct mbgcg {
@@ -337,6 +341,17 @@ void mbgcg_load_ref_timing(const mbgcg_t* h, float ms[2], uint64_t* appended) {
     if (appended) *appended = h->m->lastLoadRefBases;
 }
 void* mbgcg_stream(const mbgcg_t* h) { return h->m->streamHandle(); }
+
+// ---- the reverse-complement redundancy pass of mode 3 (row f3) -----------------------------------------------------------
+int mbgcg_rc_match_sequence(mbgcg_t* h, uint8_t* seq, uint64_t n, uint32_t targetMatchLength, uint32_t minMatchLength, uint64_t* newLen,
+                            uint8_t* mapOff, uint64_t* mapOffLen, uint8_t* mapLen, uint64_t* mapLenLen, float deviceMs[2]) {
+    return guarded(h, [&] {
+        if ((n && !seq) || !newLen || !mapOff || !mapOffLen || !mapLen || !mapLenLen)
+            throw MatcherError(MBGCG_E_PARAM, "rc_match_sequence: null argument");
+        *newLen = mbgc_b200::rc_match_sequence(h->m, seq, n, targetMatchLength, minMatchLength, mapOff, mapOffLen, mapLen, mapLenLen,
+                                              deviceMs, nullptr);
+    });
+}
 
 // ---- the two legacy symbol packers (row a14) ---------------------------------------------------------------------------
 int mbgcg_symbols_pack(mbgcg_t* h, const char* symbols, int nSymbols, const char* src, uint64_t n, uint8_t* dst, uint64_t* nOut) {

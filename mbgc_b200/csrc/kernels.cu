@@ -397,6 +397,12 @@ static int scan_exclusive(const uint32_t* in, uint32_t* out, const uint32_t* nPt
     return 1;
 }
 
+// exclusive scan for other translation units (rcmatch.cpp): in[0 .. n) -> out[0 .. n], out[n] = total; `state` = zeroed
+// scratch of n / 4096 + 8 words
+int launch_scan_u32(const uint32_t* in, uint32_t* out, uint32_t n, unsigned long long* state, cudaStream_t st) {
+    return scan_exclusive(in, out, nullptr, n, n, state, n / SCAN_BLOCK + 8, nullptr, st);
+}
+
 // ------------------------------------------------------------------------------------------------------
 // K3: probe  (.cpp:200-226 and the K-mer verify of :298, for every target position)
 //

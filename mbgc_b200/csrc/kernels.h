@@ -159,6 +159,7 @@ struct ExcRunDev {       // = mbgc_b200::ExcRun (hostpack.hpp): a run of one non
 int launch_unpack(const PackedBlock* blocks, uint32_t nBlocks, const uint8_t* packed, const ExcRunDev* runs, uint32_t nRuns,
                   uint8_t* text, cudaStream_t st);
 
+int launch_scan_u32(const uint32_t* in, uint32_t* out, uint32_t n, unsigned long long* state, cudaStream_t st);
 bool probe_supports_K(int K);
 int device_sm_count();
 

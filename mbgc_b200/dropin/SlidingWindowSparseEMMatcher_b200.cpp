@@ -39,6 +39,7 @@ const mbgcg_seq_event_t* g_prepacked = nullptr;
 mbgc_b200_dropin::EncoderState* g_encoderStateRequest = nullptr;
 bool g_replay = false;
 uint64_t g_replayLock = 0;
+int g_firstDevice = 0;
 
 // The reference's parallel mode enters matchTexts from several OpenMP threads while another one runs loadRef
 // (SURVEY.md 8b "Threading").  A handle is not thread-safe; serialising is a legal schedule of that mode.
@@ -117,6 +118,7 @@ SlidingWindowSparseEMMatcher::SlidingWindowSparseEMMatcher(const size_t refLengt
     Trace tr("create", refLengthLimit);
     mbgcg_t* h = nullptr;
     const std::vector<int> devs = devices_from_env();
+    g_firstDevice = devs[0];
     if (mbgcg_create_multi(&h, refLengthLimit, targetMatchLength, _k1, _k2, skipMargin, devs.data(), static_cast<int>(devs.size())) != MBGCG_OK)
         die(mbgcg_create_error());
     ht64bit = reinterpret_cast<std::uint64_t*>(h);
@@ -255,6 +257,7 @@ struct Access : SlidingWindowSparseEMMatcher {
 };
 
 std::mutex& handle_lock() { return g_lock; }
+int first_device() { return g_firstDevice; }
 
 mbgcg_t* synced_handle(SlidingWindowSparseEMMatcher* m) {
     mbgcg_t* h = handle_of(m->*Access::ht());

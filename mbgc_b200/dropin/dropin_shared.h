@@ -55,6 +55,9 @@ void set_replay(bool on, uint64_t lockPos);
 // members of the reference matcher object <- the handle (take handle_lock() first)
 void pull_state(SlidingWindowSparseEMMatcher* m);
 
+// the CUDA device (as this process numbers them) the matcher shim put replica 0 on; 0 before any matcher was built
+int first_device();
+
 std::mutex& handle_lock();
 // the C-ABI handle of a matcher built by the shim, after pushing the members the reference header's inline
 // setters may have changed (take handle_lock() first)

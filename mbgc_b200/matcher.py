@@ -148,6 +148,8 @@ def load_library():
     L.mbgcg_image_free.restype = C.c_int
     L.mbgcg_image_free.argtypes = [vp, vp]
     L.mbgcg_set_host_mirror.argtypes = [vp, C.c_int]
+    L.mbgcg_rc_match_sequence.restype = C.c_int
+    L.mbgcg_rc_match_sequence.argtypes = [vp, vp, C.c_uint64, C.c_uint32, C.c_uint32, u64p, vp, u64p, vp, u64p, C.POINTER(C.c_float)]
     L.mbgcg_symbols_pack.restype = C.c_int
     L.mbgcg_symbols_pack.argtypes = [vp, C.c_char_p, C.c_int, vp, C.c_uint64, vp, u64p]
     L.mbgcg_symbols_unpack.restype = C.c_int
@@ -246,6 +248,19 @@ class Matcher:
         if rc != 0:
             raise MatcherError(rc, self.lib.mbgcg_create_error().decode())
         self.h = h
+
+    # -- row f3: SimpleSequenceMatcher::rcMatchSequence (matching/SimpleSequenceMatcher.cpp:165-176) ------------------------------
+    def rcMatchSequence(self, sequence, targetMatchLength=55, minMatchLength=2**32 - 1):
+        """-> (rewritten sequence, rcMapOff, rcMapLen, {"index_ms", "query_ms"}) as uint8 arrays"""
+        s = _as_u8(sequence).copy()
+        cap = s.size // 24 + 4
+        off = np.zeros(4 * cap, dtype=np.uint8)
+        ln = np.zeros(10 * cap, dtype=np.uint8)
+        n, no, nl = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        ms = (C.c_float * 2)()
+        self._check(self.lib.mbgcg_rc_match_sequence(self.h, s.ctypes.data if s.size else None, s.size, targetMatchLength, minMatchLength,
+                                                     C.byref(n), off.ctypes.data, C.byref(no), ln.ctypes.data, C.byref(nl), ms))
+        return s[:n.value].copy(), off[:no.value].copy(), ln[:nl.value].copy(), {"index_ms": ms[0], "query_ms": ms[1]}
 
     # -- row a14: the reference's legacy symbol packers (coders/SymbolsPackingFacility.cpp, coders/VarLenDNACoder.cpp) ------
     def packSymbols(self, symbols, src):
