@@ -610,6 +610,9 @@ __global__ void __launch_bounds__(FILTER ? PROBE_THREADS_FILTER : PROBE_THREADS_
         }
         if (valid && sum && lane == __ffs(peers) - 1) atomicAdd(&a.chunkCount[g], sum);
     }
+    // a warp without items never reached the wait in the loop: no thread may leave the CTA while the bulk copy into its
+    // shared memory is still in flight (the async proxy would write into memory of a retired CTA)
+    if (FILTER && filterPending) mbar_wait(barAddr, 0);
 }
 
 // ------------------------------------------------------------------------------------------------------

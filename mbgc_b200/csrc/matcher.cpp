@@ -704,6 +704,11 @@ int B200SparseEMMatcher::stageTexts(const std::vector<TextView>& texts, size_t f
     Blk* bp = blks.data();
     uint8_t* fp = failed.data();
     std::vector<std::vector<ExcRun>>* runsAll = &blockRuns;
+    // the workers hold pointers into blks / failed: whatever throws below must not unwind past them while they run
+    struct PoolGuard {
+        WorkerPool* p;
+        ~PoolGuard() { p->wait(); }
+    } poolGuard{pool};
     pool->run(nB, [bp, hp, fp, runsAll](uint32_t b, int) {
         std::vector<ExcRun>& runs = (*runsAll)[b];
         runs.clear();

@@ -819,7 +819,7 @@ int launch_pack_pass1(const PackParams& p, const PackState& s, const PackBatch& 
     launches++;
     if (p.enableExt)
         for (int i = 0; i < sweeps; i++) {
-            k_pk_removal<<<blocks, PK_THREADS, 0, st>>>(p, s, b, w.mContig, w.removed, w.flags + (i < 15 ? i : 15));
+            k_pk_removal<<<blocks, PK_THREADS, 0, st>>>(p, s, b, w.mContig, w.removed, w.flags + (i == sweeps - 1 ? 15 : i % 15));  // the last sweep has a flag of its own
             launches++;
         }
     k_pk_kept_tot<<<blocks, PK_THREADS, 0, st>>>(nM, w.removed, w.blockTot);
@@ -845,7 +845,7 @@ int launch_pack_claims(const PackParams& p, const PackState& s, const PackBatch&
             k_pk_claim_scatter<<<blocks, PK_THREADS, 0, st>>>(b.nContigs, w.kOff, w.claim, w.claimedBy);
             launches++;
         }
-        k_pk_claim_sweep<<<blocks, PK_THREADS, 0, st>>>(p, s, b, w, w.flags + 16 + (i < 15 ? i : 15));
+        k_pk_claim_sweep<<<blocks, PK_THREADS, 0, st>>>(p, s, b, w, w.flags + 16 + (i == sweeps - 1 ? 15 : i % 15));
         launches++;
     }
     // the claims of the last sweep decide which matches omit their offset

@@ -146,6 +146,9 @@ void B200SparseEMMatcher::packBatch(const PackParams& p, const std::vector<TextV
             const int xl = stageTexts(texts, first, nC, off);
             totalLaunches += static_cast<uint64_t>(xl);
             packLaunches += static_cast<uint64_t>(xl);
+            lastOffsets = off;  // mbgcg_copy_staged_text describes the texts that are on the device NOW
+            lastLens.resize(nC);
+            for (int c = 0; c < nC; c++) lastLens[c] = texts[first + c].len;
             b.text = dText;
             b.matches = reinterpret_cast<const TextMatchRec*>(dPackIn + oM);
             b.matchOff = reinterpret_cast<const uint32_t*>(dPackIn + oMOff);
@@ -253,10 +256,13 @@ void B200SparseEMMatcher::packBatch(const PackParams& p, const std::vector<TextV
             check(cudaEventRecord(pkEv[2], stream), "event");
             check(cudaStreamSynchronize(stream), "pack sync");
             // a sweep that still changed something means the fixed point was not reached: run again with more sweeps
-            const bool remOpen = nM && p.enableExt && hFlags[std::min(remSweeps - 1, 15)];
-            const bool claimOpen = nM && p.gapDepthOffset > 0 && hFlags[16 + std::min(claimSweeps - 1, 15)];
+            // (slot 15 / 31 belongs to the last sweep alone: earlier sweeps share the other slots)
+            const bool remOpen = nM && p.enableExt && hFlags[15];
+            const bool claimOpen = nM && p.gapDepthOffset > 0 && hFlags[16 + 15];
             if (!remOpen && !claimOpen) break;
-            if (attempt > 24) throw MatcherError(MBGCG_E_CUDA, "stream packing did not reach its fixed point");
+            // a dependency chain is at most as long as the list: more sweeps than matches cannot be needed
+            if (attempt > 24 || static_cast<uint64_t>(std::max(remSweeps, claimSweeps)) > 2ull * nM + 4)
+                throw MatcherError(MBGCG_E_CUDA, "stream packing did not reach its fixed point");
             if (remOpen) remSweeps *= 2;
             if (claimOpen) claimSweeps *= 2;
         }
