@@ -162,6 +162,38 @@ int64_t mbo_copmem_rc_matches(const uint8_t* seq, uint64_t N, uint32_t L, uint32
 uint64_t mbo_rc_match_sequence(uint8_t* seq, uint64_t N, uint32_t targetMatchLength, uint32_t minMatchLength, uint8_t* mapOff,
                                uint64_t* mapOffLen, uint8_t* mapLen, uint64_t* mapLenLen, uint64_t* nMatchesRaw);
 
+/* ---- row f4: the decoder's match-copy path (mbgccoder/MBGC_Decoder.cpp:243-675), oracle/mbgc_oracle_dec.c ---- */
+typedef struct {
+    const uint8_t* literals; uint64_t nLiterals;   /* literalStr (after restoreRCMatchedSequence in mode 3) */
+    const uint8_t* mapOff;   uint64_t nMapOff;     /* mapOffStream: u32 LE per match that carries its offset */
+    const uint8_t* mapOff5;  uint64_t nMapOff5;    /* mapOff5thByteStream (only read when refTotalLength > UINT32_MAX) */
+    const uint8_t* mapLen;   uint64_t nMapLen;     /* mapLenStream as archived: u32 each, or frugal u16/u32/u64 words */
+    const uint8_t* gapDelta; uint64_t nGapDelta;   /* gapDeltaStr */
+    const uint8_t* gapFlags; uint64_t nGapFlags;   /* gapMismatchesFlagsStr */
+} mbo_dec_streams_t;
+typedef struct mbo_decoder mbo_decoder;
+/* the streams are borrowed; refTotalLength as archived (MBGC_Decoder.cpp:1309-1311) */
+mbo_decoder* mbo_dec_create(const mbo_pack_params_t* p, uint64_t refTotalLength, int rcInReference,
+                            int contigsIndividuallyReversed, const mbo_dec_streams_t* s);
+void mbo_dec_destroy(mbo_decoder* d);
+/* coders/ContextAwareMismatchesCoder.cpp:29-34 */
+uint8_t mbo_code2mismatch(uint8_t actual, uint8_t code);
+/* MBGC_Decoder.cpp:243-262 / :264-317 */
+void mbo_dec_init_reference(mbo_decoder* d);
+uint64_t mbo_dec_decode_reference(mbo_decoder* d, uint32_t seqCount, uint8_t* out, uint64_t* contigLens);
+/* MBGC_Decoder.cpp:319-432 (+ extendMatchRight :434-462, extendMatchLeft :464-527) */
+uint64_t mbo_dec_decode_sequence(mbo_decoder* d, uint64_t refLockPos, uint8_t* dest, uint64_t* unmatchedOut);
+/* MBGC_Decoder.cpp:651-675 */
+void mbo_dec_load_ref(mbo_decoder* d, const uint8_t* seqText, uint64_t seqLength, uint64_t refLockPos, int loadRCRef);
+/* MBGC_Decoder.cpp:532-649, sequences only */
+uint64_t mbo_dec_decode_target(mbo_decoder* d, uint32_t seqCount, int unmatchedFractionFactor, int unmatchedFractionRCFactor,
+                               uint64_t refLockPos, uint8_t* out, uint64_t* contigLens, uint64_t* contigUnmatched);
+const uint8_t* mbo_dec_ref(const mbo_decoder* d);
+uint64_t mbo_dec_ref_pos(const mbo_decoder* d);
+int mbo_dec_reached_count(const mbo_decoder* d);
+/* literal position, offsets read, 5th bytes read, lengths read, gap deltas read, flag position */
+void mbo_dec_cursors(const mbo_decoder* d, uint64_t out6[6]);
+
 #ifdef __cplusplus
 }
 #endif
