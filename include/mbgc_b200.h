@@ -349,6 +349,48 @@ void mbgcg_set_host_mirror(mbgcg_t* h, int on);
 int mbgcg_rc_match_sequence(mbgcg_t* h, uint8_t* seq, uint64_t n, uint32_t targetMatchLength, uint32_t minMatchLength, uint64_t* newLen,
                             uint8_t* mapOff, uint64_t* mapOffLen, uint8_t* mapLen, uint64_t* mapLenLen, float deviceMs[2]);
 
+/* ---- the decoder's match-copy path (row f4 of SURVEY.md 8) -------------------------------------------------------------
+ * What MBGC_Decoder does between "the streams are decompressed" and "the DNA of every file is in memory"
+ * (/root/reference/mbgccoder/MBGC_Decoder.cpp: initReference :243-262 or decodeReference :264-317 for G0, then per target
+ * decodeTarget :532-649 = per contig decodeSequenceAndReturnUnmatchedChars :319-432 with extendMatchRight / extendMatchLeft
+ * :434-527, the extension decision of matching/MGMP_Params.h:179-190 and loadRef :651-675).  Headers, line breaks, file output,
+ * lazy / filtered extraction and the back-end coders stay with the caller.  All targets are parsed at once on the device and
+ * written in as few launches as the growth of the reference allows. */
+typedef struct {
+    const uint8_t* stream[MBGCG_S_COUNT];  /* HOST: literalStr (after restoreRCMatchedSequence in mode 3), mapOffStream,
+                                            * mapOff5thByteStream, mapLenStream (as archived), gapDeltaStr, gapMismatchesFlagsStr */
+    uint64_t streamLen[MBGCG_S_COUNT];
+    uint64_t refTotalLength;               /* readStats :1309-1311 */
+    int32_t g0IsTarget;                    /* params->g0IsTarget: initReference (the first contig seeds the reference, file 0 is a
+                                            * target) instead of decodeReference (G0 = g0SeqCount verbatim contigs) */
+    uint32_t g0SeqCount;
+    int32_t rcInReference;                 /* !isRCinReferenceDisabled() */
+    int32_t contigsIndividuallyReversed;   /* params->contigsIndivduallyReversed */
+    uint32_t nTargets;
+    const uint32_t* seqCounts;             /* [nTargets] seqsCountArr of the targets */
+    const uint8_t* unmatchedFractionFactors; /* [2 * nTargets] as archived (factor, RC factor) */
+    const uint64_t* lockPos;               /* [nTargets] matchingLocksPosArr, or NULL (= refTotalLength, :587) */
+} mbgcg_decode_input_t;
+typedef struct {
+    uint64_t nContigs;                 /* decoded contigs in output order: G0's (decodeReference only), then every target's */
+    const uint64_t* contigLen;         /* handle-owned, valid until the next decode call */
+    const uint64_t* contigUnmatched;   /* unmatchedChars of decodeSequenceAndReturnUnmatchedChars (0 for verbatim G0 contigs) */
+    uint64_t dnaLen;                   /* sum of contigLen */
+    uint64_t refPos;                   /* the decoder's refPos and reachedRefLengthCount after the last target */
+    int32_t reachedRefLengthCount;
+    uint32_t batches;                  /* launches of the copy pass */
+    float parseMs, copyMs;             /* CUDA events: uploads + markers + parse; copy pass + reference growth */
+    uint64_t launches;
+} mbgcg_decode_result_t;
+/* p: the fields the decoder reads (extensions, gap depths, lazy support, frugal lengths, the four score values) */
+int mbgcg_decode_targets(mbgcg_t* h, const mbgcg_pack_params_t* p, const mbgcg_decode_input_t* in, mbgcg_decode_result_t* out);
+/* contigs [first, first + n) of the last decode call, back to back, to HOST memory (pinned memory travels at PCIe speed) */
+int mbgcg_decode_fetch(mbgcg_t* h, uint64_t firstContig, uint64_t n, uint8_t* dst);
+/* the same contigs where they are: a device pointer to contig `firstContig` (valid until the next decode call) */
+const void* mbgcg_decode_device_dna(mbgcg_t* h, uint64_t firstContig);
+/* bytes [pos, pos + n) of the decoder's reference buffer (refStr) to HOST memory */
+int mbgcg_decode_fetch_ref(mbgcg_t* h, uint64_t pos, uint64_t n, uint8_t* dst);
+
 /* ---- the two legacy symbol packers the reference carries (row a14 of SURVEY.md 8; no live call site in MBGC) ----
  * SymbolsPackingFacility::packSequence (/root/reference/coders/SymbolsPackingFacility.cpp:123-139, packSuffixSymbols
  * :149-159): symbols of an alphabet of nSymbols letters (`symbols`, in order), as many per byte as fit -- 4 for ACGT,

@@ -12,9 +12,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmbgc_b200.so")
-SOURCES = ["kernels.cu", "pack.cu", "ingest.cu", "coders.cu", "coders.cpp", "rcmatch.cu", "rcmatch.cpp", "matcher.cpp", "packer.cpp", "ingest.cpp", "collection.cpp", "capi.cpp"]
+SOURCES = ["kernels.cu", "pack.cu", "ingest.cu", "coders.cu", "coders.cpp", "rcmatch.cu", "rcmatch.cpp", "decode.cu", "decode.cpp", "matcher.cpp", "packer.cpp", "ingest.cpp", "collection.cpp", "capi.cpp"]
 HOST_SOURCES = ["hostpack.cpp"]  # plain g++ (AVX2 via function targets), linked into the same library
-HEADERS = ["kernels.h", "pack.h", "ingest.h", "coders.h", "rcmatch.h", "matcher.hpp", "collection.hpp", "hostpack.hpp", os.path.join("..", "..", "include", "mbgc_b200.h")]
+HEADERS = ["kernels.h", "pack.h", "ingest.h", "coders.h", "rcmatch.h", "decode.h", "decode.hpp", "matcher.hpp", "collection.hpp", "hostpack.hpp", os.path.join("..", "..", "include", "mbgc_b200.h")]
 CXX = os.environ.get("CXX_HOST", "/usr/bin/g++")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -5,6 +5,7 @@
 
 #include "../../include/mbgc_b200.h"
 #include "collection.hpp"
+#include "decode.hpp"
 #include "matcher.hpp"
 
 using mbgc_b200::B200SparseEMMatcher;
@@ -29,6 +30,7 @@ struct mbgcg {
     ReplicaSet* rs = nullptr;            // the replicas (one per device); m = replica 0
     B200SparseEMMatcher* m = nullptr;
     SequentialPass* pass = nullptr;      // the collection pass in progress, if any
+    mbgc_b200::Decoder* dec = nullptr;   // the last decode call (its DNA and reference stay on the device)
     struct RunResult {                    // what mbgcg_seq_run accumulates (valid until mbgcg_seq_end)
         std::string stream[MBGCG_S_COUNT];
         std::vector<uint64_t> seqCounts, dnaLineLens, refExtSizes, lockPos;
@@ -97,6 +99,7 @@ int mbgcg_device_count(const mbgcg_t* h) { return h->rs->size(); }
 void mbgcg_destroy(mbgcg_t* h) {
     if (!h) return;
     delete h->pass;
+    delete h->dec;
     delete h->rs;   // owns the matchers
     delete h;
 }
@@ -350,6 +353,76 @@ int mbgcg_rc_match_sequence(mbgcg_t* h, uint8_t* seq, uint64_t n, uint32_t targe
             throw MatcherError(MBGCG_E_PARAM, "rc_match_sequence: null argument");
         *newLen = mbgc_b200::rc_match_sequence(h->m, seq, n, targetMatchLength, minMatchLength, mapOff, mapOffLen, mapLen, mapLenLen,
                                               deviceMs, nullptr);
+    });
+}
+
+// ---- the decoder's match-copy path (row f4) ---------------------------------------------------------------------------------
+int mbgcg_decode_targets(mbgcg_t* h, const mbgcg_pack_params_t* p, const mbgcg_decode_input_t* in, mbgcg_decode_result_t* out) {
+    if (!out) return MBGCG_E_PARAM;
+    std::memset(out, 0, sizeof(*out));
+    return guarded(h, [&] {
+        if (!p || !in) throw MatcherError(MBGCG_E_PARAM, "decode_targets: null argument");
+        if (in->nTargets && (!in->seqCounts || !in->unmatchedFractionFactors))
+            throw MatcherError(MBGCG_E_PARAM, "decode_targets: sequence counts and extension factors are required");
+        mbgc_b200::DecodeStreamsHost hs{};
+        for (int i = 0; i < MBGCG_S_COUNT; i++) {
+            if (in->streamLen[i] && !in->stream[i]) throw MatcherError(MBGCG_E_PARAM, "decode_targets: a stream without data");
+            hs.p[i] = in->stream[i];
+            hs.n[i] = in->streamLen[i];
+        }
+        mbgc_b200::DcParams dp{};
+        dp.enableExt = p->enableExtensionsWithMismatches;
+        dp.gapDepthOffset = p->gapDepthOffsetEncoding;
+        dp.gapDepthMismatches = p->gapDepthMismatchesEncoding;
+        dp.lazy = p->lazyDecompressionSupport;
+        dp.initialScore = p->mmsMismatchesInitialScore;
+        dp.scoreThreshold = p->mmsMismatchesScoreThreshold;
+        dp.mismatchPenalty = p->mmsMismatchPenalty;
+        dp.matchBonus = p->mmsMatchBonus;
+        dp.refTotalLength = in->refTotalLength;
+        mbgc_b200::DecodeLayout L{};
+        L.refTotalLength = in->refTotalLength;
+        L.g0IsTarget = in->g0IsTarget;
+        L.g0SeqCount = in->g0SeqCount;
+        L.rcInReference = in->rcInReference;
+        L.contigsIndividuallyReversed = in->contigsIndividuallyReversed;
+        L.frugalLen = p->frugal64bitLenEncoding;
+        L.nTargets = in->nTargets;
+        L.seqCounts = in->seqCounts;
+        L.factors = in->unmatchedFractionFactors;
+        L.lockPos = in->lockPos;
+        if (!h->dec) h->dec = new mbgc_b200::Decoder(h->m);
+        h->dec->run(dp, hs, L);
+        const mbgc_b200::Decoder& d = *h->dec;
+        out->nContigs = d.contigLen.size() - d.firstOutputContig;
+        out->contigLen = d.contigLen.data() + d.firstOutputContig;
+        out->contigUnmatched = d.contigUnmatched.data() + d.firstOutputContig;
+        out->dnaLen = d.dnaLen - d.contigBase[d.firstOutputContig];
+        out->refPos = d.refPos;
+        out->reachedRefLengthCount = d.reachedCount;
+        out->batches = d.batches;
+        out->parseMs = d.ms[0];
+        out->copyMs = d.ms[1];
+        out->launches = d.launches;
+    });
+}
+int mbgcg_decode_fetch(mbgcg_t* h, uint64_t firstContig, uint64_t n, uint8_t* dst) {
+    return guarded(h, [&] {
+        if (!h->dec) throw MatcherError(MBGCG_E_PARAM, "decode_fetch: no decode call on this handle");
+        if (!dst && n) throw MatcherError(MBGCG_E_PARAM, "decode_fetch: null destination");
+        if (firstContig + n >= (1ull << 31)) throw MatcherError(MBGCG_E_PARAM, "decode_fetch: contig range");
+        h->dec->fetch(static_cast<uint32_t>(firstContig + h->dec->firstOutputContig), static_cast<uint32_t>(n), dst);
+    });
+}
+const void* mbgcg_decode_device_dna(mbgcg_t* h, uint64_t firstContig) {
+    if (!h || !h->dec || firstContig + h->dec->firstOutputContig >= h->dec->contigBase.size()) return nullptr;
+    return h->dec->deviceDna() + h->dec->contigBase[firstContig + h->dec->firstOutputContig];
+}
+int mbgcg_decode_fetch_ref(mbgcg_t* h, uint64_t pos, uint64_t n, uint8_t* dst) {
+    return guarded(h, [&] {
+        if (!h->dec) throw MatcherError(MBGCG_E_PARAM, "decode_fetch_ref: no decode call on this handle");
+        if (!dst && n) throw MatcherError(MBGCG_E_PARAM, "decode_fetch_ref: null destination");
+        h->dec->fetchRef(pos, n, dst);
     });
 }
 

@@ -51,6 +51,21 @@ class PackParams(C.Structure):
                           125, 500, 50, 50, 0, 256)
 
 
+class DecodeInput(C.Structure):
+    """mbgcg_decode_input_t"""
+    _fields_ = [("stream", C.c_void_p * 6), ("streamLen", C.c_uint64 * 6), ("refTotalLength", C.c_uint64), ("g0IsTarget", C.c_int32),
+                ("g0SeqCount", C.c_uint32), ("rcInReference", C.c_int32), ("contigsIndividuallyReversed", C.c_int32),
+                ("nTargets", C.c_uint32), ("seqCounts", C.POINTER(C.c_uint32)), ("unmatchedFractionFactors", C.POINTER(C.c_uint8)),
+                ("lockPos", C.POINTER(C.c_uint64))]
+
+
+class DecodeResult(C.Structure):
+    """mbgcg_decode_result_t"""
+    _fields_ = [("nContigs", C.c_uint64), ("contigLen", C.POINTER(C.c_uint64)), ("contigUnmatched", C.POINTER(C.c_uint64)),
+                ("dnaLen", C.c_uint64), ("refPos", C.c_uint64), ("reachedRefLengthCount", C.c_int32), ("batches", C.c_uint32),
+                ("parseMs", C.c_float), ("copyMs", C.c_float), ("launches", C.c_uint64)]
+
+
 class SeqConfig(C.Structure):
     """mbgcg_seq_config_t: what the sequential target schedule reads from MGMP_Params / MBGC_Params"""
     _fields_ = [("pack", PackParams), ("minMatchLength", C.c_uint32), ("unmatchedFractionFactor", C.c_int32),
@@ -150,6 +165,14 @@ def load_library():
     L.mbgcg_set_host_mirror.argtypes = [vp, C.c_int]
     L.mbgcg_rc_match_sequence.restype = C.c_int
     L.mbgcg_rc_match_sequence.argtypes = [vp, vp, C.c_uint64, C.c_uint32, C.c_uint32, u64p, vp, u64p, vp, u64p, C.POINTER(C.c_float)]
+    L.mbgcg_decode_targets.restype = C.c_int
+    L.mbgcg_decode_targets.argtypes = [vp, C.POINTER(PackParams), C.POINTER(DecodeInput), C.POINTER(DecodeResult)]
+    L.mbgcg_decode_fetch.restype = C.c_int
+    L.mbgcg_decode_fetch.argtypes = [vp, C.c_uint64, C.c_uint64, vp]
+    L.mbgcg_decode_device_dna.restype = vp
+    L.mbgcg_decode_device_dna.argtypes = [vp, C.c_uint64]
+    L.mbgcg_decode_fetch_ref.restype = C.c_int
+    L.mbgcg_decode_fetch_ref.argtypes = [vp, C.c_uint64, C.c_uint64, vp]
     L.mbgcg_symbols_pack.restype = C.c_int
     L.mbgcg_symbols_pack.argtypes = [vp, C.c_char_p, C.c_int, vp, C.c_uint64, vp, u64p]
     L.mbgcg_symbols_unpack.restype = C.c_int
@@ -261,6 +284,53 @@ class Matcher:
         self._check(self.lib.mbgcg_rc_match_sequence(self.h, s.ctypes.data if s.size else None, s.size, targetMatchLength, minMatchLength,
                                                      C.byref(n), off.ctypes.data, C.byref(no), ln.ctypes.data, C.byref(nl), ms))
         return s[:n.value].copy(), off[:no.value].copy(), ln[:nl.value].copy(), {"index_ms": ms[0], "query_ms": ms[1]}
+
+    # -- row f4: the decoder's match-copy path (mbgccoder/MBGC_Decoder.cpp:243-675) ----------------------------------------------
+    def decodeTargets(self, params, streams, refTotalLength, seqCounts, factors, g0IsTarget=True, g0SeqCount=0, rcInReference=True,
+                      contigsIndividuallyReversed=True, lockPos=None, fetch=True):
+        """streams: the six streams (bytes / uint8 arrays) in MBGCG_S_* order; seqCounts: contigs per target; factors:
+        (unmatchedFractionFactor, unmatchedFractionRCFactor) per target or one pair for all.
+        -> dict(contigs=[uint8 arrays], lens, unmatched, refPos, reached, batches, launches, parse_ms, copy_ms)"""
+        keep = [_as_u8(x) for x in streams]
+        inp = DecodeInput()
+        for i, a in enumerate(keep):
+            inp.stream[i] = a.ctypes.data if a.size else None
+            inp.streamLen[i] = a.size
+        n = len(seqCounts)
+        cnt = (C.c_uint32 * max(n, 1))(*seqCounts)
+        fac = np.asarray(factors, dtype=np.uint8).reshape(-1)
+        if fac.size == 2:
+            fac = np.tile(fac, max(n, 1))
+        fac = np.ascontiguousarray(fac)
+        inp.refTotalLength = refTotalLength
+        inp.g0IsTarget = 1 if g0IsTarget else 0
+        inp.g0SeqCount = g0SeqCount
+        inp.rcInReference = 1 if rcInReference else 0
+        inp.contigsIndividuallyReversed = 1 if contigsIndividuallyReversed else 0
+        inp.nTargets = n
+        inp.seqCounts = cnt
+        inp.unmatchedFractionFactors = fac.ctypes.data_as(C.POINTER(C.c_uint8))
+        lk = None
+        if lockPos is not None:
+            lk = (C.c_uint64 * max(n, 1))(*lockPos)
+            inp.lockPos = lk
+        res = DecodeResult()
+        self._check(self.lib.mbgcg_decode_targets(self.h, C.byref(params), C.byref(inp), C.byref(res)))
+        k = res.nContigs
+        lens = np.ctypeslib.as_array(res.contigLen, shape=(k,)).copy() if k else np.zeros(0, dtype=np.uint64)
+        unm = np.ctypeslib.as_array(res.contigUnmatched, shape=(k,)).copy() if k else np.zeros(0, dtype=np.uint64)
+        out = dict(lens=lens, unmatched=unm, refPos=res.refPos, reached=res.reachedRefLengthCount, batches=res.batches,
+                   launches=res.launches, parse_ms=res.parseMs, copy_ms=res.copyMs, dnaLen=res.dnaLen)
+        if fetch:
+            dna = np.empty(max(int(res.dnaLen), 1), dtype=np.uint8)
+            self._check(self.lib.mbgcg_decode_fetch(self.h, 0, k, dna.ctypes.data))
+            out["contigs"] = np.split(dna[:res.dnaLen], np.cumsum(lens)[:-1].astype(np.int64)) if k else []
+        return out
+
+    def decodeFetchRef(self, pos, n):
+        out = np.empty(max(n, 1), dtype=np.uint8)
+        self._check(self.lib.mbgcg_decode_fetch_ref(self.h, pos, n, out.ctypes.data))
+        return out[:n]
 
     # -- row a14: the reference's legacy symbol packers (coders/SymbolsPackingFacility.cpp, coders/VarLenDNACoder.cpp) ------
     def packSymbols(self, symbols, src):
