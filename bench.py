@@ -60,6 +60,7 @@ def parse_args():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--batches", type=int, default=2, help="distinct batches the timed steps rotate through")
     ap.add_argument("--long-seconds", type=float, default=1.0, help="length of the additional long timed region")
+    ap.add_argument("--no-decode", action="store_true", help="skip the decoder leg (row f4: collection pass -> streams -> device decode)")
     ap.add_argument("--no-collection", action="store_true", help="skip the C3 collection pass (1k genomes, strong scaling)")
     ap.add_argument("--collection-genomes", type=int, default=1000)
     ap.add_argument("--collection-length", type=int, default=4_900_000)
@@ -543,9 +544,12 @@ def measure_tier(args, tier, rank, world, dist, local):
     ks = max(1, min(16, n))
     lists_sample = m.matchBatchDevice(dbuf.data_ptr(), offs[:ks], lens[:ks], 32)  # copies, for the CPU pack baseline
     state = m.state()
+    decode = None
+    if not args.no_decode:
+        decode = measure_decode(args, m, base, targets, rank)
     out = dict(base=base, targets=targets, limit=limit, sm=sm, n=n, lens=lens, fbytes=fbytes, index_s=index_s, pack=pack,
                index_tm=index_tm, index_warm=index_warm, long_run=long_run, wire=wire, covered_dev=covered_dev, covered_e2e=covered_e2e, nb=nb,
-               ingest=ingest,
+               ingest=ingest, decode=decode,
                lists_sample=lists_sample,
                ms_dev=ms_dev, stage_dev=stage_dev, launches=launches, n_matches=n_matches, counters=counters,
                ms_e2e=ms_e2e, stage_e2e=stage_e2e, table_slots=state["hashSize"], ref_bytes=int(state["pos1"]))
@@ -553,6 +557,62 @@ def measure_tier(args, tier, rank, world, dist, local):
     del dbuf, dev
     torch.cuda.empty_cache()
     return out
+
+
+def measure_decode(args, m, base, targets, rank):
+    """Row f4: the batch goes through the collection pass (one FASTA image per genome, the reference's sequential schedule)
+    and the streams it leaves are decoded again on the device (mbgcg_decode_targets) -- an encode -> decode round trip at the
+    bench's full size, every decoded contig compared with the genome it came from.  Runs last: the pass appends separators
+    (and, on the divergent tier, the genomes themselves) to the matcher's reference."""
+    import torch
+    from mbgc_b200.matcher import STREAM_NAMES, SeqConfig
+
+    cfg = SeqConfig.for_mode(args.mode)
+    images = [fasta_image([t], rank * len(targets) + 1 + i) for i, t in enumerate(targets)]
+    t0 = time.perf_counter()
+    streams, info = m.compressSequential(images, cfg)
+    enc_s = time.perf_counter() - t0
+    del images
+    sep = bytes([(ord('"') + 128) & 0xFF])
+    full = [base.tobytes() + sep + streams["literals"]] + [streams[k] for k in STREAM_NAMES[1:]]
+    ref_total = m.getRefLength()
+    factors = (cfg.unmatchedFractionFactor, cfg.unmatchedFractionRCFactor)
+
+    def run():
+        t0 = time.perf_counter()
+        r = m.decodeTargets(cfg.pack, full, ref_total, info["seqCounts"], factors, g0IsTarget=False, g0SeqCount=1,
+                            lockPos=info["lockPos"], fetch=False)
+        r["wall_s"] = time.perf_counter() - t0
+        return r
+
+    run()
+    runs = [run() for _ in range(3)]
+    best = min(runs, key=lambda r: r["parse_ms"] + r["copy_ms"])
+    dna = int(best["dnaLen"])
+    # the decoded contigs back on the host (pinned), compared with what went in
+    host = torch.empty(max(dna, 1), dtype=torch.uint8).pin_memory()
+    t0 = time.perf_counter()
+    m._check(m.lib.mbgcg_decode_fetch(m.h, 0, len(best["lens"]), host.data_ptr()))
+    d2h_s = time.perf_counter() - t0
+    got = host.numpy()
+    at, ok = 0, int(best["lens"][0]) == base.size and bool(np.array_equal(got[:base.size], base))
+    at = base.size
+    for t, ln in zip(targets, best["lens"][1:]):
+        ok = ok and int(ln) == t.size and bool(np.array_equal(got[at:at + t.size], t))
+        at += int(ln)
+    if not ok:
+        raise RuntimeError("decode round trip: the decoded contigs differ from the genomes that were encoded")
+    dev_ms = best["parse_ms"] + best["copy_ms"]
+    sb = {k: len(v) for k, v in zip(STREAM_NAMES, full)}
+    return {"what": "row f4: the six streams of this batch (collection pass, sequential schedule) decoded on the device "
+                    "(MBGC_Decoder::decodeTarget for all targets at once); round trip checked byte for byte against the genomes",
+            "dna_bytes": dna, "stream_bytes": sb, "contigs": len(best["lens"]), "copy_batches": int(best["batches"]),
+            "launches": int(best["launches"]), "parse_ms": best["parse_ms"], "copy_ms": best["copy_ms"],
+            "value": dna / (dev_ms / 1e3) / 1e9, "unit": "GB/s of DNA written (CUDA events: stream upload + markers + parse + copy pass)",
+            "copy_pass_gbs": dna / (max(best["copy_ms"], 1e-6) / 1e3) / 1e9,
+            "copy_pass_hbm_bytes": 2 * dna, "wall_ms": min(r["wall_s"] for r in runs) * 1e3,
+            "d2h_ms": d2h_s * 1e3, "e2e_value": dna / (min(r["wall_s"] for r in runs) + d2h_s) / 1e9,
+            "encode_pass_s": enc_s, "round_trip_ok": True}
 
 
 def collection_dir(args):
@@ -766,6 +826,8 @@ def run_b200(args, rank, world):
         return p
 
     line["pack"] = pack_report(r, world)
+    if r.get("decode"):
+        line["decode"] = r["decode"]
     if r["ingest"]:
         image = r["ingest"].pop("image")
         line["ingest"] = r["ingest"]
@@ -815,6 +877,8 @@ def run_b200(args, rank, world):
             "chunks": o["counters"]["chunks"], "lanes_full_probe": o["counters"]["lanes_full_probe"],
             "stage_frac": ALG_BYTES_PER_POSITION * o["counters"]["positions"] / (okern / 1e3) / 1e9 / peak,
             "stage_ms": o["stage_dev"], "pack": pack_report(o, world)}
+        if o.get("decode"):
+            line["other_tier"]["decode"] = o["decode"]
         if rank == 0 and world == 1 and not args.no_cpu and o["lists_sample"]:
             k = min(4, len(o["lists_sample"]))
             dt, nb = cpu_pack_stage(o["base"], o["targets"][:k], o["lists_sample"][:k], o["limit"], o["sm"], args.mode)

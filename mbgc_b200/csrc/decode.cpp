@@ -31,13 +31,17 @@ constexpr uint64_t REF_SHIFT = 1;
 
 }  // namespace
 
+// the buffers only grow: a decoder that is called again (the next archive, the next block) allocates nothing
 void DevBuf::reset(uint64_t bytes) {
+    if (bytes <= cap) {
+        n = bytes;
+        return;
+    }
     if (p) cudaFree(p);
     p = nullptr;
-    n = 0;
-    if (!bytes) return;
+    n = cap = 0;
     check(cudaMalloc(&p, bytes), "cudaMalloc(decode)");
-    n = bytes;
+    n = cap = bytes;
 }
 
 DevBuf::~DevBuf() {

@@ -272,6 +272,7 @@ struct ParseCtx {
     const DcStreams& s;
     uint64_t litPos, flagsPos;
     bool bad;
+    uint64_t flagWord, flagBase;  // the 8 flag bytes at flagBase (one load per 8 steps of the automaton)
 };
 
 __device__ __forceinline__ int score_step(const DcParams& p, int score, bool mismatch) {
@@ -285,7 +286,12 @@ __device__ __forceinline__ bool read_flag(ParseCtx& x, uint64_t at) {
         x.bad = true;
         return true;
     }
-    return x.s.flags[at] != 0;
+    const uint64_t base = at & ~7ull;
+    if (base != x.flagBase) {  // the stream buffers are 16-byte aligned and padded
+        x.flagBase = base;
+        x.flagWord = *reinterpret_cast<const uint64_t*>(x.s.flags + base);
+    }
+    return ((x.flagWord >> ((at & 7) * 8)) & 0xFF) != 0;
 }
 
 // extendMatchRight (:434-462): returns the extension's length; the segment describes what the copy pass has to write
@@ -380,14 +386,15 @@ __device__ __forceinline__ void put_seg(DcSeg* segs, uint64_t at, const DcSeg& g
     d[1] = q[1];
 }
 
-__global__ void __launch_bounds__(64) k_dc_parse(DcParams p, DcStreams s, DcIndex ix, const DcTarget* __restrict__ targets, uint32_t nTargets,
+// One WARP per target, lane 0 working: 32 targets in one warp would run their (completely divergent) parses one after the other.
+__global__ void __launch_bounds__(32) k_dc_parse(DcParams p, DcStreams s, DcIndex ix, const DcTarget* __restrict__ targets, uint32_t nTargets,
                                                   DcSeg* __restrict__ segs, uint64_t* __restrict__ contigLen,
                                                   uint64_t* __restrict__ contigUnmatched, uint32_t* __restrict__ error) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nTargets) return;
+    const uint32_t t = blockIdx.x;
+    if (t >= nTargets || threadIdx.x) return;
     const DcTarget tg = targets[t];
     int64_t pairedGapOffsetDelta[MAX_GAP_DEPTH];
-    ParseCtx x{p, s, 0, 0, false};
+    ParseCtx x{p, s, 0, 0, false, 0, UINT64_MAX};
     const uint32_t c0 = tg.firstContig;
     x.litPos = c0 ? static_cast<uint64_t>(ix.sepPos[c0 - 1]) + 1 : 0;
     x.flagsPos = (tg.flagIdx == UINT32_MAX || tg.flagIdx == 0) ? 0 : static_cast<uint64_t>(ix.flagSep[tg.flagIdx - 1]) + 1;
@@ -594,39 +601,78 @@ __device__ __forceinline__ void copy_extension(const DcSeg& g, uint8_t* __restri
     }
 }
 
+// One CTA per 16 KiB of output.  The segments that may touch the tile are staged in shared memory a chunk at a time (one
+// coalesced load instead of a chain of dependent ones); long copies are done by the whole CTA, everything else by one warp per
+// segment.  Destinations are disjoint, so the warps never wait for each other.
+constexpr int DC_STAGE = 256;
+
 __global__ void __launch_bounds__(DC_THREADS) k_dc_copy(const DcSeg* __restrict__ segs, uint64_t segEnd, const uint64_t* __restrict__ contigBase,
                                                         const uint32_t* __restrict__ tileSeg, uint64_t tileBegin, uint64_t dstBegin,
                                                         uint64_t dstEnd, const uint8_t* __restrict__ ref, DcStreams s,
                                                         uint8_t* __restrict__ dna) {
+    __shared__ uint4 sSeg[DC_STAGE][2];
+    __shared__ uint64_t sAbs[DC_STAGE];
     const uint64_t tile = tileBegin + blockIdx.x;
     uint64_t lo = tile * DC_TILE, hi = lo + DC_TILE;
     if (lo < dstBegin) lo = dstBegin;
     if (hi > dstEnd) hi = dstEnd;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t small = 0;
-    for (uint64_t si = tileSeg[tile]; si < segEnd; si++) {
-        const uint4* q = reinterpret_cast<const uint4*>(segs + si);
-        const uint4 q0 = q[0], q1 = q[1];
-        DcSeg g;
-        g.dst = q0.x | (static_cast<uint64_t>(q0.y) << 32);
-        g.src = q0.z | (static_cast<uint64_t>(q0.w) << 32);
-        g.len = q1.x; g.flagsPos = q1.y; g.litPos = q1.z; g.meta = q1.w;
-        if (!g.len) continue;
-        const uint64_t a = contigBase[g.meta >> 4] + g.dst;
-        if (a >= hi) break;
-        const uint32_t kind = g.meta & 3;
-        if (kind <= DC_MATCH) {
-            const uint64_t i0 = a > lo ? a : lo;
-            const uint64_t i1 = a + g.len < hi ? a + g.len : hi;
-            if (i1 <= i0) continue;
-            const uint8_t* src = (kind == DC_MATCH ? ref : s.lit) + g.src + (i0 - a);
-            if (i1 - i0 >= 1024)
-                copy_bytes(dna + i0, src, i1 - i0, threadIdx.x, DC_THREADS);
-            else if ((small++ & 7) == static_cast<uint32_t>(warp))
-                copy_bytes(dna + i0, src, i1 - i0, lane, 32);
-        } else if (a >= lo) {  // an extension is written whole by the tile it starts in
-            if ((small++ & 7) == static_cast<uint32_t>(warp)) copy_extension(g, dna + a, ref, s, lane);
+    int chunk = 32;  // most tiles of a near-identical collection lie inside one long match: look at few segments first
+    for (uint64_t base = tileSeg[tile]; base < segEnd; base += chunk, chunk = DC_STAGE) {
+        __syncthreads();
+        if (threadIdx.x < chunk) {
+            const uint64_t si = base + threadIdx.x;
+            uint64_t a = UINT64_MAX;  // behind the list: ends the walk
+            uint4 q0 = make_uint4(0, 0, 0, 0), q1 = make_uint4(0, 0, 0, 0);
+            if (si < segEnd) {
+                const uint4* q = reinterpret_cast<const uint4*>(segs + si);
+                q0 = q[0];
+                q1 = q[1];
+                a = q1.x ? contigBase[q1.w >> 4] + (q0.x | (static_cast<uint64_t>(q0.y) << 32)) : 0;  // empty segments are skipped
+            }
+            sSeg[threadIdx.x][0] = q0;
+            sSeg[threadIdx.x][1] = q1;
+            sAbs[threadIdx.x] = a;
         }
+        __syncthreads();
+        bool done = false;
+        // long copies: every thread
+        for (int k = 0; k < chunk; k++) {
+            const uint4 q1 = sSeg[k][1];
+            const uint64_t a = sAbs[k];
+            if (a == UINT64_MAX || (q1.x && a >= hi)) {
+                done = true;
+                break;
+            }
+            if (!q1.x || (q1.w & 3) > DC_MATCH) continue;
+            const uint64_t i0 = a > lo ? a : lo;
+            const uint64_t i1 = a + q1.x < hi ? a + q1.x : hi;
+            if (i1 <= i0 || i1 - i0 < 1024) continue;
+            const uint4 q0 = sSeg[k][0];
+            const uint64_t src = q0.z | (static_cast<uint64_t>(q0.w) << 32);
+            copy_bytes(dna + i0, ((q1.w & 3) == DC_MATCH ? ref : s.lit) + src + (i0 - a), i1 - i0, threadIdx.x, DC_THREADS);
+        }
+        // short copies and extensions: a warp each
+        for (int k = warp; k < chunk; k += DC_THREADS / 32) {
+            const uint4 q1 = sSeg[k][1];
+            const uint64_t a = sAbs[k];
+            if (a == UINT64_MAX || (q1.x && a >= hi)) break;
+            if (!q1.x) continue;
+            const uint4 q0 = sSeg[k][0];
+            const uint32_t kind = q1.w & 3;
+            const uint64_t src = q0.z | (static_cast<uint64_t>(q0.w) << 32);
+            if (kind <= DC_MATCH) {
+                const uint64_t i0 = a > lo ? a : lo;
+                const uint64_t i1 = a + q1.x < hi ? a + q1.x : hi;
+                if (i1 <= i0 || i1 - i0 >= 1024) continue;
+                copy_bytes(dna + i0, (kind == DC_MATCH ? ref : s.lit) + src + (i0 - a), i1 - i0, lane, 32);
+            } else if (a >= lo) {  // an extension is written whole by the tile it starts in
+                DcSeg g;
+                g.dst = 0; g.src = src; g.len = q1.x; g.flagsPos = q1.y; g.litPos = q1.z; g.meta = q1.w;
+                copy_extension(g, dna + a, ref, s, lane);
+            }
+        }
+        if (done) break;
     }
 }
 
@@ -698,7 +744,7 @@ int launch_dc_len_expand(const uint8_t* src, uint64_t nBytes, uint32_t* chunkMap
 int launch_dc_parse(const DcParams& p, const DcStreams& s, const DcIndex& ix, const DcTarget* targets, uint32_t nTargets, DcSeg* segs,
                     uint64_t* contigLen, uint64_t* contigUnmatched, uint32_t* error, cudaStream_t st) {
     if (!nTargets) return 0;
-    k_dc_parse<<<blocks_for(nTargets, 64), 64, 0, st>>>(p, s, ix, targets, nTargets, segs, contigLen, contigUnmatched, error);
+    k_dc_parse<<<nTargets, 32, 0, st>>>(p, s, ix, targets, nTargets, segs, contigLen, contigUnmatched, error);
     return 1;
 }
 

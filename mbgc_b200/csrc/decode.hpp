@@ -28,7 +28,7 @@ struct DecodeLayout {  // what the archive's header and side streams say (MBGC_D
 
 struct DevBuf {
     void* p = nullptr;
-    uint64_t n = 0;
+    uint64_t n = 0, cap = 0;
     DevBuf() = default;
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
