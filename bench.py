@@ -61,6 +61,7 @@ def parse_args():
     ap.add_argument("--batches", type=int, default=2, help="distinct batches the timed steps rotate through")
     ap.add_argument("--long-seconds", type=float, default=1.0, help="length of the additional long timed region")
     ap.add_argument("--no-decode", action="store_true", help="skip the decoder leg (row f4: collection pass -> streams -> device decode)")
+    ap.add_argument("--no-c4", action="store_true", help="skip the mode-3 run of the collection (C4: C3 + the reverse-complement pass)")
     ap.add_argument("--no-collection", action="store_true", help="skip the C3 collection pass (1k genomes, strong scaling)")
     ap.add_argument("--collection-genomes", type=int, default=1000)
     ap.add_argument("--collection-length", type=int, default=4_900_000)
@@ -559,6 +560,85 @@ def measure_tier(args, tier, rank, world, dist, local):
     return out
 
 
+def cpu_decode_stage(cfg, full, ref_total, seq_counts, factors, locks, g0_count, n_sample):
+    """The reference's own decoder (MBGC_Decoder<false>::decodeReference + decodeTarget, oracle/_ref/libref_decoder.so) on the
+    first n_sample targets of the same streams, one host thread (the stock sequential decoder; its parallel mode is the
+    lazy one and needs region separators to find independent targets).  Falls back to the oracle port.  -> (seconds, bytes, kind)"""
+    ref_so = os.path.join(ROOT, "oracle", "_ref", "libref_decoder.so")
+    u8p = C.POINTER(C.c_uint8)
+    arrs = [np.frombuffer(x, dtype=np.uint8) if len(x) else np.zeros(8, dtype=np.uint8) for x in full]
+    n = len(seq_counts)
+    k = max(1, min(n_sample, n))
+    pk = cfg.pack
+    if os.path.exists(ref_so):
+        L = C.CDLL(ref_so)
+        L.refd_create.restype = C.c_void_p
+        L.refd_create.argtypes = [C.POINTER(C.c_int), C.c_uint64] + [u8p, C.c_uint64] * 6 + [C.POINTER(C.c_uint32), u8p, C.POINTER(C.c_uint64), C.c_uint32]
+        L.refd_destroy.argtypes = [C.c_void_p]
+        L.refd_decode_reference.argtypes = [C.c_void_p]
+        L.refd_decode_target.restype = C.c_uint64
+        L.refd_decode_target.argtypes = [C.c_void_p, C.c_uint32, u8p, C.c_uint64]
+        pp = (C.c_int * 11)(pk.enableExtensionsWithMismatches, pk.gapDepthOffsetEncoding, pk.gapDepthMismatchesEncoding,
+                            pk.lazyDecompressionSupport, pk.frugal64bitLenEncoding, pk.mmsMismatchesInitialScore,
+                            pk.mmsMismatchesScoreThreshold, pk.mmsMismatchPenalty, pk.mmsMatchBonus, 1, 1)
+        args_ = []
+        for a, x in zip(arrs, full):
+            args_ += [a.ctypes.data_as(u8p), len(x)]
+        counts = (C.c_uint32 * (n + 1))(g0_count, *seq_counts)
+        fac = np.array(list(factors) * n, dtype=np.uint8)
+        lk = (C.c_uint64 * n)(*locks)
+        h = L.refd_create(pp, ref_total, *args_, counts, fac.ctypes.data_as(u8p), lk, n)
+        cap = 64 << 20
+        out = np.empty(cap, dtype=np.uint8)
+        t0 = time.perf_counter()
+        L.refd_decode_reference(h)
+        total = 0
+        for t in range(k):
+            total += L.refd_decode_target(h, t, out.ctypes.data_as(u8p), cap)
+        dt = time.perf_counter() - t0
+        L.refd_destroy(h)
+        return dt, int(total), "reference"
+    subprocess.run(["make", "-s", "oracle"], cwd=os.path.join(ROOT, "oracle"), check=True)
+    L = C.CDLL(os.path.join(ROOT, "oracle", "libmbgc_oracle.so"))
+
+    class PP(C.Structure):
+        _fields_ = [(x, C.c_int) for x in ("a", "b", "c", "d", "e", "f", "g", "h", "i", "j", "k", "l", "m", "n")]
+
+    class DS(C.Structure):
+        _fields_ = [(f"x{i}", t) for i in range(6) for t in (u8p, C.c_uint64)]
+    pp = PP(pk.enableExtensionsWithMismatches, int(pk.gapBreakingMatchMinLength), pk.gapDepthOffsetEncoding, pk.gapDepthMismatchesEncoding,
+            pk.lazyDecompressionSupport, pk.frugal64bitLenEncoding, pk.enable40bitReference, pk.mismatchesWithExclusion,
+            pk.mmsMismatchesInitialScore, pk.mmsMismatchesScoreThreshold, pk.mmsMismatchPenalty, pk.mmsMatchBonus, 32, factors[0])
+    ds = DS()
+    for i, (a, x) in enumerate(zip(arrs, full)):
+        setattr(ds, f"x{2 * i}", a.ctypes.data_as(u8p))
+        setattr(ds, f"x{2 * i + 1}", len(x))
+    L.mbo_dec_create.restype = C.c_void_p
+    L.mbo_dec_create.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p]
+    L.mbo_dec_destroy.argtypes = [C.c_void_p]
+    L.mbo_dec_decode_reference.restype = C.c_uint64
+    L.mbo_dec_decode_reference.argtypes = [C.c_void_p, C.c_uint32, u8p, C.POINTER(C.c_uint64)]
+    L.mbo_dec_decode_target.restype = C.c_uint64
+    L.mbo_dec_decode_target.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_uint64, u8p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    d = L.mbo_dec_create(C.byref(pp), ref_total, 1, 1, C.byref(ds))
+    cap = 64 << 20
+    out = np.empty(cap, dtype=np.uint8)
+    lens = (C.c_uint64 * 64)()
+    unm = (C.c_uint64 * 64)()
+    t0 = time.perf_counter()
+    L.mbo_dec_decode_reference(d, g0_count, out.ctypes.data_as(u8p), lens)
+    total = 0
+    for t in range(k):
+        total += L.mbo_dec_decode_target(d, seq_counts[t], factors[0], factors[1], locks[t], out.ctypes.data_as(u8p), lens, unm)
+    dt = time.perf_counter() - t0
+    L.mbo_dec_destroy(d)
+    return dt, int(total), "port"
+
+
+def args_tier_is_near(best):
+    return best["batches"] <= 4   # a collection that (almost) never extends the reference
+
+
 def measure_decode(args, m, base, targets, rank):
     """Row f4: the batch goes through the collection pass (one FASTA image per genome, the reference's sequential schedule)
     and the streams it leaves are decoded again on the device (mbgcg_decode_targets) -- an encode -> decode round trip at the
@@ -604,7 +684,14 @@ def measure_decode(args, m, base, targets, rank):
         raise RuntimeError("decode round trip: the decoded contigs differ from the genomes that were encoded")
     dev_ms = best["parse_ms"] + best["copy_ms"]
     sb = {k: len(v) for k, v in zip(STREAM_NAMES, full)}
-    return {"what": "row f4: the six streams of this batch (collection pass, sequential schedule) decoded on the device "
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        ks = 24 if args_tier_is_near(best) else 6
+        dt, nb, kind = cpu_decode_stage(cfg, full, ref_total, info["seqCounts"], factors, info["lockPos"], 1, ks)
+        cpu = {"value": nb / dt / 1e9, "unit": "GB/s", "cores": 1, "kind": kind,
+               "sample": f"decodeReference + decodeTarget for the first {min(ks, len(info['seqCounts']))} targets of the same streams, "
+                         f"{nb / 1e6:.0f} MB of output in {dt * 1e3:.0f} ms"}
+    return {"cpu_baseline": cpu, "what": "row f4: the six streams of this batch (collection pass, sequential schedule) decoded on the device "
                     "(MBGC_Decoder::decodeTarget for all targets at once); round trip checked byte for byte against the genomes",
             "dna_bytes": dna, "stream_bytes": sb, "contigs": len(best["lens"]), "copy_batches": int(best["batches"]),
             "launches": int(best["launches"]), "parse_ms": best["parse_ms"], "copy_ms": best["copy_ms"],
@@ -686,6 +773,58 @@ def measure_collection(args, rank, world, dist, local, peak):
                      "wait_staging_ms": st["waitStageMs"], "pageable_bytes": st["pageableBytes"],
                      "stream_bytes": info["stream_bytes"], "reader_threads": readers},
            "generate_s": gen_s, "hbm_frac_of_pass": (1.0 * total_bytes / world) / best / 1e9 / peak}
+    m.close()
+    torch.cuda.empty_cache()
+    if not args.no_c4:
+        out["c4"] = measure_c4(args, rank, world, dist, local, paths, base, limit, readers, total_bytes)
+    return out
+
+
+def measure_c4(args, rank, world, dist, local, paths, base, limit, readers, total_bytes):
+    """C4 of SURVEY.md 8d (BASELINE.json configs[3]): the C3 files in mode 3 -- mode-2 matcher parameters (skip margin 24, RC
+    factor 128) plus the reverse-complement redundancy pass over the archive's literal stream
+    (SimpleSequenceMatcher::rcMatchSequence, MBGC_Encoder.cpp:637-638).  The collection pass is sharded over the ranks as in C3;
+    the literal streams are gathered on rank 0, which runs the RC pass once, as the encoder does."""
+    import torch
+    import mbgc_b200
+    from mbgc_b200.dist import compress_sharded_files, max_over_ranks
+    from mbgc_b200.matcher import SeqConfig
+
+    m = mbgc_b200.Matcher(limit, 32, 16, 1, skip_margin_of(3), device=local)
+    m.disableSlidingWindow()
+    m.loadRef(base, True, True, 0)
+    cfg = SeqConfig.for_mode(3)
+    pos0 = m.getLoadingPosition()
+
+    def one_pass():
+        m.setPosition(pos0, 0)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        streams, info, ext = compress_sharded_files(m, paths, cfg, device="cuda", readers=readers, keep_streams=True)
+        lit = streams["literals"]
+        if dist is not None:
+            parts = [None] * world
+            dist.all_gather_object(parts, lit)
+            lit = b"".join(parts)
+        rc = None
+        if rank == 0:
+            sep = bytes([(ord('"') + 128) & 0xFF])
+            seq, off, ln, tm = m.rcMatchSequence(np.frombuffer(base.tobytes() + sep + lit, dtype=np.uint8), 55)
+            rc = {"literal_bytes_in": len(lit) + base.size + 1, "literal_bytes_out": int(seq.size), "rc_matches": int(off.size // 4),
+                  "index_ms": tm["index_ms"], "query_ms": tm["query_ms"]}
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        return max_over_ranks(dt, "cuda"), info, rc
+
+    one_pass()
+    runs = [one_pass() for _ in range(2)]
+    best = min(x[0] for x in runs)
+    out = {"what": "BASELINE configs[3] (C4): the C3 files in mode 3 -- collection pass sharded over the ranks, then the "
+                   "reverse-complement pass over the gathered literal stream on rank 0 (rcMatchSequence on the device)",
+           "mode": 3, "scaling": "strong", "n_gpus": world, "seconds": [x[0] for x in runs], "value": total_bytes / best / 1e9,
+           "unit": "GB/s", "rc_pass": runs[-1][2], "matches": runs[-1][1]["matches"]}
     m.close()
     torch.cuda.empty_cache()
     return out

@@ -272,26 +272,81 @@ struct ParseCtx {
     const DcStreams& s;
     uint64_t litPos, flagsPos;
     bool bad;
-    uint64_t flagWord, flagBase;  // the 8 flag bytes at flagBase (one load per 8 steps of the automaton)
+    int lane;
 };
 
-__device__ __forceinline__ int score_step(const DcParams& p, int score, bool mismatch) {
-    if (mismatch) return score + p.mismatchPenalty;
-    score -= p.matchBonus;
-    return score < 0 ? 0 : score;
-}
+// The mismatch-score automaton of extendMatchRight / extendMatchLeft over a stretch of the flag stream, 32 flags per step of
+// the WARP (every lane calls this with the same arguments).  One step of the reference's loops is
+//     stop if the step limit is reached, the literal cursor sits at the guard (stopAtGuard), or the score reached the threshold;
+//     read a flag; stop (flag consumed) if it is a mismatch and literal cursor + litBias == guard;
+//     score = mismatch ? score + penalty : max(0, score - bonus); a mismatch moves the literal cursor.
+// The cursor before step i is l0 + (mismatches before i): a ballot.  The score before step i is a Lindley recursion,
+// W_i = P_i + max(W_0, -min_{1<=j<=i} P_j) with P the prefix sums of the +penalty / -bonus steps: two warp scans.
+struct Walk {
+    uint64_t steps;   // complete steps (= flags consumed by them)
+    uint64_t mism;    // mismatches among them
+    bool atGuard;     // stopped by a mismatch flag at the guard (that flag is consumed as well)
+    bool limit;       // stopped by the step limit
+};
 
-__device__ __forceinline__ bool read_flag(ParseCtx& x, uint64_t at) {
-    if (at >= x.s.nFlags) {
-        x.bad = true;
-        return true;
+__device__ Walk warp_walk(ParseCtx& x, uint64_t fp, uint64_t l0, uint64_t guard, uint32_t litBias, uint64_t maxSteps, bool useScore,
+                          bool stopAtGuard) {
+    const int lane = x.lane;
+    const uint32_t lt = (1u << lane) - 1u;
+    Walk w{0, 0, false, false};
+    int s0 = x.p.initialScore;
+    for (;;) {
+        const uint64_t i = w.steps + lane;
+        const bool inRange = fp + i < x.s.nFlags;
+        const bool f = inRange ? x.s.flags[fp + i] != 0 : true;
+        const uint32_t ball = __ballot_sync(0xFFFFFFFFu, f);
+        const uint32_t c = __popc(ball & lt);
+        const uint64_t l = l0 + w.mism + c;
+        int sc = 0;
+        if (useScore) {
+            const int d = f ? x.p.mismatchPenalty : -x.p.matchBonus;
+            int P = d;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xFFFFFFFFu, P, o);
+                if (lane >= o) P += t;
+            }
+            const int Pe = P - d;  // sum of the steps before this one
+            int M = lane >= 1 ? Pe : INT32_MAX;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xFFFFFFFFu, M, o);
+                if (lane >= o && t < M) M = t;
+            }
+            const int floor0 = M == INT32_MAX ? s0 : (s0 > -M ? s0 : -M);
+            sc = Pe + floor0;
+        }
+        const bool lim = i >= maxSteps;
+        const bool A = lim || (stopAtGuard && l == guard) || (useScore && sc >= x.p.scoreThreshold);
+        const bool B = f && (l + litBias == guard);
+        const uint32_t stop = __ballot_sync(0xFFFFFFFFu, A || !inRange || B);
+        if (stop) {
+            const int k = __ffs(stop) - 1;
+            const uint32_t packed = (A ? 1u : 0u) | (inRange ? 2u : 0u) | (lim ? 4u : 0u) | (c << 8);
+            const uint32_t pk = __shfl_sync(0xFFFFFFFFu, packed, k);
+            w.steps += k;
+            w.mism += pk >> 8;
+            if (pk & 1u) {
+                w.limit = (pk & 4u) != 0;
+            } else if (!(pk & 2u)) {
+                x.bad = true;  // the automaton wants a flag behind the stream's end
+            } else {
+                w.atGuard = true;
+            }
+            return w;
+        }
+        w.steps += 32;
+        w.mism += __popc(ball);
+        if (useScore) {
+            const int after = f ? sc + x.p.mismatchPenalty : (sc - x.p.matchBonus < 0 ? 0 : sc - x.p.matchBonus);
+            s0 = __shfl_sync(0xFFFFFFFFu, after, 31);
+        }
     }
-    const uint64_t base = at & ~7ull;
-    if (base != x.flagBase) {  // the stream buffers are 16-byte aligned and padded
-        x.flagBase = base;
-        x.flagWord = *reinterpret_cast<const uint64_t*>(x.s.flags + base);
-    }
-    return ((x.flagWord >> ((at & 7) * 8)) & 0xFF) != 0;
 }
 
 // extendMatchRight (:434-462): returns the extension's length; the segment describes what the copy pass has to write
@@ -308,19 +363,15 @@ __device__ uint64_t parse_extend_right(ParseCtx& x, uint64_t destSize, int64_t o
         n++;
     }
     seg.flagsPos = static_cast<uint32_t>(x.flagsPos);
-    int score = x.p.initialScore;
-    while ((!gapEnd || x.litPos != guardLitPos) && (isGap || score < x.p.scoreThreshold)) {
-        const bool mismatch = read_flag(x, x.flagsPos++);
-        if (x.bad) break;
-        if (mismatch && x.litPos == guardLitPos) break;
-        score = score_step(x.p, score, mismatch);
-        if (mismatch) x.litPos++;
-        n++;
-    }
+    // while ((!gapEnd || litPos != guard) && (isGap || score < threshold)) { flag; if (flag && litPos == guard) break; ... }
+    const Walk w = warp_walk(x, x.flagsPos, x.litPos, guardLitPos, 0, UINT64_MAX, !isGap, gapEnd);
+    x.flagsPos += w.steps + (w.atGuard ? 1 : 0);
+    x.litPos += w.mism;
+    n += w.steps;
     seg.len = static_cast<uint32_t>(n);
     seg.meta = DC_EXT_RIGHT | (implicitFirst ? 4u : 0u);
     // the reference's buffer has maxConsecutiveMismatches (a uint8) spare bytes behind refTotalLength (:1083); ours has 256
-    if (static_cast<int64_t>(seg.src) < 0 || seg.src + n > x.p.refTotalLength + 255) x.bad = true;
+    if (static_cast<int64_t>(seg.src) < 0 || seg.src + n > x.p.refTotalLength + 255 || n >= (1ull << 32)) x.bad = true;
     return n;
 }
 
@@ -336,20 +387,12 @@ __device__ uint64_t parse_extend_left(ParseCtx& x, uint64_t& matchSrcPos, bool s
     }
     if (srcGuard == srcMatch) return 0;
     if (skipOffset) {
-        int64_t srcPtr = srcMatch - 1;
-        uint64_t length = 0, mismatches = 0;
-        bool known = true;
-        int score = x.p.initialScore;
-        while (--srcPtr > srcGuard && score < x.p.scoreThreshold) {
-            const bool mismatch = read_flag(x, x.flagsPos + length++);
-            if (x.bad) return 0;
-            if (mismatch && x.litPos + ++mismatches == markPos) {
-                known = false;
-                break;
-            }
-            score = score_step(x.p, score, mismatch);
-        }
-        if (srcPtr == srcGuard && known) {
+        // while (--srcPtr > srcGuard && score < threshold) { flag (peeked); if (flag && litPos + ++mismatches == markPos) break; ... }
+        const int64_t room = srcMatch - 2 - srcGuard;
+        const Walk w = warp_walk(x, x.flagsPos, x.litPos, markPos, 1, room > 0 ? static_cast<uint64_t>(room) : 0, true, false);
+        if (x.bad) return 0;
+        uint64_t length = w.steps + (w.atGuard ? 1 : 0), mismatches = w.mism + (w.atGuard ? 1 : 0);
+        if (w.limit && !w.atGuard) {  // srcPtr == srcGuard && isExtLenKnown
             mismatches++;
             length++;
         }
@@ -361,18 +404,13 @@ __device__ uint64_t parse_extend_left(ParseCtx& x, uint64_t& matchSrcPos, bool s
     seg.src = static_cast<uint64_t>(srcMatch);  // the copy pass reads src - 1 - w for the w-th byte it walks
     seg.litPos = static_cast<uint32_t>(x.litPos);
     seg.flagsPos = static_cast<uint32_t>(x.flagsPos);
-    int64_t srcPtr = srcMatch - 1;
     x.litPos++;
-    uint64_t n = 1;
-    int score = x.p.initialScore;
-    while (--srcPtr >= srcGuard && score < x.p.scoreThreshold) {
-        const bool mismatch = read_flag(x, x.flagsPos++);
-        if (x.bad) break;
-        if (mismatch && x.litPos == markPos) break;
-        score = score_step(x.p, score, mismatch);
-        if (mismatch) x.litPos++;
-        n++;
-    }
+    // while (--srcPtr >= srcGuard && score < threshold) { flag; if (flag && litPos == markPos) break; ... }
+    const int64_t room = srcMatch - 1 - srcGuard;
+    const Walk w = warp_walk(x, x.flagsPos, x.litPos, markPos, 0, room > 0 ? static_cast<uint64_t>(room) : 0, true, false);
+    x.flagsPos += w.steps + (w.atGuard ? 1 : 0);
+    x.litPos += w.mism;
+    const uint64_t n = 1 + w.steps;
     seg.len = static_cast<uint32_t>(n);
     seg.meta = DC_EXT_LEFT | 4u;
     if (srcMatch < static_cast<int64_t>(n) || static_cast<uint64_t>(srcMatch) > x.p.refTotalLength) x.bad = true;
@@ -380,21 +418,25 @@ __device__ uint64_t parse_extend_left(ParseCtx& x, uint64_t& matchSrcPos, bool s
 }
 
 __device__ __forceinline__ void put_seg(DcSeg* segs, uint64_t at, const DcSeg& g) {
+    if (threadIdx.x) return;  // the lanes hold identical values
     uint4* d = reinterpret_cast<uint4*>(segs + at);
     const uint4* q = reinterpret_cast<const uint4*>(&g);
     d[0] = q[0];
     d[1] = q[1];
 }
 
-// One WARP per target, lane 0 working: 32 targets in one warp would run their (completely divergent) parses one after the other.
+// One WARP per target.  All 32 lanes run the (scalar) replay with identical values -- for a warp that costs what one lane
+// would -- so that the flag walks of the extensions, where the time goes, can use the whole warp (warp_walk).  32 targets in one
+// warp would instead run their completely divergent parses one after the other.
 __global__ void __launch_bounds__(32) k_dc_parse(DcParams p, DcStreams s, DcIndex ix, const DcTarget* __restrict__ targets, uint32_t nTargets,
                                                   DcSeg* __restrict__ segs, uint64_t* __restrict__ contigLen,
                                                   uint64_t* __restrict__ contigUnmatched, uint32_t* __restrict__ error) {
     const uint32_t t = blockIdx.x;
-    if (t >= nTargets || threadIdx.x) return;
+    if (t >= nTargets) return;
+    const int lane = threadIdx.x;
     const DcTarget tg = targets[t];
-    int64_t pairedGapOffsetDelta[MAX_GAP_DEPTH];
-    ParseCtx x{p, s, 0, 0, false, 0, UINT64_MAX};
+    __shared__ int64_t pairedGapOffsetDelta[MAX_GAP_DEPTH];  // every lane reads and writes the same entries
+    ParseCtx x{p, s, 0, 0, false, lane};
     const uint32_t c0 = tg.firstContig;
     x.litPos = c0 ? static_cast<uint64_t>(ix.sepPos[c0 - 1]) + 1 : 0;
     x.flagsPos = (tg.flagIdx == UINT32_MAX || tg.flagIdx == 0) ? 0 : static_cast<uint64_t>(ix.flagSep[tg.flagIdx - 1]) + 1;
@@ -407,7 +449,9 @@ __global__ void __launch_bounds__(32) k_dc_parse(DcParams p, DcStreams s, DcInde
         uint64_t gdPos = ix.gdStart[c];
         uint64_t offIdx = marksLo - ix.nzStart[c];
         uint64_t destSize = 0, unmatched = 0;
-        for (int i = 0; i < MAX_GAP_DEPTH; i++) pairedGapOffsetDelta[i] = INT64_MAX;
+        __syncwarp();
+        for (int i = lane; i < MAX_GAP_DEPTH; i += 32) pairedGapOffsetDelta[i] = INT64_MAX;
+        __syncwarp();
         int64_t gapStartIdx = NO_GAP, gapEndIdx = NO_GAP;
         int gapCurIdx = 0;
         int64_t offsetDelta = -1;
@@ -420,10 +464,13 @@ __global__ void __launch_bounds__(32) k_dc_parse(DcParams p, DcStreams s, DcInde
             const uint64_t markPos = ix.markPos[mk];
             const uint64_t literalsLeft = markPos - x.litPos;
             uint64_t matchSrcPos;
-            const bool skipOffset = pairedGapOffsetDelta[gapCurIdx] != INT64_MAX;
+            const int64_t pairedDelta = pairedGapOffsetDelta[gapCurIdx];
+            const bool skipOffset = pairedDelta != INT64_MAX;
+            __syncwarp();  // every lane has read the entry before lane 0 clears it
             if (skipOffset) {
-                matchSrcPos = static_cast<uint64_t>(pairedGapOffsetDelta[gapCurIdx] + static_cast<int64_t>(destSize) + static_cast<int64_t>(literalsLeft));
-                pairedGapOffsetDelta[gapCurIdx] = INT64_MAX;
+                matchSrcPos = static_cast<uint64_t>(pairedDelta + static_cast<int64_t>(destSize) + static_cast<int64_t>(literalsLeft));
+                if (lane == 0) pairedGapOffsetDelta[gapCurIdx] = INT64_MAX;
+                __syncwarp();
             } else {
                 if (offIdx >= s.nOff) { x.bad = true; break; }
                 const uint8_t* o = s.off + 4 * offIdx;
@@ -488,7 +535,9 @@ __global__ void __launch_bounds__(32) k_dc_parse(DcParams p, DcStreams s, DcInde
                             gg++;
                         if (++guard > 4 * MAX_GAP_DEPTH) { x.bad = true; break; }  // a full ring: corrupt stream
                     }
-                    pairedGapOffsetDelta[gapIdx] = static_cast<int64_t>(matchSrcPos) - static_cast<int64_t>(prevMatchDestPos);
+                    __syncwarp();
+                    if (lane == 0) pairedGapOffsetDelta[gapIdx] = static_cast<int64_t>(matchSrcPos) - static_cast<int64_t>(prevMatchDestPos);
+                    __syncwarp();
                     if (p.enableExt && gapEndIdx <= j + gg && gg <= p.gapDepthMismatches) {
                         gapStartIdx = j;
                         gapEndIdx = j + gg;
@@ -519,10 +568,12 @@ __global__ void __launch_bounds__(32) k_dc_parse(DcParams p, DcStreams s, DcInde
         put_seg(segs, 4 * marksHi + c, g);
         destSize += plain;
         x.litPos = seqEnd + 1;
-        contigLen[c] = destSize;
-        contigUnmatched[c] = unmatched & 0xFFFFFFFFull;  // uint32_t unmatchedChars (:329)
+        if (lane == 0) {
+            contigLen[c] = destSize;
+            contigUnmatched[c] = unmatched & 0xFFFFFFFFull;  // uint32_t unmatchedChars (:329)
+        }
     }
-    if (x.bad) atomicOr(error, 1u);
+    if (x.bad && lane == 0) atomicOr(error, 1u);
 }
 
 // ---- the copy pass --------------------------------------------------------------------------------------------------------------

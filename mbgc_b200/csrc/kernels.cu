@@ -182,6 +182,17 @@ __global__ void k_table_low32(const unsigned long long* __restrict__ ht, uint32_
         out[i] = static_cast<uint32_t>(ht[i]);
 }
 
+// epoch rebase of the insert sequence numbers: every slot keeps its entry (low half) and forgets its number
+__global__ void k_table_rebase(unsigned long long* __restrict__ ht, uint64_t n) {
+    for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<uint64_t>(gridDim.x) * blockDim.x)
+        ht[i] &= 0xFFFFFFFFull;
+}
+
+void launch_table_rebase(unsigned long long* ht, uint64_t n, cudaStream_t st) {
+    k_table_rebase<<<device_sm_count() * 8, 256, 0, st>>>(ht, n);
+}
+
 void launch_table_low32(const unsigned long long* ht, uint32_t* out, uint64_t n, cudaStream_t st) {
     k_table_low32<<<device_sm_count() * 8, 256, 0, st>>>(ht, out, n);
 }

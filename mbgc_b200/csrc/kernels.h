@@ -114,6 +114,7 @@ struct InsertRange {
 };
 void launch_index_insert(const uint8_t* ref, unsigned long long* ht, uint32_t* occ, uint32_t* filter, uint32_t filterBits,
                          uint32_t hashMask, int K, int k1, int k1ord, InsertRange r0, InsertRange r1, cudaStream_t st);
+void launch_table_rebase(unsigned long long* ht, uint64_t n, cudaStream_t st);
 void launch_table_low32(const unsigned long long* ht, uint32_t* out, uint64_t n, cudaStream_t st);
 // reference segment from the staged text of a loadRef call: copy or upper-casing reverse complement (table uploaded once
 // per process with upload_complement_table)

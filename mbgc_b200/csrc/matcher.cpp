@@ -128,6 +128,10 @@ B200SparseEMMatcher::B200SparseEMMatcher(uint64_t refLengthLimit, uint32_t targe
             throw MatcherError(MBGCG_E_UNSUPPORTED, "reference needs the 64-bit table (ref .cpp:347-350)");
     }
 
+    if (const char* e = std::getenv("MBGC_B200_SEQ_LIMIT")) {  // tests: rebase the insert sequence numbers early
+        const unsigned long long v = std::strtoull(e, nullptr, 10);
+        if (v >= 1024 && v < (1ull << 32)) seqLimit = v;
+    }
     upload_complement_table(g_lut.t);
     // anonymous mapping (zero pages, like calloc) with transparent huge pages asked for: the mirror is written once,
     // front to back, and with 4 KiB pages every loadRef call would spend most of its time in first-touch page faults
@@ -197,9 +201,21 @@ void B200SparseEMMatcher::indexPass() {
     samplingPos = static_cast<uint64_t>(t);
     const uint64_t n = static_cast<uint64_t>(r0.count + r1.count);
     if (n == 0) return;
-    if (insertSeq + n >= (1ull << 32))
-        throw MatcherError(MBGCG_E_UNSUPPORTED, "more than 2^32 index samples over the life of one matcher");
+    if (insertSeq + n >= seqLimit) {
+        // Epoch rebase: the sequence numbers only order samples that race for a slot, and every sample still to come must win
+        // over everything in the table.  So the table forgets its numbers (each slot keeps its entry, sequence 0) and the
+        // count restarts at 1 -- the table's low halves, i.e. the reference's ht32bit, do not change.
+        if (n + 1 >= seqLimit) throw MatcherError(MBGCG_E_UNSUPPORTED, "one loadRef call with 2^32 index samples or more");
+        launch_table_rebase(dHt, hashSize, stream);
+        totalLaunches++;
+        memoSeq = memoSeq == insertSeq ? 1 : 0;
+        insertSeq = 1;
+        r0.seqBase = insertSeq;
+        r1.seqBase = insertSeq + static_cast<uint64_t>(r0.count);
+        seqRebases++;
+    }
     insertSeq += n;
+    samplesInserted += n;
     passesSinceInsert = 0;
     launch_index_insert(dRef, dHt, dOcc, dFilter, PROBE_FILTER_BITS, hashSize - 1, K, k1, k1ord, r0, r1, stream);
     totalLaunches++;
@@ -597,7 +613,7 @@ void B200SparseEMMatcher::buildMemo() {
 bool B200SparseEMMatcher::useSharedFilter() const {
     static const bool noFilterEnv = std::getenv("MBGC_B200_NO_FILTER") != nullptr;
     // the shared-memory filter only pays while it is sparse (entries <~ bits)
-    return insertSeq < static_cast<uint64_t>(PROBE_FILTER_BITS) * 3 / 2 && !noFilterEnv;
+    return samplesInserted < static_cast<uint64_t>(PROBE_FILTER_BITS) * 3 / 2 && !noFilterEnv;
 }
 
 void B200SparseEMMatcher::growPinned(void** p, uint64_t* cap, uint64_t need, const char* what) {

@@ -194,7 +194,10 @@ private:
     unsigned long long* dHt = nullptr;
     uint32_t* dOcc = nullptr;
     uint32_t* dFilter = nullptr;         // first-level probe filter (copied to shared memory by the probe kernel)
-    uint64_t insertSeq = 1;              // program-order sequence number of the next index sample
+    uint64_t insertSeq = 1;              // program-order sequence number of the next index sample (restarts at an epoch rebase)
+    uint64_t seqLimit = 1ull << 32;      // rebase when the numbers would leave 32 bits (MBGC_B200_SEQ_LIMIT lowers it: tests)
+    uint64_t samplesInserted = 0;        // index samples over the matcher's life
+    uint32_t seqRebases = 0;
     // fast path (kernels.cu, k_anchor / k_clean): self-probe memo of the reference + adaptive policy
     uint32_t* dMemoX = nullptr; uint64_t memoCapWords = 0;
     uint64_t memoSeq = 0;                // insertSeq the memo was built at (0 = none)

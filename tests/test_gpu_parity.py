@@ -195,3 +195,35 @@ def test_grown_reference_long_islands():
             os.environ.pop("MBGC_B200_FASTPATH", None)
             g.close()
             o.close()
+
+
+def test_insert_sequence_rebase(monkeypatch):
+    """The table orders racing index samples by a 32-bit sequence number; when the numbers run out the table
+    forgets them (epoch rebase) and counting restarts.  With the limit lowered to 60 000 samples, eight appended genomes
+    (25 000 samples each with their reverse complements, overlapping k-mers racing for slots all the time) cross it several
+    times: table, match lists and cursors must not notice."""
+    monkeypatch.setenv("MBGC_B200_SEQ_LIMIT", "60000")
+    base = synth_base(200_000, 88)
+    muts = [synth_mutant(base, 8800 + i, 5e-3, 5e-4) for i in range(8)]
+    probes = [synth_mutant(base, 8900 + i, 2e-3, 2e-4) for i in range(3)]
+    limit = mgmp_ref_limit(16, base.size)
+    o = OracleMatcher(limit, 32, 16, 1, 16)
+    g = CudaFace(limit, 32, 16, 1, 16)
+    try:
+        for m in (o, g):
+            m.disable_sliding_window()
+            m.load_ref(base, rc=True)
+        for i, t in enumerate(muts):
+            for m in (o, g):
+                m.load_ref(t, rc=True)
+                m.load_separator(0)
+            if i % 3 == 2:
+                a, b = g.match(probes[i // 3]), o.match(probes[i // 3])
+                assert np.array_equal(a, b), _diff(a, b)
+        assert np.array_equal(g.table(), o.table()), "hash table differs after the rebases"
+        for t in probes:
+            a, b = g.match(t), o.match(t)
+            assert np.array_equal(a, b), _diff(a, b)
+    finally:
+        g.close()
+        o.close()
