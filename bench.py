@@ -771,7 +771,8 @@ def measure_collection(args, rank, world, dist, local, peak):
            "rank0": {"files": b - a if rank == 0 else None, "windows": st["windows"], "launches": st["launches"],
                      "ingest_ms": st["ingestMs"], "match_ms": st["matchMs"], "pack_ms": st["packMs"],
                      "wait_staging_ms": st["waitStageMs"], "pageable_bytes": st["pageableBytes"],
-                     "stream_bytes": info["stream_bytes"], "reader_threads": readers},
+                     "stream_bytes": info["stream_bytes"], "reader_threads": readers, "wire_bytes": st.get("wireBytes"),
+                     "host": info.get("host")},
            "generate_s": gen_s, "hbm_frac_of_pass": (1.0 * total_bytes / world) / best / 1e9 / peak}
     m.close()
     torch.cuda.empty_cache()

@@ -286,6 +286,7 @@ typedef struct {
     uint64_t files, contigs, windows, runs, rerunContigs, extensions;
     uint64_t imageBytes, textBytes, pageableBytes, launches, chunks;
     double ingestMs, matchMs, packMs, loadRefMs, waitStageMs;  /* host wall time inside the respective calls */
+    uint64_t wireBytes;   /* image bytes that crossed PCIe (packed images travel at about a quarter of their size) */
 } mbgcg_seq_stats_t;
 
 /* loadedPosArr = refExtLoadedPosArr as it stands (MBGC_Encoder.cpp:786-791); the pass appends to its own copy */
@@ -293,6 +294,9 @@ int mbgcg_seq_begin(mbgcg_t* h, const mbgcg_seq_config_t* cfg, const uint64_t* l
 /* next file image, HOST pointer.  Memory from mbgcg_image_alloc now belongs to the pass (it is released as soon as the
  * image is on the device); any other memory must stay valid until the file's FILE_END event has been returned. */
 int mbgcg_seq_push_file(mbgcg_t* h, const char* bytes, uint64_t n);
+/* The same for an image that was packed on the host (below): 4 bases per byte cross PCIe, the device rebuilds the file byte for
+ * byte before the reader's kernels look at it. */
+int mbgcg_seq_push_packed(mbgcg_t* h, const void* packedImage);
 int mbgcg_seq_finish_input(mbgcg_t* h);
 /* 1 while the pass can use more images to keep the devices busy (about two windows ahead of the commit cursor) */
 int mbgcg_seq_wants_input(mbgcg_t* h);
@@ -325,10 +329,32 @@ typedef struct {
 /* call between mbgcg_seq_begin and mbgcg_seq_end; *out stays valid until mbgcg_seq_end */
 int mbgcg_seq_run(mbgcg_t* h, mbgcg_next_image_fn next_image, void* user, int keepStreams, mbgcg_seq_result_t* out);
 
+/* mbgcg_seq_run for files on disk: `readers` threads inside the library bring them into pinned memory ahead of the pass (in
+ * order of need; read() into the arena, or packed 4 bases per byte on the way when packImages != 0 -- mbgcg_image_pack_file),
+ * files that do not fit the arena through pageable memory.  gzip is the caller's business (libdeflate stays on the host side of
+ * the reference).  hostMs (may be NULL): [0] time the readers spent reading / packing, summed over threads, [1] time the pass
+ * waited for a file. */
+int mbgcg_seq_run_files(mbgcg_t* h, const char* const* paths, uint64_t nFiles, int readers, int packImages, int keepStreams,
+                        mbgcg_seq_result_t* out, double hostMs[2]);
+
 /* Pinned host memory for file images, cut from large slabs (cudaHostAlloc costs ~0.5 ms per MiB): DMA reads it at PCIe
  * speed, pageable images travel through bounce buffers at ~1/4 of that.  NULL when the arena is full -- use any other
  * memory then.  mbgcg_image_free only for images that were never pushed. */
 void* mbgcg_image_alloc(mbgcg_t* h, uint64_t n);
+/* A file image packed for the trip to the device: header, 2-bit codes, exception runs for every byte that is not A/C/G/T (the
+ * line ends of a FASTA file are ONE run: first offset, count, distance).  Reading the file from the page cache and writing a
+ * quarter of it into pinned memory costs the host half the memory traffic of copying it there, and PCIe a quarter -- on a box
+ * whose cores feed several GPUs that is what the whole pipeline is bound by.  dst: 16-byte aligned memory of
+ * mbgcg_image_pack_bound(n) bytes (normally from mbgcg_image_alloc); *used = the bytes that have to travel.  Thread-safe; the
+ * reader threads of a caller run it in parallel.  MBGCG_E_UNSUPPORTED: too many exceptional bytes (soft-masked or protein
+ * text) -- push the file as it is.  src may be pageable (an mmap of the file).
+ * mbgcg_seq_run's image source returns such an image with MBGCG_IMAGE_PACKED set in *n. */
+#define MBGCG_IMAGE_PACKED (1ull << 63)
+uint64_t mbgcg_image_pack_bound(uint64_t n);
+int mbgcg_image_pack(const void* src, uint64_t n, void* dst, uint64_t dstCap, uint64_t* used);
+/* the same for a file on disk: read() in pieces that stay in the core's cache and packed from there, so the page cache is read
+ * once and a quarter of it written (sixteen threads faulting in mmaps of their files would queue up on the memory-map lock) */
+int mbgcg_image_pack_file(const char* path, void* dst, uint64_t dstCap, uint64_t* used, uint64_t* fileSize);
 /* the largest image the arena can hold in one piece (larger requests always return NULL) */
 uint64_t mbgcg_image_max(mbgcg_t* h);
 int mbgcg_image_free(mbgcg_t* h, const void* p);
@@ -438,6 +464,7 @@ int mbgcg_copy_staged_text(mbgcg_t* h, uint64_t textIndex, char* out);
 /* Host-only self-test of the 2-bit text packer (no device needed): packs text[0..n) as the transfer path does and
  * expands it again on the host into out[0..n).  Returns 0, or 1 if the text has too many non-ACGT bytes to be
  * packed (such a block travels raw; out is then untouched). */
+int mbgcg_selftest_pack_image(const char* image, uint64_t n, char* out, uint64_t* packedBytes, uint64_t* nRuns);
 int mbgcg_selftest_pack(const char* text, uint64_t n, char* out);
 
 /* Host-only self-test of the reverse complement mbgcg_load_ref writes for loadRC (no device needed):

@@ -1,4 +1,15 @@
 // mbgc_b200/csrc/capi.cpp -- the extern "C" layer of include/mbgc_b200.h over B200SparseEMMatcher.
+#include <chrono>
+#include <cerrno>
+#include <unistd.h>
+#include <sys/stat.h>
+#include <fcntl.h>
+#include <thread>
+#include <mutex>
+#include <memory>
+#include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -6,6 +17,7 @@
 #include "../../include/mbgc_b200.h"
 #include "collection.hpp"
 #include "decode.hpp"
+#include "hostpack.hpp"
 #include "matcher.hpp"
 
 using mbgc_b200::B200SparseEMMatcher;
@@ -321,6 +333,27 @@ int mbgcg_selftest_pack(const char* text, uint64_t n, char* out) {
     return 0;
 }
 
+int mbgcg_selftest_pack_image(const char* image, uint64_t n, char* out, uint64_t* packedBytes, uint64_t* nRuns) {
+    const uint64_t cap = mbgc_b200::packed_image_bound(n);
+    std::vector<uint8_t> buf(cap + 16);
+    uint8_t* dst = buf.data() + ((16 - (reinterpret_cast<uintptr_t>(buf.data()) & 15)) & 15);
+    const uint64_t used = mbgc_b200::pack_image_into(reinterpret_cast<const uint8_t*>(image), n, dst, cap);
+    if (!used) return 1;
+    mbgc_b200::PackedImageHeader h;
+    std::memcpy(&h, dst, sizeof(h));
+    if (packedBytes) *packedBytes = used;
+    if (nRuns) *nRuns = h.nRuns;
+    static const char lut[4] = {'A', 'C', 'T', 'G'};
+    const uint8_t* packed = dst + h.packedOff;
+    for (uint64_t i = 0; i < n; i++) out[i] = lut[(packed[i >> 2] >> (2 * (i & 3))) & 3];
+    const auto* runs = reinterpret_cast<const mbgc_b200::ExcRun*>(dst + h.runsOff);
+    for (uint32_t r = 0; r < h.nRuns; r++) {
+        const uint64_t step = (runs[r].byte >> 8) ? (runs[r].byte >> 8) : 1;
+        for (uint32_t k = 0; k < runs[r].len; k++) out[runs[r].off + k * step] = static_cast<char>(runs[r].byte & 0xFF);
+    }
+    return h.firstByte == static_cast<uint8_t>(image[0]) && h.n == n ? 0 : 2;
+}
+
 void mbgcg_set_stage_timing(mbgcg_t* h, int on) { h->m->stageTiming = on != 0; }
 
 void mbgcg_last_timing(const mbgcg_t* h, float ms[MBGCG_T_COUNT]) {
@@ -513,6 +546,38 @@ int mbgcg_seq_push_file(mbgcg_t* h, const char* bytes, uint64_t n) {
     });
 }
 
+int mbgcg_seq_push_packed(mbgcg_t* h, const void* packedImage) {
+    return guarded(h, [&] {
+        if (!h->pass) throw MatcherError(MBGCG_E_PARAM, "seq_push_packed: no pass in progress");
+        const auto* ph = static_cast<const mbgc_b200::PackedImageHeader*>(packedImage);
+        if (!ph || ph->magic != mbgc_b200::PACKED_IMAGE_MAGIC) throw MatcherError(MBGCG_E_PARAM, "seq_push_packed: not a packed image");
+        h->pass->pushFile(static_cast<const char*>(packedImage), ph->n, true);
+    });
+}
+
+uint64_t mbgcg_image_pack_bound(uint64_t n) { return mbgc_b200::packed_image_bound(n); }
+
+int mbgcg_image_pack(const void* src, uint64_t n, void* dst, uint64_t dstCap, uint64_t* used) {
+    if (!used) return MBGCG_E_PARAM;
+    *used = 0;
+    if ((n && !src) || !dst) return MBGCG_E_PARAM;
+    *used = mbgc_b200::pack_image_into(static_cast<const uint8_t*>(src), n, static_cast<uint8_t*>(dst), dstCap);
+    return *used ? MBGCG_OK : MBGCG_E_UNSUPPORTED;
+}
+
+int mbgcg_image_pack_file(const char* path, void* dst, uint64_t dstCap, uint64_t* used, uint64_t* fileSize) {
+    if (!used || !fileSize || !path || !dst) return MBGCG_E_PARAM;
+    *used = 0;
+    try {
+        *used = mbgc_b200::pack_image_from_file(path, static_cast<uint8_t*>(dst), dstCap, fileSize);
+    } catch (const MatcherError& e) {
+        return e.code;
+    } catch (const std::exception&) {
+        return MBGCG_E_NOMEM;
+    }
+    return *used ? MBGCG_OK : MBGCG_E_UNSUPPORTED;
+}
+
 int mbgcg_seq_finish_input(mbgcg_t* h) {
     return guarded(h, [&] {
         if (!h->pass) throw MatcherError(MBGCG_E_PARAM, "seq_finish_input: no pass in progress");
@@ -567,8 +632,19 @@ int mbgcg_seq_run(mbgcg_t* h, mbgcg_next_image_fn next_image, void* user, int ke
             const char* bytes = nullptr;
             uint64_t n = 0;
             const int rc = next_image(user, block ? 1 : 0, &bytes, &n);
+            if (rc == 3) return true;       // (internal) the source pushes its images itself and has made progress
+            if (rc == -2) {                 // (internal) ... and has pushed the last one and closed the input
+                finished = true;
+                return true;
+            }
             if (rc > 0) {
-                h->pass->pushFile(bytes, n);
+                if (n & MBGCG_IMAGE_PACKED) {
+                    const auto* ph = reinterpret_cast<const mbgc_b200::PackedImageHeader*>(bytes);
+                    if (!ph || ph->magic != mbgc_b200::PACKED_IMAGE_MAGIC) throw MatcherError(MBGCG_E_PARAM, "seq_run: not a packed image");
+                    h->pass->pushFile(bytes, ph->n, true);
+                } else {
+                    h->pass->pushFile(bytes, n);
+                }
                 return true;
             }
             if (rc < 0) {
@@ -583,10 +659,23 @@ int mbgcg_seq_run(mbgcg_t* h, mbgcg_next_image_fn next_image, void* user, int ke
         uint64_t contigs = 0, matches = 0, unmatched = 0, extensions = 0, digest = 0;
         uint64_t sizes[MBGCG_S_COUNT] = {0, 0, 0, 0, 0, 0};
         mbgc_b200::SeqEvent e;
+        const bool trace = std::getenv("MBGC_B200_TRACE") != nullptr;
+        auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+        double feedMs = 0, nextMs = 0;
+        const double tStart = now();
         for (;;) {
+            double t0 = now();
             while (!finished && h->pass->wantsInput() && feed(false)) {}
+            double t1 = now();
             h->pass->next(e);
-            if (e.type == mbgc_b200::SeqEvent::DONE) break;
+            feedMs += t1 - t0;
+            nextMs += now() - t1;
+            if (e.type == mbgc_b200::SeqEvent::DONE) {
+                if (trace)
+                    fprintf(stderr, "[mbgc_b200] seq_run: %.1f ms, of which feeding images %.1f, waiting for / producing events %.1f\n",
+                            now() - tStart, feedMs, nextMs);
+                break;
+            }
             if (e.type == mbgc_b200::SeqEvent::NEED_INPUT) {
                 if (finished) throw MatcherError(MBGCG_E_PARAM, "seq_run: the pass asks for input after the last file");
                 feed(true);
@@ -643,6 +732,238 @@ int mbgcg_seq_run(mbgcg_t* h, mbgcg_next_image_fn next_image, void* user, int ke
     });
 }
 
+// ---- the pass over files on disk: reader threads inside the library ---------------------------------------------------------
+namespace {
+
+// Reader threads bring the files into pinned memory (ahead of the pass, in order of need), packed 4 bases per byte on the way
+// when asked to; the pass pulls them through next().  Pinned memory is handed out in FILE ORDER, so however small the arena is,
+// the file the pass is waiting for always has its memory and the readers behind it wait for space.
+class FileFeeder {
+public:
+    FileFeeder(mbgcg_t* h, const char* const* paths, uint64_t n, int readers, bool pack)
+        : h(h), paths(paths), n(n), pack(pack), ready(n), bytes(n, nullptr), sizes(n, 0) {
+        arenaMax = h->rs->arena().maxPiece();
+        if (readers < 1) readers = 1;
+        if (n == 0) {
+            h->pass->finishInput();
+            inputClosed = true;
+        }
+        for (int t = 0; t < readers && static_cast<uint64_t>(t) < n; t++) threads.emplace_back([this] { work(); });
+    }
+    ~FileFeeder() {
+        {
+            std::lock_guard<std::mutex> g(mu);
+            stop = true;
+        }
+        cv.notify_all();
+        for (auto& t : threads) t.join();
+        // images that were read but never handed to the pass go back
+        for (uint64_t i = handed; i < n; i++)
+            if (ready[i] && bytes[i]) h->rs->arena().release(bytes[i]);
+    }
+    static int next(void* user, int block, const char** bytesOut, uint64_t* nOut) {
+        return static_cast<FileFeeder*>(user)->nextImage(block != 0, bytesOut, nOut);
+    }
+    double busyMs = 0, feedWaitMs = 0;
+
+private:
+    static double now() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+    // The readers push their images into the pass themselves, in file order, as soon as they are complete (the pass's entry
+    // points are thread-safe): the thread that runs the commit loop spends its time in next(), and a file must not wait for it.
+    // For the loop this source therefore never has an image; it only reports progress (3) and the end of the input (-2).
+    int nextImage(bool block, const char**, uint64_t*) {
+        std::unique_lock<std::mutex> lk(mu);
+        if (!error.empty()) throw MatcherError(MBGCG_E_PARAM, error);
+        if (inputClosed) return -2;
+        if (!block) {
+            seenPushes = pushes;
+            return 0;
+        }
+        const double t0 = now();
+        cv.wait(lk, [&] { return pushes != seenPushes || inputClosed || !error.empty(); });
+        feedWaitMs += now() - t0;
+        if (!error.empty()) throw MatcherError(MBGCG_E_PARAM, error);
+        seenPushes = pushes;
+        return inputClosed ? -2 : 3;
+    }
+    // (mu held on entry and exit) pushes every complete file that is next in line; one thread at a time
+    void pushReady(std::unique_lock<std::mutex>& lk) {
+        while (!pushing && handed < n && ready[handed] && !stop) {
+            pushing = true;
+            const uint64_t i = handed;
+            lk.unlock();
+            try {
+                while (!h->pass->wantsInput()) {
+                    {
+                        std::lock_guard<std::mutex> g(mu);
+                        if (stop) break;
+                    }
+                    std::this_thread::sleep_for(std::chrono::microseconds(50));
+                }
+                if (sizes[i] & MBGCG_IMAGE_PACKED)
+                    h->pass->pushFile(bytes[i], reinterpret_cast<const mbgc_b200::PackedImageHeader*>(bytes[i])->n, true);
+                else
+                    h->pass->pushFile(bytes[i], sizes[i]);
+            } catch (...) {
+                lk.lock();
+                pushing = false;
+                throw;
+            }
+            lk.lock();
+            handed++;
+            pushes++;
+            pushing = false;
+            cv.notify_all();
+        }
+        if (handed == n && !inputClosed && !pushing && !stop) {
+            pushing = true;
+            lk.unlock();
+            try {
+                h->pass->finishInput();
+            } catch (...) {
+                lk.lock();
+                pushing = false;
+                throw;
+            }
+            lk.lock();
+            pushing = false;
+            inputClosed = true;
+            cv.notify_all();
+        }
+    }
+    void fail(const std::string& what) {
+        std::lock_guard<std::mutex> g(mu);
+        if (error.empty()) error = what;
+        stop = true;
+        cv.notify_all();
+    }
+    void work() {
+        for (;;) {
+            uint64_t i;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                if (stop || nextFile >= n) return;
+                i = nextFile++;
+                cv.wait(lk, [&] { return stop || turn == i; });  // pinned memory goes out in file order
+                if (stop) return;
+            }
+            try {
+                struct stat sb;
+                if (::stat(paths[i], &sb) != 0) throw MatcherError(MBGCG_E_PARAM, std::string("cannot stat ") + paths[i]);
+                const uint64_t size = static_cast<uint64_t>(sb.st_size);
+                const uint64_t want = pack ? mbgc_b200::packed_image_bound(size) : size;
+                uint8_t* p = nullptr;
+                if (size && want <= arenaMax) {
+                    for (;;) {
+                        p = static_cast<uint8_t*>(h->rs->arena().alloc(want));
+                        if (p) break;
+                        {
+                            std::lock_guard<std::mutex> g(mu);
+                            if (stop) return;
+                        }
+                        std::this_thread::sleep_for(std::chrono::microseconds(50));
+                    }
+                }
+                {
+                    std::lock_guard<std::mutex> g(mu);
+                    turn = i + 1;
+                }
+                cv.notify_all();
+                const double t0 = now();
+                uint64_t outSize = size;
+                bool done = false;
+                if (p && pack) {
+                    uint64_t fsize = 0;
+                    const uint64_t used = mbgc_b200::pack_image_from_file(paths[i], p, want, &fsize);
+                    if (used) {
+                        if (fsize != size) throw MatcherError(MBGCG_E_PARAM, std::string(paths[i]) + " changed size while it was read");
+                        outSize = used | MBGCG_IMAGE_PACKED;
+                        done = true;
+                    } else {  // too many exceptional bytes: the file travels as it is (from pageable memory: the piece is too small)
+                        h->rs->arena().release(p);
+                        p = nullptr;
+                    }
+                }
+                if (!done && size) {
+                    if (!p) {
+                        std::unique_ptr<uint8_t[]> mem(new uint8_t[size]);
+                        p = mem.get();
+                        std::lock_guard<std::mutex> g(mu);
+                        pageable.push_back(std::move(mem));
+                    }
+                    const int fd = ::open(paths[i], O_RDONLY);
+                    if (fd < 0) throw MatcherError(MBGCG_E_PARAM, std::string("cannot open ") + paths[i]);
+                    uint64_t got = 0;
+                    while (got < size) {
+                        const ssize_t k = ::read(fd, p + got, size - got);
+                        if (k < 0 && errno == EINTR) continue;
+                        if (k <= 0) {
+                            ::close(fd);
+                            throw MatcherError(MBGCG_E_PARAM, std::string("short read on ") + paths[i]);
+                        }
+                        got += static_cast<uint64_t>(k);
+                    }
+                    ::close(fd);
+                }
+                const double dt = now() - t0;
+                {
+                    std::unique_lock<std::mutex> lk(mu);
+                    bytes[i] = reinterpret_cast<const char*>(p);
+                    sizes[i] = outSize;
+                    ready[i] = 1;
+                    busyMs += dt;
+                    pushReady(lk);
+                }
+                cv.notify_all();
+            } catch (const std::exception& e) {
+                fail(e.what());
+                return;
+            }
+        }
+    }
+    mbgcg_t* h;
+    const char* const* paths;
+    uint64_t n;
+    bool pack;
+    uint64_t arenaMax = 0;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<uint8_t> ready;
+    std::vector<const char*> bytes;
+    std::vector<uint64_t> sizes;
+    std::vector<std::unique_ptr<uint8_t[]>> pageable;  // files that did not fit the arena: they stay until the pass is over
+    std::vector<std::thread> threads;
+    uint64_t nextFile = 0, turn = 0, handed = 0, pushes = 0, seenPushes = 0;
+    bool stop = false, pushing = false, inputClosed = false;
+    std::string error;
+};
+
+}  // namespace
+
+int mbgcg_seq_run_files(mbgcg_t* h, const char* const* paths, uint64_t nFiles, int readers, int packImages, int keepStreams,
+                        mbgcg_seq_result_t* out, double hostMs[2]) {
+    if (!out) return MBGCG_E_PARAM;
+    std::memset(out, 0, sizeof(*out));
+    if (hostMs) hostMs[0] = hostMs[1] = 0;
+    if (!h->pass) {
+        h->err = "seq_run_files: no pass in progress";
+        return MBGCG_E_PARAM;
+    }
+    if (nFiles && !paths) return MBGCG_E_PARAM;
+    try {
+        FileFeeder feeder(h, paths, nFiles, readers, packImages != 0);
+        const int rc = mbgcg_seq_run(h, &FileFeeder::next, &feeder, keepStreams, out);
+        if (hostMs) {
+            hostMs[0] = feeder.busyMs;
+            hostMs[1] = feeder.feedWaitMs;
+        }
+        return rc;
+    } catch (const std::exception& e) {
+        h->err = e.what();
+        return MBGCG_E_NOMEM;
+    }
+}
+
 int mbgcg_seq_end(mbgcg_t* h, mbgcg_seq_stats_t* stats) {
     return guarded(h, [&] {
         if (!h->pass) throw MatcherError(MBGCG_E_PARAM, "seq_end: no pass in progress");
@@ -664,6 +985,7 @@ int mbgcg_seq_end(mbgcg_t* h, mbgcg_seq_stats_t* stats) {
             stats->packMs = s.packMs;
             stats->loadRefMs = s.loadRefMs;
             stats->waitStageMs = s.waitStageMs;
+            stats->wireBytes = s.wireBytes;
         }
         delete h->pass;
         h->pass = nullptr;

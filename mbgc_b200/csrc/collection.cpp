@@ -4,9 +4,15 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdlib>
+#include <cerrno>
 #include <cstring>
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include "../../include/mbgc_b200.h"
+#include "hostpack.hpp"
+#include "kernels.h"
 
 namespace mbgc_b200 {
 
@@ -27,6 +33,85 @@ bool is_pinned(const void* p) {
     return attr.type == cudaMemoryTypeHost;
 }
 }  // namespace
+
+uint64_t packed_image_bound(uint64_t n) {
+    const uint64_t maxRuns = n / 256 + 256;
+    return sizeof(PackedImageHeader) + align_up((n + 3) / 4 + 16, 16) + maxRuns * sizeof(ExcRun) + 64;
+}
+
+uint64_t pack_image_into(const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t cap) {
+    if (n == 0 || cap < packed_image_bound(n) || (reinterpret_cast<uintptr_t>(dst) & 15)) return 0;
+    const uint64_t maxRuns = n / 256 + 256;
+    static thread_local std::vector<ExcRun> runs;
+    runs.clear();
+    PackedImageHeader h{};
+    h.magic = PACKED_IMAGE_MAGIC;
+    h.n = n;
+    h.packedOff = sizeof(PackedImageHeader);
+    h.packedBytes = align_up((n + 3) / 4 + 16, 16);
+    if (!pack_fasta_image(src, n, dst + h.packedOff, runs, maxRuns)) return 0;
+    h.runsOff = h.packedOff + h.packedBytes;
+    h.nRuns = static_cast<uint32_t>(runs.size());
+    h.firstByte = src[0];
+    h.total = h.runsOff + runs.size() * sizeof(ExcRun);
+    if (!runs.empty()) std::memcpy(dst + h.runsOff, runs.data(), runs.size() * sizeof(ExcRun));
+    std::memcpy(dst, &h, sizeof(h));
+    return h.total;
+}
+
+// The same straight from a file: read() into a buffer that stays in the core's cache, packed from there -- the page cache is
+// read once, a quarter of it is written.  (An mmap of the file would save the copy into the buffer, but sixteen reader threads
+// faulting pages in and unmapping files serialise on the process's memory-map lock.)
+uint64_t pack_image_from_file(const char* path, uint8_t* dst, uint64_t cap, uint64_t* fileSize) {
+    *fileSize = 0;
+    const int fd = ::open(path, O_RDONLY);
+    if (fd < 0) throw MatcherError(MBGCG_E_PARAM, std::string("cannot open ") + path);
+    struct FdGuard {
+        int fd;
+        ~FdGuard() { ::close(fd); }
+    } guard{fd};
+    struct stat sb;
+    if (::fstat(fd, &sb) != 0) throw MatcherError(MBGCG_E_PARAM, std::string("cannot stat ") + path);
+    const uint64_t n = static_cast<uint64_t>(sb.st_size);
+    *fileSize = n;
+    if (n == 0 || cap < packed_image_bound(n) || (reinterpret_cast<uintptr_t>(dst) & 15)) return 0;
+    const uint64_t maxRuns = n / 256 + 256;
+    static thread_local std::vector<ExcRun> runs;
+    static thread_local std::vector<uint8_t> buf;
+    constexpr uint64_t PIECE = 256 << 10;
+    if (buf.size() < PIECE + 64) buf.resize(PIECE + 64);
+    uint8_t* b = buf.data() + ((64 - (reinterpret_cast<uintptr_t>(buf.data()) & 63)) & 63);
+    runs.clear();
+    PackedImageHeader h{};
+    h.magic = PACKED_IMAGE_MAGIC;
+    h.n = n;
+    h.packedOff = sizeof(PackedImageHeader);
+    h.packedBytes = align_up((n + 3) / 4 + 16, 16);
+    ImagePacker packer(dst + h.packedOff, runs, maxRuns);
+    uint64_t done = 0;
+    uint8_t first = 0;
+    while (done < n) {
+        const uint64_t want = std::min<uint64_t>(PIECE, n - done);
+        uint64_t got = 0;
+        while (got < want) {
+            const ssize_t k = ::read(fd, b + got, want - got);
+            if (k < 0 && errno == EINTR) continue;
+            if (k <= 0) throw MatcherError(MBGCG_E_PARAM, std::string("short read on ") + path);
+            got += static_cast<uint64_t>(k);
+        }
+        if (done == 0) first = b[0];
+        if (!packer.add(b, want)) return 0;
+        done += want;
+    }
+    if (!packer.finish()) return 0;
+    h.runsOff = h.packedOff + h.packedBytes;
+    h.nRuns = static_cast<uint32_t>(runs.size());
+    h.firstByte = first;
+    h.total = h.runsOff + runs.size() * sizeof(ExcRun);
+    if (!runs.empty()) std::memcpy(dst + h.runsOff, runs.data(), runs.size() * sizeof(ExcRun));
+    std::memcpy(dst, &h, sizeof(h));
+    return h.total;
+}
 
 // ---------------------------------------------------------------------------------------------------------------------
 // FastaBatchIngest
@@ -60,7 +145,11 @@ FastaBatchIngest::FastaBatchIngest(int dev) : device(dev) {
 FastaBatchIngest::~FastaBatchIngest() {
     cudaSetDevice(device);
     if (stream) cudaStreamSynchronize(stream);
+    for (auto& f : inflight)
+        if (f.ev) cudaEventDestroy(f.ev);
+    for (auto e : evPool) cudaEventDestroy(e);
     cudaFree(dIn);
+    if (dPk) cudaFree(dPk);
     cudaFree(dWork);
     cudaFree(dText);
     cudaFree(dHdr);
@@ -87,9 +176,10 @@ void FastaBatchIngest::begin(uint64_t expectedBytes) {
     spans.clear();
     cursor = 0;
     launches = 0;
-    imageBytes = textBytes = pageableBytes = 0;
+    imageBytes = textBytes = pageableBytes = wireBytes = 0;
     ms[0] = ms[1] = 0;
     bounceUse = 0;
+    if (!inflight.empty()) throw MatcherError(MBGCG_E_PARAM, "FASTA ingest: images of the previous batch were never reaped");
     grow(&dIn, &dInCap, 16 + expectedBytes + expectedBytes / 8 + 4096, "cudaMalloc(fasta images)");
     check(cudaEventRecord(ev[0], stream), "event");
 }
@@ -100,16 +190,35 @@ void FastaBatchIngest::add(const HostImage& im) {
     files.push_back(IngestedFile{});
     fileBytes.push_back(im.n);
     // only images that can hold a record travel (the others are decided here: kseq.h:239-240)
-    if (im.n == 0) return;                         // end of file before the first header: status -1, no records
-    if (im.bytes[0] != '>') {                      // not FASTA
+    if (im.n == 0) {                               // end of file before the first header: status -1, no records
+        inflight.push_back(InFlight{nullptr, im.bytes});
+        return;
+    }
+    const PackedImageHeader* ph = im.packed ? reinterpret_cast<const PackedImageHeader*>(im.bytes) : nullptr;
+    if (ph && (ph->magic != PACKED_IMAGE_MAGIC || ph->n != im.n || ph->total < sizeof(PackedImageHeader)))
+        throw MatcherError(MBGCG_E_PARAM, "a packed file image with a damaged header");
+    if ((ph ? static_cast<char>(ph->firstByte) : im.bytes[0]) != '>') {  // not FASTA
         files[f].status = -3;
+        inflight.push_back(InFlight{nullptr, im.bytes});
         return;
     }
     if (im.n >= (1ull << 40)) throw MatcherError(MBGCG_E_UNSUPPORTED, "FASTA image of 1 TiB or more");
     const uint64_t end = cursor + im.n;
     grow(&dIn, &dInCap, 16 + align_up(end, 16) + 16 + 64, "cudaMalloc(fasta images)", true, 16 + cursor);
     uint8_t* dst = dIn + 16 + cursor;
-    if (is_pinned(im.bytes)) {
+    if (ph) {
+        // 4 bases per byte + exception runs over PCIe, the exact bytes of the file rebuilt here (kernels.cu: k_unpack_image,
+        // k_patch_exceptions).  The slot's stream orders copy and kernels; the sync below hands the host memory back.
+        const uint64_t body = ph->total - sizeof(PackedImageHeader);
+        grow(&dPk, &dPkCap, body + 64, "cudaMalloc(packed image)");
+        check(cudaMemcpyAsync(dPk, im.bytes + sizeof(PackedImageHeader), body, cudaMemcpyHostToDevice, stream), "H2D(packed image)");
+        launches += launch_unpack_image(dPk + (ph->packedOff - sizeof(PackedImageHeader)), im.n,
+                                        reinterpret_cast<const ExcRunDev*>(dPk + (ph->runsOff - sizeof(PackedImageHeader))), ph->nRuns, dst,
+                                        stream);
+        if (!is_pinned(im.bytes)) pageableBytes += ph->total;
+        wireBytes += ph->total;
+    } else if (is_pinned(im.bytes)) {
+        wireBytes += im.n;
         check(cudaMemcpyAsync(dst, im.bytes, im.n, cudaMemcpyHostToDevice, stream), "H2D(fasta image)");
     } else {  // pageable: through the pinned bounce buffers, one being filled while the other is on the wire
         for (uint64_t o = 0; o < im.n; o += BOUNCE_BYTES) {
@@ -123,13 +232,44 @@ void FastaBatchIngest::add(const HostImage& im) {
             bounceUse++;
         }
         pageableBytes += im.n;
+        wireBytes += im.n;
     }
     live.push_back(f);
     spans.push_back(cursor);
     spans.push_back(end);
     cursor = align_up(end, 16) + 16;
     imageBytes += im.n;
-    check(cudaStreamSynchronize(stream), "H2D(fasta image) sync");  // the caller gets its memory back
+    // the caller gets its memory back when the copy is over (reap); a pageable image has been copied into the bounce buffers
+    // by now and is free at once
+    cudaEvent_t e = nullptr;
+    if (ph || is_pinned(im.bytes)) {
+        if (evPool.empty()) {
+            check(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
+        } else {
+            e = evPool.back();
+            evPool.pop_back();
+        }
+        check(cudaEventRecord(e, stream), "event");
+    }
+    inflight.push_back(InFlight{e, im.bytes});
+}
+
+void FastaBatchIngest::reap(std::vector<const char*>& released, bool wait) {
+    while (!inflight.empty()) {
+        InFlight& f = inflight.front();
+        if (f.ev) {
+            if (wait) {
+                check(cudaEventSynchronize(f.ev), "image copy sync");
+            } else {
+                const cudaError_t q = cudaEventQuery(f.ev);
+                if (q == cudaErrorNotReady) break;
+                check(q, "image copy");
+            }
+            evPool.push_back(f.ev);
+        }
+        released.push_back(f.bytes);
+        inflight.pop_front();
+    }
 }
 
 void FastaBatchIngest::finish() {
@@ -411,6 +551,7 @@ ReplicaSet::~ReplicaSet() {
             w->cv.notify_all();
             w->th.join();
         }
+    slotStore.clear();
     pinned.reset();
     for (auto* m : rep) delete m;
 }
@@ -559,12 +700,12 @@ PinnedArena& ReplicaSet::arena() {
 // ---------------------------------------------------------------------------------------------------------------------
 
 SequentialPass::SequentialPass(ReplicaSet& rs_, const SeqConfig& c, const uint64_t* loadedPosArr, uint64_t nLoaded)
-    : rs(rs_), cfg(c), loaded(loadedPosArr, loadedPosArr + nLoaded) {
+    : rs(rs_), cfg(c), loaded(loadedPosArr, loadedPosArr + nLoaded), slots(rs_.ingestSlots()) {
     const int nd = rs.size();
     if (const char* e = std::getenv("MBGC_B200_CHUNK_MB")) cfg.chunkBytes = std::max<uint64_t>(1, std::strtoull(e, nullptr, 10)) << 20;
     if (const char* e = std::getenv("MBGC_B200_WINDOW")) cfg.maxWindowContigs = static_cast<uint32_t>(std::max(1, std::atoi(e)));
     rs.setHostMirror(false);  // extensions come from device memory; nothing on this path reads getRef()
-    slots.resize(static_cast<size_t>(nd) * NSLOT);
+    if (slots.size() < static_cast<size_t>(nd) * NSLOT) slots.resize(static_cast<size_t>(nd) * NSLOT);
     slotFree.assign(static_cast<size_t>(nd) * NSLOT, true);
     stageQ.resize(static_cast<size_t>(nd) * NSLOT);
     runState.resize(static_cast<size_t>(nd));
@@ -581,13 +722,12 @@ SequentialPass::~SequentialPass() {
     for (auto& t : stagers) t.join();
     // whatever was pushed but never consumed: arena images go back
     for (auto& im : pending) rs.arena().release(im.bytes);
-    slots.clear();
 }
 
-void SequentialPass::pushFile(const char* bytes, uint64_t n) {
+void SequentialPass::pushFile(const char* bytes, uint64_t n, bool packed) {
     std::lock_guard<std::mutex> g(mu);
     if (inputDone) throw MatcherError(MBGCG_E_PARAM, "pushFile after finishInput");
-    pending.push_back(HostImage{bytes, n});
+    pending.push_back(HostImage{bytes, n, packed});
     pendingBytes += n;
     pushedFiles++;
     dispatch();
@@ -669,20 +809,33 @@ void SequentialPass::stagerLoop(int q) {
         }
         Chunk& c = *msg.chunk;
         const double t0 = now_ms();
+        bool added = false;
+        std::vector<const char*> released;
         try {
             auto& slot = slots[r * NSLOT + c.slot];
             if (!slot) slot.reset(new FastaBatchIngest(rs.at(r)->deviceIndex()));
             if (msg.type == StageMsg::BEGIN) {
                 slot->begin(msg.image.n);
             } else if (msg.type == StageMsg::ADD) {
-                if (!c.err) slot->add(msg.image);
+                if (!c.err) {
+                    slot->add(msg.image);
+                    added = true;
+                }
             } else if (!c.err) {
+                slot->reap(released, true);
                 slot->finish();
             }
+            if (added) slot->reap(released, false);
         } catch (...) {
             if (!c.err) c.err = std::current_exception();
+            try {  // whatever is still on its way: wait for it, the memory goes back either way
+                auto& slot = slots[r * NSLOT + c.slot];
+                if (slot) slot->reap(released, true);
+            } catch (...) {
+            }
         }
-        if (msg.type == StageMsg::ADD) rs.arena().release(msg.image.bytes);  // arena images are ours to give back; others stay with the caller
+        if (msg.type == StageMsg::ADD && !added) released.push_back(msg.image.bytes);  // never reached the slot
+        for (const char* p : released) rs.arena().release(p);  // arena images are ours to give back; others stay with the caller
         std::lock_guard<std::mutex> g(mu);
         st.ingestMs += now_ms() - t0;
         if (msg.type == StageMsg::FINISH) {
@@ -692,6 +845,7 @@ void SequentialPass::stagerLoop(int q) {
                 st.textBytes += slot->textBytes;
                 st.ingestLaunches += slot->launches;
                 st.pageableBytes += slot->pageableBytes;
+                st.wireBytes += slot->wireBytes;
             }
             st.chunks++;
             c.ready = true;

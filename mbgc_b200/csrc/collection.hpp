@@ -32,8 +32,28 @@ namespace mbgc_b200 {
 
 struct HostImage {         // one FASTA file as it is on disk (after gunzip), host memory
     const char* bytes;
-    uint64_t n;
+    uint64_t n;            // size of the file image
+    bool packed = false;   // bytes -> a PackedImageHeader: the image travels 4 bases per byte and is rebuilt on the device
 };
+
+// A file image packed by the host for the trip to the device (pack_image_into): header, the 2-bit codes, the exception runs.
+constexpr uint64_t PACKED_IMAGE_MAGIC = 0x4942324743474D42ull;  // "MBGCG2BI"
+struct PackedImageHeader {  // 64 bytes
+    uint64_t magic;
+    uint64_t n;             // bytes of the file image
+    uint64_t packedOff, packedBytes;   // from the header's start; both multiples of 16
+    uint64_t runsOff;
+    uint32_t nRuns;
+    uint32_t firstByte;     // image[0] (the reader's "is this FASTA" test looks at it)
+    uint64_t total;         // bytes of the whole packed image
+    uint64_t reserved;
+};
+uint64_t packed_image_bound(uint64_t n);
+// returns the bytes used in dst (16-byte aligned memory of at least packed_image_bound(n) bytes), or 0 when the image has more
+// exceptional bytes than fit (it then travels as it is)
+uint64_t pack_image_into(const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t cap);
+// the same for a file on disk, read in cache-sized pieces; *fileSize = its size (also when 0 is returned)
+uint64_t pack_image_from_file(const char* path, uint8_t* dst, uint64_t cap, uint64_t* fileSize);
 
 struct IngestedFile {
     int status = -1;               // what ended the reader's loop: -1 end of file, -3 not FASTA, -4 DNA not well-formed
@@ -61,15 +81,19 @@ public:
 
     void begin(uint64_t expectedBytes);
     // Pinned images are copied by DMA straight from the caller's memory, pageable ones through this slot's pinned bounce
-    // buffers.  Blocking: the image may be released when the call returns.
+    // buffers.  Does not wait for the copy: the image's memory is free again once reap() has handed its pointer back.
     void add(const HostImage& image);
+    // images whose trip to the device is over (all of them after wait = true); call after add() and before finish() returns
+    void reap(std::vector<const char*>& released, bool wait);
     // blocking; afterwards files / contigs / headers / dTexts() describe the batch
     void finish();
     void run(const HostImage* images, int nFiles) {
         uint64_t b = 0;
         for (int i = 0; i < nFiles; i++) b += images[i].n;
         begin(b);
+        std::vector<const char*> done;
         for (int i = 0; i < nFiles; i++) add(images[i]);
+        reap(done, true);
         finish();
     }
     const uint8_t* dTexts() const { return dText; }
@@ -78,7 +102,7 @@ public:
     std::vector<uint64_t> fileBytes;   // image size per file
     const char* header(size_t contig) const { return reinterpret_cast<const char*>(hHdr) + hdrAt[contig]; }
     uint64_t launches = 0;         // kernel launches of the last batch
-    uint64_t imageBytes = 0, textBytes = 0, pageableBytes = 0;
+    uint64_t imageBytes = 0, textBytes = 0, pageableBytes = 0, wireBytes = 0;
     float ms[2] = {0, 0};          // last batch: kernels (incl. the two host round trips) of finish(); begin -> end of finish
     int deviceIndex() const { return device; }
 
@@ -89,9 +113,13 @@ private:
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[3] = {};
     cudaEvent_t bounceEv[2] = {};
+    struct InFlight { cudaEvent_t ev; const char* bytes; };
+    std::deque<InFlight> inflight;       // images on their way, oldest first (ev == nullptr: already there)
+    std::vector<cudaEvent_t> evPool;
     uint8_t* hBounce[2] = {nullptr, nullptr};
     int bounceUse = 0;
     uint8_t* dIn = nullptr; uint64_t dInCap = 0;
+    uint8_t* dPk = nullptr; uint64_t dPkCap = 0;     // a packed image on its way to dIn
     uint8_t* dWork = nullptr; uint64_t dWorkCap = 0;
     uint8_t* dText = nullptr; uint64_t dTextCap = 0;
     uint8_t* dHdr = nullptr; uint64_t dHdrCap = 0;
@@ -146,6 +174,8 @@ public:
     // run f(replica index) on the worker thread of every replica in `which` (bit mask) and wait; exceptions are rethrown
     void parallel(uint64_t which, const std::function<void(int)>& f);
     PinnedArena& arena();
+    // the ingest slots (streams, device and pinned buffers) outlive a pass: the next pass on this handle allocates nothing
+    std::vector<std::unique_ptr<FastaBatchIngest>>& ingestSlots() { return slotStore; }
 
 private:
     struct Worker {
@@ -161,6 +191,7 @@ private:
     std::vector<std::unique_ptr<Worker>> workers;
     std::unique_ptr<PinnedArena> pinned;
     std::mutex arenaMu;
+    std::vector<std::unique_ptr<FastaBatchIngest>> slotStore;
 };
 
 struct SeqConfig {                 // what the sequential schedule reads from MGMP_Params / MBGC_Params
@@ -206,6 +237,7 @@ struct SeqStats {
     uint64_t files = 0, contigs = 0, windows = 0, runs = 0, rerunContigs = 0, extensions = 0;
     uint64_t imageBytes = 0, textBytes = 0, launches = 0, ingestLaunches = 0, chunks = 0, pageableBytes = 0;
     double ingestMs = 0, matchMs = 0, packMs = 0, loadRefMs = 0, waitStageMs = 0;
+    uint64_t wireBytes = 0;
 };
 
 // One pass of the sequential schedule over a collection.  Pull interface: push file images in target order, call next()
@@ -216,7 +248,7 @@ public:
     ~SequentialPass();
     // image memory: from the set's pinned arena -> released by the pass as soon as it is on the device; anything else
     // must stay valid until the file's FILE_END event has been returned
-    void pushFile(const char* bytes, uint64_t n);
+    void pushFile(const char* bytes, uint64_t n, bool packed = false);
     void finishInput();
     bool wantsInput();
     void next(SeqEvent& ev);       // pointers in ev stay valid until the next call
@@ -271,7 +303,7 @@ private:
     uint64_t chunkSeq = 0;
 
     // staging: NSLOT ingest slots per replica, one stager thread per slot
-    std::vector<std::unique_ptr<FastaBatchIngest>> slots;   // [replica * NSLOT + slot]
+    std::vector<std::unique_ptr<FastaBatchIngest>>& slots;  // [replica * NSLOT + slot], owned by the replica set
     std::vector<bool> slotFree;
     std::vector<std::deque<StageMsg>> stageQ;                // per ingest slot
     std::vector<std::thread> stagers;

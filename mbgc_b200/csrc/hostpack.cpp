@@ -111,6 +111,167 @@ bool pack_block(const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t devOff, s
     return pack_scalar(src, n, dst, devOff, runs, maxRuns, 0);
 }
 
+// ---- FASTA file images -------------------------------------------------------------------------------------
+
+namespace {
+
+struct LineEnds {  // the progression of '\n' being followed
+    uint64_t first = 0, last = 0, stride = 0;
+    uint32_t count = 0;
+};
+
+inline bool flush_line_ends(LineEnds& nl, std::vector<ExcRun>& runs, size_t maxRuns) {
+    if (nl.count == 0) return true;
+    if (runs.size() >= maxRuns) return false;
+    runs.push_back(ExcRun{nl.first, nl.count, static_cast<uint32_t>('\n') | (static_cast<uint32_t>(nl.count > 1 ? nl.stride : 0) << 8)});
+    nl.count = 0;
+    return true;
+}
+
+constexpr uint32_t LINE_RUN_CAP = 8192;  // line ends per run: the device patches a run with one warp
+
+inline bool on_line_end(LineEnds& nl, uint64_t p, std::vector<ExcRun>& runs, size_t maxRuns) {
+    if (nl.count >= 1) {
+        const uint64_t d = p - nl.last;
+        if (nl.stride == 0 && d < (1u << 24)) nl.stride = d;  // the second line end of a run sets the distance
+        if (d == nl.stride && nl.count < LINE_RUN_CAP) {
+            nl.count++;
+            nl.last = p;
+            return true;
+        }
+    }
+    const uint64_t keep = nl.count >= 1 && p - nl.last == nl.stride ? nl.stride : 0;  // a full run: the next one goes on alike
+    if (!flush_line_ends(nl, runs, maxRuns)) return false;
+    nl.first = nl.last = p;
+    nl.count = 1;
+    nl.stride = keep;
+    return true;
+}
+
+inline bool image_exception(LineEnds& nl, uint64_t p, uint8_t c, std::vector<ExcRun>& runs, size_t maxRuns) {
+    return c == '\n' ? on_line_end(nl, p, runs, maxRuns) : add_exception(runs, maxRuns, p, c);
+}
+
+// src[0 .. n) = bytes base .. base + n of the image (base a multiple of 64), dst = where their codes go
+bool image_scalar(const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t base, LineEnds& nl, std::vector<ExcRun>& runs, size_t maxRuns,
+                  uint64_t from) {
+    for (uint64_t i = from; i < n; i += 4) {  // from is a multiple of 4
+        uint8_t b = 0;
+        for (uint64_t k = 0; k < 4 && i + k < n; k++) {
+            const uint8_t c = src[i + k];
+            b |= static_cast<uint8_t>(((c >> 1) & 3) << (2 * k));
+            if (!is_acgt(c) && !image_exception(nl, base + i + k, c, runs, maxRuns)) return false;
+        }
+        dst[i >> 2] = b;
+    }
+    return true;
+}
+
+__attribute__((target("avx2"))) bool image_avx2(const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t base, LineEnds& nl,
+                                                std::vector<ExcRun>& runs, size_t maxRuns) {
+    const __m256i lut = _mm256_setr_epi8(-1, 0x41, -1, 0x43, 0x54, -1, -1, 0x47, -1, -1, -1, -1, -1, -1, -1, -1,  //
+                                         -1, 0x41, -1, 0x43, 0x54, -1, -1, 0x47, -1, -1, -1, -1, -1, -1, -1, -1);
+    const __m256i lowNib = _mm256_set1_epi8(0x0f);
+    const __m256i three = _mm256_set1_epi8(3);
+    const __m256i newline = _mm256_set1_epi8('\n');
+    const __m256i w14 = _mm256_set1_epi16(0x0401);
+    const __m256i w116 = _mm256_set1_epi32(0x00100001);
+    const __m256i gather = _mm256_setr_epi8(0, 4, 8, 12, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1,  //
+                                            0, 4, 8, 12, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1);
+    const bool ntOk = (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
+    uint64_t i = 0;
+    for (; i + 64 <= n; i += 64) {
+        uint32_t out[4];
+        uint64_t bad = 0, nls = 0;
+#pragma GCC unroll 2
+        for (int h = 0; h < 2; h++) {
+            const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i + 32 * h));
+            const __m256i expect = _mm256_shuffle_epi8(lut, _mm256_and_si256(v, lowNib));
+            const uint32_t valid = static_cast<uint32_t>(_mm256_movemask_epi8(_mm256_cmpeq_epi8(expect, v)));
+            const uint32_t isNl = static_cast<uint32_t>(_mm256_movemask_epi8(_mm256_cmpeq_epi8(newline, v)));
+            const __m256i codes = _mm256_and_si256(_mm256_srli_epi16(v, 1), three);
+            const __m256i p16 = _mm256_maddubs_epi16(codes, w14);
+            const __m256i p32 = _mm256_madd_epi16(p16, w116);
+            const __m256i pb = _mm256_shuffle_epi8(p32, gather);
+            out[2 * h] = static_cast<uint32_t>(_mm256_extract_epi32(pb, 0));
+            out[2 * h + 1] = static_cast<uint32_t>(_mm256_extract_epi32(pb, 4));
+            bad |= static_cast<uint64_t>(~valid) << (32 * h);
+            nls |= static_cast<uint64_t>(isNl) << (32 * h);
+        }
+        const __m128i o = _mm_loadu_si128(reinterpret_cast<const __m128i*>(out));
+        if (ntOk)
+            _mm_stream_si128(reinterpret_cast<__m128i*>(dst + (i >> 2)), o);
+        else
+            _mm_storeu_si128(reinterpret_cast<__m128i*>(dst + (i >> 2)), o);
+        if (bad == 0) continue;
+        // the one byte that is not a base is the line end the progression predicts: count it and go on
+        if (bad == nls && (bad & (bad - 1)) == 0 && nl.count >= 1 && nl.stride && nl.count < LINE_RUN_CAP &&
+            base + i + static_cast<uint64_t>(__builtin_ctzll(bad)) == nl.last + nl.stride) {
+            nl.count++;
+            nl.last += nl.stride;
+            continue;
+        }
+        while (bad) {
+            const int k = __builtin_ctzll(bad);
+            // a long run of one byte (N): take all of it that lies in this group in one step
+            int runLen = 1;
+            const uint8_t c = src[i + k];
+            if (c != '\n') {
+                while (k + runLen < 64 && ((bad >> (k + runLen)) & 1) && src[i + k + runLen] == c) runLen++;
+            }
+            if (runLen > 1) {
+                bool merged = false;
+                if (!runs.empty()) {
+                    ExcRun& last = runs.back();
+                    if (last.off + last.len == base + i + k && last.byte == c && last.len <= 0xFFFFFFFFu - 64) {
+                        last.len += static_cast<uint32_t>(runLen);
+                        merged = true;
+                    }
+                }
+                if (!merged) {
+                    if (runs.size() >= maxRuns) return false;
+                    runs.push_back(ExcRun{base + i + static_cast<uint64_t>(k), static_cast<uint32_t>(runLen), c});
+                }
+                bad &= runLen + k >= 64 ? 0 : ~((1ull << (k + runLen)) - 1);
+            } else {
+                if (!image_exception(nl, base + i + k, c, runs, maxRuns)) return false;
+                bad &= bad - 1;
+            }
+        }
+    }
+    if (ntOk) _mm_sfence();
+    return image_scalar(src, n, dst, base, nl, runs, maxRuns, i);
+}
+
+struct ImagePackState {
+    LineEnds nl;
+    uint64_t done = 0;
+};
+
+}  // namespace
+
+ImagePacker::ImagePacker(uint8_t* dst, std::vector<ExcRun>& runs, size_t maxRuns)
+    : dst(dst), runs(runs), maxRuns(maxRuns), state(new ImagePackState()) {}
+
+ImagePacker::~ImagePacker() { delete static_cast<ImagePackState*>(state); }
+
+bool ImagePacker::add(const uint8_t* src, uint64_t n) {
+    static const bool haveAvx2 = __builtin_cpu_supports("avx2");
+    ImagePackState& st = *static_cast<ImagePackState*>(state);
+    if (st.done % 64) return false;  // only the last piece may have a length that is not a multiple of 64
+    const bool ok = haveAvx2 ? image_avx2(src, n, dst + st.done / 4, st.done, st.nl, runs, maxRuns)
+                             : image_scalar(src, n, dst + st.done / 4, st.done, st.nl, runs, maxRuns, 0);
+    st.done += n;
+    return ok;
+}
+
+bool ImagePacker::finish() { return flush_line_ends(static_cast<ImagePackState*>(state)->nl, runs, maxRuns); }
+
+bool pack_fasta_image(const uint8_t* src, uint64_t n, uint8_t* dst, std::vector<ExcRun>& runs, size_t maxRuns) {
+    ImagePacker p(dst, runs, maxRuns);
+    return p.add(src, n) && p.finish();
+}
+
 // ---- reverse complement ----------------------------------------------------------------------------------
 
 namespace {

@@ -22,14 +22,37 @@ namespace mbgc_b200 {
 
 struct ExcRun {          // a run of identical non-ACGT bytes, device layout (16 bytes)
     uint64_t off;        // byte offset in the device text buffer
-    uint32_t len;
-    uint32_t byte;
+    uint32_t len;        // number of bytes
+    uint32_t byte;       // bits 0-7 the byte; bits 8-31 the distance between two of them (0: they are adjacent) -- the line
+                         // ends of a FASTA file are ONE run (pack_fasta_image)
 };
 
 // packs n bytes of src (4 bases per byte, first base in the lowest bits: code = (c >> 1) & 3, i.e. A 0, C 1, T 2,
 // G 3) into dst[(n + 3) / 4]; appends exception runs (offsets relative to devOff).  Returns false -- dst contents
 // then undefined -- as soon as more than maxRuns runs would be needed.
 bool pack_block(const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t devOff, std::vector<ExcRun>& runs, size_t maxRuns);
+
+// A whole FASTA file image, packed like pack_block does.  Line ends come at a fixed distance in a well-formed file: they are
+// recognised as an arithmetic progression and leave as one run (first offset, count, distance) instead of one run per line;
+// header lines and everything else that is not A/C/G/T go the ordinary way.  The image a device rebuilds from (dst, runs) is
+// byte-identical to src whatever it contains -- nothing is assumed about the format, only exploited.
+bool pack_fasta_image(const uint8_t* src, uint64_t n, uint8_t* dst, std::vector<ExcRun>& runs, size_t maxRuns);
+// the same for an image that arrives in pieces (a reader's buffer that stays in the cache): every piece but the last a
+// multiple of 64 bytes long
+class ImagePacker {
+public:
+    ImagePacker(uint8_t* dst, std::vector<ExcRun>& runs, size_t maxRuns);
+    ~ImagePacker();
+    ImagePacker(const ImagePacker&) = delete;
+    ImagePacker& operator=(const ImagePacker&) = delete;
+    bool add(const uint8_t* src, uint64_t n);   // false: too many runs
+    bool finish();
+private:
+    uint8_t* dst;
+    std::vector<ExcRun>& runs;
+    size_t maxRuns;
+    void* state;
+};
 
 // dst[n - 1 - i] = lut[src[i]]: the reverse complement the reference computes with upperReverseComplement
 // (utils/helper.cpp:405-410) through its 256-entry table (:312-358).  AVX2 where the CPU has it and the table has the

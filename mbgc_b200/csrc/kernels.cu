@@ -949,8 +949,47 @@ __global__ void __launch_bounds__(256) k_patch_exceptions(const ExcRunDev* __res
     const uint32_t warpsTotal = gridDim.x * (blockDim.x >> 5);
     for (uint32_t r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < nRuns; r += warpsTotal) {
         const ExcRunDev e = runs[r];
-        for (uint32_t k = lane; k < e.len; k += 32) text[e.off + k] = static_cast<uint8_t>(e.byte);
+        const uint64_t step = (e.byte >> 8) ? (e.byte >> 8) : 1u;  // bits 8-31: distance between the bytes of the run (line ends)
+        for (uint32_t k = lane; k < e.len; k += 32) text[e.off + k * step] = static_cast<uint8_t>(e.byte);
     }
+}
+
+// a whole file image that travelled 4 bases per byte (hostpack.cpp: pack_fasta_image): 16 bytes of text per thread
+__global__ void __launch_bounds__(256) k_unpack_image(const uint32_t* __restrict__ packed, uint64_t n, uint8_t* __restrict__ text) {
+    const uint64_t groups = (n + 15) / 16;
+    for (uint64_t g = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; g < groups;
+         g += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+        const uint32_t w = __ldg(packed + g);
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t q = (w >> (8 * j)) & 0xffu;
+            const uint32_t sel = (q & 3u) | ((q & 0xcu) << 2) | ((q & 0x30u) << 4) | ((q & 0xc0u) << 6);
+            o[j] = __byte_perm(0x47544341u, 0u, sel);
+        }
+        if (g * 16 + 16 <= n) {
+            reinterpret_cast<uint4*>(text)[g] = make_uint4(o[0], o[1], o[2], o[3]);
+        } else {
+            for (uint64_t k = g * 16; k < n; k++) text[k] = static_cast<uint8_t>(o[(k & 15) >> 2] >> (8 * (k & 3)));
+        }
+    }
+}
+
+int launch_unpack_image(const uint8_t* packed, uint64_t n, const ExcRunDev* runs, uint32_t nRuns, uint8_t* text, cudaStream_t st) {
+    int launches = 0;
+    if (n) {
+        const uint64_t blocks = ((n + 15) / 16 + 255) / 256;
+        const uint64_t cap = static_cast<uint64_t>(device_sm_count()) * 16;
+        k_unpack_image<<<static_cast<unsigned>(blocks < cap ? blocks : cap), 256, 0, st>>>(reinterpret_cast<const uint32_t*>(packed), n, text);
+        launches++;
+    }
+    if (nRuns) {
+        uint32_t blocksN = (nRuns + 7) / 8;
+        const uint32_t cap = static_cast<uint32_t>(device_sm_count()) * 8;
+        k_patch_exceptions<<<blocksN < cap ? blocksN : cap, 256, 0, st>>>(runs, nRuns, text);
+        launches++;
+    }
+    return launches;
 }
 
 int launch_unpack(const PackedBlock* blocks, uint32_t nBlocks, const uint8_t* packed, const ExcRunDev* runs, uint32_t nRuns,

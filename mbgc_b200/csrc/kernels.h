@@ -157,6 +157,7 @@ struct ExcRunDev {       // = mbgc_b200::ExcRun (hostpack.hpp): a run of one non
     uint32_t len;
     uint32_t byte;
 };
+int launch_unpack_image(const uint8_t* packed, uint64_t n, const ExcRunDev* runs, uint32_t nRuns, uint8_t* text, cudaStream_t st);
 int launch_unpack(const PackedBlock* blocks, uint32_t nBlocks, const uint8_t* packed, const ExcRunDev* runs, uint32_t nRuns,
                   uint8_t* text, cudaStream_t st);
 

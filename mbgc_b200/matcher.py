@@ -100,7 +100,7 @@ class SeqEvent(C.Structure):
 class SeqStats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("files", "contigs", "windows", "runs", "rerunContigs", "extensions",
                                           "imageBytes", "textBytes", "pageableBytes", "launches", "chunks")] + \
-               [(n, C.c_double) for n in ("ingestMs", "matchMs", "packMs", "loadRefMs", "waitStageMs")]
+               [(n, C.c_double) for n in ("ingestMs", "matchMs", "packMs", "loadRefMs", "waitStageMs")] + [("wireBytes", C.c_uint64)]
 
 
 class SeqResult(C.Structure):
@@ -160,6 +160,17 @@ def load_library():
     L.mbgcg_image_alloc.argtypes = [vp, C.c_uint64]
     L.mbgcg_image_max.restype = C.c_uint64
     L.mbgcg_image_max.argtypes = [vp]
+    L.mbgcg_image_pack_bound.restype = C.c_uint64
+    L.mbgcg_image_pack_bound.argtypes = [C.c_uint64]
+    L.mbgcg_image_pack.restype = C.c_int
+    L.mbgcg_image_pack.argtypes = [vp, C.c_uint64, vp, C.c_uint64, u64p]
+    L.mbgcg_image_pack_file.restype = C.c_int
+    L.mbgcg_image_pack_file.argtypes = [C.c_char_p, vp, C.c_uint64, u64p, u64p]
+    L.mbgcg_seq_run_files.restype = C.c_int
+    L.mbgcg_seq_run_files.argtypes = [vp, C.POINTER(C.c_char_p), C.c_uint64, C.c_int, C.c_int, C.c_int, C.POINTER(SeqResult),
+                                      C.POINTER(C.c_double)]
+    L.mbgcg_seq_push_packed.restype = C.c_int
+    L.mbgcg_seq_push_packed.argtypes = [vp, vp]
     L.mbgcg_image_free.restype = C.c_int
     L.mbgcg_image_free.argtypes = [vp, vp]
     L.mbgcg_set_host_mirror.argtypes = [vp, C.c_int]
@@ -391,16 +402,36 @@ class Matcher:
 
         return self._run_pass(len(images), provider, None, cfg, loadedPosArr, on_event, keep_streams)
 
-    def compressFiles(self, paths, cfg, loadedPosArr=None, readers=None, on_event=None, keep_streams=True):
-        """compressSequential for files on disk: `readers` threads read them (ahead of the pass, in order of need) straight
-        into pinned memory of the handle's arena, pageable memory when that is full.  gzip is not handled here (the
-        reference's own reader does that in the drop-in)."""
+    def compressFiles(self, paths, cfg, loadedPosArr=None, readers=None, on_event=None, keep_streams=True, pack=None):
+        """compressSequential for files on disk: `readers` threads bring them (ahead of the pass, in order of need) into pinned
+        memory of the handle's arena -- packed 4 bases per byte on the way (mbgcg_image_pack_file;
+        pack=False or MBGC_B200_PACK_IMAGES=0: read as they are) -- or into pageable memory when the arena is full.
+        gzip is not handled here (the reference's own reader does that in the drop-in)."""
         import threading
+        if pack is None:
+            pack = os.environ.get("MBGC_B200_PACK_IMAGES", "1") != "0"
+        if on_event is None:
+            # the whole thing inside the library: reader threads, pinned arena, the pass (no Python between a file and the device)
+            n = len(paths)
+            readers = max(1, min(readers or (os.cpu_count() or 1), 64, max(n, 1)))
+            loaded = list(loadedPosArr) if loadedPosArr is not None else [self.getLoadingPosition()]
+            arr = (C.c_uint64 * len(loaded))(*loaded)
+            self._check(self.lib.mbgcg_seq_begin(self.h, C.byref(cfg), arr, len(loaded)))
+            cpaths = (C.c_char_p * max(n, 1))(*[os.fsencode(x) for x in paths])
+            host = (C.c_double * 2)()
+
+            def call(res):
+                return self.lib.mbgcg_seq_run_files(self.h, cpaths, n, readers, int(bool(pack)), int(bool(keep_streams)), C.byref(res), host)
+            out, info = self._finish_run(call, keep_streams)
+            info["host"] = dict(reader_busy_s=host[0] / 1e3, feed_wait_s=host[1] / 1e3, readers=readers, packed=bool(pack))
+            return out, info
+        pack = False   # the event loop pushes with mbgcg_seq_push_file
         n = len(paths)
         readers = max(1, min(readers or (os.cpu_count() or 1), 32, max(n, 1)))
         ready = [None] * n
         cond = threading.Condition()
         state = {"next": 0, "turn": 0, "consumed": 0, "stop": False}
+        prof = {"reader_busy_s": 0.0, "reader_turn_wait_s": 0.0, "reader_alloc_wait_s": 0.0, "feed_wait_s": 0.0}
         arena_max = self.lib.mbgcg_image_max(self.h)
         keep = {}
 
@@ -411,21 +442,41 @@ class Matcher:
                     if i >= n or state["stop"]:
                         return
                     state["next"] = i + 1
+                    t0 = time.perf_counter()
                     cond.wait_for(lambda: i < state["consumed"] + 64 or state["stop"])
                     cond.wait_for(lambda: state["turn"] == i or state["stop"])   # pinned memory goes out in file order
+                    prof["reader_turn_wait_s"] += time.perf_counter() - t0
                     if state["stop"]:
                         return
                 size = os.path.getsize(paths[i])
                 p = None
-                if 0 < size <= arena_max:
+                want = self.lib.mbgcg_image_pack_bound(size) if pack else size
+                t0 = time.perf_counter()
+                if 0 < size and want <= arena_max:
                     for _ in range(20000):
-                        p = self.lib.mbgcg_image_alloc(self.h, size)
+                        p = self.lib.mbgcg_image_alloc(self.h, want)
                         if p or state["stop"]:
                             break
                         time.sleep(50e-6)
+                t1 = time.perf_counter()
                 with cond:
                     state["turn"] = i + 1
+                    prof["reader_alloc_wait_s"] += t1 - t0
                     cond.notify_all()
+                t0 = time.perf_counter()
+                if p and pack:
+                    used, fsize = C.c_uint64(), C.c_uint64()
+                    rc = self.lib.mbgcg_image_pack_file(os.fsencode(paths[i]), p, want, C.byref(used), C.byref(fsize))
+                    if rc == 0 and fsize.value != size:
+                        raise IOError(f"{paths[i]} changed size while it was read")
+                    if rc == 0:
+                        with cond:
+                            ready[i] = (p, used.value | (1 << 63))
+                            prof["reader_busy_s"] += time.perf_counter() - t0
+                            cond.notify_all()
+                        continue
+                    self.lib.mbgcg_image_free(self.h, p)   # too many exceptional bytes: the file travels as it is
+                    p = None
                 if p:
                     buf = (C.c_char * size).from_address(p)
                 else:
@@ -443,6 +494,7 @@ class Matcher:
                         got += k
                 with cond:
                     ready[i] = (p, size)
+                    prof["reader_busy_s"] += time.perf_counter() - t0
                     cond.notify_all()
 
         threads = [threading.Thread(target=work, daemon=True) for _ in range(readers)]
@@ -454,7 +506,9 @@ class Matcher:
                 if ready[i] is None:
                     if not block:
                         return None
+                    t0 = time.perf_counter()
                     cond.wait_for(lambda: ready[i] is not None)
+                    prof["feed_wait_s"] += time.perf_counter() - t0
                 return ready[i]
 
         def consumed(i, drop=True):
@@ -465,7 +519,9 @@ class Matcher:
                 cond.notify_all()
 
         try:
-            return self._run_pass(n, None, (provider, consumed), cfg, loadedPosArr, on_event, keep_streams)
+            out, info = self._run_pass(n, None, (provider, consumed), cfg, loadedPosArr, on_event, keep_streams)
+            info["host"] = dict(prof, readers=readers, packed=bool(pack))
+            return out, info
         finally:
             with cond:
                 state["stop"] = True
@@ -507,13 +563,20 @@ class Matcher:
                 return -1
 
         cb = NEXT_IMAGE_FN(next_image)
-        res = SeqResult()
-        st = SeqStats()
-        try:
+
+        def call(res):
             rc = self.lib.mbgcg_seq_run(self.h, cb, None, int(bool(keep_streams)), C.byref(res))
             if state["err"] is not None:
                 raise state["err"]
-            self._check(rc)
+            return rc
+        return self._finish_run(call, keep_streams)
+
+    def _finish_run(self, call, keep_streams):
+        """call(res) runs the pass to its end (mbgcg_seq_run / mbgcg_seq_run_files); -> (streams, info), pass closed"""
+        res = SeqResult()
+        st = SeqStats()
+        try:
+            self._check(call(res))
             nf = int(res.nFiles)
 
             def arr64(p):

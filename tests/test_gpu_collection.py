@@ -146,6 +146,69 @@ def test_bad_files_report_the_readers_status(tmp_path):
         g.close()
 
 
+def _files_pass(paths, mode, pack, chunk_bytes=1 << 20):
+    recs0 = read_fasta(paths[0])
+    c0 = recs0[0][1]
+    limit = max(min(reference_factor(len(paths)) * max(os.path.getsize(paths[0]), 1 << 21) * 2, 2**32 - 1), len(c0))
+    g = mbgc_b200.Matcher(limit, 32, 16, 1, 24 if mode >= 2 else 16, device=0)
+    try:
+        g.disableSlidingWindow()
+        g.loadRef(c0, True, True, 0)
+        out, info = g.compressFiles(paths, SeqConfig.for_mode(mode, chunk_bytes), readers=4, pack=pack)
+        info["table"] = g.table()
+        return out, info
+    finally:
+        g.close()
+
+
+@pytest.mark.parametrize("mode", [1, 3])
+def test_packed_file_images_equal_plain_ones(mixed_dir, tmp_path, mode):
+    """file images that cross PCIe 4 bases per byte (mbgcg_image_pack from an mmap of the file, line ends as one run,
+    rebuilt byte for byte on the device) give the same streams, headers, meta data and index as images read as they are --
+    including files the packer refuses (CRLF line ends, lower case: too many exceptional bytes), N runs across line ends,
+    a file without a final line end, an empty file and one that is not FASTA"""
+    g = synth_collection(2, 120_000, 77, 2e-3, 2e-4)[1]
+    extra = []
+    withN = g.copy()
+    withN[1000:9000] = ord("N")
+    withN[50_000] = ord("R")
+    p = tmp_path / "withN.fna"
+    write_fasta(str(p), "genome with an N run and an IUPAC code", withN, width=60)
+    extra.append(str(p))
+    p = tmp_path / "nofinal.fna"
+    write_fasta(str(p), "no final line end", g[:70_001], width=80)
+    open(p, "wb").write(open(p, "rb").read().rstrip(b"\n"))
+    extra.append(str(p))
+    p = tmp_path / "crlf.fna"
+    write_fasta(str(p), "crlf", g[:40_000], width=80)
+    open(p, "wb").write(open(p, "rb").read().replace(b"\n", b"\r\n"))
+    extra.append(str(p))
+    p = tmp_path / "lower.fna"
+    write_fasta(str(p), "soft-masked", g[:30_000], width=80)
+    raw = open(p, "rb").read()
+    open(p, "wb").write(raw[:20] + raw[20:].lower())
+    extra.append(str(p))
+    p = tmp_path / "empty.fna"
+    open(p, "wb").close()
+    extra.append(str(p))
+    p = tmp_path / "notfasta.txt"
+    open(p, "wb").write(b"hello\nworld\n" * 100)
+    extra.append(str(p))
+    p = tmp_path / "oneline.fna"
+    open(p, "wb").write(b">one line\n" + bytes(g[:5000]) + b"\n>second\n" + bytes(g[5000:5100]) + b"\n")
+    extra.append(str(p))
+    paths = list(mixed_dir[:9]) + extra
+    plain, pi = _files_pass(paths, mode, False)
+    packed, qi = _files_pass(paths, mode, True)
+    for name in STREAMS:
+        assert packed[name] == plain[name], f"stream {name} differs between packed and plain images"
+    for k in ("seqCounts", "dnaLineLens", "status", "headers", "refExtSizes", "unmatched", "matches", "extensions", "digest"):
+        assert qi[k] == pi[k], k
+    assert np.array_equal(qi["table"], pi["table"])
+    assert qi["stats"]["wireBytes"] < 0.45 * pi["stats"]["wireBytes"], "most of the bytes must travel packed"
+    assert pi["stats"]["wireBytes"] == pi["stats"]["imageBytes"]
+
+
 # ---- the batch-frozen schedule of the reference's parallel mode ---------------------------------------------------------
 
 def check_parallel_schedule(paths, mode, devices, chunk_bytes, outrun):

@@ -174,6 +174,51 @@ def test_host_packer_round_trip():
     assert lib.mbgcg_selftest_pack(lower.ctypes.data, lower.size, out.ctypes.data) == 1
 
 
+def test_fasta_image_packer_round_trip():
+    """mbgcg_image_pack (hostpack.cpp: pack_fasta_image): whatever the file holds, header + codes + exception runs rebuild it
+    byte for byte; the line ends of a well-formed file leave as one run per 8192 lines, so a genome travels at a quarter of its
+    size; files with too many exceptional bytes are refused (they travel as they are)"""
+    import ctypes as C
+    lib = mbgc_b200.load_library()
+    lib.mbgcg_selftest_pack_image.restype = C.c_int
+    lib.mbgcg_selftest_pack_image.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    rng = np.random.default_rng(3)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+
+    def fasta(nrec, length, width, final=True, eol=b"\n"):
+        parts = []
+        for r in range(nrec):
+            parts.append(f">rec{r} some header text | x=1".encode() + eol)
+            s = acgt[rng.integers(0, 4, length)].copy()
+            if length > 2000:
+                s[500:1500] = ord("N")
+                s[1700] = ord("n")
+                s[1800:1810] = np.frombuffer(b"acgtRYKMac", dtype=np.uint8)
+            b = bytes(s)
+            parts.append(eol.join(b[i:i + width] for i in range(0, len(b), width)))
+            if final or r < nrec - 1:
+                parts.append(eol)
+        return np.frombuffer(b"".join(parts), dtype=np.uint8)
+
+    def run(img):
+        out = np.zeros(max(img.size, 1), dtype=np.uint8)
+        pb, nr = C.c_uint64(), C.c_uint64()
+        rc = lib.mbgcg_selftest_pack_image(img.ctypes.data, img.size, out.ctypes.data, C.byref(pb), C.byref(nr))
+        return rc, out[:img.size], pb.value, nr.value
+
+    big = fasta(1, 2_000_000, 80)
+    rc, out, pb, nr = run(big)
+    assert rc == 0 and np.array_equal(out, big)
+    assert pb < 0.26 * big.size and nr < 80, (pb, nr)
+    for img in (fasta(3, 100_003, 60), fasta(2, 7000, 80, final=False), fasta(1, 300_000, 1000),
+                np.frombuffer(b">x\nACGT", dtype=np.uint8), np.frombuffer(b"\n\n\n\n>a\n\nAC\n\n\nGT\n", dtype=np.uint8),
+                np.frombuffer(b">only a header", dtype=np.uint8)):
+        rc, out, pb, nr = run(img)
+        assert rc == 0 and np.array_equal(out, img), img.size
+    assert run(fasta(2, 9000, 70, eol=b"\r\n"))[0] == 1      # two exceptional bytes per line: refused
+    assert run(np.frombuffer(bytes(fasta(1, 20_000, 80)).lower(), dtype=np.uint8))[0] == 1
+
+
 def test_header_is_plain_c(tmp_path):
     """include/mbgc_b200.h is the drop-in boundary for any host language: it must compile as C99 on its own"""
     import os
