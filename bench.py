@@ -742,7 +742,7 @@ def measure_collection(args, rank, world, dist, local, peak):
     m.loadRef(base, True, True, 0)
     cfg = SeqConfig.for_mode(1)
     pos0 = m.getLoadingPosition()
-    readers = int(os.environ.get("MBGC_B200_BENCH_READERS", max(2, min(32, (os.cpu_count() or 1) // world - 3))))  # the commit loop, the worker and the stagers need cores too
+    readers = int(os.environ.get("MBGC_B200_BENCH_READERS", max(2, min(32, (os.cpu_count() or 1) // world - (3 if world == 1 else 2)))))  # the commit loop, the worker and the stagers need cores too
 
     def one_pass():
         m.setPosition(pos0, 0)   # back to the state after G0 (a near-identical collection never extends the reference)
