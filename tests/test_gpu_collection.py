@@ -209,6 +209,24 @@ def test_packed_file_images_equal_plain_ones(mixed_dir, tmp_path, mode):
     assert pi["stats"]["wireBytes"] == pi["stats"]["imageBytes"]
 
 
+def test_files_pass_errors_and_empty_list(mixed_dir, tmp_path):
+    """mbgcg_seq_run_files: a file that cannot be read ends the pass with an error (and leaves the handle usable), an empty
+    list is an empty pass"""
+    c0 = read_fasta(mixed_dir[0])[0][1]
+    g = mbgc_b200.Matcher(1 << 24, 32, 16, 1, 16, device=0)
+    try:
+        g.disableSlidingWindow()
+        g.loadRef(c0, True, True, 0)
+        with pytest.raises(mbgc_b200.MatcherError):
+            g.compressFiles([mixed_dir[8], str(tmp_path / "does_not_exist.fna"), mixed_dir[9]], SeqConfig.for_mode(1, 1 << 20), readers=3)
+        out, info = g.compressFiles([], SeqConfig.for_mode(1, 1 << 20))
+        assert info["seqCounts"] == [] and all(v == b"" for v in out.values())
+        out, info = g.compressFiles(list(mixed_dir[8:11]), SeqConfig.for_mode(1, 1 << 20), readers=2)
+        assert info["seqCounts"] == [len(read_fasta(p)) for p in mixed_dir[8:11]] and info["status"] == [-1, -1, -1]
+    finally:
+        g.close()
+
+
 # ---- the batch-frozen schedule of the reference's parallel mode ---------------------------------------------------------
 
 def check_parallel_schedule(paths, mode, devices, chunk_bytes, outrun):
