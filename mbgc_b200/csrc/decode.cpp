@@ -228,7 +228,7 @@ void Decoder::run(const DcParams& p, const DecodeStreamsHost& hs, const DecodeLa
     check(cudaMemsetAsync(dRef.p, 0, dRef.n, st), "memset(reference)");
     dBase.reset((static_cast<uint64_t>(nContigs) + 1) * 8);
     check(cudaMemcpyAsync(dBase.p, contigBase.data(), (static_cast<uint64_t>(nContigs) + 1) * 8, cudaMemcpyHostToDevice, st), "H2D(bases)");
-    dTileSeg.reset((dnaLen / DC_TILE + 2) * 4);
+    dTileSeg.reset(((dnaLen >> DC_TILE_SHIFT_MIN) + 2) * 4);
     uint8_t* ref = dRef.as<uint8_t>();
     uint8_t* dna = dDna.as<uint8_t>();
     refPos = REF_SHIFT;
@@ -241,9 +241,13 @@ void Decoder::run(const DcParams& p, const DecodeStreamsHost& hs, const DecodeLa
         const uint64_t segBegin = 4 * marksBefore(batchStart) + batchStart, segEnd = 4 * marksBefore(cEnd) + cEnd;
         const uint64_t d0 = contigBase[batchStart], d1 = contigBase[cEnd];
         if (d1 > d0) {
-            launches += launch_dc_tiles(dSegs.as<DcSeg>(), segBegin, segEnd, dBase.as<uint64_t>(), d0, dTileSeg.as<uint32_t>(), st);
-            launches += launch_dc_copy(dSegs.as<DcSeg>(), segEnd, dBase.as<uint64_t>(), dTileSeg.as<uint32_t>(), d0 / DC_TILE,
-                                       (d1 + DC_TILE - 1) / DC_TILE, d0, d1, ref, s, dna, st);
+            // long matches: large tiles (the walk over a tile's segments is overhead per tile); short ones: small tiles (the
+            // walk is the work, and it is serial within a tile)
+            const uint64_t matches = (segEnd - segBegin - (cEnd - batchStart)) / 4;
+            const uint64_t mean = (d1 - d0) / std::max<uint64_t>(matches, 1);
+            const int shift = mean >= 2048 ? DC_TILE_SHIFT_MAX : (mean >= 256 ? 14 : DC_TILE_SHIFT_MIN);
+            launches += launch_dc_tiles(dSegs.as<DcSeg>(), segBegin, segEnd, dBase.as<uint64_t>(), d0, shift, dTileSeg.as<uint32_t>(), st);
+            launches += launch_dc_copy(dSegs.as<DcSeg>(), segEnd, dBase.as<uint64_t>(), dTileSeg.as<uint32_t>(), shift, d0, d1, ref, s, dna, st);
             batches++;
         }
         batchStart = cEnd;

@@ -9,7 +9,7 @@
 //  * the CONTROL FLOW (how many bytes every piece has, where it reads from) depends on the six streams only, never on
 //    the reference's content.  k_dc_parse replays it -- one thread per target file, all targets at once -- and writes a
 //    list of segments (literal run | reference copy | right extension | left extension) with contig-relative positions;
-//  * given the segments, every OUTPUT BYTE is independent.  k_dc_copy writes the DNA: one CTA per 16 KiB of output walks
+//  * given the segments, every OUTPUT BYTE is independent.  k_dc_copy writes the DNA: one CTA per tile of output (8 to 64 KiB) walks
 //    the segments that intersect its tile; copies move 16 bytes per thread (aligned stores, two aligned loads and a byte
 //    shift for the source), extensions are done by a warp each behind a ballot prefix of their mismatch flags.
 //
@@ -579,53 +579,53 @@ __global__ void __launch_bounds__(32) k_dc_parse(DcParams p, DcStreams s, DcInde
 // ---- the copy pass --------------------------------------------------------------------------------------------------------------
 // which segment covers the first byte of every output tile (each tile start lies in exactly one segment of non-zero length)
 __global__ void __launch_bounds__(DC_THREADS) k_dc_tiles(const DcSeg* __restrict__ segs, uint64_t segBegin, uint64_t segEnd,
-                                                         const uint64_t* __restrict__ contigBase, uint64_t dstBegin,
+                                                         const uint64_t* __restrict__ contigBase, uint64_t dstBegin, int tileShift,
                                                          uint32_t* __restrict__ tileSeg) {
     const uint64_t s = segBegin + static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (s >= segEnd) return;
     const uint32_t len = segs[s].len;
     if (!len) return;
     const uint64_t a = contigBase[segs[s].meta >> 4] + segs[s].dst;
-    if (a == dstBegin) tileSeg[a / DC_TILE] = static_cast<uint32_t>(s);
-    for (uint64_t t = (a + DC_TILE - 1) / DC_TILE; t * DC_TILE < a + len; t++) tileSeg[t] = static_cast<uint32_t>(s);
+    const uint64_t tileBytes = 1ull << tileShift;
+    if (a == dstBegin) tileSeg[a >> tileShift] = static_cast<uint32_t>(s);
+    for (uint64_t t = (a + tileBytes - 1) >> tileShift; (t << tileShift) < a + len; t++) tileSeg[t] = static_cast<uint32_t>(s);
 }
 
-// dst[0 .. n) = src[0 .. n) by `nthr` threads (idx = this thread's rank): 16-byte aligned stores, the source through two
-// aligned 16-byte loads and a byte shift (sources are padded: up to 31 bytes behind src + n are read, never used)
-__device__ __forceinline__ void copy_bytes(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint64_t n, int idx, int nthr) {
-    uint64_t head = (16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15;
+// dst[0 .. n) = src[0 .. n) by `nthr` threads (idx = this thread's rank), n at most a tile: 16-byte aligned stores, the source
+// through two aligned 16-byte loads and a byte shift (sources are padded: up to 31 bytes behind src + n are read, never used).
+// The word offset of the shift is the same for the whole call: one loop per offset, so the words are picked at compile time.
+template <int J>
+__device__ __forceinline__ void copy_vectors(uint4* __restrict__ d, const uint4* __restrict__ q, uint32_t nvec, uint32_t bits, int idx, int nthr) {
+    for (uint32_t v = idx; v < nvec; v += nthr) {
+        const uint4 lo = q[v], hi = q[v + 1];
+        const uint32_t W[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+        d[v] = make_uint4(__funnelshift_r(W[J], W[J + 1], bits), __funnelshift_r(W[J + 1], W[J + 2], bits),
+                          __funnelshift_r(W[J + 2], W[J + 3], bits), __funnelshift_r(W[J + 3], W[J + 4], bits));
+    }
+}
+
+__device__ __forceinline__ void copy_bytes(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint64_t n64, int idx, int nthr) {
+    const uint32_t n = static_cast<uint32_t>(n64);
+    uint32_t head = (16u - (static_cast<uint32_t>(reinterpret_cast<uintptr_t>(dst)) & 15u)) & 15u;
     if (head > n) head = n;
-    for (uint64_t i = idx; i < head; i += nthr) dst[i] = src[i];
-    const uint64_t nvec = (n - head) >> 4;
+    for (uint32_t i = idx; i < head; i += nthr) dst[i] = src[i];
+    const uint32_t nvec = (n - head) >> 4;
     const uint8_t* sp = src + head;
-    const uint32_t sh = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(sp) & 15);
+    const uint32_t sh = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(sp)) & 15u;
     const uint4* q = reinterpret_cast<const uint4*>(sp - sh);
     uint4* d = reinterpret_cast<uint4*>(dst + head);
-    const uint32_t bits = (sh & 3) * 8;
-    const uint32_t j = sh >> 2;
-    for (uint64_t v = idx; v < nvec; v += nthr) {
-        const uint4 lo = q[v];
-        uint4 out = lo;
-        if (sh) {
-            const uint4 hi = q[v + 1];
-            const uint32_t W[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-            uint32_t r[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                uint32_t a, b;
-                switch (j) {  // uniform over the call
-                    case 0: a = W[k]; b = W[k + 1]; break;
-                    case 1: a = W[k + 1]; b = W[k + 2]; break;
-                    case 2: a = W[k + 2]; b = W[k + 3]; break;
-                    default: a = W[k + 3]; b = W[k + 4]; break;
-                }
-                r[k] = __funnelshift_r(a, b, bits);
-            }
-            out = make_uint4(r[0], r[1], r[2], r[3]);
+    const uint32_t bits = (sh & 3u) * 8u;
+    if (sh == 0) {
+        for (uint32_t v = idx; v < nvec; v += nthr) d[v] = q[v];
+    } else {
+        switch (sh >> 2) {  // uniform over the call
+            case 0: copy_vectors<0>(d, q, nvec, bits, idx, nthr); break;
+            case 1: copy_vectors<1>(d, q, nvec, bits, idx, nthr); break;
+            case 2: copy_vectors<2>(d, q, nvec, bits, idx, nthr); break;
+            default: copy_vectors<3>(d, q, nvec, bits, idx, nthr); break;
         }
-        d[v] = out;
     }
-    for (uint64_t i = head + (nvec << 4) + idx; i < n; i += nthr) dst[i] = src[i];
+    for (uint32_t i = head + (nvec << 4) + idx; i < n; i += nthr) dst[i] = src[i];
 }
 
 // one extension by one warp: byte w of the walk reads the reference at src + w (right) or src - 1 - w (left), is a mismatch
@@ -652,19 +652,19 @@ __device__ __forceinline__ void copy_extension(const DcSeg& g, uint8_t* __restri
     }
 }
 
-// One CTA per 16 KiB of output.  The segments that may touch the tile are staged in shared memory a chunk at a time (one
+// One CTA per tile of output (8 to 64 KiB, chosen per batch from the mean match length).  The segments that may touch the tile are staged in shared memory a chunk at a time (one
 // coalesced load instead of a chain of dependent ones); long copies are done by the whole CTA, everything else by one warp per
 // segment.  Destinations are disjoint, so the warps never wait for each other.
 constexpr int DC_STAGE = 256;
 
 __global__ void __launch_bounds__(DC_THREADS) k_dc_copy(const DcSeg* __restrict__ segs, uint64_t segEnd, const uint64_t* __restrict__ contigBase,
-                                                        const uint32_t* __restrict__ tileSeg, uint64_t tileBegin, uint64_t dstBegin,
-                                                        uint64_t dstEnd, const uint8_t* __restrict__ ref, DcStreams s,
+                                                        const uint32_t* __restrict__ tileSeg, uint64_t tileBegin, int tileShift,
+                                                        uint64_t dstBegin, uint64_t dstEnd, const uint8_t* __restrict__ ref, DcStreams s,
                                                         uint8_t* __restrict__ dna) {
     __shared__ uint4 sSeg[DC_STAGE][2];
     __shared__ uint64_t sAbs[DC_STAGE];
     const uint64_t tile = tileBegin + blockIdx.x;
-    uint64_t lo = tile * DC_TILE, hi = lo + DC_TILE;
+    uint64_t lo = tile << tileShift, hi = lo + (1ull << tileShift);
     if (lo < dstBegin) lo = dstBegin;
     if (hi > dstEnd) hi = dstEnd;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -679,7 +679,9 @@ __global__ void __launch_bounds__(DC_THREADS) k_dc_copy(const DcSeg* __restrict_
                 const uint4* q = reinterpret_cast<const uint4*>(segs + si);
                 q0 = q[0];
                 q1 = q[1];
-                a = q1.x ? contigBase[q1.w >> 4] + (q0.x | (static_cast<uint64_t>(q0.y) << 32)) : 0;  // empty segments are skipped
+                // empty segments carry their position too: the walk over a tile ends at the first segment behind it, empty or
+                // not (most slots of a near-identical collection are empty: no literals, no extensions between two matches)
+                a = contigBase[q1.w >> 4] + (q0.x | (static_cast<uint64_t>(q0.y) << 32));
             }
             sSeg[threadIdx.x][0] = q0;
             sSeg[threadIdx.x][1] = q1;
@@ -691,7 +693,7 @@ __global__ void __launch_bounds__(DC_THREADS) k_dc_copy(const DcSeg* __restrict_
         for (int k = 0; k < chunk; k++) {
             const uint4 q1 = sSeg[k][1];
             const uint64_t a = sAbs[k];
-            if (a == UINT64_MAX || (q1.x && a >= hi)) {
+            if (a >= hi) {  // (UINT64_MAX: behind the list)
                 done = true;
                 break;
             }
@@ -707,7 +709,7 @@ __global__ void __launch_bounds__(DC_THREADS) k_dc_copy(const DcSeg* __restrict_
         for (int k = warp; k < chunk; k += DC_THREADS / 32) {
             const uint4 q1 = sSeg[k][1];
             const uint64_t a = sAbs[k];
-            if (a == UINT64_MAX || (q1.x && a >= hi)) break;
+            if (a >= hi) break;
             if (!q1.x) continue;
             const uint4 q0 = sSeg[k][0];
             const uint32_t kind = q1.w & 3;
@@ -799,19 +801,19 @@ int launch_dc_parse(const DcParams& p, const DcStreams& s, const DcIndex& ix, co
     return 1;
 }
 
-int launch_dc_tiles(const DcSeg* segs, uint64_t segBegin, uint64_t segEnd, const uint64_t* contigBase, uint64_t dstBegin, uint32_t* tileSeg,
-                    cudaStream_t st) {
+int launch_dc_tiles(const DcSeg* segs, uint64_t segBegin, uint64_t segEnd, const uint64_t* contigBase, uint64_t dstBegin, int tileShift,
+                    uint32_t* tileSeg, cudaStream_t st) {
     if (segEnd <= segBegin) return 0;
-    k_dc_tiles<<<blocks_for(segEnd - segBegin, DC_THREADS), DC_THREADS, 0, st>>>(segs, segBegin, segEnd, contigBase, dstBegin, tileSeg);
+    k_dc_tiles<<<blocks_for(segEnd - segBegin, DC_THREADS), DC_THREADS, 0, st>>>(segs, segBegin, segEnd, contigBase, dstBegin, tileShift, tileSeg);
     return 1;
 }
 
-int launch_dc_copy(const DcSeg* segs, uint64_t segEnd, const uint64_t* contigBase, const uint32_t* tileSeg, uint64_t tileBegin,
-                   uint64_t tileEnd, uint64_t dstBegin, uint64_t dstEnd, const uint8_t* ref, const DcStreams& s, uint8_t* dna,
-                   cudaStream_t st) {
-    if (tileEnd <= tileBegin || dstEnd <= dstBegin) return 0;
-    k_dc_copy<<<static_cast<unsigned>(tileEnd - tileBegin), DC_THREADS, 0, st>>>(segs, segEnd, contigBase, tileSeg, tileBegin, dstBegin, dstEnd,
-                                                                                ref, s, dna);
+int launch_dc_copy(const DcSeg* segs, uint64_t segEnd, const uint64_t* contigBase, const uint32_t* tileSeg, int tileShift, uint64_t dstBegin,
+                   uint64_t dstEnd, const uint8_t* ref, const DcStreams& s, uint8_t* dna, cudaStream_t st) {
+    if (dstEnd <= dstBegin) return 0;
+    const uint64_t tileBegin = dstBegin >> tileShift, tileEnd = ((dstEnd - 1) >> tileShift) + 1;
+    k_dc_copy<<<static_cast<unsigned>(tileEnd - tileBegin), DC_THREADS, 0, st>>>(segs, segEnd, contigBase, tileSeg, tileBegin, tileShift, dstBegin,
+                                                                                dstEnd, ref, s, dna);
     return 1;
 }
 

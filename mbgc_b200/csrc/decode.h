@@ -7,7 +7,7 @@
 namespace mbgc_b200 {
 
 constexpr uint32_t DC_COUNT_BLOCK = 4096;   // bytes of a stream one CTA of the marker passes looks at
-constexpr uint32_t DC_TILE = 16384;         // output bytes one CTA of the copy pass writes
+constexpr int DC_TILE_SHIFT_MIN = 13, DC_TILE_SHIFT_MAX = 16;   // output bytes one CTA of the copy pass writes: 8 .. 64 KiB
 constexpr int DC_LEN_CHUNK = 64;            // 16-bit words of the frugal length stream per chunk map
 constexpr int DC_LEN_BLOCK = 256;           // chunk maps per block map
 
@@ -73,10 +73,9 @@ int launch_dc_len_expand(const uint8_t* src, uint64_t nBytes, uint32_t* chunkMap
                          uint64_t* total, uint32_t* out, uint64_t outCap, cudaStream_t st);
 int launch_dc_parse(const DcParams& p, const DcStreams& s, const DcIndex& ix, const DcTarget* targets, uint32_t nTargets, DcSeg* segs,
                     uint64_t* contigLen, uint64_t* contigUnmatched, uint32_t* error, cudaStream_t st);
-int launch_dc_tiles(const DcSeg* segs, uint64_t segBegin, uint64_t segEnd, const uint64_t* contigBase, uint64_t dstBegin, uint32_t* tileSeg,
-                    cudaStream_t st);
-int launch_dc_copy(const DcSeg* segs, uint64_t segEnd, const uint64_t* contigBase, const uint32_t* tileSeg, uint64_t tileBegin,
-                   uint64_t tileEnd, uint64_t dstBegin, uint64_t dstEnd, const uint8_t* ref, const DcStreams& s, uint8_t* dna,
-                   cudaStream_t st);
+int launch_dc_tiles(const DcSeg* segs, uint64_t segBegin, uint64_t segEnd, const uint64_t* contigBase, uint64_t dstBegin, int tileShift,
+                    uint32_t* tileSeg, cudaStream_t st);
+int launch_dc_copy(const DcSeg* segs, uint64_t segEnd, const uint64_t* contigBase, const uint32_t* tileSeg, int tileShift, uint64_t dstBegin,
+                   uint64_t dstEnd, const uint8_t* ref, const DcStreams& s, uint8_t* dna, cudaStream_t st);
 
 }  // namespace mbgc_b200

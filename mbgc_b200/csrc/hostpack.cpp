@@ -128,7 +128,7 @@ inline bool flush_line_ends(LineEnds& nl, std::vector<ExcRun>& runs, size_t maxR
     return true;
 }
 
-constexpr uint32_t LINE_RUN_CAP = 8192;  // line ends per run: the device patches a run with one warp
+constexpr uint32_t LINE_RUN_CAP = 512;   // line ends per run: the device patches a run with one warp (16 steps of 32 bytes)
 
 inline bool on_line_end(LineEnds& nl, uint64_t p, std::vector<ExcRun>& runs, size_t maxRuns) {
     if (nl.count >= 1) {
