@@ -304,22 +304,23 @@ __device__ Walk warp_walk(ParseCtx& x, uint64_t fp, uint64_t l0, uint64_t guard,
         const uint64_t l = l0 + w.mism + c;
         int sc = 0;
         if (useScore) {
+            // one scan of (sum, least non-empty prefix sum): (a then b) = (a.sum + b.sum, min(a.min, a.sum + b.min))
             const int d = f ? x.p.mismatchPenalty : -x.p.matchBonus;
-            int P = d;
+            int P = d, M = d;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(0xFFFFFFFFu, P, o);
-                if (lane >= o) P += t;
+                const int tp = __shfl_up_sync(0xFFFFFFFFu, P, o);
+                const int tm = __shfl_up_sync(0xFFFFFFFFu, M, o);
+                if (lane >= o) {
+                    const int m2 = tp + M;   // the earlier block comes first: its sum shifts this block's prefixes
+                    M = tm < m2 ? tm : m2;
+                    P += tp;
+                }
             }
-            const int Pe = P - d;  // sum of the steps before this one
-            int M = lane >= 1 ? Pe : INT32_MAX;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(0xFFFFFFFFu, M, o);
-                if (lane >= o && t < M) M = t;
-            }
-            const int floor0 = M == INT32_MAX ? s0 : (s0 > -M ? s0 : -M);
-            sc = Pe + floor0;
+            // this step starts from what the steps before it left: the inclusive values of the lane below
+            const int Pe = __shfl_up_sync(0xFFFFFFFFu, P, 1);
+            const int Me = __shfl_up_sync(0xFFFFFFFFu, M, 1);
+            sc = lane == 0 ? s0 : Pe + (s0 > -Me ? s0 : -Me);
         }
         const bool lim = i >= maxSteps;
         const bool A = lim || (stopAtGuard && l == guard) || (useScore && sc >= x.p.scoreThreshold);
@@ -594,10 +595,21 @@ __global__ void __launch_bounds__(DC_THREADS) k_dc_tiles(const DcSeg* __restrict
 // dst[0 .. n) = src[0 .. n) by `nthr` threads (idx = this thread's rank), n at most a tile: 16-byte aligned stores, the source
 // through two aligned 16-byte loads and a byte shift (sources are padded: up to 31 bytes behind src + n are read, never used).
 // The word offset of the shift is the same for the whole call: one loop per offset, so the words are picked at compile time.
+// Every lane loads ONE aligned 16-byte piece; the piece behind it comes from the next lane by shuffle (lane 31 loads it): the
+// kernel was bound by L1 sector throughput with two loads per store.  The calling warp is converged (idx = lane or threadIdx.x).
 template <int J>
 __device__ __forceinline__ void copy_vectors(uint4* __restrict__ d, const uint4* __restrict__ q, uint32_t nvec, uint32_t bits, int idx, int nthr) {
-    for (uint32_t v = idx; v < nvec; v += nthr) {
-        const uint4 lo = q[v], hi = q[v + 1];
+    const int lane = idx & 31;
+    for (uint32_t v0 = idx - lane; v0 < nvec; v0 += nthr) {  // warp-uniform
+        const uint32_t v = v0 + lane;
+        const uint4 lo = q[v < nvec ? v : nvec];   // q[nvec] is readable (the buffers are padded)
+        uint4 hi;
+        hi.x = __shfl_down_sync(0xFFFFFFFFu, lo.x, 1);
+        hi.y = __shfl_down_sync(0xFFFFFFFFu, lo.y, 1);
+        hi.z = __shfl_down_sync(0xFFFFFFFFu, lo.z, 1);
+        hi.w = __shfl_down_sync(0xFFFFFFFFu, lo.w, 1);
+        if (lane == 31 && v < nvec) hi = q[v + 1];
+        if (v >= nvec) continue;
         const uint32_t W[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
         d[v] = make_uint4(__funnelshift_r(W[J], W[J + 1], bits), __funnelshift_r(W[J + 1], W[J + 2], bits),
                           __funnelshift_r(W[J + 2], W[J + 3], bits), __funnelshift_r(W[J + 3], W[J + 4], bits));
