@@ -78,7 +78,11 @@ uint64_t pack_image_from_file(const char* path, uint8_t* dst, uint64_t cap, uint
     const uint64_t maxRuns = n / 256 + 256;
     static thread_local std::vector<ExcRun> runs;
     static thread_local std::vector<uint8_t> buf;
-    constexpr uint64_t PIECE = 256 << 10;
+    static const uint64_t PIECE = [] {  // a multiple of 64 that stays in the core's L2
+        const char* e = std::getenv("MBGC_B200_READ_PIECE_KB");
+        const uint64_t kb = e ? std::strtoull(e, nullptr, 10) : 256;
+        return std::max<uint64_t>(4, std::min<uint64_t>(kb, 65536)) << 10;
+    }();
     if (buf.size() < PIECE + 64) buf.resize(PIECE + 64);
     uint8_t* b = buf.data() + ((64 - (reinterpret_cast<uintptr_t>(buf.data()) & 63)) & 63);
     runs.clear();

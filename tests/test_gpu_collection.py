@@ -209,6 +209,28 @@ def test_packed_file_images_equal_plain_ones(mixed_dir, tmp_path, mode):
     assert pi["stats"]["wireBytes"] == pi["stats"]["imageBytes"]
 
 
+def test_files_pass_two_replicas(mixed_dir):
+    """the library's own readers feeding two replicas of one process (packed images, extensions device to device)"""
+    if n_devices() < 2:
+        pytest.skip("needs two CUDA devices")
+    c0 = read_fasta(mixed_dir[0])[0][1]
+    limit = max(min(reference_factor(len(mixed_dir)) * max(os.path.getsize(mixed_dir[0]), 1 << 21) * 2, 2**32 - 1), len(c0))
+    res = []
+    for devices in ([0], [0, 1]):
+        g = mbgc_b200.Matcher(limit, 32, 16, 1, 16, devices=devices)
+        try:
+            g.disableSlidingWindow()
+            g.loadRef(c0, True, True, 0)
+            out, info = g.compressFiles(list(mixed_dir), SeqConfig.for_mode(1, 1 << 20), readers=6, pack=True)
+            res.append((out, info, g.table()))
+        finally:
+            g.close()
+    for name in STREAMS:
+        assert res[0][0][name] == res[1][0][name], name
+    assert res[0][1]["digest"] == res[1][1]["digest"] and res[0][1]["extensions"] == res[1][1]["extensions"] > 0
+    assert np.array_equal(res[0][2], res[1][2])
+
+
 def test_files_pass_errors_and_empty_list(mixed_dir, tmp_path):
     """mbgcg_seq_run_files: a file that cannot be read ends the pass with an error (and leaves the handle usable), an empty
     list is an empty pass"""
