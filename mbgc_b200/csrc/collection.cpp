@@ -864,6 +864,15 @@ bool SequentialPass::startWindow() {
     size_t take = 0;
     while (take < staged.size() && take < static_cast<size_t>(rs.size()) && staged[take]->closed) take++;
     if (take == 0) return false;
+    // The batch-frozen schedule matches a window against the state at its start: WHICH targets share a window is part of the
+    // result, so it must not depend on how fast the files arrive.  A window of fewer chunks than replicas starts only when no
+    // further chunk can close before it: the input is over, or the pass does not want more of it (a function of the file
+    // sizes alone).
+    if (cfg.parallelSchedule && take < static_cast<size_t>(rs.size())) {
+        const bool noMoreChunks = inputDone && pending.empty() && !forming;
+        const bool wantsMore = !inputDone && pendingBytes + stagedBytes < 3 * cfg.chunkBytes * static_cast<uint64_t>(rs.size());
+        if (!noMoreChunks && (wantsMore || !pending.empty())) return false;
+    }
     win.clear();
     const double t0 = now_ms();
     for (size_t k = 0; k < take; k++) {
