@@ -398,13 +398,173 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_lookback(const uint32_t* 
     }
 }
 
+// Single-pass exclusive scan over contiguous RANGES: the n elements are cut into at most gridDim.x ranges of whole
+// 4096-element tiles, handed out by ticket.  A CTA reduces its range, publishes the range total ((1 << 32) | total in
+// `state`, zeroed with the pass counters; last word = ticket), adds up the totals of all ranges before it -- their CTAs
+// hold earlier tickets, so they are running, and they publish without waiting for anybody: no chain of dependent
+// look-backs, one global round trip -- and then scans its range RANGE_GROUP tiles at a time (the warp scans of the tiles
+// of a group share two barriers).  A range of at most RANGE_GROUP tiles is read once and stays in registers.
+// in / out 16-byte aligned; out may alias in.  out[n] receives the grand total.
+constexpr int RANGE_GROUP = 4;
+
+__device__ __forceinline__ uint4 scan_load4(const uint32_t* in, uint32_t i0, uint32_t n) {
+    if (i0 + 3 < n) return *reinterpret_cast<const uint4*>(in + i0);
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (i0 < n) v.x = in[i0];
+    if (i0 + 1 < n) v.y = in[i0 + 1];
+    if (i0 + 2 < n) v.z = in[i0 + 2];
+    return v;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_ranges(const uint32_t* in, uint32_t* out, const uint32_t* nPtr,
+                                                              uint32_t nConst, uint32_t nMax, unsigned long long* state,
+                                                              uint32_t stateWords, uint32_t* totalOut) {
+    __shared__ uint32_t sW[RANGE_GROUP][33];
+    __shared__ uint32_t sTileTot[RANGE_GROUP];
+    __shared__ uint32_t sRed[33];
+    __shared__ uint32_t sTicket, sPrefix;
+    const uint32_t n = scan_len(nPtr, nConst, nMax);
+    const uint32_t nTiles = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    if (nTiles == 0) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            out[0] = 0;
+            if (totalOut) *totalOut = 0;
+        }
+        return;
+    }
+    const uint32_t tpr = (nTiles + gridDim.x - 1) / gridDim.x;  // tiles per range
+    const uint32_t nRanges = (nTiles + tpr - 1) / tpr;
+    const bool keep = tpr <= RANGE_GROUP;
+    volatile unsigned long long* vs = state;
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(state + stateWords - 1);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (;;) {
+        if (threadIdx.x == 0) sTicket = atomicAdd(ticket, 1u);
+        __syncthreads();
+        const uint32_t t = sTicket;
+        if (t >= nRanges) break;
+        const uint32_t tile0 = t * tpr, tile1 = min(nTiles, tile0 + tpr);
+        uint4 v[RANGE_GROUP];
+        uint32_t s[RANGE_GROUP], inc[RANGE_GROUP];
+        uint32_t rangeTotal = 0;
+        // ---- the range total
+        if (keep) {
+#pragma unroll
+            for (int k = 0; k < RANGE_GROUP; k++) {
+                v[k] = make_uint4(0, 0, 0, 0);
+                if (tile0 + k < tile1) v[k] = scan_load4(in, (tile0 + k) * SCAN_BLOCK + threadIdx.x * SCAN_ITEMS, n);
+            }
+#pragma unroll
+            for (int k = 0; k < RANGE_GROUP; k++) {
+                s[k] = v[k].x + v[k].y + v[k].z + v[k].w;
+                inc[k] = warp_incl_scan(s[k], lane);
+                if (lane == 31) sW[k][warp] = inc[k];
+            }
+            __syncthreads();
+            if (warp < RANGE_GROUP) {
+                const uint32_t w = sW[warp][lane];
+                const uint32_t wi = warp_incl_scan(w, lane);
+                sW[warp][lane] = wi - w;
+                if (lane == 31) sTileTot[warp] = wi;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < RANGE_GROUP; k++) rangeTotal += sTileTot[k];
+        } else {
+            uint32_t acc = 0;
+            for (uint32_t tile = tile0; tile < tile1; tile++) {
+                const uint4 x = scan_load4(in, tile * SCAN_BLOCK + threadIdx.x * SCAN_ITEMS, n);
+                acc += x.x + x.y + x.z + x.w;
+            }
+            acc = __reduce_add_sync(0xFFFFFFFFu, acc);
+            if (lane == 0) sRed[warp] = acc;
+            __syncthreads();
+            if (warp == 0) {
+                const uint32_t r = __reduce_add_sync(0xFFFFFFFFu, sRed[lane]);
+                if (lane == 0) sRed[32] = r;
+            }
+            __syncthreads();
+            rangeTotal = sRed[32];
+        }
+        // ---- publish it, add up the ranges in front
+        if (warp == 0) {
+            if (lane == 0) vs[t] = (1ull << 32) | rangeTotal;
+            uint32_t p = 0;
+            for (uint32_t j = lane; j < t; j += 32) {
+                unsigned long long w;
+                do {
+                    w = vs[j];
+                } while ((w >> 32) == 0);
+                p += static_cast<uint32_t>(w);
+            }
+            p = __reduce_add_sync(0xFFFFFFFFu, p);
+            if (lane == 0) {
+                sPrefix = p;
+                if (t == nRanges - 1) {
+                    out[n] = p + rangeTotal;
+                    if (totalOut) *totalOut = p + rangeTotal;
+                }
+            }
+        }
+        __syncthreads();
+        uint32_t carry = sPrefix;
+        // ---- the scan of the range
+        for (uint32_t g0 = tile0; g0 < tile1; g0 += RANGE_GROUP) {
+            if (!keep) {
+#pragma unroll
+                for (int k = 0; k < RANGE_GROUP; k++) {
+                    v[k] = make_uint4(0, 0, 0, 0);
+                    if (g0 + k < tile1) v[k] = scan_load4(in, (g0 + k) * SCAN_BLOCK + threadIdx.x * SCAN_ITEMS, n);
+                }
+#pragma unroll
+                for (int k = 0; k < RANGE_GROUP; k++) {
+                    s[k] = v[k].x + v[k].y + v[k].z + v[k].w;
+                    inc[k] = warp_incl_scan(s[k], lane);
+                    if (lane == 31) sW[k][warp] = inc[k];
+                }
+                __syncthreads();
+                if (warp < RANGE_GROUP) {
+                    const uint32_t w = sW[warp][lane];
+                    const uint32_t wi = warp_incl_scan(w, lane);
+                    sW[warp][lane] = wi - w;
+                    if (lane == 31) sTileTot[warp] = wi;
+                }
+                __syncthreads();
+            }
+#pragma unroll
+            for (int k = 0; k < RANGE_GROUP; k++) {
+                if (g0 + k < tile1) {
+                    const uint32_t i0 = (g0 + k) * SCAN_BLOCK + threadIdx.x * SCAN_ITEMS;
+                    uint4 e;
+                    e.x = carry + sW[k][warp] + inc[k] - s[k];
+                    e.y = e.x + v[k].x;
+                    e.z = e.y + v[k].y;
+                    e.w = e.z + v[k].z;
+                    if (i0 + 3 < n) {
+                        *reinterpret_cast<uint4*>(out + i0) = e;
+                    } else {
+                        if (i0 < n) out[i0] = e.x;
+                        if (i0 + 1 < n) out[i0 + 1] = e.y;
+                        if (i0 + 2 < n) out[i0 + 2] = e.z;
+                    }
+                }
+                carry += sTileTot[k];
+            }
+            __syncthreads();  // sW / sTileTot are rewritten by the next group, sTicket / sPrefix by the next range
+        }
+    }
+}
+
 static int scan_exclusive(const uint32_t* in, uint32_t* out, const uint32_t* nPtr, uint32_t nConst, uint32_t nMax,
                           unsigned long long* state, uint32_t stateWords, uint32_t* totalOut, cudaStream_t st) {
     uint32_t blocks = (nMax + SCAN_BLOCK - 1) / SCAN_BLOCK;
     const uint32_t cap = static_cast<uint32_t>(device_sm_count()) * 2;
     if (blocks > cap) blocks = cap;
     if (blocks == 0) blocks = 1;
-    k_scan_lookback<<<blocks, SCAN_THREADS, 0, st>>>(in, out, nPtr, nConst, nMax, state, stateWords, totalOut);
+    static const bool lookback = []() { const char* e = getenv("MBGC_B200_SCAN_LOOKBACK"); return e && e[0] == '1'; }();
+    const bool aligned = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+    if (lookback || !aligned) k_scan_lookback<<<blocks, SCAN_THREADS, 0, st>>>(in, out, nPtr, nConst, nMax, state, stateWords, totalOut);
+    else k_scan_ranges<<<blocks, SCAN_THREADS, 0, st>>>(in, out, nPtr, nConst, nMax, state, stateWords, totalOut);
     return 1;
 }
 
@@ -728,19 +888,23 @@ struct CleanArgs {
     uint32_t* counters;
 };
 
-// Eight lanes per chunk, four chunks per warp: the per-chunk scalar work (descriptor, diagonal, window class,
-// memo window) is a few dozen instructions that every lane of the chunk repeats, so fewer lanes per chunk means
-// fewer issue slots; each lane compares 4 x 16 bytes, the pieces interleaved so that the 8 lanes of a chunk read
-// 128 contiguous bytes per load instruction.
-__global__ void __launch_bounds__(256, 8) k_clean(const CleanArgs a) {
-    const int lane = threadIdx.x & 31, sub = lane & 7, cg = lane >> 3;
+// LPC lanes per chunk, 32 / LPC chunks per warp: the per-chunk scalar work (descriptor, diagonal, window class, memo
+// window, the stores) is ~250 instructions that every lane of the chunk repeats, so fewer lanes per chunk means fewer
+// issue slots per chunk; each lane compares 32 / LPC pieces of 16 bytes, interleaved so that the lanes of a chunk read
+// 16 LPC contiguous bytes per load instruction (whole sectors as long as LPC >= 2).
+template <int LPC, int OCC>
+__global__ void __launch_bounds__(256, OCC) k_clean(const CleanArgs a) {
+    constexpr int CPW = 32 / LPC;  // chunks per warp
+    constexpr int PPL = 32 / LPC;  // 16-byte pieces per lane
+    constexpr uint32_t GMASK = LPC == 32 ? 0xffffffffu : (1u << (LPC & 31)) - 1u;
+    const int lane = threadIdx.x & 31, sub = lane & (LPC - 1), cg = lane / LPC;
     const int K = a.ix.K;
     const int tailWords = (K + 2) / 4;  // the K-1 bytes the chunk's last k-mers reach past it, rounded up to words
     const int span = (K + 30) / 16;     // 16-byte pieces the 16 k-mers of a lane touch
     const unsigned long long tailPieces = ((1ull << ((K + 14) / 16)) - 1ull) << 32;
     const uint32_t warpsTotal = gridDim.x * (blockDim.x >> 5);
     const uint32_t nTiles = a.b.nTiles;
-    for (uint32_t gb = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 4; gb < nTiles; gb += warpsTotal * 4) {
+    for (uint32_t gb = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * CPW; gb < nTiles; gb += warpsTotal * CPW) {
         const bool valid = gb + cg < nTiles;
         const uint32_t g = valid ? gb + cg : nTiles - 1;
         const uint4 desc = __ldg(&a.chunkDesc[g]);
@@ -773,18 +937,20 @@ __global__ void __launch_bounds__(256, 8) k_clean(const CleanArgs a) {
         // 512 + K-1 bytes of text against the reference on the diagonal.  The reference side is unaligned: three
         // 8-byte loads cover a 16-byte piece (24-byte window from the 8-byte boundary below it), a select picks the
         // 5 words the piece touches and a funnel shift per word removes the byte offset.  (Five 4-byte loads would
-        // make every lane group request the same sectors five times: L1TEX sector throughput was the limit.)
+        // make every lane group request the same sectors five times; one aligned 16-byte load per piece with the
+        // neighbouring piece taken from the next lane by shuffle halves the sector count again but costs more issue
+        // slots than it saves: measured slower, profiles/README.md r02c.)
         const uintptr_t ra = reinterpret_cast<uintptr_t>(R + 16 * sub);
         const uint2* rp = reinterpret_cast<const uint2*>(ra & ~static_cast<uintptr_t>(7));
         const bool hiHalf = (ra & 4) != 0;
         const uint32_t sh = static_cast<uint32_t>(ra & 3) * 8;
         const uint4* tp = reinterpret_cast<const uint4*>(T) + sub;
-        // which of the chunk's 32 + 2 sixteen-byte pieces differ: lane sub compares pieces sub, sub + 8, sub + 16, sub + 24
+        // which of the chunk's 32 + 2 sixteen-byte pieces differ: lane sub compares pieces sub, sub + LPC, sub + 2 LPC, ...
         uint32_t pflags = 0, pt = 0;  // bit k of pflags: this lane's k-th piece differs
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const uint4 tw = __ldg(tp + 8 * k);
-            const uint2 a0 = __ldg(rp + 16 * k), a1 = __ldg(rp + 16 * k + 1), a2 = __ldg(rp + 16 * k + 2);
+        for (int k = 0; k < PPL; k++) {
+            const uint4 tw = __ldg(tp + LPC * k);
+            const uint2 a0 = __ldg(rp + 2 * LPC * k), a1 = __ldg(rp + 2 * LPC * k + 1), a2 = __ldg(rp + 2 * LPC * k + 2);
             const uint32_t w0 = hiHalf ? a0.y : a0.x, w1 = hiHalf ? a1.x : a0.y, w2 = hiHalf ? a1.y : a1.x,
                            w3 = hiHalf ? a2.x : a1.y, w4 = hiHalf ? a2.y : a2.x;
             const uint32_t pd = (tw.x ^ __funnelshift_r(w0, w1, sh)) | (tw.y ^ __funnelshift_r(w1, w2, sh)) |
@@ -794,16 +960,16 @@ __global__ void __launch_bounds__(256, 8) k_clean(const CleanArgs a) {
         {
             const uint32_t* rw = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(R) & ~static_cast<uintptr_t>(3));
 #pragma unroll
-            for (int w = 0; w < 2; w++) {  // tail: word sub, and word sub + 8 for K > 32
-                const int tl = sub + 8 * w;
+            for (int w = 0; w < 16 / LPC; w++) {  // tail: words sub, sub + LPC, ... (at most 14: K <= 56)
+                const int tl = sub + LPC * w;
                 if (tl < tailWords) {
                     const uint32_t* rt = rw + PROBE_CHUNK / 4 + tl;  // R + PROBE_CHUNK + 4 tl, rounded down to a word
                     pt |= __ldg(reinterpret_cast<const uint32_t*>(T + PROBE_CHUNK) + tl) ^ __funnelshift_r(__ldg(rt), __ldg(rt + 1), sh);
                 }
             }
         }
-        // Most warps see no difference at all (on the near tier 3 of 4): one vote settles that, and everything that
-        // deals with dirty lanes is behind warp-uniform branches.
+        // Most warps see no difference at all: one vote settles that, and everything that deals with dirty lanes is
+        // behind warp-uniform branches.
         const uint32_t X1 = static_cast<uint32_t>(xw >> 1), X0 = static_cast<uint32_t>(xw);
         uint32_t L = ok ? (X1 | (pin ? X0 : 0u)) : 0xffffffffu;  // dirty lanes: memo first (lane l overlaps the reference
                                                                  // groups of bits l, before its grid position, and l + 1)
@@ -811,11 +977,11 @@ __global__ void __launch_bounds__(256, 8) k_clean(const CleanArgs a) {
         if (__any_sync(0xffffffffu, (pflags | pt) != 0)) {
             unsigned long long pieces = 0;  // bit q = piece q differs (pieces 32.. = the K-1 bytes past the chunk)
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const unsigned bal = (__ballot_sync(0xffffffffu, (pflags >> k) & 1u) >> (8 * cg)) & 0xffu;
-                pieces |= static_cast<unsigned long long>(bal) << (8 * k);
+            for (int k = 0; k < PPL; k++) {
+                const unsigned bal = (__ballot_sync(0xffffffffu, (pflags >> k) & 1u) >> (LPC * cg)) & GMASK;
+                pieces |= static_cast<unsigned long long>(bal) << (LPC * k);
             }
-            const unsigned balT = (__ballot_sync(0xffffffffu, pt != 0) >> (8 * cg)) & 0xffu;
+            const unsigned balT = (__ballot_sync(0xffffffffu, pt != 0) >> (LPC * cg)) & GMASK;
             if (balT) pieces |= tailPieces;  // any difference in the tail dirties all tail pieces (conservative)
             // lane l of the chunk (positions 16 l .. 16 l + 15) reads bytes [16 l, 16 l + 15 + K): pieces l .. l + span - 1
             unsigned long long dm = 0;
@@ -823,13 +989,13 @@ __global__ void __launch_bounds__(256, 8) k_clean(const CleanArgs a) {
             if (valid) L |= static_cast<uint32_t>(dm);
         }
         if (__any_sync(0xffffffffu, L != 0)) {
-            // dirty lanes -> work items.  One 64-bit atomic per warp reserves the slots of its four chunks in both
-            // lists (counters 6 = chunks with dirty lanes, 7 = dirty lanes), then the eight lanes of a chunk write its
-            // items (4 bits of L each).
+            // dirty lanes -> work items.  One 64-bit atomic per warp reserves the slots of its chunks in both lists
+            // (counters 6 = chunks with dirty lanes, 7 = dirty lanes), then the lanes of a chunk write its items
+            // (PPL bits of L each).
             uint32_t laneBase = 0, chunkBase = 0, laneTot = 0, chunkTot = 0;
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const uint32_t Lj = __shfl_sync(0xffffffffu, L, 8 * j);
+            for (int j = 0; j < CPW; j++) {
+                const uint32_t Lj = __shfl_sync(0xffffffffu, L, LPC * j);
                 if (j == cg) {
                     laneBase = laneTot;
                     chunkBase = chunkTot;
@@ -844,10 +1010,11 @@ __global__ void __launch_bounds__(256, 8) k_clean(const CleanArgs a) {
             old = __shfl_sync(0xffffffffu, old, 0);
             if (L) {
                 if (sub == 0) a.workList[static_cast<uint32_t>(old) + chunkBase] = g;
-                uint32_t mine = (L >> (4 * sub)) & 0xfu;
-                uint32_t k = static_cast<uint32_t>(old >> 32) + laneBase + __popc(L & ((1u << (4 * sub)) - 1u));
+                constexpr uint32_t PMASK = PPL == 32 ? 0xffffffffu : (1u << (PPL & 31)) - 1u;
+                uint32_t mine = (L >> (PPL * sub)) & PMASK;
+                uint32_t k = static_cast<uint32_t>(old >> 32) + laneBase + __popc(L & ((1u << (PPL * sub)) - 1u));
                 while (mine) {
-                    a.laneList[k++] = g * 32u + 4 * sub + (__ffs(mine) - 1);
+                    a.laneList[k++] = g * 32u + PPL * sub + (__ffs(mine) - 1);
                     mine &= mine - 1;
                 }
             }
@@ -1093,7 +1260,9 @@ int launch_clean(const IndexState& ix, const BatchDesc& b, const WorkBuffers& w,
     if (b.nTiles == 0) return 0;
     CleanArgs a{ix, b, w.chunkDesc, w.chunkContig, w.anchor, memo.memoX, memo.memoE, memo.memoLen, w.tileCount,
                 w.seedMask, w.scratchEnc, w.chunkSegN, w.chunkSeg, w.dirtyMask, w.workList, w.laneList, w.counters};
-    k_clean<<<device_sm_count() * 8, 256, 0, st>>>(a);
+    // 8 lanes per chunk, 8 CTAs per SM: 4 or 2 lanes per chunk execute 30-50 % fewer instructions per chunk and were measured
+    // 25 % / 2.2x slower, 6 CTAs per SM with 40 registers 6 % slower (profiles/README.md, r02c experiments)
+    k_clean<8, 8><<<device_sm_count() * 8, 256, 0, st>>>(a);
     return 1;
 }
 
