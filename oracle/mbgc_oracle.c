@@ -610,9 +610,35 @@ static uint64_t extend_right(mbo_streams* out, const mbo_pack_params_t* p, const
 }
 
 /* MBGC_Encoder.cpp:143-308 */
+/* MBGC_Encoder::processLiteral (mbgccoder/MBGC_Encoder.cpp:128-135): a literal longer than refLiteralMinimalLengthExt,
+ * with refLiteralBeforeAfterExt bytes of context on either side, is appended to targetRefExtensions -- recorded here as a
+ * range of the text instead of copied bytes. */
+static void process_literal(uint32_t pos, uint64_t length, uint64_t destLen, uint64_t minLen, uint64_t beforeAfter,
+                            mbo_lit_range_t* ranges, uint64_t cap, uint64_t* nRanges) {
+    if (length > minLen) {                                       /* MGMP_Params.h:175-177 */
+        const int before = beforeAfter < pos ? (int) beforeAfter : (int) pos;
+        const int after = (pos + length + beforeAfter < destLen) ? (int) beforeAfter : (int) (destLen - pos - length);
+        if (*nRanges < cap) {
+            ranges[*nRanges].start = (uint64_t) pos - (uint64_t) before;
+            ranges[*nRanges].len = length + (uint64_t) before + (uint64_t) after;
+        }
+        (*nRanges)++;
+    }
+}
+
 uint64_t mbo_process_matches(mbo_streams* out, const mbo_pack_params_t* p, const mbo_matcher* m, mbo_match_t* tm,
                              uint64_t* nMatches, const uint8_t* dest, uint64_t destLen, uint64_t lockPos,
                              const uint64_t* loadedArr, uint64_t nLoaded) {
+    uint64_t nRanges = 0;
+    return mbo_process_matches_lit(out, p, m, tm, nMatches, dest, destLen, lockPos, loadedArr, nLoaded, UINT64_MAX, 0, NULL, 0,
+                                   &nRanges);
+}
+
+uint64_t mbo_process_matches_lit(mbo_streams* out, const mbo_pack_params_t* p, const mbo_matcher* m, mbo_match_t* tm,
+                                 uint64_t* nMatches, const uint8_t* dest, uint64_t destLen, uint64_t lockPos,
+                                 const uint64_t* loadedArr, uint64_t nLoaded, uint64_t refLiteralMinimalLengthExt,
+                                 uint64_t refLiteralBeforeAfterExt, mbo_lit_range_t* ranges, uint64_t rangeCap,
+                                 uint64_t* nRanges) {
     const uint8_t* R = m->ref;
     const int64_t n0 = (int64_t) *nMatches;
     uint32_t pos = 0;
@@ -644,6 +670,10 @@ uint64_t mbo_process_matches(mbo_streams* out, const mbo_pack_params_t* p, const
     const int64_t n = jj;
     *nMatches = (uint64_t) n;
     unmatched += (int64_t) (destLen - pos);
+    /* :211 loadLiteralsToRef = !isContigProperForRefExtension(destLen, unmatchedChars, factor)  (MGMP_Params.h:179-187) */
+    const int loadLiteralsToRef = refLiteralMinimalLengthExt != UINT64_MAX &&
+                                  !((uint64_t) unmatched * (uint64_t) p->unmatchedFractionFactor > destLen);
+    *nRanges = 0;
 
     /* next region loading positions live beside the matches (TextMatch::nextSrcRegionLoadingPos) */
     uint64_t* nextLoad = (uint64_t*) calloc((size_t) (n > 0 ? n : 1), sizeof(uint64_t));
@@ -666,6 +696,8 @@ uint64_t mbo_process_matches(mbo_streams* out, const mbo_pack_params_t* p, const
             }
         }
         bput(lit, dest + pos, literalsLeft);
+        if (loadLiteralsToRef)                                    /* :228 */
+            process_literal(pos, literalsLeft, destLen, refLiteralMinimalLengthExt, refLiteralBeforeAfterExt, ranges, rangeCap, nRanges);
         if (!pairedGap[gapCurIdx]) {
             uint32_t off = (uint32_t) match->src;
             bput(&out->s[MBO_S_MAPOFF], &off, 4);
@@ -729,6 +761,8 @@ uint64_t mbo_process_matches(mbo_streams* out, const mbo_pack_params_t* p, const
         }
     }
     bput(lit, dest + pos, destLen - pos);
+    if (loadLiteralsToRef)                                        /* :290 */
+        process_literal(pos, destLen - pos, destLen, refLiteralMinimalLengthExt, refLiteralBeforeAfterExt, ranges, rangeCap, nRanges);
     free(nextLoad);
     return (uint64_t) unmatched;
 }

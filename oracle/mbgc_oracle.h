@@ -125,6 +125,19 @@ uint64_t mbo_process_matches(mbo_streams* out, const mbo_pack_params_t* p, const
                              mbo_match_t* matches, uint64_t* nMatches, const uint8_t* dest, uint64_t destLen,
                              uint64_t matchingLockPos, const uint64_t* refExtLoadedPosArr, uint64_t nLoadedPos);
 
+/* The same with MBGC_Encoder::processLiteral (mbgccoder/MBGC_Encoder.cpp:128-135, called at :228 and :290 when the contig
+ * is NOT proper for a whole-contig reference extension, :211; a developer-build option of the reference, `-N <minimal
+ * literal length> -F <context>`): every literal the call appends to the literal stream that is longer than
+ * refLiteralMinimalLengthExt gives a range [pos - before, pos + length + after) of the text; targetRefExtensions = the
+ * concatenation of those ranges.  UINT64_MAX switches it off (the default, MBGC_Params.h: SIZE_MAX).  *nRanges receives the
+ * number of ranges (the first rangeCap are stored). */
+typedef struct { uint64_t start, len; } mbo_lit_range_t;
+uint64_t mbo_process_matches_lit(mbo_streams* out, const mbo_pack_params_t* p, const mbo_matcher* m,
+                                 mbo_match_t* matches, uint64_t* nMatches, const uint8_t* dest, uint64_t destLen,
+                                 uint64_t matchingLockPos, const uint64_t* refExtLoadedPosArr, uint64_t nLoadedPos,
+                                 uint64_t refLiteralMinimalLengthExt, uint64_t refLiteralBeforeAfterExt,
+                                 mbo_lit_range_t* ranges, uint64_t rangeCap, uint64_t* nRanges);
+
 /* coders/ContextAwareMismatchesCoder.cpp:22-27 */
 uint8_t mbo_mismatch2code(uint8_t actual, uint8_t mismatch);
 

@@ -46,11 +46,11 @@ def golden_collection(d):
     return names
 
 
-def stream_digests(d, list_name, mode):
+def stream_digests(d, list_name, mode, extra=()):
     arch = os.path.join(d, f"m{mode}.mbgc")
     env = dict(os.environ)
     env.pop("OMP_NUM_THREADS", None)
-    subprocess.run([os.path.join(REF_DIR, "mbgc-dev"), "c", "-t", "1", "-m", str(mode), "-f", list_name, arch],
+    subprocess.run([os.path.join(REF_DIR, "mbgc-dev"), "c", "-t", "1", "-m", str(mode), *extra, "-f", list_name, arch],
                    cwd=d, check=True, capture_output=True, env=env)
     subprocess.run([os.path.join(REF_DIR, "mbgc-dev"), "v", "-Q", "-D", arch], cwd=d, check=True, capture_output=True,
                    env=env)
@@ -104,7 +104,29 @@ def rcmatch_golden():
     return out
 
 
+def literal_ext_golden():
+    """row a12: stream digests of the developer build of the stock CLI with MBGC_Encoder::processLiteral switched on
+    (`-N <minimal literal length> -F <context>`, main.cpp:308-313) on the seeded collection of tests/util.py"""
+    from util import LITERAL_EXT_CASES, literal_ext_collection
+    out = {}
+    for mode, min_len, ctx in LITERAL_EXT_CASES:
+        with tempfile.TemporaryDirectory() as d:
+            literal_ext_collection(d)
+            out[f"{mode}:{min_len}:{ctx}"] = stream_digests(d, "list.txt", mode, ("-N", str(min_len), "-F", str(ctx)))
+            off = stream_digests(d, "list.txt", mode)
+            assert off["literals"]["sha256"] != out[f"{mode}:{min_len}:{ctx}"]["literals"]["sha256"], "the option changed nothing"
+    return out
+
+
 def main():
+    if "--only-literal-ext" in sys.argv:
+        path = os.path.join(HERE, "golden.json")
+        g = json.load(open(path))
+        g["literal_ext"] = literal_ext_golden()
+        with open(path, "w") as f:
+            json.dump(g, f, indent=1, sort_keys=True)
+        print("updated literal_ext section of", path)
+        return
     if "--only-rcmatch" in sys.argv:
         path = os.path.join(HERE, "golden.json")
         g = json.load(open(path))

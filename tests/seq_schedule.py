@@ -26,9 +26,15 @@ def reference_factor(n_files):
     return 1 << (5 if tmp < 5 else (12 if tmp > 12 else tmp))
 
 
-def encode_streams(paths, mode, on_match=None):
+class LitRange(C.Structure):
+    _fields_ = [("start", C.c_uint64), ("len", C.c_uint64)]
+
+
+def encode_streams(paths, mode, on_match=None, lit_ext=None):
     """Returns ({stream name: bytes}, stats).  on_match(contig_bytes, matcher, oracle_matches) lets a caller
-    cross-check another matcher (e.g. the CUDA one) in lock step."""
+    cross-check another matcher (e.g. the CUDA one) in lock step.  lit_ext = (refLiteralMinimalLengthExt,
+    refLiteralBeforeAfterExt) switches MBGC_Encoder::processLiteral on (the reference's developer option -N / -F): a contig
+    that is not loaded as a whole extends the reference with its long literals (MultipleGenomeMatchingProcessor.cpp:281-286)."""
     lib = oracle_lib()
     recs = [read_fasta(p) for p in paths]
     c0 = recs[0][0][1]
@@ -58,11 +64,27 @@ def encode_streams(paths, mode, on_match=None):
             mt = np.ascontiguousarray(mt)
             n = C.c_uint64(len(mt))
             arr = (C.c_uint64 * len(loaded))(*loaded)
-            unmatched = lib.mbo_process_matches(streams, C.byref(pp), m.h, mt.ctypes.data_as(C.c_void_p), C.byref(n),
-                                                a.ctypes.data_as(u8p), a.size, NO_LOCK, arr, len(loaded))
+            if lit_ext is None:
+                unmatched = lib.mbo_process_matches(streams, C.byref(pp), m.h, mt.ctypes.data_as(C.c_void_p), C.byref(n),
+                                                    a.ctypes.data_as(u8p), a.size, NO_LOCK, arr, len(loaded))
+                ranges = []
+            else:
+                cap = len(mt) + 2
+                rbuf = (LitRange * cap)()
+                nr = C.c_uint64(0)
+                lib.mbo_process_matches_lit.restype = C.c_uint64
+                unmatched = lib.mbo_process_matches_lit(streams, C.byref(pp), m.h, mt.ctypes.data_as(C.c_void_p), C.byref(n),
+                                                        a.ctypes.data_as(u8p), C.c_uint64(a.size), C.c_uint64(NO_LOCK), arr,
+                                                        C.c_uint64(len(loaded)), C.c_uint64(lit_ext[0]), C.c_uint64(lit_ext[1]),
+                                                        rbuf, C.c_uint64(cap), C.byref(nr))
+                ranges = [(rbuf[k].start, rbuf[k].len) for k in range(nr.value)]
+                stats.setdefault("lit_ranges", []).append(ranges)
             stats["unmatched"] += unmatched
             if unmatched * 128 > a.size:
                 m.load_ref(a, rc=unmatched * rc_factor > a.size, add_sep=True)
+            elif ranges:
+                ext = np.concatenate([a[s0:s0 + ln] for s0, ln in ranges])
+                m.load_ref(ext, rc=unmatched * rc_factor > a.size, add_sep=True)
             lib.mbo_after_sequence(streams)
         lib.mbo_after_target(streams, C.byref(pp))
         m.load_separator(0)

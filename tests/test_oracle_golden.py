@@ -11,7 +11,7 @@ import pytest
 
 from scenarios import all_scenarios, replay
 from seq_schedule import encode_streams
-from util import FIXTURES, GOLDEN, OracleMatcher, have_fixtures, oracle_lib, ptr
+from util import FIXTURES, GOLDEN, LITERAL_EXT_CASES, OracleMatcher, have_fixtures, literal_ext_collection, oracle_lib, ptr
 
 G = json.load(open(os.path.join(GOLDEN, "golden.json")))
 
@@ -82,6 +82,22 @@ def test_streams_of_sequential_schedule(mode):
     want = G["streams"][str(mode)]
     with tempfile.TemporaryDirectory() as d:
         out, _ = encode_streams(_golden_collection(d), mode)
+    for name in ("literals", "gapDelta", "gapFlags", "mapOff", "mapLen"):
+        assert len(out[name]) == want[name]["size"], name
+        assert hashlib.sha256(out[name]).hexdigest() == want[name]["sha256"], name
+
+
+@pytest.mark.parametrize("case", LITERAL_EXT_CASES)
+def test_streams_with_literal_ref_extension(case):
+    """row a12: processLiteral (MBGC_Encoder.cpp:128-135) switched on as the reference's developer build does with -N / -F;
+    the oracle's schedule, extending the reference with the long literals of contigs that are not loaded whole, gives
+    the streams of `mbgc-dev c -t 1 -N .. -F ..`"""
+    mode, min_len, ctx = case
+    want = G["literal_ext"][f"{mode}:{min_len}:{ctx}"]
+    with tempfile.TemporaryDirectory() as d:
+        names = literal_ext_collection(d)
+        out, stats = encode_streams([os.path.join(d, n) for n in names], mode, lit_ext=(min_len, ctx))
+    assert sum(len(r) for r in stats["lit_ranges"]) > 0
     for name in ("literals", "gapDelta", "gapFlags", "mapOff", "mapLen"):
         assert len(out[name]) == want[name]["size"], name
         assert hashlib.sha256(out[name]).hexdigest() == want[name]["sha256"], name

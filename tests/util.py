@@ -344,3 +344,40 @@ def write_fasta(path, records, width=80):
 
 
 from mbgc_b200.synth import synth_base, synth_mutant, synth_collection, mgmp_ref_limit  # noqa: E402,F401
+
+
+# ----------------------------------------------------------------------------------------------
+# row a12 (MBGC_Encoder::processLiteral): a seeded collection whose contigs are NOT proper for a whole-contig reference
+# extension (few unmatched bases) but carry literals longer than the threshold -- novel islands shared between genomes
+# ----------------------------------------------------------------------------------------------
+LITERAL_EXT_CASES = ((1, 64, 8), (1, 200, 0), (0, 32, 16), (2, 100, 4))   # (mode, -N minimal literal length, -F context)
+
+
+def literal_ext_genomes(n=10, length=200_000, seed=99):
+    import numpy as np
+    from mbgc_b200.synth import synth_base, synth_mutant
+    rng = np.random.default_rng(seed + 7)
+    base = synth_base(length, seed)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    islands = [acgt[rng.integers(0, 4, size=int(rng.integers(100, 500)))] for _ in range(6)]
+    out = [base.copy()]
+    for i in range(1, n):
+        g = synth_mutant(base, seed * 1000003 + i, 1e-4, 1e-5)
+        for k in rng.choice(len(islands), size=2, replace=False):
+            p = int(rng.integers(1000, g.size - 1000))
+            g = np.concatenate([g[:p], islands[k], g[p:]])
+        out.append(np.ascontiguousarray(g))
+    return out
+
+
+def literal_ext_collection(d, n=10, length=200_000, seed=99):
+    """writes the collection as FASTA files + list.txt into d, returns the file names"""
+    from mbgc_b200.synth import write_fasta
+    names = []
+    for i, g in enumerate(literal_ext_genomes(n, length, seed)):
+        name = f"g{i:04d}.fna"
+        write_fasta(os.path.join(d, name), f"syn_{i:04d} genome {i} with islands", g)
+        names.append(name)
+    with open(os.path.join(d, "list.txt"), "w") as f:
+        f.write("\n".join(names) + "\n")
+    return names
