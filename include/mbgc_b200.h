@@ -131,7 +131,8 @@ int mbgcg_match_batch_device(mbgcg_t* h, const void* dText, int nTexts, const ui
  * text becomes the bytes the reference appends to targetLiterals / targetMapOffDests / targetMapOff5thByte /
  * targetMapLenDests / targetGapDeltas / targetGapMismatchesFlags, plus the list as pass 1 leaves it and the returned
  * unmatched count.  The caller keeps what needs encoder state: the dissimilar-contig bail-out (:202-205, decided on
- * the unmatched count returned here), processLiteral (:128-135, disabled by default) and the statistics counters. */
+ * the unmatched count returned here) and the statistics counters; processLiteral (:128-135, off by default) is
+ * mbgcg_set_literal_ref_ext / mbgcg_pack_literal_ref_ext below. */
 
 /* the MBGC_Params members processMatches reads (mbgccoder/MBGC_Params.h:66-97); field names as in the reference */
 typedef struct {
@@ -178,6 +179,25 @@ int mbgcg_pack_batch(mbgcg_t* h, const mbgcg_pack_params_t* p, int nTexts, const
                      const uint64_t* loadedPosArr, uint64_t nLoadedPos, mbgcg_pack_result_t* out);
 /* textMatches as pass 1 of the last pack call left them (MBGC_Encoder.cpp:197), all texts concatenated (kept[] each) */
 int mbgcg_pack_kept_matches(mbgcg_t* h, const mbgcg_match_t** out, uint64_t* n);
+/* MBGC_Encoder::processLiteral (/root/reference/mbgccoder/MBGC_Encoder.cpp:128-135, called from processMatches at :228
+ * and :290; params: MGMP_Params.h:68-69 refLiteralMinimalLengthExt / refLiteralBeforeAfterExt, :175-177
+ * isLiteralProperForRefExtension; a developer-build option of the reference, `-N` / `-F` of main.cpp:308-313, off by
+ * default).  After mbgcg_set_literal_ref_ext every pack call on the handle also lists what the reference would append to
+ * targetRefExtensions[targetIdx]: for a text that is NOT proper for a whole-contig reference extension (:211,
+ * unmatched * unmatchedFractionFactor <= length, MGMP_Params.h:179-187) every literal run longer than the threshold, with
+ * up to refLiteralBeforeAfterExt bytes of context on either side, as a range of that text, in append order.  The
+ * extension string of text i = the concatenation of text_i[start, start + len) over its ranges.
+ * refLiteralMinimalLengthExt = UINT64_MAX switches the option off again. */
+typedef struct {
+    uint32_t text;      /* index into the texts of the pack call */
+    uint32_t start;     /* pos - before */
+    uint32_t len;       /* length + before + after */
+    uint32_t reserved;
+} mbgcg_lit_range_t;
+int mbgcg_set_literal_ref_ext(mbgcg_t* h, uint64_t refLiteralMinimalLengthExt, uint64_t refLiteralBeforeAfterExt,
+                              int unmatchedFractionFactor);
+/* the ranges of the last pack call (handle-owned, valid until the next pack call) */
+int mbgcg_pack_literal_ref_ext(mbgcg_t* h, const mbgcg_lit_range_t** ranges, uint64_t* n);
 /* last pack call: ms[0..3] = input transfer, kernels, stream D2H, total (CUDA events); kernel launches; fixed-point
  * sweeps used for (removal, pairing) */
 void mbgcg_pack_timing(const mbgcg_t* h, float ms[4], uint64_t* launches, int sweeps[2]);

@@ -234,6 +234,28 @@ int mbgcg_pack_kept_matches(mbgcg_t* h, const mbgcg_match_t** out, uint64_t* n) 
     });
 }
 
+int mbgcg_set_literal_ref_ext(mbgcg_t* h, uint64_t refLiteralMinimalLengthExt, uint64_t refLiteralBeforeAfterExt,
+                              int unmatchedFractionFactor) {
+    return guarded(h, [&] {
+        if (unmatchedFractionFactor < 0) throw MatcherError(MBGCG_E_PARAM, "negative unmatchedFractionFactor");
+        if (refLiteralMinimalLengthExt != UINT64_MAX && refLiteralBeforeAfterExt >= (1ull << 31))
+            throw MatcherError(MBGCG_E_PARAM, "refLiteralBeforeAfterExt out of range");
+        h->m->setLiteralRefExt(refLiteralMinimalLengthExt, refLiteralBeforeAfterExt, static_cast<uint64_t>(unmatchedFractionFactor));
+    });
+}
+
+int mbgcg_pack_literal_ref_ext(mbgcg_t* h, const mbgcg_lit_range_t** ranges, uint64_t* n) {
+    if (!ranges || !n) return MBGCG_E_PARAM;
+    *ranges = nullptr;
+    *n = 0;
+    return guarded(h, [&] {
+        static_assert(sizeof(mbgcg_lit_range_t) == sizeof(mbgc_b200::LitRange), "range layout");
+        const auto& r = h->m->packLiteralRefExt();
+        *ranges = reinterpret_cast<const mbgcg_lit_range_t*>(r.data());
+        *n = r.size();
+    });
+}
+
 void mbgcg_pack_timing(const mbgcg_t* h, float ms[4], uint64_t* launches, int sweeps[2]) {
     for (int i = 0; i < 4; i++) ms[i] = h->m->packMs[i];
     if (launches) *launches = h->m->packLaunches;

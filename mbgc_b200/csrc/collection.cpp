@@ -709,6 +709,15 @@ SequentialPass::SequentialPass(ReplicaSet& rs_, const SeqConfig& c, const uint64
     if (const char* e = std::getenv("MBGC_B200_CHUNK_MB")) cfg.chunkBytes = std::max<uint64_t>(1, std::strtoull(e, nullptr, 10)) << 20;
     if (const char* e = std::getenv("MBGC_B200_WINDOW")) cfg.maxWindowContigs = static_cast<uint32_t>(std::max(1, std::atoi(e)));
     rs.setHostMirror(false);  // extensions come from device memory; nothing on this path reads getRef()
+    // MBGC_Encoder::processLiteral (row a12, mbgcg_set_literal_ref_ext on the handle): every replica lists the literal runs
+    // of its contigs; a contig that is not loaded whole extends the reference with them (MGMP.cpp:281-286)
+    const LitExtParams le = rs.primary()->literalRefExt();
+    litExtOn = le.minLen != UINT64_MAX;
+    if (litExtOn && cfg.parallelSchedule)
+        throw MatcherError(MBGCG_E_UNSUPPORTED, "literal reference extensions belong to the sequential schedule (the reference's "
+                                                "parallel loop reverse-complements the tail of targetRefExtensions, MGMP.cpp:392-397)");
+    for (int r = 0; r < nd; r++)
+        rs.at(r)->setLiteralRefExt(le.minLen, le.beforeAfter, static_cast<uint64_t>(std::max(0, cfg.unmatchedFractionFactor)));
     if (slots.size() < static_cast<size_t>(nd) * NSLOT) slots.resize(static_cast<size_t>(nd) * NSLOT);
     slotFree.assign(static_cast<size_t>(nd) * NSLOT, true);
     stageQ.resize(static_cast<size_t>(nd) * NSLOT);
@@ -1116,9 +1125,20 @@ void SequentialPass::next(SeqEvent& ev) {
             if (extend && extendRC && cfg.contigsIndividuallyReversed) fileExt.push_back(ExtPiece{ing.dTexts() + ic.textOff, ic.seqLen, true});
             continue;
         }
-        if (extend) {
+        // processLiteral: the long literal runs of a contig that is not loaded whole (targetRefExtensions[0], MGMP.cpp:281-282)
+        std::vector<ExtPiece> litPieces;
+        if (!extend && litExtOn) {
+            const auto& lr = m->packLiteralRefExt();  // ordered by text, then by position
+            auto lo = std::lower_bound(lr.begin(), lr.end(), it.resIndex, [](const LitRange& a, uint32_t t) { return a.text < t; });
+            for (; lo != lr.end() && lo->text == it.resIndex; ++lo)
+                litPieces.push_back(ExtPiece{ing.dTexts() + ic.textOff + lo->start, lo->len, false});
+        }
+        if (extend || !litPieces.empty()) {
             const double t0 = now_ms();
-            rs.loadRefFromReplica(ch.replica, ing.dTexts() + ic.textOff, ic.seqLen, extendRC, cfg.refRegionSeparators, cfg.separator);
+            if (extend)
+                rs.loadRefFromReplica(ch.replica, ing.dTexts() + ic.textOff, ic.seqLen, extendRC, cfg.refRegionSeparators, cfg.separator);
+            else
+                loadRefPieces(ch.replica, litPieces, extendRC);
             st.loadRefMs += now_ms() - t0;
             st.extensions++;
             // everything matched against the old state and not yet committed runs again; speculation that fails is wasted

@@ -292,6 +292,7 @@ private:
     struct ExtPiece { const uint8_t* dText; uint64_t len; bool rc; };
     std::vector<ExtPiece> fileExt;             // parallel schedule: the open target's reference extension (device pieces)
     void loadRefPieces(int owner, const std::vector<ExtPiece>& pieces, bool rc);
+    bool litExtOn = false;                     // MBGC_Encoder::processLiteral switched on for this pass (row a12)
 
     // input
     std::mutex mu;

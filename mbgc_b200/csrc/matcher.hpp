@@ -120,6 +120,14 @@ public:
     const std::vector<uint64_t>& packKept() const { return packKeptCounts; }          // matches left after pass 1
     // textMatches as pass 1 leaves them (MBGC_Encoder.cpp:197), all texts of the last pack call concatenated
     void packKeptMatches(std::vector<TextMatch>& out);
+    // MBGC_Encoder::processLiteral (MBGC_Encoder.cpp:128-135; a developer-build option of the reference, off by default):
+    // with minLen != UINT64_MAX every pack call also lists the literal runs that extend the reference, in append order
+    // (text = index into the texts of the call).  MGMP_Params.h:68-69,175-187.
+    void setLiteralRefExt(uint64_t minLen, uint64_t beforeAfter, uint64_t unmatchedFractionFactor) {
+        litExt = LitExtParams{minLen, beforeAfter, unmatchedFractionFactor};
+    }
+    const std::vector<LitRange>& packLiteralRefExt() const { return packLitRanges; }
+    const LitExtParams& literalRefExt() const { return litExt; }
     float packMs[4] = {0, 0, 0, 0};       // last pack call: H2D, kernels, D2H, total (CUDA events)
     uint64_t packLaunches = 0;            // kernel launches of the last pack call
     int packSweeps[2] = {0, 0};           // fixed-point sweeps the last pack call needed (removal, pairing)
@@ -260,6 +268,8 @@ private:
     struct KeptSlice { const KeptRec* dev; uint32_t n; };  // kept list of the last pass (device) for packKeptMatches
     std::vector<TextMatch> packKeptHost;                        // earlier passes of a multi-pass call
     KeptSlice packKeptLast{nullptr, 0};
+    LitExtParams litExt{UINT64_MAX, 0, 0};
+    std::vector<LitRange> packLitRanges;
 };
 
 }  // namespace mbgc_b200

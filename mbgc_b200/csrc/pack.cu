@@ -751,6 +751,8 @@ __global__ void __launch_bounds__(PK_THREADS) k_pk_emit(PackParams p, PackState 
         }
         GapOut cnt;
         process_gap<true>(p, s, b, w, c, j, n, at, cnt, plainSrc, plainDst, plainN);
+        // the (pos, literalsLeft) processLiteral sees at :228 / :290
+        if (w.litSpan) w.litSpan[gi] = make_uint2(static_cast<uint32_t>(plainSrc - (b.text + b.contigOff[c])), plainN);
         if (plainN <= 16)
             for (uint32_t i = 0; i < plainN; i++) plainDst[i] = __ldg(plainSrc + i);
     }
@@ -803,6 +805,32 @@ __global__ void __launch_bounds__(PK_THREADS) k_pk_copy_long(const LongRun* __re
             for (uint64_t i = tail0 + threadIdx.x; i < run.n; i += PK_THREADS) run.dst[i] = __ldg(run.src + i);
         }
     }
+}
+
+// MBGC_Encoder::processLiteral (mbgccoder/MBGC_Encoder.cpp:128-135): which literal runs extend the reference.  A run counts
+// when its contig is NOT proper for a whole-contig extension (loadLiteralsToRef, :211; MGMP_Params.h:179-187 on the
+// unmatched count before the extensions = length - sum of the kept match lengths) and it is longer than the threshold.
+__global__ void __launch_bounds__(PK_THREADS) k_pk_lit_flag(LitExtParams le, PackBatch b, PackWork w) {
+    const uint32_t gi = blockIdx.x * PK_THREADS + threadIdx.x;
+    uint32_t c, j, n;
+    if (!locate_gap(b, w.kOff, gi, c, j, n)) return;
+    const uint64_t destLen = b.contigLen[c];
+    const uint64_t unmatched = destLen - w.sumLen[c];
+    const bool proper = unmatched * le.factor > destLen;
+    w.litFlag[gi] = !proper && static_cast<uint64_t>(w.litSpan[gi].y) > le.minLen ? 1u : 0u;
+}
+
+__global__ void __launch_bounds__(PK_THREADS) k_pk_lit_ranges(LitExtParams le, PackBatch b, PackWork w) {
+    const uint32_t gi = blockIdx.x * PK_THREADS + threadIdx.x;
+    uint32_t c, j, n;
+    if (!locate_gap(b, w.kOff, gi, c, j, n)) return;
+    const uint32_t k = w.litFlag[gi];
+    if (w.litFlag[gi + 1] == k) return;
+    const uint64_t destLen = b.contigLen[c];
+    const uint64_t pos = w.litSpan[gi].x, length = w.litSpan[gi].y;
+    const uint64_t before = le.beforeAfter < pos ? le.beforeAfter : pos;                                       // :130
+    const uint64_t after = pos + length + le.beforeAfter < destLen ? le.beforeAfter : destLen - pos - length;  // :131-132
+    w.litRanges[k] = LitRange{c, static_cast<uint32_t>(pos - before), static_cast<uint32_t>(length + before + after), 0};
 }
 
 inline uint32_t blocks_for(uint64_t n) { return static_cast<uint32_t>((n + PK_THREADS - 1) / PK_THREADS); }
@@ -859,6 +887,15 @@ int launch_pack_count(const PackParams& p, const PackState& s, const PackBatch& 
     k_pk_count<<<blocks, PK_THREADS, 0, st>>>(p, s, b, w);
     k_pk_partials<PACK_STREAMS><<<PACK_STREAMS, 1024, 0, st>>>(w.blockTot, blocks);
     return 2;
+}
+
+int launch_pack_literal_ext(const LitExtParams& le, const PackBatch& b, const PackWork& w, cudaStream_t st) {
+    const uint32_t nGaps = b.nMatches + static_cast<uint32_t>(b.nContigs);
+    const uint32_t blocks = blocks_for(nGaps);
+    k_pk_lit_flag<<<blocks, PK_THREADS, 0, st>>>(le, b, w);
+    const int l = launch_scan_u32(w.litFlag, w.litFlag, nGaps, w.litScanState, st);
+    k_pk_lit_ranges<<<blocks, PK_THREADS, 0, st>>>(le, b, w);
+    return 2 + l;
 }
 
 int launch_pack_emit(const PackParams& p, const PackState& s, const PackBatch& b, const PackWork& w, cudaStream_t st) {

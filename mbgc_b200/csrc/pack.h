@@ -38,6 +38,7 @@ struct KeptRec {               // one match that survived pass 1, left shift app
     uint32_t len;
 };
 
+struct LitRange;
 struct LongRun {               // a long plain-literal run, copied by k_pk_copy_long
     const uint8_t* src;
     uint8_t* dst;
@@ -84,6 +85,21 @@ struct PackWork {
     LongRun* longRuns;         // [longCap]
     uint32_t longCap;
     uint8_t* out[PACK_STREAMS];
+    // MBGC_Encoder::processLiteral (row a12; all null when the option is off)
+    uint2* litSpan;            // [nGaps] (pos, length) of the plain literal run every gap appends (k_pk_emit)
+    uint32_t* litFlag;         // [nGaps+1] 1 = the run extends the reference; exclusive scan in place
+    LitRange* litRanges;       // [nGaps] ranges in append order
+    unsigned long long* litScanState;  // scan scratch, zeroed with the pack state
+};
+
+struct LitRange {              // one processLiteral append: text[start, start + len) of text `text`
+    uint32_t text, start, len, pad;
+};
+
+struct LitExtParams {          // MGMP_Params.h:68-69,175-187
+    uint64_t minLen;           // refLiteralMinimalLengthExt (UINT64_MAX = off, the reference's default)
+    uint64_t beforeAfter;      // refLiteralBeforeAfterExt
+    uint64_t factor;           // unmatchedFractionFactor of the contig-is-proper rule
 };
 
 // Each returns the number of kernel launches issued.
@@ -96,5 +112,8 @@ int launch_pack_claims(const PackParams& p, const PackState& s, const PackBatch&
 // extensions + stream sizes, scan, emission (MBGC_Encoder.cpp:214-287, 310-427)
 int launch_pack_count(const PackParams& p, const PackState& s, const PackBatch& b, const PackWork& w, cudaStream_t st);
 int launch_pack_emit(const PackParams& p, const PackState& s, const PackBatch& b, const PackWork& w, cudaStream_t st);
+// processLiteral (MBGC_Encoder.cpp:128-135, call sites :228 / :290) over the literal runs k_pk_emit recorded: flags, scan,
+// ranges; the number of ranges ends up in w.litFlag[nGaps]
+int launch_pack_literal_ext(const LitExtParams& le, const PackBatch& b, const PackWork& w, cudaStream_t st);
 
 }  // namespace mbgc_b200

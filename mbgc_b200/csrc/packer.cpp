@@ -5,7 +5,8 @@
 // outputs (the bytes appended to targetLiterals, targetMapOffDests, targetMapOff5thByte, targetMapLenDests,
 // targetGapDeltas, targetGapMismatchesFlags, the surviving match list and the returned unmatched count).  What
 // stays with the caller, because it needs encoder state the matcher does not own: the dissimilar-contig bail-out
-// (:202-205), processLiteral (:128-135, disabled by default) and the statistics counters (:289-302).
+// (:202-205) and the statistics counters (:289-302).  processLiteral (:128-135, a developer-build option, off by
+// default) comes back as a list of text ranges when setLiteralRefExt switched it on.
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -59,6 +60,8 @@ void B200SparseEMMatcher::packBatch(const PackParams& p, const std::vector<TextV
     packKeptCounts.assign(nT, 0);
     packKeptHost.clear();
     packKeptLast = KeptSlice{nullptr, 0};
+    packLitRanges.clear();
+    const bool wantLit = litExt.minLen != UINT64_MAX;
     for (auto& m : packMs) m = 0;
     packLaunches = 0;
     packSweeps[0] = packSweeps[1] = 0;
@@ -174,6 +177,7 @@ void B200SparseEMMatcher::packBatch(const PackParams& p, const std::vector<TextV
         const uint64_t oFlags = carve(64 * 4);
         const uint64_t oSumLen = carve(nC * 8ull);
         const uint64_t oNl = carve(nM * 8ull);
+        const uint64_t oLitScan = carve(wantLit ? (nGaps / 4096 + 8) * 8 : 0);
         const uint64_t oZeroEnd = woff;  // [0, oZeroEnd) is zeroed before every run
         const uint64_t oMContig = carve(nM * 4ull);
         const uint64_t oRemoved = carve(nM);
@@ -189,6 +193,9 @@ void B200SparseEMMatcher::packBatch(const PackParams& p, const std::vector<TextV
         const uint64_t oBlockTot = carve((blocks + 2) * PACK_STREAMS * 4);
         const uint64_t oStreamOff = carve(static_cast<uint64_t>(PACK_STREAMS) * (nC + 1) * 4);
         const uint64_t oLong = carve(static_cast<uint64_t>(longCap) * sizeof(LongRun));
+        const uint64_t oLitSpan = carve(wantLit ? nGaps * sizeof(uint2) : 0);
+        const uint64_t oLitFlag = carve(wantLit ? (nGaps + 1) * 4 : 0);
+        const uint64_t oLitRanges = carve(wantLit ? nGaps * sizeof(LitRange) : 0);
         uint64_t cap[PACK_STREAMS];
         uint64_t sumText = 0;
         for (int c = 0; c < nC; c++) sumText += texts[first + c].len;
@@ -221,6 +228,12 @@ void B200SparseEMMatcher::packBatch(const PackParams& p, const std::vector<TextV
         w.longRuns = reinterpret_cast<LongRun*>(dPackWork + oLong);
         w.longCap = longCap;
         for (int k = 0; k < PACK_STREAMS; k++) w.out[k] = dPackWork + oOut[k];
+        if (wantLit) {
+            w.litSpan = reinterpret_cast<uint2*>(dPackWork + oLitSpan);
+            w.litFlag = reinterpret_cast<uint32_t*>(dPackWork + oLitFlag);
+            w.litRanges = reinterpret_cast<LitRange*>(dPackWork + oLitRanges);
+            w.litScanState = reinterpret_cast<unsigned long long*>(dPackWork + oLitScan);
+        }
 
         // summary that comes back before the streams: flags, stream totals, kept offsets, kept length sums, offsets
         const uint64_t sumBytes = 64 * 4 + PACK_STREAMS * 4 + 8 + (nC + 1ull) * 4 + 8 + nC * 8ull +
@@ -231,6 +244,7 @@ void B200SparseEMMatcher::packBatch(const PackParams& p, const std::vector<TextV
         unsigned long long* hSumLen = reinterpret_cast<unsigned long long*>(hPackSum + align_up(64 * 4 + PACK_STREAMS * 4, 8));
         uint32_t* hKOff = reinterpret_cast<uint32_t*>(hSumLen + nC);
         uint32_t* hStreamOff = hKOff + (nC + 1) + ((nC + 1) & 1);
+        uint32_t* hLitCount = hStreamOff + static_cast<uint64_t>(PACK_STREAMS) * (nC + 1);
 
         check(cudaEventRecord(pkEv[1], stream), "event");
         // two blind sweeps each: the second only confirms the first.  MBGC_B200_PACK_SWEEPS=1 starts with one (whose
@@ -245,6 +259,7 @@ void B200SparseEMMatcher::packBatch(const PackParams& p, const std::vector<TextV
             launches += launch_pack_claims(p, s, b, w, claimSweeps, stream);
             launches += launch_pack_count(p, s, b, w, stream);
             launches += launch_pack_emit(p, s, b, w, stream);
+            if (wantLit) launches += launch_pack_literal_ext(litExt, b, w, stream);
             check(cudaGetLastError(), "pack launch");
             totalLaunches += static_cast<uint64_t>(launches);
             packLaunches += static_cast<uint64_t>(launches);
@@ -253,6 +268,7 @@ void B200SparseEMMatcher::packBatch(const PackParams& p, const std::vector<TextV
             if (nC) check(cudaMemcpyAsync(hSumLen, w.sumLen, nC * 8ull, cudaMemcpyDeviceToHost, stream), "D2H(pack sums)");
             check(cudaMemcpyAsync(hKOff, w.kOff, (nC + 1ull) * 4, cudaMemcpyDeviceToHost, stream), "D2H(kept offsets)");
             check(cudaMemcpyAsync(hStreamOff, w.streamOff, static_cast<uint64_t>(PACK_STREAMS) * (nC + 1) * 4, cudaMemcpyDeviceToHost, stream), "D2H(stream offsets)");
+            if (wantLit) check(cudaMemcpyAsync(hLitCount, w.litFlag + nGaps, 4, cudaMemcpyDeviceToHost, stream), "D2H(literal range count)");
             check(cudaEventRecord(pkEv[2], stream), "event");
             check(cudaStreamSynchronize(stream), "pack sync");
             // a sweep that still changed something means the fixed point was not reached: run again with more sweeps
@@ -290,8 +306,17 @@ void B200SparseEMMatcher::packBatch(const PackParams& p, const std::vector<TextV
             keptTmp.resize(hKOff[nC]);
             check(cudaMemcpyAsync(keptTmp.data(), w.kept, hKOff[nC] * sizeof(KeptRec), cudaMemcpyDeviceToHost, stream), "D2H(kept)");
         }
+        std::vector<LitRange> litTmp;
+        if (wantLit && *hLitCount) {
+            litTmp.resize(*hLitCount);
+            check(cudaMemcpyAsync(litTmp.data(), w.litRanges, litTmp.size() * sizeof(LitRange), cudaMemcpyDeviceToHost, stream), "D2H(literal ranges)");
+        }
         check(cudaEventRecord(pkEv[3], stream), "event");
         check(cudaStreamSynchronize(stream), "pack D2H sync");
+        for (LitRange r : litTmp) {
+            r.text += static_cast<uint32_t>(first);
+            packLitRanges.push_back(r);
+        }
         for (int c = 0; c < nC; c++) {
             for (int k = 0; k < PACK_STREAMS; k++) packOff[k][first + c] = outUsed[k] + hStreamOff[static_cast<uint64_t>(k) * (nC + 1) + c];
             packKeptCounts[first + c] = hKOff[c + 1] - hKOff[c];

@@ -214,6 +214,10 @@ def load_library():
                                    C.c_uint64, C.POINTER(_PackResult)]
     L.mbgcg_pack_kept_matches.restype = C.c_int
     L.mbgcg_pack_kept_matches.argtypes = [vp, C.POINTER(vp), u64p]
+    L.mbgcg_set_literal_ref_ext.restype = C.c_int
+    L.mbgcg_set_literal_ref_ext.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_int]
+    L.mbgcg_pack_literal_ref_ext.restype = C.c_int
+    L.mbgcg_pack_literal_ref_ext.argtypes = [vp, C.POINTER(vp), u64p]
     L.mbgcg_pack_timing.argtypes = [vp, C.POINTER(C.c_float), u64p, C.POINTER(C.c_int)]
     L.mbgcg_ingest_fasta.restype = C.c_int
     L.mbgcg_ingest_fasta.argtypes = [vp, vp, C.c_uint64, C.POINTER(vp), u64p, C.POINTER(vp), u64p, C.POINTER(C.c_int)]
@@ -790,6 +794,23 @@ class Matcher:
         n = C.c_uint64()
         self._check(self.lib.mbgcg_pack_kept_matches(self.h, C.byref(out), C.byref(n)))
         return self._matches(out, n.value)
+
+    def setLiteralRefExt(self, refLiteralMinimalLengthExt=None, refLiteralBeforeAfterExt=0, unmatchedFractionFactor=128):
+        """MBGC_Encoder::processLiteral on (the reference's developer option -N / -F) or, with None, off again
+        (mbgcg_set_literal_ref_ext): every later packBatch also lists the literal runs that extend the reference."""
+        m = 0xFFFFFFFFFFFFFFFF if refLiteralMinimalLengthExt is None else int(refLiteralMinimalLengthExt)
+        self._check(self.lib.mbgcg_set_literal_ref_ext(self.h, m, int(refLiteralBeforeAfterExt), int(unmatchedFractionFactor)))
+
+    def packLiteralRefExt(self):
+        """what processLiteral appended to targetRefExtensions during the last packBatch (mbgcg_pack_literal_ref_ext):
+        (n, 3) uint32 array of (text index, start, length), in append order"""
+        out = C.c_void_p()
+        n = C.c_uint64()
+        self._check(self.lib.mbgcg_pack_literal_ref_ext(self.h, C.byref(out), C.byref(n)))
+        if not n.value:
+            return np.zeros((0, 3), dtype=np.uint32)
+        a = np.ctypeslib.as_array(C.cast(out, C.POINTER(C.c_uint32)), shape=(n.value, 4))
+        return a[:, :3].copy()
 
     def packTiming(self):
         ms = (C.c_float * 4)()

@@ -21,7 +21,7 @@ def n_devices():
     return torch.cuda.device_count()
 
 
-def gpu_streams(paths, mode, devices, chunk_bytes, pinned=True, max_window=0):
+def gpu_streams(paths, mode, devices, chunk_bytes, pinned=True, max_window=0, lit_ext=None):
     """the GPU side of seq_schedule.encode_streams: same initial reference, then the pass over the file images"""
     recs0 = read_fasta(paths[0])
     c0 = recs0[0][1]
@@ -32,6 +32,8 @@ def gpu_streams(paths, mode, devices, chunk_bytes, pinned=True, max_window=0):
     try:
         g.disableSlidingWindow()
         g.loadRef(c0, True, True, 0)
+        if lit_ext is not None:   # MBGC_Encoder::processLiteral on (row a12)
+            g.setLiteralRefExt(lit_ext[0], lit_ext[1], 128)
         images = [open(p, "rb").read() for p in paths]
         out, info = g.compressSequential(images, SeqConfig.for_mode(mode, chunk_bytes, max_window), pinned=pinned)
         info["ref_length"] = g.getRefLength()
@@ -42,9 +44,9 @@ def gpu_streams(paths, mode, devices, chunk_bytes, pinned=True, max_window=0):
         g.close()
 
 
-def check_against_oracle(paths, mode, devices, chunk_bytes, **kw):
-    want, wstats = encode_streams(paths, mode)
-    got, info = gpu_streams(paths, mode, devices, chunk_bytes, **kw)
+def check_against_oracle(paths, mode, devices, chunk_bytes, lit_ext=None, **kw):
+    want, wstats = encode_streams(paths, mode, lit_ext=lit_ext)
+    got, info = gpu_streams(paths, mode, devices, chunk_bytes, lit_ext=lit_ext, **kw)
     lit0 = read_fasta(paths[0])[0][1]
     assert want["literals"][:len(lit0)] == lit0
     want = dict(want)
