@@ -12,7 +12,8 @@
 //
 // Kept on the host, because it needs encoder state: the dissimilar-contig bail-out (:202-205) and the statistics
 // counters (:289-302; developer output only).  processLiteral (:128-135) is switched off in every preset
-// (refLiteralMinimalLengthExt = SIZE_MAX, matching/MGMP_Params.h:45); asking for it ends with an error.
+// (refLiteralMinimalLengthExt = SIZE_MAX, matching/MGMP_Params.h:45); a developer build (-N / -F) gets it from the device
+// packer as a list of text ranges (mbgcg_pack_literal_ref_ext).
 #include "MBGC_Encoder.h"
 
 #include <cstdio>
@@ -66,8 +67,9 @@ size_t MBGC_Encoder::processMatches(vector<PgTools::TextMatch>& textMatches, cha
         removedGapBreakingMatchesAll += ev->nMatches - ev->kept;
         return ev->unmatched;
     }
-    if (params->refLiteralMinimalLengthExt != SIZE_MAX)
-        die("mbgc_b200: literal-based reference extension (refLiteralMinimalLengthExt) is not part of the device packer");
+    // processLiteral (:128-135): the device packer lists the literal runs that extend the reference (row a12); only a
+    // developer build of the reference can ask for it (main.cpp:308-313)
+    const bool literalExt = params->refLiteralMinimalLengthExt != SIZE_MAX;
     mbgcg_pack_params_t pp{};
     pp.enableExtensionsWithMismatches = params->enableExtensionsWithMismatches;
     pp.gapDepthOffsetEncoding = params->gapDepthOffsetEncoding;
@@ -98,6 +100,10 @@ size_t MBGC_Encoder::processMatches(vector<PgTools::TextMatch>& textMatches, cha
         const uint64_t locks[1] = {matchingLockPos};
         static_assert(sizeof(PgTools::TextMatch) == sizeof(mbgcg_match_t), "TextMatch layout");
         mbgcg_pack_result_t r;
+        const int factor0 = unmatchedFractionFactors[2 * (targetsCountShift + targetIdx)];
+        if (mbgcg_set_literal_ref_ext(h, literalExt ? params->refLiteralMinimalLengthExt : UINT64_MAX,
+                                      literalExt ? params->refLiteralBeforeAfterExt : 0, factor0) != MBGCG_OK)
+            die(mbgcg_last_error(h));
         const int rc = mbgcg_pack_batch(h, &pp, 1, texts, lens,
                                         residentRoute ? nullptr : reinterpret_cast<const mbgcg_match_t*>(textMatches.data()),
                                         counts, locks, refExtLoadedPosArr.data(), refExtLoadedPosArr.size(), &r);
@@ -114,6 +120,12 @@ size_t MBGC_Encoder::processMatches(vector<PgTools::TextMatch>& textMatches, cha
             for (uint64_t i = 0; i < nk; i++)
                 textMatches.push_back(PgTools::TextMatch(km[i].posSrcText, km[i].length, km[i].posDestText));
             return PROCESSING_MATCHES_SKIPPED_DUE_TO_CONTIG_DISSIMILARITY;
+        }
+        if (literalExt) {  // :228 / :290, in append order
+            const mbgcg_lit_range_t* lr = nullptr;
+            uint64_t nl = 0;
+            if (mbgcg_pack_literal_ref_ext(h, &lr, &nl) != MBGCG_OK) die(mbgcg_last_error(h));
+            for (uint64_t i = 0; i < nl; i++) targetRefExtensions[targetIdx].append(destStart + lr[i].start, lr[i].len);
         }
         auto seg = [&](int s) { return reinterpret_cast<const char*>(r.stream[s] + r.streamOff[s][0]); };
         auto len = [&](int s) { return static_cast<size_t>(r.streamOff[s][1] - r.streamOff[s][0]); };

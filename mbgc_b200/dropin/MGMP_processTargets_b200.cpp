@@ -260,12 +260,27 @@ void fill_pack_params(mbgcg_pack_params_t& p, const MBGC_Params* mp) {
     p.gapBreakingMatchMinLength = mp->gapBreakingMatchMinLength;
 }
 
-void check_supported(const MGMP_Params* params) {
+void check_supported(const MGMP_Params* params, bool parallelLoop) {
     if (!params->enableDNALineLengthDetection || params->allowLossyParsing)
         die("mbgc_b200 (batched): the lossy / FASTQ readers are not part of the device ingest; use mbgc_b200_full");
     if (params->uppercaseDNA) die("mbgc_b200 (batched): upper-casing of the input is not part of the device ingest; use mbgc_b200_full");
-    if (params->refLiteralMinimalLengthExt != SIZE_MAX)
-        die("mbgc_b200 (batched): literal-based reference extension is not part of the device packer");
+    if (params->refLiteralMinimalLengthExt != SIZE_MAX && parallelLoop)
+        die("mbgc_b200 (batched): literal-based reference extension belongs to the sequential schedule (-t 1)");
+#ifdef DEVELOPER_BUILD
+    // the experimental extension strategies of the developer build (main.cpp:302-319) other than -N / -F
+    if (params->refExtensionStrategy & (MGMP_Params::COMBINED_REF_EXTENSION_STRATEGY_MASK | MGMP_Params::ONLY_LITERAL_REF_EXTENSION_STRATEGY_MASK |
+                                        MGMP_Params::BLOCK_REF_EXTENSION_STRATEGY_MASK | MGMP_Params::DYNAMIC_REF_EXT_FACTOR_MASK))
+        die("mbgc_b200 (batched): the experimental reference extension strategies (-1 -4 -8 -W) are not part of the collection pass");
+#endif
+}
+
+// processLiteral (MBGC_Encoder.cpp:128-135; `-N` / `-F` of a developer build): the handle lists the literal runs and the
+// sequential pass extends the reference with them
+void apply_literal_ref_ext(mbgcg_t* h, const MGMP_Params* params) {
+    const bool on = params->refLiteralMinimalLengthExt != SIZE_MAX;
+    if (mbgcg_set_literal_ref_ext(h, on ? params->refLiteralMinimalLengthExt : UINT64_MAX, on ? params->refLiteralBeforeAfterExt : 0,
+                                  params->currentUnmatchedFractionFactor) != MBGCG_OK)
+        die(mbgcg_last_error(h));
 }
 
 struct LoopTimes {
@@ -295,7 +310,7 @@ void trace_pass(const char* what, mbgcg_t* h, const mbgcg_seq_stats_t& st, int n
 // ---------------------------------------------------------------------------------------------------------------------
 void MultipleGenomeMatchingProcessor::processTargetsWithParallelIO() {
     MBGC_Params* mp = static_cast<MBGC_Params*>(params);  // the driver's MGMP_Params is the encoder's MBGC_Params object
-    check_supported(params);
+    check_supported(params, false);
     const bool trace = std::getenv("MBGC_B200_TRACE") != nullptr;
     const double tStart = now_ms();
 
@@ -323,6 +338,7 @@ void MultipleGenomeMatchingProcessor::processTargetsWithParallelIO() {
     cfg.refRegionSeparators = params->refRegionSeparators;
     cfg.separatorPerFile = mp->lazyDecompressionSupport;
     cfg.regionSeparator = MGMP_Params::REF_REGION_SEPARATOR;
+    apply_literal_ref_ext(h, params);
     if (mbgcg_seq_begin(h, &cfg, es.loadedPosArr, es.nLoadedPos) != MBGCG_OK) die(mbgcg_last_error(h));
 
     const int nFiles = static_cast<int>(filesCount);
@@ -435,7 +451,7 @@ void MultipleGenomeMatchingProcessor::processTargetsWithParallelIO() {
 // ---------------------------------------------------------------------------------------------------------------------
 void MultipleGenomeMatchingProcessor::processTargetsParallel() {
     MBGC_Params* mp = static_cast<MBGC_Params*>(params);
-    check_supported(params);
+    check_supported(params, true);
     const bool trace = std::getenv("MBGC_B200_TRACE") != nullptr;
     const double tStart = now_ms();
 
