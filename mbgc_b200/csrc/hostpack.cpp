@@ -40,8 +40,21 @@ bool pack_scalar(const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t devOff, 
     return true;
 }
 
+// Software prefetch distance of the packing loops.  On the GPU boxes (16 vCPUs of a Sapphire Rapids host) a core streams
+// ~5.6 GB/s out of DRAM on its own and ~8.4 GB/s with a prefetch 4 - 8 KiB ahead: 15 packers read 86 vs 125 GB/s, the
+// box's DRAM limit (tools/hostring_probe.cu; sweep of the whole transfer in profiles/README.md r02c: 79 -> 104 GB/s end to
+// end).  MBGC_B200_PACK_PREFETCH = bytes, 0 = none.
+inline uint64_t prefetch_distance() {
+    static const uint64_t d = []() -> uint64_t {
+        const char* e = std::getenv("MBGC_B200_PACK_PREFETCH");
+        return e ? std::strtoull(e, nullptr, 10) : 8192;
+    }();
+    return d;
+}
+
 __attribute__((target("avx2"))) bool pack_avx2(const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t devOff,
                                                std::vector<ExcRun>& runs, size_t maxRuns) {
+    const uint64_t pfd = prefetch_distance();
     // expected byte per low nibble: 'A' 0x41, 'C' 0x43, 'T' 0x54, 'G' 0x47; 0xFF where no base has that nibble
     const __m256i lut = _mm256_setr_epi8(-1, 0x41, -1, 0x43, 0x54, -1, -1, 0x47, -1, -1, -1, -1, -1, -1, -1, -1,  //
                                          -1, 0x41, -1, 0x43, 0x54, -1, -1, 0x47, -1, -1, -1, -1, -1, -1, -1, -1);
@@ -59,6 +72,7 @@ __attribute__((target("avx2"))) bool pack_avx2(const uint8_t* src, uint64_t n, u
     for (; i + 64 <= n; i += 64) {
         uint32_t out[4];
         bool slow = false;
+        if (pfd) _mm_prefetch(reinterpret_cast<const char*>(src + i + pfd), _MM_HINT_T0);  // never faults, also past the end
 #pragma GCC unroll 2
         for (int h = 0; h < 2; h++) {
             const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i + 32 * h));
@@ -179,10 +193,12 @@ __attribute__((target("avx2"))) bool image_avx2(const uint8_t* src, uint64_t n, 
     const __m256i gather = _mm256_setr_epi8(0, 4, 8, 12, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1,  //
                                             0, 4, 8, 12, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1);
     const bool ntOk = (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
+    const uint64_t pfd = prefetch_distance();
     uint64_t i = 0;
     for (; i + 64 <= n; i += 64) {
         uint32_t out[4];
         uint64_t bad = 0, nls = 0;
+        if (pfd) _mm_prefetch(reinterpret_cast<const char*>(src + i + pfd), _MM_HINT_T0);
 #pragma GCC unroll 2
         for (int h = 0; h < 2; h++) {
             const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i + 32 * h));

@@ -642,7 +642,8 @@ void B200SparseEMMatcher::growDevice(void** p, uint64_t* cap, uint64_t need, con
 // copied as they finish and expanded on the device.  See hostpack.hpp for why.
 //   MBGC_B200_PACK          0 = never pack; unset / 1 = pack batches of MBGC_B200_PACK_MIN_BYTES (default 2 MiB) and more
 //   MBGC_B200_RAW_PERMILLE  share of the bytes that travels raw while the CPU packs the rest (default: from the
-//                           number of packer threads, 300 with 15 of them)
+//                           number of packer threads, 60 with 15 of them)
+//   MBGC_B200_PACK_GBPS     effective packing rate per thread the default share is computed from (11)
 //   MBGC_B200_PACK_THREADS  worker threads (default: hardware threads / LOCAL_WORLD_SIZE - 1)
 int B200SparseEMMatcher::stageTexts(const std::vector<TextView>& texts, size_t first, int nC,
                                     const std::vector<uint64_t>& off) {
@@ -685,10 +686,14 @@ int B200SparseEMMatcher::stageTexts(const std::vector<TextView>& texts, size_t f
         }
     }
     // raw share r that balances the copy engine ((r + (1 - r) / 4) bytes at ~52 GB/s) against the packers ((1 - r)
-    // bytes at ~4.8 GB/s per thread, measured on the B200 box): r = (c - 1/4) / (3/4 + c), c = 52 / (4.8 threads);
-    // 15 threads -> 0.32 (the sweep's optimum was 0.30), 5 threads (8 ranks on 48 cores) -> 0.66
-    const double cRatio = 52.0 / (4.8 * pool->size());
-    int rawPermille = static_cast<int>(1000.0 * std::max(0.3, std::min(1.0, (cRatio - 0.25) / (0.75 + cRatio))));
+    // bytes at p GB/s per thread): r = (c - 1/4) / (3/4 + c), c = 52 / (p threads).  With the software prefetch in the
+    // packing loop a thread reads ~8.4 GB/s and 15 of them saturate the host's DRAM (~126 GB/s), so every raw byte the
+    // copy engine fetches slows them down: the sweep on the B200 box (profiles/README.md r02c) has its optimum at r = 0 ..
+    // 0.05, which the formula gives with an effective p = 11; 7 threads (2 ranks on 16 cores) -> 0.30, 3 threads -> 0.57
+    double perThread = 11.0;
+    if (const char* e = std::getenv("MBGC_B200_PACK_GBPS")) perThread = std::max(0.1, std::atof(e));
+    const double cRatio = 52.0 / (perThread * pool->size());
+    int rawPermille = static_cast<int>(1000.0 * std::max(0.0, std::min(1.0, (cRatio - 0.25) / (0.75 + cRatio))));
     if (const char* e = std::getenv("MBGC_B200_RAW_PERMILLE")) rawPermille = std::max(0, std::min(1000, std::atoi(e)));
     if (!pinnedSrc) rawPermille = 0;
     uint64_t seen = 0, rawBytes = 0, packedBytes = 0;

@@ -12,6 +12,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--tier", default="near")
 ap.add_argument("--steps", type=int, default=40)
 ap.add_argument("--genomes", type=int, default=100)
+ap.add_argument("--e2e", action="store_true", help="time mbgcg_match_batch with HOST buffers (pinned) instead of the device-resident call")
 ap.add_argument("--configs", default="CLEAN_VARIANT=0,SCAN_LOOKBACK=1;CLEAN_VARIANT=1,SCAN_LOOKBACK=1;CLEAN_VARIANT=2,SCAN_LOOKBACK=1;CLEAN_VARIANT=0,SCAN_LOOKBACK=0;CLEAN_VARIANT=1,SCAN_LOOKBACK=0")
 args = ap.parse_args()
 TIERS = {"near": (1e-4, 1e-5), "div": (1e-2, 1e-3)}
@@ -24,6 +25,7 @@ m = mbgc_b200.Matcher(mgmp_ref_limit(args.genomes + 1, base.size), 32, 16, 1, 16
 m.disableSlidingWindow()
 m.loadRef(base, True, True, 0)
 dev = []
+host = [[torch.from_numpy(t).pin_memory() for t in tg] for tg in batches] if args.e2e else None
 for tg in batches:
     offs, cur = [], 64
     for t in tg:
@@ -37,6 +39,8 @@ torch.cuda.synchronize()
 stream = torch.cuda.ExternalStream(m.stream())
 
 def step(k):
+    if args.e2e:
+        return m.matchBatch([h.numpy() for h in host[k % nb]], 32, copy=False, split=False)
     d, o, l = dev[k % nb]
     return m.matchBatchDevice(d.data_ptr(), o, l, 32, copy=False, split=False)
 
@@ -66,5 +70,6 @@ for cfg in args.configs.split(";"):
     dig = hashlib.md5(np.ascontiguousarray(res[0]).tobytes()).hexdigest()
     if ref_digest is None:
         ref_digest = dig
-    print(json.dumps({"config": cfg, "ms_per_step": round(ms, 4), "matches": int(len(res[0])), "same_lists": dig == ref_digest,
+    extra = {"GBps": round(sum(t.size + 70 + t.size // 80 for t in batches[0]) / ms / 1e6, 1), "wire": m.wireBytes()} if args.e2e else {}
+    print(json.dumps({**extra, "config": cfg, "ms_per_step": round(ms, 4), "matches": int(len(res[0])), "same_lists": dig == ref_digest,
                       "stage_ms": {k: round(v, 4) for k, v in stage.items()}}), flush=True)
