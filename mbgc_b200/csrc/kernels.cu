@@ -329,6 +329,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_lookback(const uint32_t* 
                                                                 uint32_t nConst, uint32_t nMax,
                                                                 unsigned long long* state, uint32_t stateWords,
                                                                 uint32_t* totalOut) {
+    griddep_launch_dependents();
+    griddep_wait();
     __shared__ uint32_t sWarp[33];
     __shared__ uint32_t sPrefix, sTile;
     const uint32_t n = scan_len(nPtr, nConst, nMax);
@@ -419,6 +421,8 @@ __device__ __forceinline__ uint4 scan_load4(const uint32_t* in, uint32_t i0, uin
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_ranges(const uint32_t* in, uint32_t* out, const uint32_t* nPtr,
                                                               uint32_t nConst, uint32_t nMax, unsigned long long* state,
                                                               uint32_t stateWords, uint32_t* totalOut) {
+    griddep_launch_dependents();
+    griddep_wait();
     __shared__ uint32_t sW[RANGE_GROUP][33];
     __shared__ uint32_t sTileTot[RANGE_GROUP];
     __shared__ uint32_t sRed[33];
@@ -563,8 +567,8 @@ static int scan_exclusive(const uint32_t* in, uint32_t* out, const uint32_t* nPt
     if (blocks == 0) blocks = 1;
     static const bool lookback = []() { const char* e = getenv("MBGC_B200_SCAN_LOOKBACK"); return e && e[0] == '1'; }();
     const bool aligned = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
-    if (lookback || !aligned) k_scan_lookback<<<blocks, SCAN_THREADS, 0, st>>>(in, out, nPtr, nConst, nMax, state, stateWords, totalOut);
-    else k_scan_ranges<<<blocks, SCAN_THREADS, 0, st>>>(in, out, nPtr, nConst, nMax, state, stateWords, totalOut);
+    if (lookback || !aligned) launch_pdl(k_scan_lookback, blocks, SCAN_THREADS, 0, st, in, out, nPtr, nConst, nMax, state, stateWords, totalOut);
+    else launch_pdl(k_scan_ranges, blocks, SCAN_THREADS, 0, st, in, out, nPtr, nConst, nMax, state, stateWords, totalOut);
     return 1;
 }
 
@@ -701,6 +705,7 @@ __device__ __forceinline__ uint32_t verify_candidate(const IndexState& ix, const
 // loads coalesce; with it, k_clean hands over only the items it could not prove identical to the reference.
 template <int KW, bool FILTER>
 __global__ void __launch_bounds__(FILTER ? PROBE_THREADS_FILTER : PROBE_THREADS_PLAIN, 1) k_probe(const ProbeArgs a) {
+    griddep_launch_dependents();
     constexpr int NPT = PROBE_NPT;
     constexpr int NWA = probe_words(KW);
     extern __shared__ __align__(128) uint32_t sFilter[];  // [filter words][mbarrier]
@@ -721,6 +726,8 @@ __global__ void __launch_bounds__(FILTER ? PROBE_THREADS_FILTER : PROBE_THREADS_
                             min(32768u, bytes - off), barAddr);
         }
     }
+    // everything above is independent of the pass (the filter belongs to the index): the kernels in front may still run
+    griddep_wait();
     const uint32_t warpsTotal = gridDim.x * (blockDim.x >> 5);
     const uint32_t nItems = a.laneList ? *a.laneCount : a.b.nTiles * 32u;
     for (uint32_t kb = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32; kb < nItems; kb += warpsTotal * 32) {
@@ -810,6 +817,8 @@ __global__ void __launch_bounds__(FILTER ? PROBE_THREADS_FILTER : PROBE_THREADS_
 // ------------------------------------------------------------------------------------------------------
 template <int KW>
 __global__ void __launch_bounds__(256) k_anchor(const ProbeArgs a) {
+    griddep_launch_dependents();
+    griddep_wait();
     constexpr int NPT = PROBE_NPT;
     constexpr int NWA = probe_words(KW);
     // anchored chunks: every ANCHOR_STRIDE-th chunk, and the first chunk of every contig
@@ -894,6 +903,8 @@ struct CleanArgs {
 // 16 LPC contiguous bytes per load instruction (whole sectors as long as LPC >= 2).
 template <int LPC, int OCC>
 __global__ void __launch_bounds__(256, OCC) k_clean(const CleanArgs a) {
+    griddep_launch_dependents();
+    griddep_wait();
     constexpr int CPW = 32 / LPC;  // chunks per warp
     constexpr int PPL = 32 / LPC;  // 16-byte pieces per lane
     constexpr uint32_t GMASK = LPC == 32 ? 0xffffffffu : (1u << (LPC & 31)) - 1u;
@@ -1040,6 +1051,8 @@ __global__ void __launch_bounds__(256, OCC) k_clean(const CleanArgs a) {
 __global__ void __launch_bounds__(256) k_memo(uint32_t nTiles, uint32_t nValid, const uint16_t* __restrict__ seedMask,
                                               const uint32_t* __restrict__ scratchEnc, uint32_t* __restrict__ memoX,
                                               uint32_t* __restrict__ memoE) {
+    griddep_launch_dependents();
+    griddep_wait();
     const int lane = threadIdx.x & 31;
     const uint32_t warpsTotal = gridDim.x * (blockDim.x >> 5);
     for (uint32_t g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); g < nTiles; g += warpsTotal) {
@@ -1179,6 +1192,8 @@ int launch_unpack(const PackedBlock* blocks, uint32_t nBlocks, const uint8_t* pa
 // chunk -> contig table and self-contained chunk descriptors (one binary search per chunk, once per pass)
 __global__ void __launch_bounds__(256) k_chunk_contig(BatchDesc b, int K, uint32_t* __restrict__ chunkContig,
                                                       uint4* __restrict__ chunkDesc, uint32_t* __restrict__ chunkCount) {
+    griddep_launch_dependents();
+    griddep_wait();
     for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < b.nTiles; g += gridDim.x * blockDim.x) {
         const uint32_t c = static_cast<uint32_t>(upper_contig(b.tileStart, b.nContigs, g));
         chunkContig[g] = c;
@@ -1198,7 +1213,7 @@ static void launch_probe_k(const ProbeArgs& a, bool useFilter, int mode, cudaStr
         uint32_t blocks = (a.b.nTiles / ANCHOR_STRIDE + a.b.nContigs + 256) / 256;
         const uint32_t cap = static_cast<uint32_t>(sm) * 8;
         if (blocks > cap) blocks = cap;
-        k_anchor<KW><<<blocks, 256, 0, st>>>(a);
+        launch_pdl(k_anchor<KW>, blocks, 256, 0, st, a);
         return;
     }
     if (useFilter) {
@@ -1212,12 +1227,12 @@ static void launch_probe_k(const ProbeArgs& a, bool useFilter, int mode, cudaStr
             cudaFuncSetAttribute(k_probe<KW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(PROBE_FILTER_BYTES + 16));
             attrSet.fetch_or(bit, std::memory_order_release);
         }
-        k_probe<KW, true><<<sm, PROBE_THREADS_FILTER, smem, st>>>(a);
+        launch_pdl(k_probe<KW, true>, sm, PROBE_THREADS_FILTER, smem, st, a);
     } else {
         uint32_t blocks = (a.b.nTiles + PROBE_THREADS_PLAIN / 32 - 1) / (PROBE_THREADS_PLAIN / 32);
         const uint32_t cap = static_cast<uint32_t>(sm) * 2;
         if (blocks > cap) blocks = cap;
-        k_probe<KW, false><<<blocks, PROBE_THREADS_PLAIN, 0, st>>>(a);
+        launch_pdl(k_probe<KW, false>, blocks, PROBE_THREADS_PLAIN, 0, st, a);
     }
 }
 
@@ -1238,7 +1253,7 @@ int launch_chunk_desc(const IndexState& ix, const BatchDesc& b, const WorkBuffer
         cudaMemsetAsync(w.tileCount, 0, sizeof(uint32_t), st);
         return 0;
     }
-    k_chunk_contig<<<device_sm_count() * 4, 256, 0, st>>>(b, ix.K, w.chunkContig, w.chunkDesc, w.tileCount);
+    launch_pdl(k_chunk_contig, device_sm_count() * 4, 256, 0, st, b, ix.K, w.chunkContig, w.chunkDesc, w.tileCount);
     return 1;
 }
 
@@ -1262,14 +1277,14 @@ int launch_clean(const IndexState& ix, const BatchDesc& b, const WorkBuffers& w,
                 w.seedMask, w.scratchEnc, w.chunkSegN, w.chunkSeg, w.dirtyMask, w.workList, w.laneList, w.counters};
     // 8 lanes per chunk, 8 CTAs per SM: 4 or 2 lanes per chunk execute 30-50 % fewer instructions per chunk and were measured
     // 25 % / 2.2x slower, 6 CTAs per SM with 40 registers 6 % slower (profiles/README.md, r02c experiments)
-    k_clean<8, 8><<<device_sm_count() * 8, 256, 0, st>>>(a);
+    launch_pdl(k_clean<8, 8>, device_sm_count() * 8, 256, 0, st, a);
     return 1;
 }
 
 int launch_memo(const BatchDesc& b, const WorkBuffers& w, uint32_t nValid, uint32_t* memoX, uint32_t* memoE,
                 cudaStream_t st) {
     if (b.nTiles == 0) return 0;
-    k_memo<<<device_sm_count() * 4, 256, 0, st>>>(b.nTiles, nValid, w.seedMask, w.scratchEnc, memoX, memoE);
+    launch_pdl(k_memo, device_sm_count() * 4, 256, 0, st, b.nTiles, nValid, w.seedMask, w.scratchEnc, memoX, memoE);
     return 1;
 }
 
@@ -1289,6 +1304,8 @@ __global__ void __launch_bounds__(256) k_compact(BatchDesc b, const uint32_t* __
                                                  const uint32_t* __restrict__ dirtyMask,
                                                  const uint8_t* __restrict__ chunkSegN, const uint2* __restrict__ chunkSeg,
                                                  SeedRec* __restrict__ seeds, uint32_t seedCap, uint32_t* counters) {
+    griddep_launch_dependents();
+    griddep_wait();
     const uint32_t nSeeds = chunkOff[b.nTiles];
     if (nSeeds > seedCap) {
         if (blockIdx.x == 0 && threadIdx.x == 0) counters[3] = 1;  // overflow: host retries with more room
@@ -1337,6 +1354,8 @@ __global__ void __launch_bounds__(256) k_compact_clean(BatchDesc b, const uint32
                                                        const uint8_t* __restrict__ chunkSegN,
                                                        const uint2* __restrict__ chunkSeg, SeedRec* __restrict__ seeds,
                                                        uint32_t seedCap) {
+    griddep_launch_dependents();
+    griddep_wait();
     if (chunkOff[b.nTiles] > seedCap) return;
     for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < b.nTiles; g += gridDim.x * blockDim.x) {
         if (dirtyMask[g]) continue;
@@ -1368,6 +1387,8 @@ __global__ void __launch_bounds__(256) k_compact_clean(BatchDesc b, const uint32
 __global__ void __launch_bounds__(256) k_heads(IndexState ix, BatchDesc b, const uint32_t* __restrict__ chunkOff,
                                                const SeedRec* __restrict__ seeds, uint32_t* __restrict__ head,
                                                const uint32_t* counters) {
+    griddep_launch_dependents();
+    griddep_wait();
     if (counters[3]) return;
     const uint32_t nSeeds = chunkOff[b.nTiles];
     const uint32_t encStep = ix.k1ord >= 0 ? static_cast<uint32_t>(ix.k1 >> ix.k1ord) : static_cast<uint32_t>(ix.k1);
@@ -1398,6 +1419,8 @@ __global__ void __launch_bounds__(256) k_heads(IndexState ix, BatchDesc b, const
 __global__ void __launch_bounds__(256) k_runs(BatchDesc b, const uint32_t* __restrict__ tileOff,
                                               const uint32_t* __restrict__ headScan, uint32_t* __restrict__ runFirst,
                                               uint32_t* __restrict__ runStart, uint32_t* counters) {
+    griddep_launch_dependents();
+    griddep_wait();
     if (counters[3]) return;
     const uint32_t nSeeds = tileOff[b.nTiles];
     const uint32_t nRuns = headScan[nSeeds];
@@ -1421,19 +1444,19 @@ int launch_compact_and_runs(const IndexState& ix, const BatchDesc& b, const Work
     const int sm = device_sm_count();
     // tileCount -> tileOff (in place), tileOff[nTiles] = nSeeds
     launches += scan_exclusive(w.tileCount, w.tileCount, nullptr, b.nTiles, b.nTiles, w.scanState, w.scanStride, nullptr, st);
-    k_compact<<<sm * 8, 256, 0, st>>>(b, w.chunkContig, w.tileCount, w.seedMask, w.scratchEnc,
+    launch_pdl(k_compact, sm * 8, 256, 0, st, b, w.chunkContig, w.tileCount, w.seedMask, w.scratchEnc,
                                       segments ? w.workList : nullptr, segments ? w.counters + 6 : nullptr,
                                       w.dirtyMask, w.chunkSegN, w.chunkSeg, w.seeds, w.seedCap, w.counters);
     if (segments) {
-        k_compact_clean<<<sm * 8, 256, 0, st>>>(b, w.chunkContig, w.tileCount, w.dirtyMask, w.chunkSegN, w.chunkSeg,
+        launch_pdl(k_compact_clean, sm * 8, 256, 0, st, b, w.chunkContig, w.tileCount, w.dirtyMask, w.chunkSegN, w.chunkSeg,
                                                 w.seeds, w.seedCap);
         launches += 1;
     }
-    k_heads<<<sm * 8, 256, 0, st>>>(ix, b, w.tileCount, w.seeds, w.headScan, w.counters);
+    launch_pdl(k_heads, sm * 8, 256, 0, st, ix, b, w.tileCount, w.seeds, w.headScan, w.counters);
     launches += 2;
     // head flags -> exclusive scan in place; length lives on the device (tileOff[nTiles])
     launches += scan_exclusive(w.headScan, w.headScan, w.tileCount + b.nTiles, 0, w.seedCap, w.scanState + w.scanStride, w.scanStride, nullptr, st);
-    k_runs<<<sm * 8, 256, 0, st>>>(b, w.tileCount, w.headScan, w.runFirst, w.runStart, w.counters);
+    launch_pdl(k_runs, sm * 8, 256, 0, st, b, w.tileCount, w.headScan, w.runFirst, w.runStart, w.counters);
     launches += 1;
     return launches;
 }
@@ -1462,6 +1485,8 @@ struct ExtendArgs {
 };
 
 __global__ void __launch_bounds__(256) k_extend(const ExtendArgs a) {
+    griddep_launch_dependents();
+    griddep_wait();
     if (a.counters[3]) return;
     const uint32_t nRuns = a.counters[1];
     const int lane = threadIdx.x & 31, sub = lane & 7, grp = lane >> 3;
@@ -1636,6 +1661,8 @@ __global__ void __launch_bounds__(256) k_extend(const ExtendArgs a) {
 // exactly one chain and only the thread of the chain end (start) walks it: no races.
 __global__ void __launch_bounds__(256) k_links(RunRec* __restrict__ runs, const uint8_t* __restrict__ runLink,
                                                const uint32_t* counters) {
+    griddep_launch_dependents();
+    griddep_wait();
     if (counters[3]) return;
     const uint32_t nRuns = counters[1];
     for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < nRuns; r += gridDim.x * blockDim.x) {
@@ -1664,8 +1691,8 @@ __global__ void __launch_bounds__(256) k_links(RunRec* __restrict__ runs, const 
 
 int launch_extend(const IndexState& ix, const BatchDesc& b, const WorkBuffers& w, cudaStream_t st) {
     ExtendArgs a{ix, b, w.seeds, w.runFirst, w.runStart, w.runs, w.runLink, w.counters};
-    k_extend<<<device_sm_count() * 8, 256, 0, st>>>(a);
-    k_links<<<device_sm_count() * 4, 256, 0, st>>>(w.runs, w.runLink, w.counters);
+    launch_pdl(k_extend, device_sm_count() * 8, 256, 0, st, a);
+    launch_pdl(k_links, device_sm_count() * 4, 256, 0, st, w.runs, w.runLink, w.counters);
     return 2;
 }
 
@@ -1739,6 +1766,8 @@ __device__ __forceinline__ unsigned long long key_a(const RunRec& r) {
 __global__ void __launch_bounds__(ISL_THREADS) k_island_reduce(const RunRec* __restrict__ runs, const uint32_t* counters,
                                                                unsigned long long* __restrict__ tileFwd,
                                                                unsigned long long* __restrict__ tileBwd) {
+    griddep_launch_dependents();
+    griddep_wait();
     if (counters[3]) return;
     __shared__ unsigned long long sWarp[64];
     const uint32_t nRuns = counters[1];
@@ -1765,6 +1794,8 @@ __global__ void __launch_bounds__(ISL_THREADS) k_island_reduce(const RunRec* __r
 // tileFwd -> exclusive prefix max (carry into each tile); tileBwd -> exclusive suffix min
 __global__ void __launch_bounds__(1024) k_island_partials(const uint32_t* counters, unsigned long long* __restrict__ tileFwd,
                                                           unsigned long long* __restrict__ tileBwd) {
+    griddep_launch_dependents();
+    griddep_wait();
     if (counters[3]) return;
     __shared__ unsigned long long sWarp[64];
     __shared__ unsigned long long sInc[1024];
@@ -1801,6 +1832,8 @@ __global__ void __launch_bounds__(ISL_THREADS) k_island_heads(const RunRec* __re
                                                               const unsigned long long* __restrict__ tileFwd,
                                                               const unsigned long long* __restrict__ tileBwd,
                                                               uint32_t* __restrict__ isHead) {
+    griddep_launch_dependents();
+    griddep_wait();
     if (counters[3]) return;
     __shared__ unsigned long long sWarp[64];
     __shared__ unsigned long long sFwdEx[ISL_THREADS];
@@ -1978,6 +2011,8 @@ __device__ __forceinline__ void replay_run(const ResolveArgs& a, const ReplayCon
 constexpr uint32_t BIG_ISLAND = 256;  // islands longer than this go to the warp-cooperative kernel
 
 __global__ void __launch_bounds__(128) k_resolve(const ResolveArgs a) {
+    griddep_launch_dependents();
+    griddep_wait();
     if (a.counters[3]) return;
     const uint32_t nRuns = a.counters[1];
     ReplayConst rc;
@@ -2037,6 +2072,8 @@ __global__ void __launch_bounds__(128) k_resolve(const ResolveArgs a) {
 // Long islands, a warp each: lane 0 replays, all 32 lanes find the island's end and the next run that is not behind
 // the cursor (a ballot over 32 runs per step instead of one dependent load per run).
 __global__ void __launch_bounds__(128) k_resolve_big(const ResolveArgs a) {
+    griddep_launch_dependents();
+    griddep_wait();
     if (a.counters[3]) return;
     const uint32_t nRuns = a.counters[1], nBig = a.counters[8];
     const int lane = threadIdx.x & 31;
@@ -2100,6 +2137,8 @@ __global__ void __launch_bounds__(256) k_gather(const MatchRec* __restrict__ mat
                                                 const uint32_t* __restrict__ matchOffRun,
                                                 const uint32_t* __restrict__ runStart, TextMatchRec* __restrict__ dense,
                                                 uint32_t* __restrict__ matchOff, int nContigs, uint32_t* counters) {
+    griddep_launch_dependents();
+    griddep_wait();
     if (counters[3]) return;
     const uint32_t nRuns = counters[1];
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
@@ -2125,18 +2164,18 @@ int launch_resolve(const IndexState& ix, const BatchDesc& b, const WorkBuffers& 
     const int sm = device_sm_count();
     int launches = 0;
     // islands: headScan (free after k_runs) takes the island-head flags, blockSums-sized u64 temporaries the tile carries
-    k_island_reduce<<<sm * 4, ISL_THREADS, 0, st>>>(w.runs, w.counters, w.islandFwd, w.islandBwd);
-    k_island_partials<<<1, 1024, 0, st>>>(w.counters, w.islandFwd, w.islandBwd);
-    k_island_heads<<<sm * 4, ISL_THREADS, 0, st>>>(w.runs, w.counters, w.islandFwd, w.islandBwd, w.headScan);
+    launch_pdl(k_island_reduce, sm * 4, ISL_THREADS, 0, st, w.runs, w.counters, w.islandFwd, w.islandBwd);
+    launch_pdl(k_island_partials, 1, 1024, 0, st, w.counters, w.islandFwd, w.islandBwd);
+    launch_pdl(k_island_heads, sm * 4, ISL_THREADS, 0, st, w.runs, w.counters, w.islandFwd, w.islandBwd, w.headScan);
     launches += 3;
     // runFirst (free after k_extend) takes the per-island match counts, then their exclusive scan
     // scratchEnc (position-indexed seed staging, free since the compaction) holds the list of long islands
     ResolveArgs a{ix, b, w.runs, w.runStart, w.headScan, w.matches, w.runFirst, w.counters, minMatchLength, w.scratchEnc};
-    k_resolve<<<sm * 16, 128, 0, st>>>(a);
-    k_resolve_big<<<sm * 4, 128, 0, st>>>(a);
+    launch_pdl(k_resolve, sm * 16, 128, 0, st, a);
+    launch_pdl(k_resolve_big, sm * 4, 128, 0, st, a);
     launches += 2;
     launches += scan_exclusive(w.runFirst, w.runFirst, w.counters + 1, 0, w.seedCap, w.scanState + 2 * w.scanStride, w.scanStride, nullptr, st);
-    k_gather<<<sm * 8, 256, 0, st>>>(w.matches, w.headScan, w.runFirst, w.runStart, w.matchesDense, w.matchOff,
+    launch_pdl(k_gather, sm * 8, 256, 0, st, w.matches, w.headScan, w.runFirst, w.runStart, w.matchesDense, w.matchOff,
                                      b.nContigs, w.counters);
     launches += 1;
     return launches;

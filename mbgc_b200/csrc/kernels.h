@@ -10,6 +10,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <cstdlib>
 
 namespace mbgc_b200 {
 
@@ -164,5 +165,37 @@ int launch_unpack(const PackedBlock* blocks, uint32_t nBlocks, const uint8_t* pa
 int launch_scan_u32(const uint32_t* in, uint32_t* out, uint32_t n, unsigned long long* state, cudaStream_t st);
 bool probe_supports_K(int K);
 int device_sm_count();
+
+#ifdef __CUDACC__
+// Programmatic dependent launch (sm_90+): the kernels of a match pass form a chain of ~19 dependent launches, most of them a
+// few microseconds long.  Launched with cudaLaunchAttributeProgrammaticStreamSerialization, the next kernel's CTAs may take
+// their places on the SMs as soon as every CTA of the current one has called griddep_launch_dependents() -- the first
+// statement of every pass kernel -- and then sleep in griddep_wait() until the current grid has completed and its writes
+// are visible: the launch latency of each link (~2 us) overlaps its predecessor.  Everything a kernel does before
+// griddep_wait() must be independent of the kernels in front of it in the pass (only k_probe does something there: it
+// starts the bulk copy of the first-level filter, which no pass kernel writes).  Without the launch attribute both
+// instructions are no-ops.  MBGC_B200_PDL=0 switches the attribute off.
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, Args&&... args) {
+    const char* e = getenv("MBGC_B200_PDL");
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    if (!(e && e[0] == '0')) {
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+    }
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+#endif  // __CUDACC__
 
 }  // namespace mbgc_b200

@@ -93,6 +93,8 @@ __device__ __forceinline__ uint32_t left_walk(const uint8_t* __restrict__ T, con
 
 __global__ void __launch_bounds__(PK_THREADS) k_pk_init(PackBatch b, uint32_t* __restrict__ mContig,
                                                         uint8_t* __restrict__ removed) {
+    griddep_launch_dependents();
+    griddep_wait();
     const uint32_t j = blockIdx.x * PK_THREADS + threadIdx.x;
     if (j >= b.nMatches) return;
     mContig[j] = segment_of(b.matchOff, static_cast<uint32_t>(b.nContigs), j);
@@ -105,6 +107,8 @@ __global__ void __launch_bounds__(PK_THREADS) k_pk_init(PackBatch b, uint32_t* _
 __global__ void __launch_bounds__(PK_THREADS) k_pk_removal(PackParams p, PackState s, PackBatch b,
                                                            const uint32_t* __restrict__ mContig,
                                                            uint8_t* removed, uint32_t* __restrict__ changed) {
+    griddep_launch_dependents();
+    griddep_wait();
     const uint32_t j = blockIdx.x * PK_THREADS + threadIdx.x;
     if (j >= b.nMatches) return;
     const uint32_t c = mContig[j];
@@ -135,6 +139,8 @@ __global__ void __launch_bounds__(PK_THREADS) k_pk_removal(PackParams p, PackSta
 
 __global__ void __launch_bounds__(PK_THREADS) k_pk_kept_tot(uint32_t nM, const uint8_t* __restrict__ removed,
                                                             uint32_t* __restrict__ blockTot) {
+    griddep_launch_dependents();
+    griddep_wait();
     __shared__ uint32_t sWarp[33];
     const uint32_t j = blockIdx.x * PK_THREADS + threadIdx.x;
     const uint32_t v = (j < nM && !removed[j]) ? 1u : 0u;
@@ -147,6 +153,8 @@ __global__ void __launch_bounds__(PK_THREADS) k_pk_kept_tot(uint32_t nM, const u
 // thread and round); totals land at row nBlocks
 template <int COLS>
 __global__ void __launch_bounds__(1024) k_pk_partials(uint32_t* __restrict__ blockTot, uint32_t nBlocks) {
+    griddep_launch_dependents();
+    griddep_wait();
     __shared__ uint32_t sWarp[33];
     const int k = blockIdx.x;
     uint32_t carry = 0;
@@ -172,6 +180,8 @@ __global__ void __launch_bounds__(1024) k_pk_partials(uint32_t* __restrict__ blo
 
 __global__ void __launch_bounds__(PK_THREADS) k_pk_compact(PackState s, PackBatch b, PackWork w,
                                                            const uint32_t* __restrict__ blockOff) {
+    griddep_launch_dependents();
+    griddep_wait();
     __shared__ uint32_t sWarp[33];
     const uint32_t j = blockIdx.x * PK_THREADS + threadIdx.x;
     const bool in = j < b.nMatches;
@@ -217,6 +227,8 @@ __global__ void __launch_bounds__(PK_THREADS) k_pk_compact(PackState s, PackBatc
 
 __global__ void __launch_bounds__(PK_THREADS) k_pk_koff(PackBatch b, const uint32_t* __restrict__ keptScan,
                                                         uint32_t* __restrict__ kOff) {
+    griddep_launch_dependents();
+    griddep_wait();
     const uint32_t c = blockIdx.x * PK_THREADS + threadIdx.x;
     if (c <= static_cast<uint32_t>(b.nContigs)) kOff[c] = keptScan[b.matchOff[c]];
 }
@@ -249,6 +261,8 @@ __device__ __forceinline__ uint64_t next_region_loading_pos(const PackState& s, 
 __global__ void __launch_bounds__(PK_THREADS) k_pk_claim_scatter(int nContigs, const uint32_t* __restrict__ kOff,
                                                                  const uint8_t* __restrict__ claim,
                                                                  uint32_t* __restrict__ claimedBy) {
+    griddep_launch_dependents();
+    griddep_wait();
     const uint32_t m = blockIdx.x * PK_THREADS + threadIdx.x;
     if (m >= kOff[nContigs]) return;
     const uint32_t g = claim[m];
@@ -257,6 +271,8 @@ __global__ void __launch_bounds__(PK_THREADS) k_pk_claim_scatter(int nContigs, c
 
 __global__ void __launch_bounds__(PK_THREADS) k_pk_claim_sweep(PackParams p, PackState s, PackBatch b, PackWork w,
                                                                uint32_t* __restrict__ changed) {
+    griddep_launch_dependents();
+    griddep_wait();
     const uint32_t m = blockIdx.x * PK_THREADS + threadIdx.x;
     if (m >= w.kOff[b.nContigs]) return;
     const uint32_t c = w.kContig[m];
@@ -691,6 +707,8 @@ __device__ __forceinline__ bool locate_gap(const PackBatch& b, const uint32_t* _
 }
 
 __global__ void __launch_bounds__(PK_THREADS) k_pk_count(PackParams p, PackState s, PackBatch b, PackWork w) {
+    griddep_launch_dependents();
+    griddep_wait();
     __shared__ uint32_t sTot[PACK_STREAMS];
     const uint32_t gi = blockIdx.x * PK_THREADS + threadIdx.x;
     GapOut cnt;
@@ -719,6 +737,8 @@ __global__ void __launch_bounds__(PK_THREADS) k_pk_count(PackParams p, PackState
 }
 
 __global__ void __launch_bounds__(PK_THREADS) k_pk_emit(PackParams p, PackState s, PackBatch b, PackWork w) {
+    griddep_launch_dependents();
+    griddep_wait();
     __shared__ uint32_t sWarpTot[PK_THREADS / 32][PACK_STREAMS];
     const uint32_t gi = blockIdx.x * PK_THREADS + threadIdx.x;
     uint32_t c = 0, j = 0, n = 0;
@@ -780,6 +800,8 @@ __global__ void __launch_bounds__(PK_THREADS) k_pk_emit(PackParams p, PackState 
 // destinations, sources read through two aligned words and a funnel shift
 __global__ void __launch_bounds__(PK_THREADS) k_pk_copy_long(const LongRun* __restrict__ runs, const uint32_t* __restrict__ flags,
                                                              uint32_t cap) {
+    griddep_launch_dependents();
+    griddep_wait();
     constexpr uint64_t PIECE = 16384;
     uint32_t nRuns = flags[32];
     if (nRuns > cap) nRuns = cap;
@@ -811,6 +833,8 @@ __global__ void __launch_bounds__(PK_THREADS) k_pk_copy_long(const LongRun* __re
 // when its contig is NOT proper for a whole-contig extension (loadLiteralsToRef, :211; MGMP_Params.h:179-187 on the
 // unmatched count before the extensions = length - sum of the kept match lengths) and it is longer than the threshold.
 __global__ void __launch_bounds__(PK_THREADS) k_pk_lit_flag(LitExtParams le, PackBatch b, PackWork w) {
+    griddep_launch_dependents();
+    griddep_wait();
     const uint32_t gi = blockIdx.x * PK_THREADS + threadIdx.x;
     uint32_t c, j, n;
     if (!locate_gap(b, w.kOff, gi, c, j, n)) return;
@@ -821,6 +845,8 @@ __global__ void __launch_bounds__(PK_THREADS) k_pk_lit_flag(LitExtParams le, Pac
 }
 
 __global__ void __launch_bounds__(PK_THREADS) k_pk_lit_ranges(LitExtParams le, PackBatch b, PackWork w) {
+    griddep_launch_dependents();
+    griddep_wait();
     const uint32_t gi = blockIdx.x * PK_THREADS + threadIdx.x;
     uint32_t c, j, n;
     if (!locate_gap(b, w.kOff, gi, c, j, n)) return;
@@ -843,17 +869,17 @@ int launch_pack_pass1(const PackParams& p, const PackState& s, const PackBatch& 
     if (nM == 0) return 0;
     const uint32_t blocks = blocks_for(nM);
     int launches = 0;
-    k_pk_init<<<blocks, PK_THREADS, 0, st>>>(b, w.mContig, w.removed);
+    launch_pdl(k_pk_init, blocks, PK_THREADS, 0, st, b, w.mContig, w.removed);
     launches++;
     if (p.enableExt)
         for (int i = 0; i < sweeps; i++) {
-            k_pk_removal<<<blocks, PK_THREADS, 0, st>>>(p, s, b, w.mContig, w.removed, w.flags + (i == sweeps - 1 ? 15 : i % 15));  // the last sweep has a flag of its own
+            launch_pdl(k_pk_removal, blocks, PK_THREADS, 0, st, p, s, b, w.mContig, w.removed, w.flags + (i == sweeps - 1 ? 15 : i % 15));  // the last sweep has a flag of its own
             launches++;
         }
-    k_pk_kept_tot<<<blocks, PK_THREADS, 0, st>>>(nM, w.removed, w.blockTot);
-    k_pk_partials<1><<<1, 1024, 0, st>>>(w.blockTot, blocks);
-    k_pk_compact<<<blocks, PK_THREADS, 0, st>>>(s, b, w, w.blockTot);
-    k_pk_koff<<<blocks_for(static_cast<uint64_t>(b.nContigs) + 1), PK_THREADS, 0, st>>>(b, w.keptScan, w.kOff);
+    launch_pdl(k_pk_kept_tot, blocks, PK_THREADS, 0, st, nM, w.removed, w.blockTot);
+    launch_pdl(k_pk_partials<1>, 1, 1024, 0, st, w.blockTot, blocks);
+    launch_pdl(k_pk_compact, blocks, PK_THREADS, 0, st, s, b, w, w.blockTot);
+    launch_pdl(k_pk_koff, blocks_for(static_cast<uint64_t>(b.nContigs) + 1), PK_THREADS, 0, st, b, w.keptScan, w.kOff);
     return launches + 4;
 }
 
@@ -870,38 +896,38 @@ int launch_pack_claims(const PackParams& p, const PackState& s, const PackBatch&
     for (int i = 0; i < sweeps; i++) {
         cudaMemsetAsync(w.claimedBy, 0xFF, static_cast<uint64_t>(nM) * 4, st);
         if (i > 0) {
-            k_pk_claim_scatter<<<blocks, PK_THREADS, 0, st>>>(b.nContigs, w.kOff, w.claim, w.claimedBy);
+            launch_pdl(k_pk_claim_scatter, blocks, PK_THREADS, 0, st, b.nContigs, w.kOff, w.claim, w.claimedBy);
             launches++;
         }
-        k_pk_claim_sweep<<<blocks, PK_THREADS, 0, st>>>(p, s, b, w, w.flags + 16 + (i == sweeps - 1 ? 15 : i % 15));
+        launch_pdl(k_pk_claim_sweep, blocks, PK_THREADS, 0, st, p, s, b, w, w.flags + 16 + (i == sweeps - 1 ? 15 : i % 15));
         launches++;
     }
     // the claims of the last sweep decide which matches omit their offset
     cudaMemsetAsync(w.claimedBy, 0xFF, static_cast<uint64_t>(nM) * 4, st);
-    k_pk_claim_scatter<<<blocks, PK_THREADS, 0, st>>>(b.nContigs, w.kOff, w.claim, w.claimedBy);
+    launch_pdl(k_pk_claim_scatter, blocks, PK_THREADS, 0, st, b.nContigs, w.kOff, w.claim, w.claimedBy);
     return launches + 1;
 }
 
 int launch_pack_count(const PackParams& p, const PackState& s, const PackBatch& b, const PackWork& w, cudaStream_t st) {
     const uint32_t blocks = blocks_for(static_cast<uint64_t>(b.nMatches) + b.nContigs);
-    k_pk_count<<<blocks, PK_THREADS, 0, st>>>(p, s, b, w);
-    k_pk_partials<PACK_STREAMS><<<PACK_STREAMS, 1024, 0, st>>>(w.blockTot, blocks);
+    launch_pdl(k_pk_count, blocks, PK_THREADS, 0, st, p, s, b, w);
+    launch_pdl(k_pk_partials<PACK_STREAMS>, PACK_STREAMS, 1024, 0, st, w.blockTot, blocks);
     return 2;
 }
 
 int launch_pack_literal_ext(const LitExtParams& le, const PackBatch& b, const PackWork& w, cudaStream_t st) {
     const uint32_t nGaps = b.nMatches + static_cast<uint32_t>(b.nContigs);
     const uint32_t blocks = blocks_for(nGaps);
-    k_pk_lit_flag<<<blocks, PK_THREADS, 0, st>>>(le, b, w);
+    launch_pdl(k_pk_lit_flag, blocks, PK_THREADS, 0, st, le, b, w);
     const int l = launch_scan_u32(w.litFlag, w.litFlag, nGaps, w.litScanState, st);
-    k_pk_lit_ranges<<<blocks, PK_THREADS, 0, st>>>(le, b, w);
+    launch_pdl(k_pk_lit_ranges, blocks, PK_THREADS, 0, st, le, b, w);
     return 2 + l;
 }
 
 int launch_pack_emit(const PackParams& p, const PackState& s, const PackBatch& b, const PackWork& w, cudaStream_t st) {
     const uint32_t blocks = blocks_for(static_cast<uint64_t>(b.nMatches) + b.nContigs);
-    k_pk_emit<<<blocks, PK_THREADS, 0, st>>>(p, s, b, w);
-    k_pk_copy_long<<<static_cast<unsigned>(device_sm_count()) * 4, PK_THREADS, 0, st>>>(w.longRuns, w.flags, w.longCap);
+    launch_pdl(k_pk_emit, blocks, PK_THREADS, 0, st, p, s, b, w);
+    launch_pdl(k_pk_copy_long, static_cast<unsigned>(device_sm_count()) * 4, PK_THREADS, 0, st, w.longRuns, w.flags, w.longCap);
     return 2;
 }
 
