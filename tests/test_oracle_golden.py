@@ -113,3 +113,53 @@ def test_streams_listeria(mode):
         assert hashlib.sha256(out[name]).hexdigest() == want[name]["sha256"], name
     if mode == 1:  # the reference's own dev counters
         assert stats["matches"] == 29731 and stats["unmatched"] == 5009573 and stats["ref_length"] == 16584539
+
+
+def test_literal_ranges_properties():
+    """row a12, oracle alone: with the option off the call is the plain processMatches; with it on, every range lies inside
+    its text, covers a literal run longer than the threshold plus at most `context` bytes on either side, and a contig that
+    IS proper for a whole-contig extension gives none (MBGC_Encoder.cpp:211)"""
+    import ctypes as C
+    from seq_schedule import LitRange
+    from util import NO_LOCK, PackParams, literal_ext_genomes, u8p
+    lib = oracle_lib()
+    lib.mbo_process_matches_lit.restype = C.c_uint64
+    gs = literal_ext_genomes(4, 60_000, 3)
+    o = OracleMatcher(1 << 22, 32, 16, 1, 16)
+    o.disable_sliding_window()
+    o.load_ref(gs[0], rc=True, add_sep=True)
+
+    def run(t, min_len, ctx, factor):
+        pp = PackParams.for_mode(1)
+        pp.unmatchedFractionFactor = factor
+        mt = np.ascontiguousarray(o.match(t, 32))
+        st = lib.mbo_streams_create()
+        n = C.c_uint64(len(mt))
+        rb = (LitRange * (len(mt) + 2))()
+        nr = C.c_uint64(0)
+        arr = (C.c_uint64 * 1)()
+        a = np.ascontiguousarray(t, dtype=np.uint8)
+        buf = mt if len(mt) else np.zeros((1, 3), dtype=np.uint64)
+        u = lib.mbo_process_matches_lit(st, C.byref(pp), o.h, buf.ctypes.data_as(C.c_void_p), C.byref(n), a.ctypes.data_as(u8p),
+                                        C.c_uint64(a.size), C.c_uint64(NO_LOCK), arr, C.c_uint64(0), C.c_uint64(min_len),
+                                        C.c_uint64(ctx), rb, C.c_uint64(len(mt) + 2), C.byref(nr))
+        streams = []
+        for i in range(6):
+            k = lib.mbo_stream_size(st, i)
+            p = lib.mbo_stream_data(st, i)
+            streams.append(bytes(np.ctypeslib.as_array(C.cast(p, u8p), shape=(k,))) if k else b"")
+        lib.mbo_streams_destroy(st)
+        return u, streams, [(int(rb[k].start), int(rb[k].len)) for k in range(nr.value)]
+
+    for t in gs[1:]:
+        u0, s0, r0 = run(t, 2**64 - 1, 0, 16)       # off
+        u1, s1, r1 = run(t, 64, 8, 16)              # factor 16: ~700 unmatched bases of 60 k do not make the contig proper
+        u2, s2, r2 = run(t, 64, 0, 16)
+        assert r0 == [] and (u0, s0) == (u1, s1) == (u2, s2), "the option must not change the streams"
+        assert len(r1) == len(r2) > 0
+        for (a1, l1), (a2, l2) in zip(r1, r2):
+            assert l2 > 64 and a2 + l2 <= t.size                       # the bare literal run
+            assert a1 <= a2 and a2 - a1 <= 8 and a1 + l1 >= a2 + l2 and (a1 + l1) - (a2 + l2) <= 8 and a1 + l1 <= t.size
+        # proper for a whole-contig extension (unmatched * factor > length): processLiteral is not called at all
+        assert run(t, 64, 8, 1 << 20)[2] == []
+    o.close()
