@@ -836,8 +836,12 @@ __global__ void __launch_bounds__(PK_THREADS) k_pk_lit_flag(LitExtParams le, Pac
     griddep_launch_dependents();
     griddep_wait();
     const uint32_t gi = blockIdx.x * PK_THREADS + threadIdx.x;
+    if (gi >= b.nMatches + static_cast<uint32_t>(b.nContigs)) return;
     uint32_t c, j, n;
-    if (!locate_gap(b, w.kOff, gi, c, j, n)) return;
+    if (!locate_gap(b, w.kOff, gi, c, j, n)) {  // behind the last gap (pass 1 removed matches): the scan runs over all nM + nC slots
+        w.litFlag[gi] = 0;
+        return;
+    }
     const uint64_t destLen = b.contigLen[c];
     const uint64_t unmatched = destLen - w.sumLen[c];
     const bool proper = unmatched * le.factor > destLen;
